@@ -1,0 +1,251 @@
+"""coregex_b200 — Python binding of the B200 bulk-scan engine (libcoregex_b200.so).
+
+The method names and semantics follow the reference's public Go API for the bulk-scan path
+(reference regex.go): Compile :110, MustCompile :129, (*Regex).Match :282, FindAllIndex :695,
+Count :1349, FindAllSubmatchIndex :1423, NumSubexp :552, String :444 — so the parity tests read
+like the reference's own tests.  Everything runs on the GPU through the C ABI declared in
+include/coregex_b200.h; there is no CPU fallback: importing works anywhere, searching without a
+CUDA device raises NoDeviceError, and a missing shared library raises at import time.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "lib", "libcoregex_b200.so")
+
+CGX_OK = 0
+CGX_ERR_SYNTAX = -1
+CGX_ERR_UNSUPPORTED = -2
+CGX_ERR_NO_DEVICE = -3
+CGX_ERR_CUDA = -4
+CGX_ERR_ARGS = -5
+CGX_ERR_NOMEM = -6
+
+MODE_FINDALL, MODE_COUNT, MODE_ISMATCH = 0, 1, 2
+
+
+class Error(Exception):
+    """Compile error; str() is the Go-formatted message (reference meta/compile.go:775-784)."""
+
+
+class UnsupportedError(Error):
+    """Valid pattern outside the GPU engines' current scope."""
+
+
+class NoDeviceError(RuntimeError):
+    pass
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(_SO):
+        raise ImportError(
+            "coregex_b200: %s is missing — run `python -m coregex_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback." % _SO)
+    L = C.CDLL(_SO)
+    vp, u8p, i64, sz = C.c_void_p, C.c_void_p, C.c_int64, C.c_size_t
+    L.cgx_compile.argtypes = [C.c_char_p, sz, C.POINTER(vp), C.c_char_p, sz]
+    L.cgx_free.argtypes = [vp]
+    L.cgx_strategy.restype = C.c_char_p
+    L.cgx_strategy.argtypes = [vp]
+    L.cgx_engine.restype = C.c_char_p
+    L.cgx_engine.argtypes = [vp]
+    L.cgx_num_captures.argtypes = [vp]
+    L.cgx_last_error.restype = C.c_char_p
+    L.cgx_is_match.argtypes = [vp, u8p, sz, C.POINTER(C.c_int)]
+    L.cgx_find_all_index.argtypes = [vp, u8p, sz, i64, C.c_void_p, sz, C.POINTER(sz)]
+    L.cgx_count.argtypes = [vp, u8p, sz, i64, C.POINTER(sz)]
+    L.cgx_find_all_submatch_index.argtypes = [vp, u8p, sz, i64, C.c_void_p, sz, C.POINTER(sz)]
+    L.cgx_scan_device.argtypes = [vp, u8p, sz, i64, C.c_int, C.c_void_p, sz, C.c_void_p, C.c_void_p]
+    L.cgx_scan_submatch_device.argtypes = [vp, u8p, sz, i64, C.c_void_p, sz, C.c_void_p, C.c_void_p]
+    L.cgx_launch_count.restype = C.c_uint64
+    L.cgx_launch_count.argtypes = [vp]
+    L.cgx_synth_device.argtypes = [C.c_int, C.c_uint64, C.c_uint64, u8p, sz, u8p, C.c_void_p, C.c_int, C.c_void_p]
+    L.cgx_synth_host.argtypes = [C.c_int, C.c_uint64, C.c_uint64, u8p, sz, u8p, C.c_void_p, C.c_int]
+    return L
+
+
+_lib = _load()
+
+
+def _check(rc):
+    if rc == CGX_OK:
+        return
+    msg = (_lib.cgx_last_error() or b"").decode(errors="replace")
+    if rc == CGX_ERR_NO_DEVICE:
+        raise NoDeviceError(msg or "no CUDA device (coregex_b200 has no CPU fallback)")
+    if rc == CGX_ERR_UNSUPPORTED:
+        raise UnsupportedError(msg)
+    if rc == CGX_ERR_ARGS:
+        raise ValueError(msg or "bad arguments")
+    raise CudaError("status %d: %s" % (rc, msg))
+
+
+def _host_buf(b):
+    """bytes-like / numpy uint8 / torch CPU uint8 tensor -> (ptr, len, keepalive)."""
+    if isinstance(b, str):
+        b = b.encode()
+    if hasattr(b, "data_ptr") and hasattr(b, "numel"):  # torch tensor (pinned or pageable, CPU)
+        return b.data_ptr(), b.numel(), b
+    if isinstance(b, np.ndarray):
+        a = np.ascontiguousarray(b, dtype=np.uint8)
+        return a.ctypes.data, a.size, a
+    a = np.frombuffer(bytes(b), dtype=np.uint8)
+    return a.ctypes.data, a.size, a
+
+
+class Regex:
+    """A compiled pattern.  Mirrors reference regex.go `type Regex` for the bulk-scan path."""
+
+    def __init__(self, pattern):
+        if isinstance(pattern, str):
+            pattern = pattern.encode()
+        self._pattern = pattern
+        h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        rc = _lib.cgx_compile(pattern, len(pattern), C.byref(h), err, 1024)
+        if rc == CGX_ERR_SYNTAX:
+            raise Error(err.value.decode(errors="replace"))
+        if rc == CGX_ERR_UNSUPPORTED:
+            raise UnsupportedError(err.value.decode(errors="replace"))
+        _check(rc)
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.cgx_free(h)
+
+    # -- introspection --------------------------------------------------------------------------
+    def String(self):
+        return self._pattern.decode(errors="replace")
+
+    def NumSubexp(self):
+        return _lib.cgx_num_captures(self._h) - 1
+
+    @property
+    def strategy(self):
+        """Strategy the reference would select (meta.Engine.Strategy)."""
+        return _lib.cgx_strategy(self._h).decode()
+
+    @property
+    def engine(self):
+        return _lib.cgx_engine(self._h).decode()
+
+    @property
+    def launches(self):
+        return _lib.cgx_launch_count(self._h)
+
+    # -- host-buffer API (drop-in for the Go methods) ---------------------------------------------
+    def Match(self, b):
+        p, n, keep = _host_buf(b)
+        m = C.c_int(0)
+        _check(_lib.cgx_is_match(self._h, p, n, C.byref(m)))
+        return bool(m.value)
+
+    MatchString = Match
+
+    def Count(self, b, n=-1):
+        p, ln, keep = _host_buf(b)
+        c = C.c_size_t(0)
+        _check(_lib.cgx_count(self._h, p, ln, n, C.byref(c)))
+        return c.value
+
+    def find_all_index_array(self, b, n=-1, cap=None):
+        """FindAllIndex returning an int64 array of shape (count, 2) (no Python list building)."""
+        p, ln, keep = _host_buf(b)
+        if n == 0:
+            return np.empty((0, 2), dtype=np.int64)
+        if cap is None:
+            cap = max(64, ln // 64)
+        while True:
+            out = np.empty((cap, 2), dtype=np.int64)
+            c = C.c_size_t(0)
+            _check(_lib.cgx_find_all_index(self._h, p, ln, n, out.ctypes.data, cap, C.byref(c)))
+            if c.value <= cap:
+                return out[: c.value]
+            cap = c.value
+
+    def FindAllIndex(self, b, n=-1):
+        """[[start, end], ...] or None when there is no match / n == 0 (reference regex.go:695-723)."""
+        a = self.find_all_index_array(b, n)
+        if a.shape[0] == 0:
+            return None
+        return a.tolist()
+
+    FindAllStringIndex = FindAllIndex
+
+    def FindAllSubmatchIndex(self, b, n=-1):
+        p, ln, keep = _host_buf(b)
+        if n == 0:
+            return None
+        stride = 2 * _lib.cgx_num_captures(self._h)
+        cap = max(64, ln // 32)
+        while True:
+            out = np.empty((cap, stride), dtype=np.int64)
+            c = C.c_size_t(0)
+            _check(_lib.cgx_find_all_submatch_index(self._h, p, ln, n, out.ctypes.data, cap, C.byref(c)))
+            if c.value <= cap:
+                break
+            cap = c.value
+        if c.value == 0:
+            return None
+        return out[: c.value].tolist()
+
+    # -- device-resident API -----------------------------------------------------------------------
+    def scan_device(self, d_ptr, length, mode=MODE_FINDALL, out_ptr=0, cap_pairs=0, result_ptr=0,
+                    base_offset=0, stream=0):
+        """Enqueue a scan of device memory [d_ptr, d_ptr+length).  Pointers are raw ints."""
+        _check(_lib.cgx_scan_device(self._h, d_ptr, length, base_offset, mode, out_ptr, cap_pairs,
+                                    result_ptr, stream))
+
+    def scan_submatch_device(self, d_ptr, length, out_ptr, cap_matches, result_ptr, base_offset=0,
+                             stream=0):
+        _check(_lib.cgx_scan_submatch_device(self._h, d_ptr, length, base_offset, out_ptr,
+                                             cap_matches, result_ptr, stream))
+
+
+def Compile(pattern):
+    """reference regex.go:110"""
+    return Regex(pattern)
+
+
+def MustCompile(pattern):
+    """reference regex.go:129 — panics (raises) with the reference's message format"""
+    try:
+        return Regex(pattern)
+    except Error as e:
+        raise Error("regexp: Compile(`%s`): %s" % (pattern if isinstance(pattern, str) else pattern.decode(), e))
+
+
+# ---- synthetic corpora (bench / tests) ----------------------------------------------------------
+SYNTH_LOG, SYNTH_TEXT, SYNTH_EMAIL = 0, 1, 2
+SYNTH_BLOCK = {0: 4096, 1: 4096, 2: 80}
+
+
+def _pack_literals(literals):
+    if not literals:
+        return None, None, 0
+    blob = b"".join(literals)
+    offs = np.zeros(len(literals) + 1, dtype=np.int32)
+    offs[1:] = np.cumsum([len(x) for x in literals])
+    return np.frombuffer(blob, dtype=np.uint8).copy(), offs, len(literals)
+
+
+def synth_host(kind, seed, nbytes, first_block=0, literals=None):
+    """Deterministic synthetic corpus slice as a numpy uint8 array (host twin of synth_device)."""
+    out = np.empty(nbytes, dtype=np.uint8)
+    blob, offs, nlit = _pack_literals(literals)
+    _check(_lib.cgx_synth_host(kind, seed, first_block, out.ctypes.data, nbytes,
+                               blob.ctypes.data if blob is not None else None,
+                               offs.ctypes.data if offs is not None else None, nlit))
+    return out
+
+
+def synth_device(kind, seed, d_ptr, nbytes, first_block=0, d_lit_ptr=0, d_off_ptr=0, nlit=0, stream=0):
+    _check(_lib.cgx_synth_device(kind, seed, first_block, d_ptr, nbytes, d_lit_ptr, d_off_ptr, nlit, stream))

@@ -1,0 +1,330 @@
+// capi.cu — the C ABI (include/coregex_b200.h): device residency of compiled tables, scratch
+// management, host-buffer wrappers (H2D -> kernel -> D2H) and the device-resident batch entry.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+
+#include "../../include/coregex_b200.h"
+#include "host/engine.h"
+#include "scan_params.h"
+#include "synth.h"
+
+namespace cgx {
+size_t scan_dfa_smem_bytes(int nstates);
+int64_t scan_dfa_chunks(int64_t n);
+cudaError_t launch_scan_dfa(const ScanArgs& a, int sm_count, cudaStream_t stream);
+cudaError_t launch_scan_teddy(const struct TeddyArgs& a, int sm_count, cudaStream_t stream);
+}  // namespace cgx
+
+using namespace cgx;
+
+static thread_local std::string g_last_error;
+
+static int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? CGX_ERR_NO_DEVICE : CGX_ERR_CUDA;
+}
+#define CU(call)                                     \
+  do {                                               \
+    cudaError_t _e = (call);                         \
+    if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return CGX_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, n);
+      want = n;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    cap = want;
+    return CGX_OK;
+  }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
+struct cgx_regex {
+  std::unique_ptr<Compiled> c;
+  std::mutex mu;
+  int device = -1;
+  int sm_count = 0;
+  // device copies of the tables
+  DevBuf d_trans, d_eoi, d_lut, d_teddy;
+  // per-call scratch (serialised by mu)
+  DevBuf d_ticket_total, d_status, d_hay, d_out;
+  std::atomic<uint64_t> launches{0};
+
+  int ensure_device() {
+    if (device >= 0) return CGX_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      g_last_error = "no CUDA device available (this library has no CPU fallback)";
+      return CGX_ERR_NO_DEVICE;
+    }
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    sm_count = prop.multiProcessorCount;
+    if (c->kind == ENG_DFA) {
+      int r;
+      if ((r = d_trans.ensure(c->dfa.trans.size() * 2))) return r;
+      if ((r = d_eoi.ensure(c->dfa.eoi.size()))) return r;
+      if ((r = d_lut.ensure(256))) return r;
+      CU(cudaMemcpy(d_trans.p, c->dfa.trans.data(), c->dfa.trans.size() * 2, cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(d_eoi.p, c->dfa.eoi.data(), c->dfa.eoi.size(), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(d_lut.p, c->lut, 256, cudaMemcpyHostToDevice));
+    }
+    device = dev;
+    return CGX_OK;
+  }
+};
+
+extern "C" {
+
+const char* cgx_last_error(void) { return g_last_error.c_str(); }
+
+int cgx_compile(const char* pattern, size_t len, cgx_regex** out, char* errbuf, size_t errcap) {
+  if (out) *out = nullptr;
+  if (!pattern || !out) return CGX_ERR_ARGS;
+  std::unique_ptr<Compiled> c;
+  std::string err;
+  int st = CompilePattern(std::string(pattern, len), c, err);
+  if (st != COMPILE_OK) {
+    if (errbuf && errcap) {
+      strncpy(errbuf, err.c_str(), errcap - 1);
+      errbuf[errcap - 1] = 0;
+    }
+    g_last_error = err;
+    return st == COMPILE_SYNTAX ? CGX_ERR_SYNTAX : CGX_ERR_UNSUPPORTED;
+  }
+  cgx_regex* r = new cgx_regex();
+  r->c = std::move(c);
+  *out = r;
+  return CGX_OK;
+}
+
+void cgx_free(cgx_regex* re) { delete re; }
+const char* cgx_strategy(const cgx_regex* re) { return RefStrategyName(re->c->an.strategy); }
+const char* cgx_engine(const cgx_regex* re) { return re->c->engine_name.c_str(); }
+int cgx_num_captures(const cgx_regex* re) { return re->c->prog.num_captures; }
+uint64_t cgx_launch_count(const cgx_regex* re) { return re->launches.load(); }
+
+static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base, int mode,
+                       int64_t* d_out, size_t cap, uint64_t* d_result, cudaStream_t st) {
+  Compiled& c = *re->c;
+  if (((uintptr_t)d_h & 15) || ((uintptr_t)d_out & 15)) {
+    g_last_error = "device pointers must be 16-byte aligned";
+    return CGX_ERR_ARGS;
+  }
+  if (c.kind != ENG_DFA) {
+    g_last_error = "engine not available in this build";
+    return CGX_ERR_UNSUPPORTED;
+  }
+  const int64_t nchunks = scan_dfa_chunks((int64_t)len);
+  int r;
+  if ((r = re->d_ticket_total.ensure(64))) return r;
+  if ((r = re->d_status.ensure((size_t)(nchunks > 0 ? nchunks : 1) * 8))) return r;
+  CU(cudaMemsetAsync(re->d_ticket_total.p, 0, 64, st));
+  if (mode == CGX_MODE_FINDALL && nchunks > 0)
+    CU(cudaMemsetAsync(re->d_status.p, 0, (size_t)nchunks * 8, st));
+  ScanArgs a;
+  memset(&a, 0, sizeof a);
+  a.h = d_h;
+  a.n = (int64_t)len;
+  a.base = base;
+  a.dfa.trans = (const uint16_t*)re->d_trans.p;
+  a.dfa.eoi = (const uint8_t*)re->d_eoi.p;
+  a.dfa.nstates = c.dfa.nstates;
+  for (int k = 0; k < 5; k++) a.dfa.start[k] = c.dfa.start[k];
+  a.dfa.kind_lut_needed = c.kind_lut_needed ? 1 : 0;
+  a.filter.kind = c.filter_kind;
+  a.filter.nranges = c.nranges;
+  for (int k = 0; k < 4; k++) {
+    a.filter.lo[k] = c.rlo[k];
+    a.filter.hi[k] = c.rhi[k];
+  }
+  a.filter.lut = (const uint8_t*)re->d_lut.p;
+  a.skip_safe = c.skip_safe ? 1 : 0;
+  a.delim = c.delim;
+  a.mode = mode;
+  a.out = d_out;
+  a.cap = (int64_t)cap;
+  unsigned long long* tt = (unsigned long long*)re->d_ticket_total.p;
+  a.total = tt;                        // [0] count, [1] is-match flag
+  a.ticket = (unsigned int*)(tt + 4);  // separate 32-byte sector
+  a.status = (unsigned long long*)re->d_status.p;
+  a.nchunks = nchunks;
+  CU(launch_scan_dfa(a, re->sm_count, st));
+  re->launches++;
+  if (d_result) CU(cudaMemcpyAsync(d_result, tt, 16, cudaMemcpyDeviceToDevice, st));
+  return CGX_OK;
+}
+
+int cgx_scan_device(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base, int mode,
+                    int64_t* d_out, size_t cap, uint64_t* d_result, void* stream) {
+  if (!re) return CGX_ERR_ARGS;
+  std::lock_guard<std::mutex> lk(re->mu);
+  int r = re->ensure_device();
+  if (r) return r;
+  return scan_locked(re, d_h, len, base, mode, d_out, cap, d_result, (cudaStream_t)stream);
+}
+
+int cgx_scan_submatch_device(cgx_regex*, const uint8_t*, size_t, int64_t, int64_t*, size_t, uint64_t*,
+                             void*) {
+  g_last_error = "captures kernel not available in this build";
+  return CGX_ERR_UNSUPPORTED;
+}
+
+// host wrapper shared by is_match / count / find_all
+static int host_scan(cgx_regex* re, const uint8_t* h, size_t len, int mode, int64_t* out, size_t cap,
+                     uint64_t result[2]) {
+  if (!re || (!h && len)) return CGX_ERR_ARGS;
+  std::lock_guard<std::mutex> lk(re->mu);
+  int r = re->ensure_device();
+  if (r) return r;
+  if ((r = re->d_hay.ensure(len + 16))) return r;
+  if (mode == CGX_MODE_FINDALL && cap && (r = re->d_out.ensure(cap * 16))) return r;
+  cudaStream_t st = 0;
+  if (len) CU(cudaMemcpyAsync(re->d_hay.p, h, len, cudaMemcpyHostToDevice, st));
+  r = scan_locked(re, (const uint8_t*)re->d_hay.p, len, 0, mode,
+                  mode == CGX_MODE_FINDALL && cap ? (int64_t*)re->d_out.p : nullptr, cap, nullptr, st);
+  if (r) return r;
+  CU(cudaMemcpyAsync(result, re->d_ticket_total.p, 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (mode == CGX_MODE_FINDALL && out && cap) {
+    size_t w = result[0] < cap ? (size_t)result[0] : cap;
+    if (w) CU(cudaMemcpy(out, re->d_out.p, w * 16, cudaMemcpyDeviceToHost));
+  }
+  return CGX_OK;
+}
+
+int cgx_is_match(cgx_regex* re, const uint8_t* h, size_t len, int* matched) {
+  uint64_t res[2] = {0, 0};
+  int r = host_scan(re, h, len, CGX_MODE_ISMATCH, nullptr, 0, res);
+  if (r) return r;
+  if (matched) *matched = res[1] ? 1 : 0;
+  return CGX_OK;
+}
+
+int cgx_count(cgx_regex* re, const uint8_t* h, size_t len, int64_t limit, size_t* count) {
+  if (count) *count = 0;
+  if (limit == 0) return CGX_OK;
+  uint64_t res[2] = {0, 0};
+  int r = host_scan(re, h, len, CGX_MODE_COUNT, nullptr, 0, res);
+  if (r) return r;
+  size_t c = (size_t)res[0];
+  if (limit > 0 && c > (size_t)limit) c = (size_t)limit;
+  if (count) *count = c;
+  return CGX_OK;
+}
+
+int cgx_find_all_index(cgx_regex* re, const uint8_t* h, size_t len, int64_t limit, int64_t* out,
+                       size_t cap, size_t* count) {
+  if (count) *count = 0;
+  if (limit == 0) return CGX_OK;  // reference regex.go:696-698
+  uint64_t res[2] = {0, 0};
+  size_t want = cap;
+  if (limit > 0 && (size_t)limit < want) want = (size_t)limit;
+  int r = host_scan(re, h, len, (out && want) ? CGX_MODE_FINDALL : CGX_MODE_COUNT, out, want, res);
+  if (r) return r;
+  size_t c = (size_t)res[0];
+  if (limit > 0 && c > (size_t)limit) c = (size_t)limit;  // first `limit` matches are a prefix
+  if (count) *count = c;
+  return CGX_OK;
+}
+
+int cgx_find_all_submatch_index(cgx_regex*, const uint8_t*, size_t, int64_t, int64_t*, size_t, size_t*) {
+  g_last_error = "captures kernel not available in this build";
+  return CGX_ERR_UNSUPPORTED;
+}
+
+// ---- debug exports (tests only): the compiled tables exactly as the kernels see them ------------
+int cgx_debug_dfa_info(const cgx_regex* re, int* nstates, uint16_t start[5], int* filter_kind,
+                       int* skip_safe, int* kind_lut_needed, uint8_t ranges[8], int* nranges) {
+  const Compiled& c = *re->c;
+  *nstates = c.dfa.nstates;
+  for (int k = 0; k < 5; k++) start[k] = c.dfa.start[k];
+  *filter_kind = c.filter_kind;
+  *skip_safe = c.skip_safe ? 1 : 0;
+  *kind_lut_needed = c.kind_lut_needed ? 1 : 0;
+  *nranges = c.nranges;
+  for (int k = 0; k < 4; k++) {
+    ranges[2 * k] = c.rlo[k];
+    ranges[2 * k + 1] = c.rhi[k];
+  }
+  return c.kind == ENG_DFA ? 1 : 0;
+}
+int cgx_debug_dfa_copy(const cgx_regex* re, uint16_t* trans, uint8_t* eoi, uint8_t* lut) {
+  const Compiled& c = *re->c;
+  memcpy(trans, c.dfa.trans.data(), c.dfa.trans.size() * 2);
+  memcpy(eoi, c.dfa.eoi.data(), c.dfa.eoi.size());
+  memcpy(lut, c.lut, 256);
+  return CGX_OK;
+}
+
+// ---- synthetic corpora ---------------------------------------------------------------------------
+__global__ void synth_kernel(int kind, uint64_t seed, uint64_t first_block, uint8_t* out, uint64_t nblocks,
+                             const uint8_t* lits, const int32_t* offs, int nlit) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nblocks) return;
+  if (kind == 0) synth::gen_block_log(out + i * synth::kBlock01, seed, first_block + i);
+  else if (kind == 1) synth::gen_block_text(out + i * synth::kBlock01, seed, first_block + i, lits, offs, nlit);
+  else synth::gen_block_email(out + i * synth::kBlock2, seed, first_block + i);
+}
+
+static int synth_check(int kind, size_t len, size_t& bs) {
+  if (kind < 0 || kind > 2) return CGX_ERR_ARGS;
+  bs = kind == 2 ? synth::kBlock2 : synth::kBlock01;
+  if (len % bs) {
+    g_last_error = "synthetic corpus length must be a multiple of the block size";
+    return CGX_ERR_ARGS;
+  }
+  return CGX_OK;
+}
+
+int cgx_synth_device(int kind, uint64_t seed, uint64_t first_block, uint8_t* d_out, size_t len,
+                     const uint8_t* d_lits, const int32_t* d_offs, int nlit, void* stream) {
+  size_t bs;
+  int r = synth_check(kind, len, bs);
+  if (r) return r;
+  uint64_t nb = len / bs;
+  if (!nb) return CGX_OK;
+  unsigned threads = 128;
+  uint64_t grid = (nb + threads - 1) / threads;
+  synth_kernel<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(kind, seed, first_block, d_out, nb,
+                                                                      d_lits, d_offs, nlit);
+  CU(cudaGetLastError());
+  return CGX_OK;
+}
+
+int cgx_synth_host(int kind, uint64_t seed, uint64_t first_block, uint8_t* out, size_t len,
+                   const uint8_t* lits, const int32_t* offs, int nlit) {
+  size_t bs;
+  int r = synth_check(kind, len, bs);
+  if (r) return r;
+  uint64_t nb = len / bs;
+  for (uint64_t i = 0; i < nb; i++) {
+    if (kind == 0) synth::gen_block_log(out + i * bs, seed, first_block + i);
+    else if (kind == 1) synth::gen_block_text(out + i * bs, seed, first_block + i, lits, offs, nlit);
+    else synth::gen_block_email(out + i * bs, seed, first_block + i);
+  }
+  return CGX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,54 @@
+// engine.h — compiled pattern: AST, program, reference-strategy classification, and the tables
+// the GPU kernels consume.  Pure host C++ (no CUDA types); device residency lives in capi.cu.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../scan_params.h"
+#include "analysis.h"
+#include "dfa.h"
+#include "prog.h"
+#include "teddy_tables.h"
+
+namespace cgx {
+
+enum EngineKind : int {
+  ENG_DFA = 0,     // candidate filter + anchored DFA walk (scan_dfa.cu)
+  ENG_TEDDY,       // nibble-fingerprint filter + ordered literal verify (scan_teddy.cu)
+  ENG_PIKEVM,      // captures (pikevm_kernel.cu)
+};
+
+struct Compiled {
+  std::string pattern;
+  gosyntax::Arena arena;
+  const gosyntax::Regexp* re = nullptr;
+  Prog prog;
+  Analysis an;
+  EngineKind kind = ENG_DFA;
+  std::string engine_name;
+
+  // ENG_DFA
+  DfaTables dfa;
+  int filter_kind = F_LUT;
+  int nranges = 0;
+  uint8_t rlo[4] = {0, 0, 0, 0}, rhi[4] = {0, 0, 0, 0};
+  uint8_t lut[256];
+  bool skip_safe = false;
+  bool kind_lut_needed = false;
+  uint8_t delim = '\n';
+
+  // ENG_TEDDY
+  TeddyTables teddy;
+
+  // captures (FindAllSubmatchIndex)
+  bool has_pike = false;
+  std::vector<uint32_t> pike_code;  // packed program for pikevm_kernel.cu
+};
+
+enum CompileStatus { COMPILE_OK = 0, COMPILE_SYNTAX = -1, COMPILE_UNSUPPORTED = -2 };
+
+// err receives the Go-formatted syntax error or an "unsupported: ..." explanation
+int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, std::string& err);
+
+}  // namespace cgx

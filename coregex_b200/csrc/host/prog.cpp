@@ -1,0 +1,313 @@
+// prog.cpp — AST -> Pike-style program (continuation-passing construction, built back to front).
+#include "prog.h"
+
+#include <memory>
+
+namespace cgx {
+
+using namespace gosyntax;
+
+namespace {
+
+struct Builder {
+  Prog& p;
+  std::string err;
+  bool reverse = false;
+  int depth = 0;
+  std::vector<std::unique_ptr<Regexp>> synth;
+
+  int emit(const Inst& i) {
+    p.inst.push_back(i);
+    return (int)p.inst.size() - 1;
+  }
+  int emitSet(const ByteSet& s, int next) {
+    // dedupe identical sets
+    uint16_t idx = 0;
+    for (; idx < p.sets.size(); idx++)
+      if (p.sets[idx] == s) break;
+    if (idx == p.sets.size()) p.sets.push_back(s);
+    Inst i;
+    i.op = I_SET;
+    i.set = idx;
+    i.out = next;
+    return emit(i);
+  }
+  int emitSplit(int a, int b) {
+    Inst i;
+    i.op = I_SPLIT;
+    i.out = a;
+    i.out1 = b;
+    return emit(i);
+  }
+  int fail(const std::string& e) {
+    if (err.empty()) err = e;
+    return -1;
+  }
+
+  static int encodeRune(uint8_t* buf, int32_t r) {
+    if (r < 0x80) { buf[0] = (uint8_t)r; return 1; }
+    if (r < 0x800) { buf[0] = 0xC0 | (r >> 6); buf[1] = 0x80 | (r & 0x3F); return 2; }
+    if (r < 0x10000) {
+      buf[0] = 0xE0 | (r >> 12); buf[1] = 0x80 | ((r >> 6) & 0x3F); buf[2] = 0x80 | (r & 0x3F);
+      return 3;
+    }
+    buf[0] = 0xF0 | (r >> 18); buf[1] = 0x80 | ((r >> 12) & 0x3F);
+    buf[2] = 0x80 | ((r >> 6) & 0x3F); buf[3] = 0x80 | (r & 0x3F);
+    return 4;
+  }
+
+  static bool nullable(const Regexp* re) {  // reference nfa/compile.go:1390-1431
+    switch (re->op) {
+      case OpEmptyMatch: return true;
+      case OpLiteral: return re->rune.empty();
+      case OpCharClass: case OpAnyCharNotNL: case OpAnyChar: case OpNoMatch: return false;
+      case OpCapture: return re->sub.empty() || nullable(re->sub[0]);
+      case OpStar: case OpQuest: return true;
+      case OpPlus: return !re->sub.empty() && nullable(re->sub[0]);
+      case OpRepeat: return re->min == 0 || (!re->sub.empty() && nullable(re->sub[0]));
+      case OpConcat:
+        for (auto* s : re->sub) if (!nullable(s)) return false;
+        return true;
+      case OpAlternate:
+        for (auto* s : re->sub) if (nullable(s)) return true;
+        return false;
+      default: return true;  // assertions
+    }
+  }
+
+  int literal(const Regexp* re, int next) {
+    // emit bytes back to front (front to back when building the reversed language)
+    std::vector<std::pair<ByteSet, int>> bytes;  // per byte position: set
+    std::vector<ByteSet> seq;
+    for (int32_t r : re->rune) {
+      bool letter = (r >= 'a' && r <= 'z') || (r >= 'A' && r <= 'Z');
+      if ((re->flags & FoldCase) && letter) {
+        ByteSet s{};
+        unsigned u = (r >= 'a') ? r - 32 : r, l = (r <= 'Z') ? r + 32 : r;
+        set_add(s, u, u);
+        set_add(s, l, l);
+        seq.push_back(s);
+      } else {
+        uint8_t buf[4];
+        int n = encodeRune(buf, r);
+        for (int i = 0; i < n; i++) {
+          ByteSet s{};
+          set_add(s, buf[i], buf[i]);
+          seq.push_back(s);
+        }
+      }
+    }
+    if (!reverse) {
+      for (size_t i = seq.size(); i-- > 0;) next = emitSet(seq[i], next);
+    } else {
+      for (size_t i = 0; i < seq.size(); i++) next = emitSet(seq[i], next);
+    }
+    return next;
+  }
+
+  int charClass(const Regexp* re, int next) {
+    if (re->rune.empty()) {
+      Inst i;
+      i.op = I_FAIL;
+      return emit(i);
+    }
+    ByteSet s{};
+    for (size_t k = 0; k + 1 < re->rune.size(); k += 2) {
+      if (re->rune[k] > 127 || re->rune[k + 1] > 127)
+        return fail("unsupported: non-ASCII character class (UTF-8 automata out of scope)");
+      set_add(s, (unsigned)re->rune[k], (unsigned)re->rune[k + 1]);
+    }
+    return emitSet(s, next);
+  }
+
+  // loop helpers: `greedy` decides which split arm is preferred
+  int star(const Regexp* sub, bool ng, int next) {
+    if (nullable(sub)) {
+      // (x+)? : plus split P loops, quest split Q enters or skips
+      int P = emitSplit(-1, -1);
+      int body = compile(sub, P);
+      if (body < 0) return -1;
+      p.inst[P].out = ng ? next : body;
+      p.inst[P].out1 = ng ? body : next;
+      return ng ? emitSplit(next, body) : emitSplit(body, next);
+    }
+    int L = emitSplit(-1, -1);
+    int body = compile(sub, L);
+    if (body < 0) return -1;
+    p.inst[L].out = ng ? next : body;
+    p.inst[L].out1 = ng ? body : next;
+    return L;
+  }
+  int plus(const Regexp* sub, bool ng, int next) {
+    int P = emitSplit(-1, -1);
+    int body = compile(sub, P);
+    if (body < 0) return -1;
+    p.inst[P].out = ng ? next : body;
+    p.inst[P].out1 = ng ? body : next;
+    return body;
+  }
+  int quest(const Regexp* sub, bool ng, int next) {
+    int body = compile(sub, next);
+    if (body < 0) return -1;
+    return ng ? emitSplit(next, body) : emitSplit(body, next);
+  }
+  int repeat(const Regexp* re, int next) {
+    const Regexp* sub = re->sub[0];
+    bool ng = re->flags & NonGreedy;
+    int mn = re->min, mx = re->max;
+    // sequence of pieces in forward order: mn copies, then star or (mx-mn) optional copies
+    enum Kind { COPY, STAR, QUEST };
+    std::vector<Kind> pieces;
+    if (mx == -1) {
+      if (mn == 0) return star(sub, ng, next);
+      for (int i = 0; i < mn; i++) pieces.push_back(COPY);
+      pieces.push_back(STAR);
+    } else if (mn == mx) {
+      if (mn == 0) return next;
+      for (int i = 0; i < mn; i++) pieces.push_back(COPY);
+    } else {
+      for (int i = 0; i < mn; i++) pieces.push_back(COPY);
+      for (int i = 0; i < mx - mn; i++) pieces.push_back(QUEST);
+    }
+    auto one = [&](Kind k, int nx) {
+      switch (k) {
+        case COPY: return compile(sub, nx);
+        case STAR: return star(sub, ng, nx);
+        default: return quest(sub, ng, nx);
+      }
+    };
+    if (!reverse) {
+      for (size_t i = pieces.size(); i-- > 0;) {
+        next = one(pieces[i], next);
+        if (next < 0) return -1;
+      }
+    } else {
+      for (size_t i = 0; i < pieces.size(); i++) {
+        next = one(pieces[i], next);
+        if (next < 0) return -1;
+      }
+    }
+    return next;
+  }
+
+  int compile(const Regexp* re, int next) {
+    if (++depth > 200) {
+      depth--;
+      return fail("regex too complex");
+    }
+    int r = compile1(re, next);
+    depth--;
+    return r;
+  }
+
+  int compile1(const Regexp* re, int next) {
+    bool ng = re->flags & NonGreedy;
+    switch (re->op) {
+      case OpLiteral: return literal(re, next);
+      case OpCharClass: return charClass(re, next);
+      case OpAnyChar:
+      case OpAnyCharNotNL:
+        return fail("unsupported: `.` (UTF-8 automata out of scope)");
+      case OpConcat: {
+        if (!reverse) {
+          for (size_t i = re->sub.size(); i-- > 0;) {
+            next = compile(re->sub[i], next);
+            if (next < 0) return -1;
+          }
+        } else {
+          for (size_t i = 0; i < re->sub.size(); i++) {
+            next = compile(re->sub[i], next);
+            if (next < 0) return -1;
+          }
+        }
+        return next;
+      }
+      case OpAlternate: {
+        std::vector<int> entries;
+        for (auto* s : re->sub) {
+          int e = compile(s, next);
+          if (e < 0) return -1;
+          entries.push_back(e);
+        }
+        int acc = entries.back();
+        for (size_t i = entries.size() - 1; i-- > 0;) acc = emitSplit(entries[i], acc);
+        return acc;
+      }
+      case OpStar: return star(re->sub[0], ng, next);
+      case OpPlus: return plus(re->sub[0], ng, next);
+      case OpQuest: return quest(re->sub[0], ng, next);
+      case OpRepeat: return repeat(re, next);
+      case OpCapture: {
+        if (re->sub.empty()) return next;
+        if (reverse) return compile(re->sub[0], next);  // reverse programs carry no captures
+        Inst close;
+        close.op = I_SAVE;
+        close.slot = 2 * re->cap + 1;
+        close.out = next;
+        int c = emit(close);
+        int body = compile(re->sub[0], c);
+        if (body < 0) return -1;
+        Inst open;
+        open.op = I_SAVE;
+        open.slot = 2 * re->cap;
+        open.out = body;
+        return emit(open);
+      }
+      case OpBeginText: return look(reverse ? L_END_TEXT : L_START_TEXT, next);
+      case OpEndText: return look(reverse ? L_START_TEXT : L_END_TEXT, next);
+      case OpBeginLine: return look(reverse ? L_END_LINE : L_START_LINE, next);
+      case OpEndLine: return look(reverse ? L_START_LINE : L_END_LINE, next);
+      case OpWordBoundary: return look(L_WORD, next);
+      case OpNoWordBoundary: return look(L_NOT_WORD, next);
+      case OpEmptyMatch: return next;
+      case OpNoMatch: {
+        Inst i;
+        i.op = I_FAIL;
+        return emit(i);
+      }
+      default:
+        return fail("unsupported regex operation");
+    }
+  }
+
+  int look(LookKind k, int next) {
+    p.has_looks = true;
+    if (k == L_WORD || k == L_NOT_WORD) p.has_word_looks = true;
+    Inst i;
+    i.op = I_ASSERT;
+    i.look = k;
+    i.out = next;
+    return emit(i);
+  }
+};
+
+bool patternAnchored(const Regexp* re) {
+  switch (re->op) {
+    case OpBeginText: return true;
+    case OpConcat:
+    case OpCapture: return !re->sub.empty() && patternAnchored(re->sub[0]);
+    default: return false;
+  }
+}
+
+std::string build(const Regexp* re, Prog& out, bool reverse) {
+  out = Prog();
+  Builder b{out};
+  b.reverse = reverse;
+  Inst m;
+  m.op = I_MATCH;
+  int match = b.emit(m);
+  int start = b.compile(re, match);
+  if (start < 0) return b.err.empty() ? "compile failed" : b.err;
+  out.start = start;
+  out.num_captures = MaxCap(re) + 1;
+  out.anchored_start = patternAnchored(re);
+  return "";
+}
+
+}  // namespace
+
+std::string CompileProg(const Regexp* re, Prog& out) { return build(re, out, false); }
+std::string CompileReverseProg(const Regexp* re, Prog& out) { return build(re, out, true); }
+
+}  // namespace cgx

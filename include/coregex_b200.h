@@ -1,0 +1,106 @@
+/* coregex_b200.h — C ABI of the B200 bulk-scan engine (libcoregex_b200.so).
+ *
+ * The reference (coregx/coregex) is a pure-Go package with no FFI boundary of its own; the
+ * boundary this library replaces is the internal seam every public Regex method funnels into
+ * (SURVEY.md §8b).  Each entry point below names the reference interface it stands in for; the
+ * cgo binding a coregex maintainer would add is shown in INTEGRATION.md and go/coregex/.
+ *
+ * Conventions (modelled on the reference's Go->asm seam, e.g. simd/memchr_amd64.go:26-35,
+ * prefilter/teddy_ssse3_amd64.go:38): pointer + length in, scalars / caller-owned buffers out,
+ * no callbacks, haystacks are borrowed read-only and never retained.  Only cgx_compile returns
+ * an error text (the reference's search methods cannot fail either); search calls return
+ * CGX_OK or a negative status for resource/driver problems.  There is NO CPU fallback: without
+ * a CUDA device every search call returns CGX_ERR_NO_DEVICE.
+ *
+ * Thread-safety: a cgx_regex may be shared by threads; each call serialises on the regex's own
+ * device scratch (the reference pools per-goroutine SearchState, meta/engine.go:258-296).
+ */
+#ifndef COREGEX_B200_H
+#define COREGEX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cgx_regex cgx_regex;
+
+enum {
+  CGX_OK = 0,
+  CGX_ERR_SYNTAX = -1,      /* pattern rejected; errbuf holds the Go-formatted message        */
+  CGX_ERR_UNSUPPORTED = -2, /* valid pattern outside the GPU engines' scope; errbuf says why  */
+  CGX_ERR_NO_DEVICE = -3,   /* no usable CUDA device / driver                                  */
+  CGX_ERR_CUDA = -4,        /* a CUDA call failed; cgx_last_error() has the text               */
+  CGX_ERR_ARGS = -5,        /* bad arguments (null pointer, misaligned device pointer, ...)    */
+  CGX_ERR_NOMEM = -6
+};
+
+/* ---- compile -------------------------------------------------------------------------------
+ * replaces coregex.Compile / meta.Compile (reference regex.go:110, meta/compile.go:40-60).
+ * On failure *out is NULL and errbuf receives "error parsing regexp: ..." exactly as
+ * syntax.Error formats it (reference meta/compile.go:775-784), or an "unsupported: ..." text. */
+int cgx_compile(const char* pattern, size_t pattern_len, cgx_regex** out, char* errbuf, size_t errcap);
+void cgx_free(cgx_regex* re);
+
+/* reference meta.Engine.Strategy() (meta/engine.go:191): the strategy name the reference would
+ * pick for this pattern, e.g. "UseDigitPrefilter".                                            */
+const char* cgx_strategy(const cgx_regex* re);
+/* which GPU engine runs it: "dfa-runstart", "dfa-byteset", "dfa-lut", "teddy", "fat-teddy",
+ * "pikevm", "serial"                                                                          */
+const char* cgx_engine(const cgx_regex* re);
+/* reference meta.Engine.NumCaptures() (meta/engine.go:232): groups including group 0          */
+int cgx_num_captures(const cgx_regex* re);
+const char* cgx_last_error(void);
+
+/* ---- host-buffer searches (haystack in host memory; H2D/D2H inside the call) ----------------
+ * cgx_is_match            replaces meta.Engine.IsMatch (meta/ismatch.go:27) = Regex.Match
+ * cgx_find_all_index      replaces meta.Engine.FindAllIndicesStreaming (meta/findall.go:155)
+ *                         = Regex.FindAllIndex / AppendAllIndex (regex.go:695,748).
+ *                         limit<0: all matches, limit==0: none (regex.go:696-698).
+ *                         Writes up to cap_pairs (start,end) int64 pairs in match order and stores
+ *                         the TOTAL number of matches in *count (two-call sizing: call with
+ *                         cap_pairs=0 to size, or grow and retry when *count > cap_pairs).
+ * cgx_count               replaces meta.Engine.Count (meta/findall.go:297)
+ * cgx_find_all_submatch_index  replaces meta.Engine.FindAllSubmatch (meta/findall.go:390)
+ *                         = Regex.FindAllSubmatchIndex (regex.go:1423); stride is
+ *                         2*cgx_num_captures ints per match, unmatched groups are -1,-1.     */
+int cgx_is_match(cgx_regex* re, const uint8_t* haystack, size_t len, int* matched);
+int cgx_find_all_index(cgx_regex* re, const uint8_t* haystack, size_t len, int64_t limit,
+                       int64_t* out_pairs, size_t cap_pairs, size_t* count);
+int cgx_count(cgx_regex* re, const uint8_t* haystack, size_t len, int64_t limit, size_t* count);
+int cgx_find_all_submatch_index(cgx_regex* re, const uint8_t* haystack, size_t len, int64_t limit,
+                                int64_t* out, size_t cap_matches, size_t* count);
+
+/* ---- device-resident batch entry (what a GPU-side caller wants; no host copies) --------------
+ * d_haystack: device pointer, 16-byte aligned.  base_offset is added to every reported offset
+ * (shard base when a corpus is split across GPUs).  d_out_pairs: device int64 pairs, 16-byte
+ * aligned, capacity cap_pairs (may be 0/NULL for mode COUNT / ISMATCH).  d_result: device
+ * uint64[2] = {total matches, is-match flag}, written when the scan completes on `stream`
+ * (a cudaStream_t passed as void*; NULL = default stream).  The call only enqueues work.      */
+enum { CGX_MODE_FINDALL = 0, CGX_MODE_COUNT = 1, CGX_MODE_ISMATCH = 2 };
+int cgx_scan_device(cgx_regex* re, const uint8_t* d_haystack, size_t len, int64_t base_offset,
+                    int mode, int64_t* d_out_pairs, size_t cap_pairs, uint64_t* d_result,
+                    void* stream);
+/* submatch variant: d_out receives stride int64 per match */
+int cgx_scan_submatch_device(cgx_regex* re, const uint8_t* d_haystack, size_t len,
+                             int64_t base_offset, int64_t* d_out, size_t cap_matches,
+                             uint64_t* d_result, void* stream);
+
+/* number of kernels launched by this regex since creation (bench.py reports it) */
+uint64_t cgx_launch_count(const cgx_regex* re);
+
+/* ---- synthetic corpora (bench/test utility; deterministic from seed) --------------------------
+ * kind 0: access-log lines   kind 1: text with planted literals (C3/C5)
+ * kind 2: 80-byte e-mail lines (C4).  Fills d_out[0..len) on the device; every block of
+ * `block` bytes ends with '\n' so shards can be generated independently.                        */
+int cgx_synth_device(int kind, uint64_t seed, uint64_t first_block, uint8_t* d_out, size_t len,
+                     const uint8_t* d_literals, const int32_t* d_lit_offsets, int nlit, void* stream);
+int cgx_synth_host(int kind, uint64_t seed, uint64_t first_block, uint8_t* out, size_t len,
+                   const uint8_t* literals, const int32_t* lit_offsets, int nlit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COREGEX_B200_H */

@@ -284,6 +284,16 @@ std::unique_ptr<Engine> Engine::Compile(const std::string& pattern, std::string&
         e->strategy_ = UseNFA;
         e->strategy_exact_ = false;
       }
+      // reference meta/compile.go:663-686 adjustForAnchors: (?m)^ + complete literals and no
+      // other anchors -> WrapLineAnchor (the wrapper has no FindMatch, so findIndicesTeddyAt
+      // takes its Find + LiteralLen / NFA branch)
+      if (hasAnchorAssertions(pr.re) && hasMultilineLineAnchor(pr.re) && !hasNonLineAnchors(pr.re)) {
+        e->teddy_line_anchor_ = true;
+        size_t ul = pats[0].size();
+        for (auto& p : pats)
+          if (p.size() != ul) ul = 0;
+        e->teddy_uniform_len_ = (int64_t)ul;
+      }
       break;
     }
     case UseDFA:
@@ -338,6 +348,23 @@ bool Engine::findNFAAt(const uint8_t* h, int64_t n, int64_t at, int64_t& s, int6
 // reference meta/find_indices.go:925-951
 bool Engine::findTeddyAt(const uint8_t* h, int64_t n, int64_t at, int64_t& s, int64_t& e) {
   if (at >= n) return findNFAAt(h, n, at, s, e);
+  if (teddy_line_anchor_) {
+    // reference prefilter/wrap.go:48-62 (lineAnchorWrapper.Find) + meta/find_indices.go:940-950
+    int64_t pos = at;
+    for (;;) {
+      int64_t c = teddy_ ? teddy_->Find(h, n, pos) : fat_teddy_->Find(h, n, pos);
+      if (c == -1) return false;
+      if (c == 0 || h[c - 1] == '\n') {
+        if (teddy_uniform_len_ > 0) {
+          s = c;
+          e = c + teddy_uniform_len_;
+          return true;
+        }
+        return findNFAAt(h, n, c, s, e);
+      }
+      pos = c + 1;
+    }
+  }
   if (teddy_) return teddy_->FindMatch(h, n, at, s, e);
   return fat_teddy_->FindMatch(h, n, at, s, e);
 }

@@ -83,6 +83,8 @@ class Engine {
   bool strategy_exact_ = true;
   bool digit_run_skip_safe_ = false;
   bool can_match_empty_ = false;
+  bool teddy_line_anchor_ = false;  // prefilter wrapped by WrapLineAnchor (meta/compile.go:663-686)
+  int64_t teddy_uniform_len_ = 0;
   std::unique_ptr<LazyDFA> dfa_;      // forward
   std::unique_ptr<LazyDFA> rev_dfa_;  // reverse (UseDFA / UseBoth bidirectional)
   NFA rev_nfa_;

@@ -1,0 +1,88 @@
+"""CPU model of what scan_dfa.cu computes, driven by the product's own compiled tables.
+
+This is NOT the oracle and not a fallback: it replays the candidate-filter + anchored-walk +
+chain algorithm of the kernel in numpy/Python over the tables exported by the debug entry points,
+so the host compiler (parser -> program -> eager DFA -> filter choice) can be checked against the
+oracle in the CPU-only test tier.  The kernel's parallel decomposition (chunk ownership, batches,
+look-back) is only exercised by the -m gpu tests.
+"""
+import ctypes as C
+
+import numpy as np
+
+import coregex_b200 as cg
+
+_L = cg._lib
+_L.cgx_debug_dfa_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]
+_L.cgx_debug_dfa_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+
+
+def _kind(b):
+    if b == 10:
+        return 3
+    if b == 13:
+        return 4
+    c = chr(b)
+    return 1 if (c.isalnum() and b < 128) or c == "_" else 0
+
+
+class TableModel:
+    def __init__(self, regex):
+        ns, fk, ss, kl, nr = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        start = np.zeros(5, dtype=np.uint16)
+        rng = np.zeros(8, dtype=np.uint8)
+        ok = _L.cgx_debug_dfa_info(regex._h, C.byref(ns), start.ctypes.data, C.byref(fk), C.byref(ss),
+                                   C.byref(kl), rng.ctypes.data, C.byref(nr))
+        assert ok == 1, "not a DFA-engine pattern"
+        self.nstates, self.filter_kind, self.skip_safe = ns.value, fk.value, bool(ss.value)
+        self.kind_lut, self.start = bool(kl.value), start
+        self.ranges = [(int(rng[2 * k]), int(rng[2 * k + 1])) for k in range(nr.value)]
+        self.trans = np.zeros(self.nstates * 256, dtype=np.uint16)
+        self.eoi = np.zeros(self.nstates, dtype=np.uint8)
+        self.lut = np.zeros(256, dtype=np.uint8)
+        _L.cgx_debug_dfa_copy(regex._h, self.trans.ctypes.data, self.eoi.ctypes.data, self.lut.ctypes.data)
+
+    def in_set(self, b):
+        if self.filter_kind == 2:
+            return bool(self.lut[b])
+        return any(lo <= b <= hi for lo, hi in self.ranges)
+
+    def walk(self, h, p0):
+        n = len(h)
+        s = int(self.start[0])
+        if self.kind_lut:
+            s = int(self.start[2 if p0 == 0 else _kind(h[p0 - 1])])
+        last, p = -1, p0
+        while s:
+            if p >= n:
+                if self.eoi[s]:
+                    last = n
+                break
+            e = int(self.trans[s * 256 + h[p]])
+            if e & 0x8000:
+                last = p
+            s = e & 0x7FFF
+            p += 1
+        return last
+
+    def find_all(self, h):
+        """reference findAllIndicesLoop + digit-prefilter style candidate loop over the tables"""
+        h = bytes(h)
+        n, pos, out = len(h), 0, []
+        while pos < n:
+            d = pos
+            while d < n and not self.in_set(h[d]):
+                d += 1
+            if d >= n:
+                break
+            e = self.walk(h, d)
+            if e >= 0:
+                out.append([d, e])
+                pos = e if e > d else d + 1
+            else:
+                pos = d + 1
+                if self.filter_kind == 0:
+                    while pos < n and self.in_set(h[pos]):
+                        pos += 1
+        return out

@@ -1,0 +1,180 @@
+"""-m gpu: parity of the sm_100a prefilter+DFA kernel (scan_dfa.cu) against the CPU oracle,
+through the C ABI (host-buffer entry points and the device-resident entry)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import coregex_b200 as cg
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+IP = r"\d+\.\d+\.\d+\.\d+"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def check(pat, hay, oracle=None):
+    r = cg.Compile(pat)
+    o = oracle or Oracle(pat)
+    want = o.find_all(hay)
+    got = r.find_all_index_array(hay)
+    assert got.shape == want.shape, (pat, len(hay), got.shape, want.shape)
+    assert np.array_equal(got, want), (pat, len(hay))
+    assert r.Count(hay) == len(want)
+    assert r.Match(hay) == (len(want) > 0)
+
+
+EDGE = [
+    b"", b"1", b"1.2.3.4", b"1.2.3.4\n", b"\n", b"\n\n\n", b"x" * 100, b"1.2.3", b"1.2.3.", b"1..2.3.4",
+    b"1.2.3.4.5.6.7.8", b"1.2.3.4.5.6.7.8\n9.9.9.9", b"a1.2.3.4b 10.0.0.1", b"999.999.999.999x",
+    b"1.2.3.4" * 3, b"0.0.0.0\n" * 5, b"12345678901234567890.1.2.3",
+]
+
+
+@pytest.mark.parametrize("hay", EDGE)
+def test_ip_edge_cases(hay):
+    check(IP, hay)
+
+
+def test_nil_semantics():
+    r = cg.Compile(IP)
+    assert r.FindAllIndex(b"no match here") is None      # reference regex.go:711-713
+    assert r.FindAllIndex(b"1.2.3.4", 0) is None          # n == 0 -> nil (regex.go:696-698)
+    assert r.FindAllIndex(b"1.2.3.4 5.6.7.8 9.9.9.9", 2) == [[0, 7], [8, 15]]
+    assert r.Count(b"1.2.3.4 5.6.7.8 9.9.9.9", 2) == 2
+    assert r.FindAllIndex(b"x10.0.0.1 y 1.2.3 z 8.8.8.8") == [[1, 9], [20, 27]]
+
+
+def test_dense_matches_overflow_staging():
+    # 512 matches per 4 KB slice > the 320-entry shared staging buffer -> direct-write replay
+    check(IP, b"1.1.1.1 " * 20000)
+    check(IP, b"1.1.1.1\n" * 20000)
+    check(IP, (b"7.7.7.7 " * 700 + b"\n" + b"x" * 3000 + b"\n") * 30)
+
+
+def test_swallowed_candidates_and_slow_chain():
+    check(IP, b"1.2.3.4.5.6.7.8.9.10.11.12 " * 3000)
+    check(IP, (b"1.2.3.4.5.6.7\n" * 50 + b"8.8.8.8 ok\n") * 500)
+
+
+def test_long_lines_cross_chunks():
+    rng = np.random.default_rng(3)
+    body = b" ".join(b"%d.%d.%d.%d" % tuple(rng.integers(0, 256, 4)) for _ in range(12000))
+    assert len(body) > 3 * 32768
+    check(IP, body)                          # one line, no newline at all
+    check(IP, body + b"\n" + body[:50000])   # a long line, then another
+    check(IP, b"x" * 40000 + b"1.2.3.4" + b"y" * 40000 + b"\n5.6.7.8\n")
+
+
+def test_matches_straddling_chunk_and_slice_boundaries():
+    for off in list(range(32768 - 20, 32768 + 4)) + list(range(4096 - 16, 4096 + 3)):
+        hay = b"a" * off + b"192.168.100.200" + b" tail\n" + b"1.2.3.4\n"
+        check(IP, hay)
+    for off in range(32768 - 6, 32768 + 2):
+        hay = (b"z" * (off - 1)) + b"\n" + b"10.20.30.40 x\n" * 3
+        check(IP, hay)
+
+
+@pytest.mark.parametrize("blocks", [1, 7, 8, 9, 64, 300, 3000])
+def test_ip_synthetic_log_sizes(blocks):
+    hay = cg.synth_host(cg.SYNTH_LOG, 0xC0FFEE + blocks, 4096 * blocks)
+    check(IP, hay)
+
+
+def test_unaligned_tail_lengths():
+    hay = cg.synth_host(cg.SYNTH_LOG, 99, 4096 * 20)
+    for cut in [1, 15, 16, 17, 31, 33, 4095, 4097, 32767, 32769, 40001, 81919]:
+        check(IP, hay[:cut])
+
+
+OTHER = [
+    r"[1-9][0-9]*|0", r"\d{3}-\d{4}", r"\d+", "ab", r"foo\d+", r"\d+\.\d+", r"user\d+", r"[a-zA-Z]+\d+",
+    r"[0-9]+ms", r"\d{4}-\d{2}-\d{2}", r"\d+\.\d+\.\d+\.35", r"[a-f0-9]{8,}", r"\w+@\w+\.org",
+    r"\d+\.\d+\.\d+", r"word\d+", r"[0-5]+\.\d+", r"https?://[a-z.]+",
+]
+
+
+@pytest.mark.parametrize("pat", OTHER)
+def test_other_patterns_on_fixture_corpus(pat):
+    corpus = open(os.path.join(ROOT, "tests", "golden", "stdlib_corpus.txt"), "rb").read()
+    check(pat, corpus)
+    check(pat, corpus[:33000])
+
+
+LOOK = [r"\bfoo\b", r"(?m)^\d+", r"(?m)\d+$", r"\d+\b", r"(?m)^(GET|POST|PUT)", r"\Bbc", r"(?i)error\d*x?"]
+
+
+@pytest.mark.parametrize("pat", LOOK)
+def test_look_patterns_follow_stdlib(pat):
+    """Look-around patterns: the GPU DFA implements stdlib semantics (the reference's lazy DFA is
+    input-order dependent for some of these, see test_multiline_dollar_byte_class_quirk)."""
+    corpus = open(os.path.join(ROOT, "tests", "golden", "stdlib_corpus.txt"), "rb").read()
+    r = cg.Compile(pat)
+    want = np.array([[m.start(), m.end()] for m in re.finditer(pat.encode(), corpus)], dtype=np.int64).reshape(-1, 2)
+    got = r.find_all_index_array(corpus)
+    assert np.array_equal(got, want)
+
+
+def test_random_small_haystacks():
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"0123456789.. ab\n@_x-", dtype=np.uint8)
+    pats = [IP, r"\d+\.\d+", r"\d{2}-\d", r"a+b", r"ab|a", r"[1-9][0-9]*|0", r"\d+x", r"[0-5]+\.\d+"]
+    regs = {p: (cg.Compile(p), Oracle(p)) for p in pats}
+    for it in range(60):
+        n = int(rng.integers(0, 3000))
+        h = bytes(alphabet[rng.integers(0, len(alphabet), n)])
+        for p in pats:
+            r, o = regs[p]
+            assert np.array_equal(r.find_all_index_array(h), o.find_all(h)), (p, h)
+
+
+def test_device_entry_with_base_offset():
+    import torch
+    from gpu_util import dev_corpus, scan_device
+    t = dev_corpus(cg.SYNTH_LOG, 4242, 4096 * 100)
+    host = t.cpu().numpy()
+    assert np.array_equal(host, cg.synth_host(cg.SYNTH_LOG, 4242, 4096 * 100))  # host twin == device
+    r = cg.Compile(IP)
+    want = Oracle(IP).find_all(host)
+    total, flag, pairs = scan_device(r, t, base=1 << 40)
+    assert total == len(want) and np.array_equal(pairs - (1 << 40), want)
+    total, flag, _ = scan_device(r, t, mode=cg.MODE_COUNT)
+    assert total == len(want)
+    total, flag, _ = scan_device(r, t, mode=cg.MODE_ISMATCH)
+    assert flag == 1
+    # capacity smaller than the match count: count is still exact, prefix is written
+    total, flag, pairs = scan_device(r, t, cap=100)
+    assert total == len(want) and np.array_equal(pairs, want[:100])
+
+
+def test_full_size_properties_1gb():
+    """BASELINE config 2 (1 GB log lines): size-independent properties + oracle on sampled blocks."""
+    import torch
+    from gpu_util import dev_corpus, scan_device
+    n = 1 << 30
+    t = dev_corpus(cg.SYNTH_LOG, 0xC0FFEE + 2, n)
+    r = cg.Compile(IP)
+    total, _, pairs = scan_device(r, t, cap=n // 16)
+    assert total == len(pairs)
+    s, e = pairs[:, 0], pairs[:, 1]
+    assert np.all(e > s) and np.all(s[1:] >= e[:-1])            # sorted, non-overlapping
+    assert np.all(e - s >= 7) and np.all(e - s <= 15)
+    cnt, _, _ = scan_device(r, t, mode=cg.MODE_COUNT)
+    assert cnt == total
+    # shard additivity: scanning the two halves (line-aligned by construction) gives the same list
+    half = n // 2
+    t1, _, p1 = scan_device(r, t[:half], cap=n // 16)
+    t2, _, p2 = scan_device(r, t[half:], cap=n // 16, base=half)
+    assert t1 + t2 == total and np.array_equal(np.concatenate([p1, p2]), pairs)
+    # oracle on 64 random 256 KB windows regenerated on the host
+    rng = np.random.default_rng(1)
+    o = Oracle(IP)
+    win = 64 * 4096
+    for b in rng.integers(0, n // win, 64):
+        lo = int(b) * win
+        hay = cg.synth_host(cg.SYNTH_LOG, 0xC0FFEE + 2, win, first_block=lo // 4096)
+        want = o.find_all(hay) + lo
+        i0, i1 = np.searchsorted(s, lo), np.searchsorted(s, lo + win)
+        assert np.array_equal(pairs[i0:i1], want)

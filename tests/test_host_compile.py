@@ -1,0 +1,154 @@
+"""CPU-tier checks of the product's host compiler: the C-ABI library loads and exports every
+declared symbol, compile errors carry the Go-formatted text, the reference-strategy
+classification agrees with the oracle's restatement, and the compiled DFA tables + filter choice
+reproduce the oracle's matches when replayed by tests/table_model.py (no GPU involved)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import coregex_b200 as cg
+from oracle_lib import Oracle, OracleError
+from table_model import TableModel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "coregex_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(cgx_[a-z_]+)\s*\(", hdr)))
+    assert len(names) >= 14
+    lib = ctypes.CDLL(os.path.join(ROOT, "coregex_b200", "lib", "libcoregex_b200.so"))
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_compile_errors_are_go_formatted():
+    cases = {
+        "(": "error parsing regexp: missing closing ): `(`",
+        "a)": "error parsing regexp: unexpected ): `a)`",
+        "a**": "error parsing regexp: invalid nested repetition operator: `**`",
+        "[a": "error parsing regexp: missing closing ]: `[a`",
+        "x{1001}": "error parsing regexp: invalid repeat count: `{1001}`",
+        "\\8": "error parsing regexp: invalid escape sequence: `\\8`",
+    }
+    for pat, msg in cases.items():
+        with pytest.raises(cg.Error) as ei:
+            cg.Compile(pat)
+        assert str(ei.value) == msg
+    with pytest.raises(cg.Error) as ei:
+        cg.MustCompile("(")
+    assert str(ei.value).startswith("regexp: Compile(`(`): error parsing regexp")
+
+
+def test_unsupported_patterns_fail_loudly():
+    for pat in ["a*", r"x.y", r"[^a]+", r"[a-z]+\s+[a-z]+", r"\pL"]:
+        with pytest.raises(cg.UnsupportedError):
+            cg.Compile(pat)
+
+
+def test_no_device_means_error_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = cg.Compile(r"\d+")
+    with pytest.raises(cg.NoDeviceError):
+        r.Match(b"123")
+    with pytest.raises(cg.NoDeviceError):
+        r.FindAllIndex(b"123")
+
+
+STRAT_PATTERNS = [
+    r"\d+\.\d+\.\d+\.\d+", r"[1-9][0-9]*|0", "cat|dog", r"\w+@\w+\.\w+", r"(\w+)@(\w+)\.(\w+)", r"\d+",
+    "ab", "error|warning|fatal|critical", r"\d{3}-\d{4}", r"[0-5]+x", r"foo\d+", r"\bfoo\b", "^abc",
+    "abc$", "(?m)^abc$", r"\d+\.\d+\.\d+\.35", "|".join("p%02d" % i for i in range(50)),
+    "|".join("w%03dx" % i for i in range(64)), "|".join("w%03dx" % i for i in range(70)),
+    r"(?i)error", r"(?m)^(GET|POST|PUT)", r"[a-zA-Z]+\d+", r"\w+[0-9]+", r"user\d+", r"https?://[a-z.]+",
+    r"[a-f0-9]{32,}", r"(?i)(error|fail|panic)", r"\d+\.\d+", "foo|foobar|barfoo", r"a+b",
+]
+
+
+@pytest.mark.parametrize("pat", STRAT_PATTERNS)
+def test_reference_strategy_agrees_with_oracle(pat):
+    o = Oracle(pat)
+    try:
+        r = cg.Compile(pat)
+    except cg.UnsupportedError:
+        pytest.skip("outside GPU scope")
+    want = o.strategy
+    if want == "UseNFA" and not o.strategy_exact:
+        pytest.skip("oracle fell back")
+    assert r.strategy == want
+
+
+def test_ip_engine_choice():
+    r = cg.Compile(r"\d+\.\d+\.\d+\.\d+")
+    assert (r.strategy, r.engine) == ("UseDigitPrefilter", "dfa-runstart")
+    m = TableModel(r)
+    assert m.nstates <= 12 and m.filter_kind == 0 and m.skip_safe and m.ranges == [(0x30, 0x39)]
+    assert m.find_all(b"x10.0.0.1 y 1.2.3 z 8.8.8.8") == [[1, 9], [20, 27]]
+    assert m.find_all(b"1.2.3.4.5.6.7") == [[0, 7]]
+
+
+DFA_PATTERNS = [
+    r"\d+\.\d+\.\d+\.\d+", r"[1-9][0-9]*|0", r"\d{3}-\d{4}", r"\w+@\w+\.\w+", r"(\w+)@(\w+)\.(\w+)", r"\d+",
+    "ab", r"foo\d+", r"\bfoo\b", r"(?m)^\d+", r"(?m)\d+$", r"\d+\.\d+", r"user\d+", r"[a-zA-Z]+\d+",
+    r"(?i)error", r"[0-9]+ms", r"\d{4}-\d{2}-\d{2}", r"a+b", r"ab|a", r"\ba", r"\d+\.\d+\.\d+\.35", r"[a-f0-9]{8,}",
+    r"(?m)^(GET|POST|PUT)", r"\Babc\B", r"\d+\b",
+]
+
+
+@pytest.mark.parametrize("pat", DFA_PATTERNS)
+def test_tables_match_python_re_on_corpus(pat):
+    """Eager DFA + filter tables == stdlib leftmost-first semantics (Python re on bytes)."""
+    corpus = open(os.path.join(ROOT, "tests", "golden", "stdlib_corpus.txt"), "rb").read()[:6000]
+    r = cg.Compile(pat)
+    if "teddy" in r.engine:
+        pytest.skip("literal engine (covered by the teddy tests)")
+    m = TableModel(r)
+    want = [[x.start(), x.end()] for x in re.finditer(pat.encode(), corpus)]
+    assert m.find_all(corpus) == want
+
+
+def test_tables_match_oracle_random():
+    rng = np.random.default_rng(11)
+    alphabet = np.frombuffer(b"0123456789.. ab\n@_x-", dtype=np.uint8)
+    pats = [r"\d+\.\d+\.\d+\.\d+", r"\d+\.\d+", r"\d{2}-\d", r"a+b", r"\w+@\w+\.\w+", r"ab|a",
+            r"[1-9][0-9]*|0", r"\d+\.\d+\.\d+\.35", r"\d+x"]
+    models = {p: TableModel(cg.Compile(p)) for p in pats}
+    oracles = {p: Oracle(p) for p in pats}
+    for it in range(300):
+        n = int(rng.integers(0, 90))
+        h = bytes(alphabet[rng.integers(0, len(alphabet), n)])
+        for p in pats:
+            assert models[p].find_all(h) == oracles[p].find_all(h).tolist(), (p, h)
+
+
+def test_skip_safe_quirk_is_reproduced_only_when_reference_has_it():
+    # `[0-5]+x`: the reference picks UseReverseSuffix (suffix literal "x"), so stdlib semantics apply
+    r = cg.Compile(r"[0-5]+x")
+    assert r.strategy == "UseReverseSuffix"
+    assert TableModel(r).find_all(b"65x") == [[1, 3]]
+    # `[0-5]+\.\d+`: UseDigitPrefilter + digitRunSkipSafe -> the run skip hides the match at 1,
+    # exactly as the oracle (reference meta/find_indices.go:1079-1084) does
+    r = cg.Compile(r"[0-5]+\.\d+")
+    o = Oracle(r"[0-5]+\.\d+")
+    assert r.strategy == o.strategy == "UseDigitPrefilter" and o.digit_run_skip_safe
+    assert TableModel(r).find_all(b"65.1 ") == o.find_all(b"65.1 ").tolist() == []
+
+
+def test_synth_host_is_deterministic_and_line_aligned():
+    a = cg.synth_host(cg.SYNTH_LOG, 123, 4096 * 4)
+    b = cg.synth_host(cg.SYNTH_LOG, 123, 4096 * 2, first_block=2)
+    assert bytes(a[8192:]) == bytes(b)
+    for k in range(1, 5):
+        assert a[4096 * k - 1] == 10
+    lits = [b"error", b"warning", b"fatal", b"critical"]
+    t = cg.synth_host(cg.SYNTH_TEXT, 5, 4096 * 8, literals=lits)
+    assert t[-1] == 10 and sum(bytes(t).count(x) for x in lits) > 20
+    e = cg.synth_host(cg.SYNTH_EMAIL, 5, 80 * 100)
+    lines = bytes(e).split(b"\n")[:-1]
+    assert len(lines) == 100 and all(len(x) == 79 and x.count(b"@") == 1 for x in lines)
+    assert all(re.search(rb"[a-z]+@[a-z]+\.[a-z]+", x) for x in lines)
