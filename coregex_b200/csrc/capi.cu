@@ -160,6 +160,7 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
     a.filter.hi[k] = c.rhi[k];
   }
   a.filter.lut = (const uint8_t*)re->d_lut.p;
+  a.flat = c.flat;
   a.skip_safe = c.skip_safe ? 1 : 0;
   a.delim = c.delim;
   a.mode = mode;
@@ -276,6 +277,24 @@ int cgx_debug_dfa_copy(const cgx_regex* re, uint16_t* trans, uint8_t* eoi, uint8
   memcpy(eoi, c.dfa.eoi.data(), c.dfa.eoi.size());
   memcpy(lut, c.lut, 256);
   return CGX_OK;
+}
+
+// flat start-filter program: ops[2*i]=kind, ops[2*i+1]=class; ranges[c][r] = lo,hi
+int cgx_debug_flat(const cgx_regex* re, uint8_t* ops, int* nclasses, uint8_t* nranges4, uint8_t* ranges32) {
+  const FlatDev& f = re->c->flat;
+  for (int i = 0; i < f.nops; i++) {
+    ops[2 * i] = f.op_kind[i];
+    ops[2 * i + 1] = f.op_class[i];
+  }
+  *nclasses = f.nclasses;
+  for (int c = 0; c < 4; c++) {
+    nranges4[c] = f.cls_nranges[c];
+    for (int r = 0; r < 4; r++) {
+      ranges32[(c * 4 + r) * 2] = f.cls_lo[c][r];
+      ranges32[(c * 4 + r) * 2 + 1] = f.cls_hi[c][r];
+    }
+  }
+  return f.nops;
 }
 
 // ---- synthetic corpora ---------------------------------------------------------------------------

@@ -71,9 +71,133 @@ static bool setToRanges(const ByteSet& s, int& n, uint8_t* lo, uint8_t* hi) {
   return n > 0;
 }
 
+// ---- flat-pattern extraction for the bit-parallel start filter ---------------------------------
+// Accepts Concat/Capture/Literal/CharClass/Plus/Star/Quest/Repeat{m,n<=4} over ASCII classes with
+// at most 4 ranges each, at most 4 distinct classes and 24 items.  Greedy vs lazy is irrelevant
+// (the filter answers "does some match start here").
+namespace {
+struct FlatBuilder {
+  FlatDev f;
+  bool ok = true;
+  int classOf(const ByteSet& s) {
+    uint8_t lo[4], hi[4];
+    int n;
+    if (!setToRanges(s, n, lo, hi)) { ok = false; return 0; }
+    for (int c = 0; c < f.nclasses; c++) {
+      if (f.cls_nranges[c] != n) continue;
+      bool same = true;
+      for (int k = 0; k < n; k++) same &= f.cls_lo[c][k] == lo[k] && f.cls_hi[c][k] == hi[k];
+      if (same) return c;
+    }
+    if (f.nclasses == 4) { ok = false; return 0; }
+    int c = f.nclasses++;
+    f.cls_nranges[c] = (uint8_t)n;
+    for (int k = 0; k < n; k++) { f.cls_lo[c][k] = lo[k]; f.cls_hi[c][k] = hi[k]; }
+    return c;
+  }
+  void push(int kind, const ByteSet& s) {
+    if (!ok) return;
+    if (f.nops == 24) { ok = false; return; }
+    int c = classOf(s);
+    if (!ok) return;
+    f.op_kind[f.nops] = (uint8_t)kind;
+    f.op_class[f.nops] = (uint8_t)c;
+    f.nops++;
+  }
+  static bool classSet(const Regexp* re, ByteSet& s) {
+    s = ByteSet{};
+    if (re->op == OpCharClass) {
+      if (re->rune.empty()) return false;
+      for (size_t k = 0; k + 1 < re->rune.size(); k += 2) {
+        if (re->rune[k + 1] > 127) return false;
+        set_add(s, (unsigned)re->rune[k], (unsigned)re->rune[k + 1]);
+      }
+      return true;
+    }
+    if (re->op == OpLiteral && re->rune.size() == 1 && re->rune[0] < 128) {
+      unsigned r = (unsigned)re->rune[0];
+      set_add(s, r, r);
+      bool letter = (r >= 'a' && r <= 'z') || (r >= 'A' && r <= 'Z');
+      if ((re->flags & FoldCase) && letter) set_add(s, r ^ 0x20, r ^ 0x20);
+      return true;
+    }
+    if (re->op == OpCapture && re->sub.size() == 1) return classSet(re->sub[0], s);
+    return false;
+  }
+  void walk(const Regexp* re) {
+    if (!ok) return;
+    ByteSet s;
+    switch (re->op) {
+      case OpConcat:
+        for (auto* x : re->sub) walk(x);
+        return;
+      case OpCapture:
+        if (re->sub.size() == 1) return walk(re->sub[0]);
+        ok = false;
+        return;
+      case OpLiteral:
+        for (int32_t r : re->rune) {
+          if (r > 127) { ok = false; return; }
+          ByteSet b{};
+          set_add(b, (unsigned)r, (unsigned)r);
+          bool letter = (r >= 'a' && r <= 'z') || (r >= 'A' && r <= 'Z');
+          if ((re->flags & FoldCase) && letter) set_add(b, (unsigned)r ^ 0x20, (unsigned)r ^ 0x20);
+          push(0, b);
+        }
+        return;
+      case OpCharClass:
+        if (!classSet(re, s)) { ok = false; return; }
+        push(0, s);
+        return;
+      case OpPlus: case OpStar: case OpQuest:
+        if (re->sub.size() != 1 || !classSet(re->sub[0], s)) { ok = false; return; }
+        push(re->op == OpPlus ? 1 : re->op == OpStar ? 2 : 3, s);
+        return;
+      case OpRepeat: {
+        if (re->sub.size() != 1 || !classSet(re->sub[0], s)) { ok = false; return; }
+        int mx = re->max == -1 ? re->min : re->max;
+        if (mx > 8) { ok = false; return; }
+        for (int i = 0; i < re->min; i++) push(0, s);
+        if (re->max == -1) push(2, s);
+        else for (int i = re->min; i < re->max; i++) push(3, s);
+        return;
+      }
+      default:
+        ok = false;
+    }
+  }
+};
+}  // namespace
+
+static void BuildFlat(const Regexp* re, FlatDev& out) {
+  FlatBuilder b;
+  memset(&b.f, 0, sizeof b.f);
+  b.walk(re);
+  memset(&out, 0, sizeof out);
+  // worth it only when the pattern is longer than its first item (otherwise the first-level
+  // filter already is the whole pattern)
+  if (!(b.ok && b.f.nops >= 2)) return;
+  for (int c = 0; c < b.f.nclasses; c++)
+    for (int r = 0; r < b.f.cls_nranges[c]; r++) {
+      uint32_t lo = b.f.cls_lo[c][r], hi = b.f.cls_hi[c][r], w = hi - lo, m = 0;
+      while (m < w) m = m * 2 + 1;
+      if ((lo & m) == 0) {  // x in [lo,hi]  <=>  (x ^ lo) <= w
+        b.f.cls_mode[c][r] = 0;
+        b.f.cls_k1[c][r] = lo * 0x01010101u;
+        b.f.cls_k2[c][r] = (0x7Fu - w) * 0x01010101u;
+      } else {
+        b.f.cls_mode[c][r] = 1;
+        b.f.cls_k1[c][r] = 0x80808080u - lo * 0x01010101u;
+        b.f.cls_k2[c][r] = (hi * 0x01010101u) | 0x80808080u;
+      }
+    }
+  out = b.f;
+}
+
 int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, std::string& err) {
   std::unique_ptr<Compiled> c(new Compiled());
   c->pattern = pattern;
+  memset(&c->flat, 0, sizeof c->flat);
   ParseResult pr = Parse(pattern, Perl, c->arena);
   if (!pr.re) {
     err = pr.err;
@@ -123,6 +247,13 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
     for (int k = 1; k < SK_COUNT; k++)
       if (c->dfa.start[k] != c->dfa.start[0]) c->kind_lut_needed = true;
     memset(c->lut, 0, sizeof c->lut);
+    BuildFlat(pr.re, c->flat);
+    auto flat_first = [&]() {
+      FlatDev& f = c->flat;
+      f.first_is_filter = f.nops && f.cls_nranges[0] == c->nranges;
+      for (int k = 0; k < c->nranges && f.first_is_filter; k++)
+        if (f.cls_lo[0][k] != c->rlo[k] || f.cls_hi[0][k] != c->rhi[k]) f.first_is_filter = 0;
+    };
     if (c->an.strategy == RS_UseDigitPrefilter) {
       // reference meta/find_indices.go:1050-1088: candidates are ASCII digits; with
       // digitRunSkipSafe a failed candidate skips the rest of its digit run.
@@ -132,6 +263,7 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
       c->skip_safe = c->an.digit_run_skip_safe;
       c->filter_kind = c->skip_safe ? F_RUNSTART : F_BYTESET;
       c->engine_name = c->skip_safe ? "dfa-runstart" : "dfa-byteset";
+      flat_first();
     } else {
       for (int b = 0; b < 256; b++) c->lut[b] = set_has(c->dfa.first_bytes, b) ? 1 : 0;
       if (setToRanges(c->dfa.first_bytes, c->nranges, c->rlo, c->rhi)) {
@@ -142,7 +274,9 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
         c->filter_kind = F_LUT;
         c->engine_name = "dfa-lut";
       }
+      flat_first();
     }
+    if (c->flat.nops) c->engine_name += "+flat";
   }
   out = std::move(c);
   return COMPILE_OK;

@@ -36,6 +36,7 @@ struct Compiled {
   uint8_t lut[256];
   bool skip_safe = false;
   bool kind_lut_needed = false;
+  FlatDev flat;  // nops == 0 when the pattern is not flat
   uint8_t delim = '\n';
 
   // ENG_TEDDY

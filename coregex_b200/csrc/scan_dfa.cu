@@ -9,7 +9,10 @@
 // Shape: a persistent grid; each CTA repeatedly takes a 32 KB chunk ticket, pulls the chunk
 // (+16 B before, +1 KB after) into shared memory with one TMA bulk copy, then
 //   phase A  every warp classifies 1 KB tiles with SWAR compares (32 B per lane -> one 32-bit
-//            candidate word per lane) into a shared bitmap  — the memchr_digit / first-byte scan;
+//            word per lane and byte class).  For flat patterns the class words feed a
+//            bit-parallel right-to-left evaluation of the whole pattern (warp-wide carry chains
+//            through ballots) that leaves only positions a match can really start at; otherwise
+//            the first-byte / run-start set is the candidate set  — the prefilter;
 //   phase B  each warp owns the lines that START in its 4 KB slice, compacts candidates into
 //            full batches of 32, walks the shared-memory DFA table one candidate per lane, and
 //            resolves the leftmost non-overlapping chain exactly like the reference loop
@@ -33,14 +36,16 @@ constexpr int CH = 32768;         // chunk bytes owned by one CTA iteration
 constexpr int OVER = 1024;        // bytes after the chunk that are classified too
 constexpr int PRE = 16;           // bytes before the chunk kept in the window
 constexpr int WIN = PRE + CH + OVER;
+constexpr int WINPAD = 16;        // sentinel bytes after the window (always the delimiter)
 constexpr int TILE = 1024;        // bytes per warp classification step (32 B per lane)
 constexpr int NTILES = (CH + OVER) / TILE;
 constexpr int NWORDS = NTILES * 32;
 constexpr int SUB = CH / WARPS;   // slice whose line starts a warp owns
 constexpr int GROUP = 16;         // bitmap words compacted per step
 constexpr int QCAP = GROUP * 32 + 32;
-constexpr int STG = 320;          // staged matches per warp
+constexpr int STG = 192;          // staged matches per warp
 constexpr int64_t INF = (int64_t)1 << 62;
+constexpr uint32_t FULL = 0xffffffffu;
 
 struct Smem {
   uint64_t mbar;
@@ -52,23 +57,24 @@ struct Smem {
   uint32_t cand[NWORDS];
   uint16_t queue[WARPS][QCAP];
   uint2 stage[WARPS][STG];
-  alignas(128) uint8_t win[WIN];
-  // followed by: uint16_t trans[nstates*256]; uint8_t eoi[nstates]; uint8_t lut[256]
+  alignas(128) uint8_t win[WIN + WINPAD];
+  // followed by: uint32_t trans[nstates*256]; uint8_t eoi[nstates]; uint8_t lut[256]
 };
 
 struct Ctx {
   const ScanArgs& a;
   Smem& sm;
-  const uint16_t* trans;  // shared
+  const uint32_t* trans;  // shared: (next_state * 1024) | (match_before << 31)
   const uint8_t* eoi;     // shared
-  const uint8_t* lut;     // shared (F_LUT) or null
+  const uint8_t* lut;     // shared (F_LUT)
   int64_t cbeg;           // chunk begin (global)
   int64_t gw;             // global position of win[0]
+  int wend;               // number of valid bytes in the window
   int lane, warp;
 };
 
 __device__ __forceinline__ uint8_t byte_at(const Ctx& c, int64_t p) {
-  int64_t i = p - c.gw;
+  const int64_t i = p - c.gw;
   if (i >= 0 && i < WIN) return c.sm.win[i];
   return __ldg(c.a.h + p);
 }
@@ -83,56 +89,73 @@ __device__ __forceinline__ bool in_filter_set(const Ctx& c, uint8_t b) {
 __device__ __forceinline__ int start_kind(uint8_t b) {
   if (b == '\n') return 3;
   if (b == '\r') return 4;
-  bool w = (b >= 'a' && b <= 'z') || (b >= 'A' && b <= 'Z') || (b >= '0' && b <= '9') || b == '_';
+  const bool w = (b >= 'a' && b <= 'z') || (b >= 'A' && b <= 'Z') || (b >= '0' && b <= '9') || b == '_';
   return w ? 1 : 0;
 }
 
-// Anchored leftmost-first walk from p0.  Returns the match end or -1.
-__device__ __forceinline__ int64_t dfa_walk(const Ctx& c, int64_t p0) {
+// Anchored leftmost-first walk from global position p0 through global memory (any position).
+__device__ int64_t dfa_walk_slow(const Ctx& c, int64_t p0) {
   unsigned s = c.a.dfa.start[0];
-  if (c.a.dfa.kind_lut_needed) {
-    int k = p0 == 0 ? 2 : start_kind(byte_at(c, p0 - 1));
-    s = c.a.dfa.start[k];
-  }
-  int64_t last = -1;
-  int64_t p = p0;
+  if (c.a.dfa.kind_lut_needed) s = c.a.dfa.start[p0 == 0 ? 2 : start_kind(byte_at(c, p0 - 1))];
+  int64_t last = -1, p = p0;
   const int64_t n = c.a.n;
-  // fast loop while inside the shared window
-  int64_t i = p - c.gw;
-  int64_t wend = n - c.gw < WIN ? n - c.gw : WIN;
   while (s) {
-    if (i >= wend) break;
-    unsigned e = c.trans[(s << 8) + c.sm.win[i]];
-    if (e & 0x8000u) last = c.gw + i;
-    s = e & 0x7FFFu;
-    i++;
-  }
-  p = c.gw + i;
-  while (s) {  // beyond the window (long line) or at end of input
     if (p >= n) {
       if (c.eoi[s]) last = n;
       break;
     }
-    unsigned e = c.trans[(s << 8) + __ldg(c.a.h + p)];
-    if (e & 0x8000u) last = p;
-    s = e & 0x7FFFu;
+    const uint32_t e = c.trans[(s << 8) + byte_at(c, p)];
+    if (e >> 31) last = p;
+    s = (e & 0x7fffffffu) >> 10;
     p++;
   }
   return last;
 }
 
+// Anchored walk from window index i0 (global p0 = gw + i0).  Returns the match end as a window
+// index (may exceed WIN when the slow path took over) or -1.  The fast loop has no bounds check:
+// win[wend .. wend+WINPAD) holds the delimiter, which sends every state to DEAD.
+__device__ __forceinline__ int dfa_walk(const Ctx& c, int i0) {
+  uint32_t sp = (uint32_t)c.a.dfa.start[0] << 10;
+  if (c.a.dfa.kind_lut_needed) {
+    const int k = (c.gw + i0 == 0) ? 2 : start_kind(c.sm.win[i0 - 1]);
+    sp = (uint32_t)c.a.dfa.start[k] << 10;
+  }
+  int last = -1, i = i0;
+  const char* tb = reinterpret_cast<const char*>(c.trans);
+  while (sp) {
+    const uint32_t b = c.sm.win[i];
+    const uint32_t e = *reinterpret_cast<const uint32_t*>(tb + sp + b * 4);
+    if ((int)e < 0) last = i;
+    sp = e & 0x7fffffffu;
+    i++;
+  }
+  if (i > c.wend) {
+    // consumed a sentinel: the walk left the window (long line) or hit end of input
+    const int64_t e = dfa_walk_slow(c, c.gw + i0);
+    return e < 0 ? -1 : (int)(e - c.gw);
+  }
+  return last;
+}
+
 // ---- phase A: candidate bitmap -------------------------------------------------------------------
-__device__ __forceinline__ uint32_t classify32(const Ctx& c, const uint8_t* p32) {
+__device__ __forceinline__ void load32(const uint8_t* p32, uint32_t (&w)[8]) {
   const uint4 v0 = *reinterpret_cast<const uint4*>(p32);
   const uint4 v1 = *reinterpret_cast<const uint4*>(p32 + 16);
-  uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
+  w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+}
+
+__device__ __forceinline__ uint32_t classify32(const Ctx& c, const uint8_t* p32) {
+  uint32_t w[8];
+  load32(p32, w);
   uint32_t m = 0;
   if (c.a.filter.kind == F_LUT) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      uint32_t x = w[k];
-      uint32_t f = (c.lut[x & 255] ? 1u : 0u) | (c.lut[(x >> 8) & 255] ? 2u : 0u) |
-                   (c.lut[(x >> 16) & 255] ? 4u : 0u) | (c.lut[x >> 24] ? 8u : 0u);
+      const uint32_t x = w[k];
+      const uint32_t f = (c.lut[x & 255] ? 1u : 0u) | (c.lut[(x >> 8) & 255] ? 2u : 0u) |
+                         (c.lut[(x >> 16) & 255] ? 4u : 0u) | (c.lut[x >> 24] ? 8u : 0u);
       m |= f << (4 * k);
     }
     return m;
@@ -146,39 +169,152 @@ __device__ __forceinline__ uint32_t classify32(const Ctx& c, const uint8_t* p32)
   return m;
 }
 
-__device__ void phase_a(const Ctx& c) {
+__device__ void phase_a_plain(const Ctx& c) {
   for (int t = c.warp; t < NTILES; t += WARPS) {
     const int rel = t * TILE + c.lane * 32;  // relative to cbeg
     const uint8_t* p = c.sm.win + PRE + rel;
     uint32_t m = classify32(c, p);
     if (c.a.filter.kind == F_RUNSTART) {
-      uint32_t prev = in_filter_set(c, p[-1]) ? 1u : 0u;
+      const uint32_t prev = in_filter_set(c, p[-1]) ? 1u : 0u;
       m = m & ~((m << 1) | prev);
     }
-    // positions at or beyond n are never candidates
-    int64_t gp = c.cbeg + rel;
+    const int64_t gp = c.cbeg + rel;  // positions at or beyond n are never candidates
     if (gp + 32 > c.a.n) {
-      int64_t v = c.a.n - gp;
+      const int64_t v = c.a.n - gp;
       m = v <= 0 ? 0u : (m & ((1u << v) - 1u));
     }
     c.sm.cand[t * 32 + c.lane] = m;
   }
 }
 
+// Class membership of 32 bytes as a BIT-REVERSED word: bit (31-b) <=> byte b is in class `cls`.
+__device__ __forceinline__ uint32_t class_mask_rev(const FlatDev& f, int cls, const uint32_t (&w)[8]) {
+  uint32_t fl[8];
+  const int nr = f.cls_nranges[cls];
+#pragma unroll
+  for (int k = 0; k < 8; k++) fl[k] = 0;
+  for (int r = 0; r < nr; r++) {
+    const uint32_t k1 = f.cls_k1[cls][r], k2 = f.cls_k2[cls][r];
+    if (f.cls_mode[cls][r] == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const uint32_t x = w[k];
+        const uint32_t z = ((x ^ k1) & 0x7F7F7F7Fu) + k2;  // bit7 set <=> (x^lo)&0x7f > width
+        fl[k] |= ~(z | x) & 0x80808080u;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) fl[k] |= swar_in_range(w[k], k1, k2);
+    }
+  }
+  uint32_t acc[4];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    acc[a] = __dp4a(fl[2 * a], 0x10204080u, 0u);          // bytes 0..3 of the group -> weights 128..16
+    acc[a] = __dp4a(fl[2 * a + 1], 0x01020408u, acc[a]);  // bytes 4..7 -> weights 8..1
+  }
+  // acc[a] = 128 * (8-bit reversed mask of bytes 8a..8a+7)
+  return (acc[0] << 17) | (acc[1] << 9) | (acc[2] << 1) | (acc[3] >> 7);
+}
+
+// 1024-bit helpers over the warp: lane l holds word l; word 0 = the LAST 32 bytes of the tile.
+// "shl1" moves markers one position towards lower addresses (higher bits); the bit entering
+// word 0 (a position past the tile) is 1: unknown territory is assumed to allow a match.
+__device__ __forceinline__ uint32_t shl1(uint32_t m, int lane) {
+  uint32_t dn = __shfl_up_sync(FULL, m, 1);
+  if (lane == 0) dn = FULL;
+  return __funnelshift_l(dn, m, 1);
+}
+// s + c (+1 into word 0) as one 1024-bit addition; carries resolved with two ballots
+__device__ __forceinline__ uint32_t add1024(uint32_t s, uint32_t cc, int lane) {
+  uint32_t sum = s + cc;
+  const uint32_t G = __ballot_sync(FULL, sum < s);
+  const uint32_t P = __ballot_sync(FULL, sum == FULL);
+  const uint32_t A = G | P;
+  const uint32_t carries = A ^ G ^ (A + G + 1u);  // bit l = carry into word l
+  return sum + ((carries >> lane) & 1u);
+}
+
+__device__ void phase_a_flat(const Ctx& c) {
+  const FlatDev& f = c.a.flat;
+  for (int t = c.warp; t < NTILES; t += WARPS) {
+    const int chunk = 31 - c.lane;                // lane l holds the (31-l)-th 32-byte piece
+    const int rel = t * TILE + chunk * 32;        // relative to cbeg
+    const uint8_t* p = c.sm.win + PRE + rel;
+    uint32_t w[8];
+    load32(p, w);
+    uint32_t cm0 = 0, cm1 = 0, cm2 = 0, cm3 = 0;
+    cm0 = class_mask_rev(f, 0, w);
+    if (f.nclasses > 1) cm1 = class_mask_rev(f, 1, w);
+    if (f.nclasses > 2) cm2 = class_mask_rev(f, 2, w);
+    if (f.nclasses > 3) cm3 = class_mask_rev(f, 3, w);
+    // right-to-left evaluation: M = positions from which items k..end can match
+    uint32_t M = FULL;
+    bool all = true;
+    for (int k = f.nops - 1; k >= 0; k--) {
+      const int cls = f.op_class[k], kind = f.op_kind[k];
+      const uint32_t C = cls == 0 ? cm0 : cls == 1 ? cm1 : cls == 2 ? cm2 : cm3;
+      if (all) {  // M is still "everything": closed forms
+        if (kind <= 1) {
+          M = C;
+          all = false;
+        }
+        continue;
+      }
+      if (kind == 0) {
+        M = shl1(M, c.lane) & C;
+      } else if (kind == 3) {
+        M |= shl1(M, c.lane) & C;
+      } else {
+        const uint32_t s = shl1(M, c.lane) & C;
+        const uint32_t plus = ~add1024(s, C, c.lane) & C;
+        M = kind == 1 ? plus : (M | plus);
+      }
+    }
+    // first-level set restricted further (run starts keep the reference's skip semantics)
+    uint32_t first = FULL;
+    if (c.a.filter.kind == F_RUNSTART) {
+      // run starts of the FILTER set (ASCII digits for the reference's DigitPrefilter), which is
+      // class 0 unless the pattern's first class is a strict subset such as [0-5]
+      uint32_t D = cm0;
+      if (!f.first_is_filter) {
+        D = 0;
+        for (int r = 0; r < c.a.filter.nranges; r++) {
+          const uint32_t klo = swar_klo(c.a.filter.lo[r]), khi = swar_khi(c.a.filter.hi[r]);
+          uint32_t m = 0;
+#pragma unroll
+          for (int k = 0; k < 8; k++) m |= pack4(swar_in_range(w[k], klo, khi)) << (4 * k);
+          D |= __brev(m);
+        }
+      }
+      uint32_t up = __shfl_down_sync(FULL, D, 1);
+      if (c.lane == 31) up = in_filter_set(c, c.sm.win[PRE + t * TILE - 1]) ? 1u : 0u;
+      first = D & ~((D >> 1) | (up << 31));
+    }
+    uint32_t m = __brev(M & first);
+    const int64_t gp = c.cbeg + rel;
+    if (gp + 32 > c.a.n) {
+      const int64_t v = c.a.n - gp;
+      m = v <= 0 ? 0u : (m & ((1u << v) - 1u));
+    }
+    c.sm.cand[t * 32 + chunk] = m;
+  }
+}
+
 // first position q >= from with q == 0 or byte(q-1) == delim, searched inside the window only
 __device__ int64_t find_line_start(const Ctx& c, int64_t from) {
   if (from <= 0) return 0;
-  const int64_t wend_g = c.gw + WIN < c.a.n ? c.gw + WIN : c.a.n;  // bytes valid in window
-  for (int64_t q = from - 1 + c.lane; __any_sync(0xffffffffu, q < wend_g); q += 32) {
-    bool hit = q < wend_g && c.sm.win[q - c.gw] == c.a.delim;
-    unsigned b = __ballot_sync(0xffffffffu, hit);
+  const int64_t wend_g = c.gw + c.wend;
+  for (int64_t q = from - 1 + c.lane; __any_sync(FULL, q < wend_g); q += 32) {
+    const bool hit = q < wend_g && c.sm.win[q - c.gw] == c.a.delim;
+    const unsigned b = __ballot_sync(FULL, hit);
     if (b) return q - c.lane + (__ffs(b) - 1) + 1;
   }
-  // the haystack end also terminates the last line
   return INF;
 }
 
 // ---- phase B: verify + chain ---------------------------------------------------------------------
+// Positions inside phase B are window indices (int, relative to gw); a record must be < 2 GiB.
 template <bool DIRECT>
 struct Emitter {
   const Ctx& c;
@@ -187,34 +323,34 @@ struct Emitter {
   unsigned long long goff;   // DIRECT mode: global index of this warp's first match
   __device__ Emitter(const Ctx& cc, unsigned long long g) : c(cc), goff(g) {}
 
-  __device__ __forceinline__ void put(unsigned idx, int64_t s, int64_t e) {
+  __device__ __forceinline__ void put(unsigned idx, int s, int e) {
     if (c.a.mode != M_FINDALL) return;
     if (DIRECT) {
-      unsigned long long gi = goff + idx;
+      const unsigned long long gi = goff + idx;
       if ((int64_t)gi < c.a.cap) {
-        longlong2 v = make_longlong2(s + c.a.base, e + c.a.base);
-        *reinterpret_cast<longlong2*>(c.a.out + 2 * gi) = v;
+        const int64_t b = c.gw + c.a.base;
+        *reinterpret_cast<longlong2*>(c.a.out + 2 * gi) = make_longlong2(b + s, b + e);
       }
     } else {
-      if (idx < STG) c.sm.stage[c.warp][idx] = make_uint2((unsigned)(s - c.cbeg), (unsigned)(e - c.cbeg));
+      if (idx < STG) c.sm.stage[c.warp][idx] = make_uint2((unsigned)s, (unsigned)e);
     }
   }
 };
 
-// One lane replays the reference loop from `pos` while the next candidate is <= last_cand
-// (or, with to_line_end, until the current line ends).  Returns the new chain position.
+// One lane replays the reference loop from window index `pos` while the next candidate is
+// <= last_cand (or, with to_line_end, until the current line ends).  Returns the new chain position.
 template <bool DIRECT>
-__device__ int64_t serial_chain(const Ctx& c, Emitter<DIRECT>& em, int64_t pos, int64_t last_cand,
-                                bool to_line_end) {
+__device__ int serial_chain(const Ctx& c, Emitter<DIRECT>& em, int pos_i, int last_cand, bool to_line_end) {
   unsigned added = 0;
   if (c.lane == 0) {
     const int64_t n = c.a.n;
+    int64_t pos = c.gw + pos_i;
+    const int64_t lastc = c.gw + last_cand;
     while (pos < n) {
-      // reference: digitPos = prefilter.Find(haystack, pos)
-      int64_t d = pos;
+      int64_t d = pos;  // reference: digitPos = prefilter.Find(haystack, pos)
       bool stop = false;
       while (d < n) {
-        uint8_t b = byte_at(c, d);
+        const uint8_t b = byte_at(c, d);
         if (in_filter_set(c, b)) break;
         if (to_line_end && b == c.a.delim) {
           stop = true;
@@ -226,10 +362,10 @@ __device__ int64_t serial_chain(const Ctx& c, Emitter<DIRECT>& em, int64_t pos, 
         pos = d;
         break;
       }
-      if (!to_line_end && d > last_cand) break;  // chain position unchanged
-      int64_t e = dfa_walk(c, d);
+      if (!to_line_end && d > lastc) break;  // chain position unchanged
+      const int64_t e = dfa_walk_slow(c, d);
       if (e >= 0) {
-        em.put(em.nkept + added, d, e);
+        em.put(em.nkept + added, (int)(d - c.gw), (int)(e - c.gw));
         added++;
         pos = e > d ? e : d + 1;
       } else {
@@ -238,21 +374,22 @@ __device__ int64_t serial_chain(const Ctx& c, Emitter<DIRECT>& em, int64_t pos, 
           while (pos < n && in_filter_set(c, byte_at(c, pos))) pos++;
       }
     }
+    pos_i = (int)(pos - c.gw);
   }
-  added = __shfl_sync(0xffffffffu, added, 0);
-  pos = __shfl_sync(0xffffffffu, pos, 0);
+  added = __shfl_sync(FULL, added, 0);
+  pos_i = __shfl_sync(FULL, pos_i, 0);
   if (!DIRECT && em.nkept + added > STG) em.overflow = true;
   em.nkept += added;
-  return pos;
+  return pos_i;
 }
 
 template <bool DIRECT>
-__device__ int64_t process_batch(const Ctx& c, Emitter<DIRECT>& em, int64_t cand, bool valid,
-                                 int64_t kept_end) {
-  int64_t end = -1;
+__device__ __forceinline__ int process_batch(const Ctx& c, Emitter<DIRECT>& em, int cand, bool valid,
+                                             int kept_end) {
+  int end = -1;
   if (valid) end = dfa_walk(c, cand);
   const bool ok = end >= 0;
-  const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+  const unsigned okmask = __ballot_sync(FULL, ok);
   if (!okmask) return kept_end;
   if (c.a.mode == M_ISMATCH) {
     if (c.lane == 0) c.a.total[1] = 1ull;
@@ -260,24 +397,21 @@ __device__ int64_t process_batch(const Ctx& c, Emitter<DIRECT>& em, int64_t cand
     return kept_end;
   }
   const unsigned lower = okmask & ((1u << c.lane) - 1u);
-  const int src = lower ? 31 - __clz(lower) : 0;
-  int64_t pe = __shfl_sync(0xffffffffu, end, src);
+  int pe = __shfl_sync(FULL, end, lower ? 31 - __clz(lower) : 0);
   if (!lower) pe = kept_end;
   bool bad = ok && cand < pe;
-  if (c.a.skip_safe && ok && end < c.a.n) bad |= in_filter_set(c, byte_at(c, end));
-  if (__any_sync(0xffffffffu, bad)) {
+  if (c.a.skip_safe && ok && c.gw + end < c.a.n) bad |= in_filter_set(c, byte_at(c, c.gw + end));
+  if (__any_sync(FULL, bad)) {
     // replay from the chain position through the last candidate of this batch
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    const int hi = 31 - __clz(vmask);
-    const int64_t last_cand = __shfl_sync(0xffffffffu, cand, hi);
+    const unsigned vmask = __ballot_sync(FULL, valid);
+    const int last_cand = __shfl_sync(FULL, cand, 31 - __clz(vmask));
     return serial_chain<DIRECT>(c, em, kept_end, last_cand, false);
   }
   if (ok) em.put(em.nkept + __popc(lower), cand, end);
   const unsigned add = __popc(okmask);
   if (!DIRECT && em.nkept + add > STG) em.overflow = true;
   em.nkept += add;
-  const int top = 31 - __clz(okmask);
-  return __shfl_sync(0xffffffffu, end, top);
+  return __shfl_sync(FULL, end, 31 - __clz(okmask));
 }
 
 template <bool DIRECT>
@@ -287,7 +421,7 @@ __device__ void phase_b(const Ctx& c, Emitter<DIRECT>& em) {
   if (lo >= hi || lo >= c.a.n) return;
   const int64_t bm_end = c.cbeg + CH + OVER;  // bitmap covers [cbeg, bm_end)
   const int64_t hi_b = hi < bm_end ? hi : bm_end;
-  int64_t kept_end = lo;
+  int kept_end = (int)(lo - c.gw);
   uint16_t* q = c.sm.queue[c.warp];
   int qlen = 0;
   const int lo_rel = (int)(lo - c.cbeg);
@@ -301,24 +435,24 @@ __device__ void phase_b(const Ctx& c, Emitter<DIRECT>& em) {
       if (b0 < lo_rel) word &= ~0u << (lo_rel - b0);
       if (b0 + 32 > hi_rel) word &= (1u << (hi_rel - b0)) - 1u;
     }
+    if (!__any_sync(FULL, word != 0)) continue;
     int total;
     int off = qlen + warp_excl_scan(__popc(word), c.lane, total);
     while (word) {
       const int b = __ffs(word) - 1;
       word &= word - 1;
-      q[off++] = (uint16_t)(widx * 32 + b);
+      q[off++] = (uint16_t)(widx * 32 + b + PRE);  // window index
     }
     qlen += total;
     __syncwarp();
     int head = 0;
     while (qlen - head >= 32) {
-      const int64_t cand = c.cbeg + q[head + c.lane];
-      kept_end = process_batch<DIRECT>(c, em, cand, true, kept_end);
+      kept_end = process_batch<DIRECT>(c, em, q[head + c.lane], true, kept_end);
       head += 32;
     }
     if (head) {
       const int rem = qlen - head;
-      uint16_t tmp = c.lane < rem ? q[head + c.lane] : 0;
+      const uint16_t tmp = c.lane < rem ? q[head + c.lane] : 0;
       __syncwarp();
       if (c.lane < rem) q[c.lane] = tmp;
       qlen = rem;
@@ -327,30 +461,32 @@ __device__ void phase_b(const Ctx& c, Emitter<DIRECT>& em) {
   }
   if (qlen) {
     const bool valid = c.lane < qlen;
-    const int64_t cand = c.cbeg + (valid ? q[c.lane] : 0);
-    kept_end = process_batch<DIRECT>(c, em, cand, valid, kept_end);
+    kept_end = process_batch<DIRECT>(c, em, valid ? q[c.lane] : 0, valid, kept_end);
   }
   if (hi > bm_end) {
     // the last owned line runs past the classified window: finish it serially
-    int64_t from = kept_end > bm_end ? kept_end : bm_end;
-    serial_chain<DIRECT>(c, em, from, 0, true);
+    const int bme = (int)(bm_end - c.gw);
+    serial_chain<DIRECT>(c, em, kept_end > bme ? kept_end : bme, 0, true);
   }
 }
 
-__global__ void __launch_bounds__(THREADS, 2) scan_dfa_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  uint16_t* s_trans = reinterpret_cast<uint16_t*>(smem_raw + sizeof(Smem));
+  uint32_t* s_trans = reinterpret_cast<uint32_t*>(smem_raw + sizeof(Smem));
   uint8_t* s_eoi = reinterpret_cast<uint8_t*>(s_trans + (size_t)a.dfa.nstates * 256);
   uint8_t* s_lut = s_eoi + ((a.dfa.nstates + 15) & ~15);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // stage the automaton once per CTA
-  for (int i = tid; i < a.dfa.nstates * 128; i += THREADS)
-    reinterpret_cast<uint32_t*>(s_trans)[i] = reinterpret_cast<const uint32_t*>(a.dfa.trans)[i];
+  // stage the automaton once per CTA, widening u16 (state | match<<15) to premultiplied u32
+  for (int i = tid; i < a.dfa.nstates * 256; i += THREADS) {
+    const uint32_t e = a.dfa.trans[i];
+    s_trans[i] = ((e & 0x7FFFu) << 10) | ((e & 0x8000u) << 16);
+  }
   for (int i = tid; i < a.dfa.nstates; i += THREADS) s_eoi[i] = a.dfa.eoi[i];
   if (a.filter.kind == F_LUT)
     for (int i = tid; i < 256; i += THREADS) s_lut[i] = a.filter.lut[i];
+  if (tid < WINPAD) sm.win[WIN + tid] = a.delim;
   if (tid == 0) {
     mbar_init(&sm.mbar, 1);
     fence_mbar_init();
@@ -379,21 +515,23 @@ __global__ void __launch_bounds__(THREADS, 2) scan_dfa_kernel(const ScanArgs a) 
       }
     }
     // bytes the bulk copy does not cover: before position 0, the <16 B tail, past the end
-    for (int i = tid; i < WIN; i += THREADS) {
-      const int64_t g = gw + i;
-      if (g < 0 || g >= lo_g + bulk) sm.win[i] = g >= 0 && g < a.n ? a.h[g] : a.delim;
+    if (gw < 0 || bulk != (uint32_t)WIN) {
+      for (int i = tid; i < WIN; i += THREADS) {
+        const int64_t g = gw + i;
+        if (g < 0 || g >= lo_g + bulk) sm.win[i] = g >= 0 && g < a.n ? a.h[g] : a.delim;
+      }
     }
     mbar_wait(&sm.mbar, parity);
     parity ^= 1;
     __syncthreads();
 
-    Ctx c{a, sm, s_trans, s_eoi, s_lut, cbeg, gw, lane, warp};
-    phase_a(c);
+    Ctx c{a, sm, s_trans, s_eoi, s_lut, cbeg, gw, (int)(hi_g - gw), lane, warp};
+    if (a.flat.nops) phase_a_flat(c); else phase_a_plain(c);
     {
-      int64_t s = find_line_start(c, cbeg + (int64_t)warp * SUB);
+      const int64_t s = find_line_start(c, cbeg + (int64_t)warp * SUB);
       if (lane == 0) sm.ls[warp] = s;
       if (warp == WARPS - 1) {
-        int64_t e = find_line_start(c, cbeg + CH);
+        const int64_t e = find_line_start(c, cbeg + CH);
         if (lane == 0) sm.ls[WARPS] = e;
       }
       if (tid == 0) sm.woverflow = 0;
@@ -426,12 +564,11 @@ __global__ void __launch_bounds__(THREADS, 2) scan_dfa_kernel(const ScanArgs a) 
                 v = ld_acquire(&a.status[idx]);
               } while ((v >> 62) == 0);
             }
-            const unsigned pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-            // sum values of lanes up to and including the first PREFIX lane
-            const int first = pm ? __ffs(pm) - 1 : 32;
+            const unsigned pm = __ballot_sync(FULL, (v >> 62) == 2);
+            const int first = pm ? __ffs(pm) - 1 : 32;  // nearest chunk that already has a prefix
             unsigned long long val = lane <= first ? (v & LB_VALUE) : 0ull;
 #pragma unroll
-            for (int d = 16; d; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+            for (int d = 16; d; d >>= 1) val += __shfl_xor_sync(FULL, val, d);
             excl += val;
             if (pm) break;
             look -= 32;
@@ -449,12 +586,12 @@ __global__ void __launch_bounds__(THREADS, 2) scan_dfa_kernel(const ScanArgs a) 
       const unsigned long long gbase = sm.cta_base + wexcl;
       if (!sm.woverflow) {
         const unsigned cnt = sm.wcount[warp];
+        const int64_t b = gw + a.base;
         for (unsigned i = lane; i < cnt; i += 32) {
           const unsigned long long gi = gbase + i;
           if ((int64_t)gi < a.cap) {
             const uint2 m = sm.stage[warp][i];
-            longlong2 v = make_longlong2(cbeg + m.x + a.base, cbeg + m.y + a.base);
-            *reinterpret_cast<longlong2*>(a.out + 2 * gi) = v;
+            *reinterpret_cast<longlong2*>(a.out + 2 * gi) = make_longlong2(b + m.x, b + m.y);
           }
         }
       } else {
@@ -475,7 +612,7 @@ __global__ void __launch_bounds__(THREADS, 2) scan_dfa_kernel(const ScanArgs a) 
 }  // namespace
 
 size_t scan_dfa_smem_bytes(int nstates) {
-  return sizeof(Smem) + (size_t)nstates * 512 + ((nstates + 15) & ~15) + 256;
+  return sizeof(Smem) + (size_t)nstates * 1024 + ((nstates + 15) & ~15) + 256;
 }
 
 int64_t scan_dfa_chunks(int64_t n) { return n <= 0 ? 0 : (n + CH - 1) / CH; }

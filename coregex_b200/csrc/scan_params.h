@@ -28,12 +28,32 @@ struct FilterDev {
   const uint8_t* lut;  // 256 bytes (F_LUT)
 };
 
+// Bit-parallel "can a match start here" filter for flat patterns (a concatenation of byte-class
+// items with quantifiers).  Evaluated right-to-left over per-class position bitmaps, one 32-bit
+// word per lane, with warp-wide carry chains (the position-parallel formulation of an NFA walk).
+// It only has to be a superset of the true match starts: every survivor is still verified by the
+// anchored DFA.  kind: 0 = one byte of the class, 1 = class+, 2 = class*, 3 = class?
+struct FlatDev {
+  int nops;                // 0 = no second-level filter
+  int nclasses;            // <= 4
+  int first_is_filter;     // class 0 has exactly the first-level filter's ranges
+  uint8_t op_kind[24];
+  uint8_t op_class[24];    // ops are stored in PATTERN order; the kernel walks them backwards
+  uint8_t cls_nranges[4];
+  uint8_t cls_lo[4][4], cls_hi[4][4];
+  // SWAR constants per (class, range), precomputed on the host so the kernel reads them straight
+  // from the constant bank: mode 0 = XOR-alignable range (3 ops/word), 1 = generic (5 ops/word)
+  uint8_t cls_mode[4][4];
+  uint32_t cls_k1[4][4], cls_k2[4][4];
+};
+
 struct ScanArgs {
   const uint8_t* h;   // device haystack, 16-byte aligned
   int64_t n;
   int64_t base;       // added to every reported offset (shard base)
   DfaDev dfa;
   FilterDev filter;
+  FlatDev flat;
   int skip_safe;      // 1: after a match, a candidate in the middle of a run must still be tried
   uint8_t delim;      // record delimiter no match can contain
   int mode;

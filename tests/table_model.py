@@ -86,3 +86,50 @@ class TableModel:
                     while pos < n and self.in_set(h[pos]):
                         pos += 1
         return out
+
+
+_L.cgx_debug_flat.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+
+
+class FlatModel:
+    """Exact (whole-haystack, no tile edges) evaluation of the kernel's bit-parallel start filter
+    with Python big integers: bit p of the result <=> the flat program can match starting at p."""
+
+    def __init__(self, regex):
+        ops = np.zeros(48, dtype=np.uint8)
+        nr = np.zeros(4, dtype=np.uint8)
+        rg = np.zeros(32, dtype=np.uint8)
+        nc = C.c_int()
+        self.nops = _L.cgx_debug_flat(regex._h, ops.ctypes.data, C.byref(nc), nr.ctypes.data, rg.ctypes.data)
+        self.ops = [(int(ops[2 * i]), int(ops[2 * i + 1])) for i in range(self.nops)]
+        self.classes = [[(int(rg[(c * 4 + r) * 2]), int(rg[(c * 4 + r) * 2 + 1])) for r in range(nr[c])]
+                        for c in range(nc.value)]
+
+    def start_set(self, h):
+        n = len(h)
+        full = (1 << (n + 1)) - 1          # positions 0..n (n = end of input)
+        cm = []
+        for ranges in self.classes:
+            m = 0
+            for p, b in enumerate(h):
+                if any(lo <= b <= hi for lo, hi in ranges):
+                    m |= 1 << p
+            cm.append(m)
+        M = full
+        for kind, cls in reversed(self.ops):
+            Cm = cm[cls]
+            step = (M >> 1) & Cm           # p in class and p+1 in M
+            if kind == 0:
+                M = step
+            elif kind == 3:
+                M = M | step
+            else:
+                # propagate leftwards through runs of the class
+                plus = step
+                while True:
+                    nxt = plus | ((plus >> 1) & Cm)
+                    if nxt == plus:
+                        break
+                    plus = nxt
+                M = plus if kind == 1 else (M | plus)
+        return M

@@ -11,7 +11,7 @@ import pytest
 
 import coregex_b200 as cg
 from oracle_lib import Oracle, OracleError
-from table_model import TableModel
+from table_model import FlatModel, TableModel
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -85,7 +85,7 @@ def test_reference_strategy_agrees_with_oracle(pat):
 
 def test_ip_engine_choice():
     r = cg.Compile(r"\d+\.\d+\.\d+\.\d+")
-    assert (r.strategy, r.engine) == ("UseDigitPrefilter", "dfa-runstart")
+    assert (r.strategy, r.engine) == ("UseDigitPrefilter", "dfa-runstart+flat")
     m = TableModel(r)
     assert m.nstates <= 12 and m.filter_kind == 0 and m.skip_safe and m.ranges == [(0x30, 0x39)]
     assert m.find_all(b"x10.0.0.1 y 1.2.3 z 8.8.8.8") == [[1, 9], [20, 27]]
@@ -152,3 +152,28 @@ def test_synth_host_is_deterministic_and_line_aligned():
     lines = bytes(e).split(b"\n")[:-1]
     assert len(lines) == 100 and all(len(x) == 79 and x.count(b"@") == 1 for x in lines)
     assert all(re.search(rb"[a-z]+@[a-z]+\.[a-z]+", x) for x in lines)
+
+
+FLAT_PATTERNS = [r"\d+\.\d+\.\d+\.\d+", r"\d+\.\d+", r"\w+@\w+\.\w+", r"\d{3}-\d{4}", r"[a-zA-Z]+\d+", r"a+b",
+                 r"\d+x", r"[0-5]+\.\d+", r"(\w+)@(\w+)\.(\w+)", r"\d+\.\d+\.\d+\.35", r"ab?c*d",
+                 r"(?i)ab\d{2,4}z"]
+
+
+@pytest.mark.parametrize("pat", FLAT_PATTERNS)
+def test_flat_start_filter_is_exact_superset(pat):
+    """The bit-parallel filter must contain every position the anchored DFA matches from (it may
+    contain more).  On flat patterns it is in fact exact."""
+    r = cg.Compile(pat)
+    if "teddy" in r.engine:
+        pytest.skip("literal engine")
+    assert r.engine.endswith("+flat")
+    fm, tm = FlatModel(r), TableModel(r)
+    rng = np.random.default_rng(17)
+    alphabet = np.frombuffer(b"0123456789..  abABxz\n@_-d35", dtype=np.uint8)
+    for it in range(150):
+        n = int(rng.integers(0, 70))
+        h = bytes(alphabet[rng.integers(0, len(alphabet), n)])
+        S = fm.start_set(h)
+        for p in range(n):
+            ok = tm.walk(h, p) >= 0
+            assert ok == bool((S >> p) & 1), (pat, h, p)
