@@ -191,6 +191,14 @@ static void BuildFlat(const Regexp* re, FlatDev& out) {
         b.f.cls_k2[c][r] = (hi * 0x01010101u) | 0x80808080u;
       }
     }
+  // right-to-left program: skip trailing items that can be empty (they leave M = everything),
+  // the first ONE/PLUS item initialises M with its class
+  int k = b.f.nops - 1;
+  while (k >= 0 && b.f.op_kind[k] >= 2) k--;
+  if (k < 0) return;  // nullable pattern: not filtered
+  b.f.rev_init_class = b.f.op_class[k];
+  b.f.rev_nops = 0;
+  for (k--; k >= 0; k--) b.f.rev_ops[b.f.rev_nops++] = (uint8_t)(b.f.op_kind[k] | (b.f.op_class[k] << 2));
   out = b.f;
 }
 

@@ -32,7 +32,7 @@ namespace {
 
 constexpr int WARPS = 8;
 constexpr int THREADS = WARPS * 32;
-constexpr int CH = 32768;         // chunk bytes owned by one CTA iteration
+constexpr int CH = 31 * 1024;     // chunk bytes owned by one CTA iteration (CH+OVER = 32 tiles)
 constexpr int OVER = 1024;        // bytes after the chunk that are classified too
 constexpr int PRE = 16;           // bytes before the chunk kept in the window
 constexpr int WIN = PRE + CH + OVER;
@@ -43,7 +43,7 @@ constexpr int NWORDS = NTILES * 32;
 constexpr int SUB = CH / WARPS;   // slice whose line starts a warp owns
 constexpr int GROUP = 16;         // bitmap words compacted per step
 constexpr int QCAP = GROUP * 32 + 32;
-constexpr int STG = 192;          // staged matches per warp
+constexpr int STG = 96;           // staged matches per warp and buffer (two buffers: deferred output)
 constexpr int64_t INF = (int64_t)1 << 62;
 constexpr uint32_t FULL = 0xffffffffu;
 
@@ -56,7 +56,9 @@ struct Smem {
   unsigned chunk;
   uint32_t cand[NWORDS];
   uint16_t queue[WARPS][QCAP];
-  uint2 stage[WARPS][STG];
+  uint2 stage[2][WARPS][STG];
+  unsigned wcount2[2][WARPS];
+  uint32_t cmask[WARPS][4][32];  // per-lane class words of the tile a warp is evaluating
   alignas(128) uint8_t win[WIN + WINPAD];
   // followed by: uint32_t trans[nstates*256]; uint8_t eoi[nstates]; uint8_t lut[256]
 };
@@ -71,6 +73,7 @@ struct Ctx {
   int64_t gw;             // global position of win[0]
   int wend;               // number of valid bytes in the window
   int lane, warp;
+  int buf;                // staging buffer of this chunk
 };
 
 __device__ __forceinline__ uint8_t byte_at(const Ctx& c, int64_t p) {
@@ -188,25 +191,7 @@ __device__ void phase_a_plain(const Ctx& c) {
 }
 
 // Class membership of 32 bytes as a BIT-REVERSED word: bit (31-b) <=> byte b is in class `cls`.
-__device__ __forceinline__ uint32_t class_mask_rev(const FlatDev& f, int cls, const uint32_t (&w)[8]) {
-  uint32_t fl[8];
-  const int nr = f.cls_nranges[cls];
-#pragma unroll
-  for (int k = 0; k < 8; k++) fl[k] = 0;
-  for (int r = 0; r < nr; r++) {
-    const uint32_t k1 = f.cls_k1[cls][r], k2 = f.cls_k2[cls][r];
-    if (f.cls_mode[cls][r] == 0) {
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const uint32_t x = w[k];
-        const uint32_t z = ((x ^ k1) & 0x7F7F7F7Fu) + k2;  // bit7 set <=> (x^lo)&0x7f > width
-        fl[k] |= ~(z | x) & 0x80808080u;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; k++) fl[k] |= swar_in_range(w[k], k1, k2);
-    }
-  }
+__device__ __forceinline__ uint32_t pack_rev(const uint32_t (&fl)[8]) {
   uint32_t acc[4];
 #pragma unroll
   for (int a = 0; a < 4; a++) {
@@ -217,6 +202,38 @@ __device__ __forceinline__ uint32_t class_mask_rev(const FlatDev& f, int cls, co
   return (acc[0] << 17) | (acc[1] << 9) | (acc[2] << 1) | (acc[3] >> 7);
 }
 
+__device__ __forceinline__ uint32_t class_mask_rev(const FlatDev& f, int cls, const uint32_t (&w)[8]) {
+  uint32_t fl[8];
+  const int nr = f.cls_nranges[cls];
+  if (nr == 1 && f.cls_mode[cls][0] == 0) {  // one XOR-alignable range: 3 ops per word
+    const uint32_t k1 = f.cls_k1[cls][0], k2 = f.cls_k2[cls][0];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const uint32_t x = w[k];
+      const uint32_t z = ((x ^ k1) & 0x7F7F7F7Fu) + k2;  // bit7 set <=> (x^lo)&0x7f > width
+      fl[k] = ~(z | x) & 0x80808080u;
+    }
+    return pack_rev(fl);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) fl[k] = 0;
+  for (int r = 0; r < nr; r++) {
+    const uint32_t k1 = f.cls_k1[cls][r], k2 = f.cls_k2[cls][r];
+    if (f.cls_mode[cls][r] == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const uint32_t x = w[k];
+        const uint32_t z = ((x ^ k1) & 0x7F7F7F7Fu) + k2;
+        fl[k] |= ~(z | x) & 0x80808080u;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) fl[k] |= swar_in_range(w[k], k1, k2);
+    }
+  }
+  return pack_rev(fl);
+}
+
 // 1024-bit helpers over the warp: lane l holds word l; word 0 = the LAST 32 bytes of the tile.
 // "shl1" moves markers one position towards lower addresses (higher bits); the bit entering
 // word 0 (a position past the tile) is 1: unknown territory is assumed to allow a match.
@@ -225,53 +242,45 @@ __device__ __forceinline__ uint32_t shl1(uint32_t m, int lane) {
   if (lane == 0) dn = FULL;
   return __funnelshift_l(dn, m, 1);
 }
-// s + c (+1 into word 0) as one 1024-bit addition; carries resolved with two ballots
+// s + c as one 1024-bit addition; carries resolved with two ballots.  (No carry-in: the unknown
+// territory past the tile is already represented by shl1's 1-bit, which seeds the last byte.)
 __device__ __forceinline__ uint32_t add1024(uint32_t s, uint32_t cc, int lane) {
-  uint32_t sum = s + cc;
+  const uint32_t sum = s + cc;
   const uint32_t G = __ballot_sync(FULL, sum < s);
   const uint32_t P = __ballot_sync(FULL, sum == FULL);
   const uint32_t A = G | P;
-  const uint32_t carries = A ^ G ^ (A + G + 1u);  // bit l = carry into word l
+  const uint32_t carries = A ^ G ^ (A + G);  // bit l = carry into word l
   return sum + ((carries >> lane) & 1u);
 }
 
 __device__ void phase_a_flat(const Ctx& c) {
   const FlatDev& f = c.a.flat;
+  uint32_t* cmw = &c.sm.cmask[c.warp][0][c.lane];  // class k of this lane at cmw[k*32]
   for (int t = c.warp; t < NTILES; t += WARPS) {
     const int chunk = 31 - c.lane;                // lane l holds the (31-l)-th 32-byte piece
     const int rel = t * TILE + chunk * 32;        // relative to cbeg
     const uint8_t* p = c.sm.win + PRE + rel;
     uint32_t w[8];
     load32(p, w);
-    uint32_t cm0 = 0, cm1 = 0, cm2 = 0, cm3 = 0;
-    cm0 = class_mask_rev(f, 0, w);
-    if (f.nclasses > 1) cm1 = class_mask_rev(f, 1, w);
-    if (f.nclasses > 2) cm2 = class_mask_rev(f, 2, w);
-    if (f.nclasses > 3) cm3 = class_mask_rev(f, 3, w);
+    const uint32_t cm0 = class_mask_rev(f, 0, w);
+    cmw[0] = cm0;
+    for (int k = 1; k < f.nclasses; k++) cmw[k * 32] = class_mask_rev(f, k, w);
     // right-to-left evaluation: M = positions from which items k..end can match
-    uint32_t M = FULL;
-    bool all = true;
-    for (int k = f.nops - 1; k >= 0; k--) {
-      const int cls = f.op_class[k], kind = f.op_kind[k];
-      const uint32_t C = cls == 0 ? cm0 : cls == 1 ? cm1 : cls == 2 ? cm2 : cm3;
-      if (all) {  // M is still "everything": closed forms
-        if (kind <= 1) {
-          M = C;
-          all = false;
-        }
-        continue;
-      }
+    uint32_t M = cmw[f.rev_init_class * 32];
+    for (int k = 0; k < f.rev_nops; k++) {
+      const uint32_t op = f.rev_ops[k];
+      const uint32_t C = cmw[(op >> 2) * 32];
+      const uint32_t t1 = shl1(M, c.lane) & C;  // byte in class and the rest matches after it
+      const uint32_t kind = op & 3u;
       if (kind == 0) {
-        M = shl1(M, c.lane) & C;
+        M = t1;
       } else if (kind == 3) {
-        M |= shl1(M, c.lane) & C;
+        M |= t1;
       } else {
-        const uint32_t s = shl1(M, c.lane) & C;
-        const uint32_t plus = ~add1024(s, C, c.lane) & C;
+        const uint32_t plus = ~add1024(t1, C, c.lane) & C;  // extend leftwards through the run
         M = kind == 1 ? plus : (M | plus);
       }
     }
-    // first-level set restricted further (run starts keep the reference's skip semantics)
     uint32_t first = FULL;
     if (c.a.filter.kind == F_RUNSTART) {
       // run starts of the FILTER set (ASCII digits for the reference's DigitPrefilter), which is
@@ -332,7 +341,7 @@ struct Emitter {
         *reinterpret_cast<longlong2*>(c.a.out + 2 * gi) = make_longlong2(b + s, b + e);
       }
     } else {
-      if (idx < STG) c.sm.stage[c.warp][idx] = make_uint2((unsigned)s, (unsigned)e);
+      if (idx < STG) c.sm.stage[c.buf][c.warp][idx] = make_uint2((unsigned)s, (unsigned)e);
     }
   }
 };
@@ -435,15 +444,22 @@ __device__ void phase_b(const Ctx& c, Emitter<DIRECT>& em) {
       if (b0 < lo_rel) word &= ~0u << (lo_rel - b0);
       if (b0 + 32 > hi_rel) word &= (1u << (hi_rel - b0)) - 1u;
     }
-    if (!__any_sync(FULL, word != 0)) continue;
-    int total;
-    int off = qlen + warp_excl_scan(__popc(word), c.lane, total);
-    while (word) {
-      const int b = __ffs(word) - 1;
-      word &= word - 1;
-      q[off++] = (uint16_t)(widx * 32 + b + PRE);  // window index
+    const unsigned nz = __ballot_sync(FULL, word != 0);
+    if (!nz) continue;
+    if (!__any_sync(FULL, (word & (word - 1)) != 0)) {
+      // sparse case: at most one candidate per word -> offsets straight from the ballot
+      if (word) q[qlen + __popc(nz & ((1u << c.lane) - 1u))] = (uint16_t)(widx * 32 + __ffs(word) - 1 + PRE);
+      qlen += __popc(nz);
+    } else {
+      int total;
+      int off = qlen + warp_excl_scan(__popc(word), c.lane, total);
+      while (word) {
+        const int b = __ffs(word) - 1;
+        word &= word - 1;
+        q[off++] = (uint16_t)(widx * 32 + b + PRE);  // window index
+      }
+      qlen += total;
     }
-    qlen += total;
     __syncwarp();
     int head = 0;
     while (qlen - head >= 32) {
@@ -470,6 +486,52 @@ __device__ void phase_b(const Ctx& c, Emitter<DIRECT>& em) {
   }
 }
 
+// Decoupled look-back for `chunk` with local aggregate `agg` (warp 0 only): publishes the
+// inclusive prefix and returns the exclusive one.
+__device__ unsigned long long look_back(const ScanArgs& a, int64_t chunk, unsigned agg, int lane) {
+  unsigned long long excl = 0;
+  if (chunk == 0) {
+    if (lane == 0) st_release(&a.status[0], LB_PREFIX | agg);
+    return 0;
+  }
+  int64_t look = chunk - 1;
+  for (;;) {
+    const int64_t idx = look - lane;
+    unsigned long long v = LB_PREFIX;  // lanes before chunk 0 act as a zero prefix
+    if (idx >= 0) {
+      do {
+        v = ld_acquire(&a.status[idx]);
+      } while ((v >> 62) == 0);
+    }
+    const unsigned pm = __ballot_sync(FULL, (v >> 62) == 2);
+    const int first = pm ? __ffs(pm) - 1 : 32;  // nearest chunk that already has a prefix
+    unsigned long long val = lane <= first ? (v & LB_VALUE) : 0ull;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) val += __shfl_xor_sync(FULL, val, d);
+    excl += val;
+    if (pm) break;
+    look -= 32;
+  }
+  if (lane == 0) st_release(&a.status[chunk], LB_PREFIX | (excl + agg));
+  return excl;
+}
+
+__device__ __forceinline__ void write_staged(const ScanArgs& a, Smem& sm, int buf, int warp, int lane,
+                                             int64_t gw, unsigned long long cta_base) {
+  unsigned wexcl = 0;
+  for (int w = 0; w < warp; w++) wexcl += sm.wcount2[buf][w];
+  const unsigned long long gbase = cta_base + wexcl;
+  const unsigned cnt = sm.wcount2[buf][warp];
+  const int64_t b = gw + a.base;
+  for (unsigned i = lane; i < cnt; i += 32) {
+    const unsigned long long gi = gbase + i;
+    if ((int64_t)gi < a.cap) {
+      const uint2 m = sm.stage[buf][warp][i];
+      *reinterpret_cast<longlong2*>(a.out + 2 * gi) = make_longlong2(b + m.x, b + m.y);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -493,39 +555,62 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
   }
   __syncthreads();
 
+  // Output of chunk k is deferred to the start of iteration k+1 (its aggregate is published
+  // right away): by then the predecessors' prefixes are normally available, so the look-back
+  // does not stall the CTA while the next chunk's TMA load is already in flight.
   uint32_t parity = 0;
+  int buf = 0;
+  int64_t pend_chunk = -1, pend_gw = 0;  // deferred chunk (staged in buffer buf^1)
+  unsigned pend_agg = 0;
   for (;;) {
     if (tid == 0) sm.chunk = atomicAdd(a.ticket, 1u);
     __syncthreads();
-    const int64_t chunk = sm.chunk;
-    if (chunk >= a.nchunks) break;
-    if (a.mode == M_ISMATCH && *((volatile unsigned long long*)&a.total[1])) break;
-    const int64_t cbeg = chunk * CH;
-    const int64_t gw = cbeg - PRE;
-    const int64_t lo_g = gw < 0 ? 0 : gw;
-    const int64_t hi_g = gw + WIN < a.n ? gw + WIN : a.n;
-    const uint32_t bytes = (uint32_t)(hi_g - lo_g);
-    const uint32_t bulk = bytes & ~15u;
-    if (tid == 0) {
-      if (bulk) {
-        mbar_expect_tx(&sm.mbar, bulk);
-        tma_load_1d(sm.win + (lo_g - gw), a.h + lo_g, bulk, &sm.mbar);
-      } else {
-        mbar_arrive(&sm.mbar);
+    int64_t chunk = sm.chunk;
+    bool stop = chunk >= a.nchunks;
+    if (a.mode == M_ISMATCH && *((volatile unsigned long long*)&a.total[1])) stop = true;
+    int64_t cbeg = 0, gw = 0, hi_g = 0;
+    if (!stop) {
+      cbeg = chunk * CH;
+      gw = cbeg - PRE;
+      const int64_t lo_g = gw < 0 ? 0 : gw;
+      hi_g = gw + WIN < a.n ? gw + WIN : a.n;
+      const uint32_t bytes = (uint32_t)(hi_g - lo_g);
+      const uint32_t bulk = bytes & ~15u;
+      if (tid == 0) {
+        if (bulk) {
+          mbar_expect_tx(&sm.mbar, bulk);
+          tma_load_1d(sm.win + (lo_g - gw), a.h + lo_g, bulk, &sm.mbar);
+        } else {
+          mbar_arrive(&sm.mbar);
+        }
+      }
+      // bytes the bulk copy does not cover: before position 0, the <16 B tail, past the end
+      if (gw < 0 || bulk != (uint32_t)WIN) {
+        for (int i = tid; i < WIN; i += THREADS) {
+          const int64_t g = gw + i;
+          if (g < 0 || g >= lo_g + bulk) sm.win[i] = g >= 0 && g < a.n ? a.h[g] : a.delim;
+        }
       }
     }
-    // bytes the bulk copy does not cover: before position 0, the <16 B tail, past the end
-    if (gw < 0 || bulk != (uint32_t)WIN) {
-      for (int i = tid; i < WIN; i += THREADS) {
-        const int64_t g = gw + i;
-        if (g < 0 || g >= lo_g + bulk) sm.win[i] = g >= 0 && g < a.n ? a.h[g] : a.delim;
+    // ---- deferred output of the previous chunk (overlaps the load above) ----
+    if (pend_chunk >= 0) {
+      if (warp == 0) {
+        const unsigned long long excl = look_back(a, pend_chunk, pend_agg, lane);
+        if (lane == 0) {
+          sm.cta_base = excl;
+          if (pend_chunk == a.nchunks - 1) a.total[0] = excl + pend_agg;
+        }
       }
+      __syncthreads();
+      write_staged(a, sm, buf ^ 1, warp, lane, pend_gw, sm.cta_base);
+      pend_chunk = -1;
     }
+    if (stop) break;
     mbar_wait(&sm.mbar, parity);
     parity ^= 1;
     __syncthreads();
 
-    Ctx c{a, sm, s_trans, s_eoi, s_lut, cbeg, gw, (int)(hi_g - gw), lane, warp};
+    Ctx c{a, sm, s_trans, s_eoi, s_lut, cbeg, gw, (int)(hi_g - gw), lane, warp, buf};
     if (a.flat.nops) phase_a_flat(c); else phase_a_plain(c);
     {
       const int64_t s = find_line_start(c, cbeg + (int64_t)warp * SUB);
@@ -541,69 +626,40 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
     Emitter<false> em(c, 0);
     phase_b<false>(c, em);
     if (lane == 0) {
-      sm.wcount[warp] = em.nkept;
+      sm.wcount2[buf][warp] = em.nkept;
       if (em.overflow) atomicOr(&sm.woverflow, 1u);
     }
     __syncthreads();
 
+    unsigned agg = 0;
+    for (int w = 0; w < WARPS; w++) agg += sm.wcount2[buf][w];
     if (a.mode == M_FINDALL) {
-      if (warp == 0) {
-        unsigned agg = 0;
-        for (int w = 0; w < WARPS; w++) agg += sm.wcount[w];
-        unsigned long long excl = 0;
-        if (chunk == 0) {
-          if (lane == 0) st_release(&a.status[0], LB_PREFIX | agg);
-        } else {
-          if (lane == 0) st_release(&a.status[chunk], LB_AGG | agg);
-          int64_t look = chunk - 1;
-          for (;;) {
-            const int64_t idx = look - lane;
-            unsigned long long v = LB_PREFIX;  // lanes before chunk 0 act as a zero prefix
-            if (idx >= 0) {
-              do {
-                v = ld_acquire(&a.status[idx]);
-              } while ((v >> 62) == 0);
-            }
-            const unsigned pm = __ballot_sync(FULL, (v >> 62) == 2);
-            const int first = pm ? __ffs(pm) - 1 : 32;  // nearest chunk that already has a prefix
-            unsigned long long val = lane <= first ? (v & LB_VALUE) : 0ull;
-#pragma unroll
-            for (int d = 16; d; d >>= 1) val += __shfl_xor_sync(FULL, val, d);
-            excl += val;
-            if (pm) break;
-            look -= 32;
-          }
-          if (lane == 0) st_release(&a.status[chunk], LB_PREFIX | (excl + agg));
-        }
-        if (lane == 0) {
-          sm.cta_base = excl;
-          if (chunk == a.nchunks - 1) a.total[0] = excl + agg;
-        }
-      }
-      __syncthreads();
-      unsigned wexcl = 0;
-      for (int w = 0; w < warp; w++) wexcl += sm.wcount[w];
-      const unsigned long long gbase = sm.cta_base + wexcl;
       if (!sm.woverflow) {
-        const unsigned cnt = sm.wcount[warp];
-        const int64_t b = gw + a.base;
-        for (unsigned i = lane; i < cnt; i += 32) {
-          const unsigned long long gi = gbase + i;
-          if ((int64_t)gi < a.cap) {
-            const uint2 m = sm.stage[warp][i];
-            *reinterpret_cast<longlong2*>(a.out + 2 * gi) = make_longlong2(b + m.x, b + m.y);
+        // publish the aggregate now, write the matches at the start of the next iteration
+        if (tid == 0) st_release(&a.status[chunk], LB_AGG | agg);
+        pend_chunk = chunk;
+        pend_gw = gw;
+        pend_agg = agg;
+        buf ^= 1;
+      } else {
+        // more matches than the staging buffers hold: resolve the offset now and replay phase B
+        // writing straight to global memory (the window is still resident)
+        if (warp == 0) {
+          if (lane == 0 && chunk != 0) st_release(&a.status[chunk], LB_AGG | agg);
+          const unsigned long long excl = look_back(a, chunk, agg, lane);
+          if (lane == 0) {
+            sm.cta_base = excl;
+            if (chunk == a.nchunks - 1) a.total[0] = excl + agg;
           }
         }
-      } else {
-        Emitter<true> em2(c, gbase);
+        __syncthreads();
+        unsigned wexcl = 0;
+        for (int w = 0; w < warp; w++) wexcl += sm.wcount2[buf][w];
+        Emitter<true> em2(c, sm.cta_base + wexcl);
         phase_b<true>(c, em2);
       }
     } else {
-      if (tid == 0) {
-        unsigned agg = 0;
-        for (int w = 0; w < WARPS; w++) agg += sm.wcount[w];
-        if (agg) atomicAdd(a.total, (unsigned long long)agg);
-      }
+      if (tid == 0 && agg) atomicAdd(a.total, (unsigned long long)agg);
     }
     __syncthreads();  // window, bitmap and staging are reused by the next chunk
   }

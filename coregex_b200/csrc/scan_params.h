@@ -38,7 +38,13 @@ struct FlatDev {
   int nclasses;            // <= 4
   int first_is_filter;     // class 0 has exactly the first-level filter's ranges
   uint8_t op_kind[24];
-  uint8_t op_class[24];    // ops are stored in PATTERN order; the kernel walks them backwards
+  uint8_t op_class[24];    // ops in PATTERN order (host/debug view)
+  // what the kernel executes: evaluation runs right to left; trailing nullable items are dropped
+  // and the first concrete item becomes the initial marker set (M = class rev_init_class);
+  // rev_ops[i] = kind | class<<2 for the remaining items, already in right-to-left order
+  int rev_nops;
+  int rev_init_class;
+  uint8_t rev_ops[24];
   uint8_t cls_nranges[4];
   uint8_t cls_lo[4][4], cls_hi[4][4];
   // SWAR constants per (class, range), precomputed on the host so the kernel reads them straight
