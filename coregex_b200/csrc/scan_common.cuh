@@ -83,13 +83,23 @@ constexpr unsigned long long LB_AGG = 1ull << 62;
 constexpr unsigned long long LB_PREFIX = 2ull << 62;
 constexpr unsigned long long LB_VALUE = (1ull << 62) - 1;
 
-__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
+// The status word carries flag and value together and guards no other data, so relaxed
+// gpu-scope accesses are enough (an acquire load would add an L1 invalidate to every poll).
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// named barriers: producers arrive, consumers sync (count = total participating threads)
+__device__ __forceinline__ void bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 }  // namespace cgx

@@ -30,8 +30,11 @@ namespace cgx {
 
 namespace {
 
-constexpr int WARPS = 8;
-constexpr int THREADS = WARPS * 32;
+constexpr int WARPS = 8;                 // compute warps
+constexpr int CTHREADS = WARPS * 32;
+constexpr int THREADS = CTHREADS + 32;   // + one writer warp (look-back and ordered output)
+// named barriers (0 is __syncthreads)
+constexpr int BAR_COMPUTE = 1, BAR_FULL = 2 /*+buf*/, BAR_EMPTY = 4 /*+buf*/, BAR_OVF = 6;
 constexpr int CH = 31 * 1024;     // chunk bytes owned by one CTA iteration (CH+OVER = 32 tiles)
 constexpr int OVER = 1024;        // bytes after the chunk that are classified too
 constexpr int PRE = 16;           // bytes before the chunk kept in the window
@@ -58,6 +61,8 @@ struct Smem {
   uint16_t queue[WARPS][QCAP];
   uint2 stage[2][WARPS][STG];
   unsigned wcount2[2][WARPS];
+  int64_t meta_chunk[2], meta_gw[2];   // written by the compute warps, read by the writer warp
+  unsigned meta_agg[2], meta_ovf[2];
   uint32_t cmask[WARPS][4][32];  // per-lane class words of the tile a warp is evaluating
   alignas(128) uint8_t win[WIN + WINPAD];
   // followed by: uint32_t trans[nstates*256]; uint8_t eoi[nstates]; uint8_t lut[256]
@@ -202,10 +207,14 @@ __device__ __forceinline__ uint32_t pack_rev(const uint32_t (&fl)[8]) {
   return (acc[0] << 17) | (acc[1] << 9) | (acc[2] << 1) | (acc[3] >> 7);
 }
 
+__device__ __noinline__ uint32_t class_mask_rev_generic(const FlatDev& f, int cls, uint32_t w0, uint32_t w1,
+                                                        uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5,
+                                                        uint32_t w6, uint32_t w7);
+
 __device__ __forceinline__ uint32_t class_mask_rev(const FlatDev& f, int cls, const uint32_t (&w)[8]) {
-  uint32_t fl[8];
   const int nr = f.cls_nranges[cls];
   if (nr == 1 && f.cls_mode[cls][0] == 0) {  // one XOR-alignable range: 3 ops per word
+    uint32_t fl[8];
     const uint32_t k1 = f.cls_k1[cls][0], k2 = f.cls_k2[cls][0];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -215,6 +224,15 @@ __device__ __forceinline__ uint32_t class_mask_rev(const FlatDev& f, int cls, co
     }
     return pack_rev(fl);
   }
+  return class_mask_rev_generic(f, cls, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+}
+
+__device__ __noinline__ uint32_t class_mask_rev_generic(const FlatDev& f, int cls, uint32_t w0, uint32_t w1,
+                                                        uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5,
+                                                        uint32_t w6, uint32_t w7) {
+  const uint32_t w[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
+  uint32_t fl[8];
+  const int nr = f.cls_nranges[cls];
 #pragma unroll
   for (int k = 0; k < 8; k++) fl[k] = 0;
   for (int r = 0; r < nr; r++) {
@@ -491,7 +509,7 @@ __device__ void phase_b(const Ctx& c, Emitter<DIRECT>& em) {
 __device__ unsigned long long look_back(const ScanArgs& a, int64_t chunk, unsigned agg, int lane) {
   unsigned long long excl = 0;
   if (chunk == 0) {
-    if (lane == 0) st_release(&a.status[0], LB_PREFIX | agg);
+    if (lane == 0) st_status(&a.status[0], LB_PREFIX | agg);
     return 0;
   }
   int64_t look = chunk - 1;
@@ -500,7 +518,7 @@ __device__ unsigned long long look_back(const ScanArgs& a, int64_t chunk, unsign
     unsigned long long v = LB_PREFIX;  // lanes before chunk 0 act as a zero prefix
     if (idx >= 0) {
       do {
-        v = ld_acquire(&a.status[idx]);
+        v = ld_status(&a.status[idx]);
       } while ((v >> 62) == 0);
     }
     const unsigned pm = __ballot_sync(FULL, (v >> 62) == 2);
@@ -512,26 +530,30 @@ __device__ unsigned long long look_back(const ScanArgs& a, int64_t chunk, unsign
     if (pm) break;
     look -= 32;
   }
-  if (lane == 0) st_release(&a.status[chunk], LB_PREFIX | (excl + agg));
+  if (lane == 0) st_status(&a.status[chunk], LB_PREFIX | (excl + agg));
   return excl;
 }
 
-__device__ __forceinline__ void write_staged(const ScanArgs& a, Smem& sm, int buf, int warp, int lane,
-                                             int64_t gw, unsigned long long cta_base) {
-  unsigned wexcl = 0;
-  for (int w = 0; w < warp; w++) wexcl += sm.wcount2[buf][w];
-  const unsigned long long gbase = cta_base + wexcl;
-  const unsigned cnt = sm.wcount2[buf][warp];
+// all staged matches of one chunk, written by the writer warp in match order
+__device__ __forceinline__ void write_staged(const ScanArgs& a, Smem& sm, int buf, int lane, int64_t gw,
+                                             unsigned long long gbase) {
   const int64_t b = gw + a.base;
-  for (unsigned i = lane; i < cnt; i += 32) {
-    const unsigned long long gi = gbase + i;
-    if ((int64_t)gi < a.cap) {
-      const uint2 m = sm.stage[buf][warp][i];
-      *reinterpret_cast<longlong2*>(a.out + 2 * gi) = make_longlong2(b + m.x, b + m.y);
+  for (int w = 0; w < WARPS; w++) {
+    const unsigned cnt = sm.wcount2[buf][w];
+    for (unsigned i = lane; i < cnt; i += 32) {
+      const unsigned long long gi = gbase + i;
+      if ((int64_t)gi < a.cap) {
+        const uint2 m = sm.stage[buf][w][i];
+        *reinterpret_cast<longlong2*>(a.out + 2 * gi) = make_longlong2(b + m.x, b + m.y);
+      }
     }
+    gbase += cnt;
   }
 }
 
+// Roles: warps 0..7 scan (ticket -> TMA load -> phase A -> phase B into a staging buffer),
+// warp 8 turns staged chunks into ordered global output (decoupled look-back + int64 stores).
+// Two staging buffers decouple them: a scanning warp only waits if the writer is two chunks behind.
 __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -555,60 +577,62 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
   }
   __syncthreads();
 
-  // Output of chunk k is deferred to the start of iteration k+1 (its aggregate is published
-  // right away): by then the predecessors' prefixes are normally available, so the look-back
-  // does not stall the CTA while the next chunk's TMA load is already in flight.
+  if (warp == WARPS) {
+    // ---------------- writer warp ----------------
+    if (a.mode != M_FINDALL) return;
+    for (int b = 0;; b ^= 1) {
+      bar_sync(BAR_FULL + b, THREADS);
+      const int64_t chunk = sm.meta_chunk[b];
+      if (chunk < 0) break;
+      const unsigned agg = sm.meta_agg[b];
+      const unsigned long long excl = look_back(a, chunk, agg, lane);
+      if (lane == 0 && chunk == a.nchunks - 1) a.total[0] = excl + agg;
+      if (sm.meta_ovf[b]) {
+        if (lane == 0) sm.cta_base = excl;
+        __syncwarp();
+        bar_arrive(BAR_OVF, THREADS);  // the scanning warps replay phase B writing directly
+      } else {
+        write_staged(a, sm, b, lane, sm.meta_gw[b], excl);
+      }
+      bar_arrive(BAR_EMPTY + b, THREADS);
+    }
+    return;
+  }
+
+  // ---------------- scanning warps ----------------
   uint32_t parity = 0;
   int buf = 0;
-  int64_t pend_chunk = -1, pend_gw = 0;  // deferred chunk (staged in buffer buf^1)
-  unsigned pend_agg = 0;
+  unsigned used = 0;  // FINDALL chunks staged so far
   for (;;) {
     if (tid == 0) sm.chunk = atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    int64_t chunk = sm.chunk;
-    bool stop = chunk >= a.nchunks;
-    if (a.mode == M_ISMATCH && *((volatile unsigned long long*)&a.total[1])) stop = true;
-    int64_t cbeg = 0, gw = 0, hi_g = 0;
-    if (!stop) {
-      cbeg = chunk * CH;
-      gw = cbeg - PRE;
-      const int64_t lo_g = gw < 0 ? 0 : gw;
-      hi_g = gw + WIN < a.n ? gw + WIN : a.n;
-      const uint32_t bytes = (uint32_t)(hi_g - lo_g);
-      const uint32_t bulk = bytes & ~15u;
-      if (tid == 0) {
-        if (bulk) {
-          mbar_expect_tx(&sm.mbar, bulk);
-          tma_load_1d(sm.win + (lo_g - gw), a.h + lo_g, bulk, &sm.mbar);
-        } else {
-          mbar_arrive(&sm.mbar);
-        }
-      }
-      // bytes the bulk copy does not cover: before position 0, the <16 B tail, past the end
-      if (gw < 0 || bulk != (uint32_t)WIN) {
-        for (int i = tid; i < WIN; i += THREADS) {
-          const int64_t g = gw + i;
-          if (g < 0 || g >= lo_g + bulk) sm.win[i] = g >= 0 && g < a.n ? a.h[g] : a.delim;
-        }
+    bar_sync(BAR_COMPUTE, CTHREADS);
+    const int64_t chunk = sm.chunk;
+    if (chunk >= a.nchunks) break;
+    if (a.mode == M_ISMATCH && *((volatile unsigned long long*)&a.total[1])) break;
+    const int64_t cbeg = chunk * CH;
+    const int64_t gw = cbeg - PRE;
+    const int64_t lo_g = gw < 0 ? 0 : gw;
+    const int64_t hi_g = gw + WIN < a.n ? gw + WIN : a.n;
+    const uint32_t bytes = (uint32_t)(hi_g - lo_g);
+    const uint32_t bulk = bytes & ~15u;
+    if (tid == 0) {
+      if (bulk) {
+        mbar_expect_tx(&sm.mbar, bulk);
+        tma_load_1d(sm.win + (lo_g - gw), a.h + lo_g, bulk, &sm.mbar);
+      } else {
+        mbar_arrive(&sm.mbar);
       }
     }
-    // ---- deferred output of the previous chunk (overlaps the load above) ----
-    if (pend_chunk >= 0) {
-      if (warp == 0) {
-        const unsigned long long excl = look_back(a, pend_chunk, pend_agg, lane);
-        if (lane == 0) {
-          sm.cta_base = excl;
-          if (pend_chunk == a.nchunks - 1) a.total[0] = excl + pend_agg;
-        }
+    // bytes the bulk copy does not cover: before position 0, the <16 B tail, past the end
+    if (gw < 0 || bulk != (uint32_t)WIN) {
+      for (int i = tid; i < WIN; i += CTHREADS) {
+        const int64_t g = gw + i;
+        if (g < 0 || g >= lo_g + bulk) sm.win[i] = g >= 0 && g < a.n ? a.h[g] : a.delim;
       }
-      __syncthreads();
-      write_staged(a, sm, buf ^ 1, warp, lane, pend_gw, sm.cta_base);
-      pend_chunk = -1;
     }
-    if (stop) break;
     mbar_wait(&sm.mbar, parity);
     parity ^= 1;
-    __syncthreads();
+    bar_sync(BAR_COMPUTE, CTHREADS);
 
     Ctx c{a, sm, s_trans, s_eoi, s_lut, cbeg, gw, (int)(hi_g - gw), lane, warp, buf};
     if (a.flat.nops) phase_a_flat(c); else phase_a_plain(c);
@@ -621,7 +645,8 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
       }
       if (tid == 0) sm.woverflow = 0;
     }
-    __syncthreads();
+    if (a.mode == M_FINDALL && used >= 2) bar_sync(BAR_EMPTY + buf, THREADS);  // buffer released?
+    bar_sync(BAR_COMPUTE, CTHREADS);
 
     Emitter<false> em(c, 0);
     phase_b<false>(c, em);
@@ -629,39 +654,44 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
       sm.wcount2[buf][warp] = em.nkept;
       if (em.overflow) atomicOr(&sm.woverflow, 1u);
     }
-    __syncthreads();
+    bar_sync(BAR_COMPUTE, CTHREADS);
 
     unsigned agg = 0;
     for (int w = 0; w < WARPS; w++) agg += sm.wcount2[buf][w];
     if (a.mode == M_FINDALL) {
-      if (!sm.woverflow) {
-        // publish the aggregate now, write the matches at the start of the next iteration
-        if (tid == 0) st_release(&a.status[chunk], LB_AGG | agg);
-        pend_chunk = chunk;
-        pend_gw = gw;
-        pend_agg = agg;
-        buf ^= 1;
-      } else {
-        // more matches than the staging buffers hold: resolve the offset now and replay phase B
+      const bool ovf = sm.woverflow != 0;
+      if (tid == 0) {
+        // the aggregate is visible to other CTAs immediately; the prefix follows from the writer
+        if (chunk != 0) st_status(&a.status[chunk], LB_AGG | agg);
+        sm.meta_chunk[buf] = chunk;
+        sm.meta_gw[buf] = gw;
+        sm.meta_agg[buf] = agg;
+        sm.meta_ovf[buf] = ovf ? 1u : 0u;
+      }
+      __syncwarp();
+      bar_arrive(BAR_FULL + buf, THREADS);
+      if (ovf) {
+        // more matches than the staging buffer holds: wait for the offset, then replay phase B
         // writing straight to global memory (the window is still resident)
-        if (warp == 0) {
-          if (lane == 0 && chunk != 0) st_release(&a.status[chunk], LB_AGG | agg);
-          const unsigned long long excl = look_back(a, chunk, agg, lane);
-          if (lane == 0) {
-            sm.cta_base = excl;
-            if (chunk == a.nchunks - 1) a.total[0] = excl + agg;
-          }
-        }
-        __syncthreads();
+        bar_sync(BAR_OVF, THREADS);
         unsigned wexcl = 0;
         for (int w = 0; w < warp; w++) wexcl += sm.wcount2[buf][w];
         Emitter<true> em2(c, sm.cta_base + wexcl);
         phase_b<true>(c, em2);
       }
+      used++;
+      buf ^= 1;
     } else {
       if (tid == 0 && agg) atomicAdd(a.total, (unsigned long long)agg);
     }
-    __syncthreads();  // window, bitmap and staging are reused by the next chunk
+    bar_sync(BAR_COMPUTE, CTHREADS);  // window, bitmap and class scratch are reused by the next chunk
+  }
+  if (a.mode == M_FINDALL) {
+    // tell the writer to finish (after it released the buffer we are about to mark)
+    if (used >= 2) bar_sync(BAR_EMPTY + buf, THREADS);
+    if (tid == 0) sm.meta_chunk[buf] = -1;
+    __syncwarp();
+    bar_arrive(BAR_FULL + buf, THREADS);
   }
 }
 
