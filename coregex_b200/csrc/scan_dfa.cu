@@ -54,7 +54,8 @@ struct Smem {
   uint64_t mbar;
   int64_t ls[WARPS + 1];
   unsigned wcount[WARPS];
-  unsigned woverflow;
+  unsigned woverflow2[2];
+  unsigned chunk2[2];
   unsigned long long cta_base;
   unsigned chunk;
   uint32_t cand[NWORDS];
@@ -64,6 +65,7 @@ struct Smem {
   int64_t meta_chunk[2], meta_gw[2];   // written by the compute warps, read by the writer warp
   unsigned meta_agg[2], meta_ovf[2];
   uint32_t cmask[WARPS][4][32];  // per-lane class words of the tile a warp is evaluating
+  FlatDev flat;                  // copy of the flat program (indexed constant-bank loads are slow)
   alignas(128) uint8_t win[WIN + WINPAD];
   // followed by: uint32_t trans[nstates*256]; uint8_t eoi[nstates]; uint8_t lut[256]
 };
@@ -272,7 +274,7 @@ __device__ __forceinline__ uint32_t add1024(uint32_t s, uint32_t cc, int lane) {
 }
 
 __device__ void phase_a_flat(const Ctx& c) {
-  const FlatDev& f = c.a.flat;
+  const FlatDev& f = c.sm.flat;
   uint32_t* cmw = &c.sm.cmask[c.warp][0][c.lane];  // class k of this lane at cmw[k*32]
   for (int t = c.warp; t < NTILES; t += WARPS) {
     const int chunk = 31 - c.lane;                // lane l holds the (31-l)-th 32-byte piece
@@ -453,44 +455,51 @@ __device__ void phase_b(const Ctx& c, Emitter<DIRECT>& em) {
   int qlen = 0;
   const int lo_rel = (int)(lo - c.cbeg);
   const int hi_rel = (int)(hi_b - c.cbeg);
-  for (int wbase = lo_rel >> 5; wbase * 32 < hi_rel; wbase += GROUP) {
+  // One bitmap word per lane and step (1 KB of input).  A step that holds more candidates than
+  // the queue can take (dense data) is split into two half-warp passes.
+  for (int wbase = lo_rel >> 5; wbase * 32 < hi_rel; wbase += 32) {
     const int widx = wbase + c.lane;
-    uint32_t word = 0;
-    if (c.lane < GROUP && widx < NWORDS && widx * 32 < hi_rel) {
-      word = c.sm.cand[widx];
+    uint32_t word_all = 0;
+    if (widx < NWORDS && widx * 32 < hi_rel) {
+      word_all = c.sm.cand[widx];
       const int b0 = widx * 32;
-      if (b0 < lo_rel) word &= ~0u << (lo_rel - b0);
-      if (b0 + 32 > hi_rel) word &= (1u << (hi_rel - b0)) - 1u;
+      if (b0 < lo_rel) word_all &= ~0u << (lo_rel - b0);
+      if (b0 + 32 > hi_rel) word_all &= (1u << (hi_rel - b0)) - 1u;
     }
-    const unsigned nz = __ballot_sync(FULL, word != 0);
+    const unsigned nz = __ballot_sync(FULL, word_all != 0);
     if (!nz) continue;
-    if (!__any_sync(FULL, (word & (word - 1)) != 0)) {
-      // sparse case: at most one candidate per word -> offsets straight from the ballot
-      if (word) q[qlen + __popc(nz & ((1u << c.lane) - 1u))] = (uint16_t)(widx * 32 + __ffs(word) - 1 + PRE);
-      qlen += __popc(nz);
-    } else {
-      int total;
-      int off = qlen + warp_excl_scan(__popc(word), c.lane, total);
-      while (word) {
-        const int b = __ffs(word) - 1;
-        word &= word - 1;
-        q[off++] = (uint16_t)(widx * 32 + b + PRE);  // window index
+    const bool sparse = !__any_sync(FULL, (word_all & (word_all - 1)) != 0);
+    for (int pass = 0; pass < (sparse ? 1 : 2); pass++) {
+      uint32_t word = word_all;
+      if (sparse) {
+        // at most one candidate per word -> queue offsets straight from the ballot
+        if (word) q[qlen + __popc(nz & ((1u << c.lane) - 1u))] = (uint16_t)(widx * 32 + __ffs(word) - 1 + PRE);
+        qlen += __popc(nz);
+      } else {
+        if ((c.lane >> 4) != pass) word = 0;
+        int total;
+        int off = qlen + warp_excl_scan(__popc(word), c.lane, total);
+        while (word) {
+          const int b = __ffs(word) - 1;
+          word &= word - 1;
+          q[off++] = (uint16_t)(widx * 32 + b + PRE);  // window index
+        }
+        qlen += total;
       }
-      qlen += total;
-    }
-    __syncwarp();
-    int head = 0;
-    while (qlen - head >= 32) {
-      kept_end = process_batch<DIRECT>(c, em, q[head + c.lane], true, kept_end);
-      head += 32;
-    }
-    if (head) {
-      const int rem = qlen - head;
-      const uint16_t tmp = c.lane < rem ? q[head + c.lane] : 0;
       __syncwarp();
-      if (c.lane < rem) q[c.lane] = tmp;
-      qlen = rem;
-      __syncwarp();
+      int head = 0;
+      while (qlen - head >= 32) {
+        kept_end = process_batch<DIRECT>(c, em, q[head + c.lane], true, kept_end);
+        head += 32;
+      }
+      if (head) {
+        const int rem = qlen - head;
+        const uint16_t tmp = c.lane < rem ? q[head + c.lane] : 0;
+        __syncwarp();
+        if (c.lane < rem) q[c.lane] = tmp;
+        qlen = rem;
+        __syncwarp();
+      }
     }
   }
   if (qlen) {
@@ -571,6 +580,8 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
   if (a.filter.kind == F_LUT)
     for (int i = tid; i < 256; i += THREADS) s_lut[i] = a.filter.lut[i];
   if (tid < WINPAD) sm.win[WIN + tid] = a.delim;
+  for (int i = tid; i < (int)(sizeof(FlatDev) / 4); i += THREADS)
+    reinterpret_cast<uint32_t*>(&sm.flat)[i] = reinterpret_cast<const uint32_t*>(&a.flat)[i];
   if (tid == 0) {
     mbar_init(&sm.mbar, 1);
     fence_mbar_init();
@@ -603,12 +614,18 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
   uint32_t parity = 0;
   int buf = 0;
   unsigned used = 0;  // FINDALL chunks staged so far
-  for (;;) {
-    if (tid == 0) sm.chunk = atomicAdd(a.ticket, 1u);
-    bar_sync(BAR_COMPUTE, CTHREADS);
-    const int64_t chunk = sm.chunk;
-    if (chunk >= a.nchunks) break;
-    if (a.mode == M_ISMATCH && *((volatile unsigned long long*)&a.total[1])) break;
+  unsigned it = 0;
+  // one thread decides for the whole CTA, so the loop exit is uniform
+  auto next_ticket = [&]() -> unsigned {
+    if (a.mode == M_ISMATCH && *((volatile unsigned long long*)&a.total[1])) return 0xFFFFFFFFu;
+    return atomicAdd(a.ticket, 1u);
+  };
+  if (tid == 0) sm.chunk2[0] = next_ticket();
+  bar_sync(BAR_COMPUTE, CTHREADS);
+  for (;; it++) {
+    // the ticket of this iteration was fetched before the previous iteration's last barrier
+    const int64_t chunk = sm.chunk2[it & 1];
+    if (chunk >= a.nchunks) break;  // also how an is-match early exit arrives (see next_ticket)
     const int64_t cbeg = chunk * CH;
     const int64_t gw = cbeg - PRE;
     const int64_t lo_g = gw < 0 ? 0 : gw;
@@ -630,9 +647,9 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
         if (g < 0 || g >= lo_g + bulk) sm.win[i] = g >= 0 && g < a.n ? a.h[g] : a.delim;
       }
     }
-    mbar_wait(&sm.mbar, parity);
+    mbar_wait(&sm.mbar, parity);  // every scanning thread observes the TMA completion itself
     parity ^= 1;
-    bar_sync(BAR_COMPUTE, CTHREADS);
+    if (gw < 0 || bulk != (uint32_t)WIN) bar_sync(BAR_COMPUTE, CTHREADS);  // generic fill stores
 
     Ctx c{a, sm, s_trans, s_eoi, s_lut, cbeg, gw, (int)(hi_g - gw), lane, warp, buf};
     if (a.flat.nops) phase_a_flat(c); else phase_a_plain(c);
@@ -643,7 +660,10 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
         const int64_t e = find_line_start(c, cbeg + CH);
         if (lane == 0) sm.ls[WARPS] = e;
       }
-      if (tid == 0) sm.woverflow = 0;
+      if (tid == 0) {
+        sm.woverflow2[it & 1] = 0;
+        sm.chunk2[(it + 1) & 1] = next_ticket();
+      }
     }
     if (a.mode == M_FINDALL && used >= 2) bar_sync(BAR_EMPTY + buf, THREADS);  // buffer released?
     bar_sync(BAR_COMPUTE, CTHREADS);
@@ -652,14 +672,14 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
     phase_b<false>(c, em);
     if (lane == 0) {
       sm.wcount2[buf][warp] = em.nkept;
-      if (em.overflow) atomicOr(&sm.woverflow, 1u);
+      if (em.overflow) atomicOr(&sm.woverflow2[it & 1], 1u);
     }
     bar_sync(BAR_COMPUTE, CTHREADS);
 
     unsigned agg = 0;
     for (int w = 0; w < WARPS; w++) agg += sm.wcount2[buf][w];
     if (a.mode == M_FINDALL) {
-      const bool ovf = sm.woverflow != 0;
+      const bool ovf = sm.woverflow2[it & 1] != 0;
       if (tid == 0) {
         // the aggregate is visible to other CTAs immediately; the prefix follows from the writer
         if (chunk != 0) st_status(&a.status[chunk], LB_AGG | agg);
@@ -678,13 +698,15 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
         for (int w = 0; w < warp; w++) wexcl += sm.wcount2[buf][w];
         Emitter<true> em2(c, sm.cta_base + wexcl);
         phase_b<true>(c, em2);
+        bar_sync(BAR_COMPUTE, CTHREADS);  // the replay still reads the window
       }
       used++;
       buf ^= 1;
     } else {
       if (tid == 0 && agg) atomicAdd(a.total, (unsigned long long)agg);
     }
-    bar_sync(BAR_COMPUTE, CTHREADS);  // window, bitmap and class scratch are reused by the next chunk
+    // no barrier here: everything the next iteration overwrites (window, bitmap, class scratch)
+    // was last read before the barrier that followed phase B
   }
   if (a.mode == M_FINDALL) {
     // tell the writer to finish (after it released the buffer we are about to mark)
