@@ -7,6 +7,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/coregex_b200.h"
 #include "host/engine.h"
@@ -14,7 +15,7 @@
 #include "synth.h"
 
 namespace cgx {
-size_t scan_dfa_smem_bytes(int nstates);
+size_t scan_dfa_smem_bytes(int nstates, int teddy_blob_bytes);
 int64_t scan_dfa_chunks(int64_t n);
 cudaError_t launch_scan_dfa(const ScanArgs& a, int sm_count, cudaStream_t stream);
 cudaError_t launch_scan_teddy(const struct TeddyArgs& a, int sm_count, cudaStream_t stream);
@@ -64,6 +65,7 @@ struct cgx_regex {
   int sm_count = 0;
   // device copies of the tables
   DevBuf d_trans, d_eoi, d_lut, d_teddy;
+  TeddyDev teddy_dev;
   // per-call scratch (serialised by mu)
   DevBuf d_ticket_total, d_status, d_hay, d_out;
   std::atomic<uint64_t> launches{0};
@@ -89,6 +91,35 @@ struct cgx_regex {
       CU(cudaMemcpy(d_trans.p, c->dfa.trans.data(), c->dfa.trans.size() * 2, cudaMemcpyHostToDevice));
       CU(cudaMemcpy(d_eoi.p, c->dfa.eoi.data(), c->dfa.eoi.size(), cudaMemcpyHostToDevice));
       CU(cudaMemcpy(d_lut.p, c->lut, 256, cudaMemcpyHostToDevice));
+    }
+    memset(&teddy_dev, 0, sizeof teddy_dev);
+    if (c->kind == ENG_TEDDY) {
+      // one allocation: fp[256] u32 | offs[npat+1] i32 | order[npat] u16 | bucket_off[nb+1] u16 | bytes
+      const TeddyTables& t = c->teddy;
+      size_t o_fp = 0, o_offs = o_fp + 1024, o_order = o_offs + (t.npat + 1) * 4;
+      size_t o_boff = o_order + ((t.npat * 2 + 3) & ~3), o_bytes = o_boff + (((t.nbuckets + 1) * 2 + 3) & ~3);
+      size_t total = o_bytes + t.bytes.size();
+      std::vector<uint8_t> blob((total + 3) & ~(size_t)3, 0);
+      memcpy(&blob[o_fp], t.fp_packed.data(), 1024);
+      memcpy(&blob[o_offs], t.offs.data(), (t.npat + 1) * 4);
+      memcpy(&blob[o_order], t.order_simd.data(), t.npat * 2);
+      memcpy(&blob[o_boff], t.bucket_off.data(), (t.nbuckets + 1) * 2);
+      memcpy(&blob[o_bytes], t.bytes.data(), t.bytes.size());
+      int r;
+      if ((r = d_teddy.ensure(blob.size()))) return r;
+      CU(cudaMemcpy(d_teddy.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+      const uint8_t* b = (const uint8_t*)d_teddy.p;
+      teddy_dev.fp = (const uint32_t*)(b + o_fp);
+      teddy_dev.offs = (const int32_t*)(b + o_offs);
+      teddy_dev.order = (const uint16_t*)(b + o_order);
+      teddy_dev.bucket_off = (const uint16_t*)(b + o_boff);
+      teddy_dev.bytes = b + o_bytes;
+      teddy_dev.npat = t.npat;
+      teddy_dev.nbuckets = t.nbuckets;
+      teddy_dev.min_len = t.min_len;
+      teddy_dev.max_len = t.max_len;
+      teddy_dev.bytes_len = (int)t.bytes.size();
+      teddy_dev.blob_bytes = (int)((total + 3) & ~(size_t)3);
     }
     device = dev;
     return CGX_OK;
@@ -132,7 +163,7 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
     g_last_error = "device pointers must be 16-byte aligned";
     return CGX_ERR_ARGS;
   }
-  if (c.kind != ENG_DFA) {
+  if (c.kind != ENG_DFA && c.kind != ENG_TEDDY) {
     g_last_error = "engine not available in this build";
     return CGX_ERR_UNSUPPORTED;
   }
@@ -161,6 +192,12 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   }
   a.filter.lut = (const uint8_t*)re->d_lut.p;
   a.flat = c.flat;
+  a.teddy = re->teddy_dev;
+  a.engine = c.kind == ENG_TEDDY ? SEL_TEDDY : SEL_DFA;
+  if (c.kind == ENG_TEDDY) {
+    a.dfa.nstates = 0;
+    a.flat.nops = 0;
+  }
   a.skip_safe = c.skip_safe ? 1 : 0;
   a.delim = c.delim;
   a.mode = mode;

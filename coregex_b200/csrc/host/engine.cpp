@@ -47,8 +47,13 @@ bool BuildTeddyTables(const std::vector<std::string>& patterns, TeddyTables& t) 
     t.fp0[c] = lo[0][c & 15] & hi[0][c >> 4];
     t.fp1[c] = lo[1][c & 15] & hi[1][c >> 4];
   }
-  for (auto& b : buckets)
+  t.bucket_off.push_back(0);
+  for (auto& b : buckets) {
     for (uint16_t id : b) t.order_simd.push_back(id);
+    t.bucket_off.push_back((uint16_t)t.order_simd.size());
+  }
+  t.fp_packed.resize(256);
+  for (int c = 0; c < 256; c++) t.fp_packed[c] = (uint32_t)t.fp0[c] | ((uint32_t)t.fp1[c] << 16);
   return true;
 }
 

@@ -27,6 +27,8 @@ struct TeddyTables {
   std::vector<uint16_t> fp0, fp1;  // 256-entry byte tables for fingerprint positions 0 and 1
   std::vector<uint16_t> order_simd;  // pattern ids, bucket-major
   std::vector<uint8_t> bucket_of;    // per pattern id
+  std::vector<uint16_t> bucket_off;  // nbuckets+1 offsets into order_simd
+  std::vector<uint32_t> fp_packed;   // fp0 | fp1<<16
 };
 
 // patterns in reference literal order; returns false when the reference's NewTeddy/NewFatTeddy

@@ -81,6 +81,12 @@ struct Ctx {
   int wend;               // number of valid bytes in the window
   int lane, warp;
   int buf;                // staging buffer of this chunk
+  // multi-literal engine tables (shared memory copies)
+  const uint32_t* t_fp;
+  const uint8_t* t_bytes;
+  const int32_t* t_offs;
+  const uint16_t* t_order;
+  const uint16_t* t_boff;
 };
 
 __device__ __forceinline__ uint8_t byte_at(const Ctx& c, int64_t p) {
@@ -146,6 +152,79 @@ __device__ __forceinline__ int dfa_walk(const Ctx& c, int i0) {
     return e < 0 ? -1 : (int)(e - c.gw);
   }
   return last;
+}
+
+__device__ __forceinline__ void load32(const uint8_t* p32, uint32_t (&w)[8]);
+
+// ---- multi-literal (Teddy) engine -------------------------------------------------------------
+// reference prefilter/teddy.go:491-521 (candidate = AND of per-position nibble masks, here folded
+// into one byte table per position) and :532-550 (verifyBucket).
+__device__ __forceinline__ uint32_t teddy_mask(const Ctx& c, uint32_t b0, uint32_t b1) {
+  return (c.t_fp[b0] & 0xFFFFu) & (c.t_fp[b1] >> 16);
+}
+
+__device__ __forceinline__ bool lit_equal(const Ctx& c, int64_t p, int id, int& len) {
+  const int o = c.t_offs[id];
+  len = c.t_offs[id + 1] - o;
+  if (p + len > c.a.n) return false;
+  for (int k = 0; k < len; k++)
+    if (byte_at(c, p + k) != c.t_bytes[o + k]) return false;
+  return true;
+}
+
+// SIMD-regime verify at global position p: buckets low -> high, insertion order inside a bucket
+__device__ int64_t teddy_verify(const Ctx& c, int64_t p, uint32_t mask) {
+  while (mask) {
+    const int b = __ffs(mask) - 1;
+    mask &= mask - 1;
+    if (b >= c.a.teddy.nbuckets) break;
+    for (int k = c.t_boff[b]; k < c.t_boff[b + 1]; k++) {
+      int len;
+      if (lit_equal(c, p, c.t_order[k], len)) return p + len;
+    }
+  }
+  return -1;
+}
+// scalar-regime verify (haystack[start:] shorter than 16 bytes): plain literal-id order
+// (reference prefilter/teddy.go:447-458 findMatchScalar)
+__device__ int64_t teddy_verify_scalar(const Ctx& c, int64_t p) {
+  for (int id = 0; id < c.a.teddy.npat; id++) {
+    int len;
+    if (lit_equal(c, p, id, len)) return p + len;
+  }
+  return -1;
+}
+
+// batch verify from window index i0; returns end window index or -1
+__device__ __forceinline__ int teddy_walk(const Ctx& c, int i0) {
+  const uint32_t m = teddy_mask(c, c.sm.win[i0], c.sm.win[i0 + 1]);
+  if (!m) return -1;
+  const int64_t e = teddy_verify(c, c.gw + i0, m);
+  return e < 0 ? -1 : (int)(e - c.gw);
+}
+
+__device__ void phase_a_teddy(const Ctx& c) {
+  for (int t = c.warp; t < NTILES; t += WARPS) {
+    const int rel = t * TILE + c.lane * 32;
+    const uint8_t* p = c.sm.win + PRE + rel;
+    uint32_t w[8];
+    load32(p, w);
+    uint32_t m = 0;
+    uint32_t tprev = c.t_fp[w[0] & 255u];
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+      const uint32_t nb = k == 31 ? (uint32_t)p[32] : ((w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 255u);
+      const uint32_t tn = c.t_fp[nb];
+      if ((tprev & 0xFFFFu) & (tn >> 16)) m |= 1u << k;
+      tprev = tn;
+    }
+    const int64_t gp = c.cbeg + rel;  // a 2-byte fingerprint needs position+1 < n
+    if (gp + 33 > c.a.n) {
+      const int64_t v = c.a.n - 1 - gp;
+      m = v <= 0 ? 0u : (v >= 32 ? m : (m & ((1u << v) - 1u)));
+    }
+    c.sm.cand[t * 32 + c.lane] = m;
+  }
 }
 
 // ---- phase A: candidate bitmap -------------------------------------------------------------------
@@ -366,10 +445,50 @@ struct Emitter {
   }
 };
 
+// Multi-literal engine: one lane replays reference meta/findall.go:176-290 over
+// Teddy.FindMatch (prefilter/teddy.go:391-445): the regime (scalar vs SIMD verify order) is fixed
+// per call by the distance from the call's start position to the end of the haystack.
+template <bool DIRECT>
+__device__ int serial_chain_teddy(const Ctx& c, Emitter<DIRECT>& em, int pos_i, int last_cand, bool to_line_end) {
+  unsigned added = 0;
+  if (c.lane == 0) {
+    const int64_t n = c.a.n;
+    int64_t pos = c.gw + pos_i;
+    const int64_t lastc = c.gw + last_cand;
+    bool more = true;
+    while (more && pos < n) {
+      const bool scalar = n - pos < 16;
+      more = false;
+      for (int64_t p = pos; p + 2 <= n; p++) {
+        const uint8_t b0 = byte_at(c, p);
+        if (to_line_end && b0 == c.a.delim) break;
+        if (!to_line_end && p > lastc) break;
+        const uint32_t m = teddy_mask(c, b0, byte_at(c, p + 1));
+        if (!m) continue;
+        const int64_t e = scalar ? teddy_verify_scalar(c, p) : teddy_verify(c, p, m);
+        if (e >= 0) {
+          em.put(em.nkept + added, (int)(p - c.gw), (int)(e - c.gw));
+          added++;
+          pos = e;
+          more = true;
+          break;
+        }
+      }
+    }
+    pos_i = (int)(pos - c.gw);
+  }
+  added = __shfl_sync(FULL, added, 0);
+  pos_i = __shfl_sync(FULL, pos_i, 0);
+  if (!DIRECT && em.nkept + added > STG) em.overflow = true;
+  em.nkept += added;
+  return pos_i;
+}
+
 // One lane replays the reference loop from window index `pos` while the next candidate is
 // <= last_cand (or, with to_line_end, until the current line ends).  Returns the new chain position.
 template <bool DIRECT>
 __device__ int serial_chain(const Ctx& c, Emitter<DIRECT>& em, int pos_i, int last_cand, bool to_line_end) {
+  if (c.a.engine == SEL_TEDDY) return serial_chain_teddy<DIRECT>(c, em, pos_i, last_cand, to_line_end);
   unsigned added = 0;
   if (c.lane == 0) {
     const int64_t n = c.a.n;
@@ -416,7 +535,7 @@ template <bool DIRECT>
 __device__ __forceinline__ int process_batch(const Ctx& c, Emitter<DIRECT>& em, int cand, bool valid,
                                              int kept_end) {
   int end = -1;
-  if (valid) end = dfa_walk(c, cand);
+  if (valid) end = c.a.engine == SEL_TEDDY ? teddy_walk(c, cand) : dfa_walk(c, cand);
   const bool ok = end >= 0;
   const unsigned okmask = __ballot_sync(FULL, ok);
   if (!okmask) return kept_end;
@@ -430,6 +549,9 @@ __device__ __forceinline__ int process_batch(const Ctx& c, Emitter<DIRECT>& em, 
   if (!lower) pe = kept_end;
   bool bad = ok && cand < pe;
   if (c.a.skip_safe && ok && c.gw + end < c.a.n) bad |= in_filter_set(c, byte_at(c, c.gw + end));
+  // literal candidates inside the last 16 bytes of the haystack may fall under the reference's
+  // scalar verify order: let the exact replay decide
+  if (c.a.engine == SEL_TEDDY) bad |= valid && c.gw + cand > c.a.n - 16;
   if (__any_sync(FULL, bad)) {
     // replay from the chain position through the last candidate of this batch
     const unsigned vmask = __ballot_sync(FULL, valid);
@@ -577,6 +699,12 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
     s_trans[i] = ((e & 0x7FFFu) << 10) | ((e & 0x8000u) << 16);
   }
   for (int i = tid; i < a.dfa.nstates; i += THREADS) s_eoi[i] = a.dfa.eoi[i];
+  // ... or the literal tables (one blob, same layout as in global memory)
+  const unsigned char* t_blob = smem_raw + sizeof(Smem);
+  if (a.engine == SEL_TEDDY)
+    for (int i = tid; i < a.teddy.blob_bytes / 4; i += THREADS)
+      reinterpret_cast<uint32_t*>(smem_raw + sizeof(Smem))[i] = a.teddy.fp[i];
+  const unsigned char* g_blob = reinterpret_cast<const unsigned char*>(a.teddy.fp);
   if (a.filter.kind == F_LUT)
     for (int i = tid; i < 256; i += THREADS) s_lut[i] = a.filter.lut[i];
   if (tid < WINPAD) sm.win[WIN + tid] = a.delim;
@@ -651,8 +779,15 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
     parity ^= 1;
     if (gw < 0 || bulk != (uint32_t)WIN) bar_sync(BAR_COMPUTE, CTHREADS);  // generic fill stores
 
-    Ctx c{a, sm, s_trans, s_eoi, s_lut, cbeg, gw, (int)(hi_g - gw), lane, warp, buf};
-    if (a.flat.nops) phase_a_flat(c); else phase_a_plain(c);
+    Ctx c{a, sm, s_trans, s_eoi, s_lut, cbeg, gw, (int)(hi_g - gw), lane, warp, buf,
+          reinterpret_cast<const uint32_t*>(t_blob),
+          t_blob + (a.teddy.bytes - g_blob),
+          reinterpret_cast<const int32_t*>(t_blob + ((const unsigned char*)a.teddy.offs - g_blob)),
+          reinterpret_cast<const uint16_t*>(t_blob + ((const unsigned char*)a.teddy.order - g_blob)),
+          reinterpret_cast<const uint16_t*>(t_blob + ((const unsigned char*)a.teddy.bucket_off - g_blob))};
+    if (a.engine == SEL_TEDDY) phase_a_teddy(c);
+    else if (a.flat.nops) phase_a_flat(c);
+    else phase_a_plain(c);
     {
       const int64_t s = find_line_start(c, cbeg + (int64_t)warp * SUB);
       if (lane == 0) sm.ls[warp] = s;
@@ -719,7 +854,8 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
 
 }  // namespace
 
-size_t scan_dfa_smem_bytes(int nstates) {
+size_t scan_dfa_smem_bytes(int nstates, int teddy_blob_bytes) {
+  if (teddy_blob_bytes) return sizeof(Smem) + (size_t)teddy_blob_bytes + 16;
   return sizeof(Smem) + (size_t)nstates * 1024 + ((nstates + 15) & ~15) + 256;
 }
 
@@ -728,7 +864,7 @@ int64_t scan_dfa_chunks(int64_t n) { return n <= 0 ? 0 : (n + CH - 1) / CH; }
 // Launches the scan on `stream`.  ticket/status/total must be zeroed by the caller.
 cudaError_t launch_scan_dfa(const ScanArgs& a, int sm_count, cudaStream_t stream) {
   if (a.nchunks == 0) return cudaSuccess;
-  const size_t smem = scan_dfa_smem_bytes(a.dfa.nstates);
+  const size_t smem = scan_dfa_smem_bytes(a.dfa.nstates, a.engine == SEL_TEDDY ? a.teddy.blob_bytes : 0);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(scan_dfa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

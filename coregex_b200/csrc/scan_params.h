@@ -53,6 +53,19 @@ struct FlatDev {
   uint32_t cls_k1[4][4], cls_k2[4][4];
 };
 
+// Multi-literal engine tables (reference prefilter/teddy.go, teddy_fat.go), device resident.
+struct TeddyDev {
+  const uint32_t* fp;        // 256 entries: fp0[b] | fp1[b] << 16  (bucket masks per byte value)
+  const uint8_t* bytes;      // concatenated literals
+  const int32_t* offs;       // npat + 1
+  const uint16_t* order;     // literal ids, bucket-major (SIMD-regime verify order)
+  const uint16_t* bucket_off;  // nbuckets + 1 offsets into `order`
+  int npat, nbuckets, min_len, max_len, bytes_len;
+  int blob_bytes;            // size of the single allocation that starts at `fp`
+};
+
+enum EngineSel : int { SEL_DFA = 0, SEL_TEDDY = 1 };
+
 struct ScanArgs {
   const uint8_t* h;   // device haystack, 16-byte aligned
   int64_t n;
@@ -60,6 +73,8 @@ struct ScanArgs {
   DfaDev dfa;
   FilterDev filter;
   FlatDev flat;
+  TeddyDev teddy;
+  int engine;         // EngineSel
   int skip_safe;      // 1: after a match, a candidate in the middle of a run must still be tried
   uint8_t delim;      // record delimiter no match can contain
   int mode;

@@ -1,0 +1,114 @@
+"""-m gpu: parity of the multi-literal (Slim/Fat Teddy) engine against the CPU oracle, including
+the reference's verify-order regimes (bucket-major vs literal order in the last 16 bytes)."""
+import os
+
+import numpy as np
+import pytest
+
+import coregex_b200 as cg
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+LIT16 = [b"error", b"warning", b"fatal", b"critical", b"timeout", b"refused", b"denied", b"panic",
+         b"overflow", b"invalid", b"missing", b"corrupt", b"expired", b"blocked", b"aborted", b"unknown"]
+LIT64 = [("k%02dz%s" % (i, "q" * (i % 4))).encode() for i in range(64)]
+
+
+def check(pat, hay):
+    r = cg.Compile(pat)
+    o = Oracle(pat)
+    assert o.strategy == "UseTeddy" and r.strategy == "UseTeddy" and "teddy" in r.engine
+    want = o.find_all(hay)
+    got = r.find_all_index_array(hay)
+    assert got.shape == want.shape and np.array_equal(got, want), (pat, len(hay))
+    assert r.Count(hay) == len(want) and r.Match(hay) == (len(want) > 0)
+
+
+def test_known_answers():
+    r = cg.Compile("cat|dog")
+    assert r.FindAllIndex(b"a cat and dog") == [[2, 5], [10, 13]]       # meta/findall_extra_test.go:336
+    r = cg.Compile("foo|bar")
+    assert r.FindAllIndex(b"hello foo world") == [[6, 9]]              # prefilter/teddy_test.go:95
+    assert r.FindAllIndex(b"hello world") is None
+    r = cg.Compile("|".join("p%02d" % i for i in range(50)))           # meta/fat_teddy_fallback_test.go
+    assert r.engine == "fat-teddy" and r.FindAllIndex(b"test p42 here") == [[5, 8]]
+
+
+def test_fixture_corpus():
+    corpus = open(os.path.join(ROOT, "tests", "golden", "stdlib_corpus.txt"), "rb").read()
+    check("error|warning|fatal|critical", corpus)
+    check("apple|banana|cherry|grape|lemon|mango|melon|olive|peach|plum|kiwi|lime", corpus)
+    check("(?i)error", corpus)
+    check("GET|POST|PUT", corpus)
+
+
+@pytest.mark.parametrize("blocks", [1, 9, 64, 700])
+def test_slim16_on_synthetic_text(blocks):
+    hay = cg.synth_host(cg.SYNTH_TEXT, 31 + blocks, 4096 * blocks, literals=LIT16)
+    check(b"|".join(LIT16).decode(), hay)
+
+
+@pytest.mark.parametrize("blocks", [1, 9, 300])
+def test_fat64_on_synthetic_text(blocks):
+    hay = cg.synth_host(cg.SYNTH_TEXT, 77 + blocks, 4096 * blocks, literals=LIT64)
+    r = cg.Compile(b"|".join(LIT64).decode())
+    assert r.engine == "fat-teddy"
+    check(b"|".join(LIT64).decode(), hay)
+
+
+def test_prefix_overlapping_literals_and_tail_regime():
+    """One literal being a prefix of another makes the verify ORDER observable; the reference
+    switches order when fewer than 16 bytes remain from the call position (App. B hazard 1)."""
+    rng = np.random.default_rng(9)
+    sets = [["aba", "abab", "bab", "ababa", "baba", "abb", "bba", "aab", "baa", "aaa", "bbb"],
+            ["abc", "abcd", "abcde", "bcd", "bcde", "cde", "xab", "xabc", "cdea"],
+            ["foo", "foobar", "barfoo", "bar", "oba", "oof", "rfo"]]
+    for lits in sets:
+        pat = "|".join(lits)
+        r, o = cg.Compile(pat), Oracle(pat)
+        if o.strategy != "UseTeddy":
+            continue
+        alphabet = np.frombuffer("".join(sorted(set("".join(lits)))).encode() + b" \n", dtype=np.uint8)
+        for it in range(120):
+            n = int(rng.integers(0, 120))
+            h = bytes(alphabet[rng.integers(0, len(alphabet), n)])
+            assert np.array_equal(r.find_all_index_array(h), o.find_all(h)), (pat, h)
+        for n in [15, 16, 17, 31, 32, 33, 4095, 4096, 4100, 31744, 31760, 40000]:
+            h = bytes(alphabet[rng.integers(0, len(alphabet) - 1, n)])
+            assert np.array_equal(r.find_all_index_array(h), o.find_all(h)), (pat, n)
+
+
+def test_dense_and_boundaries():
+    check("foo|bar", b"foobar" * 20000)
+    check("foo|bar", b"foo\n" * 30000)
+    for off in range(31744 - 8, 31744 + 3):
+        check("error|warning|fatal|critical", b"x" * off + b"critical error\nfatal")
+    check("error|warning|fatal|critical", b"z" * 100000 + b"warning")
+
+
+def test_c3_sized_properties_512mb():
+    """BASELINE config 3 shape (16 literals) at 512 MB: ordered, non-overlapping, every match is a
+    literal; oracle agreement on sampled 256 KB windows."""
+    import torch
+    from gpu_util import dev_corpus, scan_device
+    n = 512 << 20
+    t = dev_corpus(cg.SYNTH_TEXT, 0xC0FFEE + 3, n, literals=LIT16)
+    pat = b"|".join(LIT16).decode()
+    r = cg.Compile(pat)
+    total, _, pairs = scan_device(r, t, cap=n // 64)
+    assert total == len(pairs) and total > n // 400
+    s, e = pairs[:, 0], pairs[:, 1]
+    assert np.all(s[1:] >= e[:-1])
+    lens = set(len(x) for x in LIT16)
+    assert set(np.unique(e - s).tolist()) <= lens
+    o = Oracle(pat)
+    rng = np.random.default_rng(2)
+    win = 64 * 4096
+    for b in rng.integers(0, n // win, 24):
+        lo = int(b) * win
+        hay = cg.synth_host(cg.SYNTH_TEXT, 0xC0FFEE + 3, win, first_block=lo // 4096, literals=LIT16)
+        want = o.find_all(hay) + lo
+        i0, i1 = np.searchsorted(s, lo), np.searchsorted(s, lo + win)
+        assert np.array_equal(pairs[i0:i1], want)
