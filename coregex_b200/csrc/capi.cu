@@ -197,9 +197,16 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   if (c.kind == ENG_TEDDY) {
     a.dfa.nstates = 0;
     a.flat.nops = 0;
+    a.filter.kind = F_BYTESET;  // unused by the literal engine; must not point at a LUT
+    a.filter.nranges = 0;
+    a.filter.lut = nullptr;
+    a.skip_safe = 0;
+    a.delim = '\n';
   }
-  a.skip_safe = c.skip_safe ? 1 : 0;
-  a.delim = c.delim;
+  if (c.kind != ENG_TEDDY) {
+    a.skip_safe = c.skip_safe ? 1 : 0;
+    a.delim = c.delim;
+  }
   a.mode = mode;
   a.out = d_out;
   a.cap = (int64_t)cap;

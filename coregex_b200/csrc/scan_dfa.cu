@@ -838,7 +838,10 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
       used++;
       buf ^= 1;
     } else {
-      if (tid == 0 && agg) atomicAdd(a.total, (unsigned long long)agg);
+      if (tid == 0 && agg) {
+        atomicAdd(a.total, (unsigned long long)agg);
+        a.total[1] = 1ull;  // is-match flag (also reached through the serial replay paths)
+      }
     }
     // no barrier here: everything the next iteration overwrites (window, bitmap, class scratch)
     // was last read before the barrier that followed phase B
