@@ -18,7 +18,10 @@ namespace cgx {
 size_t scan_dfa_smem_bytes(int nstates, int teddy_blob_bytes);
 int64_t scan_dfa_chunks(int64_t n);
 cudaError_t launch_scan_dfa(const ScanArgs& a, int sm_count, cudaStream_t stream);
-cudaError_t launch_scan_teddy(const struct TeddyArgs& a, int sm_count, cudaStream_t stream);
+cudaError_t launch_pike_captures(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
+                                 const unsigned long long* d_total, unsigned long long cap,
+                                 const uint32_t* code, const uint32_t* sets, int start_pc, int nslots,
+                                 int64_t* out, cudaStream_t stream);
 }  // namespace cgx
 
 using namespace cgx;
@@ -67,7 +70,7 @@ struct cgx_regex {
   DevBuf d_trans, d_eoi, d_lut, d_teddy;
   TeddyDev teddy_dev;
   // per-call scratch (serialised by mu)
-  DevBuf d_ticket_total, d_status, d_hay, d_out;
+  DevBuf d_ticket_total, d_status, d_hay, d_out, d_pairs, d_pike;
   std::atomic<uint64_t> launches{0};
 
   int ensure_device() {
@@ -120,6 +123,13 @@ struct cgx_regex {
       teddy_dev.max_len = t.max_len;
       teddy_dev.bytes_len = (int)t.bytes.size();
       teddy_dev.blob_bytes = (int)((total + 3) & ~(size_t)3);
+    }
+    if (c->has_pike) {
+      int r;
+      size_t cb = c->pike.code.size() * 4, sb = c->pike.sets.size() * 4;
+      if ((r = d_pike.ensure(cb + sb + 16))) return r;
+      CU(cudaMemcpy(d_pike.p, c->pike.code.data(), cb, cudaMemcpyHostToDevice));
+      if (sb) CU(cudaMemcpy((char*)d_pike.p + cb, c->pike.sets.data(), sb, cudaMemcpyHostToDevice));
     }
     device = dev;
     return CGX_OK;
@@ -230,10 +240,36 @@ int cgx_scan_device(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base,
   return scan_locked(re, d_h, len, base, mode, d_out, cap, d_result, (cudaStream_t)stream);
 }
 
-int cgx_scan_submatch_device(cgx_regex*, const uint8_t*, size_t, int64_t, int64_t*, size_t, uint64_t*,
-                             void*) {
-  g_last_error = "captures kernel not available in this build";
-  return CGX_ERR_UNSUPPORTED;
+// scan -> (start,end) pairs -> one Pike lane per match for the group offsets
+static int submatch_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base, int64_t* d_out,
+                           size_t cap, uint64_t* d_result, cudaStream_t st) {
+  Compiled& c = *re->c;
+  const int nslots = 2 * c.prog.num_captures;
+  if (nslots == 2)  // no groups: the pairs ARE the result (reference meta/findall.go:109-112)
+    return scan_locked(re, d_h, len, base, CGX_MODE_FINDALL, d_out, cap, d_result, st);
+  if (!c.has_pike) {
+    g_last_error = "unsupported: captures kernel limit: " + c.pike_err;
+    return CGX_ERR_UNSUPPORTED;
+  }
+  int r;
+  if ((r = re->d_pairs.ensure((cap ? cap : 1) * 16))) return r;
+  if ((r = scan_locked(re, d_h, len, base, CGX_MODE_FINDALL, (int64_t*)re->d_pairs.p, cap, d_result, st))) return r;
+  const uint32_t* code = (const uint32_t*)re->d_pike.p;
+  const uint32_t* sets = code + c.pike.code.size();
+  CU(launch_pike_captures(d_h, (int64_t)len, base, (const int64_t*)re->d_pairs.p,
+                          (const unsigned long long*)re->d_ticket_total.p, cap, code, sets, c.pike.start, nslots,
+                          d_out, st));
+  re->launches++;
+  return CGX_OK;
+}
+
+int cgx_scan_submatch_device(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base, int64_t* d_out,
+                             size_t cap, uint64_t* d_result, void* stream) {
+  if (!re) return CGX_ERR_ARGS;
+  std::lock_guard<std::mutex> lk(re->mu);
+  int r = re->ensure_device();
+  if (r) return r;
+  return submatch_locked(re, d_h, len, base, d_out, cap, d_result, (cudaStream_t)stream);
 }
 
 // host wrapper shared by is_match / count / find_all
@@ -294,9 +330,32 @@ int cgx_find_all_index(cgx_regex* re, const uint8_t* h, size_t len, int64_t limi
   return CGX_OK;
 }
 
-int cgx_find_all_submatch_index(cgx_regex*, const uint8_t*, size_t, int64_t, int64_t*, size_t, size_t*) {
-  g_last_error = "captures kernel not available in this build";
-  return CGX_ERR_UNSUPPORTED;
+int cgx_find_all_submatch_index(cgx_regex* re, const uint8_t* h, size_t len, int64_t limit, int64_t* out,
+                                size_t cap, size_t* count) {
+  if (count) *count = 0;
+  if (limit == 0) return CGX_OK;
+  if (!re || (!h && len)) return CGX_ERR_ARGS;
+  std::lock_guard<std::mutex> lk(re->mu);
+  int r = re->ensure_device();
+  if (r) return r;
+  size_t want = cap;
+  if (limit > 0 && (size_t)limit < want) want = (size_t)limit;
+  const size_t stride = 2 * (size_t)re->c->prog.num_captures;
+  if ((r = re->d_hay.ensure(len + 16))) return r;
+  if ((r = re->d_out.ensure((want ? want : 1) * stride * 8))) return r;
+  cudaStream_t st = 0;
+  if (len) CU(cudaMemcpyAsync(re->d_hay.p, h, len, cudaMemcpyHostToDevice, st));
+  if ((r = submatch_locked(re, (const uint8_t*)re->d_hay.p, len, 0, (int64_t*)re->d_out.p, want, nullptr, st)))
+    return r;
+  uint64_t res[2] = {0, 0};
+  CU(cudaMemcpyAsync(res, re->d_ticket_total.p, 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  size_t c = (size_t)res[0];
+  size_t w = c < want ? c : want;
+  if (out && w) CU(cudaMemcpy(out, re->d_out.p, w * stride * 8, cudaMemcpyDeviceToHost));
+  if (limit > 0 && c > (size_t)limit) c = (size_t)limit;
+  if (count) *count = c;
+  return CGX_OK;
 }
 
 // ---- debug exports (tests only): the compiled tables exactly as the kernels see them ------------

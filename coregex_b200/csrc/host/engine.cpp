@@ -291,6 +291,8 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
     }
     if (c->flat.nops) c->engine_name += "+flat";
   }
+  c->pike_err = PackPike(c->prog, c->pike);
+  c->has_pike = c->pike_err.empty();
   out = std::move(c);
   return COMPILE_OK;
 }

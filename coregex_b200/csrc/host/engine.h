@@ -9,6 +9,7 @@
 #include "analysis.h"
 #include "dfa.h"
 #include "prog.h"
+#include "pike_pack.h"
 #include "teddy_tables.h"
 
 namespace cgx {
@@ -44,7 +45,8 @@ struct Compiled {
 
   // captures (FindAllSubmatchIndex)
   bool has_pike = false;
-  std::vector<uint32_t> pike_code;  // packed program for pikevm_kernel.cu
+  PikePacked pike;       // packed program for pikevm_kernel.cu
+  std::string pike_err;  // why captures are unavailable (when !has_pike)
 };
 
 enum CompileStatus { COMPILE_OK = 0, COMPILE_SYNTAX = -1, COMPILE_UNSUPPORTED = -2 };

@@ -1,0 +1,97 @@
+"""-m gpu: FindAllSubmatchIndex (scan kernel + one Pike lane per match) against the CPU oracle's
+restatement of the reference PikeVM capture search."""
+import os
+
+import numpy as np
+import pytest
+
+import coregex_b200 as cg
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def check(pat, hay):
+    r, o = cg.Compile(pat), Oracle(pat)
+    want = o.find_all_submatch(hay)
+    got = r.FindAllSubmatchIndex(hay)
+    if len(want) == 0:
+        assert got is None
+        return
+    assert np.array_equal(np.array(got, dtype=np.int64), want), (pat, len(hay))
+
+
+def test_reference_known_answers():
+    # reference meta/findall_extra_test.go:147-157
+    assert cg.Compile(r"(\w+)@(\w+)").FindAllSubmatchIndex(b"user@host admin@server") == [
+        [0, 9, 0, 4, 5, 9], [10, 22, 10, 15, 16, 22]]
+    # reference nfa/pikevm_slottable_test.go:171-188
+    assert cg.Compile(r"(a+)(b+)").FindAllSubmatchIndex(b"xxxaaabbbyyy") == [[3, 9, 3, 6, 6, 9]]
+    assert cg.Compile(r"([a-z]+)([0-9]+)").FindAllSubmatchIndex(b"abc123xyz") == [[0, 6, 0, 3, 3, 6]]
+    r = cg.Compile(r"\w+@\w+\.\w+")          # no groups: stride 2 (reference meta/findall.go:109-112)
+    assert r.NumSubexp() == 0
+    assert r.FindAllSubmatchIndex(b"Contact: user@example.com for info") == [[9, 25]]
+    assert cg.Compile(r"(\d+)").FindAllSubmatchIndex(b"none") is None
+    assert cg.Compile(r"(\d+)").FindAllSubmatchIndex(b"1 2 3", 2) == [[0, 1, 0, 1], [2, 3, 2, 3]]
+
+
+PATS = [r"(\w+)@(\w+)\.(\w+)", r"(\d+)\.(\d+)\.(\d+)\.(\d+)", r"(\w+)@(\w+)", r"(a)?b", r"(foo)|(bar)",
+        r"((a)(b))+c", r"(\d+)-(\d+)?x", r"([a-z]+?)(\d+)", r"(?P<user>\w+)@(?P<host>[a-z]+)", r"(a|ab)(c|bcd)(d*)x"]
+
+
+@pytest.mark.parametrize("pat", PATS)
+def test_random_haystacks(pat):
+    rng = np.random.default_rng(13)
+    alphabet = np.frombuffer(b"0123456789.. abcdx\n@_-foobar", dtype=np.uint8)
+    r, o = cg.Compile(pat), Oracle(pat)
+    for it in range(60):
+        n = int(rng.integers(0, 400))
+        h = bytes(alphabet[rng.integers(0, len(alphabet), n)])
+        want = o.find_all_submatch(h)
+        got = r.FindAllSubmatchIndex(h)
+        if len(want) == 0:
+            assert got is None, (pat, h)
+        else:
+            assert np.array_equal(np.array(got, dtype=np.int64), want), (pat, h)
+
+
+@pytest.mark.parametrize("lines", [1, 100, 4000, 100000])
+def test_c4_email_lines(lines):
+    hay = cg.synth_host(cg.SYNTH_EMAIL, 0xC0FFEE + 4, 80 * lines)
+    check(r"(\w+)@(\w+)\.(\w+)", hay)
+    check(r"\w+@\w+\.\w+", hay)
+
+
+def test_ip_groups_on_log_corpus():
+    hay = cg.synth_host(cg.SYNTH_LOG, 5, 4096 * 200)
+    check(r"(\d+)\.(\d+)\.(\d+)\.(\d+)", hay)
+
+
+def test_c4_sized_device_entry():
+    """BASELINE config 4 shape: 10M x 80-byte lines, captures form; properties + sampled oracle."""
+    import torch
+    from gpu_util import dev_corpus
+    nlines = 10_000_000
+    n = 80 * nlines
+    t = dev_corpus(cg.SYNTH_EMAIL, 0xC0FFEE + 4, n)
+    r = cg.Compile(r"(\w+)@(\w+)\.(\w+)")
+    cap = nlines + 1024
+    out = torch.empty((cap, 8), dtype=torch.int64, device="cuda")
+    res = torch.zeros(2, dtype=torch.int64, device="cuda")
+    r.scan_submatch_device(t.data_ptr(), n, out.data_ptr(), cap, res.data_ptr())
+    torch.cuda.synchronize()
+    total = int(res[0].item())
+    assert total == nlines                       # exactly one e-mail per line
+    m = out[:total].cpu().numpy()
+    assert np.all(m[:, 0] // 80 == np.arange(nlines))            # one per line, in order
+    assert np.all(m[:, 2] == m[:, 0]) and np.all(m[:, 7] == m[:, 1])
+    assert np.all(m[:, 3] + 1 == m[:, 4]) and np.all(m[:, 5] + 1 == m[:, 6])
+    o = Oracle(r"(\w+)@(\w+)\.(\w+)")
+    rng = np.random.default_rng(4)
+    for b in rng.integers(0, nlines // 1000, 16):
+        lo = int(b) * 1000
+        hay = cg.synth_host(cg.SYNTH_EMAIL, 0xC0FFEE + 4, 80 * 1000, first_block=lo)
+        want = o.find_all_submatch(hay)
+        want = np.where(want >= 0, want + lo * 80, want)
+        assert np.array_equal(m[lo:lo + 1000], want)
