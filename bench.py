@@ -176,19 +176,23 @@ def main():
         torch.cuda.set_device(0)
     dev = torch.device("cuda", local if world > 1 else 0)
 
+    from coregex_b200 import shard
     n = int(args.gib * GIB)
     n -= n % 4096
     blocks = n // 4096
-    # shard `rank` of one logical corpus: block range [rank*blocks, (rank+1)*blocks)
+    # weak scaling: one logical corpus of world*blocks blocks, rank r owns a contiguous,
+    # line-aligned range of `blocks` blocks (every 4 KB block ends with a newline)
+    first_block, my_blocks = shard.shard_blocks(blocks * world, world, rank)
+    assert my_blocks == blocks
     hay = torch.empty(n + 64, dtype=torch.uint8, device=dev)[:n]
-    cg.synth_device(cg.SYNTH_LOG, SEED, hay.data_ptr(), n, first_block=rank * blocks)
+    cg.synth_device(cg.SYNTH_LOG, SEED, hay.data_ptr(), n, first_block=first_block)
     cap = n // 48  # ~1 match per 92 bytes in this corpus; 2x head-room
     out = torch.empty((cap, 2), dtype=torch.int64, device=dev)
     res = torch.zeros(2, dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
 
     r = cg.Compile(PATTERN)
-    base = rank * n
+    base = first_block * 4096
 
     def step():
         r.scan_device(hay.data_ptr(), n, cg.MODE_FINDALL, out.data_ptr(), cap, res.data_ptr(), base)
@@ -225,11 +229,9 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms = float(tmax.item())
         # the only collective on the path: gather per-shard (match_count, bytes) over NCCL
-        mine = torch.tensor([matches, n], dtype=torch.int64, device=dev)
-        allc = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(allc, mine)
-        total_matches = int(sum(int(x[0].item()) for x in allc))
-        total_bytes = int(sum(int(x[1].item()) for x in allc))
+        allc = shard.gather_counts(dist, dev, matches, n)
+        total_matches = sum(c for c, _ in allc)
+        total_bytes = sum(b for _, b in allc)
     else:
         total_matches, total_bytes = matches, n
     ms_step = ms / args.steps
