@@ -58,13 +58,13 @@ struct Smem {
   unsigned chunk2[2];
   unsigned long long cta_base;
   unsigned chunk;
-  uint32_t cand[NWORDS];
+  alignas(16) uint32_t cand[NWORDS];
   uint16_t queue[WARPS][QCAP];
   uint2 stage[2][WARPS][STG];
   unsigned wcount2[2][WARPS];
   int64_t meta_chunk[2], meta_gw[2];   // written by the compute warps, read by the writer warp
   unsigned meta_agg[2], meta_ovf[2];
-  uint32_t cmask[WARPS][4][32];  // per-lane class words of the tile a warp is evaluating
+  alignas(16) uint32_t cmask[WARPS][4][32];  // per-lane class words of the tile a warp is evaluating
   FlatDev flat;                  // copy of the flat program (indexed constant-bank loads are slow)
   alignas(128) uint8_t win[WIN + WINPAD];
   // followed by: uint32_t trans[nstates*256]; uint8_t eoi[nstates]; uint8_t lut[256]
@@ -333,79 +333,100 @@ __device__ __noinline__ uint32_t class_mask_rev_generic(const FlatDev& f, int cl
   return pack_rev(fl);
 }
 
-// 1024-bit helpers over the warp: lane l holds word l; word 0 = the LAST 32 bytes of the tile.
-// "shl1" moves markers one position towards lower addresses (higher bits); the bit entering
-// word 0 (a position past the tile) is 1: unknown territory is assumed to allow a match.
-__device__ __forceinline__ uint32_t shl1(uint32_t m, int lane) {
-  uint32_t dn = __shfl_up_sync(FULL, m, 1);
+// 2048-bit helpers over the warp for the flat evaluation: lane l holds the 64-bit word l of the
+// tile's bit-reversed position set; word 0 = the LAST 64 bytes of the 2 KB tile, bit (63-b) of a
+// word <=> byte b of its 64-byte piece.
+__device__ __forceinline__ uint64_t shl1_64(uint64_t m, int lane) {
+  // markers move one position towards lower addresses (higher bits); the bit entering word 0 (a
+  // position past the tile) is 1: unknown territory is assumed to allow a match
+  const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+  uint32_t dn = __shfl_up_sync(FULL, hi, 1);
   if (lane == 0) dn = FULL;
-  return __funnelshift_l(dn, m, 1);
+  return ((uint64_t)__funnelshift_l(lo, hi, 1) << 32) | __funnelshift_l(dn, lo, 1);
 }
-// s + c as one 1024-bit addition; carries resolved with two ballots.  (No carry-in: the unknown
-// territory past the tile is already represented by shl1's 1-bit, which seeds the last byte.)
-__device__ __forceinline__ uint32_t add1024(uint32_t s, uint32_t cc, int lane) {
-  const uint32_t sum = s + cc;
+__device__ __forceinline__ uint64_t add2048(uint64_t s, uint64_t cc, int lane) {
+  const uint64_t sum = s + cc;
   const uint32_t G = __ballot_sync(FULL, sum < s);
-  const uint32_t P = __ballot_sync(FULL, sum == FULL);
+  const uint32_t P = __ballot_sync(FULL, sum == ~0ull);
   const uint32_t A = G | P;
   const uint32_t carries = A ^ G ^ (A + G);  // bit l = carry into word l
   return sum + ((carries >> lane) & 1u);
 }
 
+__device__ __forceinline__ uint64_t class_mask_rev64(const FlatDev& f, int cls, const uint32_t (&w0)[8],
+                                                     const uint32_t (&w1)[8]) {
+  // bytes 0..31 of the piece land in the high word, bytes 32..63 in the low word
+  return ((uint64_t)class_mask_rev(f, cls, w0) << 32) | class_mask_rev(f, cls, w1);
+}
+
+constexpr int FTILE = 2048;                       // flat evaluation: 64 bytes per lane
+constexpr int NFTILES = (CH + OVER) / FTILE;
+
 __device__ void phase_a_flat(const Ctx& c) {
   const FlatDev& f = c.sm.flat;
-  uint32_t* cmw = &c.sm.cmask[c.warp][0][c.lane];  // class k of this lane at cmw[k*32]
-  for (int t = c.warp; t < NTILES; t += WARPS) {
-    const int chunk = 31 - c.lane;                // lane l holds the (31-l)-th 32-byte piece
-    const int rel = t * TILE + chunk * 32;        // relative to cbeg
+  uint64_t* cmw = reinterpret_cast<uint64_t*>(&c.sm.cmask[c.warp][0][0]) + c.lane;  // classes 2,3
+  const int nclasses = f.nclasses, rev_nops = f.rev_nops, init_cls = f.rev_init_class;
+  for (int t = c.warp; t < NFTILES; t += WARPS) {
+    const int piece = 31 - c.lane;                 // lane l holds the (31-l)-th 64-byte piece
+    const int rel = t * FTILE + piece * 64;        // relative to cbeg
     const uint8_t* p = c.sm.win + PRE + rel;
-    uint32_t w[8];
-    load32(p, w);
-    const uint32_t cm0 = class_mask_rev(f, 0, w);
-    cmw[0] = cm0;
-    for (int k = 1; k < f.nclasses; k++) cmw[k * 32] = class_mask_rev(f, k, w);
+    uint32_t w0[8], w1[8];
+    load32(p, w0);
+    load32(p + 32, w1);
+    const uint64_t cm0 = class_mask_rev64(f, 0, w0, w1);
+    uint64_t cm1 = 0;
+    if (nclasses > 1) cm1 = class_mask_rev64(f, 1, w0, w1);
+    for (int k = 2; k < nclasses; k++) cmw[(k - 2) * 32] = class_mask_rev64(f, k, w0, w1);
     // right-to-left evaluation: M = positions from which items k..end can match
-    uint32_t M = cmw[f.rev_init_class * 32];
-    for (int k = 0; k < f.rev_nops; k++) {
+    uint64_t M = init_cls == 0 ? cm0 : init_cls == 1 ? cm1 : cmw[(init_cls - 2) * 32];
+    for (int k = 0; k < rev_nops; k++) {
       const uint32_t op = f.rev_ops[k];
-      const uint32_t C = cmw[(op >> 2) * 32];
-      const uint32_t t1 = shl1(M, c.lane) & C;  // byte in class and the rest matches after it
-      const uint32_t kind = op & 3u;
+      const uint32_t cls = op >> 2, kind = op & 3u;
+      const uint64_t C = cls == 0 ? cm0 : cls == 1 ? cm1 : cmw[(cls - 2) * 32];
+      const uint64_t t1 = shl1_64(M, c.lane) & C;  // byte in class and the rest matches after it
       if (kind == 0) {
         M = t1;
       } else if (kind == 3) {
         M |= t1;
       } else {
-        const uint32_t plus = ~add1024(t1, C, c.lane) & C;  // extend leftwards through the run
+        const uint64_t plus = ~add2048(t1, C, c.lane) & C;  // extend leftwards through the run
         M = kind == 1 ? plus : (M | plus);
       }
     }
-    uint32_t first = FULL;
+    uint64_t first = ~0ull;
     if (c.a.filter.kind == F_RUNSTART) {
       // run starts of the FILTER set (ASCII digits for the reference's DigitPrefilter), which is
       // class 0 unless the pattern's first class is a strict subset such as [0-5]
-      uint32_t D = cm0;
+      uint64_t D = cm0;
       if (!f.first_is_filter) {
-        D = 0;
+        uint32_t dh = 0, dl = 0;
         for (int r = 0; r < c.a.filter.nranges; r++) {
           const uint32_t klo = swar_klo(c.a.filter.lo[r]), khi = swar_khi(c.a.filter.hi[r]);
-          uint32_t m = 0;
+          uint32_t mh = 0, ml = 0;
 #pragma unroll
-          for (int k = 0; k < 8; k++) m |= pack4(swar_in_range(w[k], klo, khi)) << (4 * k);
-          D |= __brev(m);
+          for (int k = 0; k < 8; k++) {
+            mh |= pack4(swar_in_range(w0[k], klo, khi)) << (4 * k);
+            ml |= pack4(swar_in_range(w1[k], klo, khi)) << (4 * k);
+          }
+          dh |= __brev(mh);
+          dl |= __brev(ml);
         }
+        D = ((uint64_t)dh << 32) | dl;
       }
-      uint32_t up = __shfl_down_sync(FULL, D, 1);
-      if (c.lane == 31) up = in_filter_set(c, c.sm.win[PRE + t * TILE - 1]) ? 1u : 0u;
-      first = D & ~((D >> 1) | (up << 31));
+      uint32_t up = __shfl_down_sync(FULL, (uint32_t)D, 1) & 1u;  // lowest address bit of the next piece
+      if (c.lane == 31) up = in_filter_set(c, c.sm.win[PRE + t * FTILE - 1]) ? 1u : 0u;
+      first = D & ~((D >> 1) | ((uint64_t)up << 63));
     }
-    uint32_t m = __brev(M & first);
+    const uint64_t R = M & first;
+    uint32_t m0 = __brev((uint32_t)(R >> 32));  // bytes 0..31 of the piece
+    uint32_t m1 = __brev((uint32_t)R);          // bytes 32..63
     const int64_t gp = c.cbeg + rel;
-    if (gp + 32 > c.a.n) {
-      const int64_t v = c.a.n - gp;
-      m = v <= 0 ? 0u : (m & ((1u << v) - 1u));
+    if (gp + 64 > c.a.n) {
+      const int64_t v0 = c.a.n - gp, v1 = c.a.n - gp - 32;
+      m0 = v0 <= 0 ? 0u : (v0 >= 32 ? m0 : (m0 & ((1u << v0) - 1u)));
+      m1 = v1 <= 0 ? 0u : (v1 >= 32 ? m1 : (m1 & ((1u << v1) - 1u)));
     }
-    c.sm.cand[t * 32 + chunk] = m;
+    *reinterpret_cast<uint2*>(&c.sm.cand[t * 64 + piece * 2]) = make_uint2(m0, m1);
   }
 }
 

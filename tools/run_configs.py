@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Times the BASELINE.json configs 2-5 on one B200 (device-resident input, CUDA events, 3 warm-up
++ 5 timed passes each; inputs are far larger than L2) and spot-checks each against the CPU oracle
+on a regenerated window.  Writes one JSON object per config.  Not the bench contract (bench.py is);
+this is the evidence for the other §8 rows."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+
+import coregex_b200 as cg
+from gpu_util import dev_corpus
+from oracle_lib import Oracle
+
+LIT16 = [b"error", b"warning", b"fatal", b"critical", b"timeout", b"refused", b"denied", b"panic",
+         b"overflow", b"invalid", b"missing", b"corrupt", b"expired", b"blocked", b"aborted", b"unknown"]
+LIT64 = [("k%02dz%s" % (i, "q" * (i % 4))).encode() for i in range(64)]
+GIB = 1 << 30
+scale = float(os.environ.get("CFG_SCALE", "1.0"))
+
+
+def timed(fn, steps=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run(name, pattern, kind, seed, nbytes, literals=None, submatch=False, window=64 * 4096):
+    bs = cg.SYNTH_BLOCK[kind]
+    nbytes -= nbytes % (bs * (window // bs) if window % bs == 0 else bs)
+    t = dev_corpus(kind, seed, nbytes, literals=literals)
+    r = cg.Compile(pattern)
+    stride = 2 * (r.NumSubexp() + 1) if submatch else 2
+    cap = nbytes // 40
+    out = torch.empty((cap, stride), dtype=torch.int64, device="cuda")
+    res = torch.zeros(2, dtype=torch.int64, device="cuda")
+    if submatch:
+        fn = lambda: r.scan_submatch_device(t.data_ptr(), nbytes, out.data_ptr(), cap, res.data_ptr())
+    else:
+        fn = lambda: r.scan_device(t.data_ptr(), nbytes, cg.MODE_FINDALL, out.data_ptr(), cap, res.data_ptr())
+    ms = timed(fn)
+    total = int(res[0].item())
+    # parity spot check on a regenerated window
+    o = Oracle(pattern)
+    wblocks = window // bs
+    b0 = (nbytes // bs // 2 // wblocks) * wblocks
+    hay = cg.synth_host(kind, seed, window, first_block=b0, literals=literals)
+    lo = b0 * bs
+    got = out[:total].cpu().numpy()
+    i0, i1 = np.searchsorted(got[:, 0], lo), np.searchsorted(got[:, 0], lo + window)
+    want = o.find_all_submatch(hay) if submatch else o.find_all(hay)
+    want = np.where(want >= 0, want + lo, want)
+    ok = bool(np.array_equal(got[i0:i1], want))
+    line = {"config": name, "pattern": pattern if len(pattern) < 80 else pattern[:77] + "...",
+            "bytes": nbytes, "matches": total, "ms": round(ms, 3), "GBps": round(nbytes / ms / 1e6, 1),
+            "engine": r.engine, "reference_strategy": r.strategy, "oracle_window_ok": ok,
+            "frac_hbm_input_only": round(nbytes / ms / 1e6 / 6570.3, 4)}
+    print(json.dumps(line), flush=True)
+    del t, out
+    torch.cuda.empty_cache()
+    return line
+
+
+if __name__ == "__main__":
+    run("C2 IP regex, 1 GB log lines", r"\d+\.\d+\.\d+\.\d+", cg.SYNTH_LOG, 0xC0FFEE + 2, int(1 * GIB * scale))
+    run("C3 16-literal Slim Teddy, 4 GB text", b"|".join(LIT16).decode(), cg.SYNTH_TEXT, 0xC0FFEE + 3,
+        int(4 * GIB * scale), literals=LIT16)
+    run("C4 as written (no groups), 10M x 80 B", r"\w+@\w+\.\w+", cg.SYNTH_EMAIL, 0xC0FFEE + 4,
+        int(80 * 10_000_000 * scale), submatch=True, window=80 * 4000)
+    run("C4 captures (\\w+)@(\\w+)\\.(\\w+), 10M x 80 B", r"(\w+)@(\w+)\.(\w+)", cg.SYNTH_EMAIL, 0xC0FFEE + 4,
+        int(80 * 10_000_000 * scale), submatch=True, window=80 * 4000)
+    run("C5 shape: 64-literal Fat Teddy, 8 GB shard (1 of 8)", b"|".join(LIT64).decode(), cg.SYNTH_TEXT,
+        0xC0FFEE + 5, int(8 * GIB * scale), literals=LIT64)
