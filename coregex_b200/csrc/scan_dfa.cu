@@ -64,7 +64,7 @@ struct Smem {
   unsigned wcount2[2][WARPS];
   int64_t meta_chunk[2], meta_gw[2];   // written by the compute warps, read by the writer warp
   unsigned meta_agg[2], meta_ovf[2];
-  alignas(16) uint32_t cmask[WARPS][4][32];  // per-lane class words of the tile a warp is evaluating
+  alignas(16) uint32_t cmask[WARPS][8][32];  // per-lane class words of the tile a warp is evaluating
   FlatDev flat;                  // copy of the flat program (indexed constant-bank loads are slow)
   alignas(128) uint8_t win[WIN + WINPAD];
   // followed by: uint32_t trans[nstates*256]; uint8_t eoi[nstates]; uint8_t lut[256]
@@ -362,72 +362,97 @@ __device__ __forceinline__ uint64_t class_mask_rev64(const FlatDev& f, int cls, 
 constexpr int FTILE = 2048;                       // flat evaluation: 64 bytes per lane
 constexpr int NFTILES = (CH + OVER) / FTILE;
 
+static_assert(NFTILES == 2 * WARPS, "each scanning warp evaluates exactly two 2 KB tiles per chunk");
+
+// classes 0 and 1 of one 64-byte piece (bit-reversed), classes 2,3 parked in shared memory
+__device__ __forceinline__ void flat_classify(const FlatDev& f, int nclasses, const uint8_t* p, uint64_t* cmw,
+                                              uint64_t& cm0, uint64_t& cm1, uint64_t& runset, const Ctx& c) {
+  uint32_t w0[8], w1[8];
+  load32(p, w0);
+  load32(p + 32, w1);
+  cm0 = class_mask_rev64(f, 0, w0, w1);
+  cm1 = 0;
+  if (nclasses > 1) cm1 = class_mask_rev64(f, 1, w0, w1);
+  for (int k = 2; k < nclasses; k++) cmw[(k - 2) * 32] = class_mask_rev64(f, k, w0, w1);
+  runset = cm0;
+  if (c.a.filter.kind == F_RUNSTART && !f.first_is_filter) {
+    // run starts are those of the FILTER set (ASCII digits for the reference's DigitPrefilter),
+    // which differs from class 0 when the pattern starts with a strict subset such as [0-5]
+    uint32_t dh = 0, dl = 0;
+    for (int r = 0; r < c.a.filter.nranges; r++) {
+      const uint32_t klo = swar_klo(c.a.filter.lo[r]), khi = swar_khi(c.a.filter.hi[r]);
+      uint32_t mh = 0, ml = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        mh |= pack4(swar_in_range(w0[k], klo, khi)) << (4 * k);
+        ml |= pack4(swar_in_range(w1[k], klo, khi)) << (4 * k);
+      }
+      dh |= __brev(mh);
+      dl |= __brev(ml);
+    }
+    runset = ((uint64_t)dh << 32) | dl;
+  }
+}
+
+__device__ __forceinline__ void flat_store(const Ctx& c, int t, int piece, uint64_t R) {
+  uint32_t m0 = __brev((uint32_t)(R >> 32));  // bytes 0..31 of the piece
+  uint32_t m1 = __brev((uint32_t)R);          // bytes 32..63
+  const int64_t gp = c.cbeg + t * FTILE + piece * 64;
+  if (gp + 64 > c.a.n) {
+    const int64_t v0 = c.a.n - gp, v1 = c.a.n - gp - 32;
+    m0 = v0 <= 0 ? 0u : (v0 >= 32 ? m0 : (m0 & ((1u << v0) - 1u)));
+    m1 = v1 <= 0 ? 0u : (v1 >= 32 ? m1 : (m1 & ((1u << v1) - 1u)));
+  }
+  *reinterpret_cast<uint2*>(&c.sm.cand[t * 64 + piece * 2]) = make_uint2(m0, m1);
+}
+
+// The warp's two tiles (t = warp and warp + WARPS) are evaluated together: the two marker chains
+// are independent, which gives the scheduler two dependency chains per warp to interleave.
 __device__ void phase_a_flat(const Ctx& c) {
   const FlatDev& f = c.sm.flat;
-  uint64_t* cmw = reinterpret_cast<uint64_t*>(&c.sm.cmask[c.warp][0][0]) + c.lane;  // classes 2,3
+  uint64_t* cmwa = reinterpret_cast<uint64_t*>(&c.sm.cmask[c.warp][0][0]) + c.lane;  // classes 2,3 tile a
+  uint64_t* cmwb = cmwa + 64;                                                          // ... tile b
   const int nclasses = f.nclasses, rev_nops = f.rev_nops, init_cls = f.rev_init_class;
-  for (int t = c.warp; t < NFTILES; t += WARPS) {
-    const int piece = 31 - c.lane;                 // lane l holds the (31-l)-th 64-byte piece
-    const int rel = t * FTILE + piece * 64;        // relative to cbeg
-    const uint8_t* p = c.sm.win + PRE + rel;
-    uint32_t w0[8], w1[8];
-    load32(p, w0);
-    load32(p + 32, w1);
-    const uint64_t cm0 = class_mask_rev64(f, 0, w0, w1);
-    uint64_t cm1 = 0;
-    if (nclasses > 1) cm1 = class_mask_rev64(f, 1, w0, w1);
-    for (int k = 2; k < nclasses; k++) cmw[(k - 2) * 32] = class_mask_rev64(f, k, w0, w1);
-    // right-to-left evaluation: M = positions from which items k..end can match
-    uint64_t M = init_cls == 0 ? cm0 : init_cls == 1 ? cm1 : cmw[(init_cls - 2) * 32];
-    for (int k = 0; k < rev_nops; k++) {
-      const uint32_t op = f.rev_ops[k];
-      const uint32_t cls = op >> 2, kind = op & 3u;
-      const uint64_t C = cls == 0 ? cm0 : cls == 1 ? cm1 : cmw[(cls - 2) * 32];
-      const uint64_t t1 = shl1_64(M, c.lane) & C;  // byte in class and the rest matches after it
-      if (kind == 0) {
-        M = t1;
-      } else if (kind == 3) {
-        M |= t1;
-      } else {
-        const uint64_t plus = ~add2048(t1, C, c.lane) & C;  // extend leftwards through the run
-        M = kind == 1 ? plus : (M | plus);
-      }
+  const int ta = c.warp, tb = c.warp + WARPS;
+  const int piece = 31 - c.lane;  // lane l holds the (31-l)-th 64-byte piece of a tile
+  uint64_t a0, a1, ra, b0, b1, rb;
+  flat_classify(f, nclasses, c.sm.win + PRE + ta * FTILE + piece * 64, cmwa, a0, a1, ra, c);
+  flat_classify(f, nclasses, c.sm.win + PRE + tb * FTILE + piece * 64, cmwb, b0, b1, rb, c);
+  // right-to-left evaluation: M = positions from which items k..end can match
+  uint64_t Ma = init_cls == 0 ? a0 : init_cls == 1 ? a1 : cmwa[(init_cls - 2) * 32];
+  uint64_t Mb = init_cls == 0 ? b0 : init_cls == 1 ? b1 : cmwb[(init_cls - 2) * 32];
+  for (int k = 0; k < rev_nops; k++) {
+    const uint32_t op = f.rev_ops[k];
+    const uint32_t cls = op >> 2, kind = op & 3u;
+    const uint64_t Ca = cls == 0 ? a0 : cls == 1 ? a1 : cmwa[(cls - 2) * 32];
+    const uint64_t Cb = cls == 0 ? b0 : cls == 1 ? b1 : cmwb[(cls - 2) * 32];
+    const uint64_t ua = shl1_64(Ma, c.lane) & Ca;  // byte in class and the rest matches after it
+    const uint64_t ub = shl1_64(Mb, c.lane) & Cb;
+    if (kind == 0) {
+      Ma = ua;
+      Mb = ub;
+    } else if (kind == 3) {
+      Ma |= ua;
+      Mb |= ub;
+    } else {
+      const uint64_t pa = ~add2048(ua, Ca, c.lane) & Ca;  // extend leftwards through the run
+      const uint64_t pb = ~add2048(ub, Cb, c.lane) & Cb;
+      Ma = kind == 1 ? pa : (Ma | pa);
+      Mb = kind == 1 ? pb : (Mb | pb);
     }
-    uint64_t first = ~0ull;
-    if (c.a.filter.kind == F_RUNSTART) {
-      // run starts of the FILTER set (ASCII digits for the reference's DigitPrefilter), which is
-      // class 0 unless the pattern's first class is a strict subset such as [0-5]
-      uint64_t D = cm0;
-      if (!f.first_is_filter) {
-        uint32_t dh = 0, dl = 0;
-        for (int r = 0; r < c.a.filter.nranges; r++) {
-          const uint32_t klo = swar_klo(c.a.filter.lo[r]), khi = swar_khi(c.a.filter.hi[r]);
-          uint32_t mh = 0, ml = 0;
-#pragma unroll
-          for (int k = 0; k < 8; k++) {
-            mh |= pack4(swar_in_range(w0[k], klo, khi)) << (4 * k);
-            ml |= pack4(swar_in_range(w1[k], klo, khi)) << (4 * k);
-          }
-          dh |= __brev(mh);
-          dl |= __brev(ml);
-        }
-        D = ((uint64_t)dh << 32) | dl;
-      }
-      uint32_t up = __shfl_down_sync(FULL, (uint32_t)D, 1) & 1u;  // lowest address bit of the next piece
-      if (c.lane == 31) up = in_filter_set(c, c.sm.win[PRE + t * FTILE - 1]) ? 1u : 0u;
-      first = D & ~((D >> 1) | ((uint64_t)up << 63));
-    }
-    const uint64_t R = M & first;
-    uint32_t m0 = __brev((uint32_t)(R >> 32));  // bytes 0..31 of the piece
-    uint32_t m1 = __brev((uint32_t)R);          // bytes 32..63
-    const int64_t gp = c.cbeg + rel;
-    if (gp + 64 > c.a.n) {
-      const int64_t v0 = c.a.n - gp, v1 = c.a.n - gp - 32;
-      m0 = v0 <= 0 ? 0u : (v0 >= 32 ? m0 : (m0 & ((1u << v0) - 1u)));
-      m1 = v1 <= 0 ? 0u : (v1 >= 32 ? m1 : (m1 & ((1u << v1) - 1u)));
-    }
-    *reinterpret_cast<uint2*>(&c.sm.cand[t * 64 + piece * 2]) = make_uint2(m0, m1);
   }
+  if (c.a.filter.kind == F_RUNSTART) {
+    uint32_t upa = __shfl_down_sync(FULL, (uint32_t)ra, 1) & 1u;  // lowest-address bit of the next piece
+    uint32_t upb = __shfl_down_sync(FULL, (uint32_t)rb, 1) & 1u;
+    if (c.lane == 31) {
+      upa = in_filter_set(c, c.sm.win[PRE + ta * FTILE - 1]) ? 1u : 0u;
+      upb = in_filter_set(c, c.sm.win[PRE + tb * FTILE - 1]) ? 1u : 0u;
+    }
+    Ma &= ra & ~((ra >> 1) | ((uint64_t)upa << 63));
+    Mb &= rb & ~((rb >> 1) | ((uint64_t)upb << 63));
+  }
+  flat_store(c, ta, piece, Ma);
+  flat_store(c, tb, piece, Mb);
 }
 
 // first position q >= from with q == 0 or byte(q-1) == delim, searched inside the window only
