@@ -47,6 +47,14 @@ LazyDFA::LazyDFA(const NFA* nfa, LazyConfig cfg) : nfa_(nfa), cfg_(cfg) {
   }
   for (auto& row : start_)
     for (auto& x : row) x = -1;
+  stride_ = nfa->alphabet_len;
+}
+
+int LazyDFA::newState(DState&& s) {
+  int id = (int)states_.size();
+  states_.push_back(std::move(s));
+  flat_.resize((size_t)(id + 1) * stride_, -2);
+  return id;
 }
 
 // reference dfa/lazy/builder.go:245-293: add-on-pop, push right then left
@@ -189,34 +197,32 @@ int LazyDFA::determinize(int cur, uint8_t b) {
   std::vector<StateID> next = move(cur_nfa, b, states_[cur].from_word, bam);
   bool is_match = source_has_match;
   if (next.empty() && !is_match) {
-    states_[cur].trans[cls] = -1;
+    flat_[(size_t)cur * stride_ + cls] = -1;
     return -1;
   }
   bool next_from_word = isWordByte(b);
   Key key = makeKey(next, next_from_word, is_match);
   auto it = cache_.find(key);
   if (it != cache_.end()) {
-    states_[cur].trans[cls] = it->second;
+    flat_[(size_t)cur * stride_ + cls] = it->second;
     return it->second;
   }
   DState ns;
   ns.nfa = next;
   ns.is_match = is_match;
   ns.from_word = next_from_word;
-  ns.trans.assign(nfa_->alphabet_len, -2);
   if (has_wb_ && !is_match) {
     ns.match_at_wb = containsMatch(resolveWB(next, true));
     ns.match_at_nwb = containsMatch(resolveWB(next, false));
   }
-  int id = (int)states_.size();
-  states_.push_back(std::move(ns));
+  int id = newState(std::move(ns));
   cache_[key] = id;
-  states_[cur].trans[cls] = id;
+  flat_[(size_t)cur * stride_ + cls] = id;
   return id;
 }
 
 int LazyDFA::step(int sid, uint8_t b) {
-  int32_t t = states_[sid].trans[nfa_->byte_classes[b]];
+  int32_t t = flat_[(size_t)sid * stride_ + nfa_->byte_classes[b]];
   if (t == -2) return determinize(sid, b);
   return t;
 }
@@ -238,11 +244,9 @@ int LazyDFA::getStart(const uint8_t* h, int64_t pos, bool anchored) {
   DState ns;
   ns.nfa = set;
   ns.from_word = from_word;
-  ns.trans.assign(nfa_->alphabet_len, -2);
   // NOTE: start states do not get matchAtWordBoundary flags in the reference
   // (ComputeStartStateWithStride does not set them) — keep false.
-  int id = (int)states_.size();
-  states_.push_back(std::move(ns));
+  int id = newState(std::move(ns));
   cache_[key] = id;
   slot = id;
   return id;
@@ -277,6 +281,19 @@ int64_t LazyDFA::SearchAtAnchored(const uint8_t* h, int64_t n, int64_t at) {
   if (at == n) return matchesEmpty() ? at : -1;
   int sid = getStart(h, at, true);
   int64_t last = -1;
+  if (!has_wb_) {
+    // hot loop (reference lazy.go:251-313 without the word-boundary branch)
+    const uint8_t* cls = nfa_->byte_classes;
+    for (int64_t pos = at; pos < n; pos++) {
+      int32_t nx = flat_[(size_t)sid * stride_ + cls[h[pos]]];
+      if (nx == -2) nx = determinize(sid, h[pos]);
+      if (nx < 0) return last;
+      sid = nx;
+      if (states_[sid].is_match) last = pos;
+    }
+    if (checkEOI(sid)) return n;
+    return last;
+  }
   for (int64_t pos = at; pos < n; pos++) {
     uint8_t b = h[pos];
     if (has_wb_ && wbFast(states_[sid], b)) return pos;
@@ -330,9 +347,7 @@ int64_t LazyDFA::SearchReverse(const uint8_t* h, int64_t n, int64_t start, int64
       DState ns;
       ns.nfa = set;
       ns.from_word = from_word;
-      ns.trans.assign(nfa_->alphabet_len, -2);
-      sid = (int)states_.size();
-      states_.push_back(std::move(ns));
+      sid = newState(std::move(ns));
       cache_[key] = sid;
     }
     slot = sid;

@@ -39,7 +39,8 @@ struct DState {
   bool is_match = false;     // delayed match tag
   bool from_word = false;
   bool match_at_wb = false, match_at_nwb = false;
-  std::vector<int32_t> trans;  // per class: -2 unknown, -1 dead, else state index
+  // transitions live in LazyDFA::flat_ (state*stride + class): -2 unknown, -1 dead, else state
+  // index — the flat layout of reference dfa/lazy/cache.go:44-50 so the hot loop is two loads
 };
 
 struct LazyConfig {
@@ -68,7 +69,10 @@ class LazyDFA {
   LazyConfig cfg_;
   bool has_wb_ = false, has_endline_ = false;
   std::vector<DState> states_;
+  std::vector<int32_t> flat_;
+  int stride_ = 1;
   std::map<Key, int> cache_;
+  int newState(DState&& s);
   int start_[2][kStartKinds];
 
   void closureInto(std::vector<StateID>& set, std::vector<uint8_t>& in_set, StateID seed,
