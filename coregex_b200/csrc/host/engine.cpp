@@ -288,6 +288,15 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
         c->engine_name = "dfa-lut";
       }
       flat_first();
+      // A flat pattern that opens with C+ and whose possible first bytes are exactly C: a match
+      // starting inside a run of C implies one starting at the run's first byte, so only run
+      // starts (and resume positions after a match, handled by the replay) can begin a match.
+      if (c->flat.nops && c->flat.first_is_filter && c->flat.op_kind[0] == 1 &&
+          c->filter_kind == F_BYTESET) {
+        c->filter_kind = F_RUNSTART;
+        c->skip_safe = true;
+        c->engine_name = "dfa-runstart";
+      }
     }
     if (c->flat.nops) c->engine_name += "+flat";
   }

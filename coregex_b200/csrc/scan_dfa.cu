@@ -435,8 +435,10 @@ __device__ void phase_a_flat(const Ctx& c) {
       Ma |= ua;
       Mb |= ub;
     } else {
-      const uint64_t pa = ~add2048(ua, Ca, c.lane) & Ca;  // extend leftwards through the run
-      const uint64_t pb = ~add2048(ub, Cb, c.lane) & Cb;
+      // extend leftwards through the run; a second marker inside one run survives the carry of
+      // the first as a 1 in the sum, so the markers themselves are OR-ed back
+      const uint64_t pa = (~add2048(ua, Ca, c.lane) & Ca) | ua;
+      const uint64_t pb = (~add2048(ub, Cb, c.lane) & Cb) | ub;
       Ma = kind == 1 ? pa : (Ma | pa);
       Mb = kind == 1 ? pb : (Mb | pb);
     }
@@ -540,6 +542,7 @@ __device__ int serial_chain(const Ctx& c, Emitter<DIRECT>& em, int pos_i, int la
     const int64_t n = c.a.n;
     int64_t pos = c.gw + pos_i;
     const int64_t lastc = c.gw + last_cand;
+    bool after_match = false;
     while (pos < n) {
       int64_t d = pos;  // reference: digitPos = prefilter.Find(haystack, pos)
       bool stop = false;
@@ -556,12 +559,18 @@ __device__ int serial_chain(const Ctx& c, Emitter<DIRECT>& em, int pos_i, int la
         pos = d;
         break;
       }
-      if (!to_line_end && d > lastc) break;  // chain position unchanged
+      // Later candidates belong to later batches — except a resume position in the middle of a
+      // run, which the run-start filter never lists: it is tried here, right after its match.
+      const bool mid_run = after_match && d == pos && c.a.filter.kind == F_RUNSTART && d > 0 &&
+                           in_filter_set(c, byte_at(c, d - 1));
+      if (!to_line_end && d > lastc && !mid_run) break;  // chain position unchanged
+      after_match = false;
       const int64_t e = dfa_walk_slow(c, d);
       if (e >= 0) {
         em.put(em.nkept + added, (int)(d - c.gw), (int)(e - c.gw));
         added++;
         pos = e > d ? e : d + 1;
+        after_match = true;
       } else {
         pos = d + 1;
         if (c.a.filter.kind == F_RUNSTART)
@@ -597,8 +606,42 @@ __device__ __forceinline__ int process_batch(const Ctx& c, Emitter<DIRECT>& em, 
   if (c.a.skip_safe && ok && c.gw + end < c.a.n) bad |= in_filter_set(c, byte_at(c, c.gw + end));
   // literal candidates inside the last 16 bytes of the haystack may fall under the reference's
   // scalar verify order: let the exact replay decide
-  if (c.a.engine == SEL_TEDDY) bad |= valid && c.gw + cand > c.a.n - 16;
-  if (__any_sync(FULL, bad)) {
+  bool replay = false;
+  if (c.a.engine == SEL_TEDDY) replay = valid && c.gw + cand > c.a.n - 16;
+  if (c.a.filter.kind == F_RUNSTART) replay |= bad;  // a resume position inside a run is no candidate
+  replay = __any_sync(FULL, replay);
+  if (!replay && __any_sync(FULL, bad)) {
+    // Candidates overlap kept matches.  The filter is exhaustive (every possible match start is
+    // a candidate), so the reference loop (meta/findall.go:176-290: search from the previous end,
+    // take the first start that matches) is a walk over "first matching candidate at or after my
+    // end" links.  Links by binary search over the (ascending) candidates, then follow the chain.
+    const int cv = valid ? cand : 0x7fffffff;
+    auto first_ok_at_or_after = [&](int t) {
+      int lo = 0;
+#pragma unroll
+      for (int s = 16; s; s >>= 1) {
+        const int probe = __shfl_sync(FULL, cv, lo + s - 1);
+        if (probe < t) lo += s;
+      }
+      const int last = __shfl_sync(FULL, cv, lo);
+      const unsigned m = last < t ? 0u : okmask & (~0u << lo);
+      return m ? __ffs(m) - 1 : 32;
+    };
+    const int nxt = first_ok_at_or_after(ok ? end : 0x7fffffff);
+    int cur = first_ok_at_or_after(kept_end);
+    unsigned keptmask = 0;
+    while (cur < 32) {
+      keptmask |= 1u << cur;
+      cur = __shfl_sync(FULL, nxt, cur);
+    }
+    if (!keptmask) return kept_end;
+    if (keptmask >> c.lane & 1u) em.put(em.nkept + __popc(keptmask & ((1u << c.lane) - 1u)), cand, end);
+    const unsigned add = __popc(keptmask);
+    if (!DIRECT && em.nkept + add > STG) em.overflow = true;
+    em.nkept += add;
+    return __shfl_sync(FULL, end, 31 - __clz(keptmask));
+  }
+  if (replay) {
     // replay from the chain position through the last candidate of this batch
     const unsigned vmask = __ballot_sync(FULL, valid);
     const int last_cand = __shfl_sync(FULL, cand, 31 - __clz(vmask));

@@ -178,3 +178,49 @@ def test_full_size_properties_1gb():
         want = o.find_all(hay) + lo
         i0, i1 = np.searchsorted(s, lo), np.searchsorted(s, lo + win)
         assert np.array_equal(pairs[i0:i1], want)
+
+
+# Candidates that overlap kept matches: resolved on the GPU by following "first matching candidate
+# at or after my end" links (exhaustive filters) or by the serial replay (run-start filters).
+OVERLAP = [
+    (r"\w+@\w+\.\w+", "email"),
+    (r"[a-c][a-z]*x", "lower"),
+    (r"\d\d\d", "digits"),
+    (r"(ab|abc|b)c*", "abc"),
+    (r"aa", "as"),
+    (r"[a-z]+\d", "lowerdigit"),
+    (r"\d+\.\d", "dotted"),
+    (r"[0-5]+\.\d+", "dotted"),
+    (r"x[a-z]{2,5}", "lower"),
+]
+
+
+def _overlap_text(kind, rng, n):
+    if kind == "email":
+        words = [b"alice", b"bob", b"carol_x", b"d9", b"example", b"mail", b"corp", b"com", b"org", b"io"]
+        parts = []
+        for _ in range(n // 24):
+            k = rng.integers(0, 5)
+            w = lambda: words[rng.integers(0, len(words))]
+            parts.append([w() + b"@" + w() + b"." + w(), w() + b"@" + w(), w() + b" " + w(),
+                          b"@" + w() + b"." + w() + b"@" + w() + b"." + w(), w() + b"." + w()][k])
+            parts.append(b"\n" if rng.integers(0, 4) == 0 else b" ")
+        return b"".join(parts)
+    alpha = {"lower": b"abcxyz  \n", "digits": b"0123456789 \n", "abc": b"abcabc \n", "as": b"aaaab \n",
+             "lowerdigit": b"abz09 \n", "dotted": b"0123456789.. \n"}[kind]
+    return bytes(np.frombuffer(alpha, dtype=np.uint8)[rng.integers(0, len(alpha), n)])
+
+
+@pytest.mark.parametrize("pat,kind", OVERLAP)
+def test_overlapping_candidates_chain(pat, kind):
+    rng = np.random.default_rng(11)
+    o = Oracle(pat)
+    for n in (200, 5000, 150000):
+        check(pat, _overlap_text(kind, rng, n), o)
+
+
+def test_overlap_chain_dense_single_line():
+    # every byte a candidate, matches back to back and overlapping candidates inside each match
+    check(r"\d\d\d", b"1234567890" * 9000)
+    check(r"aa", b"a" * 70001)
+    check(r"[a-c][a-z]*x", b"abcabcx" * 9000 + b"\n" + b"aaaa" * 5000)
