@@ -97,6 +97,8 @@ __device__ __forceinline__ uint8_t byte_at(const Ctx& c, int64_t p) {
 
 __device__ __forceinline__ bool in_filter_set(const Ctx& c, uint8_t b) {
   if (c.a.filter.kind == F_LUT) return c.lut[b] != 0;
+  if (c.a.filter.nranges == 1)
+    return (unsigned)(b - c.a.filter.lo[0]) <= (unsigned)(c.a.filter.hi[0] - c.a.filter.lo[0]);
   bool r = false;
   for (int k = 0; k < c.a.filter.nranges; k++) r |= (b >= c.a.filter.lo[k] && b <= c.a.filter.hi[k]);
   return r;
@@ -139,12 +141,16 @@ __device__ __forceinline__ int dfa_walk(const Ctx& c, int i0) {
   }
   int last = -1, i = i0;
   const char* tb = reinterpret_cast<const char*>(c.trans);
+  // the next byte is fetched one step ahead so that only the transition load is on the
+  // loop-carried dependency chain (win[] is readable WINPAD bytes past the last valid byte)
+  uint32_t b = c.sm.win[i];
   while (sp) {
-    const uint32_t b = c.sm.win[i];
+    const uint32_t nb = c.sm.win[i + 1];
     const uint32_t e = *reinterpret_cast<const uint32_t*>(tb + sp + b * 4);
     if ((int)e < 0) last = i;
     sp = e & 0x7fffffffu;
     i++;
+    b = nb;
   }
   if (i > c.wend) {
     // consumed a sentinel: the walk left the window (long line) or hit end of input
@@ -666,50 +672,68 @@ __device__ void phase_b(const Ctx& c, Emitter<DIRECT>& em) {
   int qlen = 0;
   const int lo_rel = (int)(lo - c.cbeg);
   const int hi_rel = (int)(hi_b - c.cbeg);
-  // One bitmap word per lane and step (1 KB of input).  A step that holds more candidates than
-  // the queue can take (dense data) is split into two half-warp passes.
-  for (int wbase = lo_rel >> 5; wbase * 32 < hi_rel; wbase += 32) {
-    const int widx = wbase + c.lane;
-    uint32_t word_all = 0;
-    if (widx < NWORDS && widx * 32 < hi_rel) {
-      word_all = c.sm.cand[widx];
-      const int b0 = widx * 32;
-      if (b0 < lo_rel) word_all &= ~0u << (lo_rel - b0);
-      if (b0 + 32 > hi_rel) word_all &= (1u << (hi_rel - b0)) - 1u;
+  // Four bitmap words per lane and step (4 KB of input): count, warp-scan, then every lane appends
+  // its own candidates to the queue in position order.  A step that holds more candidates than the
+  // queue can take (dense data) is split into passes of four lanes each.
+  const int w_lo = lo_rel >> 5, w_hi = (hi_rel + 31) >> 5;  // bitmap words [w_lo, w_hi)
+  auto drain = [&]() {
+    __syncwarp();
+    int head = 0;
+    while (qlen - head >= 32) {
+      kept_end = process_batch<DIRECT>(c, em, q[head + c.lane], true, kept_end);
+      head += 32;
     }
-    const unsigned nz = __ballot_sync(FULL, word_all != 0);
-    if (!nz) continue;
-    const bool sparse = !__any_sync(FULL, (word_all & (word_all - 1)) != 0);
-    for (int pass = 0; pass < (sparse ? 1 : 2); pass++) {
-      uint32_t word = word_all;
-      if (sparse) {
-        // at most one candidate per word -> queue offsets straight from the ballot
-        if (word) q[qlen + __popc(nz & ((1u << c.lane) - 1u))] = (uint16_t)(widx * 32 + __ffs(word) - 1 + PRE);
-        qlen += __popc(nz);
-      } else {
-        if ((c.lane >> 4) != pass) word = 0;
-        int total;
-        int off = qlen + warp_excl_scan(__popc(word), c.lane, total);
-        while (word) {
-          const int b = __ffs(word) - 1;
-          word &= word - 1;
-          q[off++] = (uint16_t)(widx * 32 + b + PRE);  // window index
-        }
-        qlen += total;
-      }
+    if (head) {
+      const int rem = qlen - head;
+      const uint16_t tmp = c.lane < rem ? q[head + c.lane] : 0;
       __syncwarp();
-      int head = 0;
-      while (qlen - head >= 32) {
-        kept_end = process_batch<DIRECT>(c, em, q[head + c.lane], true, kept_end);
-        head += 32;
+      if (c.lane < rem) q[c.lane] = tmp;
+      qlen = rem;
+      __syncwarp();
+    }
+  };
+  for (int wbase = w_lo & ~3; wbase < w_hi; wbase += 128) {
+    const int w0 = wbase + 4 * c.lane;
+    uint4 ld = make_uint4(0u, 0u, 0u, 0u);
+    if (w0 < w_hi && w0 < NWORDS) ld = *reinterpret_cast<const uint4*>(&c.sm.cand[w0]);
+    uint32_t wd[4] = {ld.x, ld.y, ld.z, ld.w};
+    if (w0 * 32 < lo_rel || (w0 + 4) * 32 > hi_rel) {  // a lane at either end of the owned range
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int lo_sh = lo_rel - (w0 + k) * 32, hi_sh = hi_rel - (w0 + k) * 32;
+        if (lo_sh > 0) wd[k] = lo_sh >= 32 ? 0u : wd[k] & (~0u << lo_sh);
+        if (hi_sh < 32) wd[k] = hi_sh <= 0 ? 0u : wd[k] & ((1u << hi_sh) - 1u);
       }
-      if (head) {
-        const int rem = qlen - head;
-        const uint16_t tmp = c.lane < rem ? q[head + c.lane] : 0;
-        __syncwarp();
-        if (c.lane < rem) q[c.lane] = tmp;
-        qlen = rem;
-        __syncwarp();
+    }
+    const int cnt = __popc(wd[0]) + __popc(wd[1]) + __popc(wd[2]) + __popc(wd[3]);
+    int total;
+    const int excl = warp_excl_scan(cnt, c.lane, total);
+    if (!total) continue;
+    auto append = [&](int off) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t v = wd[k];
+        const int base = (w0 + k) * 32 + PRE;  // window index of bit 0
+        while (v) {
+          q[off++] = (uint16_t)(base + __ffs(v) - 1);
+          v &= v - 1;
+        }
+      }
+    };
+    if (qlen + total <= QCAP) {
+      append(qlen + excl);
+      qlen += total;
+      drain();
+    } else {
+      // dense: four lanes (512 bytes, at most 512 new entries on top of a remainder < 32) per pass
+      for (int pass = 0; pass < 8; pass++) {
+        const bool mine = (c.lane >> 2) == pass;
+        int tot2;
+        const int off = qlen + warp_excl_scan(mine ? cnt : 0, c.lane, tot2);
+        if (!tot2) continue;
+        if (mine) append(off);
+        qlen += tot2;
+        drain();
       }
     }
   }
