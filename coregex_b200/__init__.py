@@ -62,6 +62,7 @@ def _load():
     L.cgx_count.argtypes = [vp, u8p, sz, i64, C.POINTER(sz)]
     L.cgx_find_all_submatch_index.argtypes = [vp, u8p, sz, i64, C.c_void_p, sz, C.POINTER(sz)]
     L.cgx_scan_device.argtypes = [vp, u8p, sz, i64, C.c_int, C.c_void_p, sz, C.c_void_p, C.c_void_p]
+    L.cgx_scan_shard_device.argtypes = [vp, u8p, sz, i64, i64, C.c_int, C.c_void_p, sz, C.c_void_p, C.c_void_p]
     L.cgx_scan_submatch_device.argtypes = [vp, u8p, sz, i64, C.c_void_p, sz, C.c_void_p, C.c_void_p]
     L.cgx_launch_count.restype = C.c_uint64
     L.cgx_launch_count.argtypes = [vp]
@@ -199,10 +200,11 @@ class Regex:
 
     # -- device-resident API -----------------------------------------------------------------------
     def scan_device(self, d_ptr, length, mode=MODE_FINDALL, out_ptr=0, cap_pairs=0, result_ptr=0,
-                    base_offset=0, stream=0):
-        """Enqueue a scan of device memory [d_ptr, d_ptr+length).  Pointers are raw ints."""
-        _check(_lib.cgx_scan_device(self._h, d_ptr, length, base_offset, mode, out_ptr, cap_pairs,
-                                    result_ptr, stream))
+                    base_offset=0, stream=0, bytes_after=0):
+        """Enqueue a scan of device memory [d_ptr, d_ptr+length).  Pointers are raw ints.
+        base_offset / bytes_after place the buffer inside a larger logical haystack (a shard)."""
+        _check(_lib.cgx_scan_shard_device(self._h, d_ptr, length, base_offset, bytes_after, mode, out_ptr,
+                                          cap_pairs, result_ptr, stream))
 
     def scan_submatch_device(self, d_ptr, length, out_ptr, cap_matches, result_ptr, base_offset=0,
                              stream=0):

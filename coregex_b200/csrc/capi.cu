@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -71,7 +72,39 @@ struct cgx_regex {
   TeddyDev teddy_dev;
   // per-call scratch (serialised by mu)
   DevBuf d_ticket_total, d_status, d_hay, d_out, d_pairs, d_pike;
+  // pipelined host path: two haystack/output slots, three streams, pinned per-slot results
+  DevBuf d_hay2[2], d_out2[2];
+  cudaStream_t s_h2d = nullptr, s_scan = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_scan[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  uint64_t* pinned_res = nullptr;  // [2][2]
   std::atomic<uint64_t> launches{0};
+
+  int ensure_pipeline() {
+    if (s_h2d) return CGX_OK;
+    CU(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s_scan, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      CU(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ev_scan[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming));
+    }
+    CU(cudaHostAlloc((void**)&pinned_res, 4 * sizeof(uint64_t), cudaHostAllocDefault));
+    return CGX_OK;
+  }
+  ~cgx_regex() {
+    if (s_h2d) {
+      cudaStreamDestroy(s_h2d);
+      cudaStreamDestroy(s_scan);
+      cudaStreamDestroy(s_d2h);
+      for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(ev_h2d[i]);
+        cudaEventDestroy(ev_scan[i]);
+        cudaEventDestroy(ev_d2h[i]);
+      }
+      cudaFreeHost(pinned_res);
+    }
+  }
 
   int ensure_device() {
     if (device >= 0) return CGX_OK;
@@ -167,7 +200,7 @@ int cgx_num_captures(const cgx_regex* re) { return re->c->prog.num_captures; }
 uint64_t cgx_launch_count(const cgx_regex* re) { return re->launches.load(); }
 
 static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base, int mode,
-                       int64_t* d_out, size_t cap, uint64_t* d_result, cudaStream_t st) {
+                       int64_t* d_out, size_t cap, uint64_t* d_result, cudaStream_t st, int64_t after = 0) {
   Compiled& c = *re->c;
   if (((uintptr_t)d_h & 15) || ((uintptr_t)d_out & 15)) {
     g_last_error = "device pointers must be 16-byte aligned";
@@ -189,6 +222,7 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   a.h = d_h;
   a.n = (int64_t)len;
   a.base = base;
+  a.after = after;
   a.dfa.trans = (const uint16_t*)re->d_trans.p;
   a.dfa.eoi = (const uint8_t*)re->d_eoi.p;
   a.dfa.nstates = c.dfa.nstates;
@@ -240,6 +274,15 @@ int cgx_scan_device(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base,
   return scan_locked(re, d_h, len, base, mode, d_out, cap, d_result, (cudaStream_t)stream);
 }
 
+int cgx_scan_shard_device(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base, int64_t bytes_after,
+                          int mode, int64_t* d_out, size_t cap, uint64_t* d_result, void* stream) {
+  if (!re || base < 0 || bytes_after < 0) return CGX_ERR_ARGS;
+  std::lock_guard<std::mutex> lk(re->mu);
+  int r = re->ensure_device();
+  if (r) return r;
+  return scan_locked(re, d_h, len, base, mode, d_out, cap, d_result, (cudaStream_t)stream, bytes_after);
+}
+
 // scan -> (start,end) pairs -> one Pike lane per match for the group offsets
 static int submatch_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base, int64_t* d_out,
                            size_t cap, uint64_t* d_result, cudaStream_t st) {
@@ -272,6 +315,145 @@ int cgx_scan_submatch_device(cgx_regex* re, const uint8_t* d_h, size_t len, int6
   return submatch_locked(re, d_h, len, base, d_out, cap, d_result, (cudaStream_t)stream);
 }
 
+// Large host haystacks are cut at record delimiters into pieces that flow through
+// H2D(k+1) | scan(k) | D2H(k-1) on three streams, so that the PCIe link is busy in both directions
+// while the scan runs.  A piece is independent of its neighbours because no match contains the
+// delimiter (the condition the record-parallel kernel already relies on).
+static const size_t kPipelineMin = (size_t)64 << 20;
+// CGX_PIPELINE_PIECE=<bytes> forces the piece size (tests use it to pipeline small inputs)
+static size_t forced_piece() {
+  static const size_t v = [] {
+    const char* e = getenv("CGX_PIPELINE_PIECE");
+    return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)0;
+  }();
+  return v;
+}
+
+static int host_scan_pipelined(cgx_regex* re, const uint8_t* h, size_t len, int mode, int64_t* out, size_t cap,
+                               uint64_t result[2]) {
+  int r;
+  if ((r = re->ensure_pipeline())) return r;
+  const uint8_t delim = re->c->kind == ENG_TEDDY ? (uint8_t)'\n' : (uint8_t)re->c->delim;
+  size_t nominal = len / 16;
+  if (nominal < ((size_t)32 << 20)) nominal = (size_t)32 << 20;
+  if (nominal > ((size_t)256 << 20)) nominal = (size_t)256 << 20;
+  if (forced_piece()) nominal = forced_piece();
+  nominal &= ~(size_t)15;
+  if (!nominal) nominal = 16;
+  // piece boundaries: multiples of 16 bytes are not required for the END of a piece, but every
+  // piece is copied to a 16-byte aligned device slot, so any delimiter position will do
+  std::vector<size_t> cut{0};
+  while (cut.back() < len) {
+    size_t b = cut.back() + nominal;
+    if (b >= len) {
+      cut.push_back(len);
+      break;
+    }
+    const void* q = memrchr(h + cut.back(), delim, b - cut.back());
+    if (q) {
+      b = (size_t)((const uint8_t*)q - h) + 1;
+    } else {
+      const void* f = memchr(h + b, delim, len - b);
+      b = f ? (size_t)((const uint8_t*)f - h) + 1 : len;
+    }
+    cut.push_back(b);
+  }
+  const int np = (int)cut.size() - 1;
+  size_t maxlen = 0;
+  for (int k = 0; k < np; k++) maxlen = cut[k + 1] - cut[k] > maxlen ? cut[k + 1] - cut[k] : maxlen;
+  for (int i = 0; i < 2; i++)
+    if ((r = re->d_hay2[i].ensure(maxlen + 16))) return r;
+
+  uint64_t total = 0, flag = 0;
+  size_t written = 0;           // pairs delivered to `out`
+  size_t pcap[2] = {0, 0};      // output capacity used by the in-flight scan of each slot
+  int pmode[2] = {mode, mode};
+  bool stop = false;
+
+  auto enqueue = [&](int k) -> int {
+    const int sl = k & 1;
+    const size_t off = cut[k], plen = cut[k + 1] - cut[k];
+    // the slot's previous piece (k-2) was finished — scan consumed, output copied out — by finish(k-2)
+    CU(cudaMemcpyAsync(re->d_hay2[sl].p, h + off, plen, cudaMemcpyHostToDevice, re->s_h2d));
+    CU(cudaEventRecord(re->ev_h2d[sl], re->s_h2d));
+    CU(cudaStreamWaitEvent(re->s_scan, re->ev_h2d[sl], 0));
+    int m = mode;
+    size_t pc = 0;
+    if (mode == CGX_MODE_FINDALL) {
+      const size_t remaining = cap - written;  // lower bound: earlier in-flight pieces may still add
+      if (remaining == 0) {
+        m = CGX_MODE_COUNT;
+      } else {
+        pc = plen / 16 + 1024;
+        if (pc > cap) pc = cap;
+        int rr;
+        if ((rr = re->d_out2[sl].ensure(pc * 16))) return rr;
+        CU(cudaStreamWaitEvent(re->s_scan, re->ev_d2h[sl], 0));  // output slot drained (piece k-2)
+      }
+    }
+    pcap[sl] = pc;
+    pmode[sl] = m;
+    int rr = scan_locked(re, (const uint8_t*)re->d_hay2[sl].p, plen, (int64_t)off, m,
+                         pc ? (int64_t*)re->d_out2[sl].p : nullptr, pc, nullptr, re->s_scan,
+                         (int64_t)(len - cut[k + 1]));
+    if (rr) return rr;
+    CU(cudaMemcpyAsync(re->pinned_res + 2 * sl, re->d_ticket_total.p, 16, cudaMemcpyDeviceToHost, re->s_scan));
+    CU(cudaEventRecord(re->ev_scan[sl], re->s_scan));
+    return CGX_OK;
+  };
+  auto finish = [&](int k) -> int {
+    const int sl = k & 1;
+    const size_t off = cut[k], plen = cut[k + 1] - cut[k];
+    for (;;) {
+      CU(cudaEventSynchronize(re->ev_scan[sl]));
+      const uint64_t t = re->pinned_res[2 * sl], f = re->pinned_res[2 * sl + 1];
+      if (pmode[sl] == CGX_MODE_FINDALL) {
+        const size_t remaining = cap - written;
+        const size_t need = t < remaining ? (size_t)t : remaining;
+        if (need > pcap[sl]) {
+          // denser than estimated: scan this piece again into a buffer that holds what is wanted
+          CU(cudaStreamSynchronize(re->s_d2h));
+          CU(cudaStreamSynchronize(re->s_scan));
+          int rr;
+          if ((rr = re->d_out2[sl].ensure(need * 16))) return rr;
+          pcap[sl] = need;
+          if ((rr = scan_locked(re, (const uint8_t*)re->d_hay2[sl].p, plen, (int64_t)off, CGX_MODE_FINDALL,
+                                (int64_t*)re->d_out2[sl].p, need, nullptr, re->s_scan,
+                                (int64_t)(len - cut[k + 1]))))
+            return rr;
+          CU(cudaMemcpyAsync(re->pinned_res + 2 * sl, re->d_ticket_total.p, 16, cudaMemcpyDeviceToHost,
+                             re->s_scan));
+          CU(cudaEventRecord(re->ev_scan[sl], re->s_scan));
+          continue;
+        }
+        if (need) {
+          CU(cudaStreamWaitEvent(re->s_d2h, re->ev_scan[sl], 0));
+          CU(cudaMemcpyAsync(out + 2 * written, re->d_out2[sl].p, need * 16, cudaMemcpyDeviceToHost, re->s_d2h));
+          written += need;
+        }
+        CU(cudaEventRecord(re->ev_d2h[sl], re->s_d2h));
+      }
+      total += t;
+      flag |= f;
+      if (mode == CGX_MODE_ISMATCH && flag) stop = true;
+      return CGX_OK;
+    }
+  };
+  int queued = 0;
+  for (int k = 0; k < np && !stop; k++) {
+    if ((r = enqueue(k))) return r;
+    queued = k + 1;
+    if (k >= 1 && (r = finish(k - 1))) return r;
+  }
+  if (queued && !stop && (r = finish(queued - 1))) return r;
+  CU(cudaStreamSynchronize(re->s_h2d));
+  CU(cudaStreamSynchronize(re->s_scan));
+  CU(cudaStreamSynchronize(re->s_d2h));
+  result[0] = total;
+  result[1] = flag ? 1 : 0;
+  return CGX_OK;
+}
+
 // host wrapper shared by is_match / count / find_all
 static int host_scan(cgx_regex* re, const uint8_t* h, size_t len, int mode, int64_t* out, size_t cap,
                      uint64_t result[2]) {
@@ -279,6 +461,7 @@ static int host_scan(cgx_regex* re, const uint8_t* h, size_t len, int mode, int6
   std::lock_guard<std::mutex> lk(re->mu);
   int r = re->ensure_device();
   if (r) return r;
+  if (len >= (forced_piece() ? 2 * forced_piece() : kPipelineMin)) return host_scan_pipelined(re, h, len, mode, out, cap, result);
   if ((r = re->d_hay.ensure(len + 16))) return r;
   if (mode == CGX_MODE_FINDALL && cap && (r = re->d_out.ensure(cap * 16))) return r;
   cudaStream_t st = 0;

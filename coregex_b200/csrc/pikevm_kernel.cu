@@ -32,11 +32,11 @@ __device__ __forceinline__ bool is_word(int b) {
 }
 
 // reference nfa/pikevm.go:1646-1675 checkLookAssertion
-__device__ __forceinline__ bool look_ok(int kind, const uint8_t* h, int64_t n, int64_t pos) {
+__device__ __forceinline__ bool look_ok(int kind, const uint8_t* h, int64_t n, int64_t pos, bool text0) {
   const int prev = pos > 0 ? (int)h[pos - 1] : -1;
   const int next = pos < n ? (int)h[pos] : -1;
   switch (kind) {
-    case 0: return pos == 0;
+    case 0: return pos == 0 && text0;  // a shard with base > 0 starts after a delimiter, not at \\A
     case 1: return pos == n;
     case 2: return pos == 0 || prev == '\n';
     case 3: return pos == n || next == '\n';
@@ -52,6 +52,7 @@ struct Vm {
   int64_t n;
   int64_t s;  // match start
   int nslots;
+  bool text0;  // position 0 of h is the start of the logical haystack
 };
 
 // epsilon closure of pc at position pos (relative rp = pos - s), appending to `tl`
@@ -103,7 +104,7 @@ __device__ void add_thread(const Vm& vm, ThreadList& tl, unsigned long long& vis
         }
         break;
       case 4:  // I_ASSERT
-        if (look_ok(arg, vm.h, vm.n, pos) && sp + 1 <= MAXSTK) {
+        if (look_ok(arg, vm.h, vm.n, pos, vm.text0) && sp + 1 <= MAXSTK) {
           stk_a[sp] = out; stk_b[sp++] = 0;
         }
         break;
@@ -126,7 +127,7 @@ __global__ void pike_captures_kernel(const uint8_t* h, int64_t n, int64_t base, 
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long nmatches = *d_total < cap ? *d_total : cap;
   if (i >= nmatches) return;
-  Vm vm{code, sets, h, n, matches[2 * i] - base, nslots};
+  Vm vm{code, sets, h, n, matches[2 * i] - base, nslots, base == 0};
   ThreadList a, b;
   ThreadList* cur = &a;
   ThreadList* nxt = &b;

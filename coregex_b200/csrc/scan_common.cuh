@@ -48,6 +48,10 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// asks L2 to fetch [src, src+bytes) (16-byte aligned, multiple of 16); no completion to wait for
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 
 // ---- SWAR byte-class tests ---------------------------------------------------------------------
 // bit 7 of each byte of the result is set iff that byte of x lies in [lo,hi]; requires hi <= 0x7F.

@@ -114,7 +114,7 @@ __device__ __forceinline__ int start_kind(uint8_t b) {
 // Anchored leftmost-first walk from global position p0 through global memory (any position).
 __device__ int64_t dfa_walk_slow(const Ctx& c, int64_t p0) {
   unsigned s = c.a.dfa.start[0];
-  if (c.a.dfa.kind_lut_needed) s = c.a.dfa.start[p0 == 0 ? 2 : start_kind(byte_at(c, p0 - 1))];
+  if (c.a.dfa.kind_lut_needed) s = c.a.dfa.start[p0 == 0 ? (c.a.base == 0 ? 2 : 3) : start_kind(byte_at(c, p0 - 1))];
   int64_t last = -1, p = p0;
   const int64_t n = c.a.n;
   while (s) {
@@ -136,7 +136,7 @@ __device__ int64_t dfa_walk_slow(const Ctx& c, int64_t p0) {
 __device__ __forceinline__ int dfa_walk(const Ctx& c, int i0) {
   uint32_t sp = (uint32_t)c.a.dfa.start[0] << 10;
   if (c.a.dfa.kind_lut_needed) {
-    const int k = (c.gw + i0 == 0) ? 2 : start_kind(c.sm.win[i0 - 1]);
+    const int k = (c.gw + i0 == 0) ? (c.a.base == 0 ? 2 : 3) : start_kind(c.sm.win[i0 - 1]);
     sp = (uint32_t)c.a.dfa.start[k] << 10;
   }
   int last = -1, i = i0;
@@ -511,7 +511,7 @@ __device__ int serial_chain_teddy(const Ctx& c, Emitter<DIRECT>& em, int pos_i, 
     const int64_t lastc = c.gw + last_cand;
     bool more = true;
     while (more && pos < n) {
-      const bool scalar = n - pos < 16;
+      const bool scalar = n + c.a.after - pos < 16;
       more = false;
       for (int64_t p = pos; p + 2 <= n; p++) {
         const uint8_t b0 = byte_at(c, p);
@@ -613,7 +613,7 @@ __device__ __forceinline__ int process_batch(const Ctx& c, Emitter<DIRECT>& em, 
   // literal candidates inside the last 16 bytes of the haystack may fall under the reference's
   // scalar verify order: let the exact replay decide
   bool replay = false;
-  if (c.a.engine == SEL_TEDDY) replay = valid && c.gw + cand > c.a.n - 16;
+  if (c.a.engine == SEL_TEDDY) replay = valid && c.gw + cand > c.a.n + c.a.after - 16;
   if (c.a.filter.kind == F_RUNSTART) replay |= bad;  // a resume position inside a run is no candidate
   replay = __any_sync(FULL, replay);
   if (!replay && __any_sync(FULL, bad)) {
@@ -910,7 +910,15 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
       }
       if (tid == 0) {
         sm.woverflow2[it & 1] = 0;
-        sm.chunk2[(it + 1) & 1] = next_ticket();
+        const unsigned nxt = next_ticket();
+        sm.chunk2[(it + 1) & 1] = nxt;
+        if ((int64_t)nxt < a.nchunks) {
+          // the next chunk's window starts moving towards L2 while this chunk is in phase B
+          const int64_t nlo = (int64_t)nxt * CH - PRE;  // nxt > 0 here: chunk 0 is never a "next"
+          const int64_t nhi = nlo + WIN < a.n ? nlo + WIN : a.n;
+          const uint32_t nb = (uint32_t)(nhi - nlo) & ~15u;
+          if (nb) tma_prefetch_l2(a.h + nlo, nb);
+        }
       }
     }
     if (a.mode == M_FINDALL && used >= 2) bar_sync(BAR_EMPTY + buf, THREADS);  // buffer released?

@@ -69,7 +69,9 @@ enum EngineSel : int { SEL_DFA = 0, SEL_TEDDY = 1 };
 struct ScanArgs {
   const uint8_t* h;   // device haystack, 16-byte aligned
   int64_t n;
-  int64_t base;       // added to every reported offset (shard base)
+  int64_t base;       // position of h[0] in the logical haystack: added to every reported offset;
+                      // base > 0 means h[-1] is the record delimiter (shards are cut at records)
+  int64_t after;      // bytes of the logical haystack after h[n-1] (0: h ends the haystack)
   DfaDev dfa;
   FilterDev filter;
   FlatDev flat;

@@ -83,6 +83,16 @@ enum { CGX_MODE_FINDALL = 0, CGX_MODE_COUNT = 1, CGX_MODE_ISMATCH = 2 };
 int cgx_scan_device(cgx_regex* re, const uint8_t* d_haystack, size_t len, int64_t base_offset,
                     int mode, int64_t* d_out_pairs, size_t cap_pairs, uint64_t* d_result,
                     void* stream);
+/* One shard of a larger logical haystack (corpus split across GPUs, or pieces of a pipelined
+ * host copy).  Shards are cut right after a record delimiter ('\n'): base_offset > 0 promises
+ * that the byte before d_haystack[0] is a delimiter, bytes_after > 0 that the shard ends with
+ * one.  base_offset == 0 marks the true start of text (\A, non-multiline ^), bytes_after == 0
+ * the true end (\z, $), and bytes_after also feeds the multi-literal engine's end-of-haystack
+ * verify regime (reference prefilter/teddy.go:415-428), so that shard results concatenate to
+ * exactly the whole-haystack result.  cgx_scan_device is the bytes_after == 0 case.            */
+int cgx_scan_shard_device(cgx_regex* re, const uint8_t* d_haystack, size_t len, int64_t base_offset,
+                          int64_t bytes_after, int mode, int64_t* d_out_pairs, size_t cap_pairs,
+                          uint64_t* d_result, void* stream);
 /* submatch variant: d_out receives stride int64 per match */
 int cgx_scan_submatch_device(cgx_regex* re, const uint8_t* d_haystack, size_t len,
                              int64_t base_offset, int64_t* d_out, size_t cap_matches,

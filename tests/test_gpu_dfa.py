@@ -224,3 +224,50 @@ def test_overlap_chain_dense_single_line():
     check(r"\d\d\d", b"1234567890" * 9000)
     check(r"aa", b"a" * 70001)
     check(r"[a-c][a-z]*x", b"abcabcx" * 9000 + b"\n" + b"aaaa" * 5000)
+
+
+# ---- pipelined host path (H2D | scan | D2H over delimiter-cut pieces) ---------------------------------
+# CGX_PIPELINE_PIECE is read once per process, so the pipelined run happens in a child process.
+_PIPE_CHILD = r"""
+import sys, json, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import coregex_b200 as cg
+from oracle_lib import Oracle
+rng = np.random.default_rng(5)
+ok = True
+def corpus(kind):
+    if kind == "log":
+        return cg.synth_host(0, 77, 1200 * 4096)
+    if kind == "lit":
+        words = [b"error", b"err", b"errors", b"warning", b"warn", b"fatal", b"xx", b"the", b"a", b"critical", b"timeout"]
+        parts = []
+        for _ in range(400000):
+            parts.append(words[rng.integers(0, len(words))])
+            parts.append(b"\n" if rng.integers(0, 9) == 0 else b" ")
+        return b"".join(parts)
+    if kind == "longline":
+        return b"1.2.3.4 " * 300000 + b"\n" + b"9.9.9.9 x\n" * 1000 + b"7.7.7.7"   # one 2.4 MB line
+for pat, kind in [(r"\d+\.\d+\.\d+\.\d+", "log"), (r"error|err|errors|warning|warn|fatal", "lit"), (r"warning|fatal|critical|timeout", "lit"),
+                  (r"^(error|warn)", "lit"), (r"(?m)^(error|warn)\w*", "lit"), (r"\d+\.\d+\.\d+\.\d+", "longline"),
+                  (r"(?m)\d$", "longline")]:
+    hay = corpus(kind)
+    hay = hay.tobytes() if hasattr(hay, 'tobytes') else hay
+    r = cg.Compile(pat)
+    want = Oracle(pat).find_all(hay)
+    got = r.find_all_index_array(hay)
+    good = got.shape == want.shape and np.array_equal(got, want) and r.Count(hay) == len(want) \
+        and r.Match(hay) == (len(want) > 0)
+    part = r.FindAllIndex(hay, 1000)
+    good = good and (part or []) == want[:1000].tolist()
+    print(pat, kind, len(hay), len(want), good)
+    ok = ok and good
+sys.exit(0 if ok else 1)
+"""
+
+
+def test_pipelined_host_path_matches_oracle(tmp_path):
+    import subprocess
+    import sys
+    env = dict(os.environ, CGX_PIPELINE_PIECE=str(192 * 1024))
+    p = subprocess.run([sys.executable, "-c", _PIPE_CHILD, ROOT], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
