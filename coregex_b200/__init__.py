@@ -43,6 +43,8 @@ class CudaError(RuntimeError):
 
 
 def _load():
+    global _SO
+    _SO = os.environ.get("COREGEX_B200_LIB", _SO)  # e.g. the -DCGX_TIMING build of tools/phase_timing.py
     if not os.path.exists(_SO):
         raise ImportError(
             "coregex_b200: %s is missing — run `python -m coregex_b200.build` (nvcc, sm_100a). "

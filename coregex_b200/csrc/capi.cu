@@ -542,6 +542,14 @@ int cgx_find_all_submatch_index(cgx_regex* re, const uint8_t* h, size_t len, int
 }
 
 // ---- debug exports (tests only): the compiled tables exactly as the kernels see them ------------
+// the 64-byte per-call scratch {total, flag, t2, t3, ticket, t5, t6, t7}; the t* slots are phase
+// cycle counters in the -DCGX_TIMING build (tools/phase_timing.py) and zero otherwise
+int cgx_debug_scratch(cgx_regex* re, uint64_t out[8]) {
+  if (!re || !re->d_ticket_total.p) return CGX_ERR_ARGS;
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out, re->d_ticket_total.p, 64, cudaMemcpyDeviceToHost));
+  return CGX_OK;
+}
 int cgx_debug_dfa_info(const cgx_regex* re, int* nstates, uint16_t start[5], int* filter_kind,
                        int* skip_safe, int* kind_lut_needed, uint8_t ranges[8], int* nranges) {
   const Compiled& c = *re->c;

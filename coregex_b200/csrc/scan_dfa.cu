@@ -463,14 +463,27 @@ __device__ void phase_a_flat(const Ctx& c) {
   flat_store(c, tb, piece, Mb);
 }
 
-// first position q >= from with q == 0 or byte(q-1) == delim, searched inside the window only
+// first position q >= from with q == 0 or byte(q-1) == delim, searched inside the window only:
+// 128 bytes per step, one word per lane, zero-byte test on (word ^ delimiter splat)
 __device__ int64_t find_line_start(const Ctx& c, int64_t from) {
   if (from <= 0) return 0;
-  const int64_t wend_g = c.gw + c.wend;
-  for (int64_t q = from - 1 + c.lane; __any_sync(FULL, q < wend_g); q += 32) {
-    const bool hit = q < wend_g && c.sm.win[q - c.gw] == c.a.delim;
-    const unsigned b = __ballot_sync(FULL, hit);
-    if (b) return q - c.lane + (__ffs(b) - 1) + 1;
+  const int i0 = (int)(from - 1 - c.gw);
+  const uint32_t splat = (uint32_t)c.a.delim * 0x01010101u;
+  for (int base = i0 & ~3; base < c.wend; base += 128) {
+    const int idx = base + 4 * c.lane;
+    uint32_t z = 0;
+    if (idx < c.wend) {  // the word may run into win[wend..]: the sentinel is filtered below
+      const uint32_t t = *reinterpret_cast<const uint32_t*>(c.sm.win + idx) ^ splat;
+      z = (t - 0x01010101u) & ~t & 0x80808080u;  // lowest set flag = first delimiter byte (exact)
+      if (idx < i0) z &= 0xFFFFFFFFu << (8 * (i0 - idx));
+    }
+    const unsigned b = __ballot_sync(FULL, z != 0);
+    if (b) {
+      const int l = __ffs(b) - 1;
+      const uint32_t zl = __shfl_sync(FULL, z, l);
+      const int pos = base + 4 * l + ((__ffs(zl) - 1) >> 3);
+      return pos < c.wend ? c.gw + pos + 1 : INF;
+    }
   }
   return INF;
 }
@@ -795,6 +808,15 @@ __device__ __forceinline__ void write_staged(const ScanArgs& a, Smem& sm, int bu
   }
 }
 
+#ifdef CGX_TIMING
+#define TSTAMP(var) const long long var = clock64()
+#define TACC(slot, t0, t1) \
+  if (lane == 0) atomicAdd(&a.total[slot], (unsigned long long)((t1) - (t0)))
+#else
+#define TSTAMP(var)
+#define TACC(slot, t0, t1)
+#endif
+
 // Roles: warps 0..7 scan (ticket -> TMA load -> phase A -> phase B into a staging buffer),
 // warp 8 turns staged chunks into ordered global output (decoupled look-back + int64 stores).
 // Two staging buffers decouple them: a scanning warp only waits if the writer is two chunks behind.
@@ -880,6 +902,16 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
       } else {
         mbar_arrive(&sm.mbar);
       }
+      // the next ticket is drawn while this chunk's window is in flight (its latency hides behind
+      // the wait below), and the next window starts moving towards L2 a whole chunk ahead
+      const unsigned nxt = next_ticket();
+      sm.chunk2[(it + 1) & 1] = nxt;
+      if ((int64_t)nxt < a.nchunks) {
+        const int64_t nlo = (int64_t)nxt * CH - PRE;  // nxt > 0 here: chunk 0 is never a "next"
+        const int64_t nhi = nlo + WIN < a.n ? nlo + WIN : a.n;
+        const uint32_t nb = (uint32_t)(nhi - nlo) & ~15u;
+        if (nb) tma_prefetch_l2(a.h + nlo, nb);
+      }
     }
     // bytes the bulk copy does not cover: before position 0, the <16 B tail, past the end
     if (gw < 0 || bulk != (uint32_t)WIN) {
@@ -888,8 +920,11 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
         if (g < 0 || g >= lo_g + bulk) sm.win[i] = g >= 0 && g < a.n ? a.h[g] : a.delim;
       }
     }
+    TSTAMP(t_0);
     mbar_wait(&sm.mbar, parity);  // every scanning thread observes the TMA completion itself
     parity ^= 1;
+    TSTAMP(t_1);
+    TACC(2, t_0, t_1);
     if (gw < 0 || bulk != (uint32_t)WIN) bar_sync(BAR_COMPUTE, CTHREADS);  // generic fill stores
 
     Ctx c{a, sm, s_trans, s_eoi, s_lut, cbeg, gw, (int)(hi_g - gw), lane, warp, buf,
@@ -901,6 +936,8 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
     if (a.engine == SEL_TEDDY) phase_a_teddy(c);
     else if (a.flat.nops) phase_a_flat(c);
     else phase_a_plain(c);
+    TSTAMP(t_1a);
+    TACC(3, t_1, t_1a);
     {
       const int64_t s = find_line_start(c, cbeg + (int64_t)warp * SUB);
       if (lane == 0) sm.ls[warp] = s;
@@ -910,19 +947,16 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
       }
       if (tid == 0) {
         sm.woverflow2[it & 1] = 0;
-        const unsigned nxt = next_ticket();
-        sm.chunk2[(it + 1) & 1] = nxt;
-        if ((int64_t)nxt < a.nchunks) {
-          // the next chunk's window starts moving towards L2 while this chunk is in phase B
-          const int64_t nlo = (int64_t)nxt * CH - PRE;  // nxt > 0 here: chunk 0 is never a "next"
-          const int64_t nhi = nlo + WIN < a.n ? nlo + WIN : a.n;
-          const uint32_t nb = (uint32_t)(nhi - nlo) & ~15u;
-          if (nb) tma_prefetch_l2(a.h + nlo, nb);
-        }
       }
     }
+    TSTAMP(t_2);
+    TACC(5, t_1a, t_2);
     if (a.mode == M_FINDALL && used >= 2) bar_sync(BAR_EMPTY + buf, THREADS);  // buffer released?
+    TSTAMP(t_2b);
+    TACC(6, t_2, t_2b);
     bar_sync(BAR_COMPUTE, CTHREADS);
+    TSTAMP(t_3);
+    TACC(7, t_2b, t_3);
 
     Emitter<false> em(c, 0);
     phase_b<false>(c, em);
