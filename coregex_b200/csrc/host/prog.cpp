@@ -111,13 +111,166 @@ struct Builder {
       i.op = I_FAIL;
       return emit(i);
     }
+    bool ascii = true;
+    for (int32_t r : re->rune) ascii = ascii && r <= 127;
+    if (!ascii) return unicodeClass(re->rune, next);
     ByteSet s{};
-    for (size_t k = 0; k + 1 < re->rune.size(); k += 2) {
-      if (re->rune[k] > 127 || re->rune[k + 1] > 127)
-        return fail("unsupported: non-ASCII character class (UTF-8 automata out of scope)");
+    for (size_t k = 0; k + 1 < re->rune.size(); k += 2)
       set_add(s, (unsigned)re->rune[k], (unsigned)re->rune[k + 1]);
-    }
     return emitSet(s, next);
+  }
+
+  // ---- UTF-8: a class or `.` becomes an ordered alternation of byte-set sequences --------------
+  // What has to equal the reference (nfa/compile.go:440-1223) is the byte LANGUAGE and the order
+  // of alternatives that can overlap; the state shape is this program's own.
+  using Seq = std::vector<ByteSet>;
+  static ByteSet range(unsigned lo, unsigned hi) {
+    ByteSet s{};
+    set_add(s, lo, hi);
+    return s;
+  }
+  int emitAlts(const std::vector<Seq>& alts, int next) {
+    if (alts.empty()) {
+      Inst i;
+      i.op = I_FAIL;
+      return emit(i);
+    }
+    std::vector<int> entries;
+    for (const Seq& q : alts) {
+      int nx = next;
+      if (!reverse) {
+        for (size_t i = q.size(); i-- > 0;) nx = emitSet(q[i], nx);
+      } else {
+        for (size_t i = 0; i < q.size(); i++) nx = emitSet(q[i], nx);
+      }
+      entries.push_back(nx);
+    }
+    int acc = entries.back();
+    for (size_t i = entries.size() - 1; i-- > 0;) acc = emitSplit(entries[i], acc);
+    return acc;
+  }
+  // every well-formed multi-byte sequence (the eight rows of the Unicode standard's table 3-7)
+  static void validMultiByte(std::vector<Seq>& alts) {
+    const ByteSet cont = range(0x80, 0xBF);
+    alts.push_back({range(0xC2, 0xDF), cont});
+    alts.push_back({range(0xE0, 0xE0), range(0xA0, 0xBF), cont});
+    alts.push_back({range(0xE1, 0xEC), cont, cont});
+    alts.push_back({range(0xED, 0xED), range(0x80, 0x9F), cont});
+    alts.push_back({range(0xEE, 0xEF), cont, cont});
+    alts.push_back({range(0xF0, 0xF0), range(0x90, 0xBF), cont, cont});
+    alts.push_back({range(0xF1, 0xF3), cont, cont, cont});
+    alts.push_back({range(0xF4, 0xF4), range(0x80, 0x8F), cont, cont});
+  }
+  // [lo,hi] inside one encoded length -> sequences of byte ranges (each a product of ranges)
+  static void splitRange(int32_t lo, int32_t hi, int nbytes, std::vector<Seq>& alts) {
+    for (int i = 1; i < nbytes; i++) {
+      const int32_t m = (1 << (6 * i)) - 1;
+      if ((lo & ~m) != (hi & ~m)) {
+        if ((lo & m) != 0) {
+          splitRange(lo, lo | m, nbytes, alts);
+          splitRange((lo | m) + 1, hi, nbytes, alts);
+          return;
+        }
+        if ((hi & m) != m) {
+          splitRange(lo, (hi & ~m) - 1, nbytes, alts);
+          splitRange(hi & ~m, hi, nbytes, alts);
+          return;
+        }
+      }
+    }
+    uint8_t a[4], b[4];
+    encodeRune(a, lo);
+    encodeRune(b, hi);
+    Seq q;
+    for (int i = 0; i < nbytes; i++) q.push_back(range(a[i], b[i]));
+    alts.push_back(q);
+  }
+  // reference nfa/compile.go:600-842 as a language: exact for 1-3 byte runes (surrogates cut
+  // out, :706-737), four-byte ranges widened to whole lead bytes (:796-842)
+  static void wideRange(int32_t lo, int32_t hi, std::vector<Seq>& alts) {
+    if (lo <= 0x7F) {
+      alts.push_back({range(lo, hi > 0x7F ? 0x7F : hi)});
+      lo = 0x80;
+    }
+    if (lo > hi) return;
+    if (lo <= 0x7FF) {
+      splitRange(lo, hi > 0x7FF ? 0x7FF : hi, 2, alts);
+      lo = 0x800;
+    }
+    if (lo > hi) return;
+    if (lo <= 0xFFFF) {
+      int32_t a = lo, b = hi > 0xFFFF ? 0xFFFF : hi;
+      if (a <= 0xD7FF && b >= 0xE000) {
+        splitRange(a, 0xD7FF, 3, alts);
+        splitRange(0xE000, b, 3, alts);
+      } else if (!(a >= 0xD800 && b <= 0xDFFF)) {
+        if (a >= 0xD800 && a <= 0xDFFF) a = 0xE000;
+        if (b >= 0xD800 && b <= 0xDFFF) b = 0xD7FF;
+        if (a <= b) splitRange(a, b, 3, alts);
+      }
+      lo = 0x10000;
+    }
+    if (lo > hi) return;
+    if (hi > 0x10FFFF) hi = 0x10FFFF;
+    int32_t a = (lo >> 18) << 18, b = ((hi >> 18) << 18) | 0x3FFFF;
+    if (a < 0x10000) a = 0x10000;
+    if (b > 0x10FFFF) b = 0x10FFFF;
+    splitRange(a, b, 4, alts);
+  }
+  int unicodeClass(const std::vector<int32_t>& r, int next) {
+    int64_t total = 0;
+    bool large = false;
+    for (size_t k = 0; k + 1 < r.size() && !large; k += 2) {
+      total += (int64_t)r[k + 1] - r[k] + 1;
+      large = total > 256;
+    }
+    std::vector<Seq> alts;
+    if (!large) {
+      // reference :463-486: one literal per code point, in class order
+      for (size_t k = 0; k + 1 < r.size(); k += 2)
+        for (int32_t c = r[k]; c <= r[k + 1]; c++) {
+          uint8_t buf[4];
+          const int n = encodeRune(buf, c);
+          Seq q;
+          for (int i = 0; i < n; i++) q.push_back(range(buf[i], buf[i]));
+          alts.push_back(q);
+        }
+      return emitAlts(alts, next);
+    }
+    // reference :491-596: ASCII part | multi-byte part (| any stray high byte when the class
+    // covers everything above 0x7F)
+    ByteSet ascii{};
+    bool has_ascii = false;
+    std::vector<std::pair<int32_t, int32_t>> wide;
+    for (size_t k = 0; k + 1 < r.size(); k += 2) {
+      const int32_t lo = r[k], hi = r[k + 1];
+      if (lo < 0x80) {
+        set_add(ascii, (unsigned)lo, (unsigned)(hi < 0x80 ? hi : 0x7F));
+        has_ascii = true;
+      }
+      if (hi >= 0x80) wide.push_back({lo < 0x80 ? 0x80 : lo, hi});
+    }
+    if (has_ascii) alts.push_back({ascii});
+    if (wide.size() == 1 && wide[0].first <= 0x80 && wide[0].second >= 0x10FFFF) {
+      validMultiByte(alts);
+      alts.push_back({range(0x80, 0xFF)});
+    } else {
+      for (auto& w : wide) wideRange(w.first, w.second, alts);
+    }
+    return emitAlts(alts, next);
+  }
+  // reference :1142-1223
+  int anyChar(bool include_nl, int next) {
+    std::vector<Seq> alts;
+    ByteSet ascii = range(0x00, 0x7F);
+    if (!include_nl) ascii[0] &= ~(1ull << '\n');
+    alts.push_back({ascii});
+    validMultiByte(alts);
+    ByteSet stray = range(0x80, 0xBF);
+    set_add(stray, 0xC0, 0xC1);
+    set_add(stray, 0xF5, 0xFF);
+    alts.push_back({stray});
+    return emitAlts(alts, next);
   }
 
   // loop helpers: `greedy` decides which split arm is preferred
@@ -205,9 +358,8 @@ struct Builder {
     switch (re->op) {
       case OpLiteral: return literal(re, next);
       case OpCharClass: return charClass(re, next);
-      case OpAnyChar:
-      case OpAnyCharNotNL:
-        return fail("unsupported: `.` (UTF-8 automata out of scope)");
+      case OpAnyChar: return anyChar(true, next);
+      case OpAnyCharNotNL: return anyChar(false, next);
       case OpConcat: {
         if (!reverse) {
           for (size_t i = re->sub.size(); i-- > 0;) {

@@ -100,6 +100,7 @@ struct Frag {
 
 struct Compiler {
   Builder b;
+  Arena scratch;  // synthetic literal nodes of small Unicode classes
   int depth = 0;
   int max_depth = 100;
   int capture_count = 0;
@@ -255,7 +256,7 @@ struct Compiler {
   bool compileCharClass(const std::vector<int32_t>& ranges, Frag& f) {
     if (ranges.empty()) return compileNoMatch(f);
     for (int32_t r : ranges)
-      if (r > 127) return fail("unsupported: non-ASCII character class (UTF-8 automata out of scope)");
+      if (r > 127) return compileUnicodeClass(ranges, f);
     std::vector<Transition> tr;
     for (size_t i = 0; i + 1 < ranges.size(); i += 2)
       tr.push_back({(uint8_t)ranges[i], (uint8_t)ranges[i + 1], InvalidState});
@@ -268,6 +269,221 @@ struct Compiler {
     for (auto& t : tr) t.next = target;
     StateID id = b.AddSparse(tr);
     f = {id, target};
+    return true;
+  }
+
+  // ---- UTF-8 automata ------------------------------------------------------------------------
+  // reference nfa/compile.go:440-487: classes of at most 256 code points become an alternation of
+  // single-rune literals, larger ones go through the range compiler
+  bool compileUnicodeClass(const std::vector<int32_t>& ranges, Frag& f) {
+    int64_t total = 0;
+    for (size_t i = 0; i + 1 < ranges.size(); i += 2) {
+      total += (int64_t)ranges[i + 1] - ranges[i] + 1;
+      if (total > 256) return compileUnicodeClassLarge(ranges, f);
+    }
+    std::vector<Regexp*> alts;
+    for (size_t i = 0; i + 1 < ranges.size(); i += 2)
+      for (int32_t r = ranges[i]; r <= ranges[i + 1]; r++) {
+        Regexp* lit = scratch.make(OpLiteral);
+        lit->rune.push_back(r);
+        alts.push_back(lit);
+      }
+    if (alts.size() == 1) return compile(alts[0], f);
+    return compileAlternate(alts, f);
+  }
+
+  // reference nfa/compile.go:491-596
+  bool compileUnicodeClassLarge(const std::vector<int32_t>& ranges, Frag& f) {
+    std::vector<Transition> ascii;
+    std::vector<std::pair<int32_t, int32_t>> wide;
+    for (size_t i = 0; i + 1 < ranges.size(); i += 2) {
+      const int32_t lo = ranges[i], hi = ranges[i + 1];
+      if (hi < 0x80) {
+        ascii.push_back({(uint8_t)lo, (uint8_t)hi, InvalidState});
+      } else if (lo >= 0x80) {
+        wide.push_back({lo, hi});
+      } else {
+        ascii.push_back({(uint8_t)lo, 0x7F, InvalidState});
+        wide.push_back({0x80, hi});
+      }
+    }
+    const bool all_wide = wide.size() == 1 && wide[0].first <= 0x80 && wide[0].second >= 0x10FFFF;
+    StateID target = b.AddEpsilon(InvalidState);
+    std::vector<StateID> starts;
+    if (!ascii.empty()) {
+      for (auto& t : ascii) t.next = target;
+      starts.push_back(ascii.size() == 1 ? b.AddByteRange(ascii[0].lo, ascii[0].hi, target) : b.AddSparse(ascii));
+    }
+    if (!wide.empty()) {
+      if (all_wide) {
+        buildUTF8NonASCIIBranches(target, starts);
+        starts.push_back(b.AddByteRange(0x80, 0xFF, target));  // any stray high byte, lowest priority
+      } else {
+        for (auto& w : wide) compileUTF8Range(w.first, w.second, target, starts);
+      }
+    }
+    if (starts.empty()) return compileNoMatch(f);
+    if (starts.size() == 1) {
+      f = {starts[0], target};
+      return true;
+    }
+    f = {buildSplitChain(starts), target};
+    return true;
+  }
+
+  // reference nfa/compile.go:600-654: split [lo,hi] by encoded length
+  void compileUTF8Range(int32_t lo, int32_t hi, StateID end, std::vector<StateID>& out) {
+    if (lo <= 0x7F) {
+      out.push_back(b.AddByteRange((uint8_t)lo, (uint8_t)(hi > 0x7F ? 0x7F : hi), end));
+      lo = 0x80;
+    }
+    if (lo > hi) return;
+    if (lo <= 0x7FF) {
+      utf8Range2(lo, hi > 0x7FF ? 0x7FF : hi, end, out);
+      lo = 0x800;
+    }
+    if (lo > hi) return;
+    if (lo <= 0xFFFF) {
+      utf8Range3(lo, hi > 0xFFFF ? 0xFFFF : hi, end, out);
+      lo = 0x10000;
+    }
+    if (lo > hi) return;
+    utf8Range4(lo, hi, end, out);
+  }
+
+  // reference nfa/compile.go:663-703
+  void utf8Range2(int32_t lo, int32_t hi, StateID end, std::vector<StateID>& out) {
+    const uint8_t l0 = 0xC0 | (lo >> 6), l1 = 0x80 | (lo & 0x3F), h0 = 0xC0 | (hi >> 6), h1 = 0x80 | (hi & 0x3F);
+    if (l0 == h0) {
+      StateID c = b.AddByteRange(l1, h1, end);
+      out.push_back(b.AddByteRange(l0, l0, c));
+      return;
+    }
+    StateID c1 = b.AddByteRange(l1, 0xBF, end);
+    out.push_back(b.AddByteRange(l0, l0, c1));
+    if (h0 > l0 + 1) {
+      StateID cm = b.AddByteRange(0x80, 0xBF, end);
+      out.push_back(b.AddByteRange(l0 + 1, h0 - 1, cm));
+    }
+    StateID c2 = b.AddByteRange(0x80, h1, end);
+    out.push_back(b.AddByteRange(h0, h0, c2));
+  }
+
+  // reference nfa/compile.go:706-737: surrogates are cut out of three-byte ranges
+  void utf8Range3(int32_t lo, int32_t hi, StateID end, std::vector<StateID>& out) {
+    if (lo <= 0xD7FF && hi >= 0xE000) {
+      utf8Range3Simple(lo, 0xD7FF, end, out);
+      utf8Range3Simple(0xE000, hi, end, out);
+      return;
+    }
+    if (lo >= 0xD800 && hi <= 0xDFFF) return;
+    if (lo >= 0xD800 && lo <= 0xDFFF) lo = 0xE000;
+    if (hi >= 0xD800 && hi <= 0xDFFF) hi = 0xD7FF;
+    if (lo > hi) return;
+    utf8Range3Simple(lo, hi, end, out);
+  }
+
+  // reference nfa/compile.go:740-793 (+ the bound helpers :922-973): one lead/cont1 pair per branch
+  void utf8Range3Simple(int32_t lo, int32_t hi, StateID end, std::vector<StateID>& out) {
+    const int l0 = 0xE0 | (lo >> 12), l1 = 0x80 | ((lo >> 6) & 0x3F), l2 = 0x80 | (lo & 0x3F);
+    const int h0 = 0xE0 | (hi >> 12), h1 = 0x80 | ((hi >> 6) & 0x3F), h2 = 0x80 | (hi & 0x3F);
+    auto branch = [&](int lead, int c1, int c2lo, int c2hi) {
+      StateID s2 = b.AddByteRange((uint8_t)c2lo, (uint8_t)c2hi, end);
+      StateID s1 = b.AddByteRange((uint8_t)c1, (uint8_t)c1, s2);
+      out.push_back(b.AddByteRange((uint8_t)lead, (uint8_t)lead, s1));
+    };
+    if (l0 == h0 && l1 == h1) {
+      branch(l0, l1, l2, h2);
+    } else if (l0 == h0) {
+      for (int c1 = l1; c1 <= h1; c1++) branch(l0, c1, c1 == l1 ? l2 : 0x80, c1 == h1 ? h2 : 0xBF);
+    } else {
+      for (int lead = l0; lead <= h0; lead++) {
+        const int c1lo = lead == l0 ? l1 : (lead == 0xE0 ? 0xA0 : 0x80);
+        const int c1hi = lead == h0 ? h1 : (lead == 0xED ? 0x9F : 0xBF);
+        for (int c1 = c1lo; c1 <= c1hi; c1++)
+          branch(lead, c1, (lead == l0 && c1 == l1) ? l2 : 0x80, (lead == h0 && c1 == h1) ? h2 : 0xBF);
+      }
+    }
+  }
+
+  // reference nfa/compile.go:796-842: four-byte ranges are widened to whole lead bytes
+  void utf8Range4(int32_t lo, int32_t hi, StateID end, std::vector<StateID>& out) {
+    if (hi > 0x10FFFF) hi = 0x10FFFF;
+    if (lo < 0x10000) lo = 0x10000;
+    if (lo > hi) return;
+    const int l0 = 0xF0 | (lo >> 18), h0 = 0xF0 | (hi >> 18);
+    for (int lead = l0; lead <= h0; lead++) {
+      StateID s3 = b.AddByteRange(0x80, 0xBF, end);
+      StateID s2 = b.AddByteRange(0x80, 0xBF, s3);
+      StateID s1 = b.AddByteRange(lead == 0xF0 ? 0x90 : 0x80, lead == 0xF4 ? 0x8F : 0xBF, s2);
+      out.push_back(b.AddByteRange((uint8_t)lead, (uint8_t)lead, s1));
+    }
+  }
+
+  // reference nfa/compile.go:845-917: all valid multi-byte sequences, no state sharing
+  void buildUTF8NonASCIIBranches(StateID end, std::vector<StateID>& out) {
+    struct Seq { uint8_t n, r[4][2]; };
+    static const Seq seqs[8] = {
+        {2, {{0xC2, 0xDF}, {0x80, 0xBF}}},
+        {3, {{0xE0, 0xE0}, {0xA0, 0xBF}, {0x80, 0xBF}}},
+        {3, {{0xE1, 0xEC}, {0x80, 0xBF}, {0x80, 0xBF}}},
+        {3, {{0xED, 0xED}, {0x80, 0x9F}, {0x80, 0xBF}}},
+        {3, {{0xEE, 0xEF}, {0x80, 0xBF}, {0x80, 0xBF}}},
+        {4, {{0xF0, 0xF0}, {0x90, 0xBF}, {0x80, 0xBF}, {0x80, 0xBF}}},
+        {4, {{0xF1, 0xF3}, {0x80, 0xBF}, {0x80, 0xBF}, {0x80, 0xBF}}},
+        {4, {{0xF4, 0xF4}, {0x80, 0x8F}, {0x80, 0xBF}, {0x80, 0xBF}}},
+    };
+    for (const Seq& q : seqs) {
+      StateID t = end;
+      for (int i = q.n - 1; i >= 0; i--) t = b.AddByteRange(q.r[i][0], q.r[i][1], t);
+      out.push_back(t);
+    }
+  }
+
+  // reference nfa/utf8_suffix.go:30-123: direct-mapped 64-entry cache keyed by (target, lo, hi);
+  // a colliding key simply overwrites, so which suffix states are shared depends on the hash
+  struct SuffixCache {
+    struct E { bool used = false; StateID from = 0; uint8_t lo = 0, hi = 0; StateID val = 0; };
+    E e[64];
+    static int slot(StateID from, uint8_t lo, uint8_t hi) {
+      uint64_t h = 14695981039346656037ull;
+      h = (h ^ (uint64_t)from) * 1099511628211ull;
+      h = (h ^ (uint64_t)lo) * 1099511628211ull;
+      h = (h ^ (uint64_t)hi) * 1099511628211ull;
+      return (int)(h % 64);
+    }
+  };
+  StateID suffixState(SuffixCache& c, StateID target, uint8_t lo, uint8_t hi) {
+    auto& x = c.e[SuffixCache::slot(target, lo, hi)];
+    if (x.used && x.from == target && x.lo == lo && x.hi == hi) return x.val;
+    StateID s = b.AddByteRange(lo, hi, target);
+    x.used = true; x.from = target; x.lo = lo; x.hi = hi; x.val = s;
+    return s;
+  }
+
+  // reference nfa/compile.go:1142-1223: `.` / (?s:.) = ASCII | valid multi-byte sequences (suffix
+  // states shared through the cache) | single stray bytes 80-BF, C0-C1, F5-FF
+  bool compileUTF8Any(bool include_nl, Frag& f) {
+    StateID end = b.AddEpsilon(InvalidState);
+    SuffixCache cache;
+    std::vector<StateID> br;
+    if (include_nl) {
+      br.push_back(b.AddByteRange(0x00, 0x7F, end));
+    } else {
+      br.push_back(b.AddSparse({{0x00, 0x09, end}, {0x0B, 0x7F, end}}));
+    }
+    static const uint8_t seqs[8][9] = {
+        {2, 0xC2, 0xDF, 0x80, 0xBF}, {3, 0xE0, 0xE0, 0xA0, 0xBF, 0x80, 0xBF}, {3, 0xE1, 0xEC, 0x80, 0xBF, 0x80, 0xBF},
+        {3, 0xED, 0xED, 0x80, 0x9F, 0x80, 0xBF}, {3, 0xEE, 0xEF, 0x80, 0xBF, 0x80, 0xBF},
+        {4, 0xF0, 0xF0, 0x90, 0xBF, 0x80, 0xBF, 0x80, 0xBF}, {4, 0xF1, 0xF3, 0x80, 0xBF, 0x80, 0xBF, 0x80, 0xBF},
+        {4, 0xF4, 0xF4, 0x80, 0x8F, 0x80, 0xBF, 0x80, 0xBF}};
+    for (auto& q : seqs) {
+      StateID t = end;
+      for (int i = q[0] - 1; i >= 0; i--) t = suffixState(cache, t, q[1 + 2 * i], q[2 + 2 * i]);
+      br.push_back(t);
+    }
+    br.push_back(b.AddSparse({{0x80, 0xBF, end}, {0xC0, 0xC1, end}, {0xF5, 0xFF, end}}));
+    f = {buildSplitChain(br), end};
     return true;
   }
 
@@ -449,9 +665,8 @@ struct Compiler {
     switch (re->op) {
       case OpLiteral: return compileLiteral(re, f);
       case OpCharClass: return compileCharClass(re->rune, f);
-      case OpAnyChar:
-      case OpAnyCharNotNL:
-        return fail("unsupported: `.` (UTF-8 automata out of scope)");
+      case OpAnyChar: return compileUTF8Any(true, f);        // reference nfa/compile.go:977-985
+      case OpAnyCharNotNL: return compileUTF8Any(false, f);  // reference nfa/compile.go:995-1003
       case OpConcat: return compileConcat(re->sub, f);
       case OpAlternate: return compileAlternate(re->sub, f);
       case OpStar: return compileStar(re->sub[0], ng, f);

@@ -271,3 +271,24 @@ def test_pipelined_host_path_matches_oracle(tmp_path):
     env = dict(os.environ, CGX_PIPELINE_PIECE=str(192 * 1024))
     p = subprocess.run([sys.executable, "-c", _PIPE_CHILD, ROOT], env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
+
+
+# ---- `.`, negated and non-ASCII classes (UTF-8 byte automata), well-formed and malformed input ---------
+UTF8_GPU = [r"a.c", r"foo.*bar", r"[^a\n]+", r"\S+", r"[α-ω]+", r"key=[^\s;]+", r"[^\d\n]{2,3}", r"x.y.z",
+            r"[а-я]+ [а-я]+", r"(?i)straße|x.z", r"GET .* HTTP", r"[^\x00-\x{7FF}\n]+", r"é+"]
+
+
+def _utf8_corpus(rng, n):
+    pieces = [b"a", b"b", b"c", b"x", b"y", b"z", b"foo", b"bar", b" ", b" ", b"\n", b"key=", b";", "é".encode(),
+              "α".encode(), "ω".encode(), "βγ".encode(), "привет".encode(), "мир".encode(), "ß".encode(), "€".encode(),
+              "世界".encode(), "😀".encode(), b"\x80", b"\xbf", b"\xc3", b"\xe0\x80", b"\xed\xa0\x80", b"\xf0\x90",
+              b"\xff", b"GET /", b" HTTP", b"stra", b"Stra\xc3\x9fe", b"12", b"a\xc3\xa9c"]
+    return b"".join(pieces[int(i)] for i in rng.integers(0, len(pieces), n))
+
+
+@pytest.mark.parametrize("pat", UTF8_GPU)
+def test_utf8_patterns_match_oracle(pat):
+    rng = np.random.default_rng(29)
+    o = Oracle(pat)
+    for n in (40, 3000, 60000):
+        check(pat, _utf8_corpus(rng, n), o)

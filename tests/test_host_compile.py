@@ -44,7 +44,7 @@ def test_compile_errors_are_go_formatted():
 
 
 def test_unsupported_patterns_fail_loudly():
-    for pat in ["a*", r"x.y", r"[^a]+", r"[a-z]+\s+[a-z]+", r"\pL"]:
+    for pat in ["a*", r"(?s)x.y", r"[^a]+", r"[a-z]+\s+[a-z]+", r"\pL"]:  # nullable / can span \n / Unicode tables
         with pytest.raises(cg.UnsupportedError):
             cg.Compile(pat)
 
@@ -177,3 +177,27 @@ def test_flat_start_filter_is_exact_superset(pat):
         for p in range(n):
             ok = tm.walk(h, p) >= 0
             assert ok == bool((S >> p) & 1), (pat, h, p)
+
+
+UTF8_PATTERNS = [r"a.c", r"foo.*bar", r"[^a\n]+", r"\S+", r"[α-ω]+", r"x.y.z", r"[^\s\"]+=.", r"[\x{100}-\x{17F}]+x",
+                 r"[^\x00-\x{7FF}\n]+", r"é+", r"(?i)straße|x.z", r"[\x{10000}-\x{10200}]", r"[\x{90000}-\x{10FFFF}]x", r"a[^b\n]c",
+                 r"[\x{7F0}-\x{810}]+", r"[\x{D700}-\x{E010}]", r"[^\d\n]{2,3}", r"[^x\n]{3}y"]
+
+
+@pytest.mark.parametrize("pat", UTF8_PATTERNS)
+def test_utf8_tables_match_oracle(pat):
+    """`.`, negated and non-ASCII classes: the product's own UTF-8 byte automaton (host/prog.cpp) must
+    define the same leftmost-first matches as the restated reference automaton (oracle/nfa.cpp,
+    nfa/compile.go:440-1223), on well-formed AND malformed UTF-8."""
+    rng = np.random.default_rng(23)
+    m = TableModel(cg.Compile(pat))
+    o = Oracle(pat)
+    pieces = [b"a", b"b", b"c", b"x", b"y", b"z", b"foo", b"bar", b" ", b"\n", b"=", b"\"", "é".encode(), "α".encode(),
+              "ω".encode(), "β".encode(), "Ł".encode(), "ſ".encode(), "ß".encode(), "€".encode(), "ߵ".encode(),
+              "ࠅ".encode(), "퟿".encode(), "".encode(), "𐀀".encode(), "𐀂".encode(), "😀".encode(),
+              "\U0010ffff".encode(), b"\x80", b"\xbf", b"\xc0", b"\xc3", b"\xe0", b"\xe0\x80", b"\xed\xa0\x80",
+              b"\xf0\x90", b"\xf4\x90\x80\x80", b"\xf5", b"\xff", b"stra", b"STRASSE", b"Stra\xc3\x9fe"]
+    for it in range(250):
+        k = int(rng.integers(0, 14))
+        h = b"".join(pieces[int(i)] for i in rng.integers(0, len(pieces), k))
+        assert m.find_all(h) == o.find_all(h).tolist(), (pat, h)

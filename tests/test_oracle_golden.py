@@ -173,3 +173,64 @@ def test_golden_fixture_replay():
     for v in vec:
         got = Oracle(v["pattern"]).find_all(corpus)[:1000].tolist()
         assert got == v["matches"], v["pattern"]
+
+
+# ---- reference known-answer vectors for UTF-8 patterns (harvested by tests/golden/harvest_utf8_vectors.py
+# from nfa/compile_utf8_test.go) -------------------------------------------------------------------------
+def _utf8_vectors():
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_utf8_vectors.json")
+    return json.load(open(path, encoding="utf-8"))["vectors"]
+
+
+@pytest.mark.parametrize("v", _utf8_vectors(), ids=lambda v: v["pattern"].encode("unicode_escape").decode()[:24])
+def test_reference_utf8_vectors(v):
+    pat = v["pattern"]
+    if "\\p" in pat:
+        pytest.skip("Unicode property tables (\\pL, \\pN) are out of scope (SURVEY §2.1)")
+    hay = bytes.fromhex(v["haystack_hex"])
+    o = Oracle(pat)
+    if "first" in v:
+        got = o.find_at(hay, 0)
+        assert (list(got) if got else None) == v["first"]
+        allm = o.find_all(hay).tolist()
+        assert (allm[0] if allm else None) == v["first"]
+    else:
+        assert o.is_match(hay) == v["is_match"]
+
+
+UTF8_DIFF = [r"a.c", r".*мир.*", r"[а-я]+", r"[^a\n]+", r"\S+", r"\W+", r"x.y", r"[^\s=]+=[^\s]*", r".+", r"(?s)a.b",
+             r"[一-龥]+", r"é|e", r"[^é]", r"(?i)привет|a.z"]
+
+
+@pytest.mark.parametrize("pat", UTF8_DIFF)
+def test_utf8_patterns_equal_stdlib_semantics_on_valid_utf8(pat):
+    """On well-formed UTF-8 the reference asserts equality with Go's stdlib
+    (nfa/compile_utf8_test.go TestCompileUTF8_VsStdlib); Python's str-mode `re` with re.ASCII has the
+    same semantics for these constructs, so it stands in for the stdlib here."""
+    rng = np.random.default_rng(41)
+    o = Oracle(pat)
+    rx = re.compile(pat, re.ASCII)
+    atoms = ["a", "b", "c", "x", "y", "z", " ", "\n", "=", "é", "e", "мир", "привет", "ПРИВЕТ", "я", "世", "界", "😀", "1", "Z"]
+    for it in range(120):
+        text = "".join(atoms[int(i)] for i in rng.integers(0, len(atoms), int(rng.integers(0, 16))))
+        # char index -> byte offset
+        offs = [0]
+        for ch in text:
+            offs.append(offs[-1] + len(ch.encode()))
+        want = []
+        pos = 0
+        # Go FindAll semantics for empty matches do not arise here: none of the patterns is nullable
+        for m in rx.finditer(text):
+            want.append([offs[m.start()], offs[m.end()]])
+        assert o.find_all(text.encode()).tolist() == want, (pat, text)
+
+
+def test_negated_class_stray_byte_fallback_quirk():
+    """Reference quirk (nfa/compile.go:566-570): a class that covers everything above 0x7F gets, as its
+    LAST alternative, "any single byte 0x80-0xFF".  A counted repetition that cannot be satisfied in
+    whole code points therefore backtracks into counting the bytes of one code point as several
+    characters: stdlib finds only [0,6) for `\\D{2,3}` in "мир😀", the restated automaton also yields the
+    first three bytes of the emoji.  Kept in the oracle AND reproduced by the product's tables
+    (tests/test_host_compile.py::test_utf8_tables_match_oracle)."""
+    assert Oracle(r"\D{2,3}").find_all("мир😀".encode()).tolist() == [[0, 6], [6, 9]]
