@@ -16,7 +16,7 @@
 #include "synth.h"
 
 namespace cgx {
-size_t scan_dfa_smem_bytes(int nstates, int teddy_blob_bytes);
+size_t scan_dfa_smem_bytes(int nstates, int blob_bytes);
 int64_t scan_dfa_chunks(int64_t n);
 cudaError_t launch_scan_dfa(const ScanArgs& a, int sm_count, cudaStream_t stream);
 cudaError_t launch_pike_captures(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
@@ -68,8 +68,9 @@ struct cgx_regex {
   int device = -1;
   int sm_count = 0;
   // device copies of the tables
-  DevBuf d_trans, d_eoi, d_lut, d_teddy;
+  DevBuf d_trans, d_eoi, d_lut, d_teddy, d_line;
   TeddyDev teddy_dev;
+  LineDev line_dev;
   // per-call scratch (serialised by mu)
   DevBuf d_ticket_total, d_status, d_hay, d_out, d_pairs, d_pike;
   // pipelined host path: two haystack/output slots, three streams, pinned per-slot results
@@ -127,6 +128,29 @@ struct cgx_regex {
       CU(cudaMemcpy(d_trans.p, c->dfa.trans.data(), c->dfa.trans.size() * 2, cudaMemcpyHostToDevice));
       CU(cudaMemcpy(d_eoi.p, c->dfa.eoi.data(), c->dfa.eoi.size(), cudaMemcpyHostToDevice));
       CU(cudaMemcpy(d_lut.p, c->lut, 256, cudaMemcpyHostToDevice));
+    }
+    memset(&line_dev, 0, sizeof line_dev);
+    if (c->kind == ENG_LINE) {
+      const DfaTables &u = c->udfa, &rv = c->rdfa;
+      std::vector<uint16_t> blob(u.trans.size() + rv.trans.size() + (u.nstates + rv.nstates + 3) / 2 + 8, 0);
+      memcpy(blob.data(), u.trans.data(), u.trans.size() * 2);
+      memcpy(blob.data() + u.trans.size(), rv.trans.data(), rv.trans.size() * 2);
+      uint8_t* e = reinterpret_cast<uint8_t*>(blob.data() + u.trans.size() + rv.trans.size());
+      memcpy(e, u.eoi.data(), u.nstates);
+      memcpy(e + u.nstates, rv.eoi.data(), rv.nstates);
+      int r;
+      if ((r = d_line.ensure(blob.size() * 2))) return r;
+      CU(cudaMemcpy(d_line.p, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice));
+      line_dev.blob = (const uint16_t*)d_line.p;
+      line_dev.un = u.nstates;
+      line_dev.rn = rv.nstates;
+      for (int k = 0; k < 5; k++) {
+        line_dev.ustart[k] = u.start[k];
+        line_dev.rstart[k] = rv.start[k];
+        if (u.start[k] != u.start[0]) line_dev.ukinds = 1;
+        if (rv.start[k] != rv.start[0]) line_dev.rkinds = 1;
+      }
+      line_dev.blob_bytes = (int)(blob.size() * 2);
     }
     memset(&teddy_dev, 0, sizeof teddy_dev);
     if (c->kind == ENG_TEDDY) {
@@ -206,7 +230,7 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
     g_last_error = "device pointers must be 16-byte aligned";
     return CGX_ERR_ARGS;
   }
-  if (c.kind != ENG_DFA && c.kind != ENG_TEDDY) {
+  if (c.kind != ENG_DFA && c.kind != ENG_TEDDY && c.kind != ENG_LINE) {
     g_last_error = "engine not available in this build";
     return CGX_ERR_UNSUPPORTED;
   }
@@ -250,6 +274,17 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   if (c.kind != ENG_TEDDY) {
     a.skip_safe = c.skip_safe ? 1 : 0;
     a.delim = c.delim;
+  }
+  if (c.kind == ENG_LINE) {
+    a.engine = SEL_LINE;
+    a.line = re->line_dev;
+    a.dfa.nstates = 0;  // the anchored table is not shipped; phase A marks record delimiters
+    a.flat.nops = 0;
+    a.filter.kind = F_BYTESET;
+    a.filter.nranges = 1;
+    a.filter.lo[0] = a.filter.hi[0] = c.delim;
+    a.filter.lut = nullptr;
+    a.skip_safe = 0;
   }
   a.mode = mode;
   a.out = d_out;
@@ -542,6 +577,27 @@ int cgx_find_all_submatch_index(cgx_regex* re, const uint8_t* h, size_t len, int
 }
 
 // ---- debug exports (tests only): the compiled tables exactly as the kernels see them ------------
+// record-engine tables for the CPU model in tests/table_model.py (1 = pattern runs on that engine)
+int cgx_debug_line_info(const cgx_regex* re, int* un, int* rn, uint16_t ustart[5], uint16_t rstart[5]) {
+  const Compiled& c = *re->c;
+  if (c.kind != ENG_LINE) return 0;
+  *un = c.udfa.nstates;
+  *rn = c.rdfa.nstates;
+  for (int k = 0; k < 5; k++) {
+    ustart[k] = c.udfa.start[k];
+    rstart[k] = c.rdfa.start[k];
+  }
+  return 1;
+}
+int cgx_debug_line_copy(const cgx_regex* re, uint16_t* ut, uint16_t* rt, uint8_t* ueoi, uint8_t* reoi) {
+  const Compiled& c = *re->c;
+  if (c.kind != ENG_LINE) return 0;
+  memcpy(ut, c.udfa.trans.data(), c.udfa.trans.size() * 2);
+  memcpy(rt, c.rdfa.trans.data(), c.rdfa.trans.size() * 2);
+  memcpy(ueoi, c.udfa.eoi.data(), c.udfa.eoi.size());
+  memcpy(reoi, c.rdfa.eoi.data(), c.rdfa.eoi.size());
+  return 1;
+}
 // the 64-byte per-call scratch {total, flag, t2, t3, ticket, t5, t6, t7}; the t* slots are phase
 // cycle counters in the -DCGX_TIMING build (tools/phase_timing.py) and zero otherwise
 int cgx_debug_scratch(cgx_regex* re, uint64_t out[8]) {

@@ -148,7 +148,7 @@ struct Det {
 
 }  // namespace
 
-std::string BuildDFA(const Prog& p, bool anchored, int max_states, DfaTables& out) {
+std::string BuildDFA(const Prog& p, bool anchored, int max_states, DfaTables& out, bool longest) {
   Det d(p, !anchored);
   d.states.emplace_back();  // DEAD
   out = DfaTables();
@@ -182,7 +182,7 @@ std::string BuildDFA(const Prog& p, bool anchored, int max_states, DfaTables& ou
       for (size_t i = 0; i < ex.size(); i++)
         if (ex[i] != RESTART && p.inst[ex[i]].op == I_MATCH) {
           match_before = true;
-          cut = i;
+          if (!longest) cut = i;
           break;
         }
       Ctx nc;

@@ -43,7 +43,11 @@ struct DfaTables {
 // anchored: true -> match must begin at the walk start (the only mode the candidate kernels use)
 //           false -> prepend the (?s:.)*? prefix (unanchored forward DFA, N1)
 // Returns "" or an error ("dfa too large: ...").
-std::string BuildDFA(const Prog& p, bool anchored, int max_states, DfaTables& out);
+// longest:  false -> leftmost-first (everything after the first Match thread is cut)
+//           true  -> no cut: the flag says "some thread matches here"; walking on and keeping the
+//                    last flag yields the longest match (reverse DFAs: the leftmost start,
+//                    reference dfa/lazy/lazy.go:1769-1920 with BreakAtMatch=false)
+std::string BuildDFA(const Prog& p, bool anchored, int max_states, DfaTables& out, bool longest = false);
 
 // true when no match can contain byte d (every live state goes DEAD on d)
 bool DelimiterSafe(const DfaTables& t, uint8_t d);

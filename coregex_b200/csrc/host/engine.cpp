@@ -299,6 +299,22 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
       }
     }
     if (c->flat.nops) c->engine_name += "+flat";
+    // A pattern that can begin with (almost) any byte has no useful candidate filter: every
+    // position would start an anchored walk, which is quadratic per record.  Such patterns run
+    // the way the reference runs UseDFA patterns (meta/find_indices.go:686-705): one unanchored
+    // forward DFA pass for the match end, one reverse DFA pass for its start — per record, linear.
+    int first = 0;
+    for (int b = 0; b < 256; b++) first += set_has(c->dfa.first_bytes, b) ? 1 : 0;
+    if (!c->flat.nops && first > 64) {
+      Prog rprog;
+      if (CompileReverseProg(pr.re, rprog).empty() &&
+          BuildDFA(c->prog, /*anchored=*/false, 160, c->udfa).empty() &&
+          BuildDFA(rprog, /*anchored=*/true, 160, c->rdfa, /*longest=*/true).empty() &&
+          c->udfa.nstates + c->rdfa.nstates <= 200 && !c->rdfa.matches_empty) {
+        c->kind = ENG_LINE;
+        c->engine_name = "line-dfa";
+      }
+    }
   }
   c->pike_err = PackPike(c->prog, c->pike);
   c->has_pike = c->pike_err.empty();

@@ -18,6 +18,7 @@ enum EngineKind : int {
   ENG_DFA = 0,     // candidate filter + anchored DFA walk (scan_dfa.cu)
   ENG_TEDDY,       // nibble-fingerprint filter + ordered literal verify (scan_teddy.cu)
   ENG_PIKEVM,      // captures (pikevm_kernel.cu)
+  ENG_LINE,        // one lane per record: unanchored forward DFA + reverse DFA (scan_dfa.cu)
 };
 
 struct Compiled {
@@ -39,6 +40,9 @@ struct Compiled {
   bool kind_lut_needed = false;
   FlatDev flat;  // nops == 0 when the pattern is not flat
   uint8_t delim = '\n';
+
+  // ENG_LINE: unanchored forward DFA (leftmost-first end) and reverse DFA (longest = leftmost start)
+  DfaTables udfa, rdfa;
 
   // ENG_TEDDY
   TeddyTables teddy;

@@ -87,6 +87,11 @@ struct Ctx {
   const int32_t* t_offs;
   const uint16_t* t_order;
   const uint16_t* t_boff;
+  // record engine tables (shared memory copies)
+  const uint16_t* l_ut;
+  const uint16_t* l_rt;
+  const uint8_t* l_ueoi;
+  const uint8_t* l_reoi;
 };
 
 __device__ __forceinline__ uint8_t byte_at(const Ctx& c, int64_t p) {
@@ -605,6 +610,104 @@ __device__ int serial_chain(const Ctx& c, Emitter<DIRECT>& em, int pos_i, int la
   return pos_i;
 }
 
+// ---- record engine: one lane per record ----------------------------------------------------------
+// The reference's UseDFA path (meta/find_indices.go:686-705, dfa/lazy/lazy.go:1102-1315 forward,
+// :1769-1920 reverse): the unanchored forward DFA yields the end of the leftmost-first match, the
+// reverse DFA (no break at match, last flag wins) its start; the search resumes at the end.
+// Positions are window indices; bytes past the window come from global memory.
+__device__ __forceinline__ unsigned line_byte(const Ctx& c, int i) {
+  return i < WIN ? (unsigned)c.sm.win[i] : (unsigned)__ldg(c.a.h + c.gw + i);
+}
+__device__ __forceinline__ int kind_before(const Ctx& c, int i) {
+  return (c.gw + i == 0) ? (c.a.base == 0 ? 2 : 3) : start_kind((uint8_t)line_byte(c, i - 1));
+}
+// start of the match that ends at e, not before lo
+__device__ int line_reverse(const Ctx& c, int e, int lo, int nrel) {
+  unsigned st = c.a.line.rstart[0];
+  if (c.a.line.rkinds) st = c.a.line.rstart[e >= nrel ? (c.a.after == 0 ? 2 : 3) : start_kind((uint8_t)line_byte(c, e))];
+  int last = lo, q = e;
+  while (st) {
+    if (q == lo) {
+      // lower bound reached: only the pending flag counts (look-behind needs the byte before lo)
+      if (c.gw + q == 0 && c.a.base == 0) {
+        if (c.l_reoi[st]) last = q;
+      } else {
+        const unsigned b = c.gw + q == 0 ? (unsigned)c.a.delim : line_byte(c, q - 1);
+        if (c.l_rt[(st << 8) + b] & 0x8000u) last = q;
+      }
+      break;
+    }
+    const unsigned t = c.l_rt[(st << 8) + line_byte(c, q - 1)];
+    if (t & 0x8000u) last = q;
+    st = t & 0x7FFFu;
+    q--;
+  }
+  return last;
+}
+// all matches of the record that starts at window index i0.  EMIT=false: count them and remember
+// the first two ends; EMIT=true: write (start,end) to consecutive output slots from `idx`.
+template <bool EMIT, bool DIRECT>
+__device__ void line_scan(const Ctx& c, Emitter<DIRECT>& em, int i0, unsigned idx, int& cnt, int& e0, int& e1) {
+  const int64_t nr64 = c.a.n - c.gw;
+  const int nrel = nr64 > 0x7fffffff ? 0x7fffffff : (int)nr64;
+  int pos = i0;
+  for (;;) {
+    unsigned st = c.a.line.ustart[0];
+    if (c.a.line.ukinds) st = c.a.line.ustart[kind_before(c, pos)];
+    int last = -1, i = pos;
+    while (st) {
+      if (i >= nrel) {
+        if (c.l_ueoi[st]) last = i;
+        break;
+      }
+      const unsigned b = line_byte(c, i);
+      const unsigned t = c.l_ut[(st << 8) + b];
+      if (t & 0x8000u) last = i;
+      st = t & 0x7FFFu;
+      if (b == c.a.delim) break;
+      i++;
+    }
+    if (last < 0) break;
+    if (EMIT) {
+      em.put(idx + cnt, line_reverse(c, last, pos, nrel), last);
+    } else {
+      if (cnt == 0) e0 = last;
+      if (cnt == 1) e1 = last;
+    }
+    cnt++;
+    if (c.a.mode == M_ISMATCH) break;
+    pos = last;  // matches are non-empty, so this advances
+  }
+}
+
+template <bool DIRECT>
+__device__ void process_batch_lines(const Ctx& c, Emitter<DIRECT>& em, int cand, bool valid) {
+  int cnt = 0, e0 = -1, e1 = -1;
+  if (valid) line_scan<false, DIRECT>(c, em, cand, 0, cnt, e0, e1);
+  int total;
+  const int excl = warp_excl_scan(cnt, c.lane, total);
+  if (!total) return;
+  if (c.a.mode == M_ISMATCH) {
+    if (c.lane == 0) c.a.total[1] = 1ull;
+    em.nkept += total;
+    return;
+  }
+  if (c.a.mode == M_FINDALL && cnt) {
+    const int64_t nr64 = c.a.n - c.gw;
+    const int nrel = nr64 > 0x7fffffff ? 0x7fffffff : (int)nr64;
+    const unsigned idx = em.nkept + excl;
+    if (cnt <= 2) {
+      em.put(idx, line_reverse(c, e0, cand, nrel), e0);
+      if (cnt == 2) em.put(idx + 1, line_reverse(c, e1, e0, nrel), e1);
+    } else {
+      int k = 0, x0, x1;
+      line_scan<true, DIRECT>(c, em, cand, idx, k, x0, x1);
+    }
+  }
+  if (!DIRECT && em.nkept + total > STG) em.overflow = true;
+  em.nkept += total;
+}
+
 template <bool DIRECT>
 __device__ __forceinline__ int process_batch(const Ctx& c, Emitter<DIRECT>& em, int cand, bool valid,
                                              int kept_end) {
@@ -683,8 +786,17 @@ __device__ void phase_b(const Ctx& c, Emitter<DIRECT>& em) {
   int kept_end = (int)(lo - c.gw);
   uint16_t* q = c.sm.queue[c.warp];
   int qlen = 0;
+  const bool lines = c.a.engine == SEL_LINE;
   const int lo_rel = (int)(lo - c.cbeg);
-  const int hi_rel = (int)(hi_b - c.cbeg);
+  int hi_rel = (int)(hi_b - c.cbeg);
+  if (lines) {
+    // the bitmap marks record delimiters: the owned records are the one starting at `lo` plus
+    // one after every delimiter in [lo, hi-1) (the delimiter at hi-1 opens the next owner's record)
+    if (hi <= bm_end) hi_rel -= 1;
+    if (c.lane == 0) q[0] = (uint16_t)(lo - c.gw);
+    qlen = 1;
+    __syncwarp();
+  }
   // Four bitmap words per lane and step (4 KB of input): count, warp-scan, then every lane appends
   // its own candidates to the queue in position order.  A step that holds more candidates than the
   // queue can take (dense data) is split into passes of four lanes each.
@@ -693,7 +805,8 @@ __device__ void phase_b(const Ctx& c, Emitter<DIRECT>& em) {
     __syncwarp();
     int head = 0;
     while (qlen - head >= 32) {
-      kept_end = process_batch<DIRECT>(c, em, q[head + c.lane], true, kept_end);
+      if (lines) process_batch_lines<DIRECT>(c, em, q[head + c.lane], true);
+      else kept_end = process_batch<DIRECT>(c, em, q[head + c.lane], true, kept_end);
       head += 32;
     }
     if (head) {
@@ -726,7 +839,7 @@ __device__ void phase_b(const Ctx& c, Emitter<DIRECT>& em) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         uint32_t v = wd[k];
-        const int base = (w0 + k) * 32 + PRE;  // window index of bit 0
+        const int base = (w0 + k) * 32 + PRE + (lines ? 1 : 0);  // window index of bit 0 (record: byte after)
         while (v) {
           q[off++] = (uint16_t)(base + __ffs(v) - 1);
           v &= v - 1;
@@ -752,9 +865,10 @@ __device__ void phase_b(const Ctx& c, Emitter<DIRECT>& em) {
   }
   if (qlen) {
     const bool valid = c.lane < qlen;
-    kept_end = process_batch<DIRECT>(c, em, valid ? q[c.lane] : 0, valid, kept_end);
+    if (lines) process_batch_lines<DIRECT>(c, em, valid ? q[c.lane] : 0, valid);
+    else kept_end = process_batch<DIRECT>(c, em, valid ? q[c.lane] : 0, valid, kept_end);
   }
-  if (hi > bm_end) {
+  if (hi > bm_end && !lines) {
     // the last owned line runs past the classified window: finish it serially
     const int bme = (int)(bm_end - c.gw);
     serial_chain<DIRECT>(c, em, kept_end > bme ? kept_end : bme, 0, true);
@@ -839,6 +953,12 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
   if (a.engine == SEL_TEDDY)
     for (int i = tid; i < a.teddy.blob_bytes / 4; i += THREADS)
       reinterpret_cast<uint32_t*>(smem_raw + sizeof(Smem))[i] = a.teddy.fp[i];
+  if (a.engine == SEL_LINE)
+    for (int i = tid; i < a.line.blob_bytes / 4; i += THREADS)
+      reinterpret_cast<uint32_t*>(smem_raw + sizeof(Smem))[i] = reinterpret_cast<const uint32_t*>(a.line.blob)[i];
+  const uint16_t* l_ut = reinterpret_cast<const uint16_t*>(smem_raw + sizeof(Smem));
+  const uint16_t* l_rt = l_ut + (size_t)a.line.un * 256;
+  const uint8_t* l_ueoi = reinterpret_cast<const uint8_t*>(l_rt + (size_t)a.line.rn * 256);
   const unsigned char* g_blob = reinterpret_cast<const unsigned char*>(a.teddy.fp);
   if (a.filter.kind == F_LUT)
     for (int i = tid; i < 256; i += THREADS) s_lut[i] = a.filter.lut[i];
@@ -932,7 +1052,8 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
           t_blob + (a.teddy.bytes - g_blob),
           reinterpret_cast<const int32_t*>(t_blob + ((const unsigned char*)a.teddy.offs - g_blob)),
           reinterpret_cast<const uint16_t*>(t_blob + ((const unsigned char*)a.teddy.order - g_blob)),
-          reinterpret_cast<const uint16_t*>(t_blob + ((const unsigned char*)a.teddy.bucket_off - g_blob))};
+          reinterpret_cast<const uint16_t*>(t_blob + ((const unsigned char*)a.teddy.bucket_off - g_blob)),
+          l_ut, l_rt, l_ueoi, l_ueoi + a.line.un};
     if (a.engine == SEL_TEDDY) phase_a_teddy(c);
     else if (a.flat.nops) phase_a_flat(c);
     else phase_a_plain(c);
@@ -1012,8 +1133,8 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
 
 }  // namespace
 
-size_t scan_dfa_smem_bytes(int nstates, int teddy_blob_bytes) {
-  if (teddy_blob_bytes) return sizeof(Smem) + (size_t)teddy_blob_bytes + 16;
+size_t scan_dfa_smem_bytes(int nstates, int blob_bytes) {
+  if (blob_bytes) return sizeof(Smem) + (size_t)blob_bytes + 16;
   return sizeof(Smem) + (size_t)nstates * 1024 + ((nstates + 15) & ~15) + 256;
 }
 
@@ -1022,7 +1143,8 @@ int64_t scan_dfa_chunks(int64_t n) { return n <= 0 ? 0 : (n + CH - 1) / CH; }
 // Launches the scan on `stream`.  ticket/status/total must be zeroed by the caller.
 cudaError_t launch_scan_dfa(const ScanArgs& a, int sm_count, cudaStream_t stream) {
   if (a.nchunks == 0) return cudaSuccess;
-  const size_t smem = scan_dfa_smem_bytes(a.dfa.nstates, a.engine == SEL_TEDDY ? a.teddy.blob_bytes : 0);
+  const size_t smem = scan_dfa_smem_bytes(a.dfa.nstates, a.engine == SEL_TEDDY ? a.teddy.blob_bytes
+                                                               : a.engine == SEL_LINE ? a.line.blob_bytes : 0);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(scan_dfa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

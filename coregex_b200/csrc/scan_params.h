@@ -64,7 +64,17 @@ struct TeddyDev {
   int blob_bytes;            // size of the single allocation that starts at `fp`
 };
 
-enum EngineSel : int { SEL_DFA = 0, SEL_TEDDY = 1 };
+// Record engine tables: unanchored forward DFA (u*) and reverse DFA (r*), one u16 blob
+// utrans[un*256] | rtrans[rn*256] | ueoi[un] | reoi[rn]; entries = next | flag<<15 as in DfaDev.
+struct LineDev {
+  const uint16_t* blob;
+  int un, rn;
+  uint16_t ustart[5], rstart[5];
+  uint8_t ukinds, rkinds;  // 1 when the start state depends on the neighbouring byte
+  int blob_bytes;
+};
+
+enum EngineSel : int { SEL_DFA = 0, SEL_TEDDY = 1, SEL_LINE = 2 };
 
 struct ScanArgs {
   const uint8_t* h;   // device haystack, 16-byte aligned
@@ -76,6 +86,7 @@ struct ScanArgs {
   FilterDev filter;
   FlatDev flat;
   TeddyDev teddy;
+  LineDev line;
   int engine;         // EngineSel
   int skip_safe;      // 1: after a match, a candidate in the middle of a run must still be tried
   uint8_t delim;      // record delimiter no match can contain

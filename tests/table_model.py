@@ -133,3 +133,79 @@ class FlatModel:
                     plus = nxt
                 M = plus if kind == 1 else (M | plus)
         return M
+
+
+_L.cgx_debug_line_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+_L.cgx_debug_line_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+
+
+class LineModel:
+    """CPU replay of the record engine (one lane per record in scan_dfa.cu): unanchored forward DFA
+    for the leftmost-first end, reverse DFA (last flag wins) for the start, resume at the end."""
+
+    def __init__(self, regex):
+        un, rn = C.c_int(), C.c_int()
+        us, rs = np.zeros(5, dtype=np.uint16), np.zeros(5, dtype=np.uint16)
+        ok = _L.cgx_debug_line_info(regex._h, C.byref(un), C.byref(rn), us.ctypes.data, rs.ctypes.data)
+        assert ok == 1, "not a record-engine pattern"
+        self.un, self.rn, self.us, self.rs = un.value, rn.value, us, rs
+        self.ut = np.zeros(self.un * 256, dtype=np.uint16)
+        self.rt = np.zeros(self.rn * 256, dtype=np.uint16)
+        self.ueoi = np.zeros(self.un, dtype=np.uint8)
+        self.reoi = np.zeros(self.rn, dtype=np.uint8)
+        _L.cgx_debug_line_copy(regex._h, self.ut.ctypes.data, self.rt.ctypes.data, self.ueoi.ctypes.data,
+                               self.reoi.ctypes.data)
+
+    def _reverse(self, h, e, lo):
+        n = len(h)
+        st = int(self.rs[2 if e >= n else _kind(h[e])])
+        last, q = lo, e
+        while st:
+            if q == lo:
+                if q == 0:
+                    if self.reoi[st]:
+                        last = q
+                elif int(self.rt[st * 256 + h[q - 1]]) & 0x8000:
+                    last = q
+                break
+            t = int(self.rt[st * 256 + h[q - 1]])
+            if t & 0x8000:
+                last = q
+            st = t & 0x7FFF
+            q -= 1
+        return last
+
+    def find_all(self, h, delim=10):
+        h = bytes(h)
+        n, out = len(h), []
+        line = 0
+        while line < n:
+            pos = line
+            line_end = None
+            while True:
+                st = int(self.us[2 if pos == 0 else _kind(h[pos - 1])])
+                last, i = -1, pos
+                while st:
+                    if i >= n:
+                        if self.ueoi[st]:
+                            last = i
+                        line_end = n
+                        break
+                    b = h[i]
+                    t = int(self.ut[st * 256 + b])
+                    if t & 0x8000:
+                        last = i
+                    st = t & 0x7FFF
+                    if b == delim:
+                        line_end = i + 1
+                        break
+                    i += 1
+                if last < 0:
+                    break
+                out.append([self._reverse(h, last, pos), last])
+                pos = last
+            if line_end is None:  # the scan died before the delimiter: find the record's end
+                j = h.find(bytes([delim]), pos)
+                line_end = n if j < 0 else j + 1
+            line = line_end
+        return out

@@ -292,3 +292,66 @@ def test_utf8_patterns_match_oracle(pat):
     o = Oracle(pat)
     for n in (40, 3000, 60000):
         check(pat, _utf8_corpus(rng, n), o)
+
+
+# ---- record engine (one lane per record: unanchored forward DFA + reverse DFA) ------------------------
+LINE_GPU = [r".*error", r"\S+@\S+", r".+", r"[^,\n]+,[^,\n]+", r".*\d{3}.*", r"(?m)^.*error.*$", r".*?b", r"\S+\.\S+",
+            r".*\bfoo\b", r"(?i).*warn(ing)?", r".+?,", r"[^\s]+=[^\s]*;?"]
+
+
+def _line_corpus(rng, n):
+    pieces = [b"a", b"b", b"x", b" ", b" ", b" ", b"\n", b",", b"@", b".", b"=", b";", b"error", b"foo", b"food",
+              b"warn", b"WARNING", b"12", b"123", b"4567", "é".encode(), "мир".encode(), b"\xff", b"\xe0",
+              b"user@host.tld", b"lorem ipsum", b"GET /index.html"]
+    return b"".join(pieces[int(i)] for i in rng.integers(0, len(pieces), n))
+
+
+@pytest.mark.parametrize("pat", LINE_GPU)
+def test_record_engine_matches_oracle(pat):
+    rng = np.random.default_rng(37)
+    r = cg.Compile(pat)
+    assert r.engine == "line-dfa"
+    o = Oracle(pat)
+    for n in (0, 1, 30, 4000, 90000):
+        check(pat, _line_corpus(rng, n), o)
+
+
+def test_record_engine_edges():
+    o = Oracle(r".*error")
+    for hay in [b"", b"\n", b"error", b"error\n", b"x error", b"\nerror\n\n", b"no\nmatch\n", b"error" * 3,
+                b"a" * 40000 + b" error tail\nshort error\n",             # record longer than the window
+                b"error\n" * 30000,                                        # dense: staging overflow -> direct
+                (b"x" * 4090 + b"error\n") * 40,                          # records straddling slices/chunks
+                b"e" * 100000]:                                            # one long record, no match, no newline
+        check(r".*error", hay, o)
+    check(r".+", b"a\nbb\n\nccc")
+    check(r".+", b"\n".join(b"l%d" % i for i in range(50000)))
+    check(r".*?b", b"aab ab b\nbbb\n")
+
+
+def test_record_engine_on_log_corpus_and_shards():
+    import torch
+    from gpu_util import dev_corpus, scan_device
+    pat = r".* 404 .*"
+    r = cg.Compile(pat)
+    assert r.engine == "line-dfa"
+    n = 1500 * 4096
+    hay = cg.synth_host(0, 99, n).tobytes()
+    want = Oracle(pat).find_all(hay)
+    got = r.find_all_index_array(hay)
+    assert np.array_equal(got, want)
+    # the same corpus as two shards with base offsets (cut at a record delimiter)
+    cut = hay.rfind(b"\n", 0, n // 2) + 1
+    cut -= cut % 16                      # device pointers must be 16-byte aligned ...
+    cut = hay.rfind(b"\n", 0, cut) + 1   # ... so re-cut and copy the second shard to its own buffer
+    t0 = torch.frombuffer(bytearray(hay[:cut]), dtype=torch.uint8).cuda()
+    t1 = torch.frombuffer(bytearray(hay[cut:]), dtype=torch.uint8).cuda()
+    parts = []
+    for t, base, after in ((t0, 0, n - cut), (t1, cut, 0)):
+        res = torch.zeros(2, dtype=torch.int64, device="cuda")
+        out = torch.empty((len(want) + 8, 2), dtype=torch.int64, device="cuda")
+        r.scan_device(t.data_ptr(), t.numel(), cg.MODE_FINDALL, out.data_ptr(), out.shape[0], res.data_ptr(),
+                      base_offset=base, bytes_after=after)
+        torch.cuda.synchronize()
+        parts.append(out[: int(res[0].item())].cpu().numpy())
+    assert np.array_equal(np.concatenate(parts), want)

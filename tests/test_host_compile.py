@@ -201,3 +201,23 @@ def test_utf8_tables_match_oracle(pat):
         k = int(rng.integers(0, 14))
         h = b"".join(pieces[int(i)] for i in rng.integers(0, len(pieces), k))
         assert m.find_all(h) == o.find_all(h).tolist(), (pat, h)
+
+
+LINE_PATTERNS = [r".*error", r"\S+@\S+", r".+", r"[^,\n]+,[^,\n]+", r".*\d{3}.*", r"(?m)^.*error.*$", r".*?b", r"\S+\.\S+",
+                 r"[^\n]*a[^\n]*b", r".*\bfoo\b", r"(?i).*warn(ing)?", r".+?,", r"[^\s]+=[^\s]*;?"]
+
+
+@pytest.mark.parametrize("pat", LINE_PATTERNS)
+def test_record_engine_tables_match_oracle(pat):
+    """Patterns without a useful first-byte filter: unanchored forward DFA + reverse DFA tables
+    (host/dfa.cpp, the reference's UseDFA shape) must give the oracle's leftmost-first spans."""
+    from table_model import LineModel
+    rng = np.random.default_rng(31)
+    r = cg.Compile(pat)
+    assert r.engine == "line-dfa", r.engine
+    m, o = LineModel(r), Oracle(pat)
+    pieces = [b"a", b"b", b"x", b" ", b" ", b"\n", b",", b"@", b".", b"=", b";", b"error", b"foo", b"food", b"warn",
+              b"WARNING", b"12", b"123", b"4567", "é".encode(), "мир".encode(), b"\xff", b"\xe0", b"user@host.tld"]
+    for it in range(300):
+        h = b"".join(pieces[int(i)] for i in rng.integers(0, len(pieces), int(rng.integers(0, 18))))
+        assert m.find_all(h) == o.find_all(h).tolist(), (pat, h)
