@@ -58,6 +58,7 @@ def _load():
     L.cgx_engine.restype = C.c_char_p
     L.cgx_engine.argtypes = [vp]
     L.cgx_num_captures.argtypes = [vp]
+    L.cgx_delimiter.argtypes = [vp]
     L.cgx_last_error.restype = C.c_char_p
     L.cgx_is_match.argtypes = [vp, u8p, sz, C.POINTER(C.c_int)]
     L.cgx_find_all_index.argtypes = [vp, u8p, sz, i64, C.c_void_p, sz, C.POINTER(sz)]
@@ -139,6 +140,11 @@ class Regex:
     @property
     def engine(self):
         return _lib.cgx_engine(self._h).decode()
+
+    @property
+    def delimiter(self):
+        """Record delimiter byte of this pattern (no match can contain it); b"\\n" when possible."""
+        return bytes([_lib.cgx_delimiter(self._h)])
 
     @property
     def launches(self):

@@ -222,6 +222,7 @@ const char* cgx_strategy(const cgx_regex* re) { return RefStrategyName(re->c->an
 const char* cgx_engine(const cgx_regex* re) { return re->c->engine_name.c_str(); }
 int cgx_num_captures(const cgx_regex* re) { return re->c->prog.num_captures; }
 uint64_t cgx_launch_count(const cgx_regex* re) { return re->launches.load(); }
+int cgx_delimiter(const cgx_regex* re) { return re->c->kind == ENG_TEDDY ? '\n' : re->c->delim; }
 
 static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base, int mode,
                        int64_t* d_out, size_t cap, uint64_t* d_result, cudaStream_t st, int64_t after = 0) {

@@ -251,12 +251,23 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
             "rules of meta/findall.go:247-279; not record-parallel)";
       return COMPILE_UNSUPPORTED;
     }
-    if (!DelimiterSafe(c->dfa, '\n')) {
-      err = "unsupported: a match can span '\\n' (record-parallel scan needs a delimiter no match "
-            "can contain)";
-      return COMPILE_UNSUPPORTED;
+    // Records are cut at a byte no match can contain.  '\n' whenever possible (lines are what
+    // callers think in); otherwise the most frequent text byte the pattern cannot consume, e.g.
+    // `\s+` is scanned as records between letters, `[^a]+` as records between 'a's.
+    {
+      static const char pref[] = "\n etaoinsrhldcumfpgwybvkxjqz\t,.;:/-_=0123456789ETAOINSRHLDCUMFPGWYBVKXJQZ";
+      int chosen = -1;
+      for (const char* q = pref; *q && chosen < 0; q++)
+        if (DelimiterSafe(c->dfa, (uint8_t)*q)) chosen = (uint8_t)*q;
+      for (int d = 0; d < 256 && chosen < 0; d++)
+        if (DelimiterSafe(c->dfa, (uint8_t)d)) chosen = d;
+      if (chosen < 0) {
+        err = "unsupported: a match can contain every byte value (record-parallel scan needs a "
+              "delimiter no match can contain)";
+        return COMPILE_UNSUPPORTED;
+      }
+      c->delim = (uint8_t)chosen;
     }
-    c->delim = '\n';
     for (int k = 1; k < SK_COUNT; k++)
       if (c->dfa.start[k] != c->dfa.start[0]) c->kind_lut_needed = true;
     memset(c->lut, 0, sizeof c->lut);

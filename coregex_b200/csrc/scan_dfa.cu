@@ -119,7 +119,7 @@ __device__ __forceinline__ int start_kind(uint8_t b) {
 // Anchored leftmost-first walk from global position p0 through global memory (any position).
 __device__ int64_t dfa_walk_slow(const Ctx& c, int64_t p0) {
   unsigned s = c.a.dfa.start[0];
-  if (c.a.dfa.kind_lut_needed) s = c.a.dfa.start[p0 == 0 ? (c.a.base == 0 ? 2 : 3) : start_kind(byte_at(c, p0 - 1))];
+  if (c.a.dfa.kind_lut_needed) s = c.a.dfa.start[p0 == 0 ? (c.a.base == 0 ? 2 : start_kind(c.a.delim)) : start_kind(byte_at(c, p0 - 1))];
   int64_t last = -1, p = p0;
   const int64_t n = c.a.n;
   while (s) {
@@ -141,7 +141,7 @@ __device__ int64_t dfa_walk_slow(const Ctx& c, int64_t p0) {
 __device__ __forceinline__ int dfa_walk(const Ctx& c, int i0) {
   uint32_t sp = (uint32_t)c.a.dfa.start[0] << 10;
   if (c.a.dfa.kind_lut_needed) {
-    const int k = (c.gw + i0 == 0) ? (c.a.base == 0 ? 2 : 3) : start_kind(c.sm.win[i0 - 1]);
+    const int k = (c.gw + i0 == 0) ? (c.a.base == 0 ? 2 : start_kind(c.a.delim)) : start_kind(c.sm.win[i0 - 1]);
     sp = (uint32_t)c.a.dfa.start[k] << 10;
   }
   int last = -1, i = i0;
@@ -619,12 +619,12 @@ __device__ __forceinline__ unsigned line_byte(const Ctx& c, int i) {
   return i < WIN ? (unsigned)c.sm.win[i] : (unsigned)__ldg(c.a.h + c.gw + i);
 }
 __device__ __forceinline__ int kind_before(const Ctx& c, int i) {
-  return (c.gw + i == 0) ? (c.a.base == 0 ? 2 : 3) : start_kind((uint8_t)line_byte(c, i - 1));
+  return (c.gw + i == 0) ? (c.a.base == 0 ? 2 : start_kind(c.a.delim)) : start_kind((uint8_t)line_byte(c, i - 1));
 }
 // start of the match that ends at e, not before lo
 __device__ int line_reverse(const Ctx& c, int e, int lo, int nrel) {
   unsigned st = c.a.line.rstart[0];
-  if (c.a.line.rkinds) st = c.a.line.rstart[e >= nrel ? (c.a.after == 0 ? 2 : 3) : start_kind((uint8_t)line_byte(c, e))];
+  if (c.a.line.rkinds) st = c.a.line.rstart[e >= nrel ? (c.a.after == 0 ? 2 : start_kind(c.a.delim)) : start_kind((uint8_t)line_byte(c, e))];
   int last = lo, q = e;
   while (st) {
     if (q == lo) {

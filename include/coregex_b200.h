@@ -50,6 +50,10 @@ const char* cgx_strategy(const cgx_regex* re);
 /* which GPU engine runs it: "dfa-runstart", "dfa-byteset", "dfa-lut", "teddy", "fat-teddy",
  * "pikevm", "serial"                                                                          */
 const char* cgx_engine(const cgx_regex* re);
+/* the record delimiter of this pattern: a byte no match can contain ('\n' whenever the pattern
+ * allows it).  The scan treats the haystack as records separated by it; callers that split a
+ * corpus into shards (cgx_scan_shard_device) must cut right after this byte.                   */
+int cgx_delimiter(const cgx_regex* re);
 /* reference meta.Engine.NumCaptures() (meta/engine.go:232): groups including group 0          */
 int cgx_num_captures(const cgx_regex* re);
 const char* cgx_last_error(void);
@@ -84,7 +88,7 @@ int cgx_scan_device(cgx_regex* re, const uint8_t* d_haystack, size_t len, int64_
                     int mode, int64_t* d_out_pairs, size_t cap_pairs, uint64_t* d_result,
                     void* stream);
 /* One shard of a larger logical haystack (corpus split across GPUs, or pieces of a pipelined
- * host copy).  Shards are cut right after a record delimiter ('\n'): base_offset > 0 promises
+ * host copy).  Shards are cut right after a record delimiter (cgx_delimiter, normally '\n'): base_offset > 0 promises
  * that the byte before d_haystack[0] is a delimiter, bytes_after > 0 that the shard ends with
  * one.  base_offset == 0 marks the true start of text (\A, non-multiline ^), bytes_after == 0
  * the true end (\z, $), and bytes_after also feeds the multi-literal engine's end-of-haystack

@@ -149,6 +149,7 @@ class LineModel:
         ok = _L.cgx_debug_line_info(regex._h, C.byref(un), C.byref(rn), us.ctypes.data, rs.ctypes.data)
         assert ok == 1, "not a record-engine pattern"
         self.un, self.rn, self.us, self.rs = un.value, rn.value, us, rs
+        self.delim = regex.delimiter[0]
         self.ut = np.zeros(self.un * 256, dtype=np.uint16)
         self.rt = np.zeros(self.rn * 256, dtype=np.uint16)
         self.ueoi = np.zeros(self.un, dtype=np.uint8)
@@ -175,8 +176,9 @@ class LineModel:
             q -= 1
         return last
 
-    def find_all(self, h, delim=10):
+    def find_all(self, h, delim=None):
         h = bytes(h)
+        delim = self.delim if delim is None else delim
         n, out = len(h), []
         line = 0
         while line < n:

@@ -355,3 +355,24 @@ def test_record_engine_on_log_corpus_and_shards():
         torch.cuda.synchronize()
         parts.append(out[: int(res[0].item())].cpu().numpy())
     assert np.array_equal(np.concatenate(parts), want)
+
+
+# ---- patterns whose matches can contain '\n': records are cut at another byte the pattern cannot consume ----
+NON_LF_GPU = [r"\s+", r"[^a]+", r"[a-z]+\s+[a-z]+", r"\W+", r"[^e]{3}", r"\D+", r"[\s,]+"]
+
+
+@pytest.mark.parametrize("pat", NON_LF_GPU)
+def test_non_newline_delimiter_matches_oracle(pat):
+    rng = np.random.default_rng(47)
+    r = cg.Compile(pat)
+    assert r.delimiter != b"\n"
+    o = Oracle(pat)
+    pieces = [b"a", b"e", b"t", b"x", b" ", b"  ", b"\n", b"\n\n", b"\t", b",", b"12", b"3", b"word", b"ea", "é".encode(),
+              b"\xff", b"lorem ipsum dolor", b"zzzz"]
+    for n in (0, 1, 50, 5000, 120000):
+        hay = b"".join(pieces[int(i)] for i in rng.integers(0, len(pieces), n))
+        check(pat, hay, o)
+    # a haystack in which the chosen delimiter never occurs is one single record
+    d = r.delimiter
+    hay = bytes(b for b in (b" \n\tqz,.;" * 9000) if bytes([b]) != d)
+    check(pat, hay, o)

@@ -44,7 +44,7 @@ def test_compile_errors_are_go_formatted():
 
 
 def test_unsupported_patterns_fail_loudly():
-    for pat in ["a*", r"(?s)x.y", r"[^a]+", r"[a-z]+\s+[a-z]+", r"\pL"]:  # nullable / can span \n / Unicode tables
+    for pat in ["a*", r"(?s)x.y", r"(?s).+", r"\pL"]:  # nullable / no byte is a safe delimiter / Unicode tables
         with pytest.raises(cg.UnsupportedError):
             cg.Compile(pat)
 
@@ -189,8 +189,10 @@ def test_utf8_tables_match_oracle(pat):
     """`.`, negated and non-ASCII classes: the product's own UTF-8 byte automaton (host/prog.cpp) must
     define the same leftmost-first matches as the restated reference automaton (oracle/nfa.cpp,
     nfa/compile.go:440-1223), on well-formed AND malformed UTF-8."""
+    from table_model import LineModel
     rng = np.random.default_rng(23)
-    m = TableModel(cg.Compile(pat))
+    r = cg.Compile(pat)
+    m = LineModel(r) if r.engine == "line-dfa" else TableModel(r)
     o = Oracle(pat)
     pieces = [b"a", b"b", b"c", b"x", b"y", b"z", b"foo", b"bar", b" ", b"\n", b"=", b"\"", "é".encode(), "α".encode(),
               "ω".encode(), "β".encode(), "Ł".encode(), "ſ".encode(), "ß".encode(), "€".encode(), "ߵ".encode(),
@@ -220,4 +222,30 @@ def test_record_engine_tables_match_oracle(pat):
               b"WARNING", b"12", b"123", b"4567", "é".encode(), "мир".encode(), b"\xff", b"\xe0", b"user@host.tld"]
     for it in range(300):
         h = b"".join(pieces[int(i)] for i in rng.integers(0, len(pieces), int(rng.integers(0, 18))))
+        assert m.find_all(h) == o.find_all(h).tolist(), (pat, h)
+
+
+def test_record_delimiter_choice():
+    """'\\n' whenever no match can contain it; otherwise a byte the pattern cannot consume."""
+    assert cg.Compile(r"\d+\.\d+").delimiter == b"\n"
+    assert cg.Compile(r"foo.*bar").delimiter == b"\n"
+    assert cg.Compile(r"\s+").delimiter == b"e"
+    assert cg.Compile(r"[^a]+").delimiter == b"a"
+    assert cg.Compile(r"[a-z]+\s+[a-z]+").delimiter == b","
+
+
+NON_LF_PATTERNS = [r"\s+", r"[^a]+", r"[a-z]+\s+[a-z]+", r"\W+", r"[^e]{3}", r"\D+"]
+
+
+@pytest.mark.parametrize("pat", NON_LF_PATTERNS)
+def test_non_newline_delimiter_tables_match_oracle(pat):
+    from table_model import LineModel
+    rng = np.random.default_rng(43)
+    r = cg.Compile(pat)
+    assert r.delimiter != b"\n"
+    m = LineModel(r) if r.engine == "line-dfa" else TableModel(r)
+    o = Oracle(pat)
+    pieces = [b"a", b"e", b"t", b"x", b" ", b"  ", b"\n", b"\t", b",", b"12", b"3", b"word", b"ea", "é".encode(), b"\xff"]
+    for it in range(300):
+        h = b"".join(pieces[int(i)] for i in rng.integers(0, len(pieces), int(rng.integers(0, 20))))
         assert m.find_all(h) == o.find_all(h).tolist(), (pat, h)

@@ -84,3 +84,9 @@ if __name__ == "__main__":
         int(80 * 10_000_000 * scale), submatch=True, window=80 * 4000)
     run("C5 shape: 64-literal Fat Teddy, 8 GB shard (1 of 8)", b"|".join(LIT64).decode(), cg.SYNTH_TEXT,
         0xC0FFEE + 5, int(8 * GIB * scale), literals=LIT64)
+    # beyond the BASELINE configs: the other engines on the same log corpus
+    run("X1 record engine `.* 404 .*`, 1 GB log lines", r".* 404 .*", cg.SYNTH_LOG, 0xC0FFEE + 2, int(1 * GIB * scale))
+    run("X2 generic DFA engine `GET /\\S+ HTTP`, 1 GB log lines", r"GET /\S+ HTTP", cg.SYNTH_LOG, 0xC0FFEE + 2,
+        int(1 * GIB * scale))
+    run("X3 UTF-8 dot `\"[A-Z]+ .*\" 200`, 1 GB log lines", r'"[A-Z]+ .*" 200', cg.SYNTH_LOG, 0xC0FFEE + 2,
+        int(1 * GIB * scale))
