@@ -180,8 +180,10 @@ static void BuildFlat(const Regexp* re, FlatDev& out) {
   b.walk(re);
   memset(&out, 0, sizeof out);
   // worth it only when the pattern is longer than its first item (otherwise the first-level
-  // filter already is the whole pattern)
-  if (!(b.ok && b.f.nops >= 2)) return;
+  // filter already is the whole pattern) — except a lone `C+` (the reference's CharClassSearcher
+  // patterns, nfa/charclass_searcher.go), where "flat" unlocks the run-start filter: one
+  // candidate per run instead of one per byte
+  if (!(b.ok && (b.f.nops >= 2 || (b.f.nops == 1 && b.f.op_kind[0] == 1)))) return;
   for (int c = 0; c < b.f.nclasses; c++)
     for (int r = 0; r < b.f.cls_nranges[c]; r++) {
       uint32_t lo = b.f.cls_lo[c][r], hi = b.f.cls_hi[c][r], w = hi - lo, m = 0;

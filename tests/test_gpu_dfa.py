@@ -376,3 +376,16 @@ def test_non_newline_delimiter_matches_oracle(pat):
     d = r.delimiter
     hay = bytes(b for b in (b" \n\tqz,.;" * 9000) if bytes([b]) != d)
     check(pat, hay, o)
+
+
+# ---- N2: char-class run patterns (the reference's CharClassSearcher family): dense matches ------------
+@pytest.mark.parametrize("pat", [r"\w+", r"\d+", r"[a-z]+", r"[a-z]+[0-9]+", r"[A-Z][a-z]+"])
+def test_charclass_run_patterns(pat):
+    rng = np.random.default_rng(53)
+    o = Oracle(pat)
+    corpus = open(os.path.join(ROOT, "tests", "golden", "stdlib_corpus.txt"), "rb").read()
+    check(pat, corpus, o)
+    alpha = np.frombuffer(b"abcXYZ019 _-\n", dtype=np.uint8)
+    for n in (100, 70000):
+        check(pat, bytes(alpha[rng.integers(0, len(alpha), n)]), o)
+    check(pat, cg.synth_host(0, 5, 600 * 4096).tobytes(), o)

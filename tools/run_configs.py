@@ -38,13 +38,13 @@ def timed(fn, steps=5, warm=3):
     return e0.elapsed_time(e1) / steps
 
 
-def run(name, pattern, kind, seed, nbytes, literals=None, submatch=False, window=64 * 4096):
+def run(name, pattern, kind, seed, nbytes, literals=None, submatch=False, window=64 * 4096, cap_div=40):
     bs = cg.SYNTH_BLOCK[kind]
     nbytes -= nbytes % (bs * (window // bs) if window % bs == 0 else bs)
     t = dev_corpus(kind, seed, nbytes, literals=literals)
     r = cg.Compile(pattern)
     stride = 2 * (r.NumSubexp() + 1) if submatch else 2
-    cap = nbytes // 40
+    cap = nbytes // cap_div
     out = torch.empty((cap, stride), dtype=torch.int64, device="cuda")
     res = torch.zeros(2, dtype=torch.int64, device="cuda")
     if submatch:
@@ -90,3 +90,5 @@ if __name__ == "__main__":
         int(1 * GIB * scale))
     run("X3 UTF-8 dot `\"[A-Z]+ .*\" 200`, 1 GB log lines", r'"[A-Z]+ .*" 200', cg.SYNTH_LOG, 0xC0FFEE + 2,
         int(1 * GIB * scale))
+    run("X4 char-class runs `\\w+` (dense output), 1 GB log lines", r"\w+", cg.SYNTH_LOG, 0xC0FFEE + 2, int(1 * GIB * scale),
+        cap_div=4)
