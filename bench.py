@@ -282,7 +282,7 @@ def main():
     traffic = profile_traffic()
     if traffic and traffic.get("input_bytes") != n:
         traffic = None  # the committed capture is of a different corpus size
-    roof = {"bound": "hbm", "kernel": "scan_dfa_kernel", "achieved": round(achieved, 1), "peak": peak,
+    roof = {"bound": "hbm", "kernel": "scan_flat_kernel" if r.engine.endswith("+bitstream") else "scan_dfa_kernel", "achieved": round(achieved, 1), "peak": peak,
             "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": round(kernel_ms, 4),
             "input_only_frac": round(n / (kernel_ms * 1e-3) / 1e9 / peak, 4),

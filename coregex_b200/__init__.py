@@ -59,6 +59,7 @@ def _load():
     L.cgx_engine.argtypes = [vp]
     L.cgx_num_captures.argtypes = [vp]
     L.cgx_delimiter.argtypes = [vp]
+    L.cgx_debug_set_bitstream.argtypes = [vp, C.c_int]
     L.cgx_last_error.restype = C.c_char_p
     L.cgx_is_match.argtypes = [vp, u8p, sz, C.POINTER(C.c_int)]
     L.cgx_find_all_index.argtypes = [vp, u8p, sz, i64, C.c_void_p, sz, C.POINTER(sz)]
@@ -145,6 +146,11 @@ class Regex:
     def delimiter(self):
         """Record delimiter byte of this pattern (no match can contain it); b"\\n" when possible."""
         return bytes([_lib.cgx_delimiter(self._h)])
+
+    def set_bitstream(self, on):
+        """Tests / A-B runs: keep a flat deterministic pattern on the candidate+DFA kernel
+        (on=False) instead of the bitstream kernel.  Returns the previous setting."""
+        return bool(_lib.cgx_debug_set_bitstream(self._h, 1 if on else 0))
 
     @property
     def launches(self):

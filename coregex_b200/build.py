@@ -17,6 +17,7 @@ SO = os.path.join(LIBDIR, "libcoregex_b200.so")
 SOURCES = [
     "capi.cu",
     "scan_dfa.cu",
+    "scan_flat.cu",
     "scan_teddy.cu",
     "pikevm_kernel.cu",
     "host/prog.cpp",

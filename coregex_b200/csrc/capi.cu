@@ -19,6 +19,8 @@ namespace cgx {
 size_t scan_dfa_smem_bytes(int nstates, int blob_bytes);
 int64_t scan_dfa_chunks(int64_t n);
 cudaError_t launch_scan_dfa(const ScanArgs& a, int sm_count, cudaStream_t stream);
+int64_t scan_flat_chunks(int64_t n);
+cudaError_t launch_scan_flat(const ScanArgs& a, int sm_count, cudaStream_t stream);
 cudaError_t launch_pike_captures(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
                                  const unsigned long long* d_total, unsigned long long cap,
                                  const uint32_t* code, const uint32_t* sets, int start_pc, int nslots,
@@ -79,6 +81,9 @@ struct cgx_regex {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_scan[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   uint64_t* pinned_res = nullptr;  // [2][2]
   std::atomic<uint64_t> launches{0};
+  // flat deterministic patterns run on the bitstream kernel (scan_flat.cu); CGX_BITSTREAM=0 or
+  // cgx_debug_set_bitstream keep them on the candidate/DFA kernel (A/B runs, tests of both paths)
+  bool bitstream = true;
 
   int ensure_pipeline() {
     if (s_h2d) return CGX_OK;
@@ -222,6 +227,11 @@ const char* cgx_strategy(const cgx_regex* re) { return RefStrategyName(re->c->an
 const char* cgx_engine(const cgx_regex* re) { return re->c->engine_name.c_str(); }
 int cgx_num_captures(const cgx_regex* re) { return re->c->prog.num_captures; }
 uint64_t cgx_launch_count(const cgx_regex* re) { return re->launches.load(); }
+int cgx_debug_set_bitstream(cgx_regex* re, int on) {
+  const int was = re->bitstream ? 1 : 0;
+  re->bitstream = on != 0;
+  return was;
+}
 int cgx_delimiter(const cgx_regex* re) { return re->c->kind == ENG_TEDDY ? '\n' : re->c->delim; }
 
 static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base, int mode,
@@ -235,7 +245,12 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
     g_last_error = "engine not available in this build";
     return CGX_ERR_UNSUPPORTED;
   }
-  const int64_t nchunks = scan_dfa_chunks((int64_t)len);
+  static const bool bs_env = [] {
+    const char* e = getenv("CGX_BITSTREAM");
+    return !(e && e[0] == '0');
+  }();
+  const bool use_flat = c.kind == ENG_DFA && c.flat.bs_ok && re->bitstream && bs_env;
+  const int64_t nchunks = use_flat ? scan_flat_chunks((int64_t)len) : scan_dfa_chunks((int64_t)len);
   int r;
   if ((r = re->d_ticket_total.ensure(64))) return r;
   if ((r = re->d_status.ensure((size_t)(nchunks > 0 ? nchunks : 1) * 8))) return r;
@@ -295,7 +310,8 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   a.ticket = (unsigned int*)(tt + 4);  // separate 32-byte sector
   a.status = (unsigned long long*)re->d_status.p;
   a.nchunks = nchunks;
-  CU(launch_scan_dfa(a, re->sm_count, st));
+  if (use_flat) CU(launch_scan_flat(a, re->sm_count, st));
+  else CU(launch_scan_dfa(a, re->sm_count, st));
   re->launches++;
   if (d_result) CU(cudaMemcpyAsync(d_result, tt, 16, cudaMemcpyDeviceToDevice, st));
   return CGX_OK;

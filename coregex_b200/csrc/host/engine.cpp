@@ -83,6 +83,7 @@ static bool setToRanges(const ByteSet& s, int& n, uint8_t* lo, uint8_t* hi) {
 namespace {
 struct FlatBuilder {
   FlatDev f;
+  uint8_t lazy[24] = {};  // item carries the non-greedy flag (matters only to the bitstream engine)
   bool ok = true;
   int classOf(const ByteSet& s) {
     uint8_t lo[4], hi[4];
@@ -100,11 +101,12 @@ struct FlatBuilder {
     for (int k = 0; k < n; k++) { f.cls_lo[c][k] = lo[k]; f.cls_hi[c][k] = hi[k]; }
     return c;
   }
-  void push(int kind, const ByteSet& s) {
+  void push(int kind, const ByteSet& s, bool nongreedy = false) {
     if (!ok) return;
     if (f.nops == 24) { ok = false; return; }
     int c = classOf(s);
     if (!ok) return;
+    lazy[f.nops] = nongreedy ? 1 : 0;
     f.op_kind[f.nops] = (uint8_t)kind;
     f.op_class[f.nops] = (uint8_t)c;
     f.nops++;
@@ -156,15 +158,16 @@ struct FlatBuilder {
         return;
       case OpPlus: case OpStar: case OpQuest:
         if (re->sub.size() != 1 || !classSet(re->sub[0], s)) { ok = false; return; }
-        push(re->op == OpPlus ? 1 : re->op == OpStar ? 2 : 3, s);
+        push(re->op == OpPlus ? 1 : re->op == OpStar ? 2 : 3, s, (re->flags & NonGreedy) != 0);
         return;
       case OpRepeat: {
         if (re->sub.size() != 1 || !classSet(re->sub[0], s)) { ok = false; return; }
         int mx = re->max == -1 ? re->min : re->max;
         if (mx > 8) { ok = false; return; }
+        const bool ng = (re->flags & NonGreedy) != 0;
         for (int i = 0; i < re->min; i++) push(0, s);
-        if (re->max == -1) push(2, s);
-        else for (int i = re->min; i < re->max; i++) push(3, s);
+        if (re->max == -1) push(2, s, ng);
+        else for (int i = re->min; i < re->max; i++) push(3, s, ng);
         return;
       }
       default:
@@ -174,11 +177,12 @@ struct FlatBuilder {
 };
 }  // namespace
 
-static void BuildFlat(const Regexp* re, FlatDev& out) {
+static void BuildFlat(const Regexp* re, FlatDev& out, uint8_t (&lazy)[24]) {
   FlatBuilder b;
   memset(&b.f, 0, sizeof b.f);
   b.walk(re);
   memset(&out, 0, sizeof out);
+  memcpy(lazy, b.lazy, sizeof lazy);
   // worth it only when the pattern is longer than its first item (otherwise the first-level
   // filter already is the whole pattern) — except a lone `C+` (the reference's CharClassSearcher
   // patterns, nfa/charclass_searcher.go), where "flat" unlocks the run-start filter: one
@@ -207,6 +211,58 @@ static void BuildFlat(const Regexp* re, FlatDev& out) {
   b.f.rev_nops = 0;
   for (k--; k >= 0; k--) b.f.rev_ops[b.f.rev_nops++] = (uint8_t)(b.f.op_kind[k] | (b.f.op_class[k] << 2));
   out = b.f;
+}
+
+// Is the flat pattern deterministic enough for the bitstream engine (scan_flat.cu)?  That engine
+// finds match ENDS with a forward marker pass that always takes the greedy choice; this equals
+// leftmost-first (reference nfa/pikevm.go thread priority, dfa/lazy break-at-match) when no choice
+// ever exists: the class of every quantified item is disjoint from everything that can follow it
+// up to and including the next mandatory item (later optional items of the SAME class are one
+// counted group and fine).  A lazy quantifier only matters when nothing mandatory follows it.
+static void DecideBitstream(Compiled& c, const uint8_t (&lazy)[24]) {
+  FlatDev& f = c.flat;
+  f.bs_ok = f.bs_runstart = f.bs_midrun_check = f.fwd_nops = 0;
+  if (!f.nops || c.kind_lut_needed || f.rev_nops + 1 > f.nops) return;
+  ByteSet cs[4] = {};
+  ByteSet any{};
+  for (int k = 0; k < f.nclasses; k++)
+    for (int r = 0; r < f.cls_nranges[k]; r++) {
+      set_add(cs[k], f.cls_lo[k][r], f.cls_hi[k][r]);
+      set_add(any, f.cls_lo[k][r], f.cls_hi[k][r]);
+    }
+  auto inter = [&](int a, int b) {
+    for (int x = 0; x < 256; x++)
+      if (set_has(cs[a], x) && set_has(cs[b], x)) return true;
+    return false;
+  };
+  auto nullable = [&](int i) { return f.op_kind[i] >= 2; };
+  if (nullable(0)) return;  // every byte of the first class would start its own overlapping match
+  // `a a+` / `a a?`: matches from neighbouring starts share their end, which the engine detects and
+  // sends to the serial path every time — such patterns stay on the candidate/DFA kernel
+  if (f.op_kind[0] == 0 && f.nops > 1 && f.op_kind[1] != 0 && inter(f.op_class[0], f.op_class[1])) return;
+  for (int i = 0; i < f.nops; i++) {
+    if (f.op_kind[i] == 0) continue;
+    bool tail_nullable = true;
+    for (int j = i + 1; j < f.nops; j++) {
+      const bool same_group = f.op_class[j] == f.op_class[i] && nullable(j);
+      if (!same_group && inter(f.op_class[i], f.op_class[j])) return;
+      if (!nullable(j)) {
+        tail_nullable = false;
+        break;
+      }
+    }
+    if (lazy[i] && tail_nullable) return;
+  }
+  if (c.filter_kind == F_RUNSTART) {
+    if (!(f.first_is_filter && f.op_kind[0] == 1)) return;
+    f.bs_runstart = 1;
+    f.bs_midrun_check = !(f.op_kind[f.nops - 1] == 1 && f.op_class[f.nops - 1] == f.op_class[0]);
+  }
+  for (int i = 0; i < f.nops; i++) f.fwd_ops[i] = (uint8_t)(f.op_kind[i] | (f.op_class[i] << 2));
+  f.fwd_nops = f.nops;
+  for (int x = 0; x < 256; x++)
+    if (!set_has(any, x)) f.sync_lut[x >> 5] |= 1u << (x & 31);
+  f.bs_ok = 1;
 }
 
 int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, std::string& err) {
@@ -273,7 +329,8 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
     for (int k = 1; k < SK_COUNT; k++)
       if (c->dfa.start[k] != c->dfa.start[0]) c->kind_lut_needed = true;
     memset(c->lut, 0, sizeof c->lut);
-    BuildFlat(pr.re, c->flat);
+    uint8_t flat_lazy[24];
+    BuildFlat(pr.re, c->flat, flat_lazy);
     auto flat_first = [&]() {
       FlatDev& f = c->flat;
       f.first_is_filter = f.nops && f.cls_nranges[0] == c->nranges;
@@ -311,7 +368,8 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
         c->engine_name = "dfa-runstart";
       }
     }
-    if (c->flat.nops) c->engine_name += "+flat";
+    DecideBitstream(*c, flat_lazy);
+    if (c->flat.nops) c->engine_name += c->flat.bs_ok ? "+bitstream" : "+flat";
     // A pattern that can begin with (almost) any byte has no useful candidate filter: every
     // position would start an anchored walk, which is quadratic per record.  Such patterns run
     // the way the reference runs UseDFA patterns (meta/find_indices.go:686-705): one unanchored

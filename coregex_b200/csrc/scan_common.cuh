@@ -2,10 +2,19 @@
 // SWAR byte-class tests, warp scans, decoupled look-back words.
 #pragma once
 #include <cstdint>
+#ifdef CGX_CPU_SIM
+// test harness: the kernel source compiled for the CPU SIMT emulator (tests/sim/simt_cpu.h), which
+// supplies the mbarrier / bulk-copy / status-word helpers below as plain C++
+#include "simt_cpu.h"
+#else
 #include <cuda_runtime.h>
+#define CGX_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#endif
 
 namespace cgx {
 
+#ifndef CGX_CPU_SIM
+__device__ __forceinline__ void cgx_spin_yield() {}
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS: UBLKCP) -----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -53,6 +62,8 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
+#endif  // !CGX_CPU_SIM
+
 // ---- SWAR byte-class tests ---------------------------------------------------------------------
 // bit 7 of each byte of the result is set iff that byte of x lies in [lo,hi]; requires hi <= 0x7F.
 __device__ __forceinline__ uint32_t swar_in_range(uint32_t x, uint32_t k_lo, uint32_t k_hi) {
@@ -87,6 +98,7 @@ constexpr unsigned long long LB_AGG = 1ull << 62;
 constexpr unsigned long long LB_PREFIX = 2ull << 62;
 constexpr unsigned long long LB_VALUE = (1ull << 62) - 1;
 
+#ifndef CGX_CPU_SIM
 // The status word carries flag and value together and guards no other data, so relaxed
 // gpu-scope accesses are enough (an acquire load would add an L1 invalidate to every poll).
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
@@ -105,5 +117,7 @@ __device__ __forceinline__ void bar_sync(int id, int count) {
 __device__ __forceinline__ void bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+
+#endif  // !CGX_CPU_SIM
 
 }  // namespace cgx

@@ -1,0 +1,740 @@
+// scan_flat.cu — the bitstream engine: sm_100a kernel for flat deterministic patterns
+// (`\d+\.\d+\.\d+\.\d+`, `\w+@\w+\.\w+`, `[a-z]+=\d+` ...), the north-star path.
+//
+// Replaces, for a whole corpus at once:
+//   reference meta/findall.go:176-290        findAllIndicesLoop (pos = end chaining)
+//   reference meta/find_indices.go:1050-1088 DigitPrefilter loop (candidate -> SearchAtAnchored)
+//   reference simd/memchr_digit_amd64.s:26   memchrDigitAVX2
+//   reference dfa/lazy/lazy.go:219-324       SearchAtAnchored (per-byte class + table walk)
+//
+// Where scan_dfa.cu finds candidate starts bit-parallel and then walks the DFA one candidate per
+// lane, this kernel never walks: match STARTS come from a right-to-left marker pass over per-class
+// position bitmaps, match ENDS from a left-to-right pass over the same bitmaps (forced greedy ==
+// leftmost-first because the host proved the pattern deterministic, host/engine.cpp
+// DecideBitstream).  Every warp is autonomous — no CTA barrier anywhere:
+//
+//   * a warp draws 15.5 KB chunks (8 tiles) from a ticket counter; per iteration it takes one TMA
+//     bulk copy of 4032 B (two overlapping 2 KB tiles) into its own double-buffered window;
+//   * lane l owns a 64-byte piece of each tile: 4 x LDS.128 (bank-conflict free through a rotated
+//     quarter order), SWAR range tests, dp4a bit packing -> one 64-bit word per class and tile;
+//   * tiles overlap by one piece (64 B).  A byte that belongs to no class of the pattern can never
+//     be inside a match ("sync byte"), so a tile owns the starts from the first sync byte of its
+//     first piece up to the first sync byte of its last piece: chains of overlapping candidates
+//     (`pos = end` in the reference loop) never cross tiles;
+//   * starts and ends are checked to alternate (prefix parity of S^E).  If they do not (candidates
+//     that overlap, `1.2.3.4.5`), or a span has no sync byte before the window ends, one lane
+//     replays the reference loop over global memory for that region (exact, rare);
+//   * matches are staged per chunk in shared memory (u16 offsets), the chunk's count is published
+//     at once, and a resumable non-blocking decoupled look-back — polled between iterations —
+//     yields the global offset; pairs are stored as int64 in global match order.
+// Every corpus byte crosses HBM once (+3 % tile overlap served by L2); output is 16 B per match.
+#include "scan_common.cuh"
+#include "scan_params.h"
+
+#ifndef CGX_CPU_SIM
+#include <cstdio>
+#endif
+
+namespace cgx {
+
+namespace {
+
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr int FW_WARPS = 4;
+constexpr int FW_THREADS = FW_WARPS * 32;
+constexpr int TILE = 2048;              // window bytes of one tile (64 per lane)
+constexpr int STRIDE = 1984;            // bytes between tile origins (31 pieces)
+constexpr int TPC = 8;                  // tiles per chunk
+constexpr int PAIRS = TPC / 2;          // iterations per chunk (two tiles each)
+constexpr int CHUNKB = TPC * STRIDE;    // 15872 bytes owned per chunk
+constexpr int SUPER = STRIDE + TILE;    // 4032 bytes loaded per iteration
+constexpr int CAP = 256;                // staged matches per chunk
+
+struct WarpSmem {
+  alignas(128) uint8_t win[2][SUPER];
+  uint16_t stS[2][CAP];
+  uint16_t stE[2][CAP];
+  uint64_t mbar[2];
+};
+
+__device__ __forceinline__ uint64_t mk64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
+// ---- 2048-bit vectors across the warp: lane l holds word l -------------------------------------
+// markers move one position towards higher bit indices; `in` enters bit 0 of lane 0
+__device__ __forceinline__ uint64_t shl1(uint64_t m, int lane, uint32_t in) {
+  const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+  uint32_t dn = __shfl_up_sync(FULL, hi, 1);
+  if (lane == 0) dn = in;
+  return mk64(__funnelshift_l(lo, hi, 1), __funnelshift_l(dn, lo, 1));
+}
+__device__ __forceinline__ uint64_t add2048(uint64_t s, uint64_t cc, int lane) {
+  const uint64_t sum = s + cc;
+  const uint32_t G = __ballot_sync(FULL, sum < s);
+  const uint32_t P = __ballot_sync(FULL, sum == ~0ull);
+  const uint32_t A = G | P;
+  const uint32_t carries = A ^ G ^ (A + G);  // bit l = carry into word l
+  return sum + ((carries >> lane) & 1u);
+}
+// orientation flip: reversed (lane l = piece 31-l, bit 63-b = byte b) <-> forward (lane l = piece l,
+// bit b = byte b)
+__device__ __forceinline__ uint64_t flip(uint64_t x) {
+  const uint32_t lo = __brev((uint32_t)(x >> 32)), hi = __brev((uint32_t)x);
+  return mk64(__shfl_xor_sync(FULL, hi, 31), __shfl_xor_sync(FULL, lo, 31));
+}
+
+// ---- classification ----------------------------------------------------------------------------
+// 8 flag words (bit 7 of a byte set <=> byte in class) -> bit-reversed 32-bit mask (bit 31-b <=> byte b)
+__device__ __forceinline__ uint32_t pack_rev(const uint32_t* fl) {
+  uint32_t acc[4];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    acc[a] = __dp4a(fl[2 * a], 0x10204080u, 0u);
+    acc[a] = __dp4a(fl[2 * a + 1], 0x01020408u, acc[a]);
+  }
+  return (acc[0] << 17) | (acc[1] << 9) | (acc[2] << 1) | (acc[3] >> 7);
+}
+
+template <int C>
+__device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t (&w)[16]) {
+  uint32_t fl[16];
+  const int nr = f.cls_nranges[C];
+  if (nr == 1 && f.cls_mode[C][0] == 0) {  // one XOR-alignable range: 3 ops per word
+    const uint32_t k1 = f.cls_k1[C][0], k2 = f.cls_k2[C][0];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const uint32_t z = ((w[k] ^ k1) & 0x7F7F7F7Fu) + k2;  // bit7 set <=> (x^lo)&0x7f > width
+      fl[k] = ~(z | w[k]) & 0x80808080u;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; k++) fl[k] = 0;
+    for (int r = 0; r < nr; r++) {
+      const uint32_t k1 = f.cls_k1[C][r], k2 = f.cls_k2[C][r];
+      if (f.cls_mode[C][r] == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const uint32_t z = ((w[k] ^ k1) & 0x7F7F7F7Fu) + k2;
+          fl[k] |= ~(z | w[k]) & 0x80808080u;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) fl[k] |= swar_in_range(w[k], k1, k2);
+      }
+    }
+  }
+  return mk64(pack_rev(fl), pack_rev(fl + 8));  // bytes 0..31 in the high word
+}
+
+// Class bitmaps (reversed orientation) of the 64-byte piece at `p`.  The four 16-byte quarters are
+// read in the order (j + rot) & 3 so that the 32 lanes of one LDS.128 cover all banks evenly (pieces
+// are 64 B apart: a straight order would hit 8 of 32 banks); packing them as if they were in order
+// yields the bitmap rotated by 16*rot bits, which two byte permutes undo.
+__device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* p, int rot, uint32_t sel_lo,
+                                               uint32_t sel_hi, uint64_t (&cm)[4]) {
+  uint32_t w[16];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p + (((j + rot) & 3) << 4));
+    w[4 * j] = v.x;
+    w[4 * j + 1] = v.y;
+    w[4 * j + 2] = v.z;
+    w[4 * j + 3] = v.w;
+  }
+  uint64_t raw[4];
+  raw[0] = class_rev64<0>(f, w);
+  raw[1] = f.nclasses > 1 ? class_rev64<1>(f, w) : 0ull;
+  raw[2] = f.nclasses > 2 ? class_rev64<2>(f, w) : 0ull;
+  raw[3] = f.nclasses > 3 ? class_rev64<3>(f, w) : 0ull;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const uint32_t lo = (uint32_t)raw[c], hi = (uint32_t)(raw[c] >> 32);
+    cm[c] = mk64(__byte_perm(lo, hi, sel_hi), __byte_perm(lo, hi, sel_lo));
+  }
+}
+
+// ---- marker passes -----------------------------------------------------------------------------
+// Right to left (reversed orientation): M = positions from which items k..end can match.
+template <int C>
+__device__ __forceinline__ void rev_step(uint32_t kind, const uint64_t (&ca)[4], const uint64_t (&cb)[4],
+                                         uint64_t& Ma, uint64_t& Mb, int lane) {
+  const uint64_t Ca = ca[C], Cb = cb[C];
+  // unknown territory past the window is assumed to allow a match (bit entering lane 0 is 1)
+  const uint64_t ua = shl1(Ma, lane, FULL) & Ca;
+  const uint64_t ub = shl1(Mb, lane, FULL) & Cb;
+  if (kind == 0) {
+    Ma = ua;
+    Mb = ub;
+  } else if (kind == 3) {
+    Ma |= ua;
+    Mb |= ub;
+  } else {
+    // extend through the run towards lower addresses; a second marker inside one run survives the
+    // carry of the first as a 1 in the sum, so the markers themselves are OR-ed back
+    const uint64_t pa = (~add2048(ua, Ca, lane) & Ca) | ua;
+    const uint64_t pb = (~add2048(ub, Cb, lane) & Cb) | ub;
+    Ma = kind == 1 ? pa : (Ma | pa);
+    Mb = kind == 1 ? pb : (Mb | pb);
+  }
+}
+// Left to right (forward orientation): T = positions a marker stands at before item k; the forced
+// greedy choice (take the whole run / take the optional byte whenever it is there).
+template <int C>
+__device__ __forceinline__ void fwd_step(uint32_t kind, const uint64_t (&ca)[4], const uint64_t (&cb)[4],
+                                         uint64_t& Ta, uint64_t& Tb, int lane) {
+  const uint64_t Ca = ca[C], Cb = cb[C];
+  const uint64_t ia = Ta & Ca, ib = Tb & Cb;  // markers that can take a byte
+  if (kind == 0) {
+    Ta = shl1(ia, lane, 0u);
+    Tb = shl1(ib, lane, 0u);
+  } else if (kind == 3) {
+    Ta = (Ta & ~Ca) | shl1(ia, lane, 0u);
+    Tb = (Tb & ~Cb) | shl1(ib, lane, 0u);
+  } else {
+    // a marker inside a run of ones carries out to the first zero after the run
+    const uint64_t ea = add2048(ia, Ca, lane) & ~Ca;
+    const uint64_t eb = add2048(ib, Cb, lane) & ~Cb;
+    Ta = kind == 1 ? ea : ((Ta & ~Ca) | ea);
+    Tb = kind == 1 ? eb : ((Tb & ~Cb) | eb);
+  }
+}
+
+#define CGX_CLASS_SWITCH(cls, CALL)  \
+  switch (cls) {                     \
+    case 0: { constexpr int C = 0; CALL; } break; \
+    case 1: { constexpr int C = 1; CALL; } break; \
+    case 2: { constexpr int C = 2; CALL; } break; \
+    default: { constexpr int C = 3; CALL; } break; \
+  }
+
+// exclusive prefix parity of the 2048-bit vector x: bit p = parity of the bits of x below p
+__device__ __forceinline__ uint64_t prefix_parity_excl(uint64_t x, int lane) {
+  uint64_t y = x;
+  y ^= y << 1;
+  y ^= y << 2;
+  y ^= y << 4;
+  y ^= y << 8;
+  y ^= y << 16;
+  y ^= y << 32;  // inclusive prefix inside the word
+  const uint32_t odd = __ballot_sync(FULL, (int)(y >> 63));
+  const uint32_t below = odd & ((1u << lane) - 1u);
+  const uint64_t flipmask = (__popc(below) & 1) ? ~0ull : 0ull;
+  return (y ^ x) ^ flipmask;
+}
+
+// ---- output ------------------------------------------------------------------------------------
+template <bool DIRECT>
+struct Emit {
+  const ScanArgs& a;
+  uint16_t* stS;
+  uint16_t* stE;
+  int64_t cb;               // global position of the chunk's first byte
+  unsigned long long goff;  // DIRECT: global index of the chunk's first match
+  bool far = false;         // a staged offset did not fit 16 bits
+
+  // rel = position relative to the chunk
+  __device__ __forceinline__ void put(unsigned idx, int64_t rel, bool is_end) {
+    if (a.mode != M_FINDALL) return;
+    if (DIRECT) {
+      const unsigned long long gi = goff + idx;
+      if ((int64_t)gi < a.cap) a.out[2 * gi + (is_end ? 1 : 0)] = cb + a.base + rel;
+    } else {
+      if (rel > 0xFFFF) far = true;
+      else if (idx < (unsigned)CAP) (is_end ? stE : stS)[idx] = (uint16_t)rel;
+    }
+  }
+  __device__ __forceinline__ void put_bits(uint64_t bits, unsigned idx, int rel0, bool is_end) {
+    while (bits) {
+      const int b = __ffsll((long long)bits) - 1;
+      bits &= bits - 1;
+      put(idx++, rel0 + b, is_end);
+    }
+  }
+};
+
+__device__ __forceinline__ bool in_filter(const ScanArgs& a, uint32_t b) {
+  if (a.filter.kind == F_LUT) return __ldg(a.filter.lut + b) != 0;
+  bool r = false;
+  for (int k = 0; k < a.filter.nranges; k++) r |= (b >= a.filter.lo[k] && b <= a.filter.hi[k]);
+  return r;
+}
+__device__ __forceinline__ bool is_sync(const ScanArgs& a, uint32_t b) {
+  return (a.flat.sync_lut[b >> 5] >> (b & 31)) & 1u;
+}
+
+// anchored leftmost-first walk through global memory (reference dfa/lazy/lazy.go:219-324)
+__device__ int64_t dfa_walk_global(const ScanArgs& a, int64_t p0) {
+  unsigned s = a.dfa.start[0];
+  int64_t last = -1, p = p0;
+  while (s) {
+    if (p >= a.n) {
+      if (__ldg(a.dfa.eoi + s)) last = a.n;
+      break;
+    }
+    const uint32_t e = __ldg(a.dfa.trans + (s << 8) + __ldg(a.h + p));
+    if (e & 0x8000u) last = p;
+    s = e & 0x7FFFu;
+    p++;
+  }
+  return last;
+}
+
+// One lane replays the reference loop (meta/findall.go:176-290 over meta/find_indices.go:1050-1088)
+// from global position `from` until the candidate search meets a sync byte at or after `stop_min`
+// (or the end of input).  Returns the number of matches emitted from index idx0 on.
+template <bool DIRECT>
+__device__ unsigned serial_region(const ScanArgs& a, Emit<DIRECT>& em, int64_t from, int64_t stop_min,
+                                  unsigned idx0, int lane) {
+  unsigned added = 0;
+  bool far = false;
+  if (lane == 0) {
+    atomicAdd(&a.total[2], 1ull);  // diagnostics: serial replays (cgx_debug_scratch)
+    const int64_t n = a.n;
+    int64_t pos = from;
+    while (pos < n) {
+      int64_t d = pos;
+      bool stop = false;
+      while (d < n) {
+        const uint32_t b = __ldg(a.h + d);
+        if (in_filter(a, b)) break;
+        if (d >= stop_min && is_sync(a, b)) {
+          stop = true;
+          break;
+        }
+        d++;
+      }
+      if (stop || d >= n) break;
+      const int64_t e = dfa_walk_global(a, d);
+      if (e >= 0) {
+        em.put(idx0 + added, d - em.cb, false);
+        em.put(idx0 + added, e - em.cb, true);
+        added++;
+        pos = e > d ? e : d + 1;
+      } else {
+        pos = d + 1;
+        // a failed run start fails for the whole run (digitRunSkipSafe, meta/strategy.go:525-560)
+        if (a.flat.bs_runstart)
+          while (pos < n && in_filter(a, __ldg(a.h + pos))) pos++;
+      }
+    }
+    far = em.far;
+  }
+  added = __shfl_sync(FULL, added, 0);
+  em.far = __shfl_sync(FULL, (int)far, 0) != 0;
+  return added;
+}
+
+// ---- one iteration: two overlapping tiles ------------------------------------------------------
+struct TileOut {
+  uint64_t S, E;      // forward orientation, owned starts and their ends
+  int a, lim;         // owned starts: a <= p < lim (tile-relative); a < 0: nothing owned
+  bool open;          // no sync byte in the last piece: the span after `lim` is finished serially
+};
+
+__device__ __forceinline__ uint64_t range_mask(int lo, int hi, int lane) {
+  // bits p (tile-relative) of this lane's word with lo <= p < hi
+  int l = lo - 64 * lane, h = hi - 64 * lane;
+  l = l < 0 ? 0 : l;
+  h = h > 64 ? 64 : h;
+  if (h <= l) return 0ull;
+  const uint64_t mh = h >= 64 ? ~0ull : ((1ull << h) - 1ull);
+  return mh & ~((1ull << l) - 1ull);  // l < 64 here
+}
+
+// ownership of one tile from U (union of the classes, forward orientation): see the file comment
+__device__ __forceinline__ void ownership(uint64_t U, bool first_tile, int lane, TileOut& t) {
+  const uint64_t nz = ~U;
+  const uint32_t has = __ballot_sync(FULL, nz != 0ull);
+  const int firstsync = nz ? __ffsll((long long)nz) - 1 : 64;
+  const int lastsync = nz ? 63 - __clzll((long long)nz) : -1;
+  int a;
+  if (first_tile) {
+    a = 0;
+  } else if (!has) {
+    a = -1;
+  } else {
+    const int fl = __ffs((int)has) - 1;
+    a = 64 * fl + __shfl_sync(FULL, firstsync, fl) + 1;
+  }
+  const int fs31 = __shfl_sync(FULL, firstsync, 31);
+  const int hl = has ? 31 - __clz((int)has) : 0;
+  const int ls = __shfl_sync(FULL, lastsync, hl);
+  t.a = a;
+  if (fs31 < 64) {
+    t.open = false;
+    t.lim = STRIDE + fs31 + 1;
+  } else {
+    t.open = true;
+    const int z1 = has ? 64 * hl + ls + 1 : 0;
+    t.lim = a > z1 ? a : z1;
+  }
+}
+
+template <bool DIRECT>
+__device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit<DIRECT>& em, const TileOut& t, int64_t tile_g,
+                                            unsigned cS, unsigned cE, unsigned totS, unsigned totE,
+                                            unsigned exS, unsigned exE, bool bad, unsigned& cnt, int lane) {
+  if (t.a < 0) return;
+  const int64_t stop_min = tile_g + STRIDE;
+  if (bad || totS != totE) {
+    cnt += serial_region<DIRECT>(a, em, tile_g + t.a, stop_min, cnt, lane);
+    return;
+  }
+  if (totS) {
+    const int rel0 = (int)(tile_g - em.cb) + 64 * lane;
+    if (cS) em.put_bits(t.S, cnt + exS, rel0, false);
+    if (cE) em.put_bits(t.E, cnt + exE, rel0, true);
+    cnt += totS;
+  }
+  if (t.open) cnt += serial_region<DIRECT>(a, em, tile_g + t.lim, stop_min, cnt, lane);
+}
+
+// Processes the two tiles whose windows start at `win` (global position wg) and win + STRIDE.
+template <bool DIRECT>
+__device__ void process_pair(const ScanArgs& a, Emit<DIRECT>& em, const uint8_t* win, int64_t wg, unsigned& cnt,
+                             int lane, int rot, uint32_t sel_lo, uint32_t sel_hi) {
+  const FlatDev& f = a.flat;
+  const int piece = 31 - lane;
+  uint64_t ca[4], cb[4];
+  classify_piece(f, win + piece * 64, rot, sel_lo, sel_hi, ca);
+  classify_piece(f, win + STRIDE + piece * 64, rot, sel_lo, sel_hi, cb);
+  // bytes at or beyond the end of input belong to no class
+  const int64_t nv = a.n - wg;  // valid bytes from the start of tile A
+  if (nv < SUPER) {
+    // reversed bit r of lane l <=> tile byte 2047 - (64 l + r); valid <=> byte < nv
+    const int64_t ra = TILE - nv, rb = TILE - (nv - STRIDE);  // first valid reversed index
+    auto vmask = [&](int64_t r0) -> uint64_t {
+      const int64_t s = r0 - 64 * lane;
+      return s <= 0 ? ~0ull : (s >= 64 ? 0ull : (~0ull << s));
+    };
+    const uint64_t va = vmask(ra), vb = vmask(rb);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      ca[c] &= va;
+      cb[c] &= vb;
+    }
+  }
+
+  // ---- right to left: where can a match start ----
+  const int init_cls = f.rev_init_class;
+  uint64_t Ma = init_cls == 0 ? ca[0] : init_cls == 1 ? ca[1] : init_cls == 2 ? ca[2] : ca[3];
+  uint64_t Mb = init_cls == 0 ? cb[0] : init_cls == 1 ? cb[1] : init_cls == 2 ? cb[2] : cb[3];
+  const int rev_nops = f.rev_nops;
+  for (int k = 0; k < rev_nops; k++) {
+    const uint32_t op = f.rev_ops[k];
+    const uint32_t kind = op & 3u;
+    CGX_CLASS_SWITCH(op >> 2, rev_step<C>(kind, ca, cb, Ma, Mb, lane));
+  }
+  if (f.bs_runstart) {
+    // only the first byte of a run of class 0 (pattern opens with C+); the byte before the window
+    // counts as outside the class: position 0 is owned only when it is the start of the input
+    uint32_t upa = __shfl_down_sync(FULL, (uint32_t)ca[0], 1) & 1u;
+    uint32_t upb = __shfl_down_sync(FULL, (uint32_t)cb[0], 1) & 1u;
+    if (lane == 31) upa = upb = 0u;
+    Ma &= ca[0] & ~((ca[0] >> 1) | ((uint64_t)upa << 63));
+    Mb &= cb[0] & ~((cb[0] >> 1) | ((uint64_t)upb << 63));
+  }
+
+  // ---- forward orientation from here on ----
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    ca[c] = flip(ca[c]);
+    cb[c] = flip(cb[c]);
+  }
+  TileOut ta, tb;
+  ta.S = flip(Ma);
+  tb.S = flip(Mb);
+  const uint64_t Ua = ca[0] | ca[1] | ca[2] | ca[3], Ub = cb[0] | cb[1] | cb[2] | cb[3];
+  ownership(Ua, wg == 0, lane, ta);
+  ownership(Ub, false, lane, tb);
+  ta.S &= ta.a < 0 ? 0ull : range_mask(ta.a, ta.lim, lane);
+  tb.S &= tb.a < 0 ? 0ull : range_mask(tb.a, tb.lim, lane);
+
+  const uint32_t anyS = __ballot_sync(FULL, (ta.S | tb.S) != 0ull);
+  if (a.mode == M_ISMATCH) {
+    // starts inside the owned range are exact: a set bit is a match
+    if (anyS) {
+      if (lane == 0) a.total[1] = 1ull;
+      cnt += 1;
+      return;
+    }
+    // open tails may still hide a match
+    if (ta.a >= 0 && ta.open) cnt += serial_region<DIRECT>(a, em, wg + ta.lim, wg + STRIDE, cnt, lane);
+    if (tb.a >= 0 && tb.open) cnt += serial_region<DIRECT>(a, em, wg + STRIDE + tb.lim, wg + 2 * STRIDE, cnt, lane);
+    if (cnt && lane == 0) a.total[1] = 1ull;
+    return;
+  }
+
+  // ---- left to right: where do the matches end ----
+  uint64_t Ta = ta.S, Tb = tb.S;
+  if (anyS) {
+    const int fwd_nops = f.fwd_nops;
+    for (int k = 0; k < fwd_nops; k++) {
+      const uint32_t op = f.fwd_ops[k];
+      const uint32_t kind = op & 3u;
+      CGX_CLASS_SWITCH(op >> 2, fwd_step<C>(kind, ca, cb, Ta, Tb, lane));
+    }
+  }
+  ta.E = Ta;
+  tb.E = Tb;
+
+  // ---- starts and ends must alternate: S-only at even parity, anything with an end at odd ----
+  bool bad = false, badb = false;
+  if (anyS) {
+    const uint64_t pa = prefix_parity_excl(ta.S ^ ta.E, lane);
+    const uint64_t pb = prefix_parity_excl(tb.S ^ tb.E, lane);
+    uint64_t wa = (ta.S & ~ta.E & pa) | (ta.E & ~pa);
+    uint64_t wb = (tb.S & ~tb.E & pb) | (tb.E & ~pb);
+    if (f.bs_midrun_check) {
+      // an end in the middle of a class-0 run: the reference resumes there, which is no run start
+      wa |= ta.E & ca[0] & shl1(ca[0], lane, 0u);
+      wb |= tb.E & cb[0] & shl1(cb[0], lane, 0u);
+    }
+    bad = __any_sync(FULL, wa != 0ull);
+    badb = __any_sync(FULL, wb != 0ull);
+  }
+
+  // ---- counts, ranks, emission (tile A's matches precede tile B's) ----
+  const unsigned cSa = __popcll(ta.S), cEa = __popcll(ta.E), cSb = __popcll(tb.S), cEb = __popcll(tb.E);
+  unsigned exSa = 0, exEa = 0, exSb = 0, exEb = 0, totSa = 0, totEa = 0, totSb = 0, totEb = 0;
+  if (anyS) {
+    uint32_t xa = cSa | (cEa << 16), xb = cSb | (cEb << 16);
+    const uint32_t va = xa, vb = xb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t ya = __shfl_up_sync(FULL, xa, d), yb = __shfl_up_sync(FULL, xb, d);
+      if (lane >= d) {
+        xa += ya;
+        xb += yb;
+      }
+    }
+    const uint32_t ta_tot = __shfl_sync(FULL, xa, 31), tb_tot = __shfl_sync(FULL, xb, 31);
+    xa -= va;
+    xb -= vb;
+    exSa = xa & 0xFFFFu; exEa = xa >> 16; exSb = xb & 0xFFFFu; exEb = xb >> 16;
+    totSa = ta_tot & 0xFFFFu; totEa = ta_tot >> 16; totSb = tb_tot & 0xFFFFu; totEb = tb_tot >> 16;
+  }
+  finish_tile<DIRECT>(a, em, ta, wg, cSa, cEa, totSa, totEa, exSa, exEa, bad, cnt, lane);
+  finish_tile<DIRECT>(a, em, tb, wg + STRIDE, cSb, cEb, totSb, totEb, exSb, exEb, badb, cnt, lane);
+}
+
+// ---- resumable decoupled look-back ----------------------------------------------------------------
+struct Pending {
+  int64_t chunk = -1;        // < 0: none
+  unsigned cnt = 0;
+  int sb = 0;                // staging buffer that holds its matches
+  int64_t look = 0;          // nearest status word not consumed yet
+  unsigned long long excl = 0;
+};
+
+// Advances the look-back of p.  Returns true once p.excl is the exclusive prefix of p.chunk.
+// block == false: returns false instead of waiting for a predecessor that has published nothing yet.
+__device__ bool look_back_step(const ScanArgs& a, Pending& p, int lane, bool block) {
+  for (;;) {
+    const int64_t idx = p.look - lane;
+    unsigned long long v = LB_PREFIX;  // positions before chunk 0 act as a zero prefix
+    if (idx >= 0) v = ld_status(&a.status[idx]);
+    const uint32_t empty = __ballot_sync(FULL, (v >> 62) == 0);
+    const uint32_t pm = __ballot_sync(FULL, (v >> 62) == 2);
+    const int fe = empty ? __ffs((int)empty) - 1 : 32;
+    const int fp = pm ? __ffs((int)pm) - 1 : 32;
+    if (fp < fe) {
+      // aggregates of the lanes before the prefix, then the prefix itself
+      const unsigned part = __reduce_add_sync(FULL, lane < fp ? (unsigned)(v & 0xFFFFFFFFull) : 0u);
+      const unsigned long long pv = __shfl_sync(FULL, v & LB_VALUE, fp);
+      p.excl += part + pv;
+      return true;
+    }
+    const unsigned part = __reduce_add_sync(FULL, lane < fe ? (unsigned)(v & 0xFFFFFFFFull) : 0u);
+    p.excl += part;
+    p.look -= fe;
+    if (fe < 32) {
+      if (!block) return false;
+      cgx_spin_yield();
+    }
+  }
+}
+
+// publishes the inclusive prefix of a resolved chunk and stores its staged matches in global order
+__device__ void finalize(const ScanArgs& a, WarpSmem& ws, Pending& p, int lane) {
+  if (lane == 0) {
+    st_status(&a.status[p.chunk], LB_PREFIX | (p.excl + p.cnt));
+    if (p.chunk == a.nchunks - 1) a.total[0] = p.excl + p.cnt;
+  }
+  const int64_t b = p.chunk * (int64_t)CHUNKB + a.base;
+  const uint16_t* ss = ws.stS[p.sb];
+  const uint16_t* se = ws.stE[p.sb];
+  for (unsigned i = lane; i < p.cnt; i += 32) {
+    const unsigned long long gi = p.excl + i;
+    if ((int64_t)gi < a.cap)
+      *reinterpret_cast<longlong2*>(a.out + 2 * gi) = make_longlong2(b + ss[i], b + se[i]);
+  }
+  p.chunk = -1;
+}
+
+__global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const ScanArgs a) {
+  CGX_DYN_SMEM(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+  if (lane == 0) {
+    mbar_init(&ws.mbar[0], 1);
+    mbar_init(&ws.mbar[1], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  // lane-constant addressing of the rotated quarter loads (see classify_piece)
+  const int piece = 31 - lane;
+  const int rot = (piece >> 1) & 3;
+  uint32_t sel_lo = 0, sel_hi = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    sel_lo |= (uint32_t)((i + 2 * rot) & 7) << (4 * i);
+    sel_hi |= (uint32_t)((i + 4 + 2 * rot) & 7) << (4 * i);
+  }
+  // (tile B starts 31 pieces later: its piece parity is flipped, which keeps the same rotation
+  // conflict free)
+
+  uint32_t phase = 0;  // bit b = parity to wait for on mbar[b]
+  auto take_ticket = [&]() -> unsigned {
+    unsigned t = 0;
+    if (lane == 0) {
+      if (a.mode == M_ISMATCH && *((volatile unsigned long long*)&a.total[1])) t = 0xFFFFFFFFu;
+      else t = atomicAdd(a.ticket, 1u);
+    }
+    return __shfl_sync(FULL, t, 0);
+  };
+  // starts the bulk copy of iteration `it` of `chunk` into window buffer `b`
+  auto issue = [&](int64_t chunk, int it, int b) {
+    if (lane == 0) {
+      const int64_t g = chunk * (int64_t)CHUNKB + (int64_t)it * (2 * STRIDE);
+      int64_t bytes = a.n - g;
+      bytes = bytes > SUPER ? SUPER : bytes;
+      if (bytes > 0) {
+        // whole 16-byte blocks: the last block may run up to 15 bytes past n, inside the caller's
+        // 16-byte aligned allocation granule; those bytes are masked out (process_pair, nv)
+        const uint32_t bulk = (uint32_t)((bytes + 15) & ~(int64_t)15);
+        fence_proxy_async();
+        mbar_expect_tx(&ws.mbar[b], bulk);
+        tma_load_1d(ws.win[b], a.h + g, bulk, &ws.mbar[b]);
+      } else {
+        mbar_arrive(&ws.mbar[b]);
+      }
+    }
+  };
+  auto wait = [&](int b) {
+    mbar_wait(&ws.mbar[b], (phase >> b) & 1u);
+    phase ^= 1u << b;
+  };
+
+  int64_t cur = take_ticket();
+  int64_t nxt = cur < a.nchunks ? (int64_t)take_ticket() : cur;
+  int kb = 0, sb = 0;
+  Pending pend;
+  if (cur < a.nchunks) issue(cur, 0, 0);
+  while (cur < a.nchunks) {
+    const int64_t cbeg = cur * (int64_t)CHUNKB;
+    Emit<false> em{a, ws.stS[sb], ws.stE[sb], cbeg, 0ull};
+    unsigned cnt = 0;
+    for (int it = 0; it < PAIRS; it++) {
+      // the other window buffer was last read an iteration ago: refill it now
+      __syncwarp();
+      if (it + 1 < PAIRS) issue(cur, it + 1, kb ^ 1);
+      else if (nxt < a.nchunks) issue(nxt, 0, kb ^ 1);
+      wait(kb);
+      const int64_t wg = cbeg + (int64_t)it * (2 * STRIDE);
+      if (wg < a.n) process_pair<false>(a, em, ws.win[kb], wg, cnt, lane, rot, sel_lo, sel_hi);
+      kb ^= 1;
+      if (a.mode == M_FINDALL && pend.chunk >= 0 && look_back_step(a, pend, lane, false)) {
+        __syncwarp();
+        finalize(a, ws, pend, lane);
+      }
+    }
+    if (a.mode == M_FINDALL) {
+      // the staging buffer of the pending chunk is needed next: finish it now if it still waits
+      if (pend.chunk >= 0) {
+        look_back_step(a, pend, lane, true);
+        __syncwarp();
+        finalize(a, ws, pend, lane);
+      }
+      const bool ovf = cnt > (unsigned)CAP || __any_sync(FULL, em.far);
+      if (lane == 0 && cur != 0) st_status(&a.status[cur], LB_AGG | cnt);
+      pend.chunk = cur;
+      pend.cnt = cnt;
+      pend.sb = sb;
+      pend.look = cur - 1;
+      pend.excl = 0;
+      __syncwarp();  // staged matches visible to the lanes that will store them
+      if (ovf) {
+        // more matches than the staging buffer holds: get the offset now and redo the chunk with
+        // direct stores through the window buffer the prefetch is not using
+        look_back_step(a, pend, lane, true);
+        if (lane == 0) {
+          atomicAdd(&a.total[3], 1ull);  // diagnostics: chunks redone with direct stores
+          st_status(&a.status[cur], LB_PREFIX | (pend.excl + cnt));
+          if (cur == a.nchunks - 1) a.total[0] = pend.excl + cnt;
+        }
+        pend.chunk = -1;
+        Emit<true> em2{a, nullptr, nullptr, cbeg, pend.excl};
+        unsigned cnt2 = 0;
+        const int fb = kb ^ 1;
+        for (int it = 0; it < PAIRS; it++) {
+          const int64_t wg = cbeg + (int64_t)it * (2 * STRIDE);
+          if (wg >= a.n) break;
+          __syncwarp();
+          issue(cur, it, fb);
+          wait(fb);
+          process_pair<true>(a, em2, ws.win[fb], wg, cnt2, lane, rot, sel_lo, sel_hi);
+        }
+      } else {
+        sb ^= 1;
+        if (look_back_step(a, pend, lane, false)) finalize(a, ws, pend, lane);
+      }
+    } else if (cnt && lane == 0) {
+      atomicAdd(a.total, (unsigned long long)cnt);
+      a.total[1] = 1ull;
+    }
+    cur = nxt;
+    if (cur < a.nchunks) nxt = take_ticket();
+  }
+  if (pend.chunk >= 0) {
+    look_back_step(a, pend, lane, true);
+    finalize(a, ws, pend, lane);
+  }
+}
+
+}  // namespace
+
+int64_t scan_flat_chunks(int64_t n) {
+  if (n <= 0) return 0;
+  const int64_t tiles = (n + STRIDE - 1) / STRIDE;
+  return (tiles + TPC - 1) / TPC;
+}
+
+#ifdef CGX_CPU_SIM
+void sim_launch_scan_flat(const ScanArgs& a, unsigned grid) {
+  sim::launch<ScanArgs>(scan_flat_kernel, grid, FW_THREADS, sizeof(WarpSmem) * FW_WARPS, a);
+}
+#else
+// Launches the scan on `stream`.  ticket/status/total must be zeroed by the caller.
+cudaError_t launch_scan_flat(const ScanArgs& a, int sm_count, cudaStream_t stream) {
+  if (a.nchunks == 0) return cudaSuccess;
+  const size_t smem = sizeof(WarpSmem) * FW_WARPS;
+  static bool configured = false;
+  static int per_sm = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(scan_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_flat_kernel, FW_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    configured = true;
+  }
+  int64_t grid = (int64_t)sm_count * per_sm;
+  const int64_t need = (a.nchunks + FW_WARPS - 1) / FW_WARPS;
+  if (grid > need) grid = need;
+  scan_flat_kernel<<<(unsigned)grid, FW_THREADS, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+#endif
+
+}  // namespace cgx

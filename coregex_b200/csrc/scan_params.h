@@ -51,6 +51,16 @@ struct FlatDev {
   // from the constant bank: mode 0 = XOR-alignable range (3 ops/word), 1 = generic (5 ops/word)
   uint8_t cls_mode[4][4];
   uint32_t cls_k1[4][4], cls_k2[4][4];
+  // ---- bitstream engine (scan_flat.cu) --------------------------------------------------------
+  // bs_ok: the pattern is flat AND deterministic (every repeated/optional item's class is disjoint
+  // from whatever can follow it), so the leftmost-first match from a start is the forced greedy
+  // one and its END can be computed by a forward marker pass over the same class bitmaps.
+  int bs_ok;
+  int bs_runstart;       // starts are restricted to the first byte of a run of class 0 (pattern opens with C+)
+  int bs_midrun_check;   // a match may end in the middle of a class-0 run: such tiles take the serial path
+  int fwd_nops;
+  uint8_t fwd_ops[24];   // kind | class<<2, pattern order
+  uint32_t sync_lut[8];  // bit b set <=> byte b belongs to no class: no match can contain it
 };
 
 // Multi-literal engine tables (reference prefilter/teddy.go, teddy_fat.go), device resident.

@@ -47,8 +47,9 @@ void cgx_free(cgx_regex* re);
 /* reference meta.Engine.Strategy() (meta/engine.go:191): the strategy name the reference would
  * pick for this pattern, e.g. "UseDigitPrefilter".                                            */
 const char* cgx_strategy(const cgx_regex* re);
-/* which GPU engine runs it: "dfa-runstart", "dfa-byteset", "dfa-lut", "teddy", "fat-teddy",
- * "pikevm", "serial"                                                                          */
+/* which GPU engine runs it: "dfa-runstart", "dfa-byteset", "dfa-lut" (+"+flat": bit-parallel
+ * start filter in front of the DFA walk; +"+bitstream": flat deterministic pattern, starts AND
+ * ends bit-parallel, scan_flat.cu), "line-dfa", "teddy", "fat-teddy"                            */
 const char* cgx_engine(const cgx_regex* re);
 /* the record delimiter of this pattern: a byte no match can contain ('\n' whenever the pattern
  * allows it).  The scan treats the haystack as records separated by it; callers that split a

@@ -1,0 +1,74 @@
+// sim_capi.cpp — TEST HARNESS ONLY: runs the bitstream kernel SOURCE (scan_flat.cu compiled with
+// -DCGX_CPU_SIM against tests/sim/simt_cpu.h) on the CPU SIMT emulator, with the tables the real
+// host compiler produces.  Used by tests/test_sim_flat.py to debug warp-level logic without a GPU.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "host/engine.h"
+#include "scan_params.h"
+
+namespace cgx {
+int64_t scan_flat_chunks(int64_t n);
+void sim_launch_scan_flat(const ScanArgs& a, unsigned grid);
+}  // namespace cgx
+
+using namespace cgx;
+
+extern "C" {
+
+// returns 0 ok, -1 compile error, -2 pattern not eligible for the bitstream engine
+int cgxsim_scan(const char* pat, size_t plen, const uint8_t* h, int64_t n, int64_t base, int mode,
+                int64_t* out, int64_t cap, uint64_t result[4], unsigned grid, int pad_byte) {
+  std::unique_ptr<Compiled> c;
+  std::string err;
+  if (CompilePattern(std::string(pat, plen), c, err) != COMPILE_OK) return -1;
+  if (c->kind != ENG_DFA || !c->flat.bs_ok) return -2;
+  // 16-byte aligned copy, padded with bytes the kernel must never interpret
+  const size_t padded = ((size_t)n + 15) / 16 * 16 + 64;
+  uint8_t* hb = (uint8_t*)aligned_alloc(128, (padded + 127) / 128 * 128);
+  memset(hb, pad_byte, (padded + 127) / 128 * 128);
+  if (n) memcpy(hb, h, (size_t)n);
+  const int64_t nchunks = scan_flat_chunks(n);
+  std::vector<unsigned long long> status((size_t)(nchunks > 0 ? nchunks : 1), 0ull);
+  unsigned long long scratch[8] = {0};
+  ScanArgs a;
+  memset(&a, 0, sizeof a);
+  a.h = hb;
+  a.n = n;
+  a.base = base;
+  a.dfa.trans = c->dfa.trans.data();
+  a.dfa.eoi = c->dfa.eoi.data();
+  a.dfa.nstates = c->dfa.nstates;
+  for (int k = 0; k < 5; k++) a.dfa.start[k] = c->dfa.start[k];
+  a.filter.kind = c->filter_kind;
+  a.filter.nranges = c->nranges;
+  for (int k = 0; k < 4; k++) {
+    a.filter.lo[k] = c->rlo[k];
+    a.filter.hi[k] = c->rhi[k];
+  }
+  a.filter.lut = c->lut;
+  a.flat = c->flat;
+  a.engine = SEL_DFA;
+  a.skip_safe = c->skip_safe ? 1 : 0;
+  a.delim = c->delim;
+  a.mode = mode;
+  a.out = out;
+  a.cap = cap;
+  a.total = scratch;
+  a.ticket = (unsigned*)(scratch + 4);
+  a.status = status.data();
+  a.nchunks = nchunks;
+  if (nchunks) sim_launch_scan_flat(a, grid);
+  result[0] = scratch[0];
+  result[1] = scratch[1];
+  result[2] = scratch[2];
+  result[3] = scratch[3];
+  free(hb);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+"""ctypes binding to the CPU SIMT build of the bitstream kernel (tests/sim/).
+
+TEST INFRASTRUCTURE ONLY: the kernel source compiled for a fiber-based warp emulator so that its
+warp-level logic can be checked against the oracle in a container without a GPU.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_DIR = os.path.join(_ROOT, "tests", "sim")
+_SO = os.path.join(_DIR, "_build", "libcgxsim.so")
+_lib = None
+last_diag = {}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", _DIR], stdout=subprocess.DEVNULL)
+        L = C.CDLL(_SO)
+        L.cgxsim_scan.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
+                                  C.c_void_p, C.c_int64, C.POINTER(C.c_uint64), C.c_uint, C.c_int]
+        _lib = L
+    return _lib
+
+
+class NotEligible(Exception):
+    pass
+
+
+def scan(pattern, hay, mode=0, cap=None, grid=2, base=0, pad=ord("1")):
+    """Runs the emulated kernel.  Returns (total, flag, pairs[ndarray k x 2])."""
+    if isinstance(pattern, str):
+        pattern = pattern.encode()
+    a = np.frombuffer(bytes(hay), dtype=np.uint8) if not isinstance(hay, np.ndarray) else np.ascontiguousarray(hay)
+    n = a.size
+    if cap is None:
+        cap = n + 16
+    out = np.full((max(cap, 1), 2), -7, dtype=np.int64)
+    res = (C.c_uint64 * 4)()
+    r = lib().cgxsim_scan(pattern, len(pattern), a.ctypes.data if n else None, n, base, mode,
+                          out.ctypes.data, cap, res, grid, pad)
+    if r == -2:
+        raise NotEligible(pattern)
+    if r != 0:
+        raise RuntimeError("compile failed: %r" % pattern)
+    total = int(res[0])
+    global last_diag
+    last_diag = {"serial": int(res[2]), "redo": int(res[3])}
+    return total, int(res[1]), out[: min(total, cap)]

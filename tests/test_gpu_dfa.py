@@ -15,8 +15,22 @@ IP = r"\d+\.\d+\.\d+\.\d+"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+BITSTREAM = True
+
+
+@pytest.fixture(autouse=True, params=["bitstream", "dfa-kernel"])
+def kernel_choice(request):
+    """Flat deterministic patterns can run on two kernels (scan_flat.cu / scan_dfa.cu): every case
+    that goes through check() is run on both (the switch is a no-op for other patterns)."""
+    global BITSTREAM
+    BITSTREAM = request.param == "bitstream"
+    yield
+    BITSTREAM = True
+
+
 def check(pat, hay, oracle=None):
     r = cg.Compile(pat)
+    r.set_bitstream(BITSTREAM)
     o = oracle or Oracle(pat)
     want = o.find_all(hay)
     got = r.find_all_index_array(hay)

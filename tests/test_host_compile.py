@@ -85,7 +85,7 @@ def test_reference_strategy_agrees_with_oracle(pat):
 
 def test_ip_engine_choice():
     r = cg.Compile(r"\d+\.\d+\.\d+\.\d+")
-    assert (r.strategy, r.engine) == ("UseDigitPrefilter", "dfa-runstart+flat")
+    assert (r.strategy, r.engine) == ("UseDigitPrefilter", "dfa-runstart+bitstream")
     m = TableModel(r)
     assert m.nstates <= 12 and m.filter_kind == 0 and m.skip_safe and m.ranges == [(0x30, 0x39)]
     assert m.find_all(b"x10.0.0.1 y 1.2.3 z 8.8.8.8") == [[1, 9], [20, 27]]
@@ -166,7 +166,7 @@ def test_flat_start_filter_is_exact_superset(pat):
     r = cg.Compile(pat)
     if "teddy" in r.engine:
         pytest.skip("literal engine")
-    assert r.engine.endswith("+flat")
+    assert r.engine.endswith(("+flat", "+bitstream"))
     fm, tm = FlatModel(r), TableModel(r)
     rng = np.random.default_rng(17)
     alphabet = np.frombuffer(b"0123456789..  abABxz\n@_-d35", dtype=np.uint8)

@@ -1,0 +1,188 @@
+"""Bitstream kernel (coregex_b200/csrc/scan_flat.cu) on the CPU SIMT emulator vs the oracle.
+
+The kernel SOURCE is compiled with g++ against tests/sim/simt_cpu.h (one fiber per CUDA thread),
+so these tests exercise the real warp-level code — marker passes, ownership by sync bytes, the
+alternation check, the serial replay, staging, overflow redo and the resumable look-back — in
+a container without a GPU.  The -m gpu tests repeat the same comparisons on the device.
+"""
+import random
+
+import numpy as np
+import pytest
+
+import coregex_b200 as cg
+import sim_lib
+from oracle_lib import Oracle
+
+IP = r"\d+\.\d+\.\d+\.\d+"
+STRIDE, TILE, CHUNK = 1984, 2048, 8 * 1984
+BACKEND = "sim"
+
+
+@pytest.fixture(autouse=True, params=["sim", pytest.param("gpu", marks=pytest.mark.gpu)])
+def backend(request):
+    """Every case runs on the emulator (CPU suite) and, under -m gpu, on the device through the C ABI."""
+    global BACKEND
+    BACKEND = request.param
+    yield
+    BACKEND = "sim"
+
+
+def scan(pat, hay, mode=0, cap=None, grid=2, base=0):
+    """(total, flag, pairs) from the selected backend."""
+    if BACKEND == "sim":
+        return sim_lib.scan(pat, hay, mode=mode, cap=cap, grid=grid, base=base)
+    import torch
+    from gpu_util import scan_device
+    r = cg.Compile(pat)
+    if not r.engine.endswith("+bitstream"):
+        raise sim_lib.NotEligible(pat)
+    a = np.frombuffer(bytes(hay), dtype=np.uint8) if not isinstance(hay, np.ndarray) else hay
+    t = torch.zeros(a.size + 64, dtype=torch.uint8, device="cuda")
+    t[a.size:] = ord("1")  # bytes after the haystack must never be interpreted
+    if a.size:
+        t[: a.size] = torch.from_numpy(a.copy()).cuda()
+    return scan_device(r, t[: a.size], mode=mode, cap=(a.size + 16 if cap is None else cap), base=base)
+
+
+def check(pat, hay, grid=2, **kw):
+    if isinstance(hay, (bytes, bytearray)):
+        hay = np.frombuffer(bytes(hay), dtype=np.uint8)
+    want = Oracle(pat).find_all(hay)
+    tot, _, pairs = scan(pat, hay, grid=grid, **kw)
+    assert tot == len(want), (pat, tot, len(want))
+    assert np.array_equal(pairs, want), (pat, pairs[:5], want[:5])
+    return want
+
+
+def test_log_corpus_multi_cta():
+    hay = cg.synth_host(cg.SYNTH_LOG, 7, 4096 * 48)
+    w = check(IP, hay, grid=3)
+    assert len(w) > 1500
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 15, 16, 17, 63, 64, 65, STRIDE - 1, STRIDE, STRIDE + 1, TILE - 1, TILE,
+                               TILE + 1, 2 * STRIDE - 1, 2 * STRIDE, 2 * STRIDE + 1, STRIDE + TILE - 1,
+                               STRIDE + TILE, STRIDE + TILE + 1, CHUNK - 1, CHUNK, CHUNK + 1, CHUNK + 63,
+                               CHUNK + 64, CHUNK + 65, 2 * CHUNK])
+def test_sizes_around_tile_and_chunk_edges(n):
+    unit = b"a 1.2.3.4 b 10.20.30.40.50 c9.9.9.9\n"
+    hay = (unit * (n // len(unit) + 1))[:n]
+    check(IP, hay)
+    # the input ends inside / right after a match
+    hay2 = bytearray(hay)
+    tail = b"7.7.7.77"
+    if n >= len(tail) + 1:
+        hay2[n - len(tail) - 1] = ord(" ")
+        hay2[n - len(tail):] = tail
+        check(IP, hay2)
+
+
+def test_match_straddles_every_tile_offset():
+    ip = b"123.45.67.89"
+    for off in range(STRIDE - 16, STRIDE + 70):
+        hay = bytearray(b"x" * (3 * STRIDE))
+        hay[off:off + len(ip)] = ip
+        hay[off + TILE:off + TILE + len(ip)] = ip
+        w = check(IP, hay, grid=1)
+        assert len(w) == 2
+
+
+def test_overlapping_candidates_take_the_serial_path():
+    hay = (b"v 1.2.3.4.5.6.7.8 w 1.2.3.4.5 z\n" * 200)
+    check(IP, hay)
+    hay = b"1.2.3.4.5.6.7.8.9.10.11.12" * 400  # no sync byte at all
+    check(IP, hay)
+
+
+def test_long_spans_without_sync_bytes():
+    rng = random.Random(5)
+    parts = []
+    for _ in range(40):
+        parts.append(b" " * rng.randrange(1, 50))
+        parts.append(bytes(rng.choice(b"0123456789.") for _ in range(rng.randrange(1, 5000))))
+        parts.append(b" 1.2.3.4 ")
+    check(IP, b"".join(parts), grid=2)
+    check(IP, b"9" * 5000 + b".1.1.1 " + b"8" * 3000)
+    check(IP, b"1.1.1." + b"9" * 6000)
+
+
+def test_random_digit_dot_soup():
+    rng = random.Random(11)
+    for trial in range(30):
+        alphabet = rng.choice([b"0123456789. ", b"01.", b"0. \n", b"12345.x"])
+        n = rng.choice([50, 500, 2100, 4100, 9000, 17000])
+        hay = bytes(rng.choice(alphabet) for _ in range(n))
+        check(IP, hay, grid=rng.choice([1, 2]))
+
+
+PATTERNS = [
+    r"\w+@\w+\.\w+",
+    r"[a-z]+=\d+",
+    r"ab+c",
+    r"a+ba",           # a match can end in the middle of a run of the first class
+    r"\d{1,3}\.\d{1,3}",
+    r"[A-Z][a-z]+",
+    r"x\d*y?z",
+    r"\d+",
+    r"[a-c]+[x-z]?",
+    r"GET|POST",       # not flat: must be refused by the bitstream engine
+    r"fo+\d+b",
+    r"\d{4}-\d{2}-\d{2}",
+]
+
+
+@pytest.mark.parametrize("pat", PATTERNS)
+def test_pattern_zoo(pat):
+    rng = random.Random(hash(pat) & 0xFFFF)
+    alphabet = b"abcxyz0123456789@.=- ABZGETPOSfor\n"
+    words = [b"user@host.com", b"key=123", b"abbbc", b"aabaab", b"1.22.333", b"Hello", b"x12yz", b"xz", b"foo42bar", b"fooo7b",
+             b"2024-01-31", b"aaabaaaba", b"abcabcx", b"GET", b"POST"]
+    for trial in range(6):
+        parts = []
+        size = 0
+        target = rng.choice([300, 2500, 5000, 20000])
+        while size < target:
+            if rng.random() < 0.4:
+                p = rng.choice(words)
+            else:
+                p = bytes(rng.choice(alphabet) for _ in range(rng.randrange(1, 12)))
+            parts.append(p)
+            size += len(p)
+        hay = b"".join(parts)
+        try:
+            check(pat, hay, grid=rng.choice([1, 2]))
+        except sim_lib.NotEligible:
+            # not flat, or neighbouring starts would share their end (`\d \d?`): candidate/DFA kernel
+            assert pat in (r"GET|POST", r"\d{1,3}\.\d{1,3}"), pat
+            return
+
+
+def test_dense_matches_overflow_redo():
+    hay = b"1 22 333 4 55 6 7 8 9 0 " * 2500  # far more than 256 matches per chunk
+    w = check(r"\d+", hay, grid=2)
+    assert len(w) > 20000
+    check(IP, b"1.1.1.1 " * 6000, grid=2)
+
+
+def test_count_ismatch_and_cap():
+    hay = cg.synth_host(cg.SYNTH_LOG, 3, 4096 * 16)
+    want = Oracle(IP).find_all(hay)
+    tot, flag, _ = scan(IP, hay, mode=cg.MODE_COUNT)
+    assert tot == len(want)
+    tot, flag, _ = scan(IP, hay, mode=cg.MODE_ISMATCH)
+    assert flag == 1
+    tot, flag, _ = scan(IP, b"no address here 1.2.3 \n" * 3000, mode=cg.MODE_ISMATCH)
+    assert flag == 0
+    tot, flag, _ = scan(IP, b"x" * 40000 + b" 1.2.3.4", mode=cg.MODE_ISMATCH)
+    assert flag == 1
+    # capped output: the first `cap` matches, total still counts all
+    tot, _, pairs = scan(IP, hay, cap=100)
+    assert tot == len(want) and np.array_equal(pairs, want[:100])
+
+
+def test_base_offset_is_added():
+    hay = b"a 1.2.3.4 b\n" * 500
+    want = Oracle(IP).find_all(np.frombuffer(hay, dtype=np.uint8))
+    tot, _, pairs = scan(IP, hay, base=1 << 40)
+    assert np.array_equal(pairs, want + (1 << 40))
