@@ -282,7 +282,9 @@ def main():
     traffic = profile_traffic()
     if traffic and traffic.get("input_bytes") != n:
         traffic = None  # the committed capture is of a different corpus size
-    roof = {"bound": "hbm", "kernel": "scan_flat_kernel" if r.engine.endswith("+bitstream") else "scan_dfa_kernel", "achieved": round(achieved, 1), "peak": peak,
+    jit_state = cg._lib.cgx_debug_jit_state(r._h)
+    roof = {"bound": "hbm", "kernel": "cgx_flat_jit" if jit_state == 1 else
+            "scan_flat_kernel" if r.engine.endswith("+bitstream") else "scan_dfa_kernel", "achieved": round(achieved, 1), "peak": peak,
             "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": round(kernel_ms, 4),
             "input_only_frac": round(n / (kernel_ms * 1e-3) / 1e9 / peak, 4),
@@ -311,7 +313,9 @@ def main():
                    "output": "int64 (start,end) pairs in global order, written to HBM every step",
                    "l2": "inputs (16 GiB) far exceed the 126 MB L2; no flush needed",
                    "parallelism": "corpus shards, one process per GPU, NCCL all_gather of counts only",
-                   "engine": r.engine, "reference_strategy": r.strategy},
+                   "engine": r.engine, "reference_strategy": r.strategy,
+                   "kernel": ("cgx_flat_jit (NVRTC-specialised scan_flat.cu)" if jit_state == 1 else
+                              "scan_flat_kernel (generic)" if r.engine.endswith("+bitstream") else "scan_dfa_kernel")},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
     }
     print(json.dumps(line))

@@ -150,7 +150,7 @@ class Regex:
     def set_bitstream(self, on):
         """Tests / A-B runs: keep a flat deterministic pattern on the candidate+DFA kernel
         (on=False) instead of the bitstream kernel.  Returns the previous setting."""
-        return bool(_lib.cgx_debug_set_bitstream(self._h, 1 if on else 0))
+        return bool(_lib.cgx_debug_set_bitstream(self._h, int(on)))
 
     @property
     def launches(self):

@@ -12,6 +12,7 @@
 
 #include "../../include/coregex_b200.h"
 #include "host/engine.h"
+#include "jit.h"
 #include "scan_params.h"
 #include "synth.h"
 
@@ -84,6 +85,11 @@ struct cgx_regex {
   // flat deterministic patterns run on the bitstream kernel (scan_flat.cu); CGX_BITSTREAM=0 or
   // cgx_debug_set_bitstream keep them on the candidate/DFA kernel (A/B runs, tests of both paths)
   bool bitstream = true;
+  // NVRTC-specialised build of that kernel for this pattern: 0 = not tried yet, 1 = in use,
+  // -1 = unavailable (the generic nvcc-built kernel runs; jit_error says why)
+  int jit_state = 0;
+  const JitKernel* jit = nullptr;
+  std::string jit_error;
 
   int ensure_pipeline() {
     if (s_h2d) return CGX_OK;
@@ -227,9 +233,36 @@ const char* cgx_strategy(const cgx_regex* re) { return RefStrategyName(re->c->an
 const char* cgx_engine(const cgx_regex* re) { return re->c->engine_name.c_str(); }
 int cgx_num_captures(const cgx_regex* re) { return re->c->prog.num_captures; }
 uint64_t cgx_launch_count(const cgx_regex* re) { return re->launches.load(); }
+// 1: the NVRTC-specialised kernel is in use, -1: unavailable (generic kernel; cgx_last_error has
+// the reason after this call), 0: no device scan has happened yet / pattern not on that engine
+int cgx_debug_jit_state(cgx_regex* re) {
+  if (re->jit_state < 0) g_last_error = re->jit_error;
+  return re->jit_state;
+}
+// NVRTC only (no device needed): size of the specialised cubin, or -1 with cgx_last_error set
+long cgx_debug_jit_compile(cgx_regex* re, char* cubin_out, size_t cap) {
+  if (!re->c->flat.bs_ok) {
+    g_last_error = "pattern does not run on the bitstream engine";
+    return -1;
+  }
+  std::vector<char> cubin;
+  std::string err;
+  if (!JitCompileCubin(re->c->flat, cubin, err)) {
+    g_last_error = err;
+    return -1;
+  }
+  if (cubin_out && cap >= cubin.size()) memcpy(cubin_out, cubin.data(), cubin.size());
+  return (long)cubin.size();
+}
 int cgx_debug_set_bitstream(cgx_regex* re, int on) {
   const int was = re->bitstream ? 1 : 0;
   re->bitstream = on != 0;
+  if (on == 2) {  // bitstream engine, but the generic nvcc-built kernel instead of the NVRTC one
+    re->jit_state = -1;
+    re->jit_error = "specialisation switched off by cgx_debug_set_bitstream(2)";
+  } else if (re->jit_state == -1) {
+    re->jit_state = 0;
+  }
   return was;
 }
 int cgx_delimiter(const cgx_regex* re) { return re->c->kind == ENG_TEDDY ? '\n' : re->c->delim; }
@@ -253,10 +286,13 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   const int64_t nchunks = use_flat ? scan_flat_chunks((int64_t)len) : scan_dfa_chunks((int64_t)len);
   int r;
   if ((r = re->d_ticket_total.ensure(64))) return r;
-  if ((r = re->d_status.ensure((size_t)(nchunks > 0 ? nchunks : 1) * 8))) return r;
+  // look-back words: one per chunk, then (bitstream kernel) one word + one counter per 32 chunks
+  const size_t ngroups = (size_t)(nchunks + 31) / 32 + 1;
+  const size_t status_bytes = (size_t)(nchunks > 0 ? nchunks : 1) * 8 + ngroups * 12;
+  if ((r = re->d_status.ensure(status_bytes))) return r;
   CU(cudaMemsetAsync(re->d_ticket_total.p, 0, 64, st));
   if (mode == CGX_MODE_FINDALL && nchunks > 0)
-    CU(cudaMemsetAsync(re->d_status.p, 0, (size_t)nchunks * 8, st));
+    CU(cudaMemsetAsync(re->d_status.p, 0, status_bytes, st));
   ScanArgs a;
   memset(&a, 0, sizeof a);
   a.h = d_h;
@@ -310,8 +346,18 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   a.ticket = (unsigned int*)(tt + 4);  // separate 32-byte sector
   a.status = (unsigned long long*)re->d_status.p;
   a.nchunks = nchunks;
-  if (use_flat) CU(launch_scan_flat(a, re->sm_count, st));
-  else CU(launch_scan_dfa(a, re->sm_count, st));
+  a.gstatus = a.status + (nchunks > 0 ? nchunks : 1);
+  a.gcount = (unsigned int*)(a.gstatus + ngroups);
+  if (use_flat) {
+    if (re->jit_state == 0) {
+      re->jit = GetJitKernel(c.flat, re->jit_error);
+      re->jit_state = re->jit ? 1 : -1;
+    }
+    if (re->jit_state == 1) CU(launch_scan_flat_jit(re->jit, a, re->sm_count, st));
+    else CU(launch_scan_flat(a, re->sm_count, st));
+  } else {
+    CU(launch_scan_dfa(a, re->sm_count, st));
+  }
   re->launches++;
   if (d_result) CU(cudaMemcpyAsync(d_result, tt, 16, cudaMemcpyDeviceToDevice, st));
   return CGX_OK;

@@ -1,6 +1,7 @@
 // engine.cpp — pattern -> GPU engine selection and table building.
 #include "engine.h"
 
+#include <cstdio>
 #include <cstring>
 
 namespace cgx {
@@ -263,6 +264,36 @@ static void DecideBitstream(Compiled& c, const uint8_t (&lazy)[24]) {
   for (int x = 0; x < 256; x++)
     if (!set_has(any, x)) f.sync_lut[x >> 5] |= 1u << (x & 31);
   f.bs_ok = 1;
+}
+
+std::string JitHeader(const FlatDev& f) {
+  char buf[256];
+  std::string o = "// generated by host/engine.cpp JitHeader\n";
+  auto add = [&](const char* fmt, auto... args) {
+    snprintf(buf, sizeof buf, fmt, args...);
+    o += buf;
+  };
+  add("#define CGX_JIT_NCLASSES %d\n", f.nclasses);
+  add("#define CGX_JIT_RUNSTART %d\n", f.bs_runstart);
+  add("#define CGX_JIT_MIDRUN %d\n", f.bs_midrun_check);
+  add("#define CGX_JIT_REV_INIT %d\n", f.rev_init_class);
+  o += "#define CGX_JIT_REV_PASS(STEP)";
+  for (int k = 0; k < f.rev_nops; k++) add(" STEP(%d, %d)", f.rev_ops[k] & 3, f.rev_ops[k] >> 2);
+  o += "\n#define CGX_JIT_FWD_PASS(STEP)";
+  for (int k = 0; k < f.fwd_nops; k++) add(" STEP(%d, %d)", f.fwd_ops[k] & 3, f.fwd_ops[k] >> 2);
+  o += "\ntemplate <int C> __device__ __forceinline__ uint32_t cgx_jit_flags(uint32_t w) { return 0u; }\n";
+  for (int c = 0; c < f.nclasses; c++) {
+    add("template <> __device__ __forceinline__ uint32_t cgx_jit_flags<%d>(uint32_t w) {\n  uint32_t fl = 0u;\n", c);
+    for (int r = 0; r < f.cls_nranges[c]; r++) {
+      if (f.cls_mode[c][r] == 0)
+        add("  { const uint32_t z = ((w ^ 0x%08Xu) & 0x7F7F7F7Fu) + 0x%08Xu; fl |= ~(z | w) & 0x80808080u; }\n",
+            f.cls_k1[c][r], f.cls_k2[c][r]);
+      else
+        add("  fl |= swar_in_range(w, 0x%08Xu, 0x%08Xu);\n", f.cls_k1[c][r], f.cls_k2[c][r]);
+    }
+    o += "  return fl;\n}\n";
+  }
+  return o;
 }
 
 int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, std::string& err) {

@@ -1,0 +1,24 @@
+// jit.h — NVRTC specialisation of the bitstream kernel (see jit.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "scan_params.h"
+
+namespace cgx {
+
+struct JitKernel {
+  void* func = nullptr;  // CUfunction
+  int per_sm = 0;        // resident CTAs per SM
+};
+
+// NVRTC only: works without a device (used by the CPU test that the specialised source builds)
+bool JitCompileCubin(const FlatDev& f, std::vector<char>& cubin, std::string& err);
+// compiled + loaded kernel for the current device, cached per program; nullptr (and err) when
+// NVRTC or the driver entry points are unavailable
+const JitKernel* GetJitKernel(const FlatDev& f, std::string& err);
+cudaError_t launch_scan_flat_jit(const JitKernel* k, const ScanArgs& a, int sm_count, cudaStream_t stream);
+
+}  // namespace cgx

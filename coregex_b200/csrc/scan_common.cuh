@@ -1,13 +1,15 @@
 // scan_common.cuh — device helpers for the sm_100a scan kernels: TMA 1-D bulk copy + mbarrier,
 // SWAR byte-class tests, warp scans, decoupled look-back words.
 #pragma once
-#include <cstdint>
+#include "scan_params.h"  // fixed-width integer types (also under NVRTC, which has no host headers)
 #ifdef CGX_CPU_SIM
 // test harness: the kernel source compiled for the CPU SIMT emulator (tests/sim/simt_cpu.h), which
 // supplies the mbarrier / bulk-copy / status-word helpers below as plain C++
 #include "simt_cpu.h"
 #else
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 #define CGX_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 #endif
 
@@ -15,6 +17,7 @@ namespace cgx {
 
 #ifndef CGX_CPU_SIM
 __device__ __forceinline__ void cgx_spin_yield() {}
+__device__ __forceinline__ void cgx_threadfence() { __threadfence(); }
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS: UBLKCP) -----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

@@ -31,10 +31,6 @@
 #include "scan_common.cuh"
 #include "scan_params.h"
 
-#ifndef CGX_CPU_SIM
-#include <cstdio>
-#endif
-
 namespace cgx {
 
 namespace {
@@ -49,6 +45,20 @@ constexpr int PAIRS = TPC / 2;          // iterations per chunk (two tiles each)
 constexpr int CHUNKB = TPC * STRIDE;    // 15872 bytes owned per chunk
 constexpr int SUPER = STRIDE + TILE;    // 4032 bytes loaded per iteration
 constexpr int CAP = 256;                // staged matches per chunk
+
+// The pattern-dependent parts exist twice: as an interpreter over ScanArgs::flat (this translation
+// unit as nvcc builds it, and the CPU emulator build), and — when the host JIT-compiles this file
+// with NVRTC for one pattern (csrc/jit.cpp, -DCGX_JIT + a generated cgx_jit_prog.h) — as
+// straight-line code: no program loads, no dispatch, class constants as immediates.
+#ifdef CGX_JIT
+#define P_NCLASSES CGX_JIT_NCLASSES
+#define P_RUNSTART CGX_JIT_RUNSTART
+#define P_MIDRUN CGX_JIT_MIDRUN
+#else
+#define P_NCLASSES f.nclasses
+#define P_RUNSTART f.bs_runstart
+#define P_MIDRUN f.bs_midrun_check
+#endif
 
 struct WarpSmem {
   alignas(128) uint8_t win[2][SUPER];
@@ -83,6 +93,9 @@ __device__ __forceinline__ uint64_t flip(uint64_t x) {
 }
 
 // ---- classification ----------------------------------------------------------------------------
+#ifdef CGX_JIT
+#include "cgx_jit_prog.h"  // generated per pattern (host/engine.cpp JitHeader), compiled by csrc/jit.cpp
+#endif
 // 8 flag words (bit 7 of a byte set <=> byte in class) -> bit-reversed 32-bit mask (bit 31-b <=> byte b)
 __device__ __forceinline__ uint32_t pack_rev(const uint32_t* fl) {
   uint32_t acc[4];
@@ -97,6 +110,10 @@ __device__ __forceinline__ uint32_t pack_rev(const uint32_t* fl) {
 template <int C>
 __device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t (&w)[16]) {
   uint32_t fl[16];
+#ifdef CGX_JIT
+#pragma unroll
+  for (int k = 0; k < 16; k++) fl[k] = cgx_jit_flags<C>(w[k]);  // generated: ranges as immediates
+#else
   const int nr = f.cls_nranges[C];
   if (nr == 1 && f.cls_mode[C][0] == 0) {  // one XOR-alignable range: 3 ops per word
     const uint32_t k1 = f.cls_k1[C][0], k2 = f.cls_k2[C][0];
@@ -122,6 +139,7 @@ __device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t
       }
     }
   }
+#endif
   return mk64(pack_rev(fl), pack_rev(fl + 8));  // bytes 0..31 in the high word
 }
 
@@ -142,9 +160,9 @@ __device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* 
   }
   uint64_t raw[4];
   raw[0] = class_rev64<0>(f, w);
-  raw[1] = f.nclasses > 1 ? class_rev64<1>(f, w) : 0ull;
-  raw[2] = f.nclasses > 2 ? class_rev64<2>(f, w) : 0ull;
-  raw[3] = f.nclasses > 3 ? class_rev64<3>(f, w) : 0ull;
+  raw[1] = P_NCLASSES > 1 ? class_rev64<1>(f, w) : 0ull;
+  raw[2] = P_NCLASSES > 2 ? class_rev64<2>(f, w) : 0ull;
+  raw[3] = P_NCLASSES > 3 ? class_rev64<3>(f, w) : 0ull;
 #pragma unroll
   for (int c = 0; c < 4; c++) {
     const uint32_t lo = (uint32_t)raw[c], hi = (uint32_t)(raw[c] >> 32);
@@ -222,19 +240,19 @@ __device__ __forceinline__ uint64_t prefix_parity_excl(uint64_t x, int lane) {
 }
 
 // ---- output ------------------------------------------------------------------------------------
-template <bool DIRECT>
 struct Emit {
   const ScanArgs& a;
   uint16_t* stS;
   uint16_t* stE;
   int64_t cb;               // global position of the chunk's first byte
-  unsigned long long goff;  // DIRECT: global index of the chunk's first match
+  unsigned long long goff;  // direct: global index of the chunk's first match
+  bool direct;              // store straight to global memory (chunk redone after a staging overflow)
   bool far = false;         // a staged offset did not fit 16 bits
 
   // rel = position relative to the chunk
   __device__ __forceinline__ void put(unsigned idx, int64_t rel, bool is_end) {
     if (a.mode != M_FINDALL) return;
-    if (DIRECT) {
+    if (direct) {
       const unsigned long long gi = goff + idx;
       if ((int64_t)gi < a.cap) a.out[2 * gi + (is_end ? 1 : 0)] = cb + a.base + rel;
     } else {
@@ -242,12 +260,18 @@ struct Emit {
       else if (idx < (unsigned)CAP) (is_end ? stE : stS)[idx] = (uint16_t)rel;
     }
   }
-  __device__ __forceinline__ void put_bits(uint64_t bits, unsigned idx, int rel0, bool is_end) {
+  // all set bits of one 32-bit half; most words hold zero or one
+  __device__ __forceinline__ unsigned put_bits32(uint32_t bits, unsigned idx, int rel0, bool is_end) {
     while (bits) {
-      const int b = __ffsll((long long)bits) - 1;
+      const int b = __ffs((int)bits) - 1;
       bits &= bits - 1;
       put(idx++, rel0 + b, is_end);
     }
+    return idx;
+  }
+  __device__ __forceinline__ void put_bits(uint64_t bits, unsigned idx, int rel0, bool is_end) {
+    idx = put_bits32((uint32_t)bits, idx, rel0, is_end);
+    put_bits32((uint32_t)(bits >> 32), idx, rel0 + 32, is_end);
   }
 };
 
@@ -262,7 +286,7 @@ __device__ __forceinline__ bool is_sync(const ScanArgs& a, uint32_t b) {
 }
 
 // anchored leftmost-first walk through global memory (reference dfa/lazy/lazy.go:219-324)
-__device__ int64_t dfa_walk_global(const ScanArgs& a, int64_t p0) {
+__device__ __noinline__ int64_t dfa_walk_global(const ScanArgs& a, int64_t p0) {
   unsigned s = a.dfa.start[0];
   int64_t last = -1, p = p0;
   while (s) {
@@ -280,10 +304,9 @@ __device__ int64_t dfa_walk_global(const ScanArgs& a, int64_t p0) {
 
 // One lane replays the reference loop (meta/findall.go:176-290 over meta/find_indices.go:1050-1088)
 // from global position `from` until the candidate search meets a sync byte at or after `stop_min`
-// (or the end of input).  Returns the number of matches emitted from index idx0 on.
-template <bool DIRECT>
-__device__ unsigned serial_region(const ScanArgs& a, Emit<DIRECT>& em, int64_t from, int64_t stop_min,
-                                  unsigned idx0, int lane) {
+// (or the end of input).  Returns the number of matches emitted from index idx0 on.  Cold path.
+__device__ __noinline__ unsigned serial_region(const ScanArgs& a, Emit& em, int64_t from, int64_t stop_min,
+                                               unsigned idx0, int lane) {
   unsigned added = 0;
   bool far = false;
   if (lane == 0) {
@@ -356,42 +379,40 @@ __device__ __forceinline__ void ownership(uint64_t U, bool first_tile, int lane,
     a = 64 * fl + __shfl_sync(FULL, firstsync, fl) + 1;
   }
   const int fs31 = __shfl_sync(FULL, firstsync, 31);
-  const int hl = has ? 31 - __clz((int)has) : 0;
-  const int ls = __shfl_sync(FULL, lastsync, hl);
   t.a = a;
   if (fs31 < 64) {
     t.open = false;
     t.lim = STRIDE + fs31 + 1;
   } else {
     t.open = true;
+    const int hl = has ? 31 - __clz((int)has) : 0;
+    const int ls = __shfl_sync(FULL, lastsync, hl);
     const int z1 = has ? 64 * hl + ls + 1 : 0;
     t.lim = a > z1 ? a : z1;
   }
 }
 
-template <bool DIRECT>
-__device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit<DIRECT>& em, const TileOut& t, int64_t tile_g,
-                                            unsigned cS, unsigned cE, unsigned totS, unsigned totE,
-                                            unsigned exS, unsigned exE, bool bad, unsigned& cnt, int lane) {
+__device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const TileOut& t, int64_t tile_g,
+                                            unsigned totS, unsigned totE, unsigned exS, unsigned exE, bool bad,
+                                            unsigned& cnt, int lane) {
   if (t.a < 0) return;
   const int64_t stop_min = tile_g + STRIDE;
   if (bad || totS != totE) {
-    cnt += serial_region<DIRECT>(a, em, tile_g + t.a, stop_min, cnt, lane);
+    cnt += serial_region(a, em, tile_g + t.a, stop_min, cnt, lane);
     return;
   }
   if (totS) {
     const int rel0 = (int)(tile_g - em.cb) + 64 * lane;
-    if (cS) em.put_bits(t.S, cnt + exS, rel0, false);
-    if (cE) em.put_bits(t.E, cnt + exE, rel0, true);
+    em.put_bits(t.S, cnt + exS, rel0, false);
+    em.put_bits(t.E, cnt + exE, rel0, true);
     cnt += totS;
   }
-  if (t.open) cnt += serial_region<DIRECT>(a, em, tile_g + t.lim, stop_min, cnt, lane);
+  if (t.open) cnt += serial_region(a, em, tile_g + t.lim, stop_min, cnt, lane);
 }
 
 // Processes the two tiles whose windows start at `win` (global position wg) and win + STRIDE.
-template <bool DIRECT>
-__device__ void process_pair(const ScanArgs& a, Emit<DIRECT>& em, const uint8_t* win, int64_t wg, unsigned& cnt,
-                             int lane, int rot, uint32_t sel_lo, uint32_t sel_hi) {
+__device__ __forceinline__ void process_pair(const ScanArgs& a, Emit& em, const uint8_t* win, int64_t wg,
+                                             unsigned& cnt, int lane, int rot, uint32_t sel_lo, uint32_t sel_hi) {
   const FlatDev& f = a.flat;
   const int piece = 31 - lane;
   uint64_t ca[4], cb[4];
@@ -415,6 +436,12 @@ __device__ void process_pair(const ScanArgs& a, Emit<DIRECT>& em, const uint8_t*
   }
 
   // ---- right to left: where can a match start ----
+#ifdef CGX_JIT
+  uint64_t Ma = ca[CGX_JIT_REV_INIT], Mb = cb[CGX_JIT_REV_INIT];
+#define CGX_STEP(kind, cls) rev_step<cls>(kind, ca, cb, Ma, Mb, lane);
+  CGX_JIT_REV_PASS(CGX_STEP)
+#undef CGX_STEP
+#else
   const int init_cls = f.rev_init_class;
   uint64_t Ma = init_cls == 0 ? ca[0] : init_cls == 1 ? ca[1] : init_cls == 2 ? ca[2] : ca[3];
   uint64_t Mb = init_cls == 0 ? cb[0] : init_cls == 1 ? cb[1] : init_cls == 2 ? cb[2] : cb[3];
@@ -424,7 +451,8 @@ __device__ void process_pair(const ScanArgs& a, Emit<DIRECT>& em, const uint8_t*
     const uint32_t kind = op & 3u;
     CGX_CLASS_SWITCH(op >> 2, rev_step<C>(kind, ca, cb, Ma, Mb, lane));
   }
-  if (f.bs_runstart) {
+#endif
+  if (P_RUNSTART) {
     // only the first byte of a run of class 0 (pattern opens with C+); the byte before the window
     // counts as outside the class: position 0 is owned only when it is the start of the input
     uint32_t upa = __shfl_down_sync(FULL, (uint32_t)ca[0], 1) & 1u;
@@ -437,8 +465,10 @@ __device__ void process_pair(const ScanArgs& a, Emit<DIRECT>& em, const uint8_t*
   // ---- forward orientation from here on ----
 #pragma unroll
   for (int c = 0; c < 4; c++) {
-    ca[c] = flip(ca[c]);
-    cb[c] = flip(cb[c]);
+    if (c < P_NCLASSES) {
+      ca[c] = flip(ca[c]);
+      cb[c] = flip(cb[c]);
+    }
   }
   TileOut ta, tb;
   ta.S = flip(Ma);
@@ -458,46 +488,48 @@ __device__ void process_pair(const ScanArgs& a, Emit<DIRECT>& em, const uint8_t*
       return;
     }
     // open tails may still hide a match
-    if (ta.a >= 0 && ta.open) cnt += serial_region<DIRECT>(a, em, wg + ta.lim, wg + STRIDE, cnt, lane);
-    if (tb.a >= 0 && tb.open) cnt += serial_region<DIRECT>(a, em, wg + STRIDE + tb.lim, wg + 2 * STRIDE, cnt, lane);
+    if (ta.a >= 0 && ta.open) cnt += serial_region(a, em, wg + ta.lim, wg + STRIDE, cnt, lane);
+    if (tb.a >= 0 && tb.open) cnt += serial_region(a, em, wg + STRIDE + tb.lim, wg + 2 * STRIDE, cnt, lane);
     if (cnt && lane == 0) a.total[1] = 1ull;
     return;
   }
 
-  // ---- left to right: where do the matches end ----
-  uint64_t Ta = ta.S, Tb = tb.S;
+  unsigned exSa = 0, exEa = 0, exSb = 0, exEb = 0, totSa = 0, totEa = 0, totSb = 0, totEb = 0;
+  bool bad = false, badb = false;
+  ta.E = tb.E = 0ull;
   if (anyS) {
+    // ---- left to right: where do the matches end ----
+    uint64_t Ta = ta.S, Tb = tb.S;
+#ifdef CGX_JIT
+#define CGX_STEP(kind, cls) fwd_step<cls>(kind, ca, cb, Ta, Tb, lane);
+    CGX_JIT_FWD_PASS(CGX_STEP)
+#undef CGX_STEP
+#else
     const int fwd_nops = f.fwd_nops;
     for (int k = 0; k < fwd_nops; k++) {
       const uint32_t op = f.fwd_ops[k];
       const uint32_t kind = op & 3u;
       CGX_CLASS_SWITCH(op >> 2, fwd_step<C>(kind, ca, cb, Ta, Tb, lane));
     }
-  }
-  ta.E = Ta;
-  tb.E = Tb;
+#endif
+    ta.E = Ta;
+    tb.E = Tb;
 
-  // ---- starts and ends must alternate: S-only at even parity, anything with an end at odd ----
-  bool bad = false, badb = false;
-  if (anyS) {
+    // ---- starts and ends must alternate: S-only at even parity, anything with an end at odd ----
     const uint64_t pa = prefix_parity_excl(ta.S ^ ta.E, lane);
     const uint64_t pb = prefix_parity_excl(tb.S ^ tb.E, lane);
     uint64_t wa = (ta.S & ~ta.E & pa) | (ta.E & ~pa);
     uint64_t wb = (tb.S & ~tb.E & pb) | (tb.E & ~pb);
-    if (f.bs_midrun_check) {
+    if (P_MIDRUN) {
       // an end in the middle of a class-0 run: the reference resumes there, which is no run start
       wa |= ta.E & ca[0] & shl1(ca[0], lane, 0u);
       wb |= tb.E & cb[0] & shl1(cb[0], lane, 0u);
     }
     bad = __any_sync(FULL, wa != 0ull);
     badb = __any_sync(FULL, wb != 0ull);
-  }
 
-  // ---- counts, ranks, emission (tile A's matches precede tile B's) ----
-  const unsigned cSa = __popcll(ta.S), cEa = __popcll(ta.E), cSb = __popcll(tb.S), cEb = __popcll(tb.E);
-  unsigned exSa = 0, exEa = 0, exSb = 0, exEb = 0, totSa = 0, totEa = 0, totSb = 0, totEb = 0;
-  if (anyS) {
-    uint32_t xa = cSa | (cEa << 16), xb = cSb | (cEb << 16);
+    // ---- counts and ranks (tile A's matches precede tile B's) ----
+    uint32_t xa = __popcll(ta.S) | (__popcll(ta.E) << 16), xb = __popcll(tb.S) | (__popcll(tb.E) << 16);
     const uint32_t va = xa, vb = xb;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -513,39 +545,68 @@ __device__ void process_pair(const ScanArgs& a, Emit<DIRECT>& em, const uint8_t*
     exSa = xa & 0xFFFFu; exEa = xa >> 16; exSb = xb & 0xFFFFu; exEb = xb >> 16;
     totSa = ta_tot & 0xFFFFu; totEa = ta_tot >> 16; totSb = tb_tot & 0xFFFFu; totEb = tb_tot >> 16;
   }
-  finish_tile<DIRECT>(a, em, ta, wg, cSa, cEa, totSa, totEa, exSa, exEa, bad, cnt, lane);
-  finish_tile<DIRECT>(a, em, tb, wg + STRIDE, cSb, cEb, totSb, totEb, exSb, exEb, badb, cnt, lane);
+  finish_tile(a, em, ta, wg, totSa, totEa, exSa, exEa, bad, cnt, lane);
+  finish_tile(a, em, tb, wg + STRIDE, totSb, totEb, exSb, exEb, badb, cnt, lane);
 }
 
-// ---- resumable decoupled look-back ----------------------------------------------------------------
+// ---- resumable two-level look-back ------------------------------------------------------------------
+// Chunk c publishes its match count in status[c] (flag LB_AGG).  Chunks form groups of 32; the
+// warp that finishes a group's last chunk publishes the group's sum in gstatus[g] (LB_AGG), and
+// whoever learns the prefix at a group's start publishes it as gstatus[g-1] (LB_PREFIX, the
+// inclusive prefix through group g-1).  The exclusive prefix of chunk c is therefore: counts of the
+// earlier chunks of its own group (one 32-wide load) + a decoupled look-back over GROUP words
+// (32 groups = 1024 chunks per step), instead of a walk over the ~3000 chunks that are in flight.
 struct Pending {
   int64_t chunk = -1;        // < 0: none
   unsigned cnt = 0;
   int sb = 0;                // staging buffer that holds its matches
-  int64_t look = 0;          // nearest status word not consumed yet
+  int phase = 1;             // 1: own group, 2: earlier groups
+  int64_t look = 0;          // phase 2: nearest group word not consumed yet
   unsigned long long excl = 0;
+  unsigned long long gpre = 0;  // phase 2 sum: prefix at the start of the chunk's group
 };
 
 // Advances the look-back of p.  Returns true once p.excl is the exclusive prefix of p.chunk.
-// block == false: returns false instead of waiting for a predecessor that has published nothing yet.
+// block == false: returns false instead of waiting for a word that has not been published yet.
 __device__ bool look_back_step(const ScanArgs& a, Pending& p, int lane, bool block) {
+  const int64_t g = p.chunk >> 5;
+  if (p.phase == 1) {
+    const int64_t idx = (g << 5) + lane;
+    for (;;) {
+      unsigned long long v = LB_AGG;  // lanes at or beyond the chunk contribute nothing
+      if (idx < p.chunk) v = ld_status(&a.status[idx]);
+      if (__all_sync(FULL, (v >> 62) != 0)) {
+        p.excl = __reduce_add_sync(FULL, (unsigned)(v & 0xFFFFFFFFull));
+        break;
+      }
+      if (!block) return false;
+      cgx_spin_yield();
+    }
+    if (g == 0) return true;
+    p.phase = 2;
+    p.look = g - 1;
+    p.gpre = 0;
+  }
   for (;;) {
     const int64_t idx = p.look - lane;
-    unsigned long long v = LB_PREFIX;  // positions before chunk 0 act as a zero prefix
-    if (idx >= 0) v = ld_status(&a.status[idx]);
+    unsigned long long v = LB_PREFIX;  // positions before group 0 act as a zero prefix
+    if (idx >= 0) v = ld_status(&a.gstatus[idx]);
     const uint32_t empty = __ballot_sync(FULL, (v >> 62) == 0);
     const uint32_t pm = __ballot_sync(FULL, (v >> 62) == 2);
     const int fe = empty ? __ffs((int)empty) - 1 : 32;
     const int fp = pm ? __ffs((int)pm) - 1 : 32;
     if (fp < fe) {
-      // aggregates of the lanes before the prefix, then the prefix itself
+      // sums of the groups before the prefix, then the prefix itself
       const unsigned part = __reduce_add_sync(FULL, lane < fp ? (unsigned)(v & 0xFFFFFFFFull) : 0u);
       const unsigned long long pv = __shfl_sync(FULL, v & LB_VALUE, fp);
-      p.excl += part + pv;
+      p.gpre += part + pv;
+      p.excl += p.gpre;
+      // the inclusive prefix through the previous group, for everybody behind us
+      if (lane == 0 && (p.look != g - 1 || fp != 0)) st_status(&a.gstatus[g - 1], LB_PREFIX | p.gpre);
       return true;
     }
     const unsigned part = __reduce_add_sync(FULL, lane < fe ? (unsigned)(v & 0xFFFFFFFFull) : 0u);
-    p.excl += part;
+    p.gpre += part;
     p.look -= fe;
     if (fe < 32) {
       if (!block) return false;
@@ -554,12 +615,31 @@ __device__ bool look_back_step(const ScanArgs& a, Pending& p, int lane, bool blo
   }
 }
 
-// publishes the inclusive prefix of a resolved chunk and stores its staged matches in global order
-__device__ void finalize(const ScanArgs& a, WarpSmem& ws, Pending& p, int lane) {
+// publishes the chunk's count; the warp that completes a group publishes the group's sum
+__device__ __forceinline__ void publish_count(const ScanArgs& a, int64_t chunk, unsigned cnt, int lane) {
+  const int64_t g = chunk >> 5;
+  const int64_t members = a.nchunks - (g << 5) < 32 ? a.nchunks - (g << 5) : 32;
+  unsigned old = 0;
   if (lane == 0) {
-    st_status(&a.status[p.chunk], LB_PREFIX | (p.excl + p.cnt));
-    if (p.chunk == a.nchunks - 1) a.total[0] = p.excl + p.cnt;
+    st_status(&a.status[chunk], LB_AGG | cnt);
+    cgx_threadfence();  // the count is visible before the group counter moves
+    old = atomicAdd(&a.gcount[g], 1u);
   }
+  old = __shfl_sync(FULL, old, 0);
+  if ((int64_t)old == members - 1) {
+    cgx_threadfence();
+    const int64_t idx = (g << 5) + lane;
+    const unsigned long long v = idx < a.nchunks ? ld_status(&a.status[idx]) : 0ull;
+    const unsigned sum = __reduce_add_sync(FULL, (unsigned)(v & 0xFFFFFFFFull));
+    // never overwrite a prefix a faster successor may already have published... it cannot have:
+    // a prefix for this group needs this very sum
+    if (lane == 0) st_status(&a.gstatus[g], LB_AGG | sum);
+  }
+}
+
+// stores the staged matches of a resolved chunk in global match order
+__device__ __forceinline__ void finalize(const ScanArgs& a, WarpSmem& ws, Pending& p, int lane) {
+  if (lane == 0 && p.chunk == a.nchunks - 1) a.total[0] = p.excl + p.cnt;
   const int64_t b = p.chunk * (int64_t)CHUNKB + a.base;
   const uint16_t* ss = ws.stS[p.sb];
   const uint16_t* se = ws.stE[p.sb];
@@ -571,7 +651,14 @@ __device__ void finalize(const ScanArgs& a, WarpSmem& ws, Pending& p, int lane) 
   p.chunk = -1;
 }
 
-__global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const ScanArgs a) {
+}  // namespace
+
+#ifdef CGX_JIT
+extern "C" __global__ void __launch_bounds__(FW_THREADS, 5) cgx_flat_jit(const __grid_constant__ ScanArgs a) {
+#else
+namespace {
+__global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_constant__ ScanArgs a) {
+#endif
   CGX_DYN_SMEM(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
@@ -582,7 +669,8 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const ScanArgs
   }
   __syncwarp();
 
-  // lane-constant addressing of the rotated quarter loads (see classify_piece)
+  // lane-constant addressing of the rotated quarter loads (see classify_piece); tile B starts 31
+  // pieces later: its piece parity is flipped, which keeps the same rotation conflict free
   const int piece = 31 - lane;
   const int rot = (piece >> 1) & 3;
   uint32_t sel_lo = 0, sel_hi = 0;
@@ -591,8 +679,6 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const ScanArgs
     sel_lo |= (uint32_t)((i + 2 * rot) & 7) << (4 * i);
     sel_hi |= (uint32_t)((i + 4 + 2 * rot) & 7) << (4 * i);
   }
-  // (tile B starts 31 pieces later: its piece parity is flipped, which keeps the same rotation
-  // conflict free)
 
   uint32_t phase = 0;  // bit b = parity to wait for on mbar[b]
   auto take_ticket = [&]() -> unsigned {
@@ -631,9 +717,12 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const ScanArgs
   int kb = 0, sb = 0;
   Pending pend;
   if (cur < a.nchunks) issue(cur, 0, 0);
+  bool direct = false;
+  unsigned long long goff = 0;
   while (cur < a.nchunks) {
+    // one pass over the chunk: staged (normal) or, after a staging overflow, with direct stores
     const int64_t cbeg = cur * (int64_t)CHUNKB;
-    Emit<false> em{a, ws.stS[sb], ws.stE[sb], cbeg, 0ull};
+    Emit em{a, ws.stS[sb], ws.stE[sb], cbeg, goff, direct};
     unsigned cnt = 0;
     for (int it = 0; it < PAIRS; it++) {
       // the other window buffer was last read an iteration ago: refill it now
@@ -642,57 +731,52 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const ScanArgs
       else if (nxt < a.nchunks) issue(nxt, 0, kb ^ 1);
       wait(kb);
       const int64_t wg = cbeg + (int64_t)it * (2 * STRIDE);
-      if (wg < a.n) process_pair<false>(a, em, ws.win[kb], wg, cnt, lane, rot, sel_lo, sel_hi);
+      if (wg < a.n) process_pair(a, em, ws.win[kb], wg, cnt, lane, rot, sel_lo, sel_hi);
       kb ^= 1;
-      if (a.mode == M_FINDALL && pend.chunk >= 0 && look_back_step(a, pend, lane, false)) {
+      if (pend.chunk >= 0 && look_back_step(a, pend, lane, false)) {
         __syncwarp();
         finalize(a, ws, pend, lane);
       }
     }
-    if (a.mode == M_FINDALL) {
+    if (a.mode != M_FINDALL) {
+      if (cnt && lane == 0) {
+        atomicAdd(a.total, (unsigned long long)cnt);
+        a.total[1] = 1ull;
+      }
+    } else if (!direct) {
       // the staging buffer of the pending chunk is needed next: finish it now if it still waits
       if (pend.chunk >= 0) {
         look_back_step(a, pend, lane, true);
         __syncwarp();
         finalize(a, ws, pend, lane);
       }
-      const bool ovf = cnt > (unsigned)CAP || __any_sync(FULL, em.far);
-      if (lane == 0 && cur != 0) st_status(&a.status[cur], LB_AGG | cnt);
+      publish_count(a, cur, cnt, lane);
       pend.chunk = cur;
       pend.cnt = cnt;
       pend.sb = sb;
-      pend.look = cur - 1;
+      pend.phase = 1;
       pend.excl = 0;
       __syncwarp();  // staged matches visible to the lanes that will store them
-      if (ovf) {
-        // more matches than the staging buffer holds: get the offset now and redo the chunk with
-        // direct stores through the window buffer the prefetch is not using
+      if (cnt > (unsigned)CAP || __any_sync(FULL, em.far)) {
+        // more matches than the staging buffer holds: get the offset now and run the chunk again
+        // with direct stores.  The prefetch of the next chunk is dropped and re-issued later.
         look_back_step(a, pend, lane, true);
         if (lane == 0) {
           atomicAdd(&a.total[3], 1ull);  // diagnostics: chunks redone with direct stores
-          st_status(&a.status[cur], LB_PREFIX | (pend.excl + cnt));
           if (cur == a.nchunks - 1) a.total[0] = pend.excl + cnt;
         }
         pend.chunk = -1;
-        Emit<true> em2{a, nullptr, nullptr, cbeg, pend.excl};
-        unsigned cnt2 = 0;
-        const int fb = kb ^ 1;
-        for (int it = 0; it < PAIRS; it++) {
-          const int64_t wg = cbeg + (int64_t)it * (2 * STRIDE);
-          if (wg >= a.n) break;
-          __syncwarp();
-          issue(cur, it, fb);
-          wait(fb);
-          process_pair<true>(a, em2, ws.win[fb], wg, cnt2, lane, rot, sel_lo, sel_hi);
-        }
-      } else {
-        sb ^= 1;
-        if (look_back_step(a, pend, lane, false)) finalize(a, ws, pend, lane);
+        direct = true;
+        goff = pend.excl;
+        if (nxt < a.nchunks) wait(kb);
+        __syncwarp();
+        issue(cur, 0, kb);
+        continue;
       }
-    } else if (cnt && lane == 0) {
-      atomicAdd(a.total, (unsigned long long)cnt);
-      a.total[1] = 1ull;
+      sb ^= 1;
+      if (look_back_step(a, pend, lane, false)) finalize(a, ws, pend, lane);
     }
+    direct = false;
     cur = nxt;
     if (cur < a.nchunks) nxt = take_ticket();
   }
@@ -701,18 +785,28 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const ScanArgs
     finalize(a, ws, pend, lane);
   }
 }
-
+#ifndef CGX_JIT
 }  // namespace
+#endif
 
+#if !defined(CGX_JIT) || defined(CGX_CPU_SIM)
 int64_t scan_flat_chunks(int64_t n) {
   if (n <= 0) return 0;
   const int64_t tiles = (n + STRIDE - 1) / STRIDE;
   return (tiles + TPC - 1) / TPC;
 }
 
+size_t scan_flat_smem_bytes() { return sizeof(WarpSmem) * FW_WARPS; }
+int scan_flat_threads() { return FW_THREADS; }
+int scan_flat_warps() { return FW_WARPS; }
+
 #ifdef CGX_CPU_SIM
 void sim_launch_scan_flat(const ScanArgs& a, unsigned grid) {
+#ifdef CGX_JIT
+  sim::launch<ScanArgs>(cgx_flat_jit, grid, FW_THREADS, sizeof(WarpSmem) * FW_WARPS, a);
+#else
   sim::launch<ScanArgs>(scan_flat_kernel, grid, FW_THREADS, sizeof(WarpSmem) * FW_WARPS, a);
+#endif
 }
 #else
 // Launches the scan on `stream`.  ticket/status/total must be zeroed by the caller.
@@ -736,5 +830,7 @@ cudaError_t launch_scan_flat(const ScanArgs& a, int sm_count, cudaStream_t strea
   return cudaGetLastError();
 }
 #endif
+
+#endif  // host side
 
 }  // namespace cgx

@@ -1,6 +1,19 @@
 // scan_params.h — plain structs shared by the host engine and the sm_100a scan kernels.
 #pragma once
+#ifdef __CUDACC_RTC__
+// NVRTC (csrc/jit.cpp) compiles without host headers
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef signed char int8_t;
+typedef short int16_t;
+typedef int int32_t;
+typedef long long int64_t;
+typedef unsigned long size_t;
+#else
 #include <cstdint>
+#endif
 
 namespace cgx {
 
@@ -107,6 +120,9 @@ struct ScanArgs {
   unsigned int* ticket;        // chunk ticket counter (zeroed before launch)
   unsigned long long* status;  // nchunks look-back words (zeroed before launch)
   int64_t nchunks;
+  // bitstream kernel: one word and one arrival counter per group of 32 chunks (zeroed before launch)
+  unsigned long long* gstatus;
+  unsigned int* gcount;
 };
 
 }  // namespace cgx

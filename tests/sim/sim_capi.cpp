@@ -20,6 +20,18 @@ using namespace cgx;
 
 extern "C" {
 
+// text of cgx_jit_prog.h for the pattern (to build the specialised flavour of the emulated kernel)
+int cgxsim_jit_header(const char* pat, size_t plen, char* out, size_t cap) {
+  std::unique_ptr<Compiled> c;
+  std::string err;
+  if (CompilePattern(std::string(pat, plen), c, err) != COMPILE_OK) return -1;
+  if (c->kind != ENG_DFA || !c->flat.bs_ok) return -2;
+  const std::string h = JitHeader(c->flat);
+  if (h.size() + 1 > cap) return -3;
+  memcpy(out, h.c_str(), h.size() + 1);
+  return (int)h.size();
+}
+
 // returns 0 ok, -1 compile error, -2 pattern not eligible for the bitstream engine
 int cgxsim_scan(const char* pat, size_t plen, const uint8_t* h, int64_t n, int64_t base, int mode,
                 int64_t* out, int64_t cap, uint64_t result[4], unsigned grid, int pad_byte) {
@@ -34,6 +46,9 @@ int cgxsim_scan(const char* pat, size_t plen, const uint8_t* h, int64_t n, int64
   if (n) memcpy(hb, h, (size_t)n);
   const int64_t nchunks = scan_flat_chunks(n);
   std::vector<unsigned long long> status((size_t)(nchunks > 0 ? nchunks : 1), 0ull);
+  const size_t ngroups = (size_t)(nchunks + 31) / 32 + 1;
+  std::vector<unsigned long long> gstatus(ngroups, 0ull);
+  std::vector<unsigned> gcount(ngroups, 0u);
   unsigned long long scratch[8] = {0};
   ScanArgs a;
   memset(&a, 0, sizeof a);
@@ -62,6 +77,8 @@ int cgxsim_scan(const char* pat, size_t plen, const uint8_t* h, int64_t n, int64
   a.ticket = (unsigned*)(scratch + 4);
   a.status = status.data();
   a.nchunks = nchunks;
+  a.gstatus = gstatus.data();
+  a.gcount = gcount.data();
   if (nchunks) sim_launch_scan_flat(a, grid);
   result[0] = scratch[0];
   result[1] = scratch[1];

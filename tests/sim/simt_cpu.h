@@ -24,6 +24,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __align__(n) __attribute__((aligned(n)))
 
 namespace sim {
@@ -230,6 +231,7 @@ inline longlong2 make_longlong2(long long x, long long y) { return longlong2{x, 
 // ---- the helpers scan_common.cuh implements with inline PTX on the device --------------------------
 namespace cgx {
 inline void cgx_spin_yield() { sim::yield(); }
+inline void cgx_threadfence() {}
 // mbarrier model: the word counts completed phases
 inline void mbar_init(uint64_t* bar, unsigned) { *bar = 0; }
 inline void fence_mbar_init() {}

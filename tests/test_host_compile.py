@@ -249,3 +249,19 @@ def test_non_newline_delimiter_tables_match_oracle(pat):
     for it in range(300):
         h = b"".join(pieces[int(i)] for i in rng.integers(0, len(pieces), int(rng.integers(0, 20))))
         assert m.find_all(h) == o.find_all(h).tolist(), (pat, h)
+
+
+def test_bitstream_kernel_specialises_with_nvrtc():
+    """jit.cu: the bitstream kernel source, embedded in the library, compiles with NVRTC for
+    sm_100a with the generated per-pattern header (no device needed for this step)."""
+    import ctypes as C
+    L = cg._lib
+    L.cgx_debug_jit_compile.restype = C.c_long
+    L.cgx_debug_jit_compile.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    for pat in (r"\d+\.\d+\.\d+\.\d+", r"[a-z]+=\d+[x-z]?"):
+        r = cg.Compile(pat)
+        assert r.engine.endswith("+bitstream")
+        n = L.cgx_debug_jit_compile(r._h, None, 0)
+        assert n > 10000, L.cgx_last_error()
+    r = cg.Compile(r"GET|POST")
+    assert L.cgx_debug_jit_compile(r._h, None, 0) == -1

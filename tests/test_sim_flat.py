@@ -19,9 +19,10 @@ STRIDE, TILE, CHUNK = 1984, 2048, 8 * 1984
 BACKEND = "sim"
 
 
-@pytest.fixture(autouse=True, params=["sim", pytest.param("gpu", marks=pytest.mark.gpu)])
+@pytest.fixture(autouse=True, params=["sim", "simjit", pytest.param("gpu", marks=pytest.mark.gpu)])
 def backend(request):
-    """Every case runs on the emulator (CPU suite) and, under -m gpu, on the device through the C ABI."""
+    """Every case runs on the emulator — the interpreting build and the per-pattern specialised
+    build (what jit.cu compiles for the device) — and, under -m gpu, on the device through the C ABI."""
     global BACKEND
     BACKEND = request.param
     yield
@@ -30,8 +31,8 @@ def backend(request):
 
 def scan(pat, hay, mode=0, cap=None, grid=2, base=0):
     """(total, flag, pairs) from the selected backend."""
-    if BACKEND == "sim":
-        return sim_lib.scan(pat, hay, mode=mode, cap=cap, grid=grid, base=base)
+    if BACKEND in ("sim", "simjit"):
+        return sim_lib.scan(pat, hay, mode=mode, cap=cap, grid=grid, base=base, jit=BACKEND == "simjit")
     import torch
     from gpu_util import scan_device
     r = cg.Compile(pat)
@@ -186,3 +187,12 @@ def test_base_offset_is_added():
     want = Oracle(IP).find_all(np.frombuffer(hay, dtype=np.uint8))
     tot, _, pairs = scan(IP, hay, base=1 << 40)
     assert np.array_equal(pairs, want + (1 << 40))
+
+
+@pytest.mark.gpu
+def test_device_runs_the_nvrtc_specialised_kernel():
+    import ctypes as C
+    r = cg.Compile(IP)
+    assert r.FindAllIndex(b"a 1.2.3.4 b") == [[2, 9]]
+    st = cg._lib.cgx_debug_jit_state(r._h)
+    assert st == 1, (st, cg._lib.cgx_last_error())

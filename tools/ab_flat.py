@@ -53,7 +53,7 @@ def run(pattern, kind, seed, nbytes, cap_div=40, window=64 * 4096):
     r = cg.Compile(pattern)
     cap = nbytes // cap_div
     outs, line = [], {"pattern": pattern, "bytes": nbytes, "engine": r.engine}
-    for name, on in (("bitstream", True), ("dfa", False)):
+    for name, on in (("bitstream", 1), ("bitstream_generic", 2), ("dfa", 0)):
         r.set_bitstream(on)
         out = torch.empty((cap, 2), dtype=torch.int64, device="cuda")
         res = torch.zeros(2, dtype=torch.int64, device="cuda")
@@ -64,8 +64,9 @@ def run(pattern, kind, seed, nbytes, cap_div=40, window=64 * 4096):
         line[name] = {"ms": round(ms, 3), "GBps": round(nbytes / ms / 1e6, 1), "matches": total,
                       "serial_replays": sc[2] if on else None, "redo_chunks": sc[3] if on else None}
         outs.append((total, out))
-    (ta, oa), (tb, ob) = outs
-    line["identical"] = bool(ta == tb and ta <= cap and torch.equal(oa[:ta], ob[:tb]))
+    (ta, oa), (tg, og), (tb, ob) = outs
+    line["identical"] = bool(ta == tb == tg and ta <= cap and torch.equal(oa[:ta], ob[:tb]) and
+                             torch.equal(oa[:ta], og[:tg]))
     # oracle on a regenerated window
     wblocks = window // bs
     b0 = (nbytes // bs // 2 // wblocks) * wblocks
@@ -75,7 +76,7 @@ def run(pattern, kind, seed, nbytes, cap_div=40, window=64 * 4096):
     i0, i1 = np.searchsorted(got[:, 0], lo), np.searchsorted(got[:, 0], lo + window)
     line["oracle_window_ok"] = bool(np.array_equal(got[i0:i1], Oracle(pattern).find_all(hay) + lo))
     print(json.dumps(line), flush=True)
-    del t, outs, oa, ob
+    del t, outs, oa, ob, og
     torch.cuda.empty_cache()
     return line
 
