@@ -286,9 +286,9 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   const int64_t nchunks = use_flat ? scan_flat_chunks((int64_t)len) : scan_dfa_chunks((int64_t)len);
   int r;
   if ((r = re->d_ticket_total.ensure(64))) return r;
-  // look-back words: one per chunk, then (bitstream kernel) one word + one counter per 32 chunks
+  // look-back words: one per chunk, then (bitstream kernel) two words per 32 chunks
   const size_t ngroups = (size_t)(nchunks + 31) / 32 + 1;
-  const size_t status_bytes = (size_t)(nchunks > 0 ? nchunks : 1) * 8 + ngroups * 12;
+  const size_t status_bytes = (size_t)(nchunks > 0 ? nchunks : 1) * 8 + ngroups * 16;
   if ((r = re->d_status.ensure(status_bytes))) return r;
   CU(cudaMemsetAsync(re->d_ticket_total.p, 0, 64, st));
   if (mode == CGX_MODE_FINDALL && nchunks > 0)
@@ -347,7 +347,7 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   a.status = (unsigned long long*)re->d_status.p;
   a.nchunks = nchunks;
   a.gstatus = a.status + (nchunks > 0 ? nchunks : 1);
-  a.gcount = (unsigned int*)(a.gstatus + ngroups);
+  a.gacc = a.gstatus + ngroups;
   if (use_flat) {
     if (re->jit_state == 0) {
       re->jit = GetJitKernel(c.flat, re->jit_error);

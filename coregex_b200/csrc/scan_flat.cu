@@ -615,25 +615,17 @@ __device__ bool look_back_step(const ScanArgs& a, Pending& p, int lane, bool blo
   }
 }
 
-// publishes the chunk's count; the warp that completes a group publishes the group's sum
+// publishes the chunk's count; the warp that completes a group publishes the group's sum.  One
+// 64-bit atomic carries both the arrival count (bits 40..) and the running sum (bits 0..39), so the
+// last arrival knows the group's total without re-reading anything: no fences.
 __device__ __forceinline__ void publish_count(const ScanArgs& a, int64_t chunk, unsigned cnt, int lane) {
-  const int64_t g = chunk >> 5;
-  const int64_t members = a.nchunks - (g << 5) < 32 ? a.nchunks - (g << 5) : 32;
-  unsigned old = 0;
   if (lane == 0) {
+    const int64_t g = chunk >> 5;
+    const int64_t members = a.nchunks - (g << 5) < 32 ? a.nchunks - (g << 5) : 32;
     st_status(&a.status[chunk], LB_AGG | cnt);
-    cgx_threadfence();  // the count is visible before the group counter moves
-    old = atomicAdd(&a.gcount[g], 1u);
-  }
-  old = __shfl_sync(FULL, old, 0);
-  if ((int64_t)old == members - 1) {
-    cgx_threadfence();
-    const int64_t idx = (g << 5) + lane;
-    const unsigned long long v = idx < a.nchunks ? ld_status(&a.status[idx]) : 0ull;
-    const unsigned sum = __reduce_add_sync(FULL, (unsigned)(v & 0xFFFFFFFFull));
-    // never overwrite a prefix a faster successor may already have published... it cannot have:
-    // a prefix for this group needs this very sum
-    if (lane == 0) st_status(&a.gstatus[g], LB_AGG | sum);
+    const unsigned long long old = atomicAdd(&a.gacc[g], (1ull << 40) | cnt);
+    if ((int64_t)(old >> 40) == members - 1)
+      st_status(&a.gstatus[g], LB_AGG | ((old & ((1ull << 40) - 1)) + cnt));
   }
 }
 
@@ -712,8 +704,12 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
     phase ^= 1u << b;
   };
 
+  // The next ticket is drawn one iteration (not one chunk) ahead: chunks are then processed in
+  // about ticket order, which is what keeps the look-back of a chunk from waiting on predecessors
+  // that are still queued behind somebody's current chunk.
+  const int64_t none = (int64_t)1 << 40;
   int64_t cur = take_ticket();
-  int64_t nxt = cur < a.nchunks ? (int64_t)take_ticket() : cur;
+  int64_t nxt = none;
   int kb = 0, sb = 0;
   Pending pend;
   if (cur < a.nchunks) issue(cur, 0, 0);
@@ -727,8 +723,12 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
     for (int it = 0; it < PAIRS; it++) {
       // the other window buffer was last read an iteration ago: refill it now
       __syncwarp();
-      if (it + 1 < PAIRS) issue(cur, it + 1, kb ^ 1);
-      else if (nxt < a.nchunks) issue(nxt, 0, kb ^ 1);
+      if (it + 1 < PAIRS) {
+        issue(cur, it + 1, kb ^ 1);
+      } else {
+        if (nxt == none) nxt = take_ticket();  // (a redo pass keeps the ticket it already holds)
+        if (nxt < a.nchunks) issue(nxt, 0, kb ^ 1);
+      }
       wait(kb);
       const int64_t wg = cbeg + (int64_t)it * (2 * STRIDE);
       if (wg < a.n) process_pair(a, em, ws.win[kb], wg, cnt, lane, rot, sel_lo, sel_hi);
@@ -744,13 +744,14 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
         a.total[1] = 1ull;
       }
     } else if (!direct) {
-      // the staging buffer of the pending chunk is needed next: finish it now if it still waits
+      // first tell everybody our count (nobody may ever wait on a warp that is itself waiting) ...
+      publish_count(a, cur, cnt, lane);
+      // ... then, because its staging buffer is needed next, finish the pending chunk if it still waits
       if (pend.chunk >= 0) {
         look_back_step(a, pend, lane, true);
         __syncwarp();
         finalize(a, ws, pend, lane);
       }
-      publish_count(a, cur, cnt, lane);
       pend.chunk = cur;
       pend.cnt = cnt;
       pend.sb = sb;
@@ -778,7 +779,7 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
     }
     direct = false;
     cur = nxt;
-    if (cur < a.nchunks) nxt = take_ticket();
+    nxt = none;
   }
   if (pend.chunk >= 0) {
     look_back_step(a, pend, lane, true);

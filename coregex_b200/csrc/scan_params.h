@@ -120,9 +120,9 @@ struct ScanArgs {
   unsigned int* ticket;        // chunk ticket counter (zeroed before launch)
   unsigned long long* status;  // nchunks look-back words (zeroed before launch)
   int64_t nchunks;
-  // bitstream kernel: one word and one arrival counter per group of 32 chunks (zeroed before launch)
+  // bitstream kernel: one word and one arrival accumulator per group of 32 chunks (zeroed before launch)
   unsigned long long* gstatus;
-  unsigned int* gcount;
+  unsigned long long* gacc;
 };
 
 }  // namespace cgx

@@ -48,7 +48,7 @@ int cgxsim_scan(const char* pat, size_t plen, const uint8_t* h, int64_t n, int64
   std::vector<unsigned long long> status((size_t)(nchunks > 0 ? nchunks : 1), 0ull);
   const size_t ngroups = (size_t)(nchunks + 31) / 32 + 1;
   std::vector<unsigned long long> gstatus(ngroups, 0ull);
-  std::vector<unsigned> gcount(ngroups, 0u);
+  std::vector<unsigned long long> gacc(ngroups, 0ull);
   unsigned long long scratch[8] = {0};
   ScanArgs a;
   memset(&a, 0, sizeof a);
@@ -78,7 +78,7 @@ int cgxsim_scan(const char* pat, size_t plen, const uint8_t* h, int64_t n, int64
   a.status = status.data();
   a.nchunks = nchunks;
   a.gstatus = gstatus.data();
-  a.gcount = gcount.data();
+  a.gacc = gacc.data();
   if (nchunks) sim_launch_scan_flat(a, grid);
   result[0] = scratch[0];
   result[1] = scratch[1];
