@@ -241,7 +241,7 @@ __device__ __forceinline__ uint64_t prefix_parity_excl(uint64_t x, int lane) {
 
 // ---- output ------------------------------------------------------------------------------------
 struct Emit {
-  const ScanArgs& a;
+  const ScanArgs* ap;
   uint16_t* stS;
   uint16_t* stE;
   int64_t cb;               // global position of the chunk's first byte
@@ -251,6 +251,7 @@ struct Emit {
 
   // rel = position relative to the chunk
   __device__ __forceinline__ void put(unsigned idx, int64_t rel, bool is_end) {
+    const ScanArgs& a = *ap;
     if (a.mode != M_FINDALL) return;
     if (direct) {
       const unsigned long long gi = goff + idx;
@@ -305,8 +306,10 @@ __device__ __noinline__ int64_t dfa_walk_global(const ScanArgs& a, int64_t p0) {
 // One lane replays the reference loop (meta/findall.go:176-290 over meta/find_indices.go:1050-1088)
 // from global position `from` until the candidate search meets a sync byte at or after `stop_min`
 // (or the end of input).  Returns the number of matches emitted from index idx0 on.  Cold path.
-__device__ __noinline__ unsigned serial_region(const ScanArgs& a, Emit& em, int64_t from, int64_t stop_min,
-                                               unsigned idx0, int lane) {
+// `em` travels by value and the result comes back packed (count | far << 31): a reference would
+// pin the caller's emitter and counters in local memory for the hot path too.
+__device__ __noinline__ unsigned serial_region_cold(const ScanArgs& a, Emit em, int64_t from, int64_t stop_min,
+                                                    unsigned idx0, int lane) {
   unsigned added = 0;
   bool far = false;
   if (lane == 0) {
@@ -341,9 +344,13 @@ __device__ __noinline__ unsigned serial_region(const ScanArgs& a, Emit& em, int6
     }
     far = em.far;
   }
-  added = __shfl_sync(FULL, added, 0);
-  em.far = __shfl_sync(FULL, (int)far, 0) != 0;
-  return added;
+  return __shfl_sync(FULL, added | (far ? 0x80000000u : 0u), 0);
+}
+__device__ __forceinline__ unsigned serial_region(const ScanArgs& a, Emit& em, int64_t from, int64_t stop_min,
+                                                  unsigned idx0, int lane) {
+  const unsigned r = serial_region_cold(a, em, from, stop_min, idx0, lane);
+  if (r >> 31) em.far = true;
+  return r & 0x7FFFFFFFu;
 }
 
 // ---- one iteration: two overlapping tiles ------------------------------------------------------
@@ -560,37 +567,42 @@ struct Pending {
   int64_t chunk = -1;        // < 0: none
   unsigned cnt = 0;
   int sb = 0;                // staging buffer that holds its matches
-  int phase = 1;             // 1: own group, 2: earlier groups
-  int64_t look = 0;          // phase 2: nearest group word not consumed yet
+  bool have1 = false;        // counts of the earlier chunks of the own group are in `excl`
+  bool have2 = false;        // prefix at the start of the own group is in `gpre`
+  bool loaded = false;       // v1/v2 hold status words requested by lb_issue
+  int64_t look = 0;          // nearest group word not consumed yet
   unsigned long long excl = 0;
-  unsigned long long gpre = 0;  // phase 2 sum: prefix at the start of the chunk's group
+  unsigned long long gpre = 0;
+  unsigned long long v1 = 0, v2 = 0;  // per lane
 };
 
-// Advances the look-back of p.  Returns true once p.excl is the exclusive prefix of p.chunk.
-// block == false: returns false instead of waiting for a word that has not been published yet.
-__device__ bool look_back_step(const ScanArgs& a, Pending& p, int lane, bool block) {
+// Requests the status words the next lb_consume needs.  Issued BEFORE an iteration's work and
+// consumed after it, so that the L2 round trip of these loads is never waited for.
+__device__ __forceinline__ void lb_issue(const ScanArgs& a, Pending& p, int lane) {
   const int64_t g = p.chunk >> 5;
-  if (p.phase == 1) {
+  p.v1 = LB_AGG;  // lanes at or beyond the chunk contribute nothing
+  p.v2 = LB_PREFIX;  // positions before group 0 act as a zero prefix
+  if (!p.have1) {
     const int64_t idx = (g << 5) + lane;
-    for (;;) {
-      unsigned long long v = LB_AGG;  // lanes at or beyond the chunk contribute nothing
-      if (idx < p.chunk) v = ld_status(&a.status[idx]);
-      if (__all_sync(FULL, (v >> 62) != 0)) {
-        p.excl = __reduce_add_sync(FULL, (unsigned)(v & 0xFFFFFFFFull));
-        break;
-      }
-      if (!block) return false;
-      cgx_spin_yield();
-    }
-    if (g == 0) return true;
-    p.phase = 2;
-    p.look = g - 1;
-    p.gpre = 0;
+    if (idx < p.chunk) p.v1 = ld_status(&a.status[idx]);
   }
-  for (;;) {
+  if (!p.have2) {
     const int64_t idx = p.look - lane;
-    unsigned long long v = LB_PREFIX;  // positions before group 0 act as a zero prefix
-    if (idx >= 0) v = ld_status(&a.gstatus[idx]);
+    if (idx >= 0) p.v2 = ld_status(&a.gstatus[idx]);
+  }
+  p.loaded = true;
+}
+
+// Uses the words of the last lb_issue.  Returns true once p.excl + p.gpre is the exclusive prefix.
+__device__ __forceinline__ bool lb_consume(const ScanArgs& a, Pending& p, int lane) {
+  const int64_t g = p.chunk >> 5;
+  p.loaded = false;
+  if (!p.have1 && __all_sync(FULL, (p.v1 >> 62) != 0)) {
+    p.excl = __reduce_add_sync(FULL, (unsigned)(p.v1 & 0xFFFFFFFFull));
+    p.have1 = true;
+  }
+  if (!p.have2) {
+    const unsigned long long v = p.v2;
     const uint32_t empty = __ballot_sync(FULL, (v >> 62) == 0);
     const uint32_t pm = __ballot_sync(FULL, (v >> 62) == 2);
     const int fe = empty ? __ffs((int)empty) - 1 : 32;
@@ -600,19 +612,37 @@ __device__ bool look_back_step(const ScanArgs& a, Pending& p, int lane, bool blo
       const unsigned part = __reduce_add_sync(FULL, lane < fp ? (unsigned)(v & 0xFFFFFFFFull) : 0u);
       const unsigned long long pv = __shfl_sync(FULL, v & LB_VALUE, fp);
       p.gpre += part + pv;
-      p.excl += p.gpre;
+      p.have2 = true;
       // the inclusive prefix through the previous group, for everybody behind us
-      if (lane == 0 && (p.look != g - 1 || fp != 0)) st_status(&a.gstatus[g - 1], LB_PREFIX | p.gpre);
-      return true;
-    }
-    const unsigned part = __reduce_add_sync(FULL, lane < fe ? (unsigned)(v & 0xFFFFFFFFull) : 0u);
-    p.gpre += part;
-    p.look -= fe;
-    if (fe < 32) {
-      if (!block) return false;
-      cgx_spin_yield();
+      if (lane == 0 && g > 0 && (p.look != g - 1 || fp != 0)) st_status(&a.gstatus[g - 1], LB_PREFIX | p.gpre);
+    } else if (fe > 0) {
+      p.gpre += __reduce_add_sync(FULL, lane < fe ? (unsigned)(v & 0xFFFFFFFFull) : 0u);
+      p.look -= fe;
     }
   }
+  if (p.have1 && p.have2) {
+    p.excl += p.gpre;
+    return true;
+  }
+  return false;
+}
+
+// blocking form (chunk ends, overflow, kernel end)
+__device__ void lb_resolve(const ScanArgs& a, Pending& p, int lane) {
+  for (;;) {
+    if (!p.loaded) lb_issue(a, p, lane);
+    if (lb_consume(a, p, lane)) return;
+    cgx_spin_yield();
+  }
+}
+
+__device__ __forceinline__ void lb_begin(Pending& p, int64_t chunk, unsigned cnt, int sb) {
+  p.chunk = chunk;
+  p.cnt = cnt;
+  p.sb = sb;
+  p.have1 = p.have2 = p.loaded = false;
+  p.look = (chunk >> 5) - 1;
+  p.excl = p.gpre = 0;
 }
 
 // publishes the chunk's count; the warp that completes a group publishes the group's sum.  One
@@ -718,7 +748,7 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
   while (cur < a.nchunks) {
     // one pass over the chunk: staged (normal) or, after a staging overflow, with direct stores
     const int64_t cbeg = cur * (int64_t)CHUNKB;
-    Emit em{a, ws.stS[sb], ws.stE[sb], cbeg, goff, direct};
+    Emit em{&a, ws.stS[sb], ws.stE[sb], cbeg, goff, direct};
     unsigned cnt = 0;
     for (int it = 0; it < PAIRS; it++) {
       // the other window buffer was last read an iteration ago: refill it now
@@ -729,11 +759,12 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
         if (nxt == none) nxt = take_ticket();  // (a redo pass keeps the ticket it already holds)
         if (nxt < a.nchunks) issue(nxt, 0, kb ^ 1);
       }
+      if (pend.chunk >= 0) lb_issue(a, pend, lane);  // consumed after this iteration's work
       wait(kb);
       const int64_t wg = cbeg + (int64_t)it * (2 * STRIDE);
       if (wg < a.n) process_pair(a, em, ws.win[kb], wg, cnt, lane, rot, sel_lo, sel_hi);
       kb ^= 1;
-      if (pend.chunk >= 0 && look_back_step(a, pend, lane, false)) {
+      if (pend.chunk >= 0 && lb_consume(a, pend, lane)) {
         __syncwarp();
         finalize(a, ws, pend, lane);
       }
@@ -748,20 +779,16 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
       publish_count(a, cur, cnt, lane);
       // ... then, because its staging buffer is needed next, finish the pending chunk if it still waits
       if (pend.chunk >= 0) {
-        look_back_step(a, pend, lane, true);
+        lb_resolve(a, pend, lane);
         __syncwarp();
         finalize(a, ws, pend, lane);
       }
-      pend.chunk = cur;
-      pend.cnt = cnt;
-      pend.sb = sb;
-      pend.phase = 1;
-      pend.excl = 0;
+      lb_begin(pend, cur, cnt, sb);
       __syncwarp();  // staged matches visible to the lanes that will store them
       if (cnt > (unsigned)CAP || __any_sync(FULL, em.far)) {
         // more matches than the staging buffer holds: get the offset now and run the chunk again
         // with direct stores.  The prefetch of the next chunk is dropped and re-issued later.
-        look_back_step(a, pend, lane, true);
+        lb_resolve(a, pend, lane);
         if (lane == 0) {
           atomicAdd(&a.total[3], 1ull);  // diagnostics: chunks redone with direct stores
           if (cur == a.nchunks - 1) a.total[0] = pend.excl + cnt;
@@ -775,14 +802,13 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
         continue;
       }
       sb ^= 1;
-      if (look_back_step(a, pend, lane, false)) finalize(a, ws, pend, lane);
     }
     direct = false;
     cur = nxt;
     nxt = none;
   }
   if (pend.chunk >= 0) {
-    look_back_step(a, pend, lane, true);
+    lb_resolve(a, pend, lane);
     finalize(a, ws, pend, lane);
   }
 }
