@@ -734,12 +734,14 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
     phase ^= 1u << b;
   };
 
-  // The next ticket is drawn one iteration (not one chunk) ahead: chunks are then processed in
-  // about ticket order, which is what keeps the look-back of a chunk from waiting on predecessors
-  // that are still queued behind somebody's current chunk.
+  // Rule that keeps the look-back free of convoys: a warp only ever WAITS (lb_resolve) while it
+  // holds no ticket it has not finished — every ticket anybody holds is being scanned, so every
+  // count a waiter needs arrives within one chunk time.  Hence the next ticket is drawn early (for
+  // the prefetch of its first window) only when nothing is pending that could make us wait.
   const int64_t none = (int64_t)1 << 40;
   int64_t cur = take_ticket();
   int64_t nxt = none;
+  bool prefetched = false;  // window 0 of `nxt` is in flight into the buffer the next chunk starts with
   int kb = 0, sb = 0;
   Pending pend;
   if (cur < a.nchunks) issue(cur, 0, 0);
@@ -756,8 +758,11 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
       if (it + 1 < PAIRS) {
         issue(cur, it + 1, kb ^ 1);
       } else {
-        if (nxt == none) nxt = take_ticket();  // (a redo pass keeps the ticket it already holds)
-        if (nxt < a.nchunks) issue(nxt, 0, kb ^ 1);
+        if (nxt == none && ((pend.chunk < 0 && cnt <= (unsigned)CAP) || a.mode != M_FINDALL)) nxt = take_ticket();
+        if (nxt != none && nxt < a.nchunks) {
+          issue(nxt, 0, kb ^ 1);
+          prefetched = true;
+        }
       }
       if (pend.chunk >= 0) lb_issue(a, pend, lane);  // consumed after this iteration's work
       wait(kb);
@@ -775,9 +780,10 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
         a.total[1] = 1ull;
       }
     } else if (!direct) {
-      // first tell everybody our count (nobody may ever wait on a warp that is itself waiting) ...
+      // first tell everybody our count ...
       publish_count(a, cur, cnt, lane);
-      // ... then, because its staging buffer is needed next, finish the pending chunk if it still waits
+      // ... then, because its staging buffer is needed next, finish the pending chunk if it still
+      // waits (we hold no unfinished ticket here: `nxt` was not drawn while something was pending)
       if (pend.chunk >= 0) {
         lb_resolve(a, pend, lane);
         __syncwarp();
@@ -787,7 +793,7 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
       __syncwarp();  // staged matches visible to the lanes that will store them
       if (cnt > (unsigned)CAP || __any_sync(FULL, em.far)) {
         // more matches than the staging buffer holds: get the offset now and run the chunk again
-        // with direct stores.  The prefetch of the next chunk is dropped and re-issued later.
+        // with direct stores.  A prefetched window of the next chunk is dropped and re-issued later.
         lb_resolve(a, pend, lane);
         if (lane == 0) {
           atomicAdd(&a.total[3], 1ull);  // diagnostics: chunks redone with direct stores
@@ -796,7 +802,8 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
         pend.chunk = -1;
         direct = true;
         goff = pend.excl;
-        if (nxt < a.nchunks) wait(kb);
+        if (prefetched) wait(kb);
+        prefetched = false;
         __syncwarp();
         issue(cur, 0, kb);
         continue;
@@ -804,6 +811,12 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
       sb ^= 1;
     }
     direct = false;
+    if (nxt == none) nxt = take_ticket();
+    if (!prefetched && nxt < a.nchunks) {
+      __syncwarp();
+      issue(nxt, 0, kb);
+    }
+    prefetched = false;
     cur = nxt;
     nxt = none;
   }
