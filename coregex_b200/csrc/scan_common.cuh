@@ -18,6 +18,10 @@ namespace cgx {
 #ifndef CGX_CPU_SIM
 __device__ __forceinline__ void cgx_spin_yield() {}
 __device__ __forceinline__ void cgx_threadfence() { __threadfence(); }
+__device__ __forceinline__ void cgx_fence_block() { __threadfence_block(); }
+__device__ __forceinline__ void cgx_syncthreads() { __syncthreads(); }
+// polite spin: the waiting warp leaves the issue slots to the warps that do the work
+__device__ __forceinline__ void cgx_backoff() { __nanosleep(100); }
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS: UBLKCP) -----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

@@ -36,8 +36,9 @@ namespace cgx {
 namespace {
 
 constexpr uint32_t FULL = 0xffffffffu;
-constexpr int FW_WARPS = 4;
-constexpr int FW_THREADS = FW_WARPS * 32;
+constexpr int FW_WARPS = 7;                    // scanning warps per CTA (8 warps: a multiple of the 4 SM sub-partitions)
+constexpr int FW_THREADS = (FW_WARPS + 1) * 32;  // + one resolver warp (look-back and ordered output)
+constexpr int FW_CTAS = 3;                     // resident CTAs per SM the kernel is built for
 constexpr int TILE = 2048;              // window bytes of one tile (64 per lane)
 constexpr int STRIDE = 1984;            // bytes between tile origins (31 pieces)
 constexpr int TPC = 8;                  // tiles per chunk
@@ -65,6 +66,17 @@ struct WarpSmem {
   uint16_t stS[2][CAP];
   uint16_t stE[2][CAP];
   uint64_t mbar[2];
+};
+// a scanned chunk handed from a scanning warp to the CTA's resolver warp (one slot per staging buffer)
+struct Mail {
+  volatile int state;  // 0 = slot and staging buffer free, 1 = chunk waits for its offset
+  unsigned cnt;
+  int64_t chunk;
+};
+struct CtaSmem {
+  WarpSmem w[FW_WARPS];
+  Mail mail[FW_WARPS][2];
+  volatile int done[FW_WARPS];
 };
 
 __device__ __forceinline__ uint64_t mk64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
@@ -556,93 +568,53 @@ __device__ __forceinline__ void process_pair(const ScanArgs& a, Emit& em, const 
   finish_tile(a, em, tb, wg + STRIDE, totSb, totEb, exSb, exEb, badb, cnt, lane);
 }
 
-// ---- resumable two-level look-back ------------------------------------------------------------------
+// ---- two-level look-back ------------------------------------------------------------------------------
 // Chunk c publishes its match count in status[c] (flag LB_AGG).  Chunks form groups of 32; the
 // warp that finishes a group's last chunk publishes the group's sum in gstatus[g] (LB_AGG), and
 // whoever learns the prefix at a group's start publishes it as gstatus[g-1] (LB_PREFIX, the
 // inclusive prefix through group g-1).  The exclusive prefix of chunk c is therefore: counts of the
 // earlier chunks of its own group (one 32-wide load) + a decoupled look-back over GROUP words
 // (32 groups = 1024 chunks per step), instead of a walk over the ~3000 chunks that are in flight.
-struct Pending {
-  int64_t chunk = -1;        // < 0: none
-  unsigned cnt = 0;
-  int sb = 0;                // staging buffer that holds its matches
-  bool have1 = false;        // counts of the earlier chunks of the own group are in `excl`
-  bool have2 = false;        // prefix at the start of the own group is in `gpre`
-  bool loaded = false;       // v1/v2 hold status words requested by lb_issue
-  int64_t look = 0;          // nearest group word not consumed yet
-  unsigned long long excl = 0;
-  unsigned long long gpre = 0;
-  unsigned long long v1 = 0, v2 = 0;  // per lane
-};
-
-// Requests the status words the next lb_consume needs.  Issued BEFORE an iteration's work and
-// consumed after it, so that the L2 round trip of these loads is never waited for.
-__device__ __forceinline__ void lb_issue(const ScanArgs& a, Pending& p, int lane) {
-  const int64_t g = p.chunk >> 5;
-  p.v1 = LB_AGG;  // lanes at or beyond the chunk contribute nothing
-  p.v2 = LB_PREFIX;  // positions before group 0 act as a zero prefix
-  if (!p.have1) {
-    const int64_t idx = (g << 5) + lane;
-    if (idx < p.chunk) p.v1 = ld_status(&a.status[idx]);
-  }
-  if (!p.have2) {
-    const int64_t idx = p.look - lane;
-    if (idx >= 0) p.v2 = ld_status(&a.gstatus[idx]);
-  }
-  p.loaded = true;
-}
-
-// Uses the words of the last lb_issue.  Returns true once p.excl + p.gpre is the exclusive prefix.
-__device__ __forceinline__ bool lb_consume(const ScanArgs& a, Pending& p, int lane) {
-  const int64_t g = p.chunk >> 5;
-  p.loaded = false;
-  if (!p.have1 && __all_sync(FULL, (p.v1 >> 62) != 0)) {
-    p.excl = __reduce_add_sync(FULL, (unsigned)(p.v1 & 0xFFFFFFFFull));
-    p.have1 = true;
-  }
-  if (!p.have2) {
-    const unsigned long long v = p.v2;
-    const uint32_t empty = __ballot_sync(FULL, (v >> 62) == 0);
-    const uint32_t pm = __ballot_sync(FULL, (v >> 62) == 2);
-    const int fe = empty ? __ffs((int)empty) - 1 : 32;
-    const int fp = pm ? __ffs((int)pm) - 1 : 32;
-    if (fp < fe) {
-      // sums of the groups before the prefix, then the prefix itself
-      const unsigned part = __reduce_add_sync(FULL, lane < fp ? (unsigned)(v & 0xFFFFFFFFull) : 0u);
-      const unsigned long long pv = __shfl_sync(FULL, v & LB_VALUE, fp);
-      p.gpre += part + pv;
-      p.have2 = true;
-      // the inclusive prefix through the previous group, for everybody behind us
-      if (lane == 0 && g > 0 && (p.look != g - 1 || fp != 0)) st_status(&a.gstatus[g - 1], LB_PREFIX | p.gpre);
-    } else if (fe > 0) {
-      p.gpre += __reduce_add_sync(FULL, lane < fe ? (unsigned)(v & 0xFFFFFFFFull) : 0u);
-      p.look -= fe;
-    }
-  }
-  if (p.have1 && p.have2) {
-    p.excl += p.gpre;
-    return true;
-  }
-  return false;
-}
-
-// blocking form (chunk ends, overflow, kernel end)
-__device__ void lb_resolve(const ScanArgs& a, Pending& p, int lane) {
+// Waiting is done by the CTA's resolver warp (and by a scanning warp only for a chunk that
+// overflowed its staging buffer); scanning warps publish their count and move on.
+__device__ unsigned long long lb_resolve(const ScanArgs& a, int64_t chunk, int lane) {
+  const int64_t g = chunk >> 5;
+  const int64_t idx1 = (g << 5) + lane;
+  unsigned long long excl = 0, gpre = 0;
+  bool have1 = false, have2 = g == 0;
+  int64_t look = g - 1;
   for (;;) {
-    if (!p.loaded) lb_issue(a, p, lane);
-    if (lb_consume(a, p, lane)) return;
-    cgx_spin_yield();
+    // both levels are requested before either is looked at: one L2 round trip per attempt
+    unsigned long long v1 = LB_AGG;     // lanes at or beyond the chunk contribute nothing
+    unsigned long long v = LB_PREFIX;   // positions before group 0 act as a zero prefix
+    if (!have1 && idx1 < chunk) v1 = ld_status(&a.status[idx1]);
+    const int64_t idx2 = look - lane;
+    if (!have2 && idx2 >= 0) v = ld_status(&a.gstatus[idx2]);
+    if (!have1 && __all_sync(FULL, (v1 >> 62) != 0)) {
+      excl = __reduce_add_sync(FULL, (unsigned)(v1 & 0xFFFFFFFFull));
+      have1 = true;
+    }
+    if (!have2) {
+      const uint32_t empty = __ballot_sync(FULL, (v >> 62) == 0);
+      const uint32_t pm = __ballot_sync(FULL, (v >> 62) == 2);
+      const int fe = empty ? __ffs((int)empty) - 1 : 32;
+      const int fp = pm ? __ffs((int)pm) - 1 : 32;
+      if (fp < fe) {
+        // sums of the groups before the prefix, then the prefix itself
+        const unsigned part = __reduce_add_sync(FULL, lane < fp ? (unsigned)(v & 0xFFFFFFFFull) : 0u);
+        gpre += part + __shfl_sync(FULL, v & LB_VALUE, fp);
+        have2 = true;
+        // the inclusive prefix through the previous group, for everybody behind us
+        if (lane == 0 && (look != g - 1 || fp != 0)) st_status(&a.gstatus[g - 1], LB_PREFIX | gpre);
+      } else if (fe > 0) {
+        gpre += __reduce_add_sync(FULL, lane < fe ? (unsigned)(v & 0xFFFFFFFFull) : 0u);
+        look -= fe;
+        if (fe == 32) continue;  // a full window of sums: keep walking without a pause
+      }
+    }
+    if (have1 && have2) return excl + gpre;
+    cgx_backoff();
   }
-}
-
-__device__ __forceinline__ void lb_begin(Pending& p, int64_t chunk, unsigned cnt, int sb) {
-  p.chunk = chunk;
-  p.cnt = cnt;
-  p.sb = sb;
-  p.have1 = p.have2 = p.loaded = false;
-  p.look = (chunk >> 5) - 1;
-  p.excl = p.gpre = 0;
 }
 
 // publishes the chunk's count; the warp that completes a group publishes the group's sum.  One
@@ -660,36 +632,82 @@ __device__ __forceinline__ void publish_count(const ScanArgs& a, int64_t chunk, 
 }
 
 // stores the staged matches of a resolved chunk in global match order
-__device__ __forceinline__ void finalize(const ScanArgs& a, WarpSmem& ws, Pending& p, int lane) {
-  if (lane == 0 && p.chunk == a.nchunks - 1) a.total[0] = p.excl + p.cnt;
-  const int64_t b = p.chunk * (int64_t)CHUNKB + a.base;
-  const uint16_t* ss = ws.stS[p.sb];
-  const uint16_t* se = ws.stE[p.sb];
-  for (unsigned i = lane; i < p.cnt; i += 32) {
-    const unsigned long long gi = p.excl + i;
+__device__ __forceinline__ void write_out(const ScanArgs& a, const WarpSmem& ws, int sb, int64_t chunk, unsigned cnt,
+                                          unsigned long long excl, int lane) {
+  if (lane == 0 && chunk == a.nchunks - 1) a.total[0] = excl + cnt;
+  const int64_t b = chunk * (int64_t)CHUNKB + a.base;
+  const uint16_t* ss = ws.stS[sb];
+  const uint16_t* se = ws.stE[sb];
+  for (unsigned i = lane; i < cnt; i += 32) {
+    const unsigned long long gi = excl + i;
     if ((int64_t)gi < a.cap)
       *reinterpret_cast<longlong2*>(a.out + 2 * gi) = make_longlong2(b + ss[i], b + se[i]);
   }
-  p.chunk = -1;
+}
+
+// The resolver warp: takes the oldest handed-over chunk of its CTA (a younger one cannot resolve
+// before it: both need every earlier count), waits for its offset, stores its matches, frees the slot.
+__device__ void resolver_warp(const ScanArgs& a, CtaSmem& cs, int lane) {
+  for (;;) {
+    // lane l looks at slot l (warp l >> 1, buffer l & 1)
+    int64_t mine = (int64_t)1 << 62;
+    bool all_done = true;
+    if (lane < 2 * FW_WARPS) {
+      const Mail& m = cs.mail[lane >> 1][lane & 1];
+      all_done = cs.done[lane >> 1] != 0;  // read BEFORE the slot: a warp hands over, then sets done
+      cgx_fence_block();
+      if (m.state == 1) mine = m.chunk;
+    }
+    int64_t best = mine;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      const int64_t o = __shfl_xor_sync(FULL, best, d);
+      best = o < best ? o : best;
+    }
+    if (best == ((int64_t)1 << 62)) {
+      if (__all_sync(FULL, all_done)) return;
+      cgx_backoff();
+      continue;
+    }
+    const int slot = __ffs((int)__ballot_sync(FULL, mine == best)) - 1;
+    cgx_fence_block();
+    const unsigned cnt = cs.mail[slot >> 1][slot & 1].cnt;
+    const unsigned long long excl = lb_resolve(a, best, lane);
+    write_out(a, cs.w[slot >> 1], slot & 1, best, cnt, excl, lane);
+    __syncwarp();
+    if (lane == 0) {
+      cgx_fence_block();
+      cs.mail[slot >> 1][slot & 1].state = 0;
+    }
+  }
 }
 
 }  // namespace
 
 #ifdef CGX_JIT
-extern "C" __global__ void __launch_bounds__(FW_THREADS, 5) cgx_flat_jit(const __grid_constant__ ScanArgs a) {
+extern "C" __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) cgx_flat_jit(const __grid_constant__ ScanArgs a) {
 #else
 namespace {
-__global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_constant__ ScanArgs a) {
+__global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __grid_constant__ ScanArgs a) {
 #endif
   CGX_DYN_SMEM(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
-  if (lane == 0) {
-    mbar_init(&ws.mbar[0], 1);
-    mbar_init(&ws.mbar[1], 1);
+  CtaSmem& cs = *reinterpret_cast<CtaSmem*>(smem_raw);
+  if (tid < 2 * FW_WARPS) {
+    cs.mail[tid >> 1][tid & 1].state = 0;
+    cs.done[tid >> 1] = 0;
+  }
+  if (warp < FW_WARPS && lane == 0) {
+    mbar_init(&cs.w[warp].mbar[0], 1);
+    mbar_init(&cs.w[warp].mbar[1], 1);
     fence_mbar_init();
   }
-  __syncwarp();
+  cgx_syncthreads();
+  if (warp == FW_WARPS) {
+    if (a.mode == M_FINDALL) resolver_warp(a, cs, lane);
+    return;
+  }
+  WarpSmem& ws = cs.w[warp];
 
   // lane-constant addressing of the rotated quarter loads (see classify_piece); tile B starts 31
   // pieces later: its piece parity is flipped, which keeps the same rotation conflict free
@@ -733,17 +751,23 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
     mbar_wait(&ws.mbar[b], (phase >> b) & 1u);
     phase ^= 1u << b;
   };
+  // is staging buffer b free (its previous chunk stored by the resolver)?
+  auto stage_free = [&](int b) -> bool {
+    int st = 0;
+    if (lane == 0) st = cs.mail[warp][b].state;
+    return __shfl_sync(FULL, st, 0) == 0;
+  };
 
-  // Rule that keeps the look-back free of convoys: a warp only ever WAITS (lb_resolve) while it
-  // holds no ticket it has not finished — every ticket anybody holds is being scanned, so every
-  // count a waiter needs arrives within one chunk time.  Hence the next ticket is drawn early (for
-  // the prefetch of its first window) only when nothing is pending that could make us wait.
+  // Rule that keeps the look-back free of convoys: a warp only ever WAITS (for a staging buffer,
+  // or for the offset of an overflowed chunk) while it holds no ticket it has not finished — every
+  // ticket anybody holds is being scanned, so every count a waiter needs arrives within one chunk
+  // time.  Hence the next ticket is drawn early (for the prefetch of its first window) only when
+  // the staging buffer it will need is already free.
   const int64_t none = (int64_t)1 << 40;
   int64_t cur = take_ticket();
   int64_t nxt = none;
   bool prefetched = false;  // window 0 of `nxt` is in flight into the buffer the next chunk starts with
   int kb = 0, sb = 0;
-  Pending pend;
   if (cur < a.nchunks) issue(cur, 0, 0);
   bool direct = false;
   unsigned long long goff = 0;
@@ -758,21 +782,18 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
       if (it + 1 < PAIRS) {
         issue(cur, it + 1, kb ^ 1);
       } else {
-        if (nxt == none && ((pend.chunk < 0 && cnt <= (unsigned)CAP) || a.mode != M_FINDALL)) nxt = take_ticket();
+        if (nxt == none &&
+            (a.mode != M_FINDALL || direct || (cnt <= (unsigned)CAP && stage_free(sb ^ 1))))
+          nxt = take_ticket();
         if (nxt != none && nxt < a.nchunks) {
           issue(nxt, 0, kb ^ 1);
           prefetched = true;
         }
       }
-      if (pend.chunk >= 0) lb_issue(a, pend, lane);  // consumed after this iteration's work
       wait(kb);
       const int64_t wg = cbeg + (int64_t)it * (2 * STRIDE);
       if (wg < a.n) process_pair(a, em, ws.win[kb], wg, cnt, lane, rot, sel_lo, sel_hi);
       kb ^= 1;
-      if (pend.chunk >= 0 && lb_consume(a, pend, lane)) {
-        __syncwarp();
-        finalize(a, ws, pend, lane);
-      }
     }
     if (a.mode != M_FINDALL) {
       if (cnt && lane == 0) {
@@ -780,35 +801,33 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
         a.total[1] = 1ull;
       }
     } else if (!direct) {
-      // first tell everybody our count ...
-      publish_count(a, cur, cnt, lane);
-      // ... then, because its staging buffer is needed next, finish the pending chunk if it still
-      // waits (we hold no unfinished ticket here: `nxt` was not drawn while something was pending)
-      if (pend.chunk >= 0) {
-        lb_resolve(a, pend, lane);
-        __syncwarp();
-        finalize(a, ws, pend, lane);
-      }
-      lb_begin(pend, cur, cnt, sb);
-      __syncwarp();  // staged matches visible to the lanes that will store them
+      publish_count(a, cur, cnt, lane);  // everybody behind us can go on
       if (cnt > (unsigned)CAP || __any_sync(FULL, em.far)) {
         // more matches than the staging buffer holds: get the offset now and run the chunk again
         // with direct stores.  A prefetched window of the next chunk is dropped and re-issued later.
-        lb_resolve(a, pend, lane);
+        goff = lb_resolve(a, cur, lane);
         if (lane == 0) {
           atomicAdd(&a.total[3], 1ull);  // diagnostics: chunks redone with direct stores
-          if (cur == a.nchunks - 1) a.total[0] = pend.excl + cnt;
+          if (cur == a.nchunks - 1) a.total[0] = goff + cnt;
         }
-        pend.chunk = -1;
         direct = true;
-        goff = pend.excl;
         if (prefetched) wait(kb);
         prefetched = false;
         __syncwarp();
         issue(cur, 0, kb);
         continue;
       }
+      // hand the chunk to the resolver warp
+      __syncwarp();  // staged matches written
+      if (lane == 0) {
+        Mail& m = cs.mail[warp][sb];
+        m.chunk = cur;
+        m.cnt = cnt;
+        cgx_fence_block();
+        m.state = 1;
+      }
       sb ^= 1;
+      while (!stage_free(sb)) cgx_backoff();  // (no unfinished ticket is held here unless the buffer was free)
     }
     direct = false;
     if (nxt == none) nxt = take_ticket();
@@ -820,9 +839,10 @@ __global__ void __launch_bounds__(FW_THREADS, 5) scan_flat_kernel(const __grid_c
     cur = nxt;
     nxt = none;
   }
-  if (pend.chunk >= 0) {
-    lb_resolve(a, pend, lane);
-    finalize(a, ws, pend, lane);
+  __syncwarp();
+  if (lane == 0) {
+    cgx_fence_block();
+    cs.done[warp] = 1;
   }
 }
 #ifndef CGX_JIT
@@ -836,23 +856,23 @@ int64_t scan_flat_chunks(int64_t n) {
   return (tiles + TPC - 1) / TPC;
 }
 
-size_t scan_flat_smem_bytes() { return sizeof(WarpSmem) * FW_WARPS; }
+size_t scan_flat_smem_bytes() { return sizeof(CtaSmem); }
 int scan_flat_threads() { return FW_THREADS; }
 int scan_flat_warps() { return FW_WARPS; }
 
 #ifdef CGX_CPU_SIM
 void sim_launch_scan_flat(const ScanArgs& a, unsigned grid) {
 #ifdef CGX_JIT
-  sim::launch<ScanArgs>(cgx_flat_jit, grid, FW_THREADS, sizeof(WarpSmem) * FW_WARPS, a);
+  sim::launch<ScanArgs>(cgx_flat_jit, grid, FW_THREADS, sizeof(CtaSmem), a);
 #else
-  sim::launch<ScanArgs>(scan_flat_kernel, grid, FW_THREADS, sizeof(WarpSmem) * FW_WARPS, a);
+  sim::launch<ScanArgs>(scan_flat_kernel, grid, FW_THREADS, sizeof(CtaSmem), a);
 #endif
 }
 #else
 // Launches the scan on `stream`.  ticket/status/total must be zeroed by the caller.
 cudaError_t launch_scan_flat(const ScanArgs& a, int sm_count, cudaStream_t stream) {
   if (a.nchunks == 0) return cudaSuccess;
-  const size_t smem = sizeof(WarpSmem) * FW_WARPS;
+  const size_t smem = sizeof(CtaSmem);
   static bool configured = false;
   static int per_sm = 0;
   if (!configured) {

@@ -39,7 +39,12 @@ struct WarpState {
   int left[2] = {0, 0};
 };
 
+struct BlockState {
+  unsigned arrived = 0, gen = 0;
+};
+
 struct Fiber {
+  BlockState* block = nullptr;
   ucontext_t ctx;
   std::vector<unsigned char> stack;
   Dim3 tid, bid, bdim, gdim;
@@ -232,6 +237,19 @@ inline longlong2 make_longlong2(long long x, long long y) { return longlong2{x, 
 namespace cgx {
 inline void cgx_spin_yield() { sim::yield(); }
 inline void cgx_threadfence() {}
+inline void cgx_fence_block() {}
+inline void cgx_backoff() { sim::yield(); }
+inline void cgx_syncthreads() {
+  sim::Fiber* f = sim::cur();
+  sim::BlockState* b = f->block;
+  const unsigned gen = b->gen;
+  if (++b->arrived == f->bdim.x) {
+    b->arrived = 0;
+    b->gen++;
+  } else {
+    while (b->gen == gen) sim::yield();
+  }
+}
 // mbarrier model: the word counts completed phases
 inline void mbar_init(uint64_t* bar, unsigned) { *bar = 0; }
 inline void fence_mbar_init() {}
@@ -289,6 +307,7 @@ void launch(void (*kernel)(Args), unsigned grid, unsigned block, size_t smem, co
   Tramp<Args> tr{kernel, &args};
   std::vector<std::vector<unsigned char>> smems(grid);
   std::vector<WarpState> warps((size_t)grid * (block / 32));
+  std::vector<BlockState> blocks(grid);
   std::vector<Fiber> fibers((size_t)grid * block);
   for (unsigned b = 0; b < grid; b++) {
     smems[b].assign(smem + 256, 0xCD);
@@ -302,6 +321,7 @@ void launch(void (*kernel)(Args), unsigned grid, unsigned block, size_t smem, co
       f.gdim.x = grid;
       f.lane = t & 31;
       f.warp = &warps[(size_t)b * (block / 32) + t / 32];
+      f.block = &blocks[b];
       f.smem = base;
       f.stack.resize(256 * 1024);
       getcontext(&f.ctx);
