@@ -247,7 +247,7 @@ long cgx_debug_jit_compile(cgx_regex* re, char* cubin_out, size_t cap) {
   }
   std::vector<char> cubin;
   std::string err;
-  if (!JitCompileCubin(re->c->flat, cubin, err)) {
+  if (!JitCompileCubin(re->c->flat, JitTiles(), cubin, err)) {
     g_last_error = err;
     return -1;
   }

@@ -81,6 +81,7 @@ Nvrtc& nvrtc() {
 struct Driver {
   decltype(&cuModuleLoadData) load = nullptr;
   decltype(&cuModuleGetFunction) getfn = nullptr;
+  decltype(&cuModuleGetGlobal) getglobal = nullptr;
   decltype(&cuFuncSetAttribute) setattr = nullptr;
   decltype(&cuOccupancyMaxActiveBlocksPerMultiprocessor) occ = nullptr;
   decltype(&cuLaunchKernel) launch = nullptr;
@@ -98,6 +99,7 @@ Driver& driver() {
     };
     get("cuModuleLoadData", (void**)&d.load);
     get("cuModuleGetFunction", (void**)&d.getfn);
+    get("cuModuleGetGlobal", (void**)&d.getglobal);
     get("cuFuncSetAttribute", (void**)&d.setattr);
     get("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&d.occ);
     get("cuLaunchKernel", (void**)&d.launch);
@@ -111,11 +113,20 @@ std::map<std::pair<int, std::string>, JitKernel*> g_loaded;  // (device, header 
 
 }  // namespace
 
-bool JitCompileCubin(const FlatDev& f, std::vector<char>& cubin, std::string& err) {
+int JitTiles() {
+  static const int t = [] {
+    const char* e = getenv("CGX_TILES");
+    return e && (e[0] == '1' || e[0] == '2') ? e[0] - '0' : kJitTilesDefault;
+  }();
+  return t;
+}
+
+bool JitCompileCubin(const FlatDev& f, int tiles, std::vector<char>& cubin, std::string& err) {
   const std::string hdr = JitHeader(f);
+  const std::string key = hdr + (tiles == 1 ? "#1" : "#2");
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_cubins.find(hdr);
+    auto it = g_cubins.find(key);
     if (it != g_cubins.end()) {
       cubin = it->second;
       return true;
@@ -133,8 +144,9 @@ bool JitCompileCubin(const FlatDev& f, std::vector<char>& cubin, std::string& er
     err = "nvrtcCreateProgram failed";
     return false;
   }
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DCGX_JIT=1"};
-  const nvrtcResult rc = n.compile(prog, 4, opts);
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DCGX_JIT=1",
+                        tiles == 1 ? "-DCGX_TILES=1" : "-DCGX_TILES=2"};
+  const nvrtcResult rc = n.compile(prog, 5, opts);
   if (rc != NVRTC_SUCCESS) {
     size_t ls = 0;
     n.log_size(prog, &ls);
@@ -150,7 +162,7 @@ bool JitCompileCubin(const FlatDev& f, std::vector<char>& cubin, std::string& er
   n.cubin(prog, cubin.data());
   n.destroy(&prog);
   std::lock_guard<std::mutex> lk(g_mu);
-  g_cubins[hdr] = cubin;
+  g_cubins[key] = cubin;
   return true;
 }
 
@@ -168,14 +180,15 @@ const JitKernel* GetJitKernel(const FlatDev& f, std::string& err) {
     err = "cudaGetDevice failed";
     return nullptr;
   }
-  const std::string hdr = JitHeader(f);
+  const int tiles = JitTiles();
+  const std::string hdr = JitHeader(f) + (tiles == 1 ? "#1" : "#2");
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_loaded.find({dev, hdr});
     if (it != g_loaded.end()) return it->second;
   }
   std::vector<char> cubin;
-  if (!JitCompileCubin(f, cubin, err)) return nullptr;
+  if (!JitCompileCubin(f, tiles, cubin, err)) return nullptr;
   Driver& d = driver();
   if (!d.err.empty()) {
     err = d.err;
@@ -186,10 +199,18 @@ const JitKernel* GetJitKernel(const FlatDev& f, std::string& err) {
   CUfunction fn = nullptr;
   CUresult r = d.load(&mod, cubin.data());
   if (r == CUDA_SUCCESS) r = d.getfn(&fn, mod, "cgx_flat_jit");
-  const int smem = (int)scan_flat_smem_bytes();
+  // the module describes its own launch shape: {dynamic smem bytes, threads, scanning warps, CTAs/SM}
+  int info[4] = {0, 0, 0, 0};
+  CUdeviceptr ip = 0;
+  size_t isz = 0;
+  if (r == CUDA_SUCCESS) r = d.getglobal(&ip, &isz, mod, "cgx_flat_jit_info");
+  if (r == CUDA_SUCCESS && (isz != sizeof info ||
+                            cudaMemcpy(info, (const void*)ip, sizeof info, cudaMemcpyDeviceToHost) != cudaSuccess))
+    r = CUDA_ERROR_UNKNOWN;
+  const int smem = info[0];
   if (r == CUDA_SUCCESS) r = d.setattr(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
   int per_sm = 0;
-  if (r == CUDA_SUCCESS) r = d.occ(&per_sm, fn, scan_flat_threads(), (size_t)smem);
+  if (r == CUDA_SUCCESS) r = d.occ(&per_sm, fn, info[1], (size_t)smem);
   if (r != CUDA_SUCCESS || per_sm < 1) {
     char b[96];
     snprintf(b, sizeof b, "loading the JIT cubin failed (CUresult %d, %d blocks/SM)", (int)r, per_sm);
@@ -199,6 +220,10 @@ const JitKernel* GetJitKernel(const FlatDev& f, std::string& err) {
   JitKernel* k = new JitKernel();
   k->func = (void*)fn;
   k->per_sm = per_sm;
+  k->smem = smem;
+  k->threads = info[1];
+  k->warps = info[2];
+  k->tiles = tiles;
   std::lock_guard<std::mutex> lk(g_mu);
   g_loaded[{dev, hdr}] = k;
   return k;
@@ -208,11 +233,11 @@ cudaError_t launch_scan_flat_jit(const JitKernel* k, const ScanArgs& a, int sm_c
   if (a.nchunks == 0) return cudaSuccess;
   Driver& d = driver();
   int64_t grid = (int64_t)sm_count * k->per_sm;
-  const int64_t need = (a.nchunks + scan_flat_warps() - 1) / scan_flat_warps();
+  const int64_t need = (a.nchunks + k->warps - 1) / k->warps;
   if (grid > need) grid = need;
   void* params[] = {(void*)&a};
-  const CUresult r = d.launch((CUfunction)k->func, (unsigned)grid, 1, 1, (unsigned)scan_flat_threads(), 1, 1,
-                              (unsigned)scan_flat_smem_bytes(), (CUstream)stream, params, nullptr);
+  const CUresult r = d.launch((CUfunction)k->func, (unsigned)grid, 1, 1, (unsigned)k->threads, 1, 1,
+                              (unsigned)k->smem, (CUstream)stream, params, nullptr);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorLaunchFailure;
 }
 

@@ -12,10 +12,16 @@ namespace cgx {
 struct JitKernel {
   void* func = nullptr;  // CUfunction
   int per_sm = 0;        // resident CTAs per SM
+  int smem = 0, threads = 0, warps = 0;  // launch shape, read from the module (cgx_flat_jit_info)
+  int tiles = 0;         // tiles evaluated jointly per iteration (CGX_TILES)
 };
 
+// tiles per iteration the specialised kernel is built with: $CGX_TILES (1 or 2), default kJitTilesDefault
+constexpr int kJitTilesDefault = 2;
+int JitTiles();
+
 // NVRTC only: works without a device (used by the CPU test that the specialised source builds)
-bool JitCompileCubin(const FlatDev& f, std::vector<char>& cubin, std::string& err);
+bool JitCompileCubin(const FlatDev& f, int tiles, std::vector<char>& cubin, std::string& err);
 // compiled + loaded kernel for the current device, cached per program; nullptr (and err) when
 // NVRTC or the driver entry points are unavailable
 const JitKernel* GetJitKernel(const FlatDev& f, std::string& err);

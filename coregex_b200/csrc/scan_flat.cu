@@ -35,16 +35,26 @@ namespace cgx {
 
 namespace {
 
+#ifndef CGX_TILES
+#define CGX_TILES 2
+#endif
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int FW_WARPS = 7;                    // scanning warps per CTA (8 warps: a multiple of the 4 SM sub-partitions)
 constexpr int FW_THREADS = (FW_WARPS + 1) * 32;  // + one resolver warp (look-back and ordered output)
-constexpr int FW_CTAS = 3;                     // resident CTAs per SM the kernel is built for
+#if CGX_TILES == 1
+constexpr int FW_CTAS = 4;                     // resident CTAs per SM the kernel is built for (<= 64 registers)
+#else
+constexpr int FW_CTAS = 3;                     // (<= 80 registers)
+#endif
 constexpr int TILE = 2048;              // window bytes of one tile (64 per lane)
 constexpr int STRIDE = 1984;            // bytes between tile origins (31 pieces)
 constexpr int TPC = 8;                  // tiles per chunk
-constexpr int PAIRS = TPC / 2;          // iterations per chunk (two tiles each)
+// tiles evaluated jointly per iteration: 2 gives every warp two independent dependency chains
+// (fewer, fatter warps), 1 halves the hot loop's code and registers (more warps)
+constexpr int NT = CGX_TILES;
+constexpr int ITERS = TPC / NT;         // iterations per chunk
 constexpr int CHUNKB = TPC * STRIDE;    // 15872 bytes owned per chunk
-constexpr int SUPER = STRIDE + TILE;    // 4032 bytes loaded per iteration
+constexpr int SUPER = (NT - 1) * STRIDE + TILE;  // bytes loaded per iteration (4032 / 2048)
 constexpr int CAP = 256;                // staged matches per chunk
 
 // The pattern-dependent parts exist twice: as an interpreter over ScanArgs::flat (this translation
@@ -184,13 +194,15 @@ __device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* 
 
 // ---- marker passes -----------------------------------------------------------------------------
 // Right to left (reversed orientation): M = positions from which items k..end can match.
+// (tile B's operands are touched only when two tiles are evaluated jointly)
 template <int C>
 __device__ __forceinline__ void rev_step(uint32_t kind, const uint64_t (&ca)[4], const uint64_t (&cb)[4],
                                          uint64_t& Ma, uint64_t& Mb, int lane) {
   const uint64_t Ca = ca[C], Cb = cb[C];
   // unknown territory past the window is assumed to allow a match (bit entering lane 0 is 1)
   const uint64_t ua = shl1(Ma, lane, FULL) & Ca;
-  const uint64_t ub = shl1(Mb, lane, FULL) & Cb;
+  uint64_t ub = 0;
+  if (NT == 2) ub = shl1(Mb, lane, FULL) & Cb;
   if (kind == 0) {
     Ma = ua;
     Mb = ub;
@@ -201,9 +213,11 @@ __device__ __forceinline__ void rev_step(uint32_t kind, const uint64_t (&ca)[4],
     // extend through the run towards lower addresses; a second marker inside one run survives the
     // carry of the first as a 1 in the sum, so the markers themselves are OR-ed back
     const uint64_t pa = (~add2048(ua, Ca, lane) & Ca) | ua;
-    const uint64_t pb = (~add2048(ub, Cb, lane) & Cb) | ub;
     Ma = kind == 1 ? pa : (Ma | pa);
-    Mb = kind == 1 ? pb : (Mb | pb);
+    if (NT == 2) {
+      const uint64_t pb = (~add2048(ub, Cb, lane) & Cb) | ub;
+      Mb = kind == 1 ? pb : (Mb | pb);
+    }
   }
 }
 // Left to right (forward orientation): T = positions a marker stands at before item k; the forced
@@ -215,16 +229,18 @@ __device__ __forceinline__ void fwd_step(uint32_t kind, const uint64_t (&ca)[4],
   const uint64_t ia = Ta & Ca, ib = Tb & Cb;  // markers that can take a byte
   if (kind == 0) {
     Ta = shl1(ia, lane, 0u);
-    Tb = shl1(ib, lane, 0u);
+    if (NT == 2) Tb = shl1(ib, lane, 0u);
   } else if (kind == 3) {
     Ta = (Ta & ~Ca) | shl1(ia, lane, 0u);
-    Tb = (Tb & ~Cb) | shl1(ib, lane, 0u);
+    if (NT == 2) Tb = (Tb & ~Cb) | shl1(ib, lane, 0u);
   } else {
     // a marker inside a run of ones carries out to the first zero after the run
     const uint64_t ea = add2048(ia, Ca, lane) & ~Ca;
-    const uint64_t eb = add2048(ib, Cb, lane) & ~Cb;
     Ta = kind == 1 ? ea : ((Ta & ~Ca) | ea);
-    Tb = kind == 1 ? eb : ((Tb & ~Cb) | eb);
+    if (NT == 2) {
+      const uint64_t eb = add2048(ib, Cb, lane) & ~Cb;
+      Tb = kind == 1 ? eb : ((Tb & ~Cb) | eb);
+    }
   }
 }
 
@@ -273,18 +289,29 @@ struct Emit {
       else if (idx < (unsigned)CAP) (is_end ? stE : stS)[idx] = (uint16_t)rel;
     }
   }
-  // all set bits of one 32-bit half; most words hold zero or one
-  __device__ __forceinline__ unsigned put_bits32(uint32_t bits, unsigned idx, int rel0, bool is_end) {
+  // fast path of the fast path: staged FindAll output, offsets known to fit 16 bits
+  __device__ __forceinline__ unsigned stage_bits32(uint16_t* st, uint32_t bits, unsigned idx, int rel0) {
     while (bits) {
       const int b = __ffs((int)bits) - 1;
       bits &= bits - 1;
-      put(idx++, rel0 + b, is_end);
+      if (idx < (unsigned)CAP) st[idx] = (uint16_t)(rel0 + b);
+      idx++;
     }
     return idx;
   }
   __device__ __forceinline__ void put_bits(uint64_t bits, unsigned idx, int rel0, bool is_end) {
-    idx = put_bits32((uint32_t)bits, idx, rel0, is_end);
-    put_bits32((uint32_t)(bits >> 32), idx, rel0 + 32, is_end);
+    if (ap->mode != M_FINDALL) return;
+    if (!direct) {
+      uint16_t* st = is_end ? stE : stS;
+      idx = stage_bits32(st, (uint32_t)bits, idx, rel0);
+      stage_bits32(st, (uint32_t)(bits >> 32), idx, rel0 + 32);
+      return;
+    }
+    while (bits) {
+      const int b = __ffsll((long long)bits) - 1;
+      bits &= bits - 1;
+      put(idx++, rel0 + b, is_end);
+    }
   }
 };
 
@@ -386,24 +413,20 @@ __device__ __forceinline__ uint64_t range_mask(int lo, int hi, int lane) {
 __device__ __forceinline__ void ownership(uint64_t U, bool first_tile, int lane, TileOut& t) {
   const uint64_t nz = ~U;
   const uint32_t has = __ballot_sync(FULL, nz != 0ull);
-  const int firstsync = nz ? __ffsll((long long)nz) - 1 : 64;
-  const int lastsync = nz ? 63 - __clzll((long long)nz) : -1;
-  int a;
-  if (first_tile) {
-    a = 0;
-  } else if (!has) {
-    a = -1;
-  } else {
-    const int fl = __ffs((int)has) - 1;
-    a = 64 * fl + __shfl_sync(FULL, firstsync, fl) + 1;
+  // first sync byte of this lane's piece (64: none)
+  const uint32_t nlo = (uint32_t)nz, nhi = (uint32_t)(nz >> 32);
+  const int firstsync = nlo ? __ffs((int)nlo) - 1 : (nhi ? 31 + __ffs((int)nhi) : 64);
+  int a = 0;
+  if (!first_tile) {
+    const int fl = __ffs((int)has) - 1;  // -1 when the window has no sync byte: the shuffle wraps, a is unused
+    a = has ? 64 * fl + __shfl_sync(FULL, firstsync, fl & 31) + 1 : -1;
   }
   const int fs31 = __shfl_sync(FULL, firstsync, 31);
   t.a = a;
-  if (fs31 < 64) {
-    t.open = false;
-    t.lim = STRIDE + fs31 + 1;
-  } else {
-    t.open = true;
+  t.open = fs31 >= 64;
+  t.lim = STRIDE + fs31 + 1;
+  if (t.open) {
+    const int lastsync = nz ? 63 - __clzll((long long)nz) : -1;
     const int hl = has ? 31 - __clz((int)has) : 0;
     const int ls = __shfl_sync(FULL, lastsync, hl);
     const int z1 = has ? 64 * hl + ls + 1 : 0;
@@ -429,14 +452,14 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
   if (t.open) cnt += serial_region(a, em, tile_g + t.lim, stop_min, cnt, lane);
 }
 
-// Processes the two tiles whose windows start at `win` (global position wg) and win + STRIDE.
-__device__ __forceinline__ void process_pair(const ScanArgs& a, Emit& em, const uint8_t* win, int64_t wg,
-                                             unsigned& cnt, int lane, int rot, uint32_t sel_lo, uint32_t sel_hi) {
+// Processes the NT tiles whose windows start at `win` (global position wg), win + STRIDE.
+__device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const uint8_t* win, int64_t wg,
+                                              unsigned& cnt, int lane, int rot, uint32_t sel_lo, uint32_t sel_hi) {
   const FlatDev& f = a.flat;
   const int piece = 31 - lane;
-  uint64_t ca[4], cb[4];
+  uint64_t ca[4], cb[4] = {0ull, 0ull, 0ull, 0ull};
   classify_piece(f, win + piece * 64, rot, sel_lo, sel_hi, ca);
-  classify_piece(f, win + STRIDE + piece * 64, rot, sel_lo, sel_hi, cb);
+  if (NT == 2) classify_piece(f, win + STRIDE + piece * 64, rot, sel_lo, sel_hi, cb);
   // bytes at or beyond the end of input belong to no class
   const int64_t nv = a.n - wg;  // valid bytes from the start of tile A
   if (nv < SUPER) {
@@ -475,10 +498,13 @@ __device__ __forceinline__ void process_pair(const ScanArgs& a, Emit& em, const 
     // only the first byte of a run of class 0 (pattern opens with C+); the byte before the window
     // counts as outside the class: position 0 is owned only when it is the start of the input
     uint32_t upa = __shfl_down_sync(FULL, (uint32_t)ca[0], 1) & 1u;
-    uint32_t upb = __shfl_down_sync(FULL, (uint32_t)cb[0], 1) & 1u;
-    if (lane == 31) upa = upb = 0u;
+    if (lane == 31) upa = 0u;
     Ma &= ca[0] & ~((ca[0] >> 1) | ((uint64_t)upa << 63));
-    Mb &= cb[0] & ~((cb[0] >> 1) | ((uint64_t)upb << 63));
+    if (NT == 2) {
+      uint32_t upb = __shfl_down_sync(FULL, (uint32_t)cb[0], 1) & 1u;
+      if (lane == 31) upb = 0u;
+      Mb &= cb[0] & ~((cb[0] >> 1) | ((uint64_t)upb << 63));
+    }
   }
 
   // ---- forward orientation from here on ----
@@ -486,17 +512,22 @@ __device__ __forceinline__ void process_pair(const ScanArgs& a, Emit& em, const 
   for (int c = 0; c < 4; c++) {
     if (c < P_NCLASSES) {
       ca[c] = flip(ca[c]);
-      cb[c] = flip(cb[c]);
+      if (NT == 2) cb[c] = flip(cb[c]);
     }
   }
   TileOut ta, tb;
   ta.S = flip(Ma);
-  tb.S = flip(Mb);
-  const uint64_t Ua = ca[0] | ca[1] | ca[2] | ca[3], Ub = cb[0] | cb[1] | cb[2] | cb[3];
-  ownership(Ua, wg == 0, lane, ta);
-  ownership(Ub, false, lane, tb);
+  ownership(ca[0] | ca[1] | ca[2] | ca[3], wg == 0, lane, ta);
   ta.S &= ta.a < 0 ? 0ull : range_mask(ta.a, ta.lim, lane);
-  tb.S &= tb.a < 0 ? 0ull : range_mask(tb.a, tb.lim, lane);
+  tb.S = tb.E = 0ull;
+  tb.a = -1;
+  tb.lim = 0;
+  tb.open = false;
+  if (NT == 2) {
+    tb.S = flip(Mb);
+    ownership(cb[0] | cb[1] | cb[2] | cb[3], false, lane, tb);
+    tb.S &= tb.a < 0 ? 0ull : range_mask(tb.a, tb.lim, lane);
+  }
 
   const uint32_t anyS = __ballot_sync(FULL, (ta.S | tb.S) != 0ull);
   if (a.mode == M_ISMATCH) {
@@ -508,14 +539,15 @@ __device__ __forceinline__ void process_pair(const ScanArgs& a, Emit& em, const 
     }
     // open tails may still hide a match
     if (ta.a >= 0 && ta.open) cnt += serial_region(a, em, wg + ta.lim, wg + STRIDE, cnt, lane);
-    if (tb.a >= 0 && tb.open) cnt += serial_region(a, em, wg + STRIDE + tb.lim, wg + 2 * STRIDE, cnt, lane);
+    if (NT == 2 && tb.a >= 0 && tb.open)
+      cnt += serial_region(a, em, wg + STRIDE + tb.lim, wg + 2 * STRIDE, cnt, lane);
     if (cnt && lane == 0) a.total[1] = 1ull;
     return;
   }
 
   unsigned exSa = 0, exEa = 0, exSb = 0, exEb = 0, totSa = 0, totEa = 0, totSb = 0, totEb = 0;
   bool bad = false, badb = false;
-  ta.E = tb.E = 0ull;
+  ta.E = 0ull;
   if (anyS) {
     // ---- left to right: where do the matches end ----
     uint64_t Ta = ta.S, Tb = tb.S;
@@ -536,36 +568,42 @@ __device__ __forceinline__ void process_pair(const ScanArgs& a, Emit& em, const 
 
     // ---- starts and ends must alternate: S-only at even parity, anything with an end at odd ----
     const uint64_t pa = prefix_parity_excl(ta.S ^ ta.E, lane);
-    const uint64_t pb = prefix_parity_excl(tb.S ^ tb.E, lane);
-    uint64_t wa = (ta.S & ~ta.E & pa) | (ta.E & ~pa);
-    uint64_t wb = (tb.S & ~tb.E & pb) | (tb.E & ~pb);
-    if (P_MIDRUN) {
-      // an end in the middle of a class-0 run: the reference resumes there, which is no run start
-      wa |= ta.E & ca[0] & shl1(ca[0], lane, 0u);
-      wb |= tb.E & cb[0] & shl1(cb[0], lane, 0u);
+    uint64_t wa = (ta.S & ~ta.E & pa) | (ta.E & ~pa), wb = 0ull;
+    // (an end in the middle of a class-0 run: the reference resumes there, which is no run start)
+    if (P_MIDRUN) wa |= ta.E & ca[0] & shl1(ca[0], lane, 0u);
+    if (NT == 2) {
+      const uint64_t pb = prefix_parity_excl(tb.S ^ tb.E, lane);
+      wb = (tb.S & ~tb.E & pb) | (tb.E & ~pb);
+      if (P_MIDRUN) wb |= tb.E & cb[0] & shl1(cb[0], lane, 0u);
     }
     bad = __any_sync(FULL, wa != 0ull);
-    badb = __any_sync(FULL, wb != 0ull);
+    if (NT == 2) badb = __any_sync(FULL, wb != 0ull);
 
     // ---- counts and ranks (tile A's matches precede tile B's) ----
     uint32_t xa = __popcll(ta.S) | (__popcll(ta.E) << 16), xb = __popcll(tb.S) | (__popcll(tb.E) << 16);
     const uint32_t va = xa, vb = xb;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t ya = __shfl_up_sync(FULL, xa, d), yb = __shfl_up_sync(FULL, xb, d);
-      if (lane >= d) {
-        xa += ya;
-        xb += yb;
+      const uint32_t ya = __shfl_up_sync(FULL, xa, d);
+      if (lane >= d) xa += ya;
+      if (NT == 2) {
+        const uint32_t yb = __shfl_up_sync(FULL, xb, d);
+        if (lane >= d) xb += yb;
       }
     }
-    const uint32_t ta_tot = __shfl_sync(FULL, xa, 31), tb_tot = __shfl_sync(FULL, xb, 31);
+    const uint32_t ta_tot = __shfl_sync(FULL, xa, 31);
     xa -= va;
-    xb -= vb;
-    exSa = xa & 0xFFFFu; exEa = xa >> 16; exSb = xb & 0xFFFFu; exEb = xb >> 16;
-    totSa = ta_tot & 0xFFFFu; totEa = ta_tot >> 16; totSb = tb_tot & 0xFFFFu; totEb = tb_tot >> 16;
+    exSa = xa & 0xFFFFu; exEa = xa >> 16;
+    totSa = ta_tot & 0xFFFFu; totEa = ta_tot >> 16;
+    if (NT == 2) {
+      const uint32_t tb_tot = __shfl_sync(FULL, xb, 31);
+      xb -= vb;
+      exSb = xb & 0xFFFFu; exEb = xb >> 16;
+      totSb = tb_tot & 0xFFFFu; totEb = tb_tot >> 16;
+    }
   }
   finish_tile(a, em, ta, wg, totSa, totEa, exSa, exEa, bad, cnt, lane);
-  finish_tile(a, em, tb, wg + STRIDE, totSb, totEb, exSb, exEb, badb, cnt, lane);
+  if (NT == 2) finish_tile(a, em, tb, wg + STRIDE, totSb, totEb, exSb, exEb, badb, cnt, lane);
 }
 
 // ---- two-level look-back ------------------------------------------------------------------------------
@@ -666,7 +704,7 @@ __device__ void resolver_warp(const ScanArgs& a, CtaSmem& cs, int lane) {
     }
     if (best == ((int64_t)1 << 62)) {
       if (__all_sync(FULL, all_done)) return;
-      cgx_backoff();
+      cgx_idle();  // nothing handed over: a chunk takes tens of microseconds to scan
       continue;
     }
     const int slot = __ffs((int)__ballot_sync(FULL, mine == best)) - 1;
@@ -685,6 +723,10 @@ __device__ void resolver_warp(const ScanArgs& a, CtaSmem& cs, int lane) {
 }  // namespace
 
 #ifdef CGX_JIT
+#ifndef CGX_CPU_SIM
+// the loader (jit.cu) reads the launch shape from the module it just built
+extern "C" __device__ const int cgx_flat_jit_info[4] = {(int)sizeof(CtaSmem), FW_THREADS, FW_WARPS, FW_CTAS};
+#endif
 extern "C" __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) cgx_flat_jit(const __grid_constant__ ScanArgs a) {
 #else
 namespace {
@@ -732,7 +774,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
   // starts the bulk copy of iteration `it` of `chunk` into window buffer `b`
   auto issue = [&](int64_t chunk, int it, int b) {
     if (lane == 0) {
-      const int64_t g = chunk * (int64_t)CHUNKB + (int64_t)it * (2 * STRIDE);
+      const int64_t g = chunk * (int64_t)CHUNKB + (int64_t)it * (NT * STRIDE);
       int64_t bytes = a.n - g;
       bytes = bytes > SUPER ? SUPER : bytes;
       if (bytes > 0) {
@@ -776,10 +818,10 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     const int64_t cbeg = cur * (int64_t)CHUNKB;
     Emit em{&a, ws.stS[sb], ws.stE[sb], cbeg, goff, direct};
     unsigned cnt = 0;
-    for (int it = 0; it < PAIRS; it++) {
+    for (int it = 0; it < ITERS; it++) {
       // the other window buffer was last read an iteration ago: refill it now
       __syncwarp();
-      if (it + 1 < PAIRS) {
+      if (it + 1 < ITERS) {
         issue(cur, it + 1, kb ^ 1);
       } else {
         if (nxt == none &&
@@ -791,8 +833,8 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         }
       }
       wait(kb);
-      const int64_t wg = cbeg + (int64_t)it * (2 * STRIDE);
-      if (wg < a.n) process_pair(a, em, ws.win[kb], wg, cnt, lane, rot, sel_lo, sel_hi);
+      const int64_t wg = cbeg + (int64_t)it * (NT * STRIDE);
+      if (wg < a.n) process_tiles(a, em, ws.win[kb], wg, cnt, lane, rot, sel_lo, sel_hi);
       kb ^= 1;
     }
     if (a.mode != M_FINDALL) {

@@ -239,6 +239,7 @@ inline void cgx_spin_yield() { sim::yield(); }
 inline void cgx_threadfence() {}
 inline void cgx_fence_block() {}
 inline void cgx_backoff() { sim::yield(); }
+inline void cgx_idle() { sim::yield(); }
 inline void cgx_syncthreads() {
   sim::Fiber* f = sim::cur();
   sim::BlockState* b = f->block;
