@@ -21,7 +21,7 @@ __device__ __forceinline__ void cgx_threadfence() { __threadfence(); }
 __device__ __forceinline__ void cgx_fence_block() { __threadfence_block(); }
 __device__ __forceinline__ void cgx_syncthreads() { __syncthreads(); }
 // polite spin: the waiting warp leaves the issue slots to the warps that do the work
-__device__ __forceinline__ void cgx_backoff() { __nanosleep(200); }
+__device__ __forceinline__ void cgx_backoff() { __nanosleep(500); }
 __device__ __forceinline__ void cgx_idle() { __nanosleep(2000); }
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS: UBLKCP) -----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -15,8 +15,7 @@
 //
 //   * a warp draws 15.5 KB chunks (8 tiles) from a ticket counter; per iteration it takes one TMA
 //     bulk copy of 4032 B (two overlapping 2 KB tiles) into its own double-buffered window;
-//   * lane l owns a 64-byte piece of each tile: 4 x LDS.128 (bank-conflict free through a rotated
-//     quarter order), SWAR range tests, dp4a bit packing -> one 64-bit word per class and tile;
+//   * lane l owns a 64-byte piece of each tile: 4 x LDS.128, SWAR range tests, dp4a bit packing -> one 64-bit word per class and tile;
 //   * tiles overlap by one piece (64 B).  A byte that belongs to no class of the pattern can never
 //     be inside a match ("sync byte"), so a tile owns the starts from the first sync byte of its
 //     first piece up to the first sync byte of its last piece: chains of overlapping candidates
@@ -165,31 +164,24 @@ __device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t
   return mk64(pack_rev(fl), pack_rev(fl + 8));  // bytes 0..31 in the high word
 }
 
-// Class bitmaps (reversed orientation) of the 64-byte piece at `p`.  The four 16-byte quarters are
-// read in the order (j + rot) & 3 so that the 32 lanes of one LDS.128 cover all banks evenly (pieces
-// are 64 B apart: a straight order would hit 8 of 32 banks); packing them as if they were in order
-// yields the bitmap rotated by 16*rot bits, which two byte permutes undo.
-__device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* p, int rot, uint32_t sel_lo,
-                                               uint32_t sel_hi, uint64_t (&cm)[4]) {
+// Class bitmaps (reversed orientation) of the 64-byte piece at `p`: 4 x LDS.128.  (Pieces are 64 B
+// apart, so one LDS.128 of the warp touches 8 of the 32 banks; a rotated quarter order would fix
+// that, but the shared-memory pipe has slack here and the integer pipe, which would pay for the
+// un-rotation, has none.)
+__device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* p, uint64_t (&cm)[4]) {
   uint32_t w[16];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    const uint4 v = *reinterpret_cast<const uint4*>(p + (((j + rot) & 3) << 4));
+    const uint4 v = *reinterpret_cast<const uint4*>(p + 16 * j);
     w[4 * j] = v.x;
     w[4 * j + 1] = v.y;
     w[4 * j + 2] = v.z;
     w[4 * j + 3] = v.w;
   }
-  uint64_t raw[4];
-  raw[0] = class_rev64<0>(f, w);
-  raw[1] = P_NCLASSES > 1 ? class_rev64<1>(f, w) : 0ull;
-  raw[2] = P_NCLASSES > 2 ? class_rev64<2>(f, w) : 0ull;
-  raw[3] = P_NCLASSES > 3 ? class_rev64<3>(f, w) : 0ull;
-#pragma unroll
-  for (int c = 0; c < 4; c++) {
-    const uint32_t lo = (uint32_t)raw[c], hi = (uint32_t)(raw[c] >> 32);
-    cm[c] = mk64(__byte_perm(lo, hi, sel_hi), __byte_perm(lo, hi, sel_lo));
-  }
+  cm[0] = class_rev64<0>(f, w);
+  cm[1] = P_NCLASSES > 1 ? class_rev64<1>(f, w) : 0ull;
+  cm[2] = P_NCLASSES > 2 ? class_rev64<2>(f, w) : 0ull;
+  cm[3] = P_NCLASSES > 3 ? class_rev64<3>(f, w) : 0ull;
 }
 
 // ---- marker passes -----------------------------------------------------------------------------
@@ -395,87 +387,123 @@ __device__ __forceinline__ unsigned serial_region(const ScanArgs& a, Emit& em, i
 // ---- one iteration: two overlapping tiles ------------------------------------------------------
 struct TileOut {
   uint64_t S, E;      // forward orientation, owned starts and their ends
-  int a, lim;         // owned starts: a <= p < lim (tile-relative); a < 0: nothing owned
-  bool open;          // no sync byte in the last piece: the span after `lim` is finished serially
+  uint64_t nz;        // this lane's sync bytes (bytes that belong to no class)
+  uint32_t has;       // lanes whose piece holds a sync byte
+  bool first;         // the tile starts the haystack
+  bool owned;         // the tile owns any starts at all
+  bool open;          // no sync byte in the last piece: the span after own_lim is finished serially
 };
 
-__device__ __forceinline__ uint64_t range_mask(int lo, int hi, int lane) {
-  // bits p (tile-relative) of this lane's word with lo <= p < hi
-  int l = lo - 64 * lane, h = hi - 64 * lane;
-  l = l < 0 ? 0 : l;
-  h = h > 64 ? 64 : h;
-  if (h <= l) return 0ull;
-  const uint64_t mh = h >= 64 ? ~0ull : ((1ull << h) - 1ull);
-  return mh & ~((1ull << l) - 1ull);  // l < 64 here
-}
-
-// ownership of one tile from U (union of the classes, forward orientation): see the file comment
-__device__ __forceinline__ void ownership(uint64_t U, bool first_tile, int lane, TileOut& t) {
+// Ownership of one tile from U (union of the classes, forward orientation): owned starts run from
+// the byte after the window's first sync byte (the start of the haystack for its first tile) up to
+// the first sync byte of the last piece.  The mask costs one ballot and a few word operations;
+// the positions themselves (own_start / own_open_lim) are only needed on the rare serial paths.
+__device__ __forceinline__ uint64_t ownership(uint64_t U, bool first_tile, int lane, TileOut& t) {
   const uint64_t nz = ~U;
   const uint32_t has = __ballot_sync(FULL, nz != 0ull);
-  // first sync byte of this lane's piece (64: none)
-  const uint32_t nlo = (uint32_t)nz, nhi = (uint32_t)(nz >> 32);
-  const int firstsync = nlo ? __ffs((int)nlo) - 1 : (nhi ? 31 + __ffs((int)nhi) : 64);
-  int a = 0;
+  t.nz = nz;
+  t.has = has;
+  t.first = first_tile;
+  t.owned = first_tile || has != 0u;
+  t.open = (has >> 31) == 0u;
+  const uint64_t upto = nz ^ (nz - 1ull);  // bits up to and including this lane's first sync byte
+  uint64_t m = ~0ull;
   if (!first_tile) {
-    const int fl = __ffs((int)has) - 1;  // -1 when the window has no sync byte: the shuffle wraps, a is unused
-    a = has ? 64 * fl + __shfl_sync(FULL, firstsync, fl & 31) + 1 : -1;
+    const int fl = __ffs((int)has) - 1;
+    m = lane < fl ? 0ull : (lane == fl ? ~upto : ~0ull);
+    if (!has) m = 0ull;
   }
-  const int fs31 = __shfl_sync(FULL, firstsync, 31);
-  t.a = a;
-  t.open = fs31 >= 64;
-  t.lim = STRIDE + fs31 + 1;
-  if (t.open) {
-    const int lastsync = nz ? 63 - __clzll((long long)nz) : -1;
-    const int hl = has ? 31 - __clz((int)has) : 0;
-    const int ls = __shfl_sync(FULL, lastsync, hl);
-    const int z1 = has ? 64 * hl + ls + 1 : 0;
-    t.lim = a > z1 ? a : z1;
+  if (!t.open) {
+    if (lane == 31) m &= upto;
+  } else {
+    // starts before (and at) the window's LAST sync byte; the tail span is replayed serially
+    const int hl = has ? 31 - __clz((int)has) : -1;
+    const int top = nz ? 63 - __clzll((long long)nz) : 0;
+    const uint64_t below = top == 63 ? ~0ull : ((2ull << top) - 1ull);
+    m &= lane > hl ? 0ull : (lane == hl ? below : ~0ull);
   }
+  return m;
+}
+// first owned position (tile-relative); only valid when t.owned
+__device__ __forceinline__ int own_start(const TileOut& t, int lane) {
+  if (t.first) return 0;
+  const int fl = __ffs((int)t.has) - 1;
+  return 64 * fl + __shfl_sync(FULL, __ffsll((long long)t.nz) - 1, fl) + 1;
+}
+// open tiles: where the serially replayed tail span starts
+__device__ __forceinline__ int own_open_lim(const TileOut& t, int lane) {
+  const int a = own_start(t, lane);
+  if (!t.has) return a;
+  const int hl = 31 - __clz((int)t.has);
+  const int z1 = 64 * hl + __shfl_sync(FULL, 63 - __clzll((long long)t.nz), hl) + 1;
+  return a > z1 ? a : z1;
 }
 
 __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const TileOut& t, int64_t tile_g,
                                             unsigned totS, unsigned totE, unsigned exS, unsigned exE, bool bad,
                                             unsigned& cnt, int lane) {
-  if (t.a < 0) return;
+  if (!t.owned) return;
   const int64_t stop_min = tile_g + STRIDE;
   if (bad || totS != totE) {
-    cnt += serial_region(a, em, tile_g + t.a, stop_min, cnt, lane);
+    cnt += serial_region(a, em, tile_g + own_start(t, lane), stop_min, cnt, lane);
     return;
   }
   if (totS) {
     const int rel0 = (int)(tile_g - em.cb) + 64 * lane;
-    em.put_bits(t.S, cnt + exS, rel0, false);
-    em.put_bits(t.E, cnt + exE, rel0, true);
+    if (a.mode == M_FINDALL) {
+      if (!em.direct) {
+        // one loop takes a start and an end per round: most lanes hold none or one of each
+        uint64_t sb = t.S, eb = t.E;
+        unsigned is = cnt + exS, ie = cnt + exE;
+        while (sb | eb) {
+          if (sb) {
+            const int b = __ffsll((long long)sb) - 1;
+            sb &= sb - 1;
+            if (is < (unsigned)CAP) em.stS[is] = (uint16_t)(rel0 + b);
+            is++;
+          }
+          if (eb) {
+            const int b = __ffsll((long long)eb) - 1;
+            eb &= eb - 1;
+            if (ie < (unsigned)CAP) em.stE[ie] = (uint16_t)(rel0 + b);
+            ie++;
+          }
+        }
+      } else {
+        em.put_bits(t.S, cnt + exS, rel0, false);
+        em.put_bits(t.E, cnt + exE, rel0, true);
+      }
+    }
     cnt += totS;
   }
-  if (t.open) cnt += serial_region(a, em, tile_g + t.lim, stop_min, cnt, lane);
+  if (t.open) cnt += serial_region(a, em, tile_g + own_open_lim(t, lane), stop_min, cnt, lane);
+}
+
+// bytes at or beyond the end of input belong to no class (last chunk only: kept out of line)
+__device__ __noinline__ void mask_tail(uint64_t (&ca)[4], uint64_t (&cb)[4], int64_t nv, int lane) {
+  // reversed bit r of lane l <=> tile byte 2047 - (64 l + r); valid <=> byte < nv
+  const int64_t ra = TILE - nv, rb = TILE - (nv - STRIDE);  // first valid reversed index
+  const int64_t sa = ra - 64 * lane, sb = rb - 64 * lane;
+  const uint64_t va = sa <= 0 ? ~0ull : (sa >= 64 ? 0ull : (~0ull << sa));
+  const uint64_t vb = sb <= 0 ? ~0ull : (sb >= 64 ? 0ull : (~0ull << sb));
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    ca[c] &= va;
+    cb[c] &= vb;
+  }
 }
 
 // Processes the NT tiles whose windows start at `win` (global position wg), win + STRIDE.
 __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const uint8_t* win, int64_t wg,
-                                              unsigned& cnt, int lane, int rot, uint32_t sel_lo, uint32_t sel_hi) {
+                                              unsigned& cnt, int lane) {
   const FlatDev& f = a.flat;
   const int piece = 31 - lane;
   uint64_t ca[4], cb[4] = {0ull, 0ull, 0ull, 0ull};
-  classify_piece(f, win + piece * 64, rot, sel_lo, sel_hi, ca);
-  if (NT == 2) classify_piece(f, win + STRIDE + piece * 64, rot, sel_lo, sel_hi, cb);
+  classify_piece(f, win + piece * 64, ca);
+  if (NT == 2) classify_piece(f, win + STRIDE + piece * 64, cb);
   // bytes at or beyond the end of input belong to no class
   const int64_t nv = a.n - wg;  // valid bytes from the start of tile A
-  if (nv < SUPER) {
-    // reversed bit r of lane l <=> tile byte 2047 - (64 l + r); valid <=> byte < nv
-    const int64_t ra = TILE - nv, rb = TILE - (nv - STRIDE);  // first valid reversed index
-    auto vmask = [&](int64_t r0) -> uint64_t {
-      const int64_t s = r0 - 64 * lane;
-      return s <= 0 ? ~0ull : (s >= 64 ? 0ull : (~0ull << s));
-    };
-    const uint64_t va = vmask(ra), vb = vmask(rb);
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      ca[c] &= va;
-      cb[c] &= vb;
-    }
-  }
+  if (nv < SUPER) mask_tail(ca, cb, nv, lane);
 
   // ---- right to left: where can a match start ----
 #ifdef CGX_JIT
@@ -516,18 +544,11 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
     }
   }
   TileOut ta, tb;
-  ta.S = flip(Ma);
-  ownership(ca[0] | ca[1] | ca[2] | ca[3], wg == 0, lane, ta);
-  ta.S &= ta.a < 0 ? 0ull : range_mask(ta.a, ta.lim, lane);
-  tb.S = tb.E = 0ull;
-  tb.a = -1;
-  tb.lim = 0;
-  tb.open = false;
-  if (NT == 2) {
-    tb.S = flip(Mb);
-    ownership(cb[0] | cb[1] | cb[2] | cb[3], false, lane, tb);
-    tb.S &= tb.a < 0 ? 0ull : range_mask(tb.a, tb.lim, lane);
-  }
+  ta.S = flip(Ma) & ownership(ca[0] | ca[1] | ca[2] | ca[3], wg == 0, lane, ta);
+  tb.S = tb.E = tb.nz = 0ull;
+  tb.has = 0u;
+  tb.first = tb.owned = tb.open = false;
+  if (NT == 2) tb.S = flip(Mb) & ownership(cb[0] | cb[1] | cb[2] | cb[3], false, lane, tb);
 
   const uint32_t anyS = __ballot_sync(FULL, (ta.S | tb.S) != 0ull);
   if (a.mode == M_ISMATCH) {
@@ -538,9 +559,9 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
       return;
     }
     // open tails may still hide a match
-    if (ta.a >= 0 && ta.open) cnt += serial_region(a, em, wg + ta.lim, wg + STRIDE, cnt, lane);
-    if (NT == 2 && tb.a >= 0 && tb.open)
-      cnt += serial_region(a, em, wg + STRIDE + tb.lim, wg + 2 * STRIDE, cnt, lane);
+    if (ta.owned && ta.open) cnt += serial_region(a, em, wg + own_open_lim(ta, lane), wg + STRIDE, cnt, lane);
+    if (NT == 2 && tb.owned && tb.open)
+      cnt += serial_region(a, em, wg + STRIDE + own_open_lim(tb, lane), wg + 2 * STRIDE, cnt, lane);
     if (cnt && lane == 0) a.total[1] = 1ull;
     return;
   }
@@ -751,17 +772,6 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
   }
   WarpSmem& ws = cs.w[warp];
 
-  // lane-constant addressing of the rotated quarter loads (see classify_piece); tile B starts 31
-  // pieces later: its piece parity is flipped, which keeps the same rotation conflict free
-  const int piece = 31 - lane;
-  const int rot = (piece >> 1) & 3;
-  uint32_t sel_lo = 0, sel_hi = 0;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    sel_lo |= (uint32_t)((i + 2 * rot) & 7) << (4 * i);
-    sel_hi |= (uint32_t)((i + 4 + 2 * rot) & 7) << (4 * i);
-  }
-
   uint32_t phase = 0;  // bit b = parity to wait for on mbar[b]
   auto take_ticket = [&]() -> unsigned {
     unsigned t = 0;
@@ -834,7 +844,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       }
       wait(kb);
       const int64_t wg = cbeg + (int64_t)it * (NT * STRIDE);
-      if (wg < a.n) process_tiles(a, em, ws.win[kb], wg, cnt, lane, rot, sel_lo, sel_hi);
+      if (wg < a.n) process_tiles(a, em, ws.win[kb], wg, cnt, lane);
       kb ^= 1;
     }
     if (a.mode != M_FINDALL) {
