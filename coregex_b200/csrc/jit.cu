@@ -123,7 +123,21 @@ int JitTiles() {
 
 bool JitCompileCubin(const FlatDev& f, int tiles, std::vector<char>& cubin, std::string& err) {
   const std::string hdr = JitHeader(f);
-  const std::string key = hdr + (tiles == 1 ? "#1" : "#2");
+  // experiments: extra -D options for the specialised build, e.g. CGX_JIT_DEFS="-DCGX_ROT=0 -DCGX_BACKOFF_NS=100"
+  const char* extra = getenv("CGX_JIT_DEFS");
+  std::vector<std::string> xo;
+  if (extra) {
+    std::string e(extra), cur;
+    for (char ch : e + " ") {
+      if (ch == ' ') {
+        if (!cur.empty()) xo.push_back(cur);
+        cur.clear();
+      } else {
+        cur += ch;
+      }
+    }
+  }
+  const std::string key = hdr + (tiles == 1 ? "#1" : "#2") + (extra ? extra : "");
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_cubins.find(key);
@@ -144,9 +158,10 @@ bool JitCompileCubin(const FlatDev& f, int tiles, std::vector<char>& cubin, std:
     err = "nvrtcCreateProgram failed";
     return false;
   }
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DCGX_JIT=1",
-                        tiles == 1 ? "-DCGX_TILES=1" : "-DCGX_TILES=2"};
-  const nvrtcResult rc = n.compile(prog, 5, opts);
+  std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DCGX_JIT=1",
+                                   tiles == 1 ? "-DCGX_TILES=1" : "-DCGX_TILES=2"};
+  for (auto& o : xo) opts.push_back(o.c_str());
+  const nvrtcResult rc = n.compile(prog, (int)opts.size(), opts.data());
   if (rc != NVRTC_SUCCESS) {
     size_t ls = 0;
     n.log_size(prog, &ls);
@@ -181,7 +196,8 @@ const JitKernel* GetJitKernel(const FlatDev& f, std::string& err) {
     return nullptr;
   }
   const int tiles = JitTiles();
-  const std::string hdr = JitHeader(f) + (tiles == 1 ? "#1" : "#2");
+  const char* extra = getenv("CGX_JIT_DEFS");
+  const std::string hdr = JitHeader(f) + (tiles == 1 ? "#1" : "#2") + (extra ? extra : "");
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_loaded.find({dev, hdr});

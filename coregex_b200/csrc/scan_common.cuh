@@ -21,8 +21,14 @@ __device__ __forceinline__ void cgx_threadfence() { __threadfence(); }
 __device__ __forceinline__ void cgx_fence_block() { __threadfence_block(); }
 __device__ __forceinline__ void cgx_syncthreads() { __syncthreads(); }
 // polite spin: the waiting warp leaves the issue slots to the warps that do the work
-__device__ __forceinline__ void cgx_backoff() { __nanosleep(500); }
-__device__ __forceinline__ void cgx_idle() { __nanosleep(2000); }
+#ifndef CGX_BACKOFF_NS
+#define CGX_BACKOFF_NS 200
+#endif
+#ifndef CGX_IDLE_NS
+#define CGX_IDLE_NS 1000
+#endif
+__device__ __forceinline__ void cgx_backoff() { __nanosleep(CGX_BACKOFF_NS); }
+__device__ __forceinline__ void cgx_idle() { __nanosleep(CGX_IDLE_NS); }
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS: UBLKCP) -----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

@@ -164,15 +164,24 @@ __device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t
   return mk64(pack_rev(fl), pack_rev(fl + 8));  // bytes 0..31 in the high word
 }
 
-// Class bitmaps (reversed orientation) of the 64-byte piece at `p`: 4 x LDS.128.  (Pieces are 64 B
-// apart, so one LDS.128 of the warp touches 8 of the 32 banks; a rotated quarter order would fix
-// that, but the shared-memory pipe has slack here and the integer pipe, which would pay for the
-// un-rotation, has none.)
-__device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* p, uint64_t (&cm)[4]) {
+// Class bitmaps (reversed orientation) of the 64-byte piece at `p`: 4 x LDS.128.  Pieces are 64 B
+// apart, so with a straight quarter order one LDS.128 of the warp touches 8 of the 32 banks (4x the
+// wavefronts).  CGX_ROT=1 reads the quarters in the order (j + rot) & 3, which covers all banks
+// evenly; packing them as if they were in order yields each bitmap rotated by 16*rot bits, which two
+// byte permutes per class undo (integer-pipe work traded for shared-memory wavefronts).
+#ifndef CGX_ROT
+#define CGX_ROT 1
+#endif
+__device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* p, int lane, uint64_t (&cm)[4]) {
   uint32_t w[16];
+#if CGX_ROT
+  const int rot = ((31 - lane) >> 1) & 3;
+#else
+  const int rot = 0;
+#endif
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    const uint4 v = *reinterpret_cast<const uint4*>(p + 16 * j);
+    const uint4 v = *reinterpret_cast<const uint4*>(p + (((j + rot) & 3) << 4));
     w[4 * j] = v.x;
     w[4 * j + 1] = v.y;
     w[4 * j + 2] = v.z;
@@ -182,6 +191,18 @@ __device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* 
   cm[1] = P_NCLASSES > 1 ? class_rev64<1>(f, w) : 0ull;
   cm[2] = P_NCLASSES > 2 ? class_rev64<2>(f, w) : 0ull;
   cm[3] = P_NCLASSES > 3 ? class_rev64<3>(f, w) : 0ull;
+#if CGX_ROT
+  // rotate right by 16*rot bits = 2*rot bytes: selectors are 16-bit windows of one constant
+  const uint32_t sel_lo = (uint32_t)(0x1076765454323210ull >> (16 * rot)) & 0xFFFFu;
+  const uint32_t sel_hi = (uint32_t)(0x1076765454323210ull >> (16 * ((rot + 2) & 3))) & 0xFFFFu;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    if (c < P_NCLASSES) {
+      const uint32_t lo = (uint32_t)cm[c], hi = (uint32_t)(cm[c] >> 32);
+      cm[c] = mk64(__byte_perm(lo, hi, sel_hi), __byte_perm(lo, hi, sel_lo));
+    }
+  }
+#endif
 }
 
 // ---- marker passes -----------------------------------------------------------------------------
@@ -499,8 +520,8 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
   const FlatDev& f = a.flat;
   const int piece = 31 - lane;
   uint64_t ca[4], cb[4] = {0ull, 0ull, 0ull, 0ull};
-  classify_piece(f, win + piece * 64, ca);
-  if (NT == 2) classify_piece(f, win + STRIDE + piece * 64, cb);
+  classify_piece(f, win + piece * 64, lane, ca);
+  if (NT == 2) classify_piece(f, win + STRIDE + piece * 64, lane, cb);
   // bytes at or beyond the end of input belong to no class
   const int64_t nv = a.n - wg;  // valid bytes from the start of tile A
   if (nv < SUPER) mask_tail(ca, cb, nv, lane);
