@@ -17,7 +17,7 @@ struct JitKernel {
 };
 
 // tiles per iteration the specialised kernel is built with: $CGX_TILES (1 or 2), default kJitTilesDefault
-constexpr int kJitTilesDefault = 2;
+constexpr int kJitTilesDefault = 1;
 int JitTiles();
 
 // NVRTC only: works without a device (used by the CPU test that the specialised source builds)

@@ -415,6 +415,8 @@ struct TileOut {
   bool open;          // no sync byte in the last piece: the span after own_lim is finished serially
 };
 
+__device__ __forceinline__ int own_start(const TileOut& t, int lane);
+__device__ __forceinline__ int own_open_lim(const TileOut& t, int lane);
 // Ownership of one tile from U (union of the classes, forward orientation): owned starts run from
 // the byte after the window's first sync byte (the start of the haystack for its first tile) up to
 // the first sync byte of the last piece.  The mask costs one ballot and a few word operations;
@@ -427,6 +429,24 @@ __device__ __forceinline__ uint64_t ownership(uint64_t U, bool first_tile, int l
   t.first = first_tile;
   t.owned = first_tile || has != 0u;
   t.open = (has >> 31) == 0u;
+#ifndef CGX_OWN_MASK
+#define CGX_OWN_MASK 1
+#endif
+#if !CGX_OWN_MASK
+  {
+    // (experiment) the positional formulation: [own_start, limit) turned into a per-lane mask
+    if (!t.owned) return 0ull;
+    const int a = own_start(t, lane);
+    const int fs31 = __shfl_sync(FULL, nz ? __ffsll((long long)nz) - 1 : 64, 31);
+    const int lim = t.open ? own_open_lim(t, lane) : STRIDE + fs31 + 1;
+    int l = a - 64 * lane, h = lim - 64 * lane;
+    l = l < 0 ? 0 : l;
+    h = h > 64 ? 64 : h;
+    if (h <= l) return 0ull;
+    const uint64_t mh = h >= 64 ? ~0ull : ((1ull << h) - 1ull);
+    return mh & ~((1ull << l) - 1ull);
+  }
+#endif
   const uint64_t upto = nz ^ (nz - 1ull);  // bits up to and including this lane's first sync byte
   uint64_t m = ~0ull;
   if (!first_tile) {
@@ -472,8 +492,33 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
   if (totS) {
     const int rel0 = (int)(tile_g - em.cb) + 64 * lane;
     if (a.mode == M_FINDALL) {
-      if (!em.direct) {
-        // one loop takes a start and an end per round: most lanes hold none or one of each
+#ifndef CGX_EMIT_V
+#define CGX_EMIT_V 2
+#endif
+      if (!em.direct && CGX_EMIT_V == 2) {
+        // Rounds with a warp-uniform trip count (the largest number of starts or ends any lane
+        // holds, usually 1 or 2): every round each lane stores its next start and its next end.
+        // No divergent loop, hence no reconvergence bookkeeping.
+        uint64_t sb = t.S, eb = t.E;
+        unsigned is = cnt + exS, ie = cnt + exE;
+        const unsigned ps = __popcll(sb), pe = __popcll(eb);
+        const unsigned rounds = __reduce_max_sync(FULL, ps > pe ? ps : pe);
+        for (unsigned j = 0; j < rounds; j++) {
+          if (sb) {
+            const int b = __ffsll((long long)sb) - 1;
+            sb &= sb - 1;
+            if (is < (unsigned)CAP) em.stS[is] = (uint16_t)(rel0 + b);
+            is++;
+          }
+          if (eb) {
+            const int b = __ffsll((long long)eb) - 1;
+            eb &= eb - 1;
+            if (ie < (unsigned)CAP) em.stE[ie] = (uint16_t)(rel0 + b);
+            ie++;
+          }
+        }
+      } else if (!em.direct && CGX_EMIT_V == 1) {
+        // one divergent loop takes a start and an end per round
         uint64_t sb = t.S, eb = t.E;
         unsigned is = cnt + exS, ie = cnt + exE;
         while (sb | eb) {
@@ -501,7 +546,16 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
 }
 
 // bytes at or beyond the end of input belong to no class (last chunk only: kept out of line)
-__device__ __noinline__ void mask_tail(uint64_t (&ca)[4], uint64_t (&cb)[4], int64_t nv, int lane) {
+// (kept inline: as a real call it would pin the class bitmaps in local memory — measured -12 %)
+#ifndef CGX_TAIL_NOINLINE
+#define CGX_TAIL_NOINLINE 0
+#endif
+#if CGX_TAIL_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void mask_tail(uint64_t (&ca)[4], uint64_t (&cb)[4], int64_t nv, int lane) {
   // reversed bit r of lane l <=> tile byte 2047 - (64 l + r); valid <=> byte < nv
   const int64_t ra = TILE - nv, rb = TILE - (nv - STRIDE);  // first valid reversed index
   const int64_t sa = ra - 64 * lane, sb = rb - 64 * lane;
@@ -805,9 +859,9 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
   // starts the bulk copy of iteration `it` of `chunk` into window buffer `b`
   auto issue = [&](int64_t chunk, int it, int b) {
     if (lane == 0) {
-      const int64_t g = chunk * (int64_t)CHUNKB + (int64_t)it * (NT * STRIDE);
-      int64_t bytes = a.n - g;
-      bytes = bytes > SUPER ? SUPER : bytes;
+      const int64_t g = chunk * (int64_t)CHUNKB + it * (NT * STRIDE);
+      const int64_t left = a.n - g;
+      const int bytes = left > SUPER ? SUPER : (int)left;
       if (bytes > 0) {
         // whole 16-byte blocks: the last block may run up to 15 bytes past n, inside the caller's
         // 16-byte aligned allocation granule; those bytes are masked out (process_pair, nv)

@@ -169,6 +169,13 @@ inline unsigned __reduce_add_sync(unsigned, unsigned v) {
   return r;
 }
 
+inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+  const uint64_t* s = sim::exchange(v);
+  unsigned r = 0;
+  for (int i = 0; i < 32; i++) r = (unsigned)s[i] > r ? (unsigned)s[i] : r;
+  return r;
+}
+
 // ---- scalar intrinsics -----------------------------------------------------------------------------
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
