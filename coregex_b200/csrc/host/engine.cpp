@@ -281,13 +281,14 @@ std::string JitHeader(const FlatDev& f) {
   for (int k = 0; k < f.rev_nops; k++) add(" STEP(%d, %d)", f.rev_ops[k] & 3, f.rev_ops[k] >> 2);
   o += "\n#define CGX_JIT_FWD_PASS(STEP)";
   for (int k = 0; k < f.fwd_nops; k++) add(" STEP(%d, %d)", f.fwd_ops[k] & 3, f.fwd_ops[k] >> 2);
-  o += "\ntemplate <int C> __device__ __forceinline__ uint32_t cgx_jit_flags(uint32_t w) { return 0u; }\n";
+  o += "\ntemplate <int C> __device__ __forceinline__ uint32_t cgx_jit_flags(uint32_t w, uint32_t one) { return 0u; }\n";
   for (int c = 0; c < f.nclasses; c++) {
-    add("template <> __device__ __forceinline__ uint32_t cgx_jit_flags<%d>(uint32_t w) {\n  uint32_t fl = 0u;\n", c);
+    add("template <> __device__ __forceinline__ uint32_t cgx_jit_flags<%d>(uint32_t w, uint32_t one) {\n  uint32_t fl = 0u;\n", c);
     for (int r = 0; r < f.cls_nranges[c]; r++) {
       if (f.cls_mode[c][r] == 0)
-        add("  { const uint32_t z = ((w ^ 0x%08Xu) & 0x7F7F7F7Fu) + 0x%08Xu; fl |= ~(z | w) & 0x80808080u; }\n",
-            f.cls_k1[c][r], f.cls_k2[c][r]);
+        // 2 ALU-pipe + 1 FMA-pipe instruction per word (scan_flat.cu "pipe-aware primitives")
+        add("  { const uint32_t z = mad_fma(xor_and(w, 0x%08Xu, 0x7F7F7F7Fu), one, 0x%08Xu); fl %s nor_and(z, w, 0x80808080u); }\n",
+            f.cls_k1[c][r], f.cls_k2[c][r], r == 0 ? "=" : "|=");
       else
         add("  fl |= swar_in_range(w, 0x%08Xu, 0x%08Xu);\n", f.cls_k1[c][r], f.cls_k2[c][r]);
     }

@@ -90,6 +90,36 @@ struct CtaSmem {
 
 __device__ __forceinline__ uint64_t mk64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
+// ---- pipe-aware primitives ----------------------------------------------------------------------
+// The kernel is bound by the integer ALU pipe (LOP3/SHF/ISETP/IADD3: one warp instruction per two
+// cycles per sub-partition; ncu: alu 73 %, fma 15 %), so the per-byte work is written to need as few
+// ALU-pipe instructions as possible:
+//  * a LOP3 takes one immediate at most.  With both constants of `(w ^ k) & m` as immediates the
+//    compiler emits two LOP3s; as an explicit lop3.b32 one of them is kept in a register: one LOP3.
+//  * `x + k` as x * one + k with a multiplier the compiler cannot see through (ScanArgs-derived 1)
+//    is an IMAD: same result, issued to the FMA pipe, which is otherwise idle.
+#if defined(CGX_CPU_SIM) || !defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint32_t xor_and(uint32_t w, uint32_t k, uint32_t m) { return (w ^ k) & m; }
+__device__ __forceinline__ uint32_t nor_and(uint32_t z, uint32_t w, uint32_t m) { return ~(z | w) & m; }
+__device__ __forceinline__ uint32_t mad_fma(uint32_t x, uint32_t one, uint32_t k) { return x * one + k; }
+#else
+__device__ __forceinline__ uint32_t xor_and(uint32_t w, uint32_t k, uint32_t m) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(d) : "r"(w), "r"(k), "r"(m));  // (a ^ b) & c
+  return d;
+}
+__device__ __forceinline__ uint32_t nor_and(uint32_t z, uint32_t w, uint32_t m) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(d) : "r"(z), "r"(w), "r"(m));  // ~(a | b) & c
+  return d;
+}
+__device__ __forceinline__ uint32_t mad_fma(uint32_t x, uint32_t one, uint32_t k) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(one), "r"(k));
+  return d;
+}
+#endif
+
 // ---- 2048-bit vectors across the warp: lane l holds word l -------------------------------------
 // markers move one position towards higher bit indices; `in` enters bit 0 of lane 0
 __device__ __forceinline__ uint64_t shl1(uint64_t m, int lane, uint32_t in) {
@@ -98,9 +128,17 @@ __device__ __forceinline__ uint64_t shl1(uint64_t m, int lane, uint32_t in) {
   if (lane == 0) dn = in;
   return mk64(__funnelshift_l(lo, hi, 1), __funnelshift_l(dn, lo, 1));
 }
-__device__ __forceinline__ uint64_t add2048(uint64_t s, uint64_t cc, int lane) {
+// 2048-bit addition s + cc.  EXACT resolves generate AND propagate words (two ballots).  The fast
+// form assumes that no word propagates: with s a subset of cc (a marker can only stand on a byte
+// of the class) a word's sum is all ones only if the class word itself is all ones — 64 class
+// bytes in one lane's piece — which process_tiles tests once per tile; then the carry into a word
+// is just the carry out of its neighbour: one ballot, 6 ALU-pipe instructions fewer.
+// prevbit = bit (lane - 1), 0 for lane 0.
+template <bool EXACT>
+__device__ __forceinline__ uint64_t add2048(uint64_t s, uint64_t cc, int lane, uint32_t prevbit) {
   const uint64_t sum = s + cc;
   const uint32_t G = __ballot_sync(FULL, sum < s);
+  if (!EXACT) return sum + ((G & prevbit) ? 1ull : 0ull);
   const uint32_t P = __ballot_sync(FULL, sum == ~0ull);
   const uint32_t A = G | P;
   const uint32_t carries = A ^ G ^ (A + G);  // bit l = carry into word l
@@ -129,19 +167,19 @@ __device__ __forceinline__ uint32_t pack_rev(const uint32_t* fl) {
 }
 
 template <int C>
-__device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t (&w)[16]) {
+__device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t (&w)[16], uint32_t one) {
   uint32_t fl[16];
 #ifdef CGX_JIT
 #pragma unroll
-  for (int k = 0; k < 16; k++) fl[k] = cgx_jit_flags<C>(w[k]);  // generated: ranges as immediates
+  for (int k = 0; k < 16; k++) fl[k] = cgx_jit_flags<C>(w[k], one);  // generated: ranges as constants
 #else
   const int nr = f.cls_nranges[C];
-  if (nr == 1 && f.cls_mode[C][0] == 0) {  // one XOR-alignable range: 3 ops per word
+  if (nr == 1 && f.cls_mode[C][0] == 0) {  // one XOR-alignable range: 2 ALU + 1 FMA op per word
     const uint32_t k1 = f.cls_k1[C][0], k2 = f.cls_k2[C][0];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-      const uint32_t z = ((w[k] ^ k1) & 0x7F7F7F7Fu) + k2;  // bit7 set <=> (x^lo)&0x7f > width
-      fl[k] = ~(z | w[k]) & 0x80808080u;
+      const uint32_t z = mad_fma(xor_and(w[k], k1, 0x7F7F7F7Fu), one, k2);  // bit7 set <=> (x^lo)&0x7f > width
+      fl[k] = nor_and(z, w[k], 0x80808080u);
     }
   } else {
 #pragma unroll
@@ -151,8 +189,8 @@ __device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t
       if (f.cls_mode[C][r] == 0) {
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-          const uint32_t z = ((w[k] ^ k1) & 0x7F7F7F7Fu) + k2;
-          fl[k] |= ~(z | w[k]) & 0x80808080u;
+          const uint32_t z = mad_fma(xor_and(w[k], k1, 0x7F7F7F7Fu), one, k2);
+          fl[k] |= nor_and(z, w[k], 0x80808080u);
         }
       } else {
 #pragma unroll
@@ -172,7 +210,8 @@ __device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t
 #ifndef CGX_ROT
 #define CGX_ROT 1
 #endif
-__device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* p, int lane, uint64_t (&cm)[4]) {
+__device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* p, int lane, uint32_t one,
+                                               uint64_t (&cm)[4]) {
   uint32_t w[16];
 #if CGX_ROT
   const int rot = ((31 - lane) >> 1) & 3;
@@ -187,10 +226,10 @@ __device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* 
     w[4 * j + 2] = v.z;
     w[4 * j + 3] = v.w;
   }
-  cm[0] = class_rev64<0>(f, w);
-  cm[1] = P_NCLASSES > 1 ? class_rev64<1>(f, w) : 0ull;
-  cm[2] = P_NCLASSES > 2 ? class_rev64<2>(f, w) : 0ull;
-  cm[3] = P_NCLASSES > 3 ? class_rev64<3>(f, w) : 0ull;
+  cm[0] = class_rev64<0>(f, w, one);
+  cm[1] = P_NCLASSES > 1 ? class_rev64<1>(f, w, one) : 0ull;
+  cm[2] = P_NCLASSES > 2 ? class_rev64<2>(f, w, one) : 0ull;
+  cm[3] = P_NCLASSES > 3 ? class_rev64<3>(f, w, one) : 0ull;
 #if CGX_ROT
   // rotate right by 16*rot bits = 2*rot bytes: selectors are 16-bit windows of one constant
   const uint32_t sel_lo = (uint32_t)(0x1076765454323210ull >> (16 * rot)) & 0xFFFFu;
@@ -208,9 +247,9 @@ __device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* 
 // ---- marker passes -----------------------------------------------------------------------------
 // Right to left (reversed orientation): M = positions from which items k..end can match.
 // (tile B's operands are touched only when two tiles are evaluated jointly)
-template <int C>
+template <int C, bool EXACT>
 __device__ __forceinline__ void rev_step(uint32_t kind, const uint64_t (&ca)[4], const uint64_t (&cb)[4],
-                                         uint64_t& Ma, uint64_t& Mb, int lane) {
+                                         uint64_t& Ma, uint64_t& Mb, int lane, uint32_t prevbit) {
   const uint64_t Ca = ca[C], Cb = cb[C];
   // unknown territory past the window is assumed to allow a match (bit entering lane 0 is 1)
   const uint64_t ua = shl1(Ma, lane, FULL) & Ca;
@@ -225,19 +264,19 @@ __device__ __forceinline__ void rev_step(uint32_t kind, const uint64_t (&ca)[4],
   } else {
     // extend through the run towards lower addresses; a second marker inside one run survives the
     // carry of the first as a 1 in the sum, so the markers themselves are OR-ed back
-    const uint64_t pa = (~add2048(ua, Ca, lane) & Ca) | ua;
+    const uint64_t pa = (~add2048<EXACT>(ua, Ca, lane, prevbit) & Ca) | ua;
     Ma = kind == 1 ? pa : (Ma | pa);
     if (NT == 2) {
-      const uint64_t pb = (~add2048(ub, Cb, lane) & Cb) | ub;
+      const uint64_t pb = (~add2048<EXACT>(ub, Cb, lane, prevbit) & Cb) | ub;
       Mb = kind == 1 ? pb : (Mb | pb);
     }
   }
 }
 // Left to right (forward orientation): T = positions a marker stands at before item k; the forced
 // greedy choice (take the whole run / take the optional byte whenever it is there).
-template <int C>
+template <int C, bool EXACT>
 __device__ __forceinline__ void fwd_step(uint32_t kind, const uint64_t (&ca)[4], const uint64_t (&cb)[4],
-                                         uint64_t& Ta, uint64_t& Tb, int lane) {
+                                         uint64_t& Ta, uint64_t& Tb, int lane, uint32_t prevbit) {
   const uint64_t Ca = ca[C], Cb = cb[C];
   const uint64_t ia = Ta & Ca, ib = Tb & Cb;  // markers that can take a byte
   if (kind == 0) {
@@ -248,10 +287,10 @@ __device__ __forceinline__ void fwd_step(uint32_t kind, const uint64_t (&ca)[4],
     if (NT == 2) Tb = (Tb & ~Cb) | shl1(ib, lane, 0u);
   } else {
     // a marker inside a run of ones carries out to the first zero after the run
-    const uint64_t ea = add2048(ia, Ca, lane) & ~Ca;
+    const uint64_t ea = add2048<EXACT>(ia, Ca, lane, prevbit) & ~Ca;
     Ta = kind == 1 ? ea : ((Ta & ~Ca) | ea);
     if (NT == 2) {
-      const uint64_t eb = add2048(ib, Cb, lane) & ~Cb;
+      const uint64_t eb = add2048<EXACT>(ib, Cb, lane, prevbit) & ~Cb;
       Tb = kind == 1 ? eb : ((Tb & ~Cb) | eb);
     }
   }
@@ -265,19 +304,54 @@ __device__ __forceinline__ void fwd_step(uint32_t kind, const uint64_t (&ca)[4],
     default: { constexpr int C = 3; CALL; } break; \
   }
 
-// exclusive prefix parity of the 2048-bit vector x: bit p = parity of the bits of x below p
-__device__ __forceinline__ uint64_t prefix_parity_excl(uint64_t x, int lane) {
-  uint64_t y = x;
-  y ^= y << 1;
-  y ^= y << 2;
-  y ^= y << 4;
-  y ^= y << 8;
-  y ^= y << 16;
-  y ^= y << 32;  // inclusive prefix inside the word
-  const uint32_t odd = __ballot_sync(FULL, (int)(y >> 63));
-  const uint32_t below = odd & ((1u << lane) - 1u);
-  const uint64_t flipmask = (__popc(below) & 1) ? ~0ull : 0ull;
-  return (y ^ x) ^ flipmask;
+// The two passes of one iteration.  EXACT: see add2048.
+template <bool EXACT>
+__device__ __forceinline__ void rev_pass(const FlatDev& f, const uint64_t (&ca)[4], const uint64_t (&cb)[4],
+                                         uint64_t& Ma, uint64_t& Mb, int lane, uint32_t prevbit) {
+#ifdef CGX_JIT
+  Ma = ca[CGX_JIT_REV_INIT];
+  Mb = cb[CGX_JIT_REV_INIT];
+#define CGX_STEP(kind, cls) rev_step<cls, EXACT>(kind, ca, cb, Ma, Mb, lane, prevbit);
+  CGX_JIT_REV_PASS(CGX_STEP)
+#undef CGX_STEP
+#else
+  const int init_cls = f.rev_init_class;
+  Ma = init_cls == 0 ? ca[0] : init_cls == 1 ? ca[1] : init_cls == 2 ? ca[2] : ca[3];
+  Mb = init_cls == 0 ? cb[0] : init_cls == 1 ? cb[1] : init_cls == 2 ? cb[2] : cb[3];
+  const int rev_nops = f.rev_nops;
+  for (int k = 0; k < rev_nops; k++) {
+    const uint32_t op = f.rev_ops[k];
+    const uint32_t kind = op & 3u;
+    CGX_CLASS_SWITCH(op >> 2, (rev_step<C, EXACT>(kind, ca, cb, Ma, Mb, lane, prevbit)));
+  }
+#endif
+}
+template <bool EXACT>
+__device__ __forceinline__ void fwd_pass(const FlatDev& f, const uint64_t (&ca)[4], const uint64_t (&cb)[4],
+                                         uint64_t& Ta, uint64_t& Tb, int lane, uint32_t prevbit) {
+#ifdef CGX_JIT
+#define CGX_STEP(kind, cls) fwd_step<cls, EXACT>(kind, ca, cb, Ta, Tb, lane, prevbit);
+  CGX_JIT_FWD_PASS(CGX_STEP)
+#undef CGX_STEP
+#else
+  const int fwd_nops = f.fwd_nops;
+  for (int k = 0; k < fwd_nops; k++) {
+    const uint32_t op = f.fwd_ops[k];
+    const uint32_t kind = op & 3u;
+    CGX_CLASS_SWITCH(op >> 2, (fwd_step<C, EXACT>(kind, ca, cb, Ta, Tb, lane, prevbit)));
+  }
+#endif
+}
+
+// Do the starts S and ends E of one tile alternate (start, end, start, end ...; an end may share
+// its position with the next start)?  With in = (starts below this lane's word) - (ends below it)
+// from the rank scan — 1 when a match is open at the word's first bit — the word is consistent iff
+// D = E - S - in, the span mask, has its edges exactly at S ^ E: D ^ (D << 1 | in) == S ^ E, and
+// in is 0 or 1.  Together with equal totals this is exact (tests/test_sim_flat.py checks the
+// criterion exhaustively on short words); it replaces a 6-step prefix parity.
+__device__ __forceinline__ bool word_misordered(uint64_t S, uint64_t E, uint32_t in) {
+  const uint64_t D = E - S - in;
+  return in > 1u || (D ^ ((D << 1) | in)) != (S ^ E);
 }
 
 // ---- output ------------------------------------------------------------------------------------
@@ -574,29 +648,34 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
   const FlatDev& f = a.flat;
   const int piece = 31 - lane;
   uint64_t ca[4], cb[4] = {0ull, 0ull, 0ull, 0ull};
-  classify_piece(f, win + piece * 64, lane, ca);
-  if (NT == 2) classify_piece(f, win + STRIDE + piece * 64, lane, cb);
+  // a 1 the compiler cannot fold (a launch has at least one chunk): multiplier of mad_fma
+  const uint32_t one = (uint32_t)(a.nchunks > 0);
+  classify_piece(f, win + piece * 64, lane, one, ca);
+  if (NT == 2) classify_piece(f, win + STRIDE + piece * 64, lane, one, cb);
   // bytes at or beyond the end of input belong to no class
   const int64_t nv = a.n - wg;  // valid bytes from the start of tile A
   if (nv < SUPER) mask_tail(ca, cb, nv, lane);
 
-  // ---- right to left: where can a match start ----
-#ifdef CGX_JIT
-  uint64_t Ma = ca[CGX_JIT_REV_INIT], Mb = cb[CGX_JIT_REV_INIT];
-#define CGX_STEP(kind, cls) rev_step<cls>(kind, ca, cb, Ma, Mb, lane);
-  CGX_JIT_REV_PASS(CGX_STEP)
-#undef CGX_STEP
-#else
-  const int init_cls = f.rev_init_class;
-  uint64_t Ma = init_cls == 0 ? ca[0] : init_cls == 1 ? ca[1] : init_cls == 2 ? ca[2] : ca[3];
-  uint64_t Mb = init_cls == 0 ? cb[0] : init_cls == 1 ? cb[1] : init_cls == 2 ? cb[2] : cb[3];
-  const int rev_nops = f.rev_nops;
-  for (int k = 0; k < rev_nops; k++) {
-    const uint32_t op = f.rev_ops[k];
-    const uint32_t kind = op & 3u;
-    CGX_CLASS_SWITCH(op >> 2, rev_step<C>(kind, ca, cb, Ma, Mb, lane));
+  // a class word of all ones (64 class bytes in one piece) needs the exact carry resolution
+  uint32_t fullw = 0u;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    if (c < P_NCLASSES) {
+      const uint32_t t = (uint32_t)ca[c] & (uint32_t)(ca[c] >> 32);
+      fullw = t > fullw ? t : fullw;
+      if (NT == 2) {
+        const uint32_t u = (uint32_t)cb[c] & (uint32_t)(cb[c] >> 32);
+        fullw = u > fullw ? u : fullw;
+      }
+    }
   }
-#endif
+  const bool exact = __any_sync(FULL, fullw == 0xFFFFFFFFu);
+  const uint32_t prevbit = lane ? 1u << (lane - 1) : 0u;
+
+  // ---- right to left: where can a match start ----
+  uint64_t Ma, Mb;
+  if (exact) rev_pass<true>(f, ca, cb, Ma, Mb, lane, prevbit);
+  else rev_pass<false>(f, ca, cb, Ma, Mb, lane, prevbit);
   if (P_RUNSTART) {
     // only the first byte of a run of class 0 (pattern opens with C+); the byte before the window
     // counts as outside the class: position 0 is owned only when it is the start of the input
@@ -647,33 +726,10 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
   if (anyS) {
     // ---- left to right: where do the matches end ----
     uint64_t Ta = ta.S, Tb = tb.S;
-#ifdef CGX_JIT
-#define CGX_STEP(kind, cls) fwd_step<cls>(kind, ca, cb, Ta, Tb, lane);
-    CGX_JIT_FWD_PASS(CGX_STEP)
-#undef CGX_STEP
-#else
-    const int fwd_nops = f.fwd_nops;
-    for (int k = 0; k < fwd_nops; k++) {
-      const uint32_t op = f.fwd_ops[k];
-      const uint32_t kind = op & 3u;
-      CGX_CLASS_SWITCH(op >> 2, fwd_step<C>(kind, ca, cb, Ta, Tb, lane));
-    }
-#endif
+    if (exact) fwd_pass<true>(f, ca, cb, Ta, Tb, lane, prevbit);
+    else fwd_pass<false>(f, ca, cb, Ta, Tb, lane, prevbit);
     ta.E = Ta;
     tb.E = Tb;
-
-    // ---- starts and ends must alternate: S-only at even parity, anything with an end at odd ----
-    const uint64_t pa = prefix_parity_excl(ta.S ^ ta.E, lane);
-    uint64_t wa = (ta.S & ~ta.E & pa) | (ta.E & ~pa), wb = 0ull;
-    // (an end in the middle of a class-0 run: the reference resumes there, which is no run start)
-    if (P_MIDRUN) wa |= ta.E & ca[0] & shl1(ca[0], lane, 0u);
-    if (NT == 2) {
-      const uint64_t pb = prefix_parity_excl(tb.S ^ tb.E, lane);
-      wb = (tb.S & ~tb.E & pb) | (tb.E & ~pb);
-      if (P_MIDRUN) wb |= tb.E & cb[0] & shl1(cb[0], lane, 0u);
-    }
-    bad = __any_sync(FULL, wa != 0ull);
-    if (NT == 2) badb = __any_sync(FULL, wb != 0ull);
 
     // ---- counts and ranks (tile A's matches precede tile B's) ----
     uint32_t xa = __popcll(ta.S) | (__popcll(ta.E) << 16), xb = __popcll(tb.S) | (__popcll(tb.E) << 16);
@@ -696,6 +752,17 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
       xb -= vb;
       exSb = xb & 0xFFFFu; exEb = xb >> 16;
       totSb = tb_tot & 0xFFFFu; totEb = tb_tot >> 16;
+    }
+
+    // ---- starts and ends must alternate ----
+    bool wa = word_misordered(ta.S, ta.E, exSa - exEa), wb = false;
+    // (an end in the middle of a class-0 run: the reference resumes there, which is no run start)
+    if (P_MIDRUN) wa |= (ta.E & ca[0] & shl1(ca[0], lane, 0u)) != 0ull;
+    bad = __any_sync(FULL, wa);
+    if (NT == 2) {
+      wb = word_misordered(tb.S, tb.E, exSb - exEb);
+      if (P_MIDRUN) wb |= (tb.E & cb[0] & shl1(cb[0], lane, 0u)) != 0ull;
+      badb = __any_sync(FULL, wb);
     }
   }
   finish_tile(a, em, ta, wg, totSa, totEa, exSa, exEa, bad, cnt, lane);

@@ -109,6 +109,64 @@ def test_long_spans_without_sync_bytes():
     check(IP, b"1.1.1." + b"9" * 6000)
 
 
+def test_class_words_of_all_ones_use_exact_carries():
+    # a 64-byte piece made of class bytes only: the fast carry chain (one ballot) is not valid there
+    rng = random.Random(21)
+    parts = []
+    for _ in range(120):
+        parts.append(b"x" * rng.randrange(1, 30) + b" ")
+        parts.append(b"9" * rng.randrange(60, 400) + b"." + b"1" * rng.randrange(1, 200) + b".22.3 ")
+        parts.append(b"w" * rng.randrange(64, 300) + b"@" + b"h" * rng.randrange(1, 150) + b".org ")
+    hay = b"".join(parts)
+    check(IP, hay, grid=2)
+    check(r"\w+@\w+\.\w+", hay, grid=2)
+    check(r"\d+", hay, grid=2)
+
+
+def test_alternation_criterion_exhaustive():
+    """word_misordered() in scan_flat.cu, restated: per word, with `inn` = starts below - ends below,
+    D = E - S - inn must satisfy D ^ (D << 1 | inn) == S ^ E and inn in {0,1}; plus equal totals.
+    Checked against the definition (spans sorted by start never overlap, ends distinct) for every
+    assignment of ends to every set of starts on three 3-bit words."""
+    import itertools
+    B, NW = 3, 3
+    W, M = B * NW, (1 << B) - 1
+
+    def truth(pairs):
+        last = -1
+        for s_, e_ in sorted(pairs):
+            if s_ < last:
+                return False
+            last = e_
+        return len({e_ for _, e_ in pairs}) == len(pairs)
+
+    def kernel(S, E):
+        if bin(S).count("1") != bin(E).count("1"):
+            return False
+        cs = ce = 0
+        for w in range(NW):
+            Sw, Ew = (S >> (B * w)) & M, (E >> (B * w)) & M
+            inn = cs - ce
+            if inn not in (0, 1):
+                return False
+            D = (Ew - Sw - inn) & M
+            if D ^ (((D << 1) | inn) & M) != Sw ^ Ew:
+                return False
+            cs += bin(Sw).count("1")
+            ce += bin(Ew).count("1")
+        return True
+
+    if BACKEND != "sim":
+        pytest.skip("backend-independent")
+    for S in range(1, 1 << W):
+        starts = [p_ for p_ in range(W) if S >> p_ & 1]
+        for ends in itertools.product(*[range(s_ + 1, W) for s_ in starts]):
+            E = 0
+            for e_ in ends:
+                E |= 1 << e_
+            assert kernel(S, E) == truth(list(zip(starts, ends))), (starts, ends)
+
+
 def test_random_digit_dot_soup():
     rng = random.Random(11)
     for trial in range(30):
