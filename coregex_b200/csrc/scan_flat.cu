@@ -134,6 +134,17 @@ __device__ __forceinline__ uint64_t shl1(uint64_t m, int lane, uint32_t in) {
 // bytes in one lane's piece — which process_tiles tests once per tile; then the carry into a word
 // is just the carry out of its neighbour: one ballot, 6 ALU-pipe instructions fewer.
 // prevbit = bit (lane - 1), 0 for lane 0.
+// The same shift for the marker passes, where what enters bit 0 of lane 0 does not matter (lane 0
+// keeps the top bit of its own word): in the right-to-left pass that bit stands for the byte past
+// the window, and nothing can travel from there to an owned start without crossing the sync byte
+// that ends the owned range; in the left-to-right pass a stray marker at the window's first byte
+// dies at the first sync byte at the latest, before the owned range begins, and the ends are masked
+// with the ownership mask (process_tiles).  Saves one SEL per step on the ALU pipe.
+__device__ __forceinline__ uint64_t shl1x(uint64_t m) {
+  const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+  const uint32_t dn = __shfl_up_sync(FULL, hi, 1);
+  return mk64(__funnelshift_l(lo, hi, 1), __funnelshift_l(dn, lo, 1));
+}
 template <bool EXACT>
 __device__ __forceinline__ uint64_t add2048(uint64_t s, uint64_t cc, int lane, uint32_t prevbit) {
   const uint64_t sum = s + cc;
@@ -252,9 +263,9 @@ __device__ __forceinline__ void rev_step(uint32_t kind, const uint64_t (&ca)[4],
                                          uint64_t& Ma, uint64_t& Mb, int lane, uint32_t prevbit) {
   const uint64_t Ca = ca[C], Cb = cb[C];
   // unknown territory past the window is assumed to allow a match (bit entering lane 0 is 1)
-  const uint64_t ua = shl1(Ma, lane, FULL) & Ca;
+  const uint64_t ua = shl1x(Ma) & Ca;
   uint64_t ub = 0;
-  if (NT == 2) ub = shl1(Mb, lane, FULL) & Cb;
+  if (NT == 2) ub = shl1x(Mb) & Cb;
   if (kind == 0) {
     Ma = ua;
     Mb = ub;
@@ -280,11 +291,11 @@ __device__ __forceinline__ void fwd_step(uint32_t kind, const uint64_t (&ca)[4],
   const uint64_t Ca = ca[C], Cb = cb[C];
   const uint64_t ia = Ta & Ca, ib = Tb & Cb;  // markers that can take a byte
   if (kind == 0) {
-    Ta = shl1(ia, lane, 0u);
-    if (NT == 2) Tb = shl1(ib, lane, 0u);
+    Ta = shl1x(ia);
+    if (NT == 2) Tb = shl1x(ib);
   } else if (kind == 3) {
-    Ta = (Ta & ~Ca) | shl1(ia, lane, 0u);
-    if (NT == 2) Tb = (Tb & ~Cb) | shl1(ib, lane, 0u);
+    Ta = (Ta & ~Ca) | shl1x(ia);
+    if (NT == 2) Tb = (Tb & ~Cb) | shl1x(ib);
   } else {
     // a marker inside a run of ones carries out to the first zero after the run
     const uint64_t ea = add2048<EXACT>(ia, Ca, lane, prevbit) & ~Ca;
@@ -503,31 +514,11 @@ __device__ __forceinline__ uint64_t ownership(uint64_t U, bool first_tile, int l
   t.first = first_tile;
   t.owned = first_tile || has != 0u;
   t.open = (has >> 31) == 0u;
-#ifndef CGX_OWN_MASK
-#define CGX_OWN_MASK 1
-#endif
-#if !CGX_OWN_MASK
-  {
-    // (experiment) the positional formulation: [own_start, limit) turned into a per-lane mask
-    if (!t.owned) return 0ull;
-    const int a = own_start(t, lane);
-    const int fs31 = __shfl_sync(FULL, nz ? __ffsll((long long)nz) - 1 : 64, 31);
-    const int lim = t.open ? own_open_lim(t, lane) : STRIDE + fs31 + 1;
-    int l = a - 64 * lane, h = lim - 64 * lane;
-    l = l < 0 ? 0 : l;
-    h = h > 64 ? 64 : h;
-    if (h <= l) return 0ull;
-    const uint64_t mh = h >= 64 ? ~0ull : ((1ull << h) - 1ull);
-    return mh & ~((1ull << l) - 1ull);
-  }
-#endif
+  // nz == 0 gives upto == all ones: a lane below the first one with a sync byte owns nothing
+  // without being told apart from it
   const uint64_t upto = nz ^ (nz - 1ull);  // bits up to and including this lane's first sync byte
-  uint64_t m = ~0ull;
-  if (!first_tile) {
-    const int fl = __ffs((int)has) - 1;
-    m = lane < fl ? 0ull : (lane == fl ? ~upto : ~0ull);
-    if (!has) m = 0ull;
-  }
+  const uint32_t lt = (1u << lane) - 1u;
+  uint64_t m = (first_tile || (has & lt)) ? ~0ull : ~upto;
   if (!t.open) {
     if (lane == 31) m &= upto;
   } else {
@@ -573,22 +564,25 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
         // Rounds with a warp-uniform trip count (the largest number of starts or ends any lane
         // holds, usually 1 or 2): every round each lane stores its next start and its next end.
         // No divergent loop, hence no reconvergence bookkeeping.
-        uint64_t sb = t.S, eb = t.E;
-        unsigned is = cnt + exS, ie = cnt + exE;
-        const unsigned ps = __popcll(sb), pe = __popcll(eb);
-        const unsigned rounds = __reduce_max_sync(FULL, ps > pe ? ps : pe);
-        for (unsigned j = 0; j < rounds; j++) {
-          if (sb) {
-            const int b = __ffsll((long long)sb) - 1;
-            sb &= sb - 1;
-            if (is < (unsigned)CAP) em.stS[is] = (uint16_t)(rel0 + b);
-            is++;
-          }
-          if (eb) {
-            const int b = __ffsll((long long)eb) - 1;
-            eb &= eb - 1;
-            if (ie < (unsigned)CAP) em.stE[ie] = (uint16_t)(rel0 + b);
-            ie++;
+        // A tile that does not fit the staging buffer any more stages nothing: the chunk has
+        // overflowed and will be run again with direct stores (no per-store bound checks).
+        if (cnt + totS <= (unsigned)CAP) {
+          uint64_t sb = t.S, eb = t.E;
+          uint16_t* ps_ = em.stS + cnt + exS;
+          uint16_t* pe_ = em.stE + cnt + exE;
+          const unsigned ps = __popcll(sb), pe = __popcll(eb);
+          const unsigned rounds = __reduce_max_sync(FULL, ps > pe ? ps : pe);
+          for (unsigned j = 0; j < rounds; j++) {
+            if (sb) {
+              const int b = __ffsll((long long)sb) - 1;
+              sb &= sb - 1;
+              *ps_++ = (uint16_t)(rel0 + b);
+            }
+            if (eb) {
+              const int b = __ffsll((long long)eb) - 1;
+              eb &= eb - 1;
+              *pe_++ = (uint16_t)(rel0 + b);
+            }
           }
         }
       } else if (!em.direct && CGX_EMIT_V == 1) {
@@ -643,8 +637,9 @@ void mask_tail(uint64_t (&ca)[4], uint64_t (&cb)[4], int64_t nv, int lane) {
 }
 
 // Processes the NT tiles whose windows start at `win` (global position wg), win + STRIDE.
-__device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const uint8_t* win, int64_t wg,
-                                              unsigned& cnt, int lane) {
+// nv = valid bytes from the start of tile A, clamped to SUPER; first = the window starts the haystack.
+__device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const uint8_t* win, int64_t wg, int nv,
+                                              bool first, unsigned& cnt, int lane) {
   const FlatDev& f = a.flat;
   const int piece = 31 - lane;
   uint64_t ca[4], cb[4] = {0ull, 0ull, 0ull, 0ull};
@@ -653,7 +648,6 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
   classify_piece(f, win + piece * 64, lane, one, ca);
   if (NT == 2) classify_piece(f, win + STRIDE + piece * 64, lane, one, cb);
   // bytes at or beyond the end of input belong to no class
-  const int64_t nv = a.n - wg;  // valid bytes from the start of tile A
   if (nv < SUPER) mask_tail(ca, cb, nv, lane);
 
   // a class word of all ones (64 class bytes in one piece) needs the exact carry resolution
@@ -698,11 +692,16 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
     }
   }
   TileOut ta, tb;
-  ta.S = flip(Ma) & ownership(ca[0] | ca[1] | ca[2] | ca[3], wg == 0, lane, ta);
+  const uint64_t oma = ownership(ca[0] | ca[1] | ca[2] | ca[3], first, lane, ta);
+  uint64_t omb = 0ull;
+  ta.S = flip(Ma) & oma;
   tb.S = tb.E = tb.nz = 0ull;
   tb.has = 0u;
   tb.first = tb.owned = tb.open = false;
-  if (NT == 2) tb.S = flip(Mb) & ownership(cb[0] | cb[1] | cb[2] | cb[3], false, lane, tb);
+  if (NT == 2) {
+    omb = ownership(cb[0] | cb[1] | cb[2] | cb[3], false, lane, tb);
+    tb.S = flip(Mb) & omb;
+  }
 
   const uint32_t anyS = __ballot_sync(FULL, (ta.S | tb.S) != 0ull);
   if (a.mode == M_ISMATCH) {
@@ -728,8 +727,10 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
     uint64_t Ta = ta.S, Tb = tb.S;
     if (exact) fwd_pass<true>(f, ca, cb, Ta, Tb, lane, prevbit);
     else fwd_pass<false>(f, ca, cb, Ta, Tb, lane, prevbit);
-    ta.E = Ta;
-    tb.E = Tb;
+    // (a match from an owned start ends inside the owned range; the mask drops what a stray
+    // marker of shl1x may have left before it)
+    ta.E = Ta & oma;
+    tb.E = Tb & omb;
 
     // ---- counts and ranks (tile A's matches precede tile B's) ----
     uint32_t xa = __popcll(ta.S) | (__popcll(ta.E) << 16), xb = __popcll(tb.S) | (__popcll(tb.E) << 16);
@@ -923,21 +924,26 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     }
     return __shfl_sync(FULL, t, 0);
   };
-  // starts the bulk copy of iteration `it` of `chunk` into window buffer `b`
+  // starts the bulk copy of iteration `it` of `chunk` into window buffer `b`.  No proxy fence: the
+  // buffer's previous contents were read with LDS whose results have all been consumed (they fed
+  // the classification of an earlier iteration) before the warp gets here.
   auto issue = [&](int64_t chunk, int it, int b) {
     if (lane == 0) {
       const int64_t g = chunk * (int64_t)CHUNKB + it * (NT * STRIDE);
-      const int64_t left = a.n - g;
-      const int bytes = left > SUPER ? SUPER : (int)left;
-      if (bytes > 0) {
-        // whole 16-byte blocks: the last block may run up to 15 bytes past n, inside the caller's
-        // 16-byte aligned allocation granule; those bytes are masked out (process_pair, nv)
-        const uint32_t bulk = (uint32_t)((bytes + 15) & ~(int64_t)15);
-        fence_proxy_async();
-        mbar_expect_tx(&ws.mbar[b], bulk);
-        tma_load_1d(ws.win[b], a.h + g, bulk, &ws.mbar[b]);
+      if (g + SUPER <= a.n) {  // the common case: a whole window
+        mbar_expect_tx(&ws.mbar[b], (uint32_t)SUPER);
+        tma_load_1d(ws.win[b], a.h + g, (uint32_t)SUPER, &ws.mbar[b]);
       } else {
-        mbar_arrive(&ws.mbar[b]);
+        const int64_t left = a.n - g;
+        if (left > 0) {
+          // whole 16-byte blocks: the last block may run up to 15 bytes past n, inside the caller's
+          // 16-byte aligned allocation granule; those bytes are masked out (process_tiles, nv)
+          const uint32_t bulk = (uint32_t)((left + 15) & ~(int64_t)15);
+          mbar_expect_tx(&ws.mbar[b], bulk);
+          tma_load_1d(ws.win[b], a.h + g, bulk, &ws.mbar[b]);
+        } else {
+          mbar_arrive(&ws.mbar[b]);
+        }
       }
     }
   };
@@ -968,6 +974,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
   while (cur < a.nchunks) {
     // one pass over the chunk: staged (normal) or, after a staging overflow, with direct stores
     const int64_t cbeg = cur * (int64_t)CHUNKB;
+    const bool whole = cbeg + (CHUNKB + TILE - STRIDE) <= a.n;  // every window of the chunk lies inside the input
     Emit em{&a, ws.stS[sb], ws.stE[sb], cbeg, goff, direct};
     unsigned cnt = 0;
     for (int it = 0; it < ITERS; it++) {
@@ -986,7 +993,12 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       }
       wait(kb);
       const int64_t wg = cbeg + (int64_t)it * (NT * STRIDE);
-      if (wg < a.n) process_tiles(a, em, ws.win[kb], wg, cnt, lane);
+      int nv = SUPER;
+      if (!whole) {
+        const int64_t left = a.n - wg;
+        nv = left >= SUPER ? SUPER : (left > 0 ? (int)left : 0);
+      }
+      if (nv > 0) process_tiles(a, em, ws.win[kb], wg, nv, wg == 0, cnt, lane);
       kb ^= 1;
     }
     if (a.mode != M_FINDALL) {
