@@ -120,6 +120,28 @@ __device__ __forceinline__ uint32_t mad_fma(uint32_t x, uint32_t one, uint32_t k
 }
 #endif
 
+// one step of an inclusive warp scan: x += (value of lane - d), lanes below d keep x.  The shuffle's
+// own "source lane in range" predicate guards the add: no lane compare, no select.
+__device__ __forceinline__ uint32_t scan_step(uint32_t x, int d, int lane) {
+#if defined(CGX_CPU_SIM) || !defined(__CUDA_ARCH__)
+  const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+  return lane >= d ? x + y : x;
+#else
+  uint32_t r;
+  asm volatile(
+      "{\n"
+      ".reg .u32 t;\n"
+      ".reg .pred p;\n"
+      "shfl.sync.up.b32 t|p, %1, %2, 0, 0xffffffff;\n"
+      "mov.u32 %0, %1;\n"
+      "@p add.u32 %0, %1, t;\n"
+      "}\n"
+      : "=&r"(r)
+      : "r"(x), "r"(d));
+  return r;
+#endif
+}
+
 // ---- 2048-bit vectors across the warp: lane l holds word l -------------------------------------
 // markers move one position towards higher bit indices; `in` enters bit 0 of lane 0
 __device__ __forceinline__ uint64_t shl1(uint64_t m, int lane, uint32_t in) {
@@ -572,16 +594,29 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
           uint16_t* pe_ = em.stE + cnt + exE;
           const unsigned ps = __popcll(sb), pe = __popcll(eb);
           const unsigned rounds = __reduce_max_sync(FULL, ps > pe ? ps : pe);
+          // straight-line rounds on 32-bit halves: the half that still has bits is picked by
+          // select, the stores are predicated (no divergent branches, half the 64-bit arithmetic)
+          uint32_t slo = (uint32_t)sb, shi = (uint32_t)(sb >> 32), elo = (uint32_t)eb, ehi = (uint32_t)(eb >> 32);
           for (unsigned j = 0; j < rounds; j++) {
-            if (sb) {
-              const int b = __ffsll((long long)sb) - 1;
-              sb &= sb - 1;
-              *ps_++ = (uint16_t)(rel0 + b);
+            {
+              const bool any = (slo | shi) != 0u, l = slo != 0u;
+              const uint32_t w = l ? slo : shi;
+              const int pos = rel0 + (l ? 0 : 32) + (__ffs((int)w) - 1);
+              if (any) *ps_ = (uint16_t)pos;
+              ps_ += any ? 1 : 0;
+              const uint32_t w2 = w & (w - 1u);
+              slo = l ? w2 : 0u;
+              shi = l ? shi : w2;
             }
-            if (eb) {
-              const int b = __ffsll((long long)eb) - 1;
-              eb &= eb - 1;
-              *pe_++ = (uint16_t)(rel0 + b);
+            {
+              const bool any = (elo | ehi) != 0u, l = elo != 0u;
+              const uint32_t w = l ? elo : ehi;
+              const int pos = rel0 + (l ? 0 : 32) + (__ffs((int)w) - 1);
+              if (any) *pe_ = (uint16_t)pos;
+              pe_ += any ? 1 : 0;
+              const uint32_t w2 = w & (w - 1u);
+              elo = l ? w2 : 0u;
+              ehi = l ? ehi : w2;
             }
           }
         }
@@ -737,12 +772,8 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
     const uint32_t va = xa, vb = xb;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t ya = __shfl_up_sync(FULL, xa, d);
-      if (lane >= d) xa += ya;
-      if (NT == 2) {
-        const uint32_t yb = __shfl_up_sync(FULL, xb, d);
-        if (lane >= d) xb += yb;
-      }
+      xa = scan_step(xa, d, lane);
+      if (NT == 2) xb = scan_step(xb, d, lane);
     }
     const uint32_t ta_tot = __shfl_sync(FULL, xa, 31);
     xa -= va;
