@@ -38,13 +38,24 @@ namespace {
 #define CGX_TILES 2
 #endif
 constexpr uint32_t FULL = 0xffffffffu;
-constexpr int FW_WARPS = 7;                    // scanning warps per CTA (8 warps: a multiple of the 4 SM sub-partitions)
-constexpr int FW_THREADS = (FW_WARPS + 1) * 32;  // + one resolver warp (look-back and ordered output)
+// Launch shape (overridable for experiments: CGX_JIT_DEFS="-DCGX_WARPS=31 -DCGX_CTAS=1").
+// Few large CTAs: every CTA spends one warp on the resolver, and the scan is bound by how many
+// scanning warps share an SM's integer pipe (measured, 16 GiB IP scan: 4 x (7+1) warps 2064 GB/s,
+// 2 x (15+1) warps 2464 GB/s at the same 64 registers per thread).
+#ifndef CGX_WARPS
 #if CGX_TILES == 1
-constexpr int FW_CTAS = 4;                     // resident CTAs per SM the kernel is built for (<= 64 registers)
+#define CGX_WARPS 15
 #else
-constexpr int FW_CTAS = 3;                     // (<= 80 registers)
+#define CGX_WARPS 11
 #endif
+#endif
+#ifndef CGX_CTAS
+#define CGX_CTAS 2
+#endif
+constexpr int FW_WARPS = CGX_WARPS;              // scanning warps per CTA
+constexpr int FW_THREADS = (FW_WARPS + 1) * 32;  // + one resolver warp (look-back and ordered output)
+constexpr int FW_CTAS = CGX_CTAS;                // resident CTAs per SM the kernel is built for
+static_assert(FW_WARPS <= 31, "one CTA holds at most 31 scanning warps and the resolver");
 constexpr int TILE = 2048;              // window bytes of one tile (64 per lane)
 constexpr int STRIDE = 1984;            // bytes between tile origins (31 pieces)
 constexpr int TPC = 8;                  // tiles per chunk
@@ -597,6 +608,7 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
           // straight-line rounds on 32-bit halves: the half that still has bits is picked by
           // select, the stores are predicated (no divergent branches, half the 64-bit arithmetic)
           uint32_t slo = (uint32_t)sb, shi = (uint32_t)(sb >> 32), elo = (uint32_t)eb, ehi = (uint32_t)(eb >> 32);
+#pragma unroll 1
           for (unsigned j = 0; j < rounds; j++) {
             {
               const bool any = (slo | shi) != 0u, l = slo != 0u;
@@ -882,14 +894,19 @@ __device__ __forceinline__ void write_out(const ScanArgs& a, const WarpSmem& ws,
 // before it: both need every earlier count), waits for its offset, stores its matches, frees the slot.
 __device__ void resolver_warp(const ScanArgs& a, CtaSmem& cs, int lane) {
   for (;;) {
-    // lane l looks at slot l (warp l >> 1, buffer l & 1)
+    // lane l looks at slots l and l + 32 (slot s = warp s >> 1, buffer s & 1)
     int64_t mine = (int64_t)1 << 62;
+    int myslot = 0;
     bool all_done = true;
-    if (lane < 2 * FW_WARPS) {
-      const Mail& m = cs.mail[lane >> 1][lane & 1];
-      all_done = cs.done[lane >> 1] != 0;  // read BEFORE the slot: a warp hands over, then sets done
+#pragma unroll
+    for (int s = lane; s < 2 * FW_WARPS; s += 32) {
+      const Mail& m = cs.mail[s >> 1][s & 1];
+      all_done = all_done && cs.done[s >> 1] != 0;  // read BEFORE the slot: a warp hands over, then sets done
       cgx_fence_block();
-      if (m.state == 1) mine = m.chunk;
+      if (m.state == 1 && m.chunk < mine) {
+        mine = m.chunk;
+        myslot = s;
+      }
     }
     int64_t best = mine;
 #pragma unroll
@@ -902,7 +919,7 @@ __device__ void resolver_warp(const ScanArgs& a, CtaSmem& cs, int lane) {
       cgx_idle();  // nothing handed over: a chunk takes tens of microseconds to scan
       continue;
     }
-    const int slot = __ffs((int)__ballot_sync(FULL, mine == best)) - 1;
+    const int slot = __shfl_sync(FULL, myslot, __ffs((int)__ballot_sync(FULL, mine == best)) - 1);
     cgx_fence_block();
     const unsigned cnt = cs.mail[slot >> 1][slot & 1].cnt;
     const unsigned long long excl = lb_resolve(a, best, lane);
@@ -934,6 +951,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     cs.mail[tid >> 1][tid & 1].state = 0;
     cs.done[tid >> 1] = 0;
   }
+  static_assert(2 * FW_WARPS <= FW_THREADS, "one thread per mail slot at start-up");
   if (warp < FW_WARPS && lane == 0) {
     mbar_init(&cs.w[warp].mbar[0], 1);
     mbar_init(&cs.w[warp].mbar[1], 1);
