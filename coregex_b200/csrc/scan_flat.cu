@@ -89,9 +89,10 @@ struct WarpSmem {
 };
 // a scanned chunk handed from a scanning warp to the CTA's resolver warp (one slot per staging buffer)
 struct Mail {
-  volatile int state;  // 0 = slot and staging buffer free, 1 = chunk waits for its offset
+  volatile int state;  // 0 = slot and staging buffer free, 1 = chunk waits for its offset, 2 = offset known
   unsigned cnt;
   int64_t chunk;
+  unsigned long long excl;  // state 2: global index of the chunk's first match
 };
 struct CtaSmem {
   WarpSmem w[FW_WARPS];
@@ -891,11 +892,13 @@ __device__ __forceinline__ void write_out(const ScanArgs& a, const WarpSmem& ws,
 }
 
 // The resolver warp: takes the oldest handed-over chunk of its CTA (a younger one cannot resolve
-// before it: both need every earlier count), waits for its offset, stores its matches, frees the slot.
+// before it: both need every earlier count), waits for its offset and hands the offset back; the
+// scanning warp stores its own staged matches when it next needs the buffer.  (Storing them here
+// made this warp the bottleneck of a 15-warp CTA: 336 instructions per chunk, always busy.)
 __device__ void resolver_warp(const ScanArgs& a, CtaSmem& cs, int lane) {
   for (;;) {
     // lane l looks at slots l and l + 32 (slot s = warp s >> 1, buffer s & 1)
-    int64_t mine = (int64_t)1 << 62;
+    unsigned mine = 0xFFFFFFFFu;  // chunk numbers are 32-bit tickets
     int myslot = 0;
     bool all_done = true;
 #pragma unroll
@@ -903,31 +906,24 @@ __device__ void resolver_warp(const ScanArgs& a, CtaSmem& cs, int lane) {
       const Mail& m = cs.mail[s >> 1][s & 1];
       all_done = all_done && cs.done[s >> 1] != 0;  // read BEFORE the slot: a warp hands over, then sets done
       cgx_fence_block();
-      if (m.state == 1 && m.chunk < mine) {
-        mine = m.chunk;
+      if (m.state == 1 && (unsigned)m.chunk < mine) {
+        mine = (unsigned)m.chunk;
         myslot = s;
       }
     }
-    int64_t best = mine;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-      const int64_t o = __shfl_xor_sync(FULL, best, d);
-      best = o < best ? o : best;
-    }
-    if (best == ((int64_t)1 << 62)) {
+    const unsigned best = __reduce_min_sync(FULL, mine);
+    if (best == 0xFFFFFFFFu) {
       if (__all_sync(FULL, all_done)) return;
       cgx_idle();  // nothing handed over: a chunk takes tens of microseconds to scan
       continue;
     }
     const int slot = __shfl_sync(FULL, myslot, __ffs((int)__ballot_sync(FULL, mine == best)) - 1);
-    cgx_fence_block();
-    const unsigned cnt = cs.mail[slot >> 1][slot & 1].cnt;
-    const unsigned long long excl = lb_resolve(a, best, lane);
-    write_out(a, cs.w[slot >> 1], slot & 1, best, cnt, excl, lane);
-    __syncwarp();
+    const unsigned long long excl = lb_resolve(a, (int64_t)best, lane);
     if (lane == 0) {
+      Mail& m = cs.mail[slot >> 1][slot & 1];
+      m.excl = excl;
       cgx_fence_block();
-      cs.mail[slot >> 1][slot & 1].state = 0;
+      m.state = 2;
     }
   }
 }
@@ -1000,11 +996,25 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     mbar_wait(&ws.mbar[b], (phase >> b) & 1u);
     phase ^= 1u << b;
   };
-  // is staging buffer b free (its previous chunk stored by the resolver)?
-  auto stage_free = [&](int b) -> bool {
-    int st = 0;
-    if (lane == 0) st = cs.mail[warp][b].state;
-    return __shfl_sync(FULL, st, 0) == 0;
+  // Stores the chunk staged in buffer b (if any) once the resolver has supplied its offset;
+  // returns whether the buffer is free afterwards.  Blocking, or one look.
+  auto flush = [&](int b, bool block) -> bool {
+    Mail& m = cs.mail[warp][b];
+    for (;;) {
+      int st = 0;
+      if (lane == 0) st = m.state;
+      st = __shfl_sync(FULL, st, 0);
+      if (st == 0) return true;
+      if (st == 2) break;
+      if (!block) return false;
+      cgx_backoff();
+    }
+    cgx_fence_block();
+    write_out(a, ws, b, m.chunk, m.cnt, m.excl, lane);
+    __syncwarp();
+    if (lane == 0) m.state = 0;
+    __syncwarp();
+    return true;
   };
 
   // Rule that keeps the look-back free of convoys: a warp only ever WAITS (for a staging buffer,
@@ -1033,7 +1043,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         issue(cur, it + 1, kb ^ 1);
       } else {
         if (nxt == none &&
-            (a.mode != M_FINDALL || direct || (cnt <= (unsigned)CAP && stage_free(sb ^ 1))))
+            (a.mode != M_FINDALL || direct || (cnt <= (unsigned)CAP && flush(sb ^ 1, false))))
           nxt = take_ticket();
         if (nxt != none && nxt < a.nchunks) {
           issue(nxt, 0, kb ^ 1);
@@ -1082,7 +1092,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         m.state = 1;
       }
       sb ^= 1;
-      while (!stage_free(sb)) cgx_backoff();  // (no unfinished ticket is held here unless the buffer was free)
+      flush(sb, true);  // (no unfinished ticket is held here unless the buffer was free)
     }
     direct = false;
     if (nxt == none) nxt = take_ticket();
@@ -1093,6 +1103,10 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     prefetched = false;
     cur = nxt;
     nxt = none;
+  }
+  if (a.mode == M_FINDALL) {
+    flush(sb, true);
+    flush(sb ^ 1, true);
   }
   __syncwarp();
   if (lane == 0) {

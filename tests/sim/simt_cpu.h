@@ -176,6 +176,13 @@ inline unsigned __reduce_max_sync(unsigned, unsigned v) {
   return r;
 }
 
+inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+  const uint64_t* s = sim::exchange(v);
+  unsigned r = 0xffffffffu;
+  for (int i = 0; i < 32; i++) r = (unsigned)s[i] < r ? (unsigned)s[i] : r;
+  return r;
+}
+
 // ---- scalar intrinsics -----------------------------------------------------------------------------
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
@@ -219,6 +226,11 @@ inline T __ldg(const T* p) {
 inline unsigned atomicAdd(unsigned* p, unsigned v) {
   unsigned o = *p;
   *p = o + v;
+  return o;
+}
+inline int atomicCAS(int* p, int cmp, int val) {
+  const int o = *p;
+  if (o == cmp) *p = val;
   return o;
 }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
