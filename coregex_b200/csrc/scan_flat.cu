@@ -166,8 +166,7 @@ __device__ __forceinline__ uint64_t shl1(uint64_t m, int lane, uint32_t in) {
 // form assumes that no word propagates: with s a subset of cc (a marker can only stand on a byte
 // of the class) a word's sum is all ones only if the class word itself is all ones — 64 class
 // bytes in one lane's piece — which process_tiles tests once per tile; then the carry into a word
-// is just the carry out of its neighbour: one ballot, 6 ALU-pipe instructions fewer.
-// prevbit = bit (lane - 1), 0 for lane 0.
+// is just the carry out of its neighbour: no ballot at all, 8 ALU-pipe instructions fewer.
 // The same shift for the marker passes, where what enters bit 0 of lane 0 does not matter (lane 0
 // keeps the top bit of its own word): in the right-to-left pass that bit stands for the byte past
 // the window, and nothing can travel from there to an owned start without crossing the sync byte
@@ -179,11 +178,32 @@ __device__ __forceinline__ uint64_t shl1x(uint64_t m) {
   const uint32_t dn = __shfl_up_sync(FULL, hi, 1);
   return mk64(__funnelshift_l(lo, hi, 1), __funnelshift_l(dn, lo, 1));
 }
+// 64-bit a + b and its carry out as a 0/1 register: the carry comes straight from the adder's flag
+// (IADD3 / IADD3.X / IADD3.X) instead of a 64-bit compare (two ISETP).
+__device__ __forceinline__ uint64_t add_carry(uint64_t x, uint64_t y, uint32_t& carry) {
+#if defined(CGX_CPU_SIM) || !defined(__CUDA_ARCH__)
+  const uint64_t sum = x + y;
+  carry = sum < x ? 1u : 0u;
+  return sum;
+#else
+  uint32_t lo, hi;
+  asm("add.cc.u32 %0, %3, %5;\n\taddc.cc.u32 %1, %4, %6;\n\taddc.u32 %2, 0, 0;"
+      : "=r"(lo), "=r"(hi), "=r"(carry)
+      : "r"((uint32_t)x), "r"((uint32_t)(x >> 32)), "r"((uint32_t)y), "r"((uint32_t)(y >> 32)));
+  return mk64(hi, lo);
+#endif
+}
 template <bool EXACT>
 __device__ __forceinline__ uint64_t add2048(uint64_t s, uint64_t cc, int lane, uint32_t prevbit) {
+  if (!EXACT) {
+    // the carry into a word is the carry out of the word below: one shuffle.  Lane 0 receives its
+    // own carry — a stray marker at the first bit, harmless for the reasons given at shl1x.
+    uint32_t g;
+    const uint64_t sum = add_carry(s, cc, g);
+    return sum + __shfl_up_sync(FULL, g, 1);
+  }
   const uint64_t sum = s + cc;
   const uint32_t G = __ballot_sync(FULL, sum < s);
-  if (!EXACT) return sum + ((G & prevbit) ? 1ull : 0ull);
   const uint32_t P = __ballot_sync(FULL, sum == ~0ull);
   const uint32_t A = G | P;
   const uint32_t carries = A ^ G ^ (A + G);  // bit l = carry into word l
@@ -200,15 +220,20 @@ __device__ __forceinline__ uint64_t flip(uint64_t x) {
 #ifdef CGX_JIT
 #include "cgx_jit_prog.h"  // generated per pattern (host/engine.cpp JitHeader), compiled by csrc/jit.cpp
 #endif
-// 8 flag words (bit 7 of a byte set <=> byte in class) -> bit-reversed 32-bit mask (bit 31-b <=> byte b)
-__device__ __forceinline__ uint32_t pack_rev(const uint32_t* fl) {
-  uint32_t acc[4];
-#pragma unroll
-  for (int a = 0; a < 4; a++) {
-    acc[a] = __dp4a(fl[2 * a], 0x10204080u, 0u);
-    acc[a] = __dp4a(fl[2 * a + 1], 0x01020408u, acc[a]);
-  }
-  return (acc[0] << 17) | (acc[1] << 9) | (acc[2] << 1) | (acc[3] >> 7);
+// 8 flag words (bit 7 of a byte set <=> byte in class) -> bit-reversed 32-bit mask (bit 31-b <=> byte b).
+// Each dp4a pair gathers 8 flags into bits 7..14; the groups are chained through the accumulator
+// input (shifted by 8 each time: IMAD.SHL, FMA pipe) and the last one is joined by a multiply-add,
+// so the whole pack costs one ALU-pipe instruction (the final right shift).
+__device__ __forceinline__ uint32_t pack_rev(const uint32_t* fl, uint32_t one) {
+  uint32_t acc = __dp4a(fl[0], 0x10204080u, 0u);
+  acc = __dp4a(fl[1], 0x01020408u, acc);
+  acc = __dp4a(fl[2], 0x10204080u, acc << 8);
+  acc = __dp4a(fl[3], 0x01020408u, acc);
+  acc = __dp4a(fl[4], 0x10204080u, acc << 8);
+  acc = __dp4a(fl[5], 0x01020408u, acc);  // 24 flags in bits 7..30
+  uint32_t last = __dp4a(fl[6], 0x10204080u, 0u);
+  last = __dp4a(fl[7], 0x01020408u, last);
+  return mad_fma(acc, one + one, last >> 7);
 }
 
 template <int C>
@@ -244,7 +269,7 @@ __device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t
     }
   }
 #endif
-  return mk64(pack_rev(fl), pack_rev(fl + 8));  // bytes 0..31 in the high word
+  return mk64(pack_rev(fl, one), pack_rev(fl + 8, one));  // bytes 0..31 in the high word
 }
 
 // Class bitmaps (reversed orientation) of the 64-byte piece at `p`: 4 x LDS.128.  Pieces are 64 B
@@ -579,17 +604,18 @@ __device__ __forceinline__ int own_open_lim(const TileOut& t, int lane) {
   return a > z1 ? a : z1;
 }
 
-__device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const TileOut& t, int64_t tile_g,
+// trel = position of the tile's first byte relative to the chunk
+__device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const TileOut& t, int trel,
                                             unsigned totS, unsigned totE, unsigned exS, unsigned exE, bool bad,
                                             unsigned& cnt, int lane) {
   if (!t.owned) return;
-  const int64_t stop_min = tile_g + STRIDE;
   if (bad || totS != totE) {
-    cnt += serial_region(a, em, tile_g + own_start(t, lane), stop_min, cnt, lane);
+    const int64_t tile_g = em.cb + trel;
+    cnt += serial_region(a, em, tile_g + own_start(t, lane), tile_g + STRIDE, cnt, lane);
     return;
   }
   if (totS) {
-    const int rel0 = (int)(tile_g - em.cb) + 64 * lane;
+    const int rel0 = trel + 64 * lane;
     if (a.mode == M_FINDALL) {
 #ifndef CGX_EMIT_V
 #define CGX_EMIT_V 2
@@ -658,7 +684,7 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
     }
     cnt += totS;
   }
-  if (t.open) cnt += serial_region(a, em, tile_g + own_open_lim(t, lane), stop_min, cnt, lane);
+  if (t.open) cnt += serial_region(a, em, em.cb + trel + own_open_lim(t, lane), em.cb + trel + STRIDE, cnt, lane);
 }
 
 // bytes at or beyond the end of input belong to no class (last chunk only: kept out of line)
@@ -684,9 +710,9 @@ void mask_tail(uint64_t (&ca)[4], uint64_t (&cb)[4], int64_t nv, int lane) {
   }
 }
 
-// Processes the NT tiles whose windows start at `win` (global position wg), win + STRIDE.
+// Processes the NT tiles whose windows start at `win` (position wrel in the chunk), win + STRIDE.
 // nv = valid bytes from the start of tile A, clamped to SUPER; first = the window starts the haystack.
-__device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const uint8_t* win, int64_t wg, int nv,
+__device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const uint8_t* win, int wrel, int nv,
                                               bool first, unsigned& cnt, int lane) {
   const FlatDev& f = a.flat;
   const int piece = 31 - lane;
@@ -760,6 +786,7 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
       return;
     }
     // open tails may still hide a match
+    const int64_t wg = em.cb + wrel;
     if (ta.owned && ta.open) cnt += serial_region(a, em, wg + own_open_lim(ta, lane), wg + STRIDE, cnt, lane);
     if (NT == 2 && tb.owned && tb.open)
       cnt += serial_region(a, em, wg + STRIDE + own_open_lim(tb, lane), wg + 2 * STRIDE, cnt, lane);
@@ -810,8 +837,8 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
       badb = __any_sync(FULL, wb);
     }
   }
-  finish_tile(a, em, ta, wg, totSa, totEa, exSa, exEa, bad, cnt, lane);
-  if (NT == 2) finish_tile(a, em, tb, wg + STRIDE, totSb, totEb, exSb, exEb, badb, cnt, lane);
+  finish_tile(a, em, ta, wrel, totSa, totEa, exSa, exEa, bad, cnt, lane);
+  if (NT == 2) finish_tile(a, em, tb, wrel + STRIDE, totSb, totEb, exSb, exEb, badb, cnt, lane);
 }
 
 // ---- two-level look-back ------------------------------------------------------------------------------
@@ -1034,13 +1061,23 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     // one pass over the chunk: staged (normal) or, after a staging overflow, with direct stores
     const int64_t cbeg = cur * (int64_t)CHUNKB;
     const bool whole = cbeg + (CHUNKB + TILE - STRIDE) <= a.n;  // every window of the chunk lies inside the input
+    const uint8_t* csrc = a.h + cbeg;
+    const int chunk0 = __shfl_sync(FULL, cur == 0 ? 1 : 0, 0);  // (one register, not a 64-bit compare per use)
     Emit em{&a, ws.stS[sb], ws.stE[sb], cbeg, goff, direct};
     unsigned cnt = 0;
     for (int it = 0; it < ITERS; it++) {
       // the other window buffer was last read an iteration ago: refill it now
       __syncwarp();
       if (it + 1 < ITERS) {
-        issue(cur, it + 1, kb ^ 1);
+        if (whole) {
+          // a whole window of a chunk that lies inside the input: no bounds to look at
+          if (lane == 0) {
+            mbar_expect_tx(&ws.mbar[kb ^ 1], (uint32_t)SUPER);
+            tma_load_1d(ws.win[kb ^ 1], csrc + (it + 1) * (NT * STRIDE), (uint32_t)SUPER, &ws.mbar[kb ^ 1]);
+          }
+        } else {
+          issue(cur, it + 1, kb ^ 1);
+        }
       } else {
         if (nxt == none &&
             (a.mode != M_FINDALL || direct || (cnt <= (unsigned)CAP && flush(sb ^ 1, false))))
@@ -1051,13 +1088,13 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         }
       }
       wait(kb);
-      const int64_t wg = cbeg + (int64_t)it * (NT * STRIDE);
+      const int wrel = it * (NT * STRIDE);
       int nv = SUPER;
       if (!whole) {
-        const int64_t left = a.n - wg;
+        const int64_t left = a.n - (cbeg + wrel);
         nv = left >= SUPER ? SUPER : (left > 0 ? (int)left : 0);
       }
-      if (nv > 0) process_tiles(a, em, ws.win[kb], wg, nv, wg == 0, cnt, lane);
+      if (nv > 0) process_tiles(a, em, ws.win[kb], wrel, nv, (chunk0 & (it == 0 ? 1 : 0)) != 0, cnt, lane);
       kb ^= 1;
     }
     if (a.mode != M_FINDALL) {
