@@ -275,10 +275,12 @@ __device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t
 // Class bitmaps (reversed orientation) of the 64-byte piece at `p`: 4 x LDS.128.  Pieces are 64 B
 // apart, so with a straight quarter order one LDS.128 of the warp touches 8 of the 32 banks (4x the
 // wavefronts).  CGX_ROT=1 reads the quarters in the order (j + rot) & 3, which covers all banks
-// evenly; packing them as if they were in order yields each bitmap rotated by 16*rot bits, which two
-// byte permutes per class undo (integer-pipe work traded for shared-memory wavefronts).
+// evenly, and undoes the resulting rotation of each bitmap with two byte permutes per class.  That
+// trades ~10 ALU-pipe instructions per tile for shared-memory wavefronts; the kernel is bound by
+// the ALU pipe and the LSU pipe is at 17 %, so the straight order is the default (measured:
+// 2584 -> 2689 GB/s).
 #ifndef CGX_ROT
-#define CGX_ROT 1
+#define CGX_ROT 0
 #endif
 __device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* p, int lane, uint32_t one,
                                                uint64_t (&cm)[4]) {
