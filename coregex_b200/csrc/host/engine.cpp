@@ -277,8 +277,24 @@ std::string JitHeader(const FlatDev& f) {
   add("#define CGX_JIT_RUNSTART %d\n", f.bs_runstart);
   add("#define CGX_JIT_MIDRUN %d\n", f.bs_midrun_check);
   add("#define CGX_JIT_REV_INIT %d\n", f.rev_init_class);
-  o += "#define CGX_JIT_REV_PASS(STEP)";
-  for (int k = 0; k < f.rev_nops; k++) add(" STEP(%d, %d)", f.rev_ops[k] & 3, f.rev_ops[k] >> 2);
+  // right to left, a single byte of class A followed by a run of class B (`B+ A` in the pattern) is
+  // one fused step over the precomputed bitmap "A right after B": one 2-position shift, no
+  // intermediate marker set (scan_flat.cu rev_fused)
+  std::string fused_defs;
+  o += "#define CGX_JIT_REV_PASS(STEP, FUSE)";
+  for (int k = 0; k < f.rev_nops; k++) {
+    const int kind = f.rev_ops[k] & 3, cls = f.rev_ops[k] >> 2;
+    if (kind == 0 && k + 1 < f.rev_nops && (f.rev_ops[k + 1] & 3) == 1) {
+      const int cls2 = f.rev_ops[k + 1] >> 2;
+      add(" FUSE(%d, %d)", cls, cls2);
+      snprintf(buf, sizeof buf, " DEF(%d, %d)", cls, cls2);
+      if (fused_defs.find(buf) == std::string::npos) fused_defs += buf;
+      k++;
+    } else {
+      add(" STEP(%d, %d)", kind, cls);
+    }
+  }
+  o += "\n#define CGX_JIT_REV_FUSED(DEF)" + fused_defs;
   o += "\n#define CGX_JIT_FWD_PASS(STEP)";
   for (int k = 0; k < f.fwd_nops; k++) add(" STEP(%d, %d)", f.fwd_ops[k] & 3, f.fwd_ops[k] >> 2);
   o += "\ntemplate <int C> __device__ __forceinline__ uint32_t cgx_jit_flags(uint32_t w, uint32_t one) { return 0u; }\n";

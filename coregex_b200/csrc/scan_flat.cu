@@ -37,6 +37,10 @@ namespace {
 #ifndef CGX_TILES
 #define CGX_TILES 2
 #endif
+#ifndef CGX_IT_UNROLL
+#define CGX_IT_UNROLL 1  // 2: both window buffers in one loop body (constant buffer index, twice the hot code)
+#endif
+constexpr int IT_UNROLL = CGX_IT_UNROLL;
 constexpr uint32_t FULL = 0xffffffffu;
 // Launch shape (overridable for experiments: CGX_JIT_DEFS="-DCGX_WARPS=31 -DCGX_CTAS=1").
 // Few large CTAs: every CTA spends one warp on the resolver, and the scan is bound by how many
@@ -193,6 +197,11 @@ __device__ __forceinline__ uint64_t add_carry(uint64_t x, uint64_t y, uint32_t& 
   return mk64(hi, lo);
 #endif
 }
+__device__ __forceinline__ uint64_t shl2x(uint64_t m) {  // shl1x twice
+  const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+  const uint32_t dn = __shfl_up_sync(FULL, hi, 1);
+  return mk64(__funnelshift_l(lo, hi, 2), __funnelshift_l(dn, lo, 2));
+}
 template <bool EXACT>
 __device__ __forceinline__ uint64_t add2048(uint64_t s, uint64_t cc, int lane, uint32_t prevbit) {
   if (!EXACT) {
@@ -344,6 +353,19 @@ __device__ __forceinline__ void rev_step(uint32_t kind, const uint64_t (&ca)[4],
     }
   }
 }
+// `C+ a` seen from the right: one byte of class A, then a run of class C.  q = shl1x(A) & C marks the
+// run bytes that directly follow (in marker direction) a byte of A, so shl1x(shl1x(M) & A) & C ==
+// shl2x(M) & q: the two steps cost one shift.
+template <int C, bool EXACT>
+__device__ __forceinline__ void rev_fused(const uint64_t (&ca)[4], const uint64_t (&cb)[4], uint64_t qa, uint64_t qb,
+                                          uint64_t& Ma, uint64_t& Mb, int lane, uint32_t prevbit) {
+  const uint64_t ua = shl2x(Ma) & qa;
+  Ma = (~add2048<EXACT>(ua, ca[C], lane, prevbit) & ca[C]) | ua;
+  if (NT == 2) {
+    const uint64_t ub = shl2x(Mb) & qb;
+    Mb = (~add2048<EXACT>(ub, cb[C], lane, prevbit) & cb[C]) | ub;
+  }
+}
 // Left to right (forward orientation): T = positions a marker stands at before item k; the forced
 // greedy choice (take the whole run / take the optional byte whenever it is there).
 template <int C, bool EXACT>
@@ -383,9 +405,17 @@ __device__ __forceinline__ void rev_pass(const FlatDev& f, const uint64_t (&ca)[
 #ifdef CGX_JIT
   Ma = ca[CGX_JIT_REV_INIT];
   Mb = cb[CGX_JIT_REV_INIT];
+#define CGX_QDEF(A, B)                                 \
+  const uint64_t qa##A##_##B = shl1x(ca[A]) & ca[B];   \
+  uint64_t qb##A##_##B = 0ull;                         \
+  if (NT == 2) qb##A##_##B = shl1x(cb[A]) & cb[B];
+  CGX_JIT_REV_FUSED(CGX_QDEF)
 #define CGX_STEP(kind, cls) rev_step<cls, EXACT>(kind, ca, cb, Ma, Mb, lane, prevbit);
-  CGX_JIT_REV_PASS(CGX_STEP)
+#define CGX_FUSE(A, B) rev_fused<B, EXACT>(ca, cb, qa##A##_##B, qb##A##_##B, Ma, Mb, lane, prevbit);
+  CGX_JIT_REV_PASS(CGX_STEP, CGX_FUSE)
 #undef CGX_STEP
+#undef CGX_FUSE
+#undef CGX_QDEF
 #else
   const int init_cls = f.rev_init_class;
   Ma = init_cls == 0 ? ca[0] : init_cls == 1 ? ca[1] : init_cls == 2 ? ca[2] : ca[3];
@@ -1067,6 +1097,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     const int chunk0 = __shfl_sync(FULL, cur == 0 ? 1 : 0, 0);  // (one register, not a 64-bit compare per use)
     Emit em{&a, ws.stS[sb], ws.stE[sb], cbeg, goff, direct};
     unsigned cnt = 0;
+#pragma unroll IT_UNROLL
     for (int it = 0; it < ITERS; it++) {
       // the other window buffer was last read an iteration ago: refill it now
       __syncwarp();
