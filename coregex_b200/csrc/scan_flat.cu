@@ -62,14 +62,14 @@ constexpr int FW_CTAS = CGX_CTAS;                // resident CTAs per SM the ker
 static_assert(FW_WARPS <= 31, "one CTA holds at most 31 scanning warps and the resolver");
 constexpr int TILE = 2048;              // window bytes of one tile (64 per lane)
 constexpr int STRIDE = 1984;            // bytes between tile origins (31 pieces)
-constexpr int TPC = 8;                  // tiles per chunk
+constexpr int TPC = 12;                 // tiles per chunk (per-chunk costs — ticket, count, look-back, hand-over — are paid once per 23.8 KB)
 // tiles evaluated jointly per iteration: 2 gives every warp two independent dependency chains
 // (fewer, fatter warps), 1 halves the hot loop's code and registers (more warps)
 constexpr int NT = CGX_TILES;
 constexpr int ITERS = TPC / NT;         // iterations per chunk
 constexpr int CHUNKB = TPC * STRIDE;    // 15872 bytes owned per chunk
 constexpr int SUPER = (NT - 1) * STRIDE + TILE;  // bytes loaded per iteration (4032 / 2048)
-constexpr int CAP = 256;                // staged matches per chunk
+constexpr int CAP = 384;                // staged matches per chunk
 
 // The pattern-dependent parts exist twice: as an interpreter over ScanArgs::flat (this translation
 // unit as nvcc builds it, and the CPU emulator build), and — when the host JIT-compiles this file

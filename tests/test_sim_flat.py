@@ -15,7 +15,7 @@ import sim_lib
 from oracle_lib import Oracle
 
 IP = r"\d+\.\d+\.\d+\.\d+"
-STRIDE, TILE, CHUNK = 1984, 2048, 8 * 1984
+STRIDE, TILE, CHUNK = 1984, 2048, 12 * 1984
 BACKEND = "sim"
 
 
