@@ -11,22 +11,30 @@
 // lane, this kernel never walks: match STARTS come from a right-to-left marker pass over per-class
 // position bitmaps, match ENDS from a left-to-right pass over the same bitmaps (forced greedy ==
 // leftmost-first because the host proved the pattern deterministic, host/engine.cpp
-// DecideBitstream).  Every warp is autonomous — no CTA barrier anywhere:
+// DecideBitstream).  Every scanning warp is autonomous — no CTA barrier anywhere:
 //
-//   * a warp draws 15.5 KB chunks (8 tiles) from a ticket counter; per iteration it takes one TMA
-//     bulk copy of 4032 B (two overlapping 2 KB tiles) into its own double-buffered window;
-//   * lane l owns a 64-byte piece of each tile: 4 x LDS.128, SWAR range tests, dp4a bit packing -> one 64-bit word per class and tile;
+//   * a warp draws 23.8 KB chunks (12 tiles) from a ticket counter; per iteration it takes one TMA
+//     bulk copy of one 2 KB tile into its own double-buffered window (CGX_TILES=2: two overlapping
+//     tiles evaluated jointly);
+//   * lane l owns a 64-byte piece of the tile: 4 x LDS.128, SWAR range tests (2 LOP3 + 1 IMAD per
+//     word and class), dp4a bit packing -> one 64-bit word per class;
 //   * tiles overlap by one piece (64 B).  A byte that belongs to no class of the pattern can never
 //     be inside a match ("sync byte"), so a tile owns the starts from the first sync byte of its
 //     first piece up to the first sync byte of its last piece: chains of overlapping candidates
 //     (`pos = end` in the reference loop) never cross tiles;
-//   * starts and ends are checked to alternate (prefix parity of S^E).  If they do not (candidates
-//     that overlap, `1.2.3.4.5`), or a span has no sync byte before the window ends, one lane
-//     replays the reference loop over global memory for that region (exact, rare);
-//   * matches are staged per chunk in shared memory (u16 offsets), the chunk's count is published
-//     at once, and a resumable non-blocking decoupled look-back — polled between iterations —
-//     yields the global offset; pairs are stored as int64 in global match order.
+//   * the passes add 2048-bit numbers; a carry crosses a lane boundary by one shuffle (a tile with
+//     a piece made of class bytes only takes the exact two-ballot carry resolution instead);
+//   * starts and ends are checked to alternate (per word, from the rank scan: word_misordered).
+//     If they do not (candidates that overlap, `1.2.3.4.5`), or a span has no sync byte before the
+//     window ends, one lane replays the reference loop over global memory for that region (exact,
+//     rare);
+//   * matches are staged per chunk in shared memory (u16 offsets) and the chunk's count is
+//     published at once.  One resolver warp per CTA performs the decoupled look-back for the
+//     CTA's chunks, oldest first, and hands each offset back; the scanning warp stores its staged
+//     pairs as int64 in global match order when it next needs that staging buffer.
 // Every corpus byte crosses HBM once (+3 % tile overlap served by L2); output is 16 B per match.
+// The kernel is bound by the integer ALU pipe (ncu: alu ~78 %, issue ~81 %), so its inner parts are
+// written for ALU-pipe instruction count; see "pipe-aware primitives" below and DESIGN.md §5.0.
 #include "scan_common.cuh"
 #include "scan_params.h"
 
@@ -90,6 +98,10 @@ struct WarpSmem {
   uint16_t stS[2][CAP];
   uint16_t stE[2][CAP];
   uint64_t mbar[2];
+  // what only the cold paths need of the current chunk (kept out of registers: the hot loop is at
+  // its register limit and was recomputing loop invariants every iteration)
+  int64_t cb;               // global position of the chunk's first byte
+  unsigned long long goff;  // direct: global index of the chunk's first match
 };
 // a scanned chunk handed from a scanning warp to the CTA's resolver warp (one slot per staging buffer)
 struct Mail {
@@ -459,23 +471,22 @@ __device__ __forceinline__ bool word_misordered(uint64_t S, uint64_t E, uint32_t
 // ---- output ------------------------------------------------------------------------------------
 struct Emit {
   const ScanArgs* ap;
-  uint16_t* stS;
-  uint16_t* stE;
-  int64_t cb;               // global position of the chunk's first byte
-  unsigned long long goff;  // direct: global index of the chunk's first match
+  WarpSmem* w;
+  int sb;                   // staging buffer in use
   bool direct;              // store straight to global memory (chunk redone after a staging overflow)
   bool far = false;         // a staged offset did not fit 16 bits
 
+  __device__ __forceinline__ int64_t cb() const { return w->cb; }
   // rel = position relative to the chunk
   __device__ __forceinline__ void put(unsigned idx, int64_t rel, bool is_end) {
     const ScanArgs& a = *ap;
     if (a.mode != M_FINDALL) return;
     if (direct) {
-      const unsigned long long gi = goff + idx;
-      if ((int64_t)gi < a.cap) a.out[2 * gi + (is_end ? 1 : 0)] = cb + a.base + rel;
+      const unsigned long long gi = w->goff + idx;
+      if ((int64_t)gi < a.cap) a.out[2 * gi + (is_end ? 1 : 0)] = w->cb + a.base + rel;
     } else {
       if (rel > 0xFFFF) far = true;
-      else if (idx < (unsigned)CAP) (is_end ? stE : stS)[idx] = (uint16_t)rel;
+      else if (idx < (unsigned)CAP) (is_end ? w->stE[sb] : w->stS[sb])[idx] = (uint16_t)rel;
     }
   }
   // fast path of the fast path: staged FindAll output, offsets known to fit 16 bits
@@ -491,7 +502,7 @@ struct Emit {
   __device__ __forceinline__ void put_bits(uint64_t bits, unsigned idx, int rel0, bool is_end) {
     if (ap->mode != M_FINDALL) return;
     if (!direct) {
-      uint16_t* st = is_end ? stE : stS;
+      uint16_t* st = is_end ? w->stE[sb] : w->stS[sb];
       idx = stage_bits32(st, (uint32_t)bits, idx, rel0);
       stage_bits32(st, (uint32_t)(bits >> 32), idx, rel0 + 32);
       return;
@@ -559,8 +570,8 @@ __device__ __noinline__ unsigned serial_region_cold(const ScanArgs& a, Emit em, 
       if (stop || d >= n) break;
       const int64_t e = dfa_walk_global(a, d);
       if (e >= 0) {
-        em.put(idx0 + added, d - em.cb, false);
-        em.put(idx0 + added, e - em.cb, true);
+        em.put(idx0 + added, d - em.cb(), false);
+        em.put(idx0 + added, e - em.cb(), true);
         added++;
         pos = e > d ? e : d + 1;
       } else {
@@ -642,7 +653,7 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
                                             unsigned& cnt, int lane) {
   if (!t.owned) return;
   if (bad || totS != totE) {
-    const int64_t tile_g = em.cb + trel;
+    const int64_t tile_g = em.cb() + trel;
     cnt += serial_region(a, em, tile_g + own_start(t, lane), tile_g + STRIDE, cnt, lane);
     return;
   }
@@ -660,8 +671,8 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
         // overflowed and will be run again with direct stores (no per-store bound checks).
         if (cnt + totS <= (unsigned)CAP) {
           uint64_t sb = t.S, eb = t.E;
-          uint16_t* ps_ = em.stS + cnt + exS;
-          uint16_t* pe_ = em.stE + cnt + exE;
+          uint16_t* ps_ = em.w->stS[em.sb] + cnt + exS;
+          uint16_t* pe_ = em.w->stE[em.sb] + cnt + exE;
           const unsigned ps = __popcll(sb), pe = __popcll(eb);
           const unsigned rounds = __reduce_max_sync(FULL, ps > pe ? ps : pe);
           // straight-line rounds on 32-bit halves: the half that still has bits is picked by
@@ -699,13 +710,13 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
           if (sb) {
             const int b = __ffsll((long long)sb) - 1;
             sb &= sb - 1;
-            if (is < (unsigned)CAP) em.stS[is] = (uint16_t)(rel0 + b);
+            if (is < (unsigned)CAP) em.w->stS[em.sb][is] = (uint16_t)(rel0 + b);
             is++;
           }
           if (eb) {
             const int b = __ffsll((long long)eb) - 1;
             eb &= eb - 1;
-            if (ie < (unsigned)CAP) em.stE[ie] = (uint16_t)(rel0 + b);
+            if (ie < (unsigned)CAP) em.w->stE[em.sb][ie] = (uint16_t)(rel0 + b);
             ie++;
           }
         }
@@ -716,7 +727,7 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
     }
     cnt += totS;
   }
-  if (t.open) cnt += serial_region(a, em, em.cb + trel + own_open_lim(t, lane), em.cb + trel + STRIDE, cnt, lane);
+  if (t.open) cnt += serial_region(a, em, em.cb() + trel + own_open_lim(t, lane), em.cb() + trel + STRIDE, cnt, lane);
 }
 
 // bytes at or beyond the end of input belong to no class (last chunk only: kept out of line)
@@ -818,7 +829,7 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
       return;
     }
     // open tails may still hide a match
-    const int64_t wg = em.cb + wrel;
+    const int64_t wg = em.cb() + wrel;
     if (ta.owned && ta.open) cnt += serial_region(a, em, wg + own_open_lim(ta, lane), wg + STRIDE, cnt, lane);
     if (NT == 2 && tb.owned && tb.open)
       cnt += serial_region(a, em, wg + STRIDE + own_open_lim(tb, lane), wg + 2 * STRIDE, cnt, lane);
@@ -1095,7 +1106,12 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     const bool whole = cbeg + (CHUNKB + TILE - STRIDE) <= a.n;  // every window of the chunk lies inside the input
     const uint8_t* csrc = a.h + cbeg;
     const int chunk0 = __shfl_sync(FULL, cur == 0 ? 1 : 0, 0);  // (one register, not a 64-bit compare per use)
-    Emit em{&a, ws.stS[sb], ws.stE[sb], cbeg, goff, direct};
+    if (lane == 0) {
+      ws.cb = cbeg;
+      ws.goff = goff;
+    }
+    __syncwarp();
+    Emit em{&a, &ws, sb, direct};
     unsigned cnt = 0;
 #pragma unroll IT_UNROLL
     for (int it = 0; it < ITERS; it++) {
