@@ -102,6 +102,9 @@ struct WarpSmem {
   // its register limit and was recomputing loop invariants every iteration)
   int64_t cb;               // global position of the chunk's first byte
   unsigned long long goff;  // direct: global index of the chunk's first match
+  const uint8_t* csrc;      // the chunk's first byte in global memory
+  int whole;                // every window of the chunk lies inside the input
+  int chunk0;               // the chunk starts the haystack
 };
 // a scanned chunk handed from a scanning warp to the CTA's resolver warp (one slot per staging buffer)
 struct Mail {
@@ -1099,30 +1102,31 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
   int kb = 0, sb = 0;
   if (cur < a.nchunks) issue(cur, 0, 0);
   bool direct = false;
-  unsigned long long goff = 0;
   while (cur < a.nchunks) {
     // one pass over the chunk: staged (normal) or, after a staging overflow, with direct stores
-    const int64_t cbeg = cur * (int64_t)CHUNKB;
-    const bool whole = cbeg + (CHUNKB + TILE - STRIDE) <= a.n;  // every window of the chunk lies inside the input
-    const uint8_t* csrc = a.h + cbeg;
-    const int chunk0 = __shfl_sync(FULL, cur == 0 ? 1 : 0, 0);  // (one register, not a 64-bit compare per use)
-    if (lane == 0) {
-      ws.cb = cbeg;
-      ws.goff = goff;
+    {
+      const int64_t cbeg = cur * (int64_t)CHUNKB;
+      if (lane == 0) {
+        ws.cb = cbeg;
+        ws.csrc = a.h + cbeg;
+        ws.whole = cbeg + (CHUNKB + TILE - STRIDE) <= a.n;
+        ws.chunk0 = cur == 0;
+      }
+      __syncwarp();
     }
-    __syncwarp();
     Emit em{&a, &ws, sb, direct};
     unsigned cnt = 0;
 #pragma unroll IT_UNROLL
     for (int it = 0; it < ITERS; it++) {
       // the other window buffer was last read an iteration ago: refill it now
       __syncwarp();
+      const int whole = ws.whole;
       if (it + 1 < ITERS) {
         if (whole) {
           // a whole window of a chunk that lies inside the input: no bounds to look at
           if (lane == 0) {
             mbar_expect_tx(&ws.mbar[kb ^ 1], (uint32_t)SUPER);
-            tma_load_1d(ws.win[kb ^ 1], csrc + (it + 1) * (NT * STRIDE), (uint32_t)SUPER, &ws.mbar[kb ^ 1]);
+            tma_load_1d(ws.win[kb ^ 1], ws.csrc + (it + 1) * (NT * STRIDE), (uint32_t)SUPER, &ws.mbar[kb ^ 1]);
           }
         } else {
           issue(cur, it + 1, kb ^ 1);
@@ -1140,10 +1144,10 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       const int wrel = it * (NT * STRIDE);
       int nv = SUPER;
       if (!whole) {
-        const int64_t left = a.n - (cbeg + wrel);
+        const int64_t left = a.n - (ws.cb + wrel);
         nv = left >= SUPER ? SUPER : (left > 0 ? (int)left : 0);
       }
-      if (nv > 0) process_tiles(a, em, ws.win[kb], wrel, nv, (chunk0 & (it == 0 ? 1 : 0)) != 0, cnt, lane);
+      if (nv > 0) process_tiles(a, em, ws.win[kb], wrel, nv, it == 0 && ws.chunk0 != 0, cnt, lane);
       kb ^= 1;
     }
     if (a.mode != M_FINDALL) {
@@ -1156,8 +1160,9 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       if (cnt > (unsigned)CAP || __any_sync(FULL, em.far)) {
         // more matches than the staging buffer holds: get the offset now and run the chunk again
         // with direct stores.  A prefetched window of the next chunk is dropped and re-issued later.
-        goff = lb_resolve(a, cur, lane);
+        const unsigned long long goff = lb_resolve(a, cur, lane);
         if (lane == 0) {
+          ws.goff = goff;
           atomicAdd(&a.total[3], 1ull);  // diagnostics: chunks redone with direct stores
           if (cur == a.nchunks - 1) a.total[0] = goff + cnt;
         }
