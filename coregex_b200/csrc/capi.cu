@@ -284,6 +284,10 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   }();
   const bool use_flat = c.kind == ENG_DFA && c.flat.bs_ok && re->bitstream && bs_env;
   const int64_t nchunks = use_flat ? scan_flat_chunks((int64_t)len) : scan_dfa_chunks((int64_t)len);
+  if (nchunks >= 0xFFFF0000ll) {
+    g_last_error = "haystack too large for one scan call (32-bit chunk tickets); shard it";
+    return CGX_ERR_ARGS;
+  }
   int r;
   if ((r = re->d_ticket_total.ensure(64))) return r;
   // look-back words: one per chunk, then (bitstream kernel) two words per 32 chunks

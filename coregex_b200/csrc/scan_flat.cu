@@ -957,10 +957,15 @@ __device__ __forceinline__ void write_out(const ScanArgs& a, const WarpSmem& ws,
   const int64_t b = chunk * (int64_t)CHUNKB + a.base;
   const uint16_t* ss = ws.stS[sb];
   const uint16_t* se = ws.stE[sb];
-  for (unsigned i = lane; i < cnt; i += 32) {
-    const unsigned long long gi = excl + i;
-    if ((int64_t)gi < a.cap)
-      *reinterpret_cast<longlong2*>(a.out + 2 * gi) = make_longlong2(b + ss[i], b + se[i]);
+  if ((int64_t)(excl + cnt) <= a.cap) {  // the usual case: the whole chunk fits the output
+    longlong2* o = reinterpret_cast<longlong2*>(a.out) + excl;
+    for (unsigned i = lane; i < cnt; i += 32) o[i] = make_longlong2(b + ss[i], b + se[i]);
+  } else {
+    for (unsigned i = lane; i < cnt; i += 32) {
+      const unsigned long long gi = excl + i;
+      if ((int64_t)gi < a.cap)
+        *reinterpret_cast<longlong2*>(a.out + 2 * gi) = make_longlong2(b + ss[i], b + se[i]);
+    }
   }
 }
 
@@ -1095,14 +1100,16 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
   // ticket anybody holds is being scanned, so every count a waiter needs arrives within one chunk
   // time.  Hence the next ticket is drawn early (for the prefetch of its first window) only when
   // the staging buffer it will need is already free.
-  const int64_t none = (int64_t)1 << 40;
-  int64_t cur = take_ticket();
-  int64_t nxt = none;
+  // chunk numbers are 32-bit tickets (the host refuses haystacks of more than 0xFFFF0000 chunks)
+  const unsigned none = 0xFFFFFFFEu;
+  const unsigned nch = (unsigned)a.nchunks;
+  unsigned cur = take_ticket();
+  unsigned nxt = none;
   bool prefetched = false;  // window 0 of `nxt` is in flight into the buffer the next chunk starts with
   int kb = 0, sb = 0;
-  if (cur < a.nchunks) issue(cur, 0, 0);
+  if (cur < nch) issue(cur, 0, 0);
   bool direct = false;
-  while (cur < a.nchunks) {
+  while (cur < nch) {
     // one pass over the chunk: staged (normal) or, after a staging overflow, with direct stores
     {
       const int64_t cbeg = cur * (int64_t)CHUNKB;
@@ -1135,7 +1142,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         if (nxt == none &&
             (a.mode != M_FINDALL || direct || (cnt <= (unsigned)CAP && flush(sb ^ 1, false))))
           nxt = take_ticket();
-        if (nxt != none && nxt < a.nchunks) {
+        if (nxt != none && nxt < nch) {
           issue(nxt, 0, kb ^ 1);
           prefetched = true;
         }
@@ -1164,7 +1171,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         if (lane == 0) {
           ws.goff = goff;
           atomicAdd(&a.total[3], 1ull);  // diagnostics: chunks redone with direct stores
-          if (cur == a.nchunks - 1) a.total[0] = goff + cnt;
+          if (cur == nch - 1u) a.total[0] = goff + cnt;
         }
         direct = true;
         if (prefetched) wait(kb);
@@ -1187,7 +1194,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     }
     direct = false;
     if (nxt == none) nxt = take_ticket();
-    if (!prefetched && nxt < a.nchunks) {
+    if (!prefetched && nxt < nch) {
       __syncwarp();
       issue(nxt, 0, kb);
     }
