@@ -68,6 +68,8 @@ def _load():
     L.cgx_scan_device.argtypes = [vp, u8p, sz, i64, C.c_int, C.c_void_p, sz, C.c_void_p, C.c_void_p]
     L.cgx_scan_shard_device.argtypes = [vp, u8p, sz, i64, i64, C.c_int, C.c_void_p, sz, C.c_void_p, C.c_void_p]
     L.cgx_scan_submatch_device.argtypes = [vp, u8p, sz, i64, C.c_void_p, sz, C.c_void_p, C.c_void_p]
+    L.cgx_scan_records_device.argtypes = [vp, u8p, sz, C.c_void_p, sz, i64, C.c_void_p, sz, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
     L.cgx_launch_count.restype = C.c_uint64
     L.cgx_launch_count.argtypes = [vp]
     L.cgx_synth_device.argtypes = [C.c_int, C.c_uint64, C.c_uint64, u8p, sz, u8p, C.c_void_p, C.c_int, C.c_void_p]
@@ -219,6 +221,13 @@ class Regex:
         base_offset / bytes_after place the buffer inside a larger logical haystack (a shard)."""
         _check(_lib.cgx_scan_shard_device(self._h, d_ptr, length, base_offset, bytes_after, mode, out_ptr,
                                           cap_pairs, result_ptr, stream))
+
+    def scan_records_device(self, d_ptr, length, rec_off_ptr, nrec, out_ptr, cap_pairs, rec_prefix_ptr,
+                            result_ptr, base_offset=0, stream=0):
+        """Batch of independent delimiter-terminated records in one scan (include/coregex_b200.h
+        cgx_scan_records_device): pairs in global order + per-record pair-index prefix."""
+        _check(_lib.cgx_scan_records_device(self._h, d_ptr, length, rec_off_ptr, nrec, base_offset, out_ptr,
+                                            cap_pairs, rec_prefix_ptr, result_ptr, stream))
 
     def scan_submatch_device(self, d_ptr, length, out_ptr, cap_matches, result_ptr, base_offset=0,
                              stream=0):

@@ -385,6 +385,61 @@ int cgx_scan_shard_device(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t
   return scan_locked(re, d_h, len, base, mode, d_out, cap, d_result, (cudaStream_t)stream, bytes_after);
 }
 
+// ---- batch of independent records (the batch entry a GPU-side caller wants) ------
+// The reference searches a batch by calling FindAllIndex once per haystack (regex.go:695).  When
+// every record ends with the record delimiter no match can span two records, and for a pattern
+// without anchors or look-around a match does not depend on where its record begins or ends, so the
+// batch equals ONE scan of the concatenation; what remains is to tell the caller which pairs belong
+// to which record: prefix[r] = number of matches that start before record r.
+__global__ void rec_prefix_kernel(const uint8_t* h, const uint64_t* rec_off, uint64_t nrec, int64_t base,
+                                  const int64_t* pairs, const unsigned long long* total, uint64_t cap, uint8_t delim,
+                                  uint64_t* prefix, unsigned long long* bad) {
+  const uint64_t nm = total[0] < cap ? total[0] : cap;  // pairs actually written
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= nrec;
+       r += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t off = rec_off[r];
+    // the promise that makes the batch one scan: a delimiter before every inner record boundary
+    if (r > 0 && r < nrec && (off == 0 || h[off - 1] != delim || off < rec_off[r - 1])) atomicAdd(bad, 1ull);
+    const int64_t key = (int64_t)off + base;
+    uint64_t lo = 0, hi = nm;  // first pair whose start is >= key
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi) >> 1;
+      if (pairs[2 * mid] < key) lo = mid + 1;
+      else hi = mid;
+    }
+    prefix[r] = lo;
+  }
+}
+
+int cgx_scan_records_device(cgx_regex* re, const uint8_t* d_h, size_t len, const uint64_t* d_rec_off, size_t nrec,
+                            int64_t base, int64_t* d_out, size_t cap, uint64_t* d_rec_prefix, uint64_t* d_result,
+                            void* stream) {
+  if (!re || !d_rec_off || !d_rec_prefix || !d_result || base < 0) return CGX_ERR_ARGS;
+  std::lock_guard<std::mutex> lk(re->mu);
+  int r = re->ensure_device();
+  if (r) return r;
+  Compiled& c = *re->c;
+  if (c.an.has_anchors) {
+    g_last_error = "unsupported: a pattern with anchors or look-around depends on where each record begins and ends; "
+                   "scan such records one call at a time";
+    return CGX_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((r = scan_locked(re, d_h, len, base, CGX_MODE_FINDALL, d_out, cap, nullptr, st))) return r;
+  const unsigned long long* tt = (const unsigned long long*)re->d_ticket_total.p;
+  CU(cudaMemcpyAsync(d_result, tt, 16, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemsetAsync(d_result + 2, 0, 8, st));
+  const uint8_t delim = c.kind == ENG_TEDDY ? (uint8_t)'\n' : (uint8_t)c.delim;
+  const unsigned threads = 256;
+  uint64_t blocks = (nrec + 1 + threads - 1) / threads;
+  if (blocks > (uint64_t)re->sm_count * 8) blocks = (uint64_t)re->sm_count * 8;
+  rec_prefix_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_h, d_rec_off, (uint64_t)nrec, base, d_out, tt, (uint64_t)cap,
+                                                          delim, d_rec_prefix, (unsigned long long*)(d_result + 2));
+  CU(cudaGetLastError());
+  re->launches++;
+  return CGX_OK;
+}
+
 // scan -> (start,end) pairs -> one Pike lane per match for the group offsets
 static int submatch_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base, int64_t* d_out,
                            size_t cap, uint64_t* d_result, cudaStream_t st) {

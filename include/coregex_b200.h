@@ -98,6 +98,21 @@ int cgx_scan_device(cgx_regex* re, const uint8_t* d_haystack, size_t len, int64_
 int cgx_scan_shard_device(cgx_regex* re, const uint8_t* d_haystack, size_t len, int64_t base_offset,
                           int64_t bytes_after, int mode, int64_t* d_out_pairs, size_t cap_pairs,
                           uint64_t* d_result, void* stream);
+/* Batch of independent records — what the reference does with one FindAllIndex call per haystack
+ * (regex.go:695) — in one scan.  Record r is d_haystack[d_rec_off[r] .. d_rec_off[r+1]): nrec + 1
+ * ascending device offsets, d_rec_off[0] = 0, d_rec_off[nrec] = len.  Every record but the last
+ * must END with the record delimiter (cgx_delimiter, normally '\n'), so that no match spans two
+ * records, and the pattern must be free of anchors and look-around (else CGX_ERR_UNSUPPORTED): then
+ * the batch result is exactly the per-record results, concatenated.  Pairs are written in global
+ * order with offsets relative to d_haystack (+ base_offset); d_rec_prefix[r] (nrec + 1 entries) =
+ * number of written pairs that start before record r, so record r owns pairs
+ * [d_rec_prefix[r], d_rec_prefix[r+1]) and record-relative offsets are pair - d_rec_off[r].
+ * d_result: device uint64[3] = {total matches, is-match flag, number of inner record boundaries
+ * that are NOT preceded by the delimiter (the caller must see 0)}.                              */
+int cgx_scan_records_device(cgx_regex* re, const uint8_t* d_haystack, size_t len,
+                            const uint64_t* d_rec_off, size_t nrec, int64_t base_offset,
+                            int64_t* d_out_pairs, size_t cap_pairs, uint64_t* d_rec_prefix,
+                            uint64_t* d_result, void* stream);
 /* submatch variant: d_out receives stride int64 per match */
 int cgx_scan_submatch_device(cgx_regex* re, const uint8_t* d_haystack, size_t len,
                              int64_t base_offset, int64_t* d_out, size_t cap_matches,

@@ -403,3 +403,56 @@ def test_charclass_run_patterns(pat):
     for n in (100, 70000):
         check(pat, bytes(alpha[rng.integers(0, len(alpha), n)]), o)
     check(pat, cg.synth_host(0, 5, 600 * 4096).tobytes(), o)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pat", [r"\d+\.\d+\.\d+\.\d+", r"[a-z]+/\d+", r"GET|POST|PUT"])
+def test_records_batch_equals_one_search_per_record(pat):
+    """cgx_scan_records_device: the reference searches a batch with one FindAllIndex call per
+    haystack (regex.go:695); delimiter-terminated records in one scan must give the same pairs,
+    record by record (oracle run on every record separately)."""
+    import torch
+    hay = cg.synth_host(cg.SYNTH_LOG, 77, 4096 * 24)
+    a = np.frombuffer(bytes(hay), dtype=np.uint8) if not isinstance(hay, np.ndarray) else hay
+    nl = np.flatnonzero(a == ord("\n"))
+    # records = groups of 1..3 lines; the last record ends the buffer
+    cuts = [0]
+    rng = np.random.default_rng(5)
+    i = 0
+    while i < len(nl):
+        i += int(rng.integers(1, 4))
+        cuts.append(int(nl[min(i, len(nl)) - 1]) + 1)
+    if cuts[-1] != a.size:
+        cuts.append(a.size)
+    cuts = sorted(set(cuts))
+    nrec = len(cuts) - 1
+    r = cg.Compile(pat)
+    t = torch.from_numpy(a.copy()).cuda()
+    off = torch.tensor(cuts, dtype=torch.int64, device="cuda")
+    cap = a.size // 8
+    out = torch.zeros((cap, 2), dtype=torch.int64, device="cuda")
+    pre = torch.zeros(nrec + 1, dtype=torch.int64, device="cuda")
+    res = torch.zeros(3, dtype=torch.int64, device="cuda")
+    r.scan_records_device(t.data_ptr(), a.size, off.data_ptr(), nrec, out.data_ptr(), cap, pre.data_ptr(),
+                          res.data_ptr())
+    torch.cuda.synchronize()
+    total, bad = int(res[0]), int(res[2])
+    assert bad == 0 and total <= cap
+    pairs, prefix = out[:total].cpu().numpy(), pre.cpu().numpy()
+    assert prefix[0] == 0 and prefix[-1] == total and np.all(np.diff(prefix) >= 0)
+    orc = Oracle(pat)
+    for k in range(nrec):
+        want = orc.find_all(a[cuts[k]:cuts[k + 1]])
+        got = pairs[prefix[k]:prefix[k + 1]] - cuts[k]
+        assert np.array_equal(got, want), (k, got[:3], want[:3])
+    # a boundary that is not preceded by the delimiter is reported, not silently accepted
+    off2 = off.clone()
+    off2[1] = off2[1] - 1
+    r.scan_records_device(t.data_ptr(), a.size, off2.data_ptr(), nrec, out.data_ptr(), cap, pre.data_ptr(),
+                          res.data_ptr())
+    torch.cuda.synchronize()
+    assert int(res[2]) == 1
+    # anchors depend on record boundaries: refused
+    with pytest.raises(cg.Error):
+        cg.Compile(r"^\d+").scan_records_device(t.data_ptr(), a.size, off.data_ptr(), nrec, out.data_ptr(), cap,
+                                                 pre.data_ptr(), res.data_ptr())
