@@ -293,7 +293,7 @@ def main():
         roof["traffic_note"] = traffic.get("note")
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # reported at N=1 only (the N>1 lines scale the GPU arm)
         threads = os.cpu_count() or 1
         sample = (args.cpu_sample_mib << 20) if args.cpu_sample_mib else min(4 * GIB, max(256 << 20, threads * (32 << 20)))
         sample -= sample % 4096
