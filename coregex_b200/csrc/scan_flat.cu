@@ -663,10 +663,7 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
   if (totS) {
     const int rel0 = trel + 64 * lane;
     if (a.mode == M_FINDALL) {
-#ifndef CGX_EMIT_V
-#define CGX_EMIT_V 2
-#endif
-      if (!em.direct && CGX_EMIT_V == 2) {
+      if (!em.direct) {
         // Rounds with a warp-uniform trip count (the largest number of starts or ends any lane
         // holds, usually 1 or 2): every round each lane stores its next start and its next end.
         // No divergent loop, hence no reconvergence bookkeeping.
@@ -705,24 +702,6 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
             }
           }
         }
-      } else if (!em.direct && CGX_EMIT_V == 1) {
-        // one divergent loop takes a start and an end per round
-        uint64_t sb = t.S, eb = t.E;
-        unsigned is = cnt + exS, ie = cnt + exE;
-        while (sb | eb) {
-          if (sb) {
-            const int b = __ffsll((long long)sb) - 1;
-            sb &= sb - 1;
-            if (is < (unsigned)CAP) em.w->stS[em.sb][is] = (uint16_t)(rel0 + b);
-            is++;
-          }
-          if (eb) {
-            const int b = __ffsll((long long)eb) - 1;
-            eb &= eb - 1;
-            if (ie < (unsigned)CAP) em.w->stE[em.sb][ie] = (uint16_t)(rel0 + b);
-            ie++;
-          }
-        }
       } else {
         em.put_bits(t.S, cnt + exS, rel0, false);
         em.put_bits(t.E, cnt + exE, rel0, true);
@@ -733,16 +712,9 @@ __device__ __forceinline__ void finish_tile(const ScanArgs& a, Emit& em, const T
   if (t.open) cnt += serial_region(a, em, em.cb() + trel + own_open_lim(t, lane), em.cb() + trel + STRIDE, cnt, lane);
 }
 
-// bytes at or beyond the end of input belong to no class (last chunk only: kept out of line)
-// (kept inline: as a real call it would pin the class bitmaps in local memory — measured -12 %)
-#ifndef CGX_TAIL_NOINLINE
-#define CGX_TAIL_NOINLINE 0
-#endif
-#if CGX_TAIL_NOINLINE
-__device__ __noinline__
-#else
+// bytes at or beyond the end of input belong to no class (last chunk only).  Inline on purpose: as
+// a real call it would pin the class bitmaps in local memory (measured -12 %).
 __device__ __forceinline__
-#endif
 void mask_tail(uint64_t (&ca)[4], uint64_t (&cb)[4], int64_t nv, int lane) {
   // reversed bit r of lane l <=> tile byte 2047 - (64 l + r); valid <=> byte < nv
   const int64_t ra = TILE - nv, rb = TILE - (nv - STRIDE);  // first valid reversed index
