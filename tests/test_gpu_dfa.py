@@ -456,3 +456,23 @@ def test_records_batch_equals_one_search_per_record(pat):
     with pytest.raises(cg.Error):
         cg.Compile(r"^\d+").scan_records_device(t.data_ptr(), a.size, off.data_ptr(), nrec, out.data_ptr(), cap,
                                                  pre.data_ptr(), res.data_ptr())
+
+
+import json as _json
+
+_REF_FINDALL = _json.load(open(os.path.join(ROOT, "tests", "golden", "ref_findall_vectors.json")))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("v", _REF_FINDALL, ids=[v["src"].split(" ")[0] for v in _REF_FINDALL])
+def test_reference_findall_vectors_on_device(v):
+    """The reference's own literal FindAll expectations (tests/golden/ref_findall_vectors.json)
+    through the C ABI; patterns the GPU engines refuse must say so at compile time."""
+    try:
+        r = cg.Compile(v["pattern"])
+    except cg.Error as e:
+        assert "unsupported" in str(e)
+        pytest.skip("refused at compile time: %s" % e)
+    r.set_bitstream(1 if BITSTREAM else 0)
+    got = r.FindAllIndex(v["input"].encode(), -1) or []
+    assert got == v["want"], v["src"]

@@ -234,3 +234,13 @@ def test_negated_class_stray_byte_fallback_quirk():
     first three bytes of the emoji.  Kept in the oracle AND reproduced by the product's tables
     (tests/test_host_compile.py::test_utf8_tables_match_oracle)."""
     assert Oracle(r"\D{2,3}").find_all("мир😀".encode()).tolist() == [[0, 6], [6, 9]]
+
+
+REF_FINDALL = json.load(open(os.path.join(GOLDEN, "ref_findall_vectors.json")))
+
+
+@pytest.mark.parametrize("v", REF_FINDALL, ids=[v["src"].split(" ")[0] for v in REF_FINDALL])
+def test_reference_findall_vectors(v):
+    """Literal `[][2]int{...}` expectations of the reference's own tests (char-class searcher,
+    non-greedy iteration, backtracker iteration), harvested by tests/golden/harvest_findall_vectors.py."""
+    assert fa(v["pattern"], v["input"].encode()) == v["want"], v["src"]
