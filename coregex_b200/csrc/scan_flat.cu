@@ -45,6 +45,15 @@ namespace {
 #ifndef CGX_TILES
 #define CGX_TILES 2
 #endif
+// CGX_PAIR=1 (experiment, one-tile build only): one bulk copy brings TWO tiles (4032 B) into the
+// warp's single 4 KB window; the tiles are evaluated one after the other and the window is refilled
+// as soon as the second one has been classified.  Halves the per-tile cost of TMA issue and
+// mbarrier wait (~85 of ~620 instructions per tile); the copy's latency is hidden by the second
+// tile's passes and by the other warps instead of by a second buffer.  Same chunk geometry as the
+// default, so it can be A/B-ed with CGX_JIT_DEFS="-DCGX_PAIR=1" (tools/micro/exp.sh).
+#ifndef CGX_PAIR
+#define CGX_PAIR 0
+#endif
 #ifndef CGX_IT_UNROLL
 #define CGX_IT_UNROLL 1  // 2: both window buffers in one loop body (constant buffer index, twice the hot code)
 #endif
@@ -730,8 +739,14 @@ void mask_tail(uint64_t (&ca)[4], uint64_t (&cb)[4], int64_t nv, int lane) {
 
 // Processes the NT tiles whose windows start at `win` (position wrel in the chunk), win + STRIDE.
 // nv = valid bytes from the start of tile A, clamped to SUPER; first = the window starts the haystack.
+// after_classify() runs as soon as the window's bytes are in registers: the pair-load variant
+// (CGX_PAIR) refills the window from there.
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+template <class Hook>
 __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const uint8_t* win, int wrel, int nv,
-                                              bool first, unsigned& cnt, int lane) {
+                                              bool first, unsigned& cnt, int lane, Hook after_classify) {
   const FlatDev& f = a.flat;
   const int piece = 31 - lane;
   uint64_t ca[4], cb[4] = {0ull, 0ull, 0ull, 0ull};
@@ -739,6 +754,7 @@ __device__ __forceinline__ void process_tiles(const ScanArgs& a, Emit& em, const
   const uint32_t one = (uint32_t)(a.nchunks > 0);
   classify_piece(f, win + piece * 64, lane, one, ca);
   if (NT == 2) classify_piece(f, win + STRIDE + piece * 64, lane, one, cb);
+  after_classify();
   // bytes at or beyond the end of input belong to no class
   if (nv < SUPER) mask_tail(ca, cb, nv, lane);
 
@@ -1042,6 +1058,37 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       }
     }
   };
+#if CGX_PAIR
+  static_assert(NT == 1 && TPC % 2 == 0, "CGX_PAIR is a variant of the one-tile build");
+  constexpr int PSUPER = STRIDE + TILE;  // two overlapping tiles
+  // starts the bulk copy of tile pair `p` of `chunk` into the warp's (single) window
+  auto issue_pair = [&](int64_t chunk, int p) {
+    if (lane == 0) {
+      const int64_t g = chunk * (int64_t)CHUNKB + p * (2 * STRIDE);
+      if (g + PSUPER <= a.n) {
+        mbar_expect_tx(&ws.mbar[0], (uint32_t)PSUPER);
+        tma_load_1d(ws.win[0], a.h + g, (uint32_t)PSUPER, &ws.mbar[0]);
+      } else {
+        const int64_t left = a.n - g;
+        if (left > 0) {
+          const uint32_t bulk = (uint32_t)((left + 15) & ~(int64_t)15);  // < PSUPER + 16 <= 2 * SUPER
+          mbar_expect_tx(&ws.mbar[0], bulk);
+          tma_load_1d(ws.win[0], a.h + g, bulk, &ws.mbar[0]);
+        } else {
+          mbar_arrive(&ws.mbar[0]);
+        }
+      }
+    }
+  };
+#endif
+  // first window of a chunk (into the buffer the chunk will start with)
+  auto issue_first = [&](int64_t chunk, int b) {
+#if CGX_PAIR
+    issue_pair(chunk, 0);
+#else
+    issue(chunk, 0, b);
+#endif
+  };
   auto wait = [&](int b) {
     mbar_wait(&ws.mbar[b], (phase >> b) & 1u);
     phase ^= 1u << b;
@@ -1079,7 +1126,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
   unsigned nxt = none;
   bool prefetched = false;  // window 0 of `nxt` is in flight into the buffer the next chunk starts with
   int kb = 0, sb = 0;
-  if (cur < nch) issue(cur, 0, 0);
+  if (cur < nch) issue_first(cur, 0);
   bool direct = false;
   while (cur < nch) {
     // one pass over the chunk: staged (normal) or, after a staging overflow, with direct stores
@@ -1095,6 +1142,52 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     }
     Emit em{&a, &ws, sb, direct};
     unsigned cnt = 0;
+#if CGX_PAIR
+    for (int p = 0; p < TPC / 2; p++) {
+      // what fills the window once this pair's second tile is classified — decided here, while
+      // nothing of a tile is live in registers
+      unsigned fill = none;
+      int fillp = 0;
+      if (p + 1 < TPC / 2) {
+        fill = cur;
+        fillp = p + 1;
+      } else {
+        if (nxt == none &&
+            (a.mode != M_FINDALL || direct || (cnt <= (unsigned)CAP && flush(sb ^ 1, false))))
+          nxt = take_ticket();
+        if (nxt != none && nxt < nch) {
+          fill = nxt;
+          prefetched = true;
+        }
+      }
+      auto refill = [&]() {
+        __syncwarp();  // every lane has its piece of the window in registers
+        if (fill != none) issue_pair(fill, fillp);
+      };
+      wait(0);
+      const int wrel = p * (2 * STRIDE);
+      int nvp = PSUPER;
+      if (!ws.whole) {
+        const int64_t left = a.n - (ws.cb + wrel);
+        nvp = left >= PSUPER ? PSUPER : (left > 0 ? (int)left : 0);
+      }
+      const int nva = nvp < TILE ? nvp : TILE;
+      const int nvb = nvp - STRIDE < TILE ? nvp - STRIDE : TILE;
+      const bool first = p == 0 && ws.chunk0 != 0;
+      // one copy of the tile code, run once or twice (a second inlined copy would double the hot
+      // loop's instruction-cache footprint)
+      const int ntl = nvb > 0 ? 2 : (nva > 0 ? 1 : 0);
+      if (ntl == 0) refill();
+#pragma unroll 1
+      for (int t = 0; t < ntl; t++) {
+        auto hook = [&]() {
+          if (t == ntl - 1) refill();
+        };
+        process_tiles(a, em, ws.win[0] + t * STRIDE, wrel + t * STRIDE, t ? nvb : nva, first && t == 0, cnt, lane,
+                      hook);
+      }
+    }
+#else
 #pragma unroll IT_UNROLL
     for (int it = 0; it < ITERS; it++) {
       // the other window buffer was last read an iteration ago: refill it now
@@ -1126,9 +1219,10 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         const int64_t left = a.n - (ws.cb + wrel);
         nv = left >= SUPER ? SUPER : (left > 0 ? (int)left : 0);
       }
-      if (nv > 0) process_tiles(a, em, ws.win[kb], wrel, nv, it == 0 && ws.chunk0 != 0, cnt, lane);
+      if (nv > 0) process_tiles(a, em, ws.win[kb], wrel, nv, it == 0 && ws.chunk0 != 0, cnt, lane, NoHook());
       kb ^= 1;
     }
+#endif
     if (a.mode != M_FINDALL) {
       if (cnt && lane == 0) {
         atomicAdd(a.total, (unsigned long long)cnt);
@@ -1149,7 +1243,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         if (prefetched) wait(kb);
         prefetched = false;
         __syncwarp();
-        issue(cur, 0, kb);
+        issue_first(cur, kb);
         continue;
       }
       // hand the chunk to the resolver warp
@@ -1168,7 +1262,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     if (nxt == none) nxt = take_ticket();
     if (!prefetched && nxt < nch) {
       __syncwarp();
-      issue(nxt, 0, kb);
+      issue_first(nxt, kb);
     }
     prefetched = false;
     cur = nxt;

@@ -34,13 +34,13 @@ class NotEligible(Exception):
 _jit_libs = {}
 
 
-def jit_lib(pattern, tiles=2):
+def jit_lib(pattern, tiles=2, defs="", tag=""):
     """The emulated kernel built the way jit.cu builds it for the device: -DCGX_JIT plus the
     generated cgx_jit_prog.h of this pattern (straight-line passes)."""
     if isinstance(pattern, str):
         pattern = pattern.encode()
-    if (pattern, tiles) in _jit_libs:
-        return _jit_libs[(pattern, tiles)]
+    if (pattern, tiles, tag) in _jit_libs:
+        return _jit_libs[(pattern, tiles, tag)]
     import hashlib
     L = lib()
     buf = C.create_string_buffer(1 << 16)
@@ -54,14 +54,15 @@ def jit_lib(pattern, tiles=2):
     hp = os.path.join(d, "cgx_jit_prog.h")
     if not os.path.exists(hp) or open(hp, "rb").read() != buf.value:
         open(hp, "wb").write(buf.value)
-    subprocess.check_call(["make", "-C", _DIR, "jit", "JITDIR=" + d, "TILES=%d" % tiles], stdout=subprocess.DEVNULL)
-    J = C.CDLL(os.path.join(d, "libcgxsim_jit%d.so" % tiles))
+    subprocess.check_call(["make", "-C", _DIR, "jit", "JITDIR=" + d, "TILES=%d" % tiles, "DEFS=" + defs, "TAG=" + tag],
+                          stdout=subprocess.DEVNULL)
+    J = C.CDLL(os.path.join(d, "libcgxsim_jit%d%s.so" % (tiles, tag)))
     J.cgxsim_scan.argtypes = L.cgxsim_scan.argtypes
-    _jit_libs[(pattern, tiles)] = J
+    _jit_libs[(pattern, tiles, tag)] = J
     return J
 
 
-def scan(pattern, hay, mode=0, cap=None, grid=2, base=0, pad=ord("1"), jit=False, tiles=2):
+def scan(pattern, hay, mode=0, cap=None, grid=2, base=0, pad=ord("1"), jit=False, tiles=2, defs="", tag=""):
     """Runs the emulated kernel.  Returns (total, flag, pairs[ndarray k x 2])."""
     if isinstance(pattern, str):
         pattern = pattern.encode()
@@ -71,7 +72,7 @@ def scan(pattern, hay, mode=0, cap=None, grid=2, base=0, pad=ord("1"), jit=False
         cap = n + 16
     out = np.full((max(cap, 1), 2), -7, dtype=np.int64)
     res = (C.c_uint64 * 4)()
-    r = (jit_lib(pattern, tiles) if jit else lib()).cgxsim_scan(pattern, len(pattern), a.ctypes.data if n else None, n, base, mode,
+    r = (jit_lib(pattern, tiles, defs, tag) if jit else lib()).cgxsim_scan(pattern, len(pattern), a.ctypes.data if n else None, n, base, mode,
                           out.ctypes.data, cap, res, grid, pad)
     if r == -2:
         raise NotEligible(pattern)

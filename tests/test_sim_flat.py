@@ -19,7 +19,7 @@ STRIDE, TILE, CHUNK = 1984, 2048, 12 * 1984
 BACKEND = "sim"
 
 
-@pytest.fixture(autouse=True, params=["sim", "simjit", "simjit1", pytest.param("gpu", marks=pytest.mark.gpu)])
+@pytest.fixture(autouse=True, params=["sim", "simjit", "simjit1", "simjit1pair", pytest.param("gpu", marks=pytest.mark.gpu)])
 def backend(request):
     """Every case runs on the emulator — the interpreting build and the per-pattern specialised
     build (what jit.cu compiles for the device) — and, under -m gpu, on the device through the C ABI."""
@@ -31,9 +31,13 @@ def backend(request):
 
 def scan(pat, hay, mode=0, cap=None, grid=2, base=0):
     """(total, flag, pairs) from the selected backend."""
-    if BACKEND in ("sim", "simjit", "simjit1"):  # simjit1: one tile per iteration (CGX_TILES=1)
+    if BACKEND in ("sim", "simjit", "simjit1", "simjit1pair"):
+        # simjit1: one tile per iteration (CGX_TILES=1, what the device runs by default);
+        # simjit1pair: the pair-load variant of it (-DCGX_PAIR=1)
+        pair = BACKEND == "simjit1pair"
         return sim_lib.scan(pat, hay, mode=mode, cap=cap, grid=grid, base=base, jit=BACKEND != "sim",
-                            tiles=1 if BACKEND == "simjit1" else 2)
+                            tiles=1 if BACKEND in ("simjit1", "simjit1pair") else 2,
+                            defs="-DCGX_PAIR=1" if pair else "", tag="pair" if pair else "")
     import torch
     from gpu_util import scan_device
     r = cg.Compile(pat)

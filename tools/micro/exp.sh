@@ -1,4 +1,5 @@
 # A/B of build-time variants of the specialised kernel (CGX_JIT_DEFS), 16 GiB IP scan + the other flat patterns
+#   bash tools/micro/exp.sh "" "-DCGX_PAIR=1" "-DCGX_WARPS=13 -DCGX_CTAS=2"      (one line of GB/s per pattern and variant)
 mkdir -p gpurun_out
 run() { # defs
   echo "== defs=$1"
