@@ -70,6 +70,11 @@ def _load():
     L.cgx_scan_submatch_device.argtypes = [vp, u8p, sz, i64, C.c_void_p, sz, C.c_void_p, C.c_void_p]
     L.cgx_scan_records_device.argtypes = [vp, u8p, sz, C.c_void_p, sz, i64, C.c_void_p, sz, C.c_void_p, C.c_void_p,
                                           C.c_void_p]
+    L.cgx_wire_bytes.restype = sz
+    L.cgx_wire_bytes.argtypes = [sz, C.c_int]
+    L.cgx_wire_segments.argtypes = [sz]
+    L.cgx_pack_offsets_device.argtypes = [C.c_void_p, sz, i64, sz, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cgx_unpack_offsets_device.argtypes = [C.c_void_p, sz, i64, sz, C.c_void_p, C.c_void_p]
     L.cgx_launch_count.restype = C.c_uint64
     L.cgx_launch_count.argtypes = [vp]
     L.cgx_synth_device.argtypes = [C.c_int, C.c_uint64, C.c_uint64, u8p, sz, u8p, C.c_void_p, C.c_int, C.c_void_p]
@@ -274,3 +279,20 @@ def synth_host(kind, seed, nbytes, first_block=0, literals=None):
 
 def synth_device(kind, seed, d_ptr, nbytes, first_block=0, d_lit_ptr=0, d_off_ptr=0, nlit=0, stream=0):
     _check(_lib.cgx_synth_device(kind, seed, first_block, d_ptr, nbytes, d_lit_ptr, d_off_ptr, nlit, stream))
+
+
+# ---- compact offset wire format (multi-GPU offset gather) ------------------------------------------
+def wire_segments(shard_len):
+    return _lib.cgx_wire_segments(shard_len)
+
+
+def wire_bytes(count, shard_len):
+    return _lib.cgx_wire_bytes(count, _lib.cgx_wire_segments(shard_len))
+
+
+def pack_offsets_device(pairs_ptr, count, shard_base, shard_len, wire_ptr, bad_ptr, stream=0):
+    _check(_lib.cgx_pack_offsets_device(pairs_ptr, count, shard_base, shard_len, wire_ptr, bad_ptr, stream))
+
+
+def unpack_offsets_device(wire_ptr, count, shard_base, shard_len, out_ptr, stream=0):
+    _check(_lib.cgx_unpack_offsets_device(wire_ptr, count, shard_base, shard_len, out_ptr, stream))

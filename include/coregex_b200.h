@@ -118,6 +118,21 @@ int cgx_scan_submatch_device(cgx_regex* re, const uint8_t* d_haystack, size_t le
                              int64_t base_offset, int64_t* d_out, size_t cap_matches,
                              uint64_t* d_result, void* stream);
 
+/* ---- compact offset wire format (multi-GPU offset gather, SURVEY.md §8e / BASELINE config 5) ----
+ * The reference returns [][2]int (16 B per match, regex.go:710-723); between GPUs a shard's sorted
+ * pairs travel as 6 B per match: the low 32 bits of the shard-relative start + a 16-bit length,
+ * behind a table of the first match index of every 4 GiB segment of the shard.  One message =
+ * seg_first[nseg] u64 | lo[count] u32 | len[count] u16, cgx_wire_bytes(count, nseg) bytes with
+ * nseg = cgx_wire_segments(shard_len).  d_bad (device uint64) counts matches that do not fit
+ * (longer than 65535 bytes): the caller then sends plain int64 pairs instead.  Both calls only
+ * enqueue work on `stream`; d_wire 8-byte aligned, pair buffers 16-byte aligned.               */
+size_t cgx_wire_bytes(size_t count, int nseg);
+int cgx_wire_segments(size_t shard_len);
+int cgx_pack_offsets_device(const int64_t* d_pairs, size_t count, int64_t shard_base, size_t shard_len,
+                            uint8_t* d_wire, uint64_t* d_bad, void* stream);
+int cgx_unpack_offsets_device(const uint8_t* d_wire, size_t count, int64_t shard_base, size_t shard_len,
+                              int64_t* d_pairs_out, void* stream);
+
 /* number of kernels launched by this regex since creation (bench.py reports it) */
 uint64_t cgx_launch_count(const cgx_regex* re);
 

@@ -29,6 +29,15 @@ def _worker(rank, world, port, blocks, q):
     pairs = torch.from_numpy(Oracle(IP).find_all(hay) + base)
     counts = shard.gather_counts(dist, torch.device("cpu"), pairs.shape[0], hay.size)
     allp = shard.gather_offsets(dist, pairs, [c for c, _ in counts])
+    # the compact 6 B/match exchange (send/recv to rank 0) must rebuild the same list
+    lens = [b for _, b in counts]
+    bases = [4096 * shard.shard_blocks(blocks, world, r)[0] for r in range(world)]
+    comp = shard.gather_offsets_compact(dist, pairs, [c for c, _ in counts], base, hay.size, dst=0,
+                                        shard_lens=lens, bases=bases)
+    if rank == 0:
+        assert torch.equal(comp, allp)
+    else:
+        assert comp is None
     t = torch.tensor([float(rank + 1)], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)      # the bench's max-over-ranks timing reduction
     if rank == 0:
@@ -71,3 +80,21 @@ def test_shard_planning():
     b = shard.split_line_aligned(buf, 4)
     assert b[0] == 0 and b[-1] == len(buf) and all(x <= y for x, y in zip(b, b[1:]))
     assert all(buf[x - 1:x] == b"\n" for x in b[1:-1])
+
+
+def test_wire_codec_host_twin_roundtrip_across_4gib():
+    """The wire layout (csrc/wire.cu) on the host twin: starts on both sides of 4 GiB segment
+    boundaries, lengths up to 65535, empty shard; a longer match is refused."""
+    from coregex_b200 import shard
+    base, shard_len = 5 << 40, (9 << 30) + 4096
+    starts = np.array([0, 1, (1 << 32) - 3, (1 << 32), (1 << 32) + 7, (2 << 32) - 1, (2 << 32) + 5, shard_len - 10],
+                      dtype=np.int64)
+    lens = np.array([1, 65535, 2, 3, 9, 1, 4, 10], dtype=np.int64)
+    pairs = torch.from_numpy(np.stack([base + starts, base + starts + lens], axis=1))
+    w = shard.pack_offsets(pairs, base, shard_len)
+    assert w.numel() == shard._wire_layout(len(starts), shard_len)[1]
+    assert torch.equal(shard.unpack_offsets(w, len(starts), base, shard_len), pairs)
+    e = torch.zeros((0, 2), dtype=torch.int64)
+    assert shard.unpack_offsets(shard.pack_offsets(e, base, shard_len), 0, base, shard_len).shape == (0, 2)
+    too_long = torch.tensor([[base, base + 65536]], dtype=torch.int64)
+    assert shard.pack_offsets(too_long, base, shard_len) is None
