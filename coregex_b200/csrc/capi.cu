@@ -21,7 +21,7 @@ size_t scan_dfa_smem_bytes(int nstates, int blob_bytes);
 int64_t scan_dfa_chunks(int64_t n);
 cudaError_t launch_scan_dfa(const ScanArgs& a, int sm_count, cudaStream_t stream);
 int64_t scan_flat_chunks(int64_t n);
-cudaError_t launch_scan_flat(const ScanArgs& a, int sm_count, cudaStream_t stream);
+cudaError_t launch_scan_flat(const ScanArgs& a, int sm_count, cudaStream_t stream, int* grid_out);
 cudaError_t launch_pike_captures(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
                                  const unsigned long long* d_total, unsigned long long cap,
                                  const uint32_t* code, const uint32_t* sets, int start_pc, int nslots,
@@ -82,14 +82,20 @@ struct cgx_regex {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_scan[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   uint64_t* pinned_res = nullptr;  // [2][2]
   std::atomic<uint64_t> launches{0};
-  // flat deterministic patterns run on the bitstream kernel (scan_flat.cu); CGX_BITSTREAM=0 or
+  // flat deterministic patterns run on the bitstream kernel (scan_bits.cu); CGX_BITSTREAM=0 or
   // cgx_debug_set_bitstream keep them on the candidate/DFA kernel (A/B runs, tests of both paths)
   bool bitstream = true;
   // NVRTC-specialised build of that kernel for this pattern: 0 = not tried yet, 1 = in use,
   // -1 = unavailable (the generic nvcc-built kernel runs; jit_error says why)
   int jit_state = 0;
-  const JitKernel* jit = nullptr;
+  const JitKernel* jit[3] = {nullptr, nullptr, nullptr};  // one specialised kernel per search mode
   std::string jit_error;
+  // bitstream kernel, FindAll: a call is ONE launch.  The look-back words carry an epoch (stale words
+  // read as empty), the group accumulators and the ticket counter are left at zero by the kernel.
+  uint32_t epoch = 0;          // last epoch handed to a launch; 0 = the words must be cleared first
+  size_t status_cap_seen = 0;  // capacity of d_status when its words were last cleared
+  bool scratch_zero = false;   // ticket counter known to be zero (left so by the previous launch)
+  bool diag = false;           // cgx_debug_scratch in use: clear the diagnostics before every launch
 
   int ensure_pipeline() {
     if (s_h2d) return CGX_OK;
@@ -247,7 +253,7 @@ long cgx_debug_jit_compile(cgx_regex* re, char* cubin_out, size_t cap) {
   }
   std::vector<char> cubin;
   std::string err;
-  if (!JitCompileCubin(re->c->flat, JitTiles(), cubin, err)) {
+  if (!JitCompileCubin(re->c->flat, CGX_MODE_FINDALL, cubin, err)) {
     g_last_error = err;
     return -1;
   }
@@ -294,9 +300,24 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   const size_t ngroups = (size_t)(nchunks + 31) / 32 + 1;
   const size_t status_bytes = (size_t)(nchunks > 0 ? nchunks : 1) * 8 + ngroups * 16;
   if ((r = re->d_status.ensure(status_bytes))) return r;
-  CU(cudaMemsetAsync(re->d_ticket_total.p, 0, 64, st));
-  if (mode == CGX_MODE_FINDALL && nchunks > 0)
-    CU(cudaMemsetAsync(re->d_status.p, 0, status_bytes, st));
+  const bool one_launch = use_flat && mode == CGX_MODE_FINDALL && nchunks > 0;
+  if (one_launch) {
+    if (re->epoch == 0 || re->epoch >= 0xFFFFFu || re->status_cap_seen != re->d_status.cap) {
+      CU(cudaMemsetAsync(re->d_status.p, 0, re->d_status.cap, st));  // new buffer, or the epoch counter wrapped
+      re->status_cap_seen = re->d_status.cap;
+      re->epoch = 0;
+    }
+    re->epoch++;
+    if (!re->scratch_zero || re->diag) CU(cudaMemsetAsync(re->d_ticket_total.p, 0, 64, st));
+    re->scratch_zero = true;
+  } else {
+    CU(cudaMemsetAsync(re->d_ticket_total.p, 0, 64, st));
+    if (mode == CGX_MODE_FINDALL && nchunks > 0) {
+      CU(cudaMemsetAsync(re->d_status.p, 0, status_bytes, st));
+      re->epoch = 0;  // the other kernel wrote un-epoched words
+    }
+    re->scratch_zero = false;  // (IsMatch leaves the ticket counter wherever the early exit found it)
+  }
   ScanArgs a;
   memset(&a, 0, sizeof a);
   a.h = d_h;
@@ -352,18 +373,20 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   a.nchunks = nchunks;
   a.gstatus = a.status + (nchunks > 0 ? nchunks : 1);
   a.gacc = a.gstatus + ngroups;
+  a.epoch = re->epoch;
+  a.result = one_launch ? (unsigned long long*)d_result : nullptr;
   if (use_flat) {
-    if (re->jit_state == 0) {
-      re->jit = GetJitKernel(c.flat, re->jit_error);
-      re->jit_state = re->jit ? 1 : -1;
+    if (re->jit_state >= 0) {
+      if (!re->jit[mode]) re->jit[mode] = GetJitKernel(c.flat, mode, re->jit_error);
+      re->jit_state = re->jit[mode] ? 1 : -1;
     }
-    if (re->jit_state == 1) CU(launch_scan_flat_jit(re->jit, a, re->sm_count, st));
-    else CU(launch_scan_flat(a, re->sm_count, st));
+    if (re->jit_state == 1) CU(launch_scan_flat_jit(re->jit[mode], a, re->sm_count, st));
+    else CU(launch_scan_flat(a, re->sm_count, st, nullptr));
   } else {
     CU(launch_scan_dfa(a, re->sm_count, st));
   }
-  re->launches++;
-  if (d_result) CU(cudaMemcpyAsync(d_result, tt, 16, cudaMemcpyDeviceToDevice, st));
+  if (nchunks > 0) re->launches++;
+  if (d_result && !one_launch) CU(cudaMemcpyAsync(d_result, tt, 16, cudaMemcpyDeviceToDevice, st));
   return CGX_OK;
 }
 
@@ -724,6 +747,7 @@ int cgx_debug_line_copy(const cgx_regex* re, uint16_t* ut, uint16_t* rt, uint8_t
 // cycle counters in the -DCGX_TIMING build (tools/phase_timing.py) and zero otherwise
 int cgx_debug_scratch(cgx_regex* re, uint64_t out[8]) {
   if (!re || !re->d_ticket_total.p) return CGX_ERR_ARGS;
+  re->diag = true;  // from now on the diagnostics are cleared before every launch
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(out, re->d_ticket_total.p, 64, cudaMemcpyDeviceToHost));
   return CGX_OK;

@@ -277,32 +277,61 @@ std::string JitHeader(const FlatDev& f) {
   add("#define CGX_JIT_RUNSTART %d\n", f.bs_runstart);
   add("#define CGX_JIT_MIDRUN %d\n", f.bs_midrun_check);
   add("#define CGX_JIT_REV_INIT %d\n", f.rev_init_class);
-  // right to left, a single byte of class A followed by a run of class B (`B+ A` in the pattern) is
-  // one fused step over the precomputed bitmap "A right after B": one 2-position shift, no
-  // intermediate marker set (scan_flat.cu rev_fused)
-  std::string fused_defs;
-  o += "#define CGX_JIT_REV_PASS(STEP, FUSE)";
+  // Every step of a pass owns one slot I of per-lane state (the carry and the shifted-out bits that
+  // travel from one word to the next, scan_bits.cu PassState).  Right to left, a single byte of
+  // class A followed by a run of class B (`B+ A` in the pattern) is one fused step over the
+  // precomputed bitmap "A right after B": one 2-position shift, no intermediate marker set
+  // (scan_bits.cu rev_fused); the bitmap itself takes a state slot too (DEF).
+  std::string fused_defs, fused_keys;
+  int slot = 0, rev_slots = 0;
+  std::string rev = "#define CGX_JIT_REV_PASS(STEP, FUSE)";
   for (int k = 0; k < f.rev_nops; k++) {
     const int kind = f.rev_ops[k] & 3, cls = f.rev_ops[k] >> 2;
     if (kind == 0 && k + 1 < f.rev_nops && (f.rev_ops[k + 1] & 3) == 1) {
       const int cls2 = f.rev_ops[k + 1] >> 2;
-      add(" FUSE(%d, %d)", cls, cls2);
-      snprintf(buf, sizeof buf, " DEF(%d, %d)", cls, cls2);
-      if (fused_defs.find(buf) == std::string::npos) fused_defs += buf;
+      snprintf(buf, sizeof buf, " FUSE(%d, %d, %d)", cls, cls2, slot++);
+      rev += buf;
+      snprintf(buf, sizeof buf, "(%d,%d)", cls, cls2);
+      if (fused_keys.find(buf) == std::string::npos) {
+        fused_keys += buf;
+        snprintf(buf, sizeof buf, " DEF(%d, %d, @%zu@)", cls, cls2, fused_keys.size());
+        fused_defs += buf;
+      }
       k++;
     } else {
-      add(" STEP(%d, %d)", kind, cls);
+      snprintf(buf, sizeof buf, " STEP(%d, %d, %d)", kind, cls, slot++);
+      rev += buf;
     }
   }
+  // the DEFs take the slots after the steps'
+  {
+    std::string d;
+    size_t pos = 0;
+    while (pos < fused_defs.size()) {
+      const size_t at = fused_defs.find('@', pos);
+      if (at == std::string::npos) {
+        d += fused_defs.substr(pos);
+        break;
+      }
+      const size_t at2 = fused_defs.find('@', at + 1);
+      d += fused_defs.substr(pos, at - pos) + std::to_string(slot++);
+      pos = at2 + 1;
+    }
+    fused_defs = d;
+  }
+  rev_slots = slot;
+  o += rev;
   o += "\n#define CGX_JIT_REV_FUSED(DEF)" + fused_defs;
   o += "\n#define CGX_JIT_FWD_PASS(STEP)";
-  for (int k = 0; k < f.fwd_nops; k++) add(" STEP(%d, %d)", f.fwd_ops[k] & 3, f.fwd_ops[k] >> 2);
-  o += "\ntemplate <int C> __device__ __forceinline__ uint32_t cgx_jit_flags(uint32_t w, uint32_t one) { return 0u; }\n";
+  for (int k = 0; k < f.fwd_nops; k++) add(" STEP(%d, %d, %d)", f.fwd_ops[k] & 3, f.fwd_ops[k] >> 2, k);
+  const int nstate = rev_slots > f.fwd_nops ? rev_slots : f.fwd_nops;
+  add("\n#define CGX_JIT_NSTATE %d\n", nstate > 0 ? nstate : 1);
+  o += "template <int C> __device__ __forceinline__ uint32_t cgx_jit_flags(uint32_t w, uint32_t one) { return 0u; }\n";
   for (int c = 0; c < f.nclasses; c++) {
     add("template <> __device__ __forceinline__ uint32_t cgx_jit_flags<%d>(uint32_t w, uint32_t one) {\n  uint32_t fl = 0u;\n", c);
     for (int r = 0; r < f.cls_nranges[c]; r++) {
       if (f.cls_mode[c][r] == 0)
-        // 2 ALU-pipe + 1 FMA-pipe instruction per word (scan_flat.cu "pipe-aware primitives")
+        // 2 ALU-pipe + 1 FMA-pipe instruction per word (scan_bits.cu "pipe-aware primitives")
         add("  { const uint32_t z = mad_fma(xor_and(w, 0x%08Xu, 0x7F7F7F7Fu), one, 0x%08Xu); fl %s nor_and(z, w, 0x80808080u); }\n",
             f.cls_k1[c][r], f.cls_k2[c][r], r == 0 ? "=" : "|=");
       else

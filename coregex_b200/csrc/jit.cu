@@ -1,4 +1,4 @@
-// jit.cu — per-pattern specialisation of the bitstream kernel (scan_flat.cu) with NVRTC.
+// jit.cu — per-pattern specialisation of the bitstream kernel (scan_bits.cu) with NVRTC.
 //
 // The reference compiles a pattern into data (NFA, lazy-DFA tables) that one generic loop
 // interprets (reference meta/compile.go:40-219, dfa/lazy/lazy.go:219-324).  On the GPU the marker
@@ -113,15 +113,7 @@ std::map<std::pair<int, std::string>, JitKernel*> g_loaded;  // (device, header 
 
 }  // namespace
 
-int JitTiles() {
-  static const int t = [] {
-    const char* e = getenv("CGX_TILES");
-    return e && (e[0] == '1' || e[0] == '2') ? e[0] - '0' : kJitTilesDefault;
-  }();
-  return t;
-}
-
-bool JitCompileCubin(const FlatDev& f, int tiles, std::vector<char>& cubin, std::string& err) {
+bool JitCompileCubin(const FlatDev& f, int mode, std::vector<char>& cubin, std::string& err) {
   const std::string hdr = JitHeader(f);
   // experiments: extra -D options for the specialised build, e.g. CGX_JIT_DEFS="-DCGX_ROT=0 -DCGX_BACKOFF_NS=100"
   const char* extra = getenv("CGX_JIT_DEFS");
@@ -137,7 +129,7 @@ bool JitCompileCubin(const FlatDev& f, int tiles, std::vector<char>& cubin, std:
       }
     }
   }
-  const std::string key = hdr + (tiles == 1 ? "#1" : "#2") + (extra ? extra : "");
+  const std::string key = hdr + "#m" + std::to_string(mode) + (extra ? extra : "");
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_cubins.find(key);
@@ -154,12 +146,13 @@ bool JitCompileCubin(const FlatDev& f, int tiles, std::vector<char>& cubin, std:
   const char* hsrc[] = {kSrcScanCommon, kSrcScanParams, hdr.c_str()};
   const char* hname[] = {"scan_common.cuh", "scan_params.h", "cgx_jit_prog.h"};
   nvrtcProgram prog;
-  if (n.create(&prog, kSrcScanFlat, "scan_flat.cu", 3, hsrc, hname) != NVRTC_SUCCESS) {
+  if (n.create(&prog, kSrcScanBits, "scan_bits.cu", 3, hsrc, hname) != NVRTC_SUCCESS) {
     err = "nvrtcCreateProgram failed";
     return false;
   }
+  const std::string mode_def = "-DCGX_JIT_MODE=" + std::to_string(mode);
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DCGX_JIT=1",
-                                   tiles == 1 ? "-DCGX_TILES=1" : "-DCGX_TILES=2"};
+                                   mode_def.c_str()};
   for (auto& o : xo) opts.push_back(o.c_str());
   const nvrtcResult rc = n.compile(prog, (int)opts.size(), opts.data());
   if (rc != NVRTC_SUCCESS) {
@@ -181,7 +174,7 @@ bool JitCompileCubin(const FlatDev& f, int tiles, std::vector<char>& cubin, std:
   return true;
 }
 
-const JitKernel* GetJitKernel(const FlatDev& f, std::string& err) {
+const JitKernel* GetJitKernel(const FlatDev& f, int mode, std::string& err) {
   static const bool off = [] {
     const char* e = getenv("CGX_JIT");
     return e && e[0] == '0';
@@ -195,16 +188,15 @@ const JitKernel* GetJitKernel(const FlatDev& f, std::string& err) {
     err = "cudaGetDevice failed";
     return nullptr;
   }
-  const int tiles = JitTiles();
   const char* extra = getenv("CGX_JIT_DEFS");
-  const std::string hdr = JitHeader(f) + (tiles == 1 ? "#1" : "#2") + (extra ? extra : "");
+  const std::string hdr = JitHeader(f) + "#m" + std::to_string(mode) + (extra ? extra : "");
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_loaded.find({dev, hdr});
     if (it != g_loaded.end()) return it->second;
   }
   std::vector<char> cubin;
-  if (!JitCompileCubin(f, tiles, cubin, err)) return nullptr;
+  if (!JitCompileCubin(f, mode, cubin, err)) return nullptr;
   Driver& d = driver();
   if (!d.err.empty()) {
     err = d.err;
@@ -239,18 +231,20 @@ const JitKernel* GetJitKernel(const FlatDev& f, std::string& err) {
   k->smem = smem;
   k->threads = info[1];
   k->warps = info[2];
-  k->tiles = tiles;
+  k->mode = mode;
   std::lock_guard<std::mutex> lk(g_mu);
   g_loaded[{dev, hdr}] = k;
   return k;
 }
 
-cudaError_t launch_scan_flat_jit(const JitKernel* k, const ScanArgs& a, int sm_count, cudaStream_t stream) {
+cudaError_t launch_scan_flat_jit(const JitKernel* k, const ScanArgs& a, int sm_count, cudaStream_t stream,
+                                 int* grid_out) {
   if (a.nchunks == 0) return cudaSuccess;
   Driver& d = driver();
   int64_t grid = (int64_t)sm_count * k->per_sm;
   const int64_t need = (a.nchunks + k->warps - 1) / k->warps;
   if (grid > need) grid = need;
+  if (grid_out) *grid_out = (int)grid;
   void* params[] = {(void*)&a};
   const CUresult r = d.launch((CUfunction)k->func, (unsigned)grid, 1, 1, (unsigned)k->threads, 1, 1,
                               (unsigned)k->smem, (CUstream)stream, params, nullptr);

@@ -1,0 +1,1059 @@
+// scan_bits.cu — the bitstream engine, second generation: sm_100a kernel for flat deterministic
+// patterns (`\d+\.\d+\.\d+\.\d+`, `\w+@\w+\.\w+`, `[a-z]+=\d+`, `\d+`, `\w+` ...), the north-star path.
+//
+// Replaces, for a whole corpus at once:
+//   reference meta/findall.go:176-290        findAllIndicesLoop (pos = end chaining)
+//   reference meta/find_indices.go:1050-1088 DigitPrefilter loop (candidate -> SearchAtAnchored)
+//   reference simd/memchr_digit_amd64.s:26   memchrDigitAVX2
+//   reference dfa/lazy/lazy.go:219-324       SearchAtAnchored (per-byte class + table walk)
+//   reference nfa/charclass_searcher.go      FindAllIndices (lone `C+` patterns)
+//
+// Match STARTS come from a right-to-left marker pass over per-class position bitmaps, match ENDS
+// from a left-to-right pass over the same bitmaps (forced greedy == leftmost-first because the
+// host proved the pattern deterministic, host/engine.cpp DecideBitstream).  The first generation
+// (round 1) ran both passes across the warp — lane l held one 64-bit word of a 2 KB tile and every
+// step of every pass paid a shuffle for the carry, a ballot for ownership and a rank scan per tile;
+// it was bound by instruction issue at 0.31 warp-instructions per byte.  Here the passes are
+// LANE-SERIAL:
+//
+//   phase A  a warp draws a chunk of TPC tiles (ticket counter); per tile one TMA bulk copy of 2 KB
+//            into the warp's window ring, lane l classifies the 64-byte piece l (4 x LDS.128, SWAR
+//            range tests, dp4a bit packing) and stores one 64-bit word per class into the chunk's
+//            class-bitmap array in shared memory — the transposition from "lane = piece of a tile"
+//            to "lane = contiguous run of K pieces" costs one STS and one LDS per word;
+//   phase B  lane l owns the K consecutive words [K l, K l + K) of the chunk plus the first word of
+//            its neighbour (overlap).  Sweep 1 walks them right to left, sweep 2 left to right; a
+//            carry or a shifted-out bit travels from one word to the next in a register.  No
+//            shuffle, no ballot, no scan inside the passes;
+//   ownership a byte of no class ("sync byte") can be in no match, so matches never cross one.  A
+//            lane owns the starts after the first sync byte at or after its first word up to the
+//            first sync byte at or after its neighbour's first word: every start has exactly one
+//            owner, and whatever enters a lane's window from outside dies at a sync byte before it
+//            reaches an owned start;
+//   output   the passes leave two bitmaps (starts, ends) per chunk in shared memory — any number of
+//            matches fits, there is no staging overflow.  The chunk's count is published at once;
+//            one resolver warp per CTA performs the two-level decoupled look-back and hands the
+//            chunk's global offset back; the scanning warp then turns its bitmaps into int64
+//            (start,end) pairs in global match order (rank = lane prefix + position in the lane).
+//   exact    starts and ends must alternate; a lane whose words fail the check (overlapping
+//            candidates, `1.2.3.4.5`) or whose last segment has no sync byte inside the window
+//            replays the reference loop for exactly its own range (serial, rare).
+// Every corpus byte crosses HBM once; output is 16 B per match.  A FindAll launch needs no memset:
+// look-back words carry the launch's epoch, group accumulators and the ticket clean themselves.
+#include "scan_common.cuh"
+#include "scan_params.h"
+
+namespace cgx {
+
+namespace {
+
+constexpr uint32_t FULL = 0xffffffffu;
+#ifndef CGX_K
+#define CGX_K 8            // words (64-byte pieces) per lane and chunk == tiles per chunk
+#endif
+#ifndef CGX_WARPS
+#ifdef CGX_JIT
+#define CGX_WARPS 14       // scanning warps per CTA (specialised build: 1 or 2 class words per slot)
+#else
+#define CGX_WARPS 8        // the interpreting build keeps four class words per slot: fewer warps fit
+#endif
+#endif
+#ifndef CGX_CTAS
+#define CGX_CTAS 1         // resident CTAs per SM the kernel is built for
+#endif
+#ifndef CGX_NB
+#define CGX_NB 2           // window ring: tiles in flight per warp
+#endif
+constexpr int K = CGX_K;
+constexpr int FW_WARPS = CGX_WARPS;
+constexpr int FW_THREADS = (FW_WARPS + 1) * 32;  // + one resolver warp
+constexpr int FW_CTAS = CGX_CTAS;
+constexpr int NB = CGX_NB;
+constexpr int TILE = 2048;                 // one bulk copy, one classification round (64 B per lane)
+constexpr int TPC = K;                     // tiles per chunk
+constexpr int NWORDS = 32 * K;             // words of a chunk's window
+constexpr int WINDOW = NWORDS * 64;        // bytes of a chunk's window
+constexpr int CHUNKB = (NWORDS - 1) * 64;  // bytes between chunk origins: chunks overlap by one word
+constexpr int NSLOTS = 32 * (K + 1);       // word w lives in slot w + w / K (one pad slot per lane region)
+static_assert(FW_WARPS <= 31, "one CTA holds at most 31 scanning warps and the resolver");
+static_assert(K >= 2 && K <= 16, "words per lane");
+
+// ---- pipe-aware primitives (the kernel is bound by the integer ALU pipe) -------
+//  * a LOP3 takes one immediate at most; as an explicit lop3.b32 `(w ^ k) & m` is one instruction;
+//  * `x + k` as x * one + k with a multiplier the compiler cannot see through is an IMAD: same
+//    result, issued to the FMA pipe, which is otherwise idle.
+#if defined(CGX_CPU_SIM) || !defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint32_t xor_and(uint32_t w, uint32_t k, uint32_t m) { return (w ^ k) & m; }
+__device__ __forceinline__ uint32_t nor_and(uint32_t z, uint32_t w, uint32_t m) { return ~(z | w) & m; }
+__device__ __forceinline__ uint32_t mad_fma(uint32_t x, uint32_t one, uint32_t k) { return x * one + k; }
+#else
+__device__ __forceinline__ uint32_t xor_and(uint32_t w, uint32_t k, uint32_t m) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(d) : "r"(w), "r"(k), "r"(m));  // (a ^ b) & c
+  return d;
+}
+__device__ __forceinline__ uint32_t nor_and(uint32_t z, uint32_t w, uint32_t m) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(d) : "r"(z), "r"(w), "r"(m));  // ~(a | b) & c
+  return d;
+}
+__device__ __forceinline__ uint32_t mad_fma(uint32_t x, uint32_t one, uint32_t k) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(one), "r"(k));
+  return d;
+}
+#endif
+
+#ifdef CGX_JIT
+#include "cgx_jit_prog.h"  // generated per pattern (host/engine.cpp JitHeader), compiled by csrc/jit.cu
+#endif
+
+// The pattern-dependent parts exist twice: as an interpreter over ScanArgs::flat (this translation
+// unit as nvcc builds it, and the CPU emulator build), and — when the host JIT-compiles this file
+// with NVRTC for one pattern (csrc/jit.cu, -DCGX_JIT + a generated cgx_jit_prog.h) — as
+// straight-line code: no program loads, no dispatch, class constants as immediates, one search mode.
+#ifdef CGX_JIT
+#define P_NCLASSES CGX_JIT_NCLASSES
+#define P_RUNSTART CGX_JIT_RUNSTART
+#define P_MIDRUN CGX_JIT_MIDRUN
+#define P_MODE CGX_JIT_MODE
+#else
+#define P_NCLASSES f.nclasses
+#define P_RUNSTART f.bs_runstart
+#define P_MIDRUN f.bs_midrun_check
+#define P_MODE a.mode
+#endif
+#ifdef CGX_JIT
+constexpr int NC = CGX_JIT_NCLASSES;       // class words per slot
+constexpr int NSTATE = CGX_JIT_NSTATE;     // per-step carry / shift state of a sweep
+#else
+constexpr int NC = 4;
+constexpr int NSTATE = 24;
+#endif
+constexpr int NPAIR = (NC + 1) / 2;        // 16-byte slot arrays: classes (0,1) and (2,3)
+
+struct alignas(16) Slot {
+  uint64_t a, b;
+};
+struct WarpSmem {
+  alignas(128) uint8_t win[NB][TILE];
+  // class bitmaps of the chunk being scanned; after sweep 2 array 0 holds (starts, ends) instead.
+  // Two buffers: a chunk's result waits here for its global offset while the next chunk is scanned.
+  Slot cls[2][NPAIR][NSLOTS];
+  uint64_t mk[NSLOTS];        // sweep 1 -> sweep 2: "a match can start here", forward orientation
+  uint64_t mbar[NB];
+  uint32_t rank[2][32];       // per buffer and lane: starts before the lane | ends before it << 16
+  // matches of a serially replayed segment that end beyond the chunk's bitmap (per buffer):
+  // found again, and stored, when the chunk's offset is known
+  int64_t far_from[2], far_stop[2];
+  uint32_t far_cnt[2];
+  uint32_t bits_cnt[2];       // matches recorded in the bitmaps
+};
+// a scanned chunk handed from a scanning warp to the CTA's resolver warp (one slot per buffer)
+struct Mail {
+  volatile int state;  // 0 = buffer free, 1 = chunk waits for its offset, 2 = offset known
+  unsigned cnt;
+  int64_t chunk;
+  unsigned long long excl;  // state 2: global index of the chunk's first match
+};
+struct CtaSmem {
+  WarpSmem w[FW_WARPS];
+  Mail mail[FW_WARPS][2];
+  volatile int done[FW_WARPS];
+};
+
+__device__ __forceinline__ uint64_t mk64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+__device__ __forceinline__ uint32_t lo32(uint64_t x) { return (uint32_t)x; }
+__device__ __forceinline__ uint32_t hi32(uint64_t x) { return (uint32_t)(x >> 32); }
+
+// 64-bit x + y + cin (cin is 0 or 1) with the carry out as a 0/1 register: the carry enters and
+// leaves through the adder's flag (four IADD3) — no 64-bit compares.
+__device__ __forceinline__ uint64_t adc64(uint64_t x, uint64_t y, uint32_t& carry) {
+#if defined(CGX_CPU_SIM) || !defined(__CUDA_ARCH__)
+  const uint64_t s1 = x + y;
+  const uint64_t s2 = s1 + carry;
+  carry = (s1 < x || s2 < s1) ? 1u : 0u;
+  return s2;
+#else
+  uint32_t lo, hi, c = carry;
+  asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %3, 0xffffffff;\n\taddc.cc.u32 %0, %4, %6;\n\taddc.cc.u32 %1, %5, %7;\n\t"
+      "addc.u32 %2, 0, 0;\n\t}"
+      : "=r"(lo), "=r"(hi), "=r"(carry)
+      : "r"(c), "r"(lo32(x)), "r"(hi32(x)), "r"(lo32(y)), "r"(hi32(y)));
+  return mk64(hi, lo);
+#endif
+}
+// markers move s positions (1 or 2) towards higher bit indices; `below` is the high half of the word
+// processed before this one (its top bits enter at the bottom)
+template <int S>
+__device__ __forceinline__ uint64_t shl_in(uint64_t m, uint32_t below) {
+  return mk64(__funnelshift_l(lo32(m), hi32(m), S), __funnelshift_l(below, lo32(m), S));
+}
+__device__ __forceinline__ uint64_t brev64(uint64_t x) { return mk64(__brev(lo32(x)), __brev(hi32(x))); }
+
+// ---- classification ----------------------------------------------------------------------------
+// 8 flag words (bit 7 of a byte set <=> byte in class) -> bit-reversed 32-bit mask (bit 31-b <=> byte b).
+// Each dp4a pair gathers 8 flags into bits 7..14; the groups are chained through the accumulator
+// input (shifted by 8 each time: IMAD.SHL, FMA pipe) and the last one is joined by a multiply-add,
+// so the whole pack costs one ALU-pipe instruction (the final right shift).
+__device__ __forceinline__ uint32_t pack_rev(const uint32_t* fl, uint32_t one) {
+  uint32_t acc = __dp4a(fl[0], 0x10204080u, 0u);
+  acc = __dp4a(fl[1], 0x01020408u, acc);
+  acc = __dp4a(fl[2], 0x10204080u, acc << 8);
+  acc = __dp4a(fl[3], 0x01020408u, acc);
+  acc = __dp4a(fl[4], 0x10204080u, acc << 8);
+  acc = __dp4a(fl[5], 0x01020408u, acc);  // 24 flags in bits 7..30
+  uint32_t last = __dp4a(fl[6], 0x10204080u, 0u);
+  last = __dp4a(fl[7], 0x01020408u, last);
+  return mad_fma(acc, one + one, last >> 7);
+}
+
+// class C of the 64 bytes in w: reversed orientation (bit 63-b <=> byte b)
+template <int C>
+__device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t (&w)[16], uint32_t one) {
+  uint32_t fl[16];
+#ifdef CGX_JIT
+#pragma unroll
+  for (int k = 0; k < 16; k++) fl[k] = cgx_jit_flags<C>(w[k], one);  // generated: ranges as constants
+#else
+#pragma unroll
+  for (int k = 0; k < 16; k++) fl[k] = 0;
+  const int nr = f.cls_nranges[C];
+  for (int r = 0; r < nr; r++) {
+    const uint32_t k1 = f.cls_k1[C][r], k2 = f.cls_k2[C][r];
+    if (f.cls_mode[C][r] == 0) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const uint32_t z = mad_fma(xor_and(w[k], k1, 0x7F7F7F7Fu), one, k2);  // bit7 set <=> (x^lo)&0x7f > width
+        fl[k] |= nor_and(z, w[k], 0x80808080u);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; k++) fl[k] |= swar_in_range(w[k], k1, k2);
+    }
+  }
+#endif
+  return mk64(pack_rev(fl, one), pack_rev(fl + 8, one));  // bytes 0..31 in the high word
+}
+
+// Class bitmaps (reversed orientation) of the 64-byte piece at `p`: 4 x LDS.128.
+__device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* p, uint32_t one, uint64_t (&cm)[4]) {
+  uint32_t w[16];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p + (j << 4));
+    w[4 * j] = v.x;
+    w[4 * j + 1] = v.y;
+    w[4 * j + 2] = v.z;
+    w[4 * j + 3] = v.w;
+  }
+  cm[0] = class_rev64<0>(f, w, one);
+  cm[1] = P_NCLASSES > 1 ? class_rev64<1>(f, w, one) : 0ull;
+  cm[2] = P_NCLASSES > 2 ? class_rev64<2>(f, w, one) : 0ull;
+  cm[3] = P_NCLASSES > 3 ? class_rev64<3>(f, w, one) : 0ull;
+}
+
+// ---- marker passes, one word at a time -----------------------------------------------------------
+// Per step of a pass the lane carries two registers from the word it processed before: the adder's
+// carry and the high half of the step's input word (its top bits are what a shift brings in).
+struct PassState {
+  uint32_t hi[NSTATE];
+  uint32_t cy[NSTATE];
+};
+__device__ __forceinline__ void pass_reset(PassState& s) {
+#pragma unroll
+  for (int i = 0; i < NSTATE; i++) s.hi[i] = s.cy[i] = 0u;
+}
+
+// Right to left (reversed orientation): M = positions from which items k..end can match.
+// kind: 0 = one byte of the class, 1 = class+, 2 = class*, 3 = class?
+template <int C>
+__device__ __forceinline__ void rev_step(uint32_t kind, const uint64_t (&c)[4], uint64_t& M, uint32_t& shi, uint32_t& scy) {
+  const uint64_t Cw = c[C];
+  const uint64_t u = shl_in<1>(M, shi) & Cw;
+  shi = hi32(M);
+  if (kind == 0) {
+    M = u;
+  } else if (kind == 3) {
+    M |= u;
+  } else {
+    // extend through the run towards lower addresses; a second marker inside one run survives the
+    // carry of the first as a 1 in the sum, so the markers themselves are OR-ed back
+    const uint64_t p = (~adc64(u, Cw, scy) & Cw) | u;
+    M = kind == 1 ? p : (M | p);
+  }
+}
+// `C+ a` seen from the right: one byte of class A, then a run of class C.  q = shl1(A) & C marks the
+// run bytes that directly follow (in marker direction) a byte of A, so shl1(shl1(M) & A) & C ==
+// shl2(M) & q: the two steps cost one shift.
+template <int C>
+__device__ __forceinline__ void rev_fused(const uint64_t (&c)[4], uint64_t q, uint64_t& M, uint32_t& shi, uint32_t& scy) {
+  const uint64_t u = shl_in<2>(M, shi) & q;
+  shi = hi32(M);
+  M = (~adc64(u, c[C], scy) & c[C]) | u;
+}
+// Left to right (forward orientation): T = positions a marker stands at before item k; the forced
+// greedy choice (take the whole run / take the optional byte whenever it is there).
+template <int C>
+__device__ __forceinline__ void fwd_step(uint32_t kind, const uint64_t (&c)[4], uint64_t& T, uint32_t& shi, uint32_t& scy) {
+  const uint64_t Cw = c[C];
+  const uint64_t i = T & Cw;  // markers that can take a byte
+  if (kind == 0) {
+    T = shl_in<1>(i, shi);
+    shi = hi32(i);
+  } else if (kind == 3) {
+    T = (T & ~Cw) | shl_in<1>(i, shi);
+    shi = hi32(i);
+  } else {
+    // a marker inside a run of ones carries out to the first zero after the run
+    const uint64_t e = adc64(i, Cw, scy) & ~Cw;
+    T = kind == 1 ? e : ((T & ~Cw) | e);
+  }
+}
+
+#define CGX_CLASS_SWITCH(cls, CALL)  \
+  switch (cls) {                     \
+    case 0: { constexpr int C = 0; CALL; } break; \
+    case 1: { constexpr int C = 1; CALL; } break; \
+    case 2: { constexpr int C = 2; CALL; } break; \
+    default: { constexpr int C = 3; CALL; } break; \
+  }
+
+// the right-to-left steps for one word (c = class words, reversed); returns M
+__device__ __forceinline__ uint64_t rev_word(const FlatDev& f, const uint64_t (&c)[4], PassState& st) {
+  uint64_t M;
+#ifdef CGX_JIT
+  M = c[CGX_JIT_REV_INIT];
+#define CGX_QDEF(A, B, I)                                          \
+  const uint64_t q##A##_##B = shl_in<1>(c[A], st.hi[I]) & c[B];    \
+  st.hi[I] = hi32(c[A]);
+  CGX_JIT_REV_FUSED(CGX_QDEF)
+#define CGX_STEP(kind, cls, I) rev_step<cls>(kind, c, M, st.hi[I], st.cy[I]);
+#define CGX_FUSE(A, B, I) rev_fused<B>(c, q##A##_##B, M, st.hi[I], st.cy[I]);
+  CGX_JIT_REV_PASS(CGX_STEP, CGX_FUSE)
+#undef CGX_STEP
+#undef CGX_FUSE
+#undef CGX_QDEF
+#else
+  const int init_cls = f.rev_init_class;
+  M = init_cls == 0 ? c[0] : init_cls == 1 ? c[1] : init_cls == 2 ? c[2] : c[3];
+  const int rev_nops = f.rev_nops;
+  for (int k = 0; k < rev_nops; k++) {
+    const uint32_t op = f.rev_ops[k];
+    const uint32_t kind = op & 3u;
+    CGX_CLASS_SWITCH(op >> 2, (rev_step<C>(kind, c, M, st.hi[k], st.cy[k])));
+  }
+#endif
+  return M;
+}
+// the left-to-right steps for one word (c = class words, forward); T enters as the starts, returns the ends
+__device__ __forceinline__ uint64_t fwd_word(const FlatDev& f, const uint64_t (&c)[4], uint64_t T, PassState& st) {
+#ifdef CGX_JIT
+#define CGX_STEP(kind, cls, I) fwd_step<cls>(kind, c, T, st.hi[I], st.cy[I]);
+  CGX_JIT_FWD_PASS(CGX_STEP)
+#undef CGX_STEP
+#else
+  const int fwd_nops = f.fwd_nops;
+  for (int k = 0; k < fwd_nops; k++) {
+    const uint32_t op = f.fwd_ops[k];
+    const uint32_t kind = op & 3u;
+    CGX_CLASS_SWITCH(op >> 2, (fwd_step<C>(kind, c, T, st.hi[k], st.cy[k])));
+  }
+#endif
+  return T;
+}
+
+// Do the starts S and ends E of one word alternate (start, end, start, end ...; an end may share
+// its position with the next start)?  With in = 1 when a match is open at the word's first bit,
+// the word is consistent iff D = E - S - in, the span mask, has its edges exactly at S ^ E:
+// D ^ (D << 1 | in) == S ^ E (tests/test_sim_flat.py checks the criterion exhaustively on short
+// words).  The span mask's top bit says whether a match is still open after the word.
+__device__ __forceinline__ bool word_misordered(uint64_t S, uint64_t E, uint32_t& in) {
+  const uint64_t D = E - S - in;
+  const bool bad = (D ^ ((D << 1) | in)) != (S ^ E);
+  in = (uint32_t)(D >> 63);
+  return bad;
+}
+
+// ---- serial replay (cold) -------------------------------------------------------------------------
+__device__ __forceinline__ bool in_filter(const ScanArgs& a, uint32_t b) {
+  if (a.filter.kind == F_LUT) return __ldg(a.filter.lut + b) != 0;
+  bool r = false;
+  for (int k = 0; k < a.filter.nranges; k++) r |= (b >= a.filter.lo[k] && b <= a.filter.hi[k]);
+  return r;
+}
+__device__ __forceinline__ bool is_sync(const ScanArgs& a, uint32_t b) {
+  return (a.flat.sync_lut[b >> 5] >> (b & 31)) & 1u;
+}
+// anchored leftmost-first walk through global memory (reference dfa/lazy/lazy.go:219-324)
+__device__ __noinline__ int64_t dfa_walk_global(const ScanArgs& a, int64_t p0) {
+  unsigned s = a.dfa.start[0];
+  int64_t last = -1, p = p0;
+  while (s) {
+    if (p >= a.n) {
+      if (__ldg(a.dfa.eoi + s)) last = a.n;
+      break;
+    }
+    const uint32_t e = __ldg(a.dfa.trans + (s << 8) + __ldg(a.h + p));
+    if (e & 0x8000u) last = p;
+    s = e & 0x7FFFu;
+    p++;
+  }
+  return last;
+}
+// Cold: region-relative position of the first (or last) sync byte among the `len` bytes from global
+// position rb on; bytes at or beyond the end of input count as sync bytes; -1 when the region
+// starts the haystack (first) or holds none.
+__device__ __noinline__ int region_sync_cold(const ScanArgs& a, int64_t rb, int len, bool last, bool hay_start) {
+  if (!last) {
+    if (hay_start) return -1;
+    for (int i = 0; i < len; i++)
+      if (rb + i >= a.n || is_sync(a, __ldg(a.h + rb + i))) return i;
+    return len - 1;  // (not reached for a lane that owns something)
+  }
+  for (int i = len - 1; i >= 0; i--)
+    if (rb + i >= a.n || is_sync(a, __ldg(a.h + rb + i))) return i;
+  return -1;
+}
+__device__ __forceinline__ void smem_or64(uint64_t* w, int bit) {
+#if defined(CGX_CPU_SIM)
+  *w |= 1ull << bit;
+#else
+  atomicOr(reinterpret_cast<unsigned int*>(w) + (bit >> 5), 1u << (bit & 31));
+#endif
+}
+// The calling lane replays the reference loop (meta/findall.go:176-290 over
+// meta/find_indices.go:1050-1088) from global position `from` until the candidate search meets a
+// sync byte at or after `stop_min` (or the end of input).  A match whose end lies inside the chunk's
+// bitmap is recorded there (res != nullptr) — the others ("far", only the chunk's last segment can
+// produce them) are counted, or, when `far_out` is given, stored from index far_idx on.
+__device__ __noinline__ unsigned replay_cold(const ScanArgs& a, int64_t cb, Slot* res, int64_t from, int64_t stop_min,
+                                             int64_t* far_out, unsigned long long far_idx, unsigned* nbits) {
+  unsigned far = 0, bits = 0;
+  const int64_t n = a.n;
+  int64_t pos = from;
+  while (pos < n) {
+    int64_t d = pos;
+    bool stop = false;
+    while (d < n) {
+      const uint32_t b = __ldg(a.h + d);
+      if (in_filter(a, b)) break;
+      if (d >= stop_min && is_sync(a, b)) {
+        stop = true;
+        break;
+      }
+      d++;
+    }
+    if (stop || d >= n) break;
+    const int64_t e = dfa_walk_global(a, d);
+    if (e >= 0) {
+      const int64_t re = e - cb, rd = d - cb;
+      if (re < (int64_t)WINDOW) {
+        if (res) {
+          const int ws = (int)(rd >> 6), we = (int)(re >> 6);
+          smem_or64(&res[ws + ws / K].a, (int)(rd & 63));
+          smem_or64(&res[we + we / K].b, (int)(re & 63));
+        }
+        bits++;
+      } else {
+        if (far_out && (int64_t)(far_idx + far) < a.cap) {
+          far_out[2 * (far_idx + far)] = d + a.base;
+          far_out[2 * (far_idx + far) + 1] = e + a.base;
+        }
+        far++;
+      }
+      pos = e > d ? e : d + 1;
+    } else {
+      pos = d + 1;
+      // a failed run start fails for the whole run (digitRunSkipSafe, meta/strategy.go:525-560)
+      if (a.flat.bs_runstart)
+        while (pos < n && in_filter(a, __ldg(a.h + pos))) pos++;
+    }
+  }
+  if (nbits) *nbits = bits;
+  return far;
+}
+
+// ---- two-level look-back ------------------------------------------------------------------------------
+// Chunk c publishes its match count in status[c] (flag LB_AGG).  Chunks form groups of 32; the
+// warp that finishes a group's last chunk publishes the group's sum in gstatus[g] (LB_AGG), and
+// whoever learns the prefix at a group's start publishes it as gstatus[g-1] (LB_PREFIX, the
+// inclusive prefix through group g-1).  The exclusive prefix of chunk c is therefore: counts of the
+// earlier chunks of its own group (one 32-wide load) + a decoupled look-back over GROUP words.
+// Words carry the launch's epoch (bits 42..61): a word of another epoch reads as empty, so nothing
+// has to be cleared between launches.
+constexpr int EP_SHIFT = 42;
+constexpr unsigned long long EP_MASK = 0xFFFFFull << EP_SHIFT;
+constexpr unsigned long long VAL_MASK = (1ull << EP_SHIFT) - 1;
+__device__ __forceinline__ unsigned long long ep_word(const ScanArgs& a, unsigned long long flag, unsigned long long v) {
+  return flag | ((unsigned long long)a.epoch << EP_SHIFT) | v;
+}
+// flag of a word as this launch sees it (0 = empty / stale)
+__device__ __forceinline__ unsigned ep_flag(const ScanArgs& a, unsigned long long v) {
+  return ((v & EP_MASK) >> EP_SHIFT) == (unsigned long long)a.epoch ? (unsigned)(v >> 62) : 0u;
+}
+__device__ unsigned long long lb_resolve(const ScanArgs& a, int64_t chunk, int lane) {
+  const int64_t g = chunk >> 5;
+  const int64_t idx1 = (g << 5) + lane;
+  unsigned long long excl = 0, gpre = 0;
+  bool have1 = false, have2 = g == 0;
+  int64_t look = g - 1;
+  for (;;) {
+    // both levels are requested before either is looked at: one L2 round trip per attempt
+    unsigned f1 = 1u, f2 = 2u;          // lanes beyond the chunk contribute nothing; before group 0: zero prefix
+    unsigned long long v1 = 0, v = 0;
+    if (!have1 && idx1 < chunk) {
+      v1 = ld_status(&a.status[idx1]);
+      f1 = ep_flag(a, v1);
+    }
+    const int64_t idx2 = look - lane;
+    if (!have2 && idx2 >= 0) {
+      v = ld_status(&a.gstatus[idx2]);
+      f2 = ep_flag(a, v);
+    }
+    if (!have1 && __all_sync(FULL, f1 != 0u)) {
+      excl = __reduce_add_sync(FULL, (unsigned)(v1 & 0xFFFFFFFFull));
+      have1 = true;
+    }
+    if (!have2) {
+      const uint32_t empty = __ballot_sync(FULL, f2 == 0u);
+      const uint32_t pm = __ballot_sync(FULL, f2 == 2u);
+      const int fe = empty ? __ffs((int)empty) - 1 : 32;
+      const int fp = pm ? __ffs((int)pm) - 1 : 32;
+      if (fp < fe) {
+        // sums of the groups before the prefix, then the prefix itself
+        const unsigned part = __reduce_add_sync(FULL, lane < fp ? (unsigned)(v & 0xFFFFFFFFull) : 0u);
+        gpre += part + __shfl_sync(FULL, v & VAL_MASK, fp);
+        have2 = true;
+        // the inclusive prefix through the previous group, for everybody behind us
+        if (lane == 0 && (look != g - 1 || fp != 0)) st_status(&a.gstatus[g - 1], ep_word(a, LB_PREFIX, gpre));
+      } else if (fe > 0) {
+        gpre += __reduce_add_sync(FULL, lane < fe ? (unsigned)(v & 0xFFFFFFFFull) : 0u);
+        look -= fe;
+        if (fe == 32) continue;  // a full window of sums: keep walking without a pause
+      }
+    }
+    if (have1 && have2) return excl + gpre;
+    cgx_backoff();
+  }
+}
+
+// publishes the chunk's count; the warp that completes a group publishes the group's sum.  One
+// 64-bit atomic carries both the arrival count (bits 40..) and the running sum (bits 0..39), so the
+// last arrival knows the group's total without re-reading anything — and puts the accumulator back
+// to zero for the next launch.
+__device__ __forceinline__ void publish_count(const ScanArgs& a, int64_t chunk, unsigned cnt, int lane) {
+  if (lane == 0) {
+    const int64_t g = chunk >> 5;
+    const int64_t members = a.nchunks - (g << 5) < 32 ? a.nchunks - (g << 5) : 32;
+    st_status(&a.status[chunk], ep_word(a, LB_AGG, cnt));
+    const unsigned long long old = atomicAdd(&a.gacc[g], (1ull << 40) | cnt);
+    if ((int64_t)(old >> 40) == members - 1) {
+      st_status(&a.gstatus[g], ep_word(a, LB_AGG, (old & ((1ull << 40) - 1)) + cnt));
+      a.gacc[g] = 0ull;
+    }
+  }
+}
+
+// The resolver warp: takes the oldest handed-over chunk of its CTA (a younger one cannot resolve
+// before it: both need every earlier count), waits for its offset and hands the offset back; the
+// scanning warp stores its own matches when it next needs the buffer.
+__device__ void resolver_warp(const ScanArgs& a, CtaSmem& cs, int lane) {
+  for (;;) {
+    // lane l looks at slots l and l + 32 (slot s = warp s >> 1, buffer s & 1)
+    unsigned mine = 0xFFFFFFFFu;  // chunk numbers are 32-bit tickets
+    int myslot = 0;
+    bool all_done = true;
+#pragma unroll
+    for (int s = lane; s < 2 * FW_WARPS; s += 32) {
+      const Mail& m = cs.mail[s >> 1][s & 1];
+      all_done = all_done && cs.done[s >> 1] != 0;  // read BEFORE the slot: a warp hands over, then sets done
+      cgx_fence_block();
+      if (m.state == 1 && (unsigned)m.chunk < mine) {
+        mine = (unsigned)m.chunk;
+        myslot = s;
+      }
+    }
+    const unsigned best = __reduce_min_sync(FULL, mine);
+    if (best == 0xFFFFFFFFu) {
+      if (__all_sync(FULL, all_done)) return;
+      cgx_idle();  // nothing handed over: a chunk takes tens of microseconds to scan
+      continue;
+    }
+    const int slot = __shfl_sync(FULL, myslot, __ffs((int)__ballot_sync(FULL, mine == best)) - 1);
+    const unsigned long long excl = lb_resolve(a, (int64_t)best, lane);
+    if (lane == 0) {
+      Mail& m = cs.mail[slot >> 1][slot & 1];
+      m.excl = excl;
+      cgx_fence_block();
+      m.state = 2;
+    }
+  }
+}
+
+// ---- output: bitmaps -> int64 pairs in global match order ---------------------------------------------
+// Lane l turns the bits of its K words into positions: the i-th start of the chunk goes to
+// out[2 (excl + i)], the i-th end to out[2 (excl + i) + 1].  Starts and ends are independent
+// streams (a match that starts in one lane's words may end in the next lane's).
+__device__ __forceinline__ void extract(const ScanArgs& a, WarpSmem& ws, int sb, int64_t chunk, unsigned long long excl,
+                                        int lane) {
+  const Slot* res = ws.cls[sb][0] + lane * (K + 1);
+  const uint32_t rk = ws.rank[sb][lane];
+  unsigned long long is = excl + (rk & 0xFFFFu), ie = excl + (rk >> 16);
+  const int64_t wb = chunk * (int64_t)CHUNKB + a.base + (int64_t)lane * (K * 64);
+  const unsigned long long cap = (unsigned long long)a.cap;
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {
+    const Slot v = res[j];
+    const int64_t pb = wb + j * 64;
+    uint32_t slo = lo32(v.a), shi = hi32(v.a), elo = lo32(v.b), ehi = hi32(v.b);
+    // one start and one end per round: usually 0..2 rounds
+    while (slo | shi | elo | ehi) {
+      {
+        const bool l = slo != 0u;
+        const uint32_t w = l ? slo : shi;
+        if (w) {
+          const int64_t pos = pb + (l ? 0 : 32) + (__ffs((int)w) - 1);
+          if (is < cap) a.out[2 * is] = pos;
+          is++;
+          const uint32_t w2 = w & (w - 1u);
+          slo = l ? w2 : 0u;
+          shi = l ? shi : w2;
+        }
+      }
+      {
+        const bool l = elo != 0u;
+        const uint32_t w = l ? elo : ehi;
+        if (w) {
+          const int64_t pos = pb + (l ? 0 : 32) + (__ffs((int)w) - 1);
+          if (ie < cap) a.out[2 * ie + 1] = pos;
+          ie++;
+          const uint32_t w2 = w & (w - 1u);
+          elo = l ? w2 : 0u;
+          ehi = l ? ehi : w2;
+        }
+      }
+    }
+  }
+  // matches of a replayed segment that end beyond the bitmap: found again, stored after the others
+  if (lane == 0 && ws.far_cnt[sb])
+    replay_cold(a, chunk * (int64_t)CHUNKB, nullptr, ws.far_from[sb], ws.far_stop[sb], a.out, excl + ws.bits_cnt[sb],
+                nullptr);
+}
+
+}  // namespace
+
+#ifdef CGX_JIT
+#ifndef CGX_CPU_SIM
+// the loader (jit.cu) reads the launch shape from the module it just built
+extern "C" __device__ const int cgx_flat_jit_info[4] = {(int)sizeof(CtaSmem), FW_THREADS, FW_WARPS, FW_CTAS};
+#endif
+extern "C" __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) cgx_flat_jit(const __grid_constant__ ScanArgs a) {
+#else
+namespace {
+__global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __grid_constant__ ScanArgs a) {
+#endif
+  CGX_DYN_SMEM(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  CtaSmem& cs = *reinterpret_cast<CtaSmem*>(smem_raw);
+  const FlatDev& f = a.flat;
+  if (tid < 2 * FW_WARPS) {
+    cs.mail[tid >> 1][tid & 1].state = 0;
+    cs.done[tid >> 1] = 0;
+  }
+  static_assert(2 * FW_WARPS <= FW_THREADS, "one thread per mail slot at start-up");
+  if (warp < FW_WARPS && lane == 0) {
+#pragma unroll
+    for (int b = 0; b < NB; b++) mbar_init(&cs.w[warp].mbar[b], 1);
+    fence_mbar_init();
+  }
+  cgx_syncthreads();
+  if (warp == FW_WARPS) {
+    if (P_MODE == M_FINDALL) resolver_warp(a, cs, lane);
+    return;
+  }
+  WarpSmem& ws = cs.w[warp];
+  const unsigned nch = (unsigned)a.nchunks;
+  const unsigned nwarps_total = gridDim.x * FW_WARPS;
+  // a 1 the compiler cannot fold (a launch has at least one chunk): multiplier of mad_fma
+  const uint32_t one = (uint32_t)(a.nchunks > 0);
+
+  // tickets: every scanning warp draws until it gets one past the last chunk; the warp that draws
+  // the very last ticket of the launch puts the counter back to zero
+  auto take_ticket = [&]() -> unsigned {
+    unsigned t = 0;
+    if (lane == 0) {
+      if (P_MODE == M_ISMATCH && *((volatile unsigned long long*)&a.total[1])) {
+        t = 0xFFFFFFFFu;
+      } else {
+        t = atomicAdd(a.ticket, 1u);
+        if (P_MODE != M_ISMATCH && t == nch + nwarps_total - 1u) *a.ticket = 0u;
+      }
+    }
+    return __shfl_sync(FULL, t, 0);
+  };
+  // ---- window ring: tile number `seq` (running count per warp) lives in buffer seq % NB ----
+  // The prefetcher runs NB tiles ahead of the classifier, across chunk borders: pf_src walks through
+  // the chunk being prefetched (lane 0's copy is the one used), pf_left counts its tiles still to
+  // be requested, pf_whole says that all of its windows lie inside the input (no bounds to look at).
+  unsigned issued = 0, consumed = 0;
+  const uint8_t* pf_src = a.h;
+  int pf_left = 0;
+  bool pf_whole = false;
+  auto prefetch_chunk = [&](unsigned chunk) {
+    const int64_t cbeg = chunk * (int64_t)CHUNKB;
+    pf_src = a.h + cbeg;
+    pf_left = TPC;
+    pf_whole = cbeg + WINDOW <= a.n;
+  };
+  auto issue_next = [&]() {
+    if (lane == 0) {
+      const int b = issued % NB;
+      if (pf_whole) {  // the common case: a whole tile
+        mbar_expect_tx(&ws.mbar[b], (uint32_t)TILE);
+        tma_load_1d(ws.win[b], pf_src, (uint32_t)TILE, &ws.mbar[b]);
+      } else {
+        const int64_t left = a.n - (pf_src - a.h);
+        if (left > 0) {
+          // whole 16-byte blocks: the last block may run up to 15 bytes past n, inside the caller's
+          // 16-byte aligned allocation granule; those bytes are masked out below (nv)
+          const uint32_t bulk = left >= TILE ? (uint32_t)TILE : (uint32_t)((left + 15) & ~(int64_t)15);
+          mbar_expect_tx(&ws.mbar[b], bulk);
+          tma_load_1d(ws.win[b], pf_src, bulk, &ws.mbar[b]);
+        } else {
+          mbar_arrive(&ws.mbar[b]);
+        }
+      }
+    }
+    pf_src += TILE;
+    pf_left--;
+    issued++;
+  };
+  // Stores the matches of the chunk parked in buffer b (if any) once the resolver has supplied its
+  // offset; returns whether the buffer is free afterwards.  Blocking, or one look.
+  auto flush = [&](int b, bool block) -> bool {
+    Mail& m = cs.mail[warp][b];
+    for (;;) {
+      int st = 0;
+      if (lane == 0) st = m.state;
+      st = __shfl_sync(FULL, st, 0);
+      if (st == 0) return true;
+      if (st == 2) break;
+      if (!block) return false;
+      cgx_backoff();
+    }
+    cgx_fence_block();
+    const int64_t chunk = m.chunk;
+    const unsigned long long excl = m.excl;
+    if (lane == 0 && chunk == (int64_t)nch - 1) {
+      a.total[0] = excl + m.cnt;
+      a.total[1] = (excl + m.cnt) ? 1ull : 0ull;
+      if (a.result) {
+        a.result[0] = excl + m.cnt;
+        a.result[1] = (excl + m.cnt) ? 1ull : 0ull;
+      }
+    }
+    extract(a, ws, b, chunk, excl, lane);
+    __syncwarp();
+    if (lane == 0) m.state = 0;
+    __syncwarp();
+    return true;
+  };
+
+  unsigned cur = take_ticket();
+  unsigned nxt = 0xFFFFFFFEu;  // none
+  static_assert(NB <= TPC, "the ring never holds more than one chunk");
+  if (cur < nch) {
+    prefetch_chunk(cur);
+#pragma unroll
+    for (int t = 0; t < NB; t++) issue_next();
+  }
+  int sb = 0;
+  while (cur < nch) {
+    const int64_t cb = cur * (int64_t)CHUNKB;
+    // the buffer this chunk's bitmaps go to must have been emptied (its chunk is two tickets old)
+    if (P_MODE == M_FINDALL) flush(sb, true);
+    Slot(*cls)[NSLOTS] = ws.cls[sb];
+
+    // ================= phase A: classify the chunk's tiles into class bitmaps ====================
+    const bool whole = cb + WINDOW <= a.n;
+#pragma unroll 1
+    for (int t = 0; t < TPC; t++) {
+      const int b = consumed % NB;
+      mbar_wait(&ws.mbar[b], (consumed / NB) & 1u);
+      consumed++;
+      uint64_t cm[4];
+      classify_piece(f, ws.win[b] + lane * 64, one, cm);
+      // every lane holds its piece in registers: the buffer can take the tile NB ahead
+      __syncwarp();
+      if (pf_left == 0 && t + NB == TPC) {  // the ring moves on to the next chunk
+        nxt = take_ticket();
+        if (nxt < nch) prefetch_chunk(nxt);
+      }
+      if (pf_left) issue_next();
+      if (!whole) {
+        // bytes at or beyond the end of input belong to no class.  Reversed bit r <=> byte 63 - r
+        const int64_t v = a.n - (cb + (int64_t)t * TILE + lane * 64);  // valid bytes of this piece
+        const uint64_t m = v >= 64 ? ~0ull : (v <= 0 ? 0ull : (~0ull << (64 - v)));
+#pragma unroll
+        for (int c = 0; c < 4; c++) cm[c] &= m;
+      }
+      const int w = t * 32 + lane;
+      const int s = w + w / K;
+      cls[0][s] = Slot{cm[0], cm[1]};
+      if (NPAIR > 1) cls[NPAIR - 1][s] = Slot{cm[2], cm[3]};
+    }
+    __syncwarp();
+
+    // ================= phase B: lane-serial marker sweeps over K words + the neighbour's first ======
+    // lane 31's neighbour word would lie outside the window: its own last word is the overlap
+    const int ovl = lane == 31 ? K - 1 : K;
+    // slot of the lane's word 0; its words follow, then the region's pad slot, then the neighbour's word 0
+    const int s0 = lane * (K + 1);
+    auto slot_of = [&](int j) { return s0 + j + (j == K ? 1 : 0); };
+    PassState st;
+    // ---- sweep 1, right to left: where can a match start (reversed orientation) ----
+    pass_reset(st);
+#pragma unroll 1
+    for (int j = K; j >= 0; j--) {
+      if (j <= ovl) {
+        uint64_t c[4];
+        {
+          const Slot v = cls[0][slot_of(j)];
+          c[0] = v.a;
+          c[1] = v.b;
+          c[2] = c[3] = 0ull;
+          if (NPAIR > 1) {
+            const Slot v2 = cls[NPAIR - 1][slot_of(j)];
+            c[2] = v2.a;
+            c[3] = v2.b;
+          }
+        }
+        const uint64_t M = rev_word(f, c, st);
+        if (j < K) {
+          // what the lane computes for its own words is what everybody uses: forward orientation
+          ws.mk[s0 + j] = brev64(M);
+          cls[0][s0 + j] = Slot{brev64(c[0]), brev64(c[1])};
+          if (NPAIR > 1) cls[NPAIR - 1][s0 + j] = Slot{brev64(c[2]), brev64(c[3])};
+        }
+      }
+      if (j == K) __syncwarp();  // the neighbour's word 0 was read before the neighbour rewrites it (at j == 0)
+    }
+    __syncwarp();
+
+    // ---- sweep 2, left to right: owned starts, their ends, alternation check ----
+    // Results replace the class words in place, except at the two ends of the region, whose class
+    // words the neighbours still read: word 0's result waits in the region's pad slot, the overlap
+    // word's result (it belongs to the neighbour's word 0) in two dead words of `mk`.
+    pass_reset(st);
+    uint32_t seen = (cur == 0u && lane == 0) ? FULL : 0u;  // the start of the haystack counts as a sync byte before it
+    uint32_t in = 0u, c0hi = 0u;
+    bool bad = false, open = false;
+    unsigned cS = 0u, cE = 0u;
+    static_assert(K >= 3, "the overlap word's result is parked in mk[1..2] of the lane's region");
+#pragma unroll 1
+    for (int j = 0; j <= K; j++) {
+      if (j <= ovl) {
+        uint64_t c[4];
+        {
+          const Slot v = cls[0][slot_of(j)];
+          c[0] = v.a;
+          c[1] = v.b;
+          c[2] = c[3] = 0ull;
+          if (NPAIR > 1) {
+            const Slot v2 = cls[NPAIR - 1][slot_of(j)];
+            c[2] = v2.a;
+            c[3] = v2.b;
+          }
+        }
+        uint64_t M = ws.mk[slot_of(j)];
+        uint64_t own = ~0ull;
+        if (seen == 0u || j == ovl) {
+          uint64_t U = c[0] | c[1];
+          if (NC > 2) U |= c[2] | c[3];
+          const uint64_t nz = ~U;                  // sync bytes of this word
+          const uint64_t upto = nz ^ (nz - 1ull);  // bits up to and including the first sync byte (all ones if none)
+          // owned: after the lane's first sync byte ...
+          own = seen ? ~0ull : ~upto;
+          if (nz) seen = FULL;
+          // ... up to the first sync byte of the neighbour's first word
+          if (j == ovl) {
+            own &= upto;
+            open = nz == 0ull;
+          }
+        }
+        const uint64_t c0prev = shl_in<1>(c[0], c0hi);
+        c0hi = hi32(c[0]);
+        // only the first byte of a run of class 0 (pattern opens with C+)
+        if (P_RUNSTART) M &= c[0] & ~c0prev;
+        const uint64_t S = M & own;
+        const uint64_t E = fwd_word(f, c, S, st) & own;
+        bad |= word_misordered(S, E, in);
+        // (an end in the middle of a class-0 run: the reference resumes there, which is no run start)
+        if (P_MIDRUN) bad |= (E & c[0] & c0prev) != 0ull;
+        if (j == K) {
+          ws.mk[s0 + 1] = S;
+          ws.mk[s0 + 2] = E;
+        } else {
+          cls[0][s0 + (j == 0 ? K : j)] = Slot{S, E};
+          cS += __popcll(S);
+          cE += __popcll(E);
+        }
+      }
+    }
+    bad |= in != 0u;
+    // ---- lanes that need the reference loop: clear what the sweeps left in the affected range ----
+    const bool replay = bad || (open && seen);
+    int64_t rp_from = 0, rp_stop = 0;
+    if (replay) {
+      // bad: everything the lane owns; open only: the segment after the lane's last sync byte
+      const int64_t rb = cb + (int64_t)lane * (K * 64);
+      const int keep = region_sync_cold(a, rb, ovl * 64, /*last=*/!bad, cur == 0u && lane == 0);  // bits <= keep stay
+      rp_from = rb + keep + 1;
+      rp_stop = bad ? rb + (int64_t)ovl * 64 : rp_from;
+      if (rp_stop < rp_from) rp_stop = rp_from;
+      cS = cE = 0u;
+      for (int j = 0; j <= ovl; j++) {
+        const int lo = keep + 1 - j * 64;  // first bit of word j to clear
+        const uint64_t m = lo <= 0 ? 0ull : (lo >= 64 ? ~0ull : ((1ull << lo) - 1ull));
+        if (j == K) {
+          ws.mk[s0 + 1] &= m;
+          ws.mk[s0 + 2] &= m;
+        } else {
+          Slot v = cls[0][s0 + (j == 0 ? K : j)];
+          v.a &= m;
+          v.b &= m;
+          cls[0][s0 + (j == 0 ? K : j)] = v;
+          cS += __popcll(v.a);
+          cE += __popcll(v.b);
+        }
+      }
+    }
+    __syncwarp();
+    // ---- word 0 = own result (pad slot) | what the left neighbour found in it (its overlap word) ----
+    {
+      Slot v = cls[0][s0 + K];
+      if (lane > 0) {
+        const uint64_t rs = ws.mk[s0 - (K + 1) + 1], re = ws.mk[s0 - (K + 1) + 2];
+        v.a |= rs;
+        v.b |= re;
+        cS += __popcll(rs);
+        cE += __popcll(re);
+      }
+      cls[0][s0] = v;
+    }
+    __syncwarp();
+    unsigned far = 0u;
+    if (__any_sync(FULL, replay)) {
+      if (lane == 0) atomicAdd(&a.total[2], 1ull);  // diagnostics: chunks with a serial replay (cgx_debug_scratch)
+      if (replay) {
+        unsigned nb = 0;
+        far = replay_cold(a, cb, cls[0], rp_from, rp_stop, nullptr, 0ull, &nb);
+        if (far) {
+          ws.far_from[sb] = rp_from;
+          ws.far_stop[sb] = rp_stop;
+        }
+      }
+      __syncwarp();
+      // bits may have landed in other lanes' words: count again
+      cS = cE = 0u;
+      for (int j = 0; j < K; j++) {
+        const Slot v = cls[0][s0 + j];
+        cS += __popcll(v.a);
+        cE += __popcll(v.b);
+      }
+    }
+    // ---- counts and ranks ----
+    uint32_t x = cS | (cE << 16);
+    const uint32_t mine = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(FULL, x, d);
+      if (lane >= d) x += y;
+    }
+    const uint32_t tot = __shfl_sync(FULL, x, 31);
+    const unsigned nbits = tot & 0xFFFFu;
+    const unsigned nfar = __reduce_add_sync(FULL, far);
+    const unsigned cnt = nbits + nfar;
+    if (P_MODE == M_FINDALL) {
+      ws.rank[sb][lane] = x - mine;
+      if (lane == 0) {
+        ws.far_cnt[sb] = nfar;
+        ws.bits_cnt[sb] = nbits;
+      }
+      publish_count(a, cur, cnt, lane);  // everybody behind us can go on
+      __syncwarp();
+      if (lane == 0) {
+        Mail& m = cs.mail[warp][sb];
+        m.chunk = cur;
+        m.cnt = cnt;
+        cgx_fence_block();
+        m.state = 1;
+      }
+      sb ^= 1;
+    } else if (cnt && lane == 0) {
+      atomicAdd(a.total, (unsigned long long)cnt);
+      a.total[1] = 1ull;
+    }
+    cur = nxt;
+    nxt = 0xFFFFFFFEu;
+  }
+  if (P_MODE == M_FINDALL) {
+    flush(sb, true);
+    flush(sb ^ 1, true);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    cgx_fence_block();
+    cs.done[warp] = 1;
+  }
+}
+#ifndef CGX_JIT
+}  // namespace
+#endif
+
+#if !defined(CGX_JIT) || defined(CGX_CPU_SIM)
+int64_t scan_flat_chunks(int64_t n) {
+  if (n <= 0) return 0;
+  return (n + CHUNKB - 1) / CHUNKB;
+}
+
+size_t scan_flat_smem_bytes() { return sizeof(CtaSmem); }
+int scan_flat_threads() { return FW_THREADS; }
+int scan_flat_warps() { return FW_WARPS; }
+
+#ifdef CGX_CPU_SIM
+void sim_launch_scan_flat(const ScanArgs& a, unsigned grid) {
+#ifdef CGX_JIT
+  sim::launch<ScanArgs>(cgx_flat_jit, grid, FW_THREADS, sizeof(CtaSmem), a);
+#else
+  sim::launch<ScanArgs>(scan_flat_kernel, grid, FW_THREADS, sizeof(CtaSmem), a);
+#endif
+}
+#else
+// Launches the scan on `stream`.  See capi.cu for what must be zero before the launch.
+cudaError_t launch_scan_flat(const ScanArgs& a, int sm_count, cudaStream_t stream, int* grid_out) {
+  if (a.nchunks == 0) return cudaSuccess;
+  const size_t smem = sizeof(CtaSmem);
+  static bool configured = false;
+  static int per_sm = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(scan_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_flat_kernel, FW_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    configured = true;
+  }
+  int64_t grid = (int64_t)sm_count * per_sm;
+  const int64_t need = (a.nchunks + FW_WARPS - 1) / FW_WARPS;
+  if (grid > need) grid = need;
+  if (grid_out) *grid_out = (int)grid;
+  scan_flat_kernel<<<(unsigned)grid, FW_THREADS, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+#endif
+
+#endif  // host side
+
+}  // namespace cgx

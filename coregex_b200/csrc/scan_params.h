@@ -123,6 +123,12 @@ struct ScanArgs {
   // bitstream kernel: one word and one arrival accumulator per group of 32 chunks (zeroed before launch)
   unsigned long long* gstatus;
   unsigned long long* gacc;
+  // bitstream kernel: look-back words of another epoch read as empty (nothing is cleared between
+  // launches; 1 .. 0xFFFFF, the host clears the words when the counter wraps)
+  unsigned int epoch;
+  // bitstream kernel, FindAll: {total, is-match flag} also written here by the kernel itself
+  // (device pointer, may be null), so that a FindAll call is exactly one launch
+  unsigned long long* result;
 };
 
 }  // namespace cgx

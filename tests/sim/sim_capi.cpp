@@ -1,4 +1,4 @@
-// sim_capi.cpp — TEST HARNESS ONLY: runs the bitstream kernel SOURCE (scan_flat.cu compiled with
+// sim_capi.cpp — TEST HARNESS ONLY: runs the bitstream kernel SOURCE (scan_bits.cu compiled with
 // -DCGX_CPU_SIM against tests/sim/simt_cpu.h) on the CPU SIMT emulator, with the tables the real
 // host compiler produces.  Used by tests/test_sim_flat.py to debug warp-level logic without a GPU.
 #include <cstdint>
@@ -34,7 +34,7 @@ int cgxsim_jit_header(const char* pat, size_t plen, char* out, size_t cap) {
 
 // returns 0 ok, -1 compile error, -2 pattern not eligible for the bitstream engine
 int cgxsim_scan(const char* pat, size_t plen, const uint8_t* h, int64_t n, int64_t base, int mode,
-                int64_t* out, int64_t cap, uint64_t result[4], unsigned grid, int pad_byte) {
+                int64_t* out, int64_t cap, uint64_t result[4], unsigned grid, int pad_byte, int launches) {
   std::unique_ptr<Compiled> c;
   std::string err;
   if (CompilePattern(std::string(pat, plen), c, err) != COMPILE_OK) return -1;
@@ -79,7 +79,24 @@ int cgxsim_scan(const char* pat, size_t plen, const uint8_t* h, int64_t n, int64
   a.nchunks = nchunks;
   a.gstatus = gstatus.data();
   a.gacc = gacc.data();
-  if (nchunks) sim_launch_scan_flat(a, grid);
+  // what the host does between launches (capi.cu): words of another epoch read as empty, the
+  // accumulators and the ticket are left at zero by the kernel.  `launches` > 1 runs the kernel
+  // again on the SAME scratch, with stale look-back words from the launch before.
+  unsigned long long result_dev[2] = {~0ull, ~0ull};
+  a.result = mode == 0 ? result_dev : nullptr;
+  for (int l = 0; l < (launches > 0 ? launches : 1); l++) {
+    a.epoch = 7u + (unsigned)l;
+    if (mode != 0) memset(scratch, 0, sizeof scratch);
+    scratch[0] = scratch[1] = 0xDEADull;  // FindAll overwrites them
+    if (mode != 0) scratch[0] = scratch[1] = 0;
+    if (nchunks) sim_launch_scan_flat(a, grid);
+    if (nchunks && mode != 2 && *a.ticket != 0u) return -5;  // the ticket counter must clean itself
+    if (nchunks && mode == 0 && (result_dev[0] != scratch[0] || result_dev[1] != scratch[1])) return -6;
+    for (size_t g = 0; g < gacc.size(); g++)
+      if (gacc[g]) return -7;  // so must the group accumulators
+    if (mode == 2) *a.ticket = 0u;
+  }
+  if (!nchunks) scratch[0] = scratch[1] = 0;
   result[0] = scratch[0];
   result[1] = scratch[1];
   result[2] = scratch[2];

@@ -228,6 +228,11 @@ inline unsigned atomicAdd(unsigned* p, unsigned v) {
   *p = o + v;
   return o;
 }
+inline unsigned atomicOr(unsigned* p, unsigned v) {
+  unsigned o = *p;
+  *p = o | v;
+  return o;
+}
 inline int atomicCAS(int* p, int cmp, int val) {
   const int o = *p;
   if (o == cmp) *p = val;

@@ -22,7 +22,7 @@ def lib():
         subprocess.check_call(["make", "-C", _DIR], stdout=subprocess.DEVNULL)
         L = C.CDLL(_SO)
         L.cgxsim_scan.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
-                                  C.c_void_p, C.c_int64, C.POINTER(C.c_uint64), C.c_uint, C.c_int]
+                                  C.c_void_p, C.c_int64, C.POINTER(C.c_uint64), C.c_uint, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -34,7 +34,7 @@ class NotEligible(Exception):
 _jit_libs = {}
 
 
-def jit_lib(pattern, tiles=2, defs="", tag=""):
+def jit_lib(pattern, tiles=0, defs="", tag=""):  # `tiles` = search mode the kernel is specialised for
     """The emulated kernel built the way jit.cu builds it for the device: -DCGX_JIT plus the
     generated cgx_jit_prog.h of this pattern (straight-line passes)."""
     if isinstance(pattern, str):
@@ -54,7 +54,7 @@ def jit_lib(pattern, tiles=2, defs="", tag=""):
     hp = os.path.join(d, "cgx_jit_prog.h")
     if not os.path.exists(hp) or open(hp, "rb").read() != buf.value:
         open(hp, "wb").write(buf.value)
-    subprocess.check_call(["make", "-C", _DIR, "jit", "JITDIR=" + d, "TILES=%d" % tiles, "DEFS=" + defs, "TAG=" + tag],
+    subprocess.check_call(["make", "-C", _DIR, "jit", "JITDIR=" + d, "MODE=%d" % tiles, "DEFS=" + defs, "TAG=" + tag],
                           stdout=subprocess.DEVNULL)
     J = C.CDLL(os.path.join(d, "libcgxsim_jit%d%s.so" % (tiles, tag)))
     J.cgxsim_scan.argtypes = L.cgxsim_scan.argtypes
@@ -62,7 +62,8 @@ def jit_lib(pattern, tiles=2, defs="", tag=""):
     return J
 
 
-def scan(pattern, hay, mode=0, cap=None, grid=2, base=0, pad=ord("1"), jit=False, tiles=2, defs="", tag=""):
+def scan(pattern, hay, mode=0, cap=None, grid=2, base=0, pad=ord("1"), jit=False, tiles=None, defs="", tag="",
+         launches=1):
     """Runs the emulated kernel.  Returns (total, flag, pairs[ndarray k x 2])."""
     if isinstance(pattern, str):
         pattern = pattern.encode()
@@ -72,12 +73,14 @@ def scan(pattern, hay, mode=0, cap=None, grid=2, base=0, pad=ord("1"), jit=False
         cap = n + 16
     out = np.full((max(cap, 1), 2), -7, dtype=np.int64)
     res = (C.c_uint64 * 4)()
-    r = (jit_lib(pattern, tiles, defs, tag) if jit else lib()).cgxsim_scan(pattern, len(pattern), a.ctypes.data if n else None, n, base, mode,
-                          out.ctypes.data, cap, res, grid, pad)
+    r = (jit_lib(pattern, mode, defs, tag) if jit else lib()).cgxsim_scan(pattern, len(pattern), a.ctypes.data if n else None, n, base, mode,
+                          out.ctypes.data, cap, res, grid, pad, launches)
     if r == -2:
         raise NotEligible(pattern)
-    if r != 0:
+    if r == -1:
         raise RuntimeError("compile failed: %r" % pattern)
+    if r != 0:
+        raise RuntimeError("emulated launch left dirty scratch behind (code %d): %r" % (r, pattern))
     total = int(res[0])
     global last_diag
     last_diag = {"serial": int(res[2]), "redo": int(res[3])}

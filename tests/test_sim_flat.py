@@ -1,8 +1,8 @@
-"""Bitstream kernel (coregex_b200/csrc/scan_flat.cu) on the CPU SIMT emulator vs the oracle.
+"""Bitstream kernel (coregex_b200/csrc/scan_bits.cu) on the CPU SIMT emulator vs the oracle.
 
 The kernel SOURCE is compiled with g++ against tests/sim/simt_cpu.h (one fiber per CUDA thread),
 so these tests exercise the real warp-level code — marker passes, ownership by sync bytes, the
-alternation check, the serial replay, staging, overflow redo and the resumable look-back — in
+alternation check, the serial replay, bitmap extraction and the epoch look-back — in
 a container without a GPU.  The -m gpu tests repeat the same comparisons on the device.
 """
 import random
@@ -15,11 +15,14 @@ import sim_lib
 from oracle_lib import Oracle
 
 IP = r"\d+\.\d+\.\d+\.\d+"
-STRIDE, TILE, CHUNK = 1984, 2048, 12 * 1984
+# geometry of the kernel (scan_bits.cu): 64-byte words, K = 8 words per lane, 2 KB tiles, chunks of
+# 32 K words that overlap by one word; STRIDE = one lane's region
+K = 8
+STRIDE, TILE, CHUNK = 64 * K, 2048, (32 * K - 1) * 64
 BACKEND = "sim"
 
 
-@pytest.fixture(autouse=True, params=["sim", "simjit", "simjit1", "simjit1pair", pytest.param("gpu", marks=pytest.mark.gpu)])
+@pytest.fixture(autouse=True, params=["sim", "simjit", "simjit_k4", pytest.param("gpu", marks=pytest.mark.gpu)])
 def backend(request):
     """Every case runs on the emulator — the interpreting build and the per-pattern specialised
     build (what jit.cu compiles for the device) — and, under -m gpu, on the device through the C ABI."""
@@ -31,13 +34,13 @@ def backend(request):
 
 def scan(pat, hay, mode=0, cap=None, grid=2, base=0):
     """(total, flag, pairs) from the selected backend."""
-    if BACKEND in ("sim", "simjit", "simjit1", "simjit1pair"):
-        # simjit1: one tile per iteration (CGX_TILES=1, what the device runs by default);
-        # simjit1pair: the pair-load variant of it (-DCGX_PAIR=1)
-        pair = BACKEND == "simjit1pair"
+    if BACKEND in ("sim", "simjit", "simjit_k4"):
+        # simjit: the per-pattern, per-mode specialised build (what jit.cu compiles for the device);
+        # simjit_k4: the same with 4 words per lane and a 3-deep window ring (other chunk geometry);
+        # every emulated scan runs twice on the same scratch (stale look-back words of the first launch)
+        k4 = BACKEND == "simjit_k4"
         return sim_lib.scan(pat, hay, mode=mode, cap=cap, grid=grid, base=base, jit=BACKEND != "sim",
-                            tiles=1 if BACKEND in ("simjit1", "simjit1pair") else 2,
-                            defs="-DCGX_PAIR=1" if pair else "", tag="pair" if pair else "")
+                            defs="-DCGX_K=4 -DCGX_NB=3" if k4 else "", tag="k4" if k4 else "", launches=2)
     import torch
     from gpu_util import scan_device
     r = cg.Compile(pat)
@@ -67,10 +70,11 @@ def test_log_corpus_multi_cta():
     assert len(w) > 1500
 
 
-@pytest.mark.parametrize("n", [0, 1, 7, 15, 16, 17, 63, 64, 65, STRIDE - 1, STRIDE, STRIDE + 1, TILE - 1, TILE,
-                               TILE + 1, 2 * STRIDE - 1, 2 * STRIDE, 2 * STRIDE + 1, STRIDE + TILE - 1,
-                               STRIDE + TILE, STRIDE + TILE + 1, CHUNK - 1, CHUNK, CHUNK + 1, CHUNK + 63,
-                               CHUNK + 64, CHUNK + 65, 2 * CHUNK])
+@pytest.mark.parametrize("n", [0, 1, 7, 15, 16, 17, 63, 64, 65, 255, 256, 257, STRIDE - 1, STRIDE, STRIDE + 1,
+                               TILE - 1, TILE, TILE + 1, 2 * STRIDE - 1, 2 * STRIDE, 2 * STRIDE + 1,
+                               STRIDE + TILE - 1, STRIDE + TILE, STRIDE + TILE + 1, 8128 - 1, 8128, 8128 + 1,
+                               8192, CHUNK - 1, CHUNK, CHUNK + 1, CHUNK + 63,
+                               CHUNK + 64, CHUNK + 65, 2 * CHUNK, 2 * CHUNK + 64])
 def test_sizes_around_tile_and_chunk_edges(n):
     unit = b"a 1.2.3.4 b 10.20.30.40.50 c9.9.9.9\n"
     hay = (unit * (n // len(unit) + 1))[:n]
@@ -222,8 +226,8 @@ def test_pattern_zoo(pat):
             return
 
 
-def test_dense_matches_overflow_redo():
-    hay = b"1 22 333 4 55 6 7 8 9 0 " * 2500  # far more than 256 matches per chunk
+def test_dense_matches():
+    hay = b"1 22 333 4 55 6 7 8 9 0 " * 2500  # every second byte starts a match
     w = check(r"\d+", hay, grid=2)
     assert len(w) > 20000
     check(IP, b"1.1.1.1 " * 6000, grid=2)
