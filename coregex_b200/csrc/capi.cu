@@ -289,7 +289,14 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
     return !(e && e[0] == '0');
   }();
   const bool use_flat = c.kind == ENG_DFA && c.flat.bs_ok && re->bitstream && bs_env;
-  const int64_t nchunks = use_flat ? scan_flat_chunks((int64_t)len) : scan_dfa_chunks((int64_t)len);
+  // the specialised kernel of this pattern and mode (built on first use); it knows its own chunk size
+  if (use_flat && re->jit_state >= 0) {
+    if (!re->jit[mode]) re->jit[mode] = GetJitKernel(c.flat, mode, re->jit_error);
+    re->jit_state = re->jit[mode] ? 1 : -1;
+  }
+  const bool use_jit = use_flat && re->jit_state == 1;
+  const int64_t nchunks = use_jit ? ((int64_t)len + re->jit[mode]->chunk_bytes - 1) / re->jit[mode]->chunk_bytes
+                          : use_flat ? scan_flat_chunks((int64_t)len) : scan_dfa_chunks((int64_t)len);
   if (nchunks >= 0xFFFF0000ll) {
     g_last_error = "haystack too large for one scan call (32-bit chunk tickets); shard it";
     return CGX_ERR_ARGS;
@@ -376,11 +383,7 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   a.epoch = re->epoch;
   a.result = one_launch ? (unsigned long long*)d_result : nullptr;
   if (use_flat) {
-    if (re->jit_state >= 0) {
-      if (!re->jit[mode]) re->jit[mode] = GetJitKernel(c.flat, mode, re->jit_error);
-      re->jit_state = re->jit[mode] ? 1 : -1;
-    }
-    if (re->jit_state == 1) CU(launch_scan_flat_jit(re->jit[mode], a, re->sm_count, st));
+    if (use_jit) CU(launch_scan_flat_jit(re->jit[mode], a, re->sm_count, st));
     else CU(launch_scan_flat(a, re->sm_count, st, nullptr));
   } else {
     CU(launch_scan_dfa(a, re->sm_count, st));

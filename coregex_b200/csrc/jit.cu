@@ -207,8 +207,8 @@ const JitKernel* GetJitKernel(const FlatDev& f, int mode, std::string& err) {
   CUfunction fn = nullptr;
   CUresult r = d.load(&mod, cubin.data());
   if (r == CUDA_SUCCESS) r = d.getfn(&fn, mod, "cgx_flat_jit");
-  // the module describes its own launch shape: {dynamic smem bytes, threads, scanning warps, CTAs/SM}
-  int info[4] = {0, 0, 0, 0};
+  // the module describes its own launch shape: {dynamic smem bytes, threads, scanning warps, CTAs/SM, chunk bytes}
+  int info[5] = {0, 0, 0, 0, 0};
   CUdeviceptr ip = 0;
   size_t isz = 0;
   if (r == CUDA_SUCCESS) r = d.getglobal(&ip, &isz, mod, "cgx_flat_jit_info");
@@ -232,6 +232,7 @@ const JitKernel* GetJitKernel(const FlatDev& f, int mode, std::string& err) {
   k->threads = info[1];
   k->warps = info[2];
   k->mode = mode;
+  k->chunk_bytes = info[4];
   std::lock_guard<std::mutex> lk(g_mu);
   g_loaded[{dev, hdr}] = k;
   return k;

@@ -14,6 +14,7 @@ struct JitKernel {
   int per_sm = 0;        // resident CTAs per SM
   int smem = 0, threads = 0, warps = 0;  // launch shape, read from the module (cgx_flat_jit_info)
   int mode = 0;          // the search mode the kernel was specialised for (ScanMode)
+  int chunk_bytes = 0;   // bytes between chunk origins of this build (the host sizes the look-back arrays by it)
 };
 
 // NVRTC only: works without a device (used by the CPU test that the specialised source builds).

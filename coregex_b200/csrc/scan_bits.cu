@@ -51,32 +51,29 @@ constexpr uint32_t FULL = 0xffffffffu;
 #ifndef CGX_K
 #define CGX_K 8            // words (64-byte pieces) per lane and chunk == tiles per chunk
 #endif
-#ifndef CGX_WARPS
-#ifdef CGX_JIT
-#define CGX_WARPS 14       // scanning warps per CTA (specialised build: 1 or 2 class words per slot)
-#else
-#define CGX_WARPS 8        // the interpreting build keeps four class words per slot: fewer warps fit
-#endif
-#endif
 #ifndef CGX_CTAS
 #define CGX_CTAS 1         // resident CTAs per SM the kernel is built for
 #endif
 #ifndef CGX_NB
 #define CGX_NB 2           // window ring: tiles in flight per warp
 #endif
+#ifndef CGX_UNROLL
+#define CGX_UNROLL 3       // words per trip of the sweep loops (independent steps of neighbouring words overlap)
+#endif
 constexpr int K = CGX_K;
-constexpr int FW_WARPS = CGX_WARPS;
-constexpr int FW_THREADS = (FW_WARPS + 1) * 32;  // + one resolver warp
 constexpr int FW_CTAS = CGX_CTAS;
 constexpr int NB = CGX_NB;
+constexpr int UNROLL = CGX_UNROLL;
 constexpr int TILE = 2048;                 // one bulk copy, one classification round (64 B per lane)
 constexpr int TPC = K;                     // tiles per chunk
 constexpr int NWORDS = 32 * K;             // words of a chunk's window
 constexpr int WINDOW = NWORDS * 64;        // bytes of a chunk's window
 constexpr int CHUNKB = (NWORDS - 1) * 64;  // bytes between chunk origins: chunks overlap by one word
 constexpr int NSLOTS = 32 * (K + 1);       // word w lives in slot w + w / K (one pad slot per lane region)
-static_assert(FW_WARPS <= 31, "one CTA holds at most 31 scanning warps and the resolver");
-static_assert(K >= 2 && K <= 16, "words per lane");
+// slot NSLOTS stays all zero: lane 31 has no neighbour word, it reads this one instead (no class
+// byte, no marker: a word that leaves every piece of per-lane state as it is)
+constexpr int NSLOTS1 = NSLOTS + 1;
+static_assert(K == 4 || K == 8 || K == 16, "words per lane: a power of two that divides 32");
 
 // ---- pipe-aware primitives (the kernel is bound by the integer ALU pipe) -------
 //  * a LOP3 takes one immediate at most; as an explicit lop3.b32 `(w ^ k) & m` is one instruction;
@@ -131,6 +128,13 @@ constexpr int NC = 4;
 constexpr int NSTATE = 24;
 #endif
 constexpr int NPAIR = (NC + 1) / 2;        // 16-byte slot arrays: classes (0,1) and (2,3)
+// scanning warps per CTA: as many as the shared memory of one SM holds (one or two slot arrays per warp)
+#ifndef CGX_WARPS
+#define CGX_WARPS (NPAIR == 1 ? 14 : 8)
+#endif
+constexpr int FW_WARPS = CGX_WARPS;
+constexpr int FW_THREADS = (FW_WARPS + 1) * 32;  // + one resolver warp
+static_assert(FW_WARPS <= 31, "one CTA holds at most 31 scanning warps and the resolver");
 
 struct alignas(16) Slot {
   uint64_t a, b;
@@ -139,8 +143,8 @@ struct WarpSmem {
   alignas(128) uint8_t win[NB][TILE];
   // class bitmaps of the chunk being scanned; after sweep 2 array 0 holds (starts, ends) instead.
   // Two buffers: a chunk's result waits here for its global offset while the next chunk is scanned.
-  Slot cls[2][NPAIR][NSLOTS];
-  uint64_t mk[NSLOTS];        // sweep 1 -> sweep 2: "a match can start here", forward orientation
+  Slot cls[2][NPAIR][NSLOTS1];
+  uint64_t mk[NSLOTS1];       // sweep 1 -> sweep 2: "a match can start here", forward orientation
   uint64_t mbar[NB];
   uint32_t rank[2][32];       // per buffer and lane: starts before the lane | ends before it << 16
   // matches of a serially replayed segment that end beyond the chunk's bitmap (per buffer):
@@ -595,46 +599,38 @@ __device__ void resolver_warp(const ScanArgs& a, CtaSmem& cs, int lane) {
 // Lane l turns the bits of its K words into positions: the i-th start of the chunk goes to
 // out[2 (excl + i)], the i-th end to out[2 (excl + i) + 1].  Starts and ends are independent
 // streams (a match that starts in one lane's words may end in the next lane's).
-__device__ __forceinline__ void extract(const ScanArgs& a, WarpSmem& ws, int sb, int64_t chunk, unsigned long long excl,
-                                        int lane) {
-  const Slot* res = ws.cls[sb][0] + lane * (K + 1);
-  const uint32_t rk = ws.rank[sb][lane];
-  unsigned long long is = excl + (rk & 0xFFFFu), ie = excl + (rk >> 16);
-  const int64_t wb = chunk * (int64_t)CHUNKB + a.base + (int64_t)lane * (K * 64);
-  const unsigned long long cap = (unsigned long long)a.cap;
+// One 32-bit half of a bitmap word: a store per set bit.  CHECK: the output may be too small.
+template <bool CHECK>
+__device__ __forceinline__ void emit_half(uint32_t w, int64_t pos0, int64_t*& o, const int64_t* end) {
+  while (w) {
+    const int b = __ffs((int)w) - 1;
+    w &= w - 1u;
+    if (!CHECK || o < end) *o = pos0 + b;
+    o += 2;
+  }
+}
+template <bool CHECK>
+__device__ __forceinline__ void extract_words(const ScanArgs& a, const Slot* res, int64_t wb, int64_t* os, int64_t* oe) {
+  const int64_t* end = a.out + 2 * a.cap;
 #pragma unroll 1
   for (int j = 0; j < K; j++) {
     const Slot v = res[j];
     const int64_t pb = wb + j * 64;
-    uint32_t slo = lo32(v.a), shi = hi32(v.a), elo = lo32(v.b), ehi = hi32(v.b);
-    // one start and one end per round: usually 0..2 rounds
-    while (slo | shi | elo | ehi) {
-      {
-        const bool l = slo != 0u;
-        const uint32_t w = l ? slo : shi;
-        if (w) {
-          const int64_t pos = pb + (l ? 0 : 32) + (__ffs((int)w) - 1);
-          if (is < cap) a.out[2 * is] = pos;
-          is++;
-          const uint32_t w2 = w & (w - 1u);
-          slo = l ? w2 : 0u;
-          shi = l ? shi : w2;
-        }
-      }
-      {
-        const bool l = elo != 0u;
-        const uint32_t w = l ? elo : ehi;
-        if (w) {
-          const int64_t pos = pb + (l ? 0 : 32) + (__ffs((int)w) - 1);
-          if (ie < cap) a.out[2 * ie + 1] = pos;
-          ie++;
-          const uint32_t w2 = w & (w - 1u);
-          elo = l ? w2 : 0u;
-          ehi = l ? ehi : w2;
-        }
-      }
-    }
+    emit_half<CHECK>(lo32(v.a), pb, os, end);
+    emit_half<CHECK>(hi32(v.a), pb + 32, os, end);
+    emit_half<CHECK>(lo32(v.b), pb, oe, end);
+    emit_half<CHECK>(hi32(v.b), pb + 32, oe, end);
   }
+}
+__device__ __forceinline__ void extract(const ScanArgs& a, WarpSmem& ws, int sb, int64_t chunk, unsigned long long excl,
+                                        unsigned cnt, int lane) {
+  const Slot* res = ws.cls[sb][0] + lane * (K + 1);
+  const uint32_t rk = ws.rank[sb][lane];
+  int64_t* os = a.out + 2 * (excl + (rk & 0xFFFFu));
+  int64_t* oe = a.out + 2 * (excl + (rk >> 16)) + 1;
+  const int64_t wb = chunk * (int64_t)CHUNKB + a.base + (int64_t)lane * (K * 64);
+  if ((int64_t)(excl + cnt) <= a.cap) extract_words<false>(a, res, wb, os, oe);  // the usual case: everything fits
+  else extract_words<true>(a, res, wb, os, oe);
   // matches of a replayed segment that end beyond the bitmap: found again, stored after the others
   if (lane == 0 && ws.far_cnt[sb])
     replay_cold(a, chunk * (int64_t)CHUNKB, nullptr, ws.far_from[sb], ws.far_stop[sb], a.out, excl + ws.bits_cnt[sb],
@@ -646,7 +642,7 @@ __device__ __forceinline__ void extract(const ScanArgs& a, WarpSmem& ws, int sb,
 #ifdef CGX_JIT
 #ifndef CGX_CPU_SIM
 // the loader (jit.cu) reads the launch shape from the module it just built
-extern "C" __device__ const int cgx_flat_jit_info[4] = {(int)sizeof(CtaSmem), FW_THREADS, FW_WARPS, FW_CTAS};
+extern "C" __device__ const int cgx_flat_jit_info[5] = {(int)sizeof(CtaSmem), FW_THREADS, FW_WARPS, FW_CTAS, CHUNKB};
 #endif
 extern "C" __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) cgx_flat_jit(const __grid_constant__ ScanArgs a) {
 #else
@@ -666,6 +662,9 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
 #pragma unroll
     for (int b = 0; b < NB; b++) mbar_init(&cs.w[warp].mbar[b], 1);
     fence_mbar_init();
+    for (int b = 0; b < 2; b++)
+      for (int q = 0; q < NPAIR; q++) cs.w[warp].cls[b][q][NSLOTS] = Slot{0ull, 0ull};
+    cs.w[warp].mk[NSLOTS] = 0ull;
   }
   cgx_syncthreads();
   if (warp == FW_WARPS) {
@@ -696,7 +695,8 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
   // The prefetcher runs NB tiles ahead of the classifier, across chunk borders: pf_src walks through
   // the chunk being prefetched (lane 0's copy is the one used), pf_left counts its tiles still to
   // be requested, pf_whole says that all of its windows lie inside the input (no bounds to look at).
-  unsigned issued = 0, consumed = 0;
+  int ib = 0, rb = 0;       // ring buffer the next request goes to / the next tile is read from
+  uint32_t rpar = 0u;       // parity of the phase the reader waits for on mbar[rb]
   const uint8_t* pf_src = a.h;
   int pf_left = 0;
   bool pf_whole = false;
@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
   };
   auto issue_next = [&]() {
     if (lane == 0) {
-      const int b = issued % NB;
+      const int b = ib;
       if (pf_whole) {  // the common case: a whole tile
         mbar_expect_tx(&ws.mbar[b], (uint32_t)TILE);
         tma_load_1d(ws.win[b], pf_src, (uint32_t)TILE, &ws.mbar[b]);
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     }
     pf_src += TILE;
     pf_left--;
-    issued++;
+    ib = ib + 1 == NB ? 0 : ib + 1;
   };
   // Stores the matches of the chunk parked in buffer b (if any) once the resolver has supplied its
   // offset; returns whether the buffer is free afterwards.  Blocking, or one look.
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         a.result[1] = (excl + m.cnt) ? 1ull : 0ull;
       }
     }
-    extract(a, ws, b, chunk, excl, lane);
+    extract(a, ws, b, chunk, excl, m.cnt, lane);
     __syncwarp();
     if (lane == 0) m.state = 0;
     __syncwarp();
@@ -773,17 +773,21 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     const int64_t cb = cur * (int64_t)CHUNKB;
     // the buffer this chunk's bitmaps go to must have been emptied (its chunk is two tickets old)
     if (P_MODE == M_FINDALL) flush(sb, true);
-    Slot(*cls)[NSLOTS] = ws.cls[sb];
+    Slot(*cls)[NSLOTS1] = ws.cls[sb];
 
     // ================= phase A: classify the chunk's tiles into class bitmaps ====================
     const bool whole = cb + WINDOW <= a.n;
+    // word t * 32 + lane lives in slot (t * 32 + lane) + (t * 32 + lane) / K: 32 + 32 / K slots further per tile
+    Slot* dst = &cls[0][lane + lane / K];
 #pragma unroll 1
     for (int t = 0; t < TPC; t++) {
-      const int b = consumed % NB;
-      mbar_wait(&ws.mbar[b], (consumed / NB) & 1u);
-      consumed++;
+      mbar_wait(&ws.mbar[rb], rpar);
       uint64_t cm[4];
-      classify_piece(f, ws.win[b] + lane * 64, one, cm);
+      classify_piece(f, ws.win[rb] + lane * 64, one, cm);
+      if (++rb == NB) {
+        rb = 0;
+        rpar ^= 1u;
+      }
       // every lane holds its piece in registers: the buffer can take the tile NB ahead
       __syncwarp();
       if (pf_left == 0 && t + NB == TPC) {  // the ring moves on to the next chunk
@@ -798,15 +802,15 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
 #pragma unroll
         for (int c = 0; c < 4; c++) cm[c] &= m;
       }
-      const int w = t * 32 + lane;
-      const int s = w + w / K;
-      cls[0][s] = Slot{cm[0], cm[1]};
-      if (NPAIR > 1) cls[NPAIR - 1][s] = Slot{cm[2], cm[3]};
+      dst[0] = Slot{cm[0], cm[1]};
+      if (NPAIR > 1) dst[NSLOTS1] = Slot{cm[2], cm[3]};
+      dst += 32 + 32 / K;
     }
     __syncwarp();
 
     // ================= phase B: lane-serial marker sweeps over K words + the neighbour's first ======
-    // lane 31's neighbour word would lie outside the window: its own last word is the overlap
+    // lane 31's neighbour word would lie outside the window: its own last word is the overlap, and
+    // where the others read their neighbour's word it reads the all-zero slot NSLOTS
     const int ovl = lane == 31 ? K - 1 : K;
     // slot of the lane's word 0; its words follow, then the region's pad slot, then the neighbour's word 0
     const int s0 = lane * (K + 1);
@@ -814,30 +818,29 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     PassState st;
     // ---- sweep 1, right to left: where can a match start (reversed orientation) ----
     pass_reset(st);
-#pragma unroll 1
+#pragma unroll UNROLL
     for (int j = K; j >= 0; j--) {
-      if (j <= ovl) {
-        uint64_t c[4];
-        {
-          const Slot v = cls[0][slot_of(j)];
-          c[0] = v.a;
-          c[1] = v.b;
-          c[2] = c[3] = 0ull;
-          if (NPAIR > 1) {
-            const Slot v2 = cls[NPAIR - 1][slot_of(j)];
-            c[2] = v2.a;
-            c[3] = v2.b;
-          }
-        }
-        const uint64_t M = rev_word(f, c, st);
-        if (j < K) {
-          // what the lane computes for its own words is what everybody uses: forward orientation
-          ws.mk[s0 + j] = brev64(M);
-          cls[0][s0 + j] = Slot{brev64(c[0]), brev64(c[1])};
-          if (NPAIR > 1) cls[NPAIR - 1][s0 + j] = Slot{brev64(c[2]), brev64(c[3])};
+      uint64_t c[4];
+      {
+        const Slot v = cls[0][slot_of(j)];
+        c[0] = v.a;
+        c[1] = v.b;
+        c[2] = c[3] = 0ull;
+        if (NPAIR > 1) {
+          const Slot v2 = cls[NPAIR - 1][slot_of(j)];
+          c[2] = v2.a;
+          c[3] = v2.b;
         }
       }
-      if (j == K) __syncwarp();  // the neighbour's word 0 was read before the neighbour rewrites it (at j == 0)
+      const uint64_t M = rev_word(f, c, st);
+      // the neighbour's word 0 has been read by everybody before its owner rewrites it (at j == 0)
+      if (j == K) __syncwarp();
+      if (j < K) {
+        // what the lane computes for its own words is what everybody uses: forward orientation
+        ws.mk[s0 + j] = brev64(M);
+        cls[0][s0 + j] = Slot{brev64(c[0]), brev64(c[1])};
+        if (NPAIR > 1) cls[NPAIR - 1][s0 + j] = Slot{brev64(c[2]), brev64(c[3])};
+      }
     }
     __syncwarp();
 
@@ -851,59 +854,60 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     bool bad = false, open = false;
     unsigned cS = 0u, cE = 0u;
     static_assert(K >= 3, "the overlap word's result is parked in mk[1..2] of the lane's region");
-#pragma unroll 1
+#pragma unroll UNROLL
     for (int j = 0; j <= K; j++) {
-      if (j <= ovl) {
-        uint64_t c[4];
-        {
-          const Slot v = cls[0][slot_of(j)];
-          c[0] = v.a;
-          c[1] = v.b;
-          c[2] = c[3] = 0ull;
-          if (NPAIR > 1) {
-            const Slot v2 = cls[NPAIR - 1][slot_of(j)];
-            c[2] = v2.a;
-            c[3] = v2.b;
-          }
+      uint64_t c[4];
+      {
+        const Slot v = cls[0][slot_of(j)];
+        c[0] = v.a;
+        c[1] = v.b;
+        c[2] = c[3] = 0ull;
+        if (NPAIR > 1) {
+          const Slot v2 = cls[NPAIR - 1][slot_of(j)];
+          c[2] = v2.a;
+          c[3] = v2.b;
         }
-        uint64_t M = ws.mk[slot_of(j)];
-        uint64_t own = ~0ull;
-        if (seen == 0u || j == ovl) {
-          uint64_t U = c[0] | c[1];
-          if (NC > 2) U |= c[2] | c[3];
-          const uint64_t nz = ~U;                  // sync bytes of this word
-          const uint64_t upto = nz ^ (nz - 1ull);  // bits up to and including the first sync byte (all ones if none)
-          // owned: after the lane's first sync byte ...
-          own = seen ? ~0ull : ~upto;
-          if (nz) seen = FULL;
-          // ... up to the first sync byte of the neighbour's first word
-          if (j == ovl) {
-            own &= upto;
-            open = nz == 0ull;
-          }
+      }
+      uint64_t M = ws.mk[slot_of(j)];
+      uint64_t own = ~0ull;
+      if (seen == 0u || j == ovl) {
+        uint64_t U = c[0] | c[1];
+        if (NC > 2) U |= c[2] | c[3];
+        const uint64_t nz = ~U;                  // sync bytes of this word
+        const uint64_t upto = nz ^ (nz - 1ull);  // bits up to and including the first sync byte (all ones if none)
+        // owned: after the lane's first sync byte ...
+        own = seen ? ~0ull : ~upto;
+        if (nz && j <= ovl) seen = FULL;  // (lane 31's pass over the all-zero slot is not part of its region)
+        // ... up to the first sync byte of the neighbour's first word
+        if (j == ovl) {
+          own &= upto;
+          open = nz == 0ull;
         }
-        const uint64_t c0prev = shl_in<1>(c[0], c0hi);
-        c0hi = hi32(c[0]);
-        // only the first byte of a run of class 0 (pattern opens with C+)
-        if (P_RUNSTART) M &= c[0] & ~c0prev;
-        const uint64_t S = M & own;
-        const uint64_t E = fwd_word(f, c, S, st) & own;
-        bad |= word_misordered(S, E, in);
-        // (an end in the middle of a class-0 run: the reference resumes there, which is no run start)
-        if (P_MIDRUN) bad |= (E & c[0] & c0prev) != 0ull;
-        if (j == K) {
-          ws.mk[s0 + 1] = S;
-          ws.mk[s0 + 2] = E;
-        } else {
-          cls[0][s0 + (j == 0 ? K : j)] = Slot{S, E};
-          cS += __popcll(S);
-          cE += __popcll(E);
-        }
+      }
+      const uint64_t c0prev = shl_in<1>(c[0], c0hi);
+      c0hi = hi32(c[0]);
+      // only the first byte of a run of class 0 (pattern opens with C+)
+      if (P_RUNSTART) M &= c[0] & ~c0prev;
+      const uint64_t S = M & own;
+      const uint64_t E = fwd_word(f, c, S, st) & own;
+      bad |= word_misordered(S, E, in);
+      // (an end in the middle of a class-0 run: the reference resumes there, which is no run start)
+      if (P_MIDRUN) bad |= (E & c[0] & c0prev) != 0ull;
+      if (j == K) {
+        ws.mk[s0 + 1] = S;
+        ws.mk[s0 + 2] = E;
+      } else {
+        cls[0][s0 + (j == 0 ? K : j)] = Slot{S, E};
+        cS += __popcll(S);
+        cE += __popcll(E);
       }
     }
     bad |= in != 0u;
     // ---- lanes that need the reference loop: clear what the sweeps left in the affected range ----
     const bool replay = bad || (open && seen);
+#ifdef CGX_DEBUG_PRINT
+    if (replay) printf("chunk %u lane %d bad %d open %d seen %u in %u\n", cur, lane, (int)bad, (int)open, seen, in);
+#endif
     int64_t rp_from = 0, rp_stop = 0;
     if (replay) {
       // bad: everything the lane owns; open only: the segment after the lane's last sync byte
