@@ -22,6 +22,7 @@ CGX_ERR_NO_DEVICE = -3
 CGX_ERR_CUDA = -4
 CGX_ERR_ARGS = -5
 CGX_ERR_NOMEM = -6
+CGX_ERR_CONFIG = -7
 
 MODE_FINDALL, MODE_COUNT, MODE_ISMATCH = 0, 1, 2
 
@@ -32,6 +33,31 @@ class Error(Exception):
 
 class UnsupportedError(Error):
     """Valid pattern outside the GPU engines' current scope."""
+
+
+class ConfigError(Error):
+    """Invalid Config; str() is the reference's message (meta/config.go:179-181)."""
+
+
+class Config(C.Structure):
+    """meta.Config (reference meta/config.go:31-113), field for field; DefaultConfig() fills the
+    reference's defaults."""
+    _fields_ = [("EnableDFA", C.c_int), ("EnablePrefilter", C.c_int), ("MaxDFAStates", C.c_uint32),
+                ("DeterminizationLimit", C.c_int), ("MinLiteralLen", C.c_int), ("MaxLiterals", C.c_int),
+                ("MaxRecursionDepth", C.c_int), ("EnableASCIIOptimization", C.c_int)]
+
+    def Validate(self):
+        """None, or the reference's error text (Config.Validate, meta/config.go:132-170)."""
+        err = C.create_string_buffer(256)
+        rc = _lib.cgx_config_validate(C.byref(self), err, 256)
+        return None if rc == CGX_OK else err.value.decode()
+
+
+def DefaultConfig():
+    """reference meta/config.go:101-112"""
+    c = Config()
+    _lib.cgx_default_config(C.byref(c))
+    return c
 
 
 class NoDeviceError(RuntimeError):
@@ -53,6 +79,10 @@ def _load():
     vp, u8p, i64, sz = C.c_void_p, C.c_void_p, C.c_int64, C.c_size_t
     L.cgx_compile.argtypes = [C.c_char_p, sz, C.POINTER(vp), C.c_char_p, sz]
     L.cgx_free.argtypes = [vp]
+    L.cgx_compile_cfg.argtypes = [C.c_char_p, sz, C.c_void_p, C.POINTER(vp), C.c_char_p, sz]
+    L.cgx_default_config.argtypes = [C.c_void_p]
+    L.cgx_config_validate.argtypes = [C.c_void_p, C.c_char_p, sz]
+    L.cgx_set_longest.argtypes = [vp, C.c_int]
     L.cgx_strategy.restype = C.c_char_p
     L.cgx_strategy.argtypes = [vp]
     L.cgx_engine.restype = C.c_char_p
@@ -114,13 +144,16 @@ def _host_buf(b):
 class Regex:
     """A compiled pattern.  Mirrors reference regex.go `type Regex` for the bulk-scan path."""
 
-    def __init__(self, pattern):
+    def __init__(self, pattern, config=None):
         if isinstance(pattern, str):
             pattern = pattern.encode()
         self._pattern = pattern
         h = C.c_void_p()
         err = C.create_string_buffer(1024)
-        rc = _lib.cgx_compile(pattern, len(pattern), C.byref(h), err, 1024)
+        rc = _lib.cgx_compile_cfg(pattern, len(pattern), C.byref(config) if config is not None else None,
+                                  C.byref(h), err, 1024)
+        if rc == CGX_ERR_CONFIG:
+            raise ConfigError(err.value.decode(errors="replace"))
         if rc == CGX_ERR_SYNTAX:
             raise Error(err.value.decode(errors="replace"))
         if rc == CGX_ERR_UNSUPPORTED:
@@ -132,6 +165,10 @@ class Regex:
         h, self._h = getattr(self, "_h", None), None
         if h:
             _lib.cgx_free(h)
+
+    def Longest(self):
+        """reference regex.go:464: leftmost-longest matching for all later searches."""
+        _check(_lib.cgx_set_longest(self._h, 1))
 
     # -- introspection --------------------------------------------------------------------------
     def String(self):
@@ -243,6 +280,11 @@ class Regex:
 def Compile(pattern):
     """reference regex.go:110"""
     return Regex(pattern)
+
+
+def CompileWithConfig(pattern, config):
+    """reference regex.go:198"""
+    return Regex(pattern, config)
 
 
 def MustCompile(pattern):

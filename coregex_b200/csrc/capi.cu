@@ -96,6 +96,7 @@ struct cgx_regex {
   size_t status_cap_seen = 0;  // capacity of d_status when its words were last cleared
   bool scratch_zero = false;   // ticket counter known to be zero (left so by the previous launch)
   bool diag = false;           // cgx_debug_scratch in use: clear the diagnostics before every launch
+  bool longest = false;        // Regex.Longest(): leftmost-longest tables in use
 
   int ensure_pipeline() {
     if (s_h2d) return CGX_OK;
@@ -214,12 +215,73 @@ extern "C" {
 
 const char* cgx_last_error(void) { return g_last_error.c_str(); }
 
+void cgx_default_config(cgx_config* cfg) {  // reference meta/config.go:101-112
+  if (!cfg) return;
+  cfg->enable_dfa = 1;
+  cfg->enable_prefilter = 1;
+  cfg->max_dfa_states = 10000;
+  cfg->determinization_limit = 1000;
+  cfg->min_literal_len = 1;
+  cfg->max_literals = 256;
+  cfg->max_recursion_depth = 100;
+  cfg->enable_ascii_optimization = 1;
+}
+
+// reference meta/config.go:132-170 (Validate) and :179-181 (ConfigError.Error)
+int cgx_config_validate(const cgx_config* cfg, char* errbuf, size_t errcap) {
+  if (!cfg) return CGX_ERR_ARGS;
+  const char* field = nullptr;
+  const char* msg = nullptr;
+  if (cfg->enable_dfa) {
+    if (cfg->max_dfa_states < 1 || cfg->max_dfa_states > 1000000) {
+      field = "MaxDFAStates";
+      msg = "must be between 1 and 1,000,000";
+    } else if (cfg->determinization_limit < 10 || cfg->determinization_limit > 100000) {
+      field = "DeterminizationLimit";
+      msg = "must be between 10 and 100,000";
+    }
+  }
+  if (!field && cfg->enable_prefilter) {
+    if (cfg->min_literal_len < 1 || cfg->min_literal_len > 64) {
+      field = "MinLiteralLen";
+      msg = "must be between 1 and 64";
+    } else if (cfg->max_literals < 1 || cfg->max_literals > 1000) {
+      field = "MaxLiterals";
+      msg = "must be between 1 and 1,000";
+    }
+  }
+  if (!field && (cfg->max_recursion_depth < 10 || cfg->max_recursion_depth > 1000)) {
+    field = "MaxRecursionDepth";
+    msg = "must be between 10 and 1,000";
+  }
+  if (!field) return CGX_OK;
+  g_last_error = std::string("regexp: invalid config: ") + field + ": " + msg;
+  if (errbuf && errcap) {
+    strncpy(errbuf, g_last_error.c_str(), errcap - 1);
+    errbuf[errcap - 1] = 0;
+  }
+  return CGX_ERR_CONFIG;
+}
+
 int cgx_compile(const char* pattern, size_t len, cgx_regex** out, char* errbuf, size_t errcap) {
+  return cgx_compile_cfg(pattern, len, nullptr, out, errbuf, errcap);
+}
+
+int cgx_compile_cfg(const char* pattern, size_t len, const cgx_config* cfg, cgx_regex** out, char* errbuf,
+                    size_t errcap) {
   if (out) *out = nullptr;
   if (!pattern || !out) return CGX_ERR_ARGS;
+  AnalysisConfig ac;
+  if (cfg) {
+    const int v = cgx_config_validate(cfg, errbuf, errcap);  // reference meta/compile.go:63-65
+    if (v) return v;
+    ac.enable_dfa = cfg->enable_dfa != 0;
+    ac.enable_prefilter = cfg->enable_prefilter != 0;
+    ac.min_literal_len = cfg->min_literal_len;
+  }
   std::unique_ptr<Compiled> c;
   std::string err;
-  int st = CompilePattern(std::string(pattern, len), c, err);
+  int st = CompilePattern(std::string(pattern, len), c, err, ac);
   if (st != COMPILE_OK) {
     if (errbuf && errcap) {
       strncpy(errbuf, err.c_str(), errcap - 1);
@@ -235,6 +297,47 @@ int cgx_compile(const char* pattern, size_t len, cgx_regex** out, char* errbuf, 
 }
 
 void cgx_free(cgx_regex* re) { delete re; }
+
+// reference regex.go:464 Longest / meta/engine.go:250 SetLongest.  The reference switches every
+// search to its PikeVM in longest mode (meta/find_indices.go:224-226); here the anchored DFA tables
+// are rebuilt without the cut at the first match (the table walk then ends at the LAST match state
+// before the dead state: leftmost-longest from each start).
+int cgx_set_longest(cgx_regex* re, int longest) {
+  if (!re) return CGX_ERR_ARGS;
+  std::lock_guard<std::mutex> lk(re->mu);
+  const bool on = longest != 0;
+  if (on == re->longest) return CGX_OK;
+  Compiled& c = *re->c;
+  if (c.kind == ENG_DFA && c.flat.bs_ok) {
+    // flat deterministic pattern: one possible match per start, first == longest
+  } else if (c.kind == ENG_DFA) {
+    DfaTables t;
+    const std::string e = BuildDFA(c.prog, /*anchored=*/true, /*max_states=*/160, t, /*longest=*/on);
+    if (!e.empty() || t.matches_empty) {
+      g_last_error = "unsupported: leftmost-longest tables: " + (e.empty() ? std::string("pattern can match the empty string") : e);
+      return CGX_ERR_UNSUPPORTED;
+    }
+    c.dfa = t;
+    c.kind_lut_needed = false;
+    for (int k = 1; k < 5; k++)
+      if (c.dfa.start[k] != c.dfa.start[0]) c.kind_lut_needed = true;
+    re->device = -1;  // upload the new tables before the next search
+  } else if (c.kind == ENG_TEDDY) {
+    // a literal alternation: first == longest unless one literal is a proper prefix of another
+    const auto& P = c.an.prefixes;
+    for (size_t i = 0; i < P.size(); i++)
+      for (size_t j = 0; j < P.size(); j++)
+        if (i != j && P[i].bytes.size() < P[j].bytes.size() && P[j].bytes.compare(0, P[i].bytes.size(), P[i].bytes) == 0) {
+          g_last_error = "unsupported: leftmost-longest for a literal set in which one literal is a prefix of another";
+          return CGX_ERR_UNSUPPORTED;
+        }
+  } else {
+    g_last_error = "unsupported: leftmost-longest on the record engine";
+    return CGX_ERR_UNSUPPORTED;
+  }
+  re->longest = on;
+  return CGX_OK;
+}
 const char* cgx_strategy(const cgx_regex* re) { return RefStrategyName(re->c->an.strategy); }
 const char* cgx_engine(const cgx_regex* re) { return re->c->engine_name.c_str(); }
 int cgx_num_captures(const cgx_regex* re) { return re->c->prog.num_captures; }
@@ -475,6 +578,10 @@ static int submatch_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_
     return scan_locked(re, d_h, len, base, CGX_MODE_FINDALL, d_out, cap, d_result, st);
   if (!c.has_pike) {
     g_last_error = "unsupported: captures kernel limit: " + c.pike_err;
+    return CGX_ERR_UNSUPPORTED;
+  }
+  if (re->longest) {
+    g_last_error = "unsupported: submatches in leftmost-longest mode (the captures kernel follows leftmost-first priorities)";
     return CGX_ERR_UNSUPPORTED;
   }
   int r;

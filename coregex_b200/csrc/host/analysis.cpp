@@ -527,7 +527,7 @@ bool safeReverseInner(const Regexp* re) {
 
 }  // namespace
 
-Analysis Analyze(const Regexp* re, int, bool anchored_start) {
+Analysis Analyze(const Regexp* re, int, bool anchored_start, const AnalysisConfig& cfg) {
   Analysis a;
   Extract ex;
   a.digit_lead = digitLead(re);
@@ -545,7 +545,8 @@ Analysis Analyze(const Regexp* re, int, bool anchored_start) {
   bool hasStartAnchor = anyOp(re, [](Op o) { return o == OpBeginText; });
   bool hasEndText = anyOp(re, [](Op o) { return o == OpEndText; });
 
-  if (!anchored_start) {
+  const size_t minlit = (size_t)(cfg.min_literal_len > 0 ? cfg.min_literal_len : 1);
+  if (!anchored_start && cfg.enable_prefilter) {  // reference meta/compile.go:466
     a.prefixes = ex.prefixes(re, 0);
     if (a.prefixes.size() > 64) {  // reference literal/extractor.go:135-149
       Lits orig = a.prefixes;
@@ -562,14 +563,14 @@ Analysis Analyze(const Regexp* re, int, bool anchored_start) {
   const int nfaSize = refStates(re) + 1 + (anchored_start ? 0 : 2);
 
   auto decide = [&]() -> int {
-    if (endAnchoredTail(re) && !anchored_start && !hasStartAnchor) return RS_UseReverseAnchored;
+    if (cfg.enable_dfa && endAnchoredTail(re) && !anchored_start && !hasStartAnchor) return RS_UseReverseAnchored;
     if (anchored_start) return RS_UseBoundedBacktracker;
-    // --- selectReverseStrategy
-    if (!hasWB && !hasEndText) {
-      bool fastPrefix = !P.empty() && (lcp(P).size() >= 1 || P.size() == 1 || minLen(P) >= 3);
+    // --- selectReverseStrategy (needs the DFA and the prefilter, meta/strategy.go:976)
+    if (!hasWB && !hasEndText && cfg.enable_dfa && cfg.enable_prefilter) {
+      bool fastPrefix = !P.empty() && (lcp(P).size() >= minlit || P.size() == 1 || minLen(P) >= 3);
       if (!fastPrefix) {
         Lits suf = ex.suffixes(re, 0);
-        if (!suf.empty() && lcs(suf).size() >= 1) {
+        if (!suf.empty() && lcs(suf).size() >= minlit) {
           if (safeReverseSuffix(re)) return RS_UseReverseSuffix;
           goto no_reverse;
         }
@@ -589,7 +590,7 @@ Analysis Analyze(const Regexp* re, int, bool anchored_start) {
             if (before && after) {
               std::string p = lcp(in);
               if (p.size() == 1 && a.digit_lead) goto no_reverse;
-              if (p.size() >= 1) {
+              if (p.size() >= minlit) {
                 if (!safeReverseInner(re)) goto no_reverse;
                 a.inner_idx = (int)i;
                 a.inner_literal = p;
@@ -602,7 +603,8 @@ Analysis Analyze(const Regexp* re, int, bool anchored_start) {
       }
     }
   no_reverse:
-    bool hasGood = !P.empty() && lcp(P).size() >= 1;
+    if (!cfg.enable_dfa) return RS_UseNFA;  // meta/strategy.go:1447
+    bool hasGood = !P.empty() && lcp(P).size() >= minlit;
     bool hasTeddy = false, hasAC = false;
     if (P.size() >= 2 && P.size() <= 64) {
       hasTeddy = true;
@@ -620,7 +622,7 @@ Analysis Analyze(const Regexp* re, int, bool anchored_start) {
       if (hasTeddy && allComplete(P) && !(a.has_anchors && nonLine)) return RS_UseTeddy;
       if (hasAC && allComplete(P)) return RS_UseAhoCorasick;
     }
-    if (nfaSize <= 100 && a.digit_lead) return RS_UseDigitPrefilter;
+    if (nfaSize <= 100 && a.digit_lead && cfg.enable_prefilter) return RS_UseDigitPrefilter;
     if (nfaSize < 20) {
       if ((hasWB && a.has_anchors) || a.can_match_empty || hasML) return RS_UseNFA;
       return RS_UseDFA;

@@ -40,6 +40,15 @@ struct Analysis {
   std::string inner_literal;
 };
 
-Analysis Analyze(const gosyntax::Regexp* re, int prog_size_hint, bool anchored_start);
+// the part of reference meta.Config (meta/config.go:31-113) that strategy selection reads
+// (meta/strategy.go:515,963,976,1265,1392,1447; meta/compile.go:466)
+struct AnalysisConfig {
+  bool enable_dfa = true;
+  bool enable_prefilter = true;
+  int min_literal_len = 1;
+};
+
+Analysis Analyze(const gosyntax::Regexp* re, int prog_size_hint, bool anchored_start,
+                 const AnalysisConfig& cfg = AnalysisConfig());
 
 }  // namespace cgx

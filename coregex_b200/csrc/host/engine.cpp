@@ -342,7 +342,8 @@ std::string JitHeader(const FlatDev& f) {
   return o;
 }
 
-int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, std::string& err) {
+int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, std::string& err,
+                   const AnalysisConfig& cfg) {
   std::unique_ptr<Compiled> c(new Compiled());
   c->pattern = pattern;
   memset(&c->flat, 0, sizeof c->flat);
@@ -357,7 +358,7 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
     err = e;
     return COMPILE_UNSUPPORTED;
   }
-  c->an = Analyze(pr.re, (int)c->prog.inst.size(), c->prog.anchored_start);
+  c->an = Analyze(pr.re, (int)c->prog.inst.size(), c->prog.anchored_start, cfg);
 
   // (?m)^-anchored literal sets use the reference's line-anchor wrapper (meta/compile.go:663-686),
   // whose results equal plain leftmost-first: they run on the DFA engine here.

@@ -61,6 +61,7 @@ std::string JitHeader(const FlatDev& f);
 enum CompileStatus { COMPILE_OK = 0, COMPILE_SYNTAX = -1, COMPILE_UNSUPPORTED = -2 };
 
 // err receives the Go-formatted syntax error or an "unsupported: ..." explanation
-int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, std::string& err);
+int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, std::string& err,
+                   const AnalysisConfig& cfg = AnalysisConfig());
 
 }  // namespace cgx

@@ -34,7 +34,8 @@ enum {
   CGX_ERR_NO_DEVICE = -3,   /* no usable CUDA device / driver                                  */
   CGX_ERR_CUDA = -4,        /* a CUDA call failed; cgx_last_error() has the text               */
   CGX_ERR_ARGS = -5,        /* bad arguments (null pointer, misaligned device pointer, ...)    */
-  CGX_ERR_NOMEM = -6
+  CGX_ERR_NOMEM = -6,
+  CGX_ERR_CONFIG = -7       /* cgx_config out of range; errbuf holds "regexp: invalid config: ..." */
 };
 
 /* ---- compile -------------------------------------------------------------------------------
@@ -43,6 +44,38 @@ enum {
  * syntax.Error formats it (reference meta/compile.go:775-784), or an "unsupported: ..." text. */
 int cgx_compile(const char* pattern, size_t pattern_len, cgx_regex** out, char* errbuf, size_t errcap);
 void cgx_free(cgx_regex* re);
+
+/* replaces coregex.CompileWithConfig / meta.CompileWithConfig (reference regex.go:198,
+ * meta/compile.go:62) with meta.Config (meta/config.go:31-113), field for field.
+ * cgx_default_config = meta.DefaultConfig (config.go:101-112); cgx_config_validate = Config.Validate
+ * (config.go:132-170, called from meta/compile.go:53): same ranges, same message ("regexp: invalid config: <Field>: <Message>",
+ * config.go:179-181) in errbuf, status CGX_ERR_CONFIG.  What the fields do here: enable_dfa,
+ * enable_prefilter and min_literal_len steer strategy selection exactly where the reference reads
+ * them (meta/strategy.go:515,963,976,1265,1392,1447; meta/compile.go:466) — cgx_strategy reports the
+ * result, and the digit-prefilter and multi-literal engines are only used when the reference would
+ * use theirs.  max_dfa_states, determinization_limit, max_literals, max_recursion_depth and
+ * enable_ascii_optimization size the reference's lazy-DFA cache and NFA compiler; they are
+ * validated and have no effect on results (the GPU tables are built eagerly, host-side).          */
+typedef struct cgx_config {
+  int enable_dfa;                /* EnableDFA               default 1     */
+  int enable_prefilter;          /* EnablePrefilter         default 1     */
+  uint32_t max_dfa_states;       /* MaxDFAStates            default 10000 */
+  int determinization_limit;     /* DeterminizationLimit    default 1000  */
+  int min_literal_len;           /* MinLiteralLen           default 1     */
+  int max_literals;              /* MaxLiterals             default 256   */
+  int max_recursion_depth;       /* MaxRecursionDepth       default 100   */
+  int enable_ascii_optimization; /* EnableASCIIOptimization default 1     */
+} cgx_config;
+void cgx_default_config(cgx_config* cfg);
+int cgx_config_validate(const cgx_config* cfg, char* errbuf, size_t errcap);
+int cgx_compile_cfg(const char* pattern, size_t pattern_len, const cgx_config* cfg /* NULL = default */,
+                    cgx_regex** out, char* errbuf, size_t errcap);
+
+/* replaces Regex.Longest / meta.Engine.SetLongest (reference regex.go:464, meta/engine.go:250):
+ * leftmost-longest (POSIX) instead of leftmost-first matching for all later searches.  Like the
+ * reference's, this call must not run concurrently with searches.  Patterns whose engine cannot
+ * switch return CGX_ERR_UNSUPPORTED (cgx_last_error says why) and keep leftmost-first.           */
+int cgx_set_longest(cgx_regex* re, int longest);
 
 /* reference meta.Engine.Strategy() (meta/engine.go:191): the strategy name the reference would
  * pick for this pattern, e.g. "UseDigitPrefilter".                                            */
