@@ -22,6 +22,12 @@ int64_t scan_dfa_chunks(int64_t n);
 cudaError_t launch_scan_dfa(const ScanArgs& a, int sm_count, cudaStream_t stream);
 int64_t scan_flat_chunks(int64_t n);
 cudaError_t launch_scan_flat(const ScanArgs& a, int sm_count, cudaStream_t stream, int* grid_out);
+int64_t pike_search_slices(int64_t n);
+size_t pike_search_scratch_bytes(int64_t n);
+cudaError_t launch_pike_search(const uint8_t* h, int64_t n, int64_t base, int64_t after, const uint32_t* code,
+                               const uint32_t* sets, int ninst, int nthreads, int start_pc, uint8_t delim, int mode,
+                               int64_t* out, int64_t cap, void* scratch, unsigned long long* total, cudaStream_t st,
+                               int* launches);
 cudaError_t launch_pike_captures(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
                                  const unsigned long long* d_total, unsigned long long cap,
                                  const uint32_t* code, const uint32_t* sets, int start_pc, int nslots,
@@ -71,7 +77,7 @@ struct cgx_regex {
   int device = -1;
   int sm_count = 0;
   // device copies of the tables
-  DevBuf d_trans, d_eoi, d_lut, d_teddy, d_line;
+  DevBuf d_trans, d_eoi, d_lut, d_teddy, d_line, d_pike_search;
   TeddyDev teddy_dev;
   LineDev line_dev;
   // per-call scratch (serialised by mu)
@@ -198,6 +204,13 @@ struct cgx_regex {
       teddy_dev.max_len = t.max_len;
       teddy_dev.bytes_len = (int)t.bytes.size();
       teddy_dev.blob_bytes = (int)((total + 3) & ~(size_t)3);
+    }
+    if (c->kind == ENG_PIKEVM) {
+      int r;
+      const size_t cb = c->pike_search.code.size() * 4, sb = c->pike_search.sets.size() * 4;
+      if ((r = d_pike_search.ensure(cb + sb + 16))) return r;
+      CU(cudaMemcpy(d_pike_search.p, c->pike_search.code.data(), cb, cudaMemcpyHostToDevice));
+      if (sb) CU(cudaMemcpy((char*)d_pike_search.p + cb, c->pike_search.sets.data(), sb, cudaMemcpyHostToDevice));
     }
     if (c->has_pike) {
       int r;
@@ -382,6 +395,22 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   if (((uintptr_t)d_h & 15) || ((uintptr_t)d_out & 15)) {
     g_last_error = "device pointers must be 16-byte aligned";
     return CGX_ERR_ARGS;
+  }
+  if (c.kind == ENG_PIKEVM) {
+    int r;
+    if ((r = re->d_ticket_total.ensure(64))) return r;
+    if ((r = re->d_status.ensure(pike_search_scratch_bytes((int64_t)len) + 64))) return r;
+    re->epoch = 0;  // the look-back words are used as plain scratch here
+    re->scratch_zero = false;
+    unsigned long long* tt = (unsigned long long*)re->d_ticket_total.p;
+    const uint32_t* code = (const uint32_t*)re->d_pike_search.p;
+    int launches = 0;
+    CU(launch_pike_search(d_h, (int64_t)len, base, after, code, code + c.pike_search.code.size(), c.pike_search.ninst,
+                          c.pike_search.nthreads, c.pike_search.start, c.delim, mode, d_out, (int64_t)cap,
+                          re->d_status.p, tt, st, &launches));
+    re->launches += (uint64_t)launches;
+    if (d_result) CU(cudaMemcpyAsync(d_result, tt, 16, cudaMemcpyDeviceToDevice, st));
+    return CGX_OK;
   }
   if (c.kind != ENG_DFA && c.kind != ENG_TEDDY && c.kind != ENG_LINE) {
     g_last_error = "engine not available in this build";

@@ -377,11 +377,41 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
   // The anchored DFA is built for every pattern: ENG_DFA needs it, and it is also how the
   // record-delimiter safety of the pattern is proven.
   std::string de = BuildDFA(c->prog, /*anchored=*/true, /*max_states=*/160, c->dfa);
-  if (c->kind == ENG_DFA) {
-    if (!de.empty()) {
-      err = "unsupported: " + de + " (PikeVM-kernel fallback for large automata is not built yet)";
+  if (c->kind == ENG_DFA && !de.empty()) {
+    // The automaton does not fit the table kernels: the PikeVM search kernel takes the pattern, as
+    // the reference's PikeVM does when it selects UseNFA or its lazy DFA gives up
+    // (meta/find_indices.go:1172, nfa/pikevm.go:1711).
+    if (c->an.can_match_empty) {
+      err = "unsupported: pattern can match the empty string (needs the sequential empty-match "
+            "rules of meta/findall.go:247-279; not record-parallel)";
       return COMPILE_UNSUPPORTED;
     }
+    const std::string pe = PackPikeSearch(c->prog, c->pike_search);
+    if (!pe.empty()) {
+      err = "unsupported: " + de + "; PikeVM search kernel: " + pe;
+      return COMPILE_UNSUPPORTED;
+    }
+    // records are cut at a byte no instruction can consume
+    ByteSet any{};
+    for (auto& in : c->prog.inst)
+      if (in.op == I_SET)
+        for (int w = 0; w < 4; w++) any[w] |= c->prog.sets[in.set][w];
+    static const char pref[] = "\n etaoinsrhldcumfpgwybvkxjqz\t,.;:/-_=0123456789ETAOINSRHLDCUMFPGWYBVKXJQZ";
+    int chosen = -1;
+    for (const char* q = pref; *q && chosen < 0; q++)
+      if (!set_has(any, (uint8_t)*q)) chosen = (uint8_t)*q;
+    for (int d = 0; d < 256 && chosen < 0; d++)
+      if (!set_has(any, (unsigned)d)) chosen = d;
+    if (chosen < 0) {
+      err = "unsupported: a match can contain every byte value (record-parallel scan needs a "
+            "delimiter no match can contain)";
+      return COMPILE_UNSUPPORTED;
+    }
+    c->delim = (uint8_t)chosen;
+    c->kind = ENG_PIKEVM;
+    c->engine_name = "pikevm";
+  }
+  if (c->kind == ENG_DFA) {
     if (c->dfa.matches_empty || c->an.can_match_empty) {
       err = "unsupported: pattern can match the empty string (needs the sequential empty-match "
             "rules of meta/findall.go:247-279; not record-parallel)";

@@ -17,7 +17,7 @@ namespace cgx {
 enum EngineKind : int {
   ENG_DFA = 0,     // candidate filter + anchored DFA walk (scan_dfa.cu)
   ENG_TEDDY,       // nibble-fingerprint filter + ordered literal verify (scan_teddy.cu)
-  ENG_PIKEVM,      // captures (pikevm_kernel.cu)
+  ENG_PIKEVM,      // PikeVM search kernel: automata too large for the table kernels (pike_search.cu)
   ENG_LINE,        // one lane per record: unanchored forward DFA + reverse DFA (scan_dfa.cu)
 };
 
@@ -46,6 +46,9 @@ struct Compiled {
 
   // ENG_TEDDY
   TeddyTables teddy;
+
+  // ENG_PIKEVM: the whole program, packed for pike_search.cu
+  PikePacked pike_search;
 
   // captures (FindAllSubmatchIndex)
   bool has_pike = false;

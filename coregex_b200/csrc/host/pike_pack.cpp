@@ -2,14 +2,19 @@
 
 namespace cgx {
 
-std::string PackPike(const Prog& p, PikePacked& out) {
+static std::string Pack(const Prog& p, PikePacked& out, size_t max_inst, int max_groups, int max_threads);
+
+std::string PackPike(const Prog& p, PikePacked& out) { return Pack(p, out, 64, 8, 32); }
+std::string PackPikeSearch(const Prog& p, PikePacked& out) { return Pack(p, out, 2048, 1 << 20, 1024); }
+
+static std::string Pack(const Prog& p, PikePacked& out, size_t max_inst, int max_groups, int max_threads) {
   out = PikePacked();
-  if (p.inst.size() > 64) return "program has more than 64 instructions";
-  if (p.num_captures > 8) return "more than 8 capture groups";
+  if (p.inst.size() > max_inst) return "program has more than " + std::to_string(max_inst) + " instructions";
+  if (p.num_captures > max_groups) return "more than " + std::to_string(max_groups) + " capture groups";
   int consuming = 0;
   for (auto& in : p.inst)
     if (in.op == I_SET || in.op == I_MATCH) consuming++;
-  if (consuming > 32) return "more than 32 byte-consuming instructions";
+  if (consuming > max_threads) return "more than " + std::to_string(max_threads) + " byte-consuming instructions";
   out.ninst = (int)p.inst.size();
   out.start = p.start;
   out.nslots = 2 * p.num_captures;

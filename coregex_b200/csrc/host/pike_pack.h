@@ -22,5 +22,7 @@ struct PikePacked {
 
 // returns "" or the reason the program does not fit the kernel
 std::string PackPike(const Prog& p, PikePacked& out);
+// the same layout for the search kernel (pike_search.cu): up to 2048 instructions, 1024 live threads
+std::string PackPikeSearch(const Prog& p, PikePacked& out);
 
 }  // namespace cgx
