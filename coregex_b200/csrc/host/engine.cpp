@@ -377,18 +377,16 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
   // The anchored DFA is built for every pattern: ENG_DFA needs it, and it is also how the
   // record-delimiter safety of the pattern is proven.
   std::string de = BuildDFA(c->prog, /*anchored=*/true, /*max_states=*/160, c->dfa);
-  if (c->kind == ENG_DFA && !de.empty()) {
-    // The automaton does not fit the table kernels: the PikeVM search kernel takes the pattern, as
-    // the reference's PikeVM does when it selects UseNFA or its lazy DFA gives up
-    // (meta/find_indices.go:1172, nfa/pikevm.go:1711).
-    if (c->an.can_match_empty) {
-      err = "unsupported: pattern can match the empty string (needs the sequential empty-match "
-            "rules of meta/findall.go:247-279; not record-parallel)";
-      return COMPILE_UNSUPPORTED;
-    }
+  const bool nullable_pat = c->an.can_match_empty || (de.empty() && c->dfa.matches_empty);
+  if ((c->kind == ENG_DFA || c->kind == ENG_TEDDY) && (!de.empty() || nullable_pat)) {
+    // The automaton does not fit the table kernels, or the pattern can match the empty string (the
+    // empty-match rules of meta/findall.go:247-279 are sequential within a record): the PikeVM
+    // search kernel takes the pattern, as the reference's PikeVM does when it selects UseNFA or its
+    // lazy DFA gives up (meta/find_indices.go:1172, nfa/pikevm.go:1711).
     const std::string pe = PackPikeSearch(c->prog, c->pike_search);
     if (!pe.empty()) {
-      err = "unsupported: " + de + "; PikeVM search kernel: " + pe;
+      err = "unsupported: " + (de.empty() ? std::string("pattern can match the empty string") : de) +
+            "; PikeVM search kernel: " + pe;
       return COMPILE_UNSUPPORTED;
     }
     // records are cut at a byte no instruction can consume
@@ -412,11 +410,6 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
     c->engine_name = "pikevm";
   }
   if (c->kind == ENG_DFA) {
-    if (c->dfa.matches_empty || c->an.can_match_empty) {
-      err = "unsupported: pattern can match the empty string (needs the sequential empty-match "
-            "rules of meta/findall.go:247-279; not record-parallel)";
-      return COMPILE_UNSUPPORTED;
-    }
     // Records are cut at a byte no match can contain.  '\n' whenever possible (lines are what
     // callers think in); otherwise the most frequent text byte the pattern cannot consume, e.g.
     // `\s+` is scanned as records between letters, `[^a]+` as records between 'a's.

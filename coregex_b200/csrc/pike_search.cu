@@ -172,13 +172,23 @@ __global__ void __launch_bounds__(128) pike_search_kernel(const PikeArgs a) {
       while (rs < a.n && __ldg(a.h + rs) != a.delim) rs++;
       rs++;
     }
-    while (rs < hi) {
+    // (the empty record after a trailing delimiter — or an empty haystack — starts at n: it belongs
+    // to the last slice; only a pattern that matches the empty string finds anything there)
+    const bool last_slice = slice == a.nslices - 1;
+    while (rs < hi || (last_slice && rs == a.n)) {
       int64_t rend = rs;
       while (rend < a.n && __ldg(a.h + rend) != a.delim) rend++;
-      int64_t pos = rs;
+      // the reference's FindAll loop (meta/findall.go:221-290) on this record.  `last` = end of the
+      // previous non-empty match: an empty match right there is skipped (:251-259).  It can never
+      // equal a record start, so records are independent.
+      int64_t pos = rs, last = -1;
       while (pos <= rend) {
         int64_t ms = -1, me = -1;
         if (!search<NT, NI>(a, L, rs, pos, rend, ms, me)) break;
+        if (ms == me && ms == last) {
+          pos++;
+          continue;
+        }
         if (EMIT) {
           if ((int64_t)idx < a.cap) {
             a.out[2 * idx] = ms + a.base;
@@ -187,9 +197,11 @@ __global__ void __launch_bounds__(128) pike_search_kernel(const PikeArgs a) {
           idx++;
         }
         cnt++;
-        pos = me > ms ? me : me + 1;
+        if (ms != me) last = me;
+        pos = ms == me ? me + 1 : (me > pos ? me : pos + 1);  // :270-279
       }
       rs = rend + 1;
+      if (rend >= a.n) break;
     }
   }
   if (EMIT) return;
@@ -245,7 +257,7 @@ cudaError_t run(const PikeArgs& a, bool emit, cudaStream_t st) {
 
 }  // namespace
 
-int64_t pike_search_slices(int64_t n) { return n > 0 ? (n + SLICE - 1) / SLICE : 0; }
+int64_t pike_search_slices(int64_t n) { return n > 0 ? (n + SLICE - 1) / SLICE : 1; }  // an empty haystack is one (empty) record
 // scratch: counts[nslices] u32, then blocksum[ceil(nslices / 128)] u64 (8-byte aligned)
 size_t pike_search_scratch_bytes(int64_t n) {
   const int64_t ns = pike_search_slices(n);
@@ -274,7 +286,6 @@ cudaError_t launch_pike_search(const uint8_t* h, int64_t n, int64_t base, int64_
   a.cap = cap;
   a.total = total;
   if (launches) *launches = 0;
-  if (a.nslices == 0) return cudaMemsetAsync(total, 0, 16, st);
   const bool emit = mode == M_FINDALL && out && cap > 0;
   if (launches) *launches = emit ? 3 : 2;
   if (ninst <= 128 && nthreads <= 64) return run<64, 128>(a, emit, st);

@@ -91,3 +91,35 @@ def test_device_entry_base_offset_and_records():
     assert tot == len(want) and flag == 1 and np.array_equal(pairs, want + (1 << 36))
     tot, flag, _ = scan_device(r, t, mode=cg.MODE_COUNT)
     assert tot == len(want)
+
+
+# ---- patterns that can match the empty string (reference meta/findall.go:247-279) --------------------
+NULLABLE = [r"a*", r"\d*", r"(?m)^", r"(?m)$", r"\b", r"x*y?", r"foo|bar|", r"(?m)^\s*", r"\w*@?"]
+
+
+@pytest.mark.gpu
+def test_empty_match_rule_reference_vector():
+    # the reference's own example (meta/findall.go:249): "a*" on "ab" -> [[0 1] [2 2]]
+    assert cg.Compile("a*").FindAllIndex(b"ab") == [[0, 1], [2, 2]]
+    assert cg.Compile("a*").FindAllIndex(b"") == [[0, 0]]
+    assert cg.Compile("a*").FindAllIndex(b"baaa\n") == [[0, 0], [1, 4], [5, 5]]
+    assert cg.Compile(r"\d*").Count(b"12 3") == 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pat", NULLABLE)
+def test_nullable_patterns_against_oracle(pat):
+    rng = random.Random(hash(pat) & 0xFFFF)
+    r, o = cg.Compile(pat), Oracle(pat)
+    assert r.engine == "pikevm"
+    for hay in [b"", b"\n", b"a", b"ab", b"aa\n", b"\n\n", b"xy foo 12\nbar@\n\n aaa", b" \t x\n\ty"]:
+        want = o.find_all(np.frombuffer(hay, dtype=np.uint8))
+        got = r.find_all_index_array(hay, cap=4 * len(hay) + 8)
+        assert np.array_equal(got, want), (pat, hay, got.tolist(), want.tolist())
+    for n_lines in (3, 40, 400):
+        hay = _corpus(rng, n_lines, b"ab12 xy@\t", [b"foo", b"bar", b"aaa", b"123", b"x@y", b"  "])
+        a = np.frombuffer(hay, dtype=np.uint8)
+        want = o.find_all(a)
+        got = r.find_all_index_array(hay, cap=2 * len(hay) + 8)
+        assert got.shape == want.shape and np.array_equal(got, want), (pat, n_lines)
+        assert r.Count(hay) == len(want) and r.Match(hay)

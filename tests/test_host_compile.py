@@ -44,9 +44,17 @@ def test_compile_errors_are_go_formatted():
 
 
 def test_unsupported_patterns_fail_loudly():
-    for pat in ["a*", r"(?s)x.y", r"(?s).+", r"\pL"]:  # nullable / no byte is a safe delimiter / Unicode tables
+    for pat in [r"(?s)x.y", r"(?s).+", r"\pL"]:  # no byte is a safe delimiter / Unicode tables
         with pytest.raises(cg.UnsupportedError):
             cg.Compile(pat)
+
+
+def test_nullable_and_large_automata_go_to_the_pikevm_engine():
+    # patterns that can match the empty string need the sequential empty-match rules of the
+    # reference's FindAll loop (meta/findall.go:247-279); automata over 160 DFA states do not fit
+    # the table kernels: both run on the PikeVM search kernel instead of being refused
+    for pat in ["a*", r"\d*", "(?m)^", r"\b", "foo|bar|", r"[ab]*a[ab]{8}"]:
+        assert cg.Compile(pat).engine == "pikevm"
 
 
 def test_no_device_means_error_not_fallback():
