@@ -103,7 +103,7 @@ def test_empty_match_rule_reference_vector():
     assert cg.Compile("a*").FindAllIndex(b"ab") == [[0, 1], [2, 2]]
     assert cg.Compile("a*").FindAllIndex(b"") == [[0, 0]]
     assert cg.Compile("a*").FindAllIndex(b"baaa\n") == [[0, 0], [1, 4], [5, 5]]
-    assert cg.Compile(r"\d*").Count(b"12 3") == 3
+    assert cg.Compile(r"\d*").Count(b"12 3") == 2
 
 
 @pytest.mark.gpu
