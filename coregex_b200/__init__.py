@@ -188,8 +188,10 @@ class Regex:
 
     @property
     def delimiter(self):
-        """Record delimiter byte of this pattern (no match can contain it); b"\\n" when possible."""
-        return bytes([_lib.cgx_delimiter(self._h)])
+        """Record delimiter byte of this pattern (no match can contain it); b"\\n" when possible.
+        None: matches may contain every byte value (the haystack is scanned as one record)."""
+        d = _lib.cgx_delimiter(self._h)
+        return None if d < 0 else bytes([d])
 
     def set_bitstream(self, on):
         """Tests / A-B runs: keep a flat deterministic pattern on the candidate+DFA kernel

@@ -25,7 +25,7 @@ cudaError_t launch_scan_flat(const ScanArgs& a, int sm_count, cudaStream_t strea
 int64_t pike_search_slices(int64_t n);
 size_t pike_search_scratch_bytes(int64_t n);
 cudaError_t launch_pike_search(const uint8_t* h, int64_t n, int64_t base, int64_t after, const uint32_t* code,
-                               const uint32_t* sets, int ninst, int nthreads, int start_pc, uint8_t delim, int mode,
+                               const uint32_t* sets, int ninst, int nthreads, int start_pc, int delim, int mode,
                                int64_t* out, int64_t cap, void* scratch, unsigned long long* total, cudaStream_t st,
                                int* launches);
 cudaError_t launch_pike_captures(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
@@ -387,7 +387,10 @@ int cgx_debug_set_bitstream(cgx_regex* re, int on) {
   }
   return was;
 }
-int cgx_delimiter(const cgx_regex* re) { return re->c->kind == ENG_TEDDY ? '\n' : re->c->delim; }
+int cgx_delimiter(const cgx_regex* re) {
+  if (!re->c->has_delim) return -1;  // matches may contain every byte value: the haystack is one record
+  return re->c->kind == ENG_TEDDY ? '\n' : re->c->delim;
+}
 
 static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base, int mode,
                        int64_t* d_out, size_t cap, uint64_t* d_result, cudaStream_t st, int64_t after = 0) {
@@ -398,6 +401,10 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   }
   if (c.kind == ENG_PIKEVM) {
     int r;
+    if (!c.has_delim && (base != 0 || after != 0)) {
+      g_last_error = "a pattern without a record delimiter cannot be scanned in shards";
+      return CGX_ERR_ARGS;
+    }
     if ((r = re->d_ticket_total.ensure(64))) return r;
     if ((r = re->d_status.ensure(pike_search_scratch_bytes((int64_t)len) + 64))) return r;
     re->epoch = 0;  // the look-back words are used as plain scratch here
@@ -406,7 +413,7 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
     const uint32_t* code = (const uint32_t*)re->d_pike_search.p;
     int launches = 0;
     CU(launch_pike_search(d_h, (int64_t)len, base, after, code, code + c.pike_search.code.size(), c.pike_search.ninst,
-                          c.pike_search.nthreads, c.pike_search.start, c.delim, mode, d_out, (int64_t)cap,
+                          c.pike_search.nthreads, c.pike_search.start, c.has_delim ? (int)c.delim : 256, mode, d_out, (int64_t)cap,
                           re->d_status.p, tt, st, &launches));
     re->launches += (uint64_t)launches;
     if (d_result) CU(cudaMemcpyAsync(d_result, tt, 16, cudaMemcpyDeviceToDevice, st));
@@ -577,6 +584,10 @@ int cgx_scan_records_device(cgx_regex* re, const uint8_t* d_h, size_t len, const
   int r = re->ensure_device();
   if (r) return r;
   Compiled& c = *re->c;
+  if (!c.has_delim) {
+    g_last_error = "unsupported: matches of this pattern can contain every byte value, records cannot be batched";
+    return CGX_ERR_UNSUPPORTED;
+  }
   if (c.an.has_anchors) {
     g_last_error = "unsupported: a pattern with anchors or look-around depends on where each record begins and ends; "
                    "scan such records one call at a time";
@@ -780,7 +791,8 @@ static int host_scan(cgx_regex* re, const uint8_t* h, size_t len, int mode, int6
   std::lock_guard<std::mutex> lk(re->mu);
   int r = re->ensure_device();
   if (r) return r;
-  if (len >= (forced_piece() ? 2 * forced_piece() : kPipelineMin)) return host_scan_pipelined(re, h, len, mode, out, cap, result);
+  if (re->c->has_delim && len >= (forced_piece() ? 2 * forced_piece() : kPipelineMin))
+    return host_scan_pipelined(re, h, len, mode, out, cap, result);
   if ((r = re->d_hay.ensure(len + 16))) return r;
   if (mode == CGX_MODE_FINDALL && cap && (r = re->d_out.ensure(cap * 16))) return r;
   cudaStream_t st = 0;

@@ -378,16 +378,16 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
   // record-delimiter safety of the pattern is proven.
   std::string de = BuildDFA(c->prog, /*anchored=*/true, /*max_states=*/160, c->dfa);
   const bool nullable_pat = c->an.can_match_empty || (de.empty() && c->dfa.matches_empty);
-  if ((c->kind == ENG_DFA || c->kind == ENG_TEDDY) && (!de.empty() || nullable_pat)) {
-    // The automaton does not fit the table kernels, or the pattern can match the empty string (the
-    // empty-match rules of meta/findall.go:247-279 are sequential within a record): the PikeVM
-    // search kernel takes the pattern, as the reference's PikeVM does when it selects UseNFA or its
-    // lazy DFA gives up (meta/find_indices.go:1172, nfa/pikevm.go:1711).
+  // The PikeVM search kernel takes what the table kernels cannot: automata over 160 DFA states,
+  // patterns that can match the empty string (the empty-match rules of meta/findall.go:247-279 are
+  // sequential within a record) and patterns whose matches may contain every byte value (no record
+  // delimiter: the haystack is one record, scanned by one lane) — as the reference's PikeVM does
+  // when it selects UseNFA or its lazy DFA gives up (meta/find_indices.go:1172, nfa/pikevm.go:1711).
+  auto to_pikevm = [&](const std::string& why) -> bool {
     const std::string pe = PackPikeSearch(c->prog, c->pike_search);
     if (!pe.empty()) {
-      err = "unsupported: " + (de.empty() ? std::string("pattern can match the empty string") : de) +
-            "; PikeVM search kernel: " + pe;
-      return COMPILE_UNSUPPORTED;
+      err = "unsupported: " + why + "; PikeVM search kernel: " + pe;
+      return false;
     }
     // records are cut at a byte no instruction can consume
     ByteSet any{};
@@ -400,14 +400,14 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
       if (!set_has(any, (uint8_t)*q)) chosen = (uint8_t)*q;
     for (int d = 0; d < 256 && chosen < 0; d++)
       if (!set_has(any, (unsigned)d)) chosen = d;
-    if (chosen < 0) {
-      err = "unsupported: a match can contain every byte value (record-parallel scan needs a "
-            "delimiter no match can contain)";
-      return COMPILE_UNSUPPORTED;
-    }
-    c->delim = (uint8_t)chosen;
+    c->has_delim = chosen >= 0;
+    c->delim = (uint8_t)(chosen >= 0 ? chosen : 0);
     c->kind = ENG_PIKEVM;
-    c->engine_name = "pikevm";
+    c->engine_name = c->has_delim ? "pikevm" : "pikevm-serial";
+    return true;
+  };
+  if ((c->kind == ENG_DFA || c->kind == ENG_TEDDY) && (!de.empty() || nullable_pat)) {
+    if (!to_pikevm(de.empty() ? std::string("pattern can match the empty string") : de)) return COMPILE_UNSUPPORTED;
   }
   if (c->kind == ENG_DFA) {
     // Records are cut at a byte no match can contain.  '\n' whenever possible (lines are what
@@ -421,12 +421,13 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
       for (int d = 0; d < 256 && chosen < 0; d++)
         if (DelimiterSafe(c->dfa, (uint8_t)d)) chosen = d;
       if (chosen < 0) {
-        err = "unsupported: a match can contain every byte value (record-parallel scan needs a "
-              "delimiter no match can contain)";
-        return COMPILE_UNSUPPORTED;
+        if (!to_pikevm("a match can contain every byte value (no record delimiter)")) return COMPILE_UNSUPPORTED;
+      } else {
+        c->delim = (uint8_t)chosen;
       }
-      c->delim = (uint8_t)chosen;
     }
+  }
+  if (c->kind == ENG_DFA) {
     for (int k = 1; k < SK_COUNT; k++)
       if (c->dfa.start[k] != c->dfa.start[0]) c->kind_lut_needed = true;
     memset(c->lut, 0, sizeof c->lut);

@@ -40,6 +40,7 @@ struct Compiled {
   bool kind_lut_needed = false;
   FlatDev flat;  // nops == 0 when the pattern is not flat
   uint8_t delim = '\n';
+  bool has_delim = true;  // false: matches may contain every byte value (PikeVM engine, one record)
 
   // ENG_LINE: unanchored forward DFA (leftmost-first end) and reverse DFA (longest = leftmost start)
   DfaTables udfa, rdfa;

@@ -33,7 +33,7 @@ struct PikeArgs {
   const uint32_t* code;  // 2 words per instruction (host/pike_pack.h)
   const uint32_t* sets;  // 8 words per byte set
   int ninst, start_pc;
-  uint8_t delim;
+  int delim;  // record delimiter byte, or 256: the whole haystack is one record
   int64_t nslices;
   unsigned* counts;             // per slice (count pass out, then exclusive offsets within the block)
   unsigned long long* blocksum; // per block of slices: total, then exclusive prefix
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(128) pike_search_kernel(const PikeArgs a) {
     const int64_t lo = slice * SLICE, hi = lo + SLICE < a.n ? lo + SLICE : a.n;
     // first record that starts in [lo, hi)
     int64_t rs = lo;
-    if (lo > 0 && __ldg(a.h + lo - 1) != a.delim) {
-      while (rs < a.n && __ldg(a.h + rs) != a.delim) rs++;
+    if (lo > 0 && (int)__ldg(a.h + lo - 1) != a.delim) {
+      while (rs < a.n && (int)__ldg(a.h + rs) != a.delim) rs++;
       rs++;
     }
     // (the empty record after a trailing delimiter — or an empty haystack — starts at n: it belongs
@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(128) pike_search_kernel(const PikeArgs a) {
     const bool last_slice = slice == a.nslices - 1;
     while (rs < hi || (last_slice && rs == a.n)) {
       int64_t rend = rs;
-      while (rend < a.n && __ldg(a.h + rend) != a.delim) rend++;
+      if (a.delim > 255) rend = a.n;
+      while (rend < a.n && (int)__ldg(a.h + rend) != a.delim) rend++;
       // the reference's FindAll loop (meta/findall.go:221-290) on this record.  `last` = end of the
       // previous non-empty match: an empty match right there is skipped (:251-259).  It can never
       // equal a record start, so records are independent.
@@ -266,7 +267,7 @@ size_t pike_search_scratch_bytes(int64_t n) {
 
 // mode: ScanMode.  total: device u64[2] {matches, flag}.  Returns the number of kernels launched in *launches.
 cudaError_t launch_pike_search(const uint8_t* h, int64_t n, int64_t base, int64_t after, const uint32_t* code,
-                               const uint32_t* sets, int ninst, int nthreads, int start_pc, uint8_t delim, int mode,
+                               const uint32_t* sets, int ninst, int nthreads, int start_pc, int delim, int mode,
                                int64_t* out, int64_t cap, void* scratch, unsigned long long* total, cudaStream_t st,
                                int* launches) {
   PikeArgs a;

@@ -123,3 +123,16 @@ def test_nullable_patterns_against_oracle(pat):
         got = r.find_all_index_array(hay, cap=2 * len(hay) + 8)
         assert got.shape == want.shape and np.array_equal(got, want), (pat, n_lines)
         assert r.Count(hay) == len(want) and r.Match(hay)
+
+
+@pytest.mark.gpu
+def test_patterns_without_a_record_delimiter_scan_the_haystack_as_one_record():
+    rng = random.Random(3)
+    for pat in [r"(?s)x.y", r"(?m)^POST\s+\S+", r"(?s)a.+?b"]:
+        r, o = cg.Compile(pat), Oracle(pat)
+        assert r.engine == "pikevm-serial"
+        hay = _corpus(rng, 300, b"abxy \tPOST", [b"POST /a", b"x\ny", b"POST\n\n /b c", b"a\nb"])
+        want = o.find_all(np.frombuffer(hay, dtype=np.uint8))
+        got = r.find_all_index_array(hay)
+        assert got.shape == want.shape and np.array_equal(got, want) and len(want) > 5, (pat, len(want))
+        assert r.Count(hay) == len(want)

@@ -44,9 +44,13 @@ def test_compile_errors_are_go_formatted():
 
 
 def test_unsupported_patterns_fail_loudly():
-    for pat in [r"(?s)x.y", r"(?s).+", r"\pL"]:  # no byte is a safe delimiter / Unicode tables
+    for pat in [r"\pL", r"\p{Greek}+"]:  # Unicode property tables
         with pytest.raises(cg.UnsupportedError):
             cg.Compile(pat)
+    # matches that may contain every byte value leave no record delimiter: one record, one lane
+    for pat in [r"(?s)x.y", r"(?s).+", r"(?m)^POST\s+\S+"]:
+        r = cg.Compile(pat)
+        assert r.engine == "pikevm-serial" and r.delimiter is None
 
 
 def test_nullable_and_large_automata_go_to_the_pikevm_engine():
