@@ -125,7 +125,14 @@ __device__ bool search(const PikeArgs& a, Lane<NT, NI>& L, int64_t rs, int64_t a
     // a new thread at the lowest priority while nothing has matched (the membership bits still
     // describe list c: it was built as the "next" list of the step before)
     if (!matched) add_thread(a, L, c, a.start_pc, p, (int32_t)(p - rs));
-    if (L.n[c] == 0) break;
+    if (L.n[c] == 0) {
+      // nothing alive: done once something has matched or the record is exhausted; otherwise the
+      // seed's closure was empty here (a look-around that fails at p, e.g. a leading `\b`) and the
+      // search moves on (reference nfa/pikevm.go:1747-1829 keeps seeding while nothing has matched)
+      if (matched || p >= rend) break;
+      for (int w = 0; w < NI / 32; w++) L.vis[w] = 0u;
+      continue;
+    }
     const int byte = p < a.n ? (int)__ldg(a.h + p) : -1;
     const int nx = c ^ 1;
     L.n[nx] = 0;

@@ -73,6 +73,10 @@ constexpr int NSLOTS = 32 * (K + 1);       // word w lives in slot w + w / K (on
 // slot NSLOTS stays all zero: lane 31 has no neighbour word, it reads this one instead (no class
 // byte, no marker: a word that leaves every piece of per-lane state as it is)
 constexpr int NSLOTS1 = NSLOTS + 1;
+#ifndef CGX_CAP
+#define CGX_CAP 320
+#endif
+constexpr int CAP = CGX_CAP;               // staged matches per chunk (the IP corpus has ~165 per 16 KB)
 static_assert(K == 4 || K == 8 || K == 16, "words per lane: a power of two that divides 32");
 
 // ---- pipe-aware primitives (the kernel is bound by the integer ALU pipe) -------
@@ -141,17 +145,19 @@ struct alignas(16) Slot {
 };
 struct WarpSmem {
   alignas(128) uint8_t win[NB][TILE];
-  // class bitmaps of the chunk being scanned; after sweep 2 array 0 holds (starts, ends) instead.
-  // Two buffers: a chunk's result waits here for its global offset while the next chunk is scanned.
-  Slot cls[2][NPAIR][NSLOTS1];
+  // class bitmaps of the chunk being scanned; after sweep 2 array 0 holds (starts, ends) instead
+  Slot cls[NPAIR][NSLOTS1];
   uint64_t mk[NSLOTS1];       // sweep 1 -> sweep 2: "a match can start here", forward orientation
+  // A chunk's matches wait here (chunk-relative u16 offsets, in match order) for the chunk's global
+  // offset while the next chunk is scanned: two buffers.  A chunk with more than CAP matches keeps
+  // its bitmaps instead and waits for its offset on the spot.
+  uint16_t stS[2][CAP], stE[2][CAP];
   uint64_t mbar[NB];
-  uint32_t rank[2][32];       // per buffer and lane: starts before the lane | ends before it << 16
-  // matches of a serially replayed segment that end beyond the chunk's bitmap (per buffer):
+  // matches of a serially replayed segment that end beyond the chunk's bitmap (per staging buffer):
   // found again, and stored, when the chunk's offset is known
   int64_t far_from[2], far_stop[2];
   uint32_t far_cnt[2];
-  uint32_t bits_cnt[2];       // matches recorded in the bitmaps
+  uint32_t bits_cnt[2];       // matches recorded in the bitmaps / staged
 };
 // a scanned chunk handed from a scanning warp to the CTA's resolver warp (one slot per buffer)
 struct Mail {
@@ -163,7 +169,13 @@ struct Mail {
 struct CtaSmem {
   WarpSmem w[FW_WARPS];
   Mail mail[FW_WARPS][2];
-  volatile int done[FW_WARPS];
+  // FindAll: the CTA's warps scan GANGS of FW_WARPS consecutive chunks (warp w takes chunk
+  // gang * FW_WARPS + w).  The resolver warp draws the gang tickets, two gangs ahead, into this ring:
+  // (sequence number + 1) << 32 | ticket.
+  volatile unsigned long long tk[4];
+  // arrivals << 40 | matches of the gang being scanned (per parity of its sequence number): the
+  // last warp to arrive publishes the gang's count in the look-back words
+  unsigned long long gang_acc[2];
 };
 
 __device__ __forceinline__ uint64_t mk64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
@@ -240,12 +252,42 @@ __device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t
   return mk64(pack_rev(fl, one), pack_rev(fl + 8, one));  // bytes 0..31 in the high word
 }
 
-// Class bitmaps (reversed orientation) of the 64-byte piece at `p`: 4 x LDS.128.
-__device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* p, uint32_t one, uint64_t (&cm)[4]) {
+// Class bitmaps (reversed orientation) of the lane's 64-byte piece of the tile at `win`: 4 x LDS.128.
+// Pieces lie 64 bytes apart, so if every lane read quarter j of its piece with load j the eight lanes
+// of a quarter-warp would meet in two groups of four banks (a 4-way conflict: 16 wavefronts per load
+// instead of 4).  Lane l therefore reads quarter j ^ r with load j, r = (l >> 1) & 3 (CGX_ROT): the
+// four lanes that share a bank group take four different quarters.  The flags are packed as if load j
+// were quarter j; two byte permutes per class word (per-lane selectors) put the 16-bit fields back.
+struct LaneRot {
+  uint32_t o0;               // lane * 64 + (r << 4): offset of the quarter load 0 reads
+  uint32_t sel_lo, sel_hi;   // __byte_perm selectors that swap the 16-bit fields q <-> q ^ r
+};
+#ifndef CGX_ROT
+#define CGX_ROT 1
+#endif
+__device__ __forceinline__ LaneRot lane_rot(int lane) {
+  LaneRot lr;
+  const uint32_t r = CGX_ROT ? ((uint32_t)lane >> 1) & 3u : 0u;
+  lr.o0 = (uint32_t)lane * 64u + (r << 4);
+  // field q (bytes 16 q .. 16 q + 15 of the piece) occupies bytes 7 - 2 q and 6 - 2 q of the word
+  uint32_t sl = 0u, sh = 0u;
+#pragma unroll
+  for (uint32_t i = 0; i < 8u; i++) {
+    const uint32_t q = (7u - i) >> 1, sub = (7u - i) & 1u;
+    const uint32_t src = 7u - (2u * (q ^ r) + sub);
+    if (i < 4u) sl |= src << (4u * i);
+    else sh |= src << (4u * (i - 4u));
+  }
+  lr.sel_lo = sl;
+  lr.sel_hi = sh;
+  return lr;
+}
+__device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* win, const LaneRot& lr, uint32_t one,
+                                               uint64_t (&cm)[4]) {
   uint32_t w[16];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    const uint4 v = *reinterpret_cast<const uint4*>(p + (j << 4));
+    const uint4 v = *reinterpret_cast<const uint4*>(win + (lr.o0 ^ (uint32_t)(j << 4)));
     w[4 * j] = v.x;
     w[4 * j + 1] = v.y;
     w[4 * j + 2] = v.z;
@@ -255,6 +297,13 @@ __device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* 
   cm[1] = P_NCLASSES > 1 ? class_rev64<1>(f, w, one) : 0ull;
   cm[2] = P_NCLASSES > 2 ? class_rev64<2>(f, w, one) : 0ull;
   cm[3] = P_NCLASSES > 3 ? class_rev64<3>(f, w, one) : 0ull;
+#if CGX_ROT
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const uint32_t lo = lo32(cm[c]), hi = hi32(cm[c]);
+    cm[c] = mk64(__byte_perm(lo, hi, lr.sel_hi), __byte_perm(lo, hi, lr.sel_lo));
+  }
+#endif
 }
 
 // ---- marker passes, one word at a time -----------------------------------------------------------
@@ -546,10 +595,10 @@ __device__ unsigned long long lb_resolve(const ScanArgs& a, int64_t chunk, int l
 // 64-bit atomic carries both the arrival count (bits 40..) and the running sum (bits 0..39), so the
 // last arrival knows the group's total without re-reading anything — and puts the accumulator back
 // to zero for the next launch.
-__device__ __forceinline__ void publish_count(const ScanArgs& a, int64_t chunk, unsigned cnt, int lane) {
-  if (lane == 0) {
+__device__ __forceinline__ void publish_count(const ScanArgs& a, int64_t chunk, unsigned cnt, int64_t nunits) {
+  {
     const int64_t g = chunk >> 5;
-    const int64_t members = a.nchunks - (g << 5) < 32 ? a.nchunks - (g << 5) : 32;
+    const int64_t members = nunits - (g << 5) < 32 ? nunits - (g << 5) : 32;
     st_status(&a.status[chunk], ep_word(a, LB_AGG, cnt));
     const unsigned long long old = atomicAdd(&a.gacc[g], (1ull << 40) | cnt);
     if ((int64_t)(old >> 40) == members - 1) {
@@ -559,39 +608,57 @@ __device__ __forceinline__ void publish_count(const ScanArgs& a, int64_t chunk, 
   }
 }
 
-// The resolver warp: takes the oldest handed-over chunk of its CTA (a younger one cannot resolve
-// before it: both need every earlier count), waits for its offset and hands the offset back; the
-// scanning warp stores its own matches when it next needs the buffer.
-__device__ void resolver_warp(const ScanArgs& a, CtaSmem& cs, int lane) {
-  for (;;) {
-    // lane l looks at slots l and l + 32 (slot s = warp s >> 1, buffer s & 1)
-    unsigned mine = 0xFFFFFFFFu;  // chunk numbers are 32-bit tickets
-    int myslot = 0;
-    bool all_done = true;
-#pragma unroll
-    for (int s = lane; s < 2 * FW_WARPS; s += 32) {
-      const Mail& m = cs.mail[s >> 1][s & 1];
-      all_done = all_done && cs.done[s >> 1] != 0;  // read BEFORE the slot: a warp hands over, then sets done
-      cgx_fence_block();
-      if (m.state == 1 && (unsigned)m.chunk < mine) {
-        mine = (unsigned)m.chunk;
-        myslot = s;
-      }
-    }
-    const unsigned best = __reduce_min_sync(FULL, mine);
-    if (best == 0xFFFFFFFFu) {
-      if (__all_sync(FULL, all_done)) return;
-      cgx_idle();  // nothing handed over: a chunk takes tens of microseconds to scan
-      continue;
-    }
-    const int slot = __shfl_sync(FULL, myslot, __ffs((int)__ballot_sync(FULL, mine == best)) - 1);
-    const unsigned long long excl = lb_resolve(a, (int64_t)best, lane);
+// The resolver warp (FindAll).  The unit of the look-back is the GANG: FW_WARPS consecutive chunks
+// scanned by the warps of one CTA.  Per gang the resolver waits until every warp has handed its
+// count over, turns the counts into offsets within the gang (one warp scan), resolves the gang's
+// global offset by the two-level look-back — one L2 round trip per gang, not per chunk — and hands
+// every warp the global index of its chunk's first match; the scanning warps store their staged
+// matches themselves when they next need the buffer.  It also draws the CTA's gang tickets.
+__device__ void resolver_warp(const ScanArgs& a, CtaSmem& cs, int lane, unsigned ngangs) {
+  auto fetch = [&](unsigned seq) -> unsigned {
+    unsigned t = 0;
     if (lane == 0) {
-      Mail& m = cs.mail[slot >> 1][slot & 1];
-      m.excl = excl;
+      t = atomicAdd(a.ticket, 1u);
+      // every CTA draws exactly one ticket past the last gang; the very last draw of the launch
+      // puts the counter back to zero
+      if (t == ngangs + gridDim.x - 1u) *a.ticket = 0u;
+      cs.tk[seq & 3u] = ((unsigned long long)(seq + 1u) << 32) | t;
+    }
+    return __shfl_sync(FULL, t, 0);
+  };
+  unsigned g = fetch(0u);
+  unsigned gn = g < ngangs ? fetch(1u) : 0xFFFFFFFFu;
+  for (unsigned i = 0; g < ngangs; i++) {
+    const unsigned gnn = gn < ngangs ? fetch(i + 2u) : 0xFFFFFFFFu;
+    const int b = (int)(i & 1u);
+    for (;;) {
+      int st = 1;
+      if (lane < FW_WARPS) st = cs.mail[lane][b].state;
+      if (__all_sync(FULL, st == 1)) break;
+      cgx_backoff();
+    }
+    cgx_fence_block();
+    const unsigned cnt = lane < FW_WARPS ? cs.mail[lane][b].cnt : 0u;
+    unsigned x = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned y = __shfl_up_sync(FULL, x, d);
+      if (lane >= d) x += y;
+    }
+#ifdef CGX_EXP_NOLB
+    // experiment only (wrong output order): what the kernel would do if offsets cost nothing
+    const unsigned long long excl = (unsigned long long)g * FW_WARPS * 100ull;
+#else
+    const unsigned long long excl = lb_resolve(a, (int64_t)g, lane);
+#endif
+    if (lane < FW_WARPS) {
+      Mail& m = cs.mail[lane][b];
+      m.excl = excl + (x - cnt);
       cgx_fence_block();
       m.state = 2;
     }
+    g = gn;
+    gn = gnn;
   }
 }
 
@@ -609,6 +676,14 @@ __device__ __forceinline__ void emit_half(uint32_t w, int64_t pos0, int64_t*& o,
     o += 2;
   }
 }
+__device__ __forceinline__ void stage_half(uint32_t w, int pos0, uint16_t*& o) {
+  while (w) {
+    const int b = __ffs((int)w) - 1;
+    w &= w - 1u;
+    *o++ = (uint16_t)(pos0 + b);
+  }
+}
+// bitmaps -> global memory (a chunk that did not fit the staging buffer; its offset is known)
 template <bool CHECK>
 __device__ __forceinline__ void extract_words(const ScanArgs& a, const Slot* res, int64_t wb, int64_t* os, int64_t* oe) {
   const int64_t* end = a.out + 2 * a.cap;
@@ -622,19 +697,63 @@ __device__ __forceinline__ void extract_words(const ScanArgs& a, const Slot* res
     emit_half<CHECK>(hi32(v.b), pb + 32, oe, end);
   }
 }
-__device__ __forceinline__ void extract(const ScanArgs& a, WarpSmem& ws, int sb, int64_t chunk, unsigned long long excl,
-                                        unsigned cnt, int lane) {
-  const Slot* res = ws.cls[sb][0] + lane * (K + 1);
-  const uint32_t rk = ws.rank[sb][lane];
+// rk: starts before this lane's words | ends before them << 16
+__device__ __forceinline__ void extract_direct(const ScanArgs& a, const WarpSmem& ws, int64_t chunk,
+                                               unsigned long long excl, unsigned cnt, uint32_t rk, int lane) {
+  const Slot* res = ws.cls[0] + lane * (K + 1);
   int64_t* os = a.out + 2 * (excl + (rk & 0xFFFFu));
   int64_t* oe = a.out + 2 * (excl + (rk >> 16)) + 1;
   const int64_t wb = chunk * (int64_t)CHUNKB + a.base + (int64_t)lane * (K * 64);
   if ((int64_t)(excl + cnt) <= a.cap) extract_words<false>(a, res, wb, os, oe);  // the usual case: everything fits
   else extract_words<true>(a, res, wb, os, oe);
-  // matches of a replayed segment that end beyond the bitmap: found again, stored after the others
-  if (lane == 0 && ws.far_cnt[sb])
-    replay_cold(a, chunk * (int64_t)CHUNKB, nullptr, ws.far_from[sb], ws.far_stop[sb], a.out, excl + ws.bits_cnt[sb],
-                nullptr);
+}
+// bitmaps -> staging buffer sb: chunk-relative offsets in match order.  Starts: every lane walks the
+// set bits of its own K words (rk = starts before them).  Ends: starts and ends alternate, so the end
+// of the i-th match is the first end bit after the i-th start — one lane per MATCH, which spreads
+// the work evenly over the warp however the matches are distributed over the lanes' words.
+__device__ __forceinline__ void extract_staged(WarpSmem& ws, int sb, uint32_t rk, unsigned n, int lane) {
+  const Slot* res = ws.cls[0] + lane * (K + 1);
+  uint16_t* os = ws.stS[sb] + (rk & 0xFFFFu);
+  const int wb = lane * (K * 64);
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {
+    const uint64_t v = res[j].a;
+    const int pb = wb + j * 64;
+    stage_half(lo32(v), pb, os);
+    stage_half(hi32(v), pb + 32, os);
+  }
+  __syncwarp();
+  const Slot* all = ws.cls[0];
+  const uint16_t* ss = ws.stS[sb];
+  uint16_t* se = ws.stE[sb];
+#pragma unroll 1
+  for (unsigned i = lane; i < n; i += 32) {
+    const unsigned p = (unsigned)ss[i] + 1u;  // a match is not empty: its end lies after its start
+    unsigned w = p >> 6;
+    uint64_t bits = all[w + w / K].b & (~0ull << (p & 63u));
+    while (bits == 0ull && w < (unsigned)NWORDS - 1u) {
+      w++;
+      bits = all[w + w / K].b;
+    }
+    const uint32_t lo = lo32(bits), hi = hi32(bits);
+    se[i] = (uint16_t)(w * 64u + (lo ? (unsigned)__ffs((int)lo) - 1u : 31u + (unsigned)__ffs((int)hi)));
+  }
+}
+// staged matches of a resolved chunk -> int64 pairs in global match order (coalesced 16-byte stores)
+__device__ __forceinline__ void write_out(const ScanArgs& a, const WarpSmem& ws, int sb, int64_t chunk, unsigned n,
+                                          unsigned long long excl, int lane) {
+  const int64_t b = chunk * (int64_t)CHUNKB + a.base;
+  const uint16_t* ss = ws.stS[sb];
+  const uint16_t* se = ws.stE[sb];
+  if ((int64_t)(excl + n) <= a.cap) {  // the usual case: the whole chunk fits the output
+    longlong2* o = reinterpret_cast<longlong2*>(a.out) + excl;
+    for (unsigned i = lane; i < n; i += 32) o[i] = make_longlong2(b + ss[i], b + se[i]);
+  } else {
+    for (unsigned i = lane; i < n; i += 32) {
+      const unsigned long long gi = excl + i;
+      if ((int64_t)gi < a.cap) *reinterpret_cast<longlong2*>(a.out + 2 * gi) = make_longlong2(b + ss[i], b + se[i]);
+    }
+  }
 }
 
 }  // namespace
@@ -653,34 +772,51 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   CtaSmem& cs = *reinterpret_cast<CtaSmem*>(smem_raw);
   const FlatDev& f = a.flat;
-  if (tid < 2 * FW_WARPS) {
-    cs.mail[tid >> 1][tid & 1].state = 0;
-    cs.done[tid >> 1] = 0;
-  }
+  if (tid < 2 * FW_WARPS) cs.mail[tid >> 1][tid & 1].state = 0;
+  if (tid < 4) cs.tk[tid] = 0ull;
+  if (tid < 2) cs.gang_acc[tid] = 0ull;
   static_assert(2 * FW_WARPS <= FW_THREADS, "one thread per mail slot at start-up");
   if (warp < FW_WARPS && lane == 0) {
 #pragma unroll
     for (int b = 0; b < NB; b++) mbar_init(&cs.w[warp].mbar[b], 1);
     fence_mbar_init();
-    for (int b = 0; b < 2; b++)
-      for (int q = 0; q < NPAIR; q++) cs.w[warp].cls[b][q][NSLOTS] = Slot{0ull, 0ull};
+    for (int q = 0; q < NPAIR; q++) cs.w[warp].cls[q][NSLOTS] = Slot{0ull, 0ull};
     cs.w[warp].mk[NSLOTS] = 0ull;
   }
   cgx_syncthreads();
+  const unsigned nch = (unsigned)a.nchunks;
+  const unsigned ngangs = (nch + FW_WARPS - 1u) / FW_WARPS;
   if (warp == FW_WARPS) {
-    if (P_MODE == M_FINDALL) resolver_warp(a, cs, lane);
+    if (P_MODE == M_FINDALL) resolver_warp(a, cs, lane, ngangs);
     return;
   }
   WarpSmem& ws = cs.w[warp];
-  const unsigned nch = (unsigned)a.nchunks;
   const unsigned nwarps_total = gridDim.x * FW_WARPS;
+  // FindAll: tickets are gangs (drawn by the resolver), warp w scans chunk gang * FW_WARPS + w — a
+  // chunk past the end is empty; the other modes need no order: every warp draws chunks on its own
+  const bool gangs = P_MODE == M_FINDALL;
+  const unsigned nunits = gangs ? ngangs : nch;
   // a 1 the compiler cannot fold (a launch has at least one chunk): multiplier of mad_fma
   const uint32_t one = (uint32_t)(a.nchunks > 0);
 
   // tickets: every scanning warp draws until it gets one past the last chunk; the warp that draws
   // the very last ticket of the launch puts the counter back to zero
+  unsigned seq = 0;  // FindAll: the next ticket is the CTA's seq-th gang
   auto take_ticket = [&]() -> unsigned {
     unsigned t = 0;
+    if (gangs) {
+      if (lane == 0) {
+        unsigned long long v;
+        for (;;) {
+          v = cs.tk[seq & 3u];
+          if ((unsigned)(v >> 32) == seq + 1u) break;
+          cgx_backoff();
+        }
+        t = (unsigned)v;
+      }
+      seq++;
+      return __shfl_sync(FULL, t, 0);
+    }
     if (lane == 0) {
       if (P_MODE == M_ISMATCH && *((volatile unsigned long long*)&a.total[1])) {
         t = 0xFFFFFFFFu;
@@ -695,8 +831,11 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
   // The prefetcher runs NB tiles ahead of the classifier, across chunk borders: pf_src walks through
   // the chunk being prefetched (lane 0's copy is the one used), pf_left counts its tiles still to
   // be requested, pf_whole says that all of its windows lie inside the input (no bounds to look at).
-  int ib = 0, rb = 0;       // ring buffer the next request goes to / the next tile is read from
-  uint32_t rpar = 0u;       // parity of the phase the reader waits for on mbar[rb]
+  // (a chunk is a whole number of trips around the ring, so tile t of every chunk lives in buffer
+  // t % NB — the buffer index is a compile-time constant in the unrolled tile loop — and a request
+  // always goes to the buffer whose tile has just been classified)
+  static_assert(TPC % NB == 0, "a chunk is a whole number of trips around the window ring");
+  uint32_t rpar = 0u;       // parity of the phase the reader waits for
   const uint8_t* pf_src = a.h;
   int pf_left = 0;
   bool pf_whole = false;
@@ -706,9 +845,8 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     pf_left = TPC;
     pf_whole = cbeg + WINDOW <= a.n;
   };
-  auto issue_next = [&]() {
+  auto issue_next = [&](const int b) {
     if (lane == 0) {
-      const int b = ib;
       if (pf_whole) {  // the common case: a whole tile
         mbar_expect_tx(&ws.mbar[b], (uint32_t)TILE);
         tma_load_1d(ws.win[b], pf_src, (uint32_t)TILE, &ws.mbar[b]);
@@ -727,9 +865,19 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     }
     pf_src += TILE;
     pf_left--;
-    ib = ib + 1 == NB ? 0 : ib + 1;
   };
-  // Stores the matches of the chunk parked in buffer b (if any) once the resolver has supplied its
+  // the last chunk's owner reports the totals
+  auto report_total = [&](int64_t chunk, unsigned long long total) {
+    if (lane == 0 && chunk == (int64_t)nch - 1) {
+      a.total[0] = total;
+      a.total[1] = total ? 1ull : 0ull;
+      if (a.result) {
+        a.result[0] = total;
+        a.result[1] = total ? 1ull : 0ull;
+      }
+    }
+  };
+  // Stores the matches staged in buffer b (if any) once the resolver has supplied the chunk's
   // offset; returns whether the buffer is free afterwards.  Blocking, or one look.
   auto flush = [&](int b, bool block) -> bool {
     Mail& m = cs.mail[warp][b];
@@ -745,66 +893,104 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     cgx_fence_block();
     const int64_t chunk = m.chunk;
     const unsigned long long excl = m.excl;
-    if (lane == 0 && chunk == (int64_t)nch - 1) {
-      a.total[0] = excl + m.cnt;
-      a.total[1] = (excl + m.cnt) ? 1ull : 0ull;
-      if (a.result) {
-        a.result[0] = excl + m.cnt;
-        a.result[1] = (excl + m.cnt) ? 1ull : 0ull;
-      }
-    }
-    extract(a, ws, b, chunk, excl, m.cnt, lane);
+    report_total(chunk, excl + m.cnt);
+    write_out(a, ws, b, chunk, ws.bits_cnt[b], excl, lane);
+    // matches of a replayed segment that end beyond the bitmap: found again, stored after the others
+    if (lane == 0 && ws.far_cnt[b])
+      replay_cold(a, chunk * (int64_t)CHUNKB, nullptr, ws.far_from[b], ws.far_stop[b], a.out, excl + ws.bits_cnt[b], nullptr);
     __syncwarp();
     if (lane == 0) m.state = 0;
     __syncwarp();
     return true;
   };
-
-  unsigned cur = take_ticket();
+  // ticket -> chunk number (>= nch: nothing to scan — no ticket, or the empty end of the last gang)
+  auto chunk_of = [&](unsigned t) -> unsigned {
+    if (!gangs) return t;
+    return t < nunits ? t * (unsigned)FW_WARPS + (unsigned)warp : 0xFFFFFFFEu;
+  };
+  unsigned tcur = take_ticket();
+  unsigned cur = chunk_of(tcur);
   unsigned nxt = 0xFFFFFFFEu;  // none
   static_assert(NB <= TPC, "the ring never holds more than one chunk");
   if (cur < nch) {
     prefetch_chunk(cur);
 #pragma unroll
-    for (int t = 0; t < NB; t++) issue_next();
+    for (int t = 0; t < NB; t++) issue_next(t);
   }
+  const LaneRot lrot = lane_rot(lane);
   int sb = 0;
-  while (cur < nch) {
+  // FindAll: the warp's count joins its gang's; the last arrival publishes the gang's count
+  auto post_count = [&](unsigned gang, unsigned cnt) {
+    if (lane == 0) {
+      const unsigned long long old = atomicAdd(&cs.gang_acc[sb], (1ull << 40) | cnt);
+      if ((unsigned)(old >> 40) == (unsigned)FW_WARPS - 1u) {
+        cs.gang_acc[sb] = 0ull;
+        publish_count(a, (int64_t)gang, (unsigned)(old & ((1ull << 40) - 1ull)) + cnt, (int64_t)ngangs);
+      }
+    }
+  };
+  while (tcur < nunits) {
+    const unsigned tnxt = take_ticket();
+    nxt = chunk_of(tnxt);
+    if (cur >= nch) {
+      // (FindAll) the empty end of the last gang: the warp still takes part in the gang's hand-over
+      post_count(tcur, 0u);
+      flush(sb, true);
+      if (lane == 0) {
+        ws.far_cnt[sb] = 0u;
+        ws.bits_cnt[sb] = 0u;
+        Mail& m = cs.mail[warp][sb];
+        m.chunk = cur;
+        m.cnt = 0u;
+        cgx_fence_block();
+        m.state = 1;
+      }
+      __syncwarp();
+      sb ^= 1;
+      tcur = tnxt;
+      cur = nxt;
+      continue;
+    }
     const int64_t cb = cur * (int64_t)CHUNKB;
-    // the buffer this chunk's bitmaps go to must have been emptied (its chunk is two tickets old)
-    if (P_MODE == M_FINDALL) flush(sb, true);
-    Slot(*cls)[NSLOTS1] = ws.cls[sb];
+    // the next chunk is known one chunk ahead: its bytes are asked into L2 now (no shared memory
+    // needed for that distance), the window ring then only has to cover the L2 latency
+    if (nxt < nch && lane == 0) {
+      const int64_t nb = nxt * (int64_t)CHUNKB;
+      const int64_t left = a.n - nb;
+      const uint32_t bytes = left >= WINDOW ? (uint32_t)WINDOW : (uint32_t)(left & ~(int64_t)15);
+      if (bytes) tma_prefetch_l2(a.h + nb, bytes);
+    }
+    if (P_MODE == M_FINDALL) flush(sb ^ 1, false);  // the older staged chunk, if its offset has arrived
+    Slot(*cls)[NSLOTS1] = ws.cls;
 
     // ================= phase A: classify the chunk's tiles into class bitmaps ====================
     const bool whole = cb + WINDOW <= a.n;
     // word t * 32 + lane lives in slot (t * 32 + lane) + (t * 32 + lane) / K: 32 + 32 / K slots further per tile
     Slot* dst = &cls[0][lane + lane / K];
 #pragma unroll 1
-    for (int t = 0; t < TPC; t++) {
-      mbar_wait(&ws.mbar[rb], rpar);
-      uint64_t cm[4];
-      classify_piece(f, ws.win[rb] + lane * 64, one, cm);
-      if (++rb == NB) {
-        rb = 0;
-        rpar ^= 1u;
-      }
-      // every lane holds its piece in registers: the buffer can take the tile NB ahead
-      __syncwarp();
-      if (pf_left == 0 && t + NB == TPC) {  // the ring moves on to the next chunk
-        nxt = take_ticket();
-        if (nxt < nch) prefetch_chunk(nxt);
-      }
-      if (pf_left) issue_next();
-      if (!whole) {
-        // bytes at or beyond the end of input belong to no class.  Reversed bit r <=> byte 63 - r
-        const int64_t v = a.n - (cb + (int64_t)t * TILE + lane * 64);  // valid bytes of this piece
-        const uint64_t m = v >= 64 ? ~0ull : (v <= 0 ? 0ull : (~0ull << (64 - v)));
+    for (int t0 = 0; t0 < TPC; t0 += NB) {
 #pragma unroll
-        for (int c = 0; c < 4; c++) cm[c] &= m;
+      for (int b = 0; b < NB; b++) {
+        const int t = t0 + b;
+        mbar_wait(&ws.mbar[b], rpar);
+        uint64_t cm[4];
+        classify_piece(f, ws.win[b], lrot, one, cm);
+        // every lane holds its piece in registers: the buffer can take the tile NB ahead
+        __syncwarp();
+        if (pf_left == 0 && t + NB == TPC && nxt < nch) prefetch_chunk(nxt);  // the ring moves on to the next chunk
+        if (pf_left) issue_next(b);
+        if (!whole) {
+          // bytes at or beyond the end of input belong to no class.  Reversed bit r <=> byte 63 - r
+          const int64_t v = a.n - (cb + (int64_t)t * TILE + lane * 64);  // valid bytes of this piece
+          const uint64_t m = v >= 64 ? ~0ull : (v <= 0 ? 0ull : (~0ull << (64 - v)));
+#pragma unroll
+          for (int c = 0; c < 4; c++) cm[c] &= m;
+        }
+        dst[0] = Slot{cm[0], cm[1]};
+        if (NPAIR > 1) dst[NSLOTS1] = Slot{cm[2], cm[3]};
+        dst += 32 + 32 / K;
       }
-      dst[0] = Slot{cm[0], cm[1]};
-      if (NPAIR > 1) dst[NSLOTS1] = Slot{cm[2], cm[3]};
-      dst += 32 + 32 / K;
+      rpar ^= 1u;
     }
     __syncwarp();
 
@@ -953,10 +1139,6 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       if (replay) {
         unsigned nb = 0;
         far = replay_cold(a, cb, cls[0], rp_from, rp_stop, nullptr, 0ull, &nb);
-        if (far) {
-          ws.far_from[sb] = rp_from;
-          ws.far_stop[sb] = rp_stop;
-        }
       }
       __syncwarp();
       // bits may have landed in other lanes' words: count again
@@ -980,12 +1162,23 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     const unsigned nfar = __reduce_add_sync(FULL, far);
     const unsigned cnt = nbits + nfar;
     if (P_MODE == M_FINDALL) {
-      ws.rank[sb][lane] = x - mine;
+      const uint32_t rk = x - mine;      // starts before this lane's words | ends before them << 16
+      post_count(tcur, cnt);             // everybody behind the gang can go on once it is complete
+      flush(sb, true);                   // (the staging buffer's previous chunk is two tickets old)
       if (lane == 0) {
         ws.far_cnt[sb] = nfar;
         ws.bits_cnt[sb] = nbits;
       }
-      publish_count(a, cur, cnt, lane);  // everybody behind us can go on
+      if (far) {  // (one lane at most: the owner of the chunk's last segment)
+        ws.far_from[sb] = rp_from;
+        ws.far_stop[sb] = rp_stop;
+      }
+      const bool staged = nbits <= (unsigned)CAP;
+      if (staged) {
+        extract_staged(ws, sb, rk, nbits, lane);
+      } else if (lane == 0) {
+        ws.bits_cnt[sb] = 0u;  // nothing staged: the bitmaps are turned into pairs below
+      }
       __syncwarp();
       if (lane == 0) {
         Mail& m = cs.mail[warp][sb];
@@ -994,22 +1187,38 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         cgx_fence_block();
         m.state = 1;
       }
+      if (!staged) {
+        // more matches than the staging buffer holds (dense patterns: `\d+`, `\w+`): wait for the
+        // offset here and store straight from the bitmaps
+        Mail& m = cs.mail[warp][sb];
+        for (;;) {
+          int st = 0;
+          if (lane == 0) st = m.state;
+          st = __shfl_sync(FULL, st, 0);
+          if (st == 2) break;
+          cgx_backoff();
+        }
+        cgx_fence_block();
+        const unsigned long long excl = m.excl;
+        report_total(cur, excl + cnt);
+        extract_direct(a, ws, cur, excl, cnt, rk, lane);
+        if (lane == 0 && nfar)
+          replay_cold(a, cb, nullptr, ws.far_from[sb], ws.far_stop[sb], a.out, excl + nbits, nullptr);
+        __syncwarp();
+        if (lane == 0) m.state = 0;
+        __syncwarp();
+      }
       sb ^= 1;
     } else if (cnt && lane == 0) {
       atomicAdd(a.total, (unsigned long long)cnt);
       a.total[1] = 1ull;
     }
+    tcur = tnxt;
     cur = nxt;
-    nxt = 0xFFFFFFFEu;
   }
   if (P_MODE == M_FINDALL) {
     flush(sb, true);
     flush(sb ^ 1, true);
-  }
-  __syncwarp();
-  if (lane == 0) {
-    cgx_fence_block();
-    cs.done[warp] = 1;
   }
 }
 #ifndef CGX_JIT

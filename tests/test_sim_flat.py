@@ -40,7 +40,7 @@ def scan(pat, hay, mode=0, cap=None, grid=2, base=0):
         # every emulated scan runs twice on the same scratch (stale look-back words of the first launch)
         k4 = BACKEND == "simjit_k4"
         return sim_lib.scan(pat, hay, mode=mode, cap=cap, grid=grid, base=base, jit=BACKEND != "sim",
-                            defs="-DCGX_K=4 -DCGX_NB=3" if k4 else "", tag="k4" if k4 else "", launches=2)
+                            defs="-DCGX_K=4 -DCGX_NB=4" if k4 else "", tag="k4" if k4 else "", launches=2)
     import torch
     from gpu_util import scan_device
     r = cg.Compile(pat)

@@ -91,6 +91,10 @@ if __name__ == "__main__":
     sizes = [float(x) for x in sys.argv[1:]] or [1.0, 16.0]
     for g in sizes:
         run(r"\d+\.\d+\.\d+\.\d+", cg.SYNTH_LOG, 0xC0FFEE, int(g * GIB))
-    run(r"\w+@\w+\.\w+", cg.SYNTH_EMAIL, 0xC0FFEE + 4, 80 * 10_000_000, window=80 * 4000)
-    run(r"[a-z]+/\d+", cg.SYNTH_LOG, 0xC0FFEE, 1 * GIB)
-    run(r"\d+", cg.SYNTH_LOG, 0xC0FFEE, 1 * GIB, cap_div=4)
+    npat = int(os.environ.get("AB_PATS", "4"))  # quick experiments: fewer patterns
+    if npat > 1:
+        run(r"\w+@\w+\.\w+", cg.SYNTH_EMAIL, 0xC0FFEE + 4, 80 * 10_000_000, window=80 * 4000)
+    if npat > 2:
+        run(r"[a-z]+/\d+", cg.SYNTH_LOG, 0xC0FFEE, 1 * GIB)
+    if npat > 3:
+        run(r"\d+", cg.SYNTH_LOG, 0xC0FFEE, 1 * GIB, cap_div=4)

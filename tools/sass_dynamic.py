@@ -78,7 +78,23 @@ rows = list(csv.reader(open(csvp)))
 hdr = rows[1]
 ci = {h: i for i, h in enumerate(hdr)}
 data = rows[2:]
-assert abs(len(data) - len(insts)) <= 1, (len(data), len(insts))
+if abs(len(data) - len(insts)) > 1:
+    # the cubin rebuilt here is not instruction-for-instruction the profiled one (another NVRTC
+    # build of nearly the same source): align the two opcode sequences and carry the line table over
+    import difflib
+    ops_prof = [re.match(r"\s*(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", r[ci["Source"]]).group(1) for r in data]
+    sm = difflib.SequenceMatcher(None, ops_prof, [i[0] for i in insts], autojunk=False)
+    mapped, last = [], insts[0]
+    j_of = {}
+    for a0, b0, sz in sm.get_matching_blocks():
+        for k in range(sz):
+            j_of[a0 + k] = b0 + k
+    for i, op in enumerate(ops_prof):
+        if i in j_of:
+            last = insts[j_of[i]]
+        mapped.append((op, last[1], last[2]))
+    sys.stderr.write("aligned %d profiled instructions with %d rebuilt ones (%d matched)\n" % (len(data), len(insts), len(j_of)))
+    insts = mapped
 
 
 def pipe(op):

@@ -36,7 +36,7 @@ marks = [("prologue", "CGX_DYN_SMEM(smem_raw)"),
          ("sweep 1 (right to left)", "phase B: lane-serial marker sweeps"),
          ("sweep 2 (left to right)", "sweep 2, left to right"),
          ("replay clear + hand-over + counts", "bad |= in != 0u;"),
-         ("publish / mail", "if (P_MODE == M_FINDALL) {\n      ws.rank"),
+         ("publish / mail", "if (P_MODE == M_FINDALL) {\n      const uint32_t rk"),
          ("epilogue", "if (P_MODE == M_FINDALL) {\n    flush(sb, true);")]
 kstart = find("CGX_DYN_SMEM(smem_raw)")
 bounds = []
@@ -49,7 +49,6 @@ for name, m in marks:
         ln = find(m, kstart - 1)
     bounds.append((ln, name))
 bounds.sort()
-fn_regions = [("extract()", find("__device__ __forceinline__ void extract("), find("}  // namespace\n") if False else None)]
 
 
 def region_of(line):
