@@ -28,6 +28,9 @@ cudaError_t launch_pike_search(const uint8_t* h, int64_t n, int64_t base, int64_
                                const uint32_t* sets, int ninst, int nthreads, int start_pc, int delim, int mode,
                                int64_t* out, int64_t cap, void* scratch, unsigned long long* total, cudaStream_t st,
                                int* launches);
+cudaError_t launch_flat_captures(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
+                                 const unsigned long long* d_total, unsigned long long cap, const FlatDev& f,
+                                 const uint8_t* at, int nslots, int64_t* out, cudaStream_t stream);
 cudaError_t launch_pike_captures(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
                                  const unsigned long long* d_total, unsigned long long cap,
                                  const uint32_t* code, const uint32_t* sets, int start_pc, int nslots,
@@ -361,6 +364,16 @@ int cgx_debug_jit_state(cgx_regex* re) {
   if (re->jit_state < 0) g_last_error = re->jit_error;
   return re->jit_state;
 }
+// which kernel FindAllSubmatchIndex runs after the scan: 0 = none (no groups), 1 = item-boundary
+// walk of a flat deterministic pattern (flat_caps.cu), 2 = Pike captures kernel, -1 = unsupported.
+// No device needed.
+int cgx_debug_captures_engine(cgx_regex* re) {
+  const Compiled& c = *re->c;
+  const int nslots = 2 * c.prog.num_captures;
+  if (nslots == 2) return 0;
+  if (c.kind == ENG_DFA && c.flat.bs_ok && c.flat_caps.ok && c.flat_caps.nslots == nslots) return 1;
+  return c.has_pike ? 2 : -1;
+}
 // NVRTC only (no device needed): size of the specialised cubin, or -1 with cgx_last_error set
 long cgx_debug_jit_compile(cgx_regex* re, char* cubin_out, size_t cap) {
   if (!re->c->flat.bs_ok) {
@@ -616,6 +629,19 @@ static int submatch_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_
   const int nslots = 2 * c.prog.num_captures;
   if (nslots == 2)  // no groups: the pairs ARE the result (reference meta/findall.go:109-112)
     return scan_locked(re, d_h, len, base, CGX_MODE_FINDALL, d_out, cap, d_result, st);
+  // flat deterministic pattern whose groups enclose whole items: the group offsets are item
+  // boundaries of the forced greedy walk (flat_caps.cu) — no NFA simulation.  Leftmost-longest
+  // changes nothing for a deterministic pattern (one match per start).
+  if (c.kind == ENG_DFA && c.flat.bs_ok && c.flat_caps.ok && c.flat_caps.nslots == nslots) {
+    int r;
+    if ((r = re->d_pairs.ensure((cap ? cap : 1) * 16))) return r;
+    if ((r = scan_locked(re, d_h, len, base, CGX_MODE_FINDALL, (int64_t*)re->d_pairs.p, cap, d_result, st))) return r;
+    CU(launch_flat_captures(d_h, (int64_t)len, base, (const int64_t*)re->d_pairs.p,
+                            (const unsigned long long*)re->d_ticket_total.p, cap, c.flat, c.flat_caps.at, nslots, d_out,
+                            st));
+    re->launches++;
+    return CGX_OK;
+  }
   if (!c.has_pike) {
     g_last_error = "unsupported: captures kernel limit: " + c.pike_err;
     return CGX_ERR_UNSUPPORTED;

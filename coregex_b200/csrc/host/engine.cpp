@@ -86,6 +86,9 @@ struct FlatBuilder {
   FlatDev f;
   uint8_t lazy[24] = {};  // item carries the non-greedy flag (matters only to the bitstream engine)
   bool ok = true;
+  // capture groups as item boundaries: slot 2g = items before group g opens, slot 2g+1 = items
+  // before it closes.  A group under a quantifier (`(\d)+`, `(a)?`) has no fixed boundary.
+  FlatCaps caps;
   int classOf(const ByteSet& s) {
     uint8_t lo[4], hi[4];
     int n;
@@ -112,7 +115,7 @@ struct FlatBuilder {
     f.op_class[f.nops] = (uint8_t)c;
     f.nops++;
   }
-  static bool classSet(const Regexp* re, ByteSet& s) {
+  static bool classSet(const Regexp* re, ByteSet& s, bool* quantified_cap = nullptr) {
     s = ByteSet{};
     if (re->op == OpCharClass) {
       if (re->rune.empty()) return false;
@@ -129,7 +132,10 @@ struct FlatBuilder {
       if ((re->flags & FoldCase) && letter) set_add(s, r ^ 0x20, r ^ 0x20);
       return true;
     }
-    if (re->op == OpCapture && re->sub.size() == 1) return classSet(re->sub[0], s);
+    if (re->op == OpCapture && re->sub.size() == 1) {
+      if (quantified_cap) *quantified_cap = true;
+      return classSet(re->sub[0], s, quantified_cap);
+    }
     return false;
   }
   void walk(const Regexp* re) {
@@ -140,7 +146,17 @@ struct FlatBuilder {
         for (auto* x : re->sub) walk(x);
         return;
       case OpCapture:
-        if (re->sub.size() == 1) return walk(re->sub[0]);
+        if (re->sub.size() == 1) {
+          const int g = re->cap;
+          if (g <= 0 || 2 * g + 1 >= (int)sizeof caps.at) caps.ok = false;
+          else caps.at[2 * g] = (uint8_t)f.nops;
+          walk(re->sub[0]);
+          if (caps.ok && g > 0) {
+            caps.at[2 * g + 1] = (uint8_t)f.nops;
+            if (2 * g + 2 > caps.nslots) caps.nslots = 2 * g + 2;
+          }
+          return;
+        }
         ok = false;
         return;
       case OpLiteral:
@@ -158,11 +174,11 @@ struct FlatBuilder {
         push(0, s);
         return;
       case OpPlus: case OpStar: case OpQuest:
-        if (re->sub.size() != 1 || !classSet(re->sub[0], s)) { ok = false; return; }
+        if (re->sub.size() != 1 || !classSet(re->sub[0], s, &caps.quantified)) { ok = false; return; }
         push(re->op == OpPlus ? 1 : re->op == OpStar ? 2 : 3, s, (re->flags & NonGreedy) != 0);
         return;
       case OpRepeat: {
-        if (re->sub.size() != 1 || !classSet(re->sub[0], s)) { ok = false; return; }
+        if (re->sub.size() != 1 || !classSet(re->sub[0], s, &caps.quantified)) { ok = false; return; }
         int mx = re->max == -1 ? re->min : re->max;
         if (mx > 8) { ok = false; return; }
         const bool ng = (re->flags & NonGreedy) != 0;
@@ -178,12 +194,14 @@ struct FlatBuilder {
 };
 }  // namespace
 
-static void BuildFlat(const Regexp* re, FlatDev& out, uint8_t (&lazy)[24]) {
+static void BuildFlat(const Regexp* re, FlatDev& out, uint8_t (&lazy)[24], FlatCaps& caps) {
   FlatBuilder b;
   memset(&b.f, 0, sizeof b.f);
   b.walk(re);
   memset(&out, 0, sizeof out);
   memcpy(lazy, b.lazy, sizeof lazy);
+  caps = b.caps;
+  if (!b.ok || b.caps.quantified) caps.ok = false;
   // worth it only when the pattern is longer than its first item (otherwise the first-level
   // filter already is the whole pattern) — except a lone `C+` (the reference's CharClassSearcher
   // patterns, nfa/charclass_searcher.go), where "flat" unlocks the run-start filter: one
@@ -406,7 +424,9 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
     c->engine_name = c->has_delim ? "pikevm" : "pikevm-serial";
     return true;
   };
-  if ((c->kind == ENG_DFA || c->kind == ENG_TEDDY) && (!de.empty() || nullable_pat)) {
+  // (the multi-literal engine needs no DFA — 64 literals do not fit 160 states — and a set of
+  // literals of three bytes and more never matches the empty string)
+  if (c->kind == ENG_DFA && (!de.empty() || nullable_pat)) {
     if (!to_pikevm(de.empty() ? std::string("pattern can match the empty string") : de)) return COMPILE_UNSUPPORTED;
   }
   if (c->kind == ENG_DFA) {
@@ -432,7 +452,7 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
       if (c->dfa.start[k] != c->dfa.start[0]) c->kind_lut_needed = true;
     memset(c->lut, 0, sizeof c->lut);
     uint8_t flat_lazy[24];
-    BuildFlat(pr.re, c->flat, flat_lazy);
+    BuildFlat(pr.re, c->flat, flat_lazy, c->flat_caps);
     auto flat_first = [&]() {
       FlatDev& f = c->flat;
       f.first_is_filter = f.nops && f.cls_nranges[0] == c->nranges;

@@ -21,6 +21,16 @@ enum EngineKind : int {
   ENG_LINE,        // one lane per record: unanchored forward DFA + reverse DFA (scan_dfa.cu)
 };
 
+// Capture groups of a flat pattern as item boundaries (flat_caps.cu): group g opens before item
+// at[2g] and closes before item at[2g+1] of FlatDev::fwd_ops.  ok == false: some group sits under a
+// quantifier (its offsets are those of the last iteration: the Pike captures kernel's business).
+struct FlatCaps {
+  bool ok = true;
+  bool quantified = false;
+  int nslots = 2;
+  uint8_t at[34] = {};
+};
+
 struct Compiled {
   std::string pattern;
   gosyntax::Arena arena;
@@ -39,6 +49,7 @@ struct Compiled {
   bool skip_safe = false;
   bool kind_lut_needed = false;
   FlatDev flat;  // nops == 0 when the pattern is not flat
+  FlatCaps flat_caps;
   uint8_t delim = '\n';
   bool has_delim = true;  // false: matches may contain every byte value (PikeVM engine, one record)
 

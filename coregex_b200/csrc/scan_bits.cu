@@ -421,11 +421,12 @@ __device__ __forceinline__ uint64_t fwd_word(const FlatDev& f, const uint64_t (&
 // the word is consistent iff D = E - S - in, the span mask, has its edges exactly at S ^ E:
 // D ^ (D << 1 | in) == S ^ E (tests/test_sim_flat.py checks the criterion exhaustively on short
 // words).  The span mask's top bit says whether a match is still open after the word.
-__device__ __forceinline__ bool word_misordered(uint64_t S, uint64_t E, uint32_t& in) {
+// Returns the word's discrepancy bits (0 = consistent): a sweep ORs them together and looks once.
+__device__ __forceinline__ uint64_t word_misordered(uint64_t S, uint64_t E, uint32_t& in) {
   const uint64_t D = E - S - in;
-  const bool bad = (D ^ ((D << 1) | in)) != (S ^ E);
+  const uint64_t x = (D ^ ((D << 1) | in)) ^ (S ^ E);
   in = (uint32_t)(D >> 63);
-  return bad;
+  return x;
 }
 
 // ---- serial replay (cold) -------------------------------------------------------------------------
@@ -697,12 +698,12 @@ __device__ __forceinline__ void extract_words(const ScanArgs& a, const Slot* res
     emit_half<CHECK>(hi32(v.b), pb + 32, oe, end);
   }
 }
-// rk: starts before this lane's words | ends before them << 16
+// rk / rke: starts / ends before this lane's words
 __device__ __forceinline__ void extract_direct(const ScanArgs& a, const WarpSmem& ws, int64_t chunk,
-                                               unsigned long long excl, unsigned cnt, uint32_t rk, int lane) {
+                                               unsigned long long excl, unsigned cnt, uint32_t rk, uint32_t rke, int lane) {
   const Slot* res = ws.cls[0] + lane * (K + 1);
-  int64_t* os = a.out + 2 * (excl + (rk & 0xFFFFu));
-  int64_t* oe = a.out + 2 * (excl + (rk >> 16)) + 1;
+  int64_t* os = a.out + 2 * (excl + rk);
+  int64_t* oe = a.out + 2 * (excl + rke) + 1;
   const int64_t wb = chunk * (int64_t)CHUNKB + a.base + (int64_t)lane * (K * 64);
   if ((int64_t)(excl + cnt) <= a.cap) extract_words<false>(a, res, wb, os, oe);  // the usual case: everything fits
   else extract_words<true>(a, res, wb, os, oe);
@@ -713,7 +714,7 @@ __device__ __forceinline__ void extract_direct(const ScanArgs& a, const WarpSmem
 // the work evenly over the warp however the matches are distributed over the lanes' words.
 __device__ __forceinline__ void extract_staged(WarpSmem& ws, int sb, uint32_t rk, unsigned n, int lane) {
   const Slot* res = ws.cls[0] + lane * (K + 1);
-  uint16_t* os = ws.stS[sb] + (rk & 0xFFFFu);
+  uint16_t* os = ws.stS[sb] + rk;
   const int wb = lane * (K * 64);
 #pragma unroll 1
   for (int j = 0; j < K; j++) {
@@ -1037,8 +1038,9 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     pass_reset(st);
     uint32_t seen = (cur == 0u && lane == 0) ? FULL : 0u;  // the start of the haystack counts as a sync byte before it
     uint32_t in = 0u, c0hi = 0u;
-    bool bad = false, open = false;
-    unsigned cS = 0u, cE = 0u;
+    bool open = false;
+    uint64_t badbits = 0ull;
+    unsigned cS = 0u;
     static_assert(K >= 3, "the overlap word's result is parked in mk[1..2] of the lane's region");
 #pragma unroll UNROLL
     for (int j = 0; j <= K; j++) {
@@ -1076,19 +1078,18 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       if (P_RUNSTART) M &= c[0] & ~c0prev;
       const uint64_t S = M & own;
       const uint64_t E = fwd_word(f, c, S, st) & own;
-      bad |= word_misordered(S, E, in);
+      badbits |= word_misordered(S, E, in);
       // (an end in the middle of a class-0 run: the reference resumes there, which is no run start)
-      if (P_MIDRUN) bad |= (E & c[0] & c0prev) != 0ull;
+      if (P_MIDRUN) badbits |= E & c[0] & c0prev;
       if (j == K) {
         ws.mk[s0 + 1] = S;
         ws.mk[s0 + 2] = E;
       } else {
         cls[0][s0 + (j == 0 ? K : j)] = Slot{S, E};
         cS += __popcll(S);
-        cE += __popcll(E);
       }
     }
-    bad |= in != 0u;
+    const bool bad = badbits != 0ull || in != 0u;
     // ---- lanes that need the reference loop: clear what the sweeps left in the affected range ----
     const bool replay = bad || (open && seen);
 #ifdef CGX_DEBUG_PRINT
@@ -1102,7 +1103,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       rp_from = rb + keep + 1;
       rp_stop = bad ? rb + (int64_t)ovl * 64 : rp_from;
       if (rp_stop < rp_from) rp_stop = rp_from;
-      cS = cE = 0u;
+      cS = 0u;
       for (int j = 0; j <= ovl; j++) {
         const int lo = keep + 1 - j * 64;  // first bit of word j to clear
         const uint64_t m = lo <= 0 ? 0ull : (lo >= 64 ? ~0ull : ((1ull << lo) - 1ull));
@@ -1115,7 +1116,6 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
           v.b &= m;
           cls[0][s0 + (j == 0 ? K : j)] = v;
           cS += __popcll(v.a);
-          cE += __popcll(v.b);
         }
       }
     }
@@ -1128,7 +1128,6 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         v.a |= rs;
         v.b |= re;
         cS += __popcll(rs);
-        cE += __popcll(re);
       }
       cls[0][s0] = v;
     }
@@ -1142,15 +1141,11 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       }
       __syncwarp();
       // bits may have landed in other lanes' words: count again
-      cS = cE = 0u;
-      for (int j = 0; j < K; j++) {
-        const Slot v = cls[0][s0 + j];
-        cS += __popcll(v.a);
-        cE += __popcll(v.b);
-      }
+      cS = 0u;
+      for (int j = 0; j < K; j++) cS += __popcll(cls[0][s0 + j].a);
     }
     // ---- counts and ranks ----
-    uint32_t x = cS | (cE << 16);
+    uint32_t x = cS;
     const uint32_t mine = x;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -1158,11 +1153,11 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       if (lane >= d) x += y;
     }
     const uint32_t tot = __shfl_sync(FULL, x, 31);
-    const unsigned nbits = tot & 0xFFFFu;
+    const unsigned nbits = tot;
     const unsigned nfar = __reduce_add_sync(FULL, far);
     const unsigned cnt = nbits + nfar;
     if (P_MODE == M_FINDALL) {
-      const uint32_t rk = x - mine;      // starts before this lane's words | ends before them << 16
+      const uint32_t rk = x - mine;      // starts before this lane's words
       post_count(tcur, cnt);             // everybody behind the gang can go on once it is complete
       flush(sb, true);                   // (the staging buffer's previous chunk is two tickets old)
       if (lane == 0) {
@@ -1201,7 +1196,16 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         cgx_fence_block();
         const unsigned long long excl = m.excl;
         report_total(cur, excl + cnt);
-        extract_direct(a, ws, cur, excl, cnt, rk, lane);
+        // ends before this lane's words (the staged path finds ends per match and needs no rank)
+        uint32_t xe = 0u;
+        for (int j = 0; j < K; j++) xe += __popcll(cls[0][s0 + j].b);
+        const uint32_t mine_e = xe;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t y = __shfl_up_sync(FULL, xe, d);
+          if (lane >= d) xe += y;
+        }
+        extract_direct(a, ws, cur, excl, cnt, rk, xe - mine_e, lane);
         if (lane == 0 && nfar)
           replay_cold(a, cb, nullptr, ws.far_from[sb], ws.far_stop[sb], a.out, excl + nbits, nullptr);
         __syncwarp();

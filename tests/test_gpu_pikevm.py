@@ -56,6 +56,41 @@ def test_random_haystacks(pat):
             assert np.array_equal(np.array(got, dtype=np.int64), want), (pat, h)
 
 
+# flat deterministic patterns: group offsets = item boundaries of the forced greedy walk (flat_caps.cu)
+FLAT_PATS = [r"(\w+)@(\w+)\.(\w+)", r"(\d+)\.(\d+)\.(\d+)\.(\d+)", r"((\w+)@(\w+))\.(\w+)", r"([a-z]+)=(\d{1,3})",
+             r"x(\d{2})(\d*)-", r"(?P<k>[a-z]+)(=)(?P<v>\d+)", r"(\d+)(\.)(\d+)", r"([a-f]+)([0-9]+)(x?)\.",
+             r"(\d+\.\d+)\.(\d+\.(\d+))"]
+# groups under a quantifier keep the Pike captures kernel
+PIKE_PATS = [r"(\d)+\.", r"(a)?b+@", r"([a-z])*=\d+"]
+
+
+def _engine(r):
+    return cg._lib.cgx_debug_captures_engine(r._h)
+
+
+@pytest.mark.parametrize("pat", FLAT_PATS + PIKE_PATS)
+def test_flat_pattern_groups(pat):
+    rng = np.random.default_rng(29)
+    alphabet = np.frombuffer(b"0123456789..== abcdefx\n@_-", dtype=np.uint8)
+    r, o = cg.Compile(pat), Oracle(pat)
+    assert _engine(r) == (1 if pat in FLAT_PATS else 2), (pat, r.engine)
+    specials = [b"user@example.com", b"10.20.30.40", b"key=123 other=4567", b"x12345- x12-", b"abc123x. ff00.", b"1.2.3.4.5.6.7.8"]
+    for it in range(80):
+        n = int(rng.integers(0, 600))
+        h = bytearray(alphabet[rng.integers(0, len(alphabet), n)])
+        for _ in range(int(rng.integers(0, 6))):
+            sp = specials[int(rng.integers(0, len(specials)))]
+            at = int(rng.integers(0, max(1, len(h))))
+            h[at:at] = sp
+        h = bytes(h)
+        want = o.find_all_submatch(h)
+        got = r.FindAllSubmatchIndex(h)
+        if len(want) == 0:
+            assert got is None, (pat, h)
+        else:
+            assert np.array_equal(np.array(got, dtype=np.int64), want), (pat, h)
+
+
 @pytest.mark.parametrize("lines", [1, 100, 4000, 100000])
 def test_c4_email_lines(lines):
     hay = cg.synth_host(cg.SYNTH_EMAIL, 0xC0FFEE + 4, 80 * lines)

@@ -24,7 +24,7 @@ from oracle_lib import Oracle
 GIB = 1 << 30
 
 
-def timed(fn, steps=5, warm=3):
+def timed(fn, steps=int(os.environ.get("AB_STEPS", "5")), warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
