@@ -181,13 +181,24 @@ struct cgx_regex {
     }
     memset(&teddy_dev, 0, sizeof teddy_dev);
     if (c->kind == ENG_TEDDY) {
-      // one allocation: fp[256] u32 | offs[npat+1] i32 | order[npat] u16 | bucket_off[nb+1] u16 | bytes
+      // one allocation: fp[256] u32 | lit8[npat] u64 | mask8[npat] u64 | offs[npat+1] i32 | order[npat] u16 |
+      // bucket_off[nb+1] u16 | bytes
       const TeddyTables& t = c->teddy;
-      size_t o_fp = 0, o_offs = o_fp + 1024, o_order = o_offs + (t.npat + 1) * 4;
+      size_t o_fp = 0, o_lit8 = o_fp + 1024, o_offs = o_lit8 + (size_t)t.npat * 16, o_order = o_offs + (t.npat + 1) * 4;
       size_t o_boff = o_order + ((t.npat * 2 + 3) & ~3), o_bytes = o_boff + (((t.nbuckets + 1) * 2 + 3) & ~3);
       size_t total = o_bytes + t.bytes.size();
       std::vector<uint8_t> blob((total + 3) & ~(size_t)3, 0);
       memcpy(&blob[o_fp], t.fp_packed.data(), 1024);
+      for (int id = 0; id < t.npat; id++) {
+        uint64_t v = 0, m = 0;
+        const int len = t.offs[id + 1] - t.offs[id];
+        for (int k = 0; k < 8 && k < len; k++) {
+          v |= (uint64_t)t.bytes[t.offs[id] + k] << (8 * k);
+          m |= 0xFFull << (8 * k);
+        }
+        memcpy(&blob[o_lit8 + 8 * (size_t)id], &v, 8);
+        memcpy(&blob[o_lit8 + 8 * (size_t)(t.npat + id)], &m, 8);
+      }
       memcpy(&blob[o_offs], t.offs.data(), (t.npat + 1) * 4);
       memcpy(&blob[o_order], t.order_simd.data(), t.npat * 2);
       memcpy(&blob[o_boff], t.bucket_off.data(), (t.nbuckets + 1) * 2);
@@ -197,6 +208,7 @@ struct cgx_regex {
       CU(cudaMemcpy(d_teddy.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
       const uint8_t* b = (const uint8_t*)d_teddy.p;
       teddy_dev.fp = (const uint32_t*)(b + o_fp);
+      teddy_dev.lit8 = (const uint64_t*)(b + o_lit8);
       teddy_dev.offs = (const int32_t*)(b + o_offs);
       teddy_dev.order = (const uint16_t*)(b + o_order);
       teddy_dev.bucket_off = (const uint16_t*)(b + o_boff);

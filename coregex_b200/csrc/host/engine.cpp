@@ -295,6 +295,13 @@ std::string JitHeader(const FlatDev& f) {
   add("#define CGX_JIT_RUNSTART %d\n", f.bs_runstart);
   add("#define CGX_JIT_MIDRUN %d\n", f.bs_midrun_check);
   add("#define CGX_JIT_REV_INIT %d\n", f.rev_init_class);
+  // a match can be one or two bytes long (`\d+`, `\w+`, `[a-z]+=`): chunks hold far more matches than
+  // the staging buffer, the kernel keeps a second set of bitmaps instead (scan_bits.cu CGX_PARK)
+  {
+    int mandatory = 0;
+    for (int i = 0; i < f.fwd_nops; i++) mandatory += (f.fwd_ops[i] & 3) <= 1 ? 1 : 0;
+    add("#define CGX_JIT_PARK %d\n", mandatory <= 2 && f.nclasses <= 2 ? 1 : 0);
+  }
   // Every step of a pass owns one slot I of per-lane state (the carry and the shifted-out bits that
   // travel from one word to the next, scan_bits.cu PassState).  Right to left, a single byte of
   // class A followed by a run of class B (`B+ A` in the pattern) is one fused step over the

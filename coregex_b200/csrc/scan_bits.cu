@@ -49,7 +49,7 @@ namespace {
 
 constexpr uint32_t FULL = 0xffffffffu;
 #ifndef CGX_K
-#define CGX_K 8            // words (64-byte pieces) per lane and chunk == tiles per chunk
+#define CGX_K 4            // words (64-byte pieces) per lane and chunk == tiles per chunk
 #endif
 #ifndef CGX_CTAS
 #define CGX_CTAS 1         // resident CTAs per SM the kernel is built for
@@ -58,7 +58,7 @@ constexpr uint32_t FULL = 0xffffffffu;
 #define CGX_NB 2           // window ring: tiles in flight per warp
 #endif
 #ifndef CGX_UNROLL
-#define CGX_UNROLL 3       // words per trip of the sweep loops (independent steps of neighbouring words overlap)
+#define CGX_UNROLL (CGX_K + 1)  // sweep loops fully unrolled: the per-step carries of a sweep stay in predicate registers
 #endif
 constexpr int K = CGX_K;
 constexpr int FW_CTAS = CGX_CTAS;
@@ -74,9 +74,9 @@ constexpr int NSLOTS = 32 * (K + 1);       // word w lives in slot w + w / K (on
 // byte, no marker: a word that leaves every piece of per-lane state as it is)
 constexpr int NSLOTS1 = NSLOTS + 1;
 #ifndef CGX_CAP
-#define CGX_CAP 320
+#define CGX_CAP 160
 #endif
-constexpr int CAP = CGX_CAP;               // staged matches per chunk (the IP corpus has ~165 per 16 KB)
+constexpr int CAP = CGX_CAP;               // staged matches per chunk (the IP corpus has ~80 per 8 KB)
 static_assert(K == 4 || K == 8 || K == 16, "words per lane: a power of two that divides 32");
 
 // ---- pipe-aware primitives (the kernel is bound by the integer ALU pipe) -------
@@ -132,9 +132,24 @@ constexpr int NC = 4;
 constexpr int NSTATE = 24;
 #endif
 constexpr int NPAIR = (NC + 1) / 2;        // 16-byte slot arrays: classes (0,1) and (2,3)
+// CGX_PARK: patterns whose matches can be a byte or two long (`\d+`, `\w+`: a chunk holds far more
+// matches than the staging buffer) get a second set of slot arrays: a chunk that does not fit the
+// staging buffer leaves its (starts, ends) bitmaps where they are and the next chunk is scanned in
+// the other set, instead of waiting for the gang's offset on the spot.
+#if defined(CGX_JIT) && defined(CGX_JIT_PARK) && !defined(CGX_PARK)
+#define CGX_PARK CGX_JIT_PARK
+#endif
+#ifndef CGX_PARK
+#define CGX_PARK 0
+#endif
+constexpr int NBUF = CGX_PARK ? 2 : 1;
 // scanning warps per CTA: as many as the shared memory of one SM holds (one or two slot arrays per warp)
+// The register file is split over the four schedulers: with the resolver the CTA has 24 warps (6 per
+// scheduler, 80 registers a thread) when one slot array per warp fits the shared memory of an SM 23
+// times, 20 warps (96 registers) with two slot arrays.  Measured on B200 (IP regex, 16 GiB):
+// K=8 x 15 warps 3225 GB/s, K=4 x 19 warps 3203 GB/s, K=4 x 23 warps 3380 GB/s.
 #ifndef CGX_WARPS
-#define CGX_WARPS (NPAIR == 1 ? 14 : 8)
+#define CGX_WARPS (NPAIR == 1 ? (CGX_PARK ? 19 : 23) : (CGX_PARK ? 11 : 19))
 #endif
 constexpr int FW_WARPS = CGX_WARPS;
 constexpr int FW_THREADS = (FW_WARPS + 1) * 32;  // + one resolver warp
@@ -146,7 +161,7 @@ struct alignas(16) Slot {
 struct WarpSmem {
   alignas(128) uint8_t win[NB][TILE];
   // class bitmaps of the chunk being scanned; after sweep 2 array 0 holds (starts, ends) instead
-  Slot cls[NPAIR][NSLOTS1];
+  Slot cls[NBUF][NPAIR][NSLOTS1];
   uint64_t mk[NSLOTS1];       // sweep 1 -> sweep 2: "a match can start here", forward orientation
   // A chunk's matches wait here (chunk-relative u16 offsets, in match order) for the chunk's global
   // offset while the next chunk is scanned: two buffers.  A chunk with more than CAP matches keeps
@@ -699,9 +714,9 @@ __device__ __forceinline__ void extract_words(const ScanArgs& a, const Slot* res
   }
 }
 // rk / rke: starts / ends before this lane's words
-__device__ __forceinline__ void extract_direct(const ScanArgs& a, const WarpSmem& ws, int64_t chunk,
+__device__ __forceinline__ void extract_direct(const ScanArgs& a, const Slot* arr, int64_t chunk,
                                                unsigned long long excl, unsigned cnt, uint32_t rk, uint32_t rke, int lane) {
-  const Slot* res = ws.cls[0] + lane * (K + 1);
+  const Slot* res = arr + lane * (K + 1);
   int64_t* os = a.out + 2 * (excl + rk);
   int64_t* oe = a.out + 2 * (excl + rke) + 1;
   const int64_t wb = chunk * (int64_t)CHUNKB + a.base + (int64_t)lane * (K * 64);
@@ -712,8 +727,8 @@ __device__ __forceinline__ void extract_direct(const ScanArgs& a, const WarpSmem
 // set bits of its own K words (rk = starts before them).  Ends: starts and ends alternate, so the end
 // of the i-th match is the first end bit after the i-th start — one lane per MATCH, which spreads
 // the work evenly over the warp however the matches are distributed over the lanes' words.
-__device__ __forceinline__ void extract_staged(WarpSmem& ws, int sb, uint32_t rk, unsigned n, int lane) {
-  const Slot* res = ws.cls[0] + lane * (K + 1);
+__device__ __forceinline__ void extract_staged(WarpSmem& ws, const Slot* all, int sb, uint32_t rk, unsigned n, int lane) {
+  const Slot* res = all + lane * (K + 1);
   uint16_t* os = ws.stS[sb] + rk;
   const int wb = lane * (K * 64);
 #pragma unroll 1
@@ -724,7 +739,6 @@ __device__ __forceinline__ void extract_staged(WarpSmem& ws, int sb, uint32_t rk
     stage_half(hi32(v), pb + 32, os);
   }
   __syncwarp();
-  const Slot* all = ws.cls[0];
   const uint16_t* ss = ws.stS[sb];
   uint16_t* se = ws.stE[sb];
 #pragma unroll 1
@@ -781,7 +795,8 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
 #pragma unroll
     for (int b = 0; b < NB; b++) mbar_init(&cs.w[warp].mbar[b], 1);
     fence_mbar_init();
-    for (int q = 0; q < NPAIR; q++) cs.w[warp].cls[q][NSLOTS] = Slot{0ull, 0ull};
+    for (int b = 0; b < NBUF; b++)
+      for (int q = 0; q < NPAIR; q++) cs.w[warp].cls[b][q][NSLOTS] = Slot{0ull, 0ull};
     cs.w[warp].mk[NSLOTS] = 0ull;
   }
   cgx_syncthreads();
@@ -792,6 +807,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     return;
   }
   WarpSmem& ws = cs.w[warp];
+  constexpr unsigned PARKED = 0xFFFFFFFFu;  // bits_cnt of a chunk whose bitmaps are parked (CGX_PARK)
   const unsigned nwarps_total = gridDim.x * FW_WARPS;
   // FindAll: tickets are gangs (drawn by the resolver), warp w scans chunk gang * FW_WARPS + w — a
   // chunk past the end is empty; the other modes need no order: every warp draws chunks on its own
@@ -895,10 +911,32 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     const int64_t chunk = m.chunk;
     const unsigned long long excl = m.excl;
     report_total(chunk, excl + m.cnt);
-    write_out(a, ws, b, chunk, ws.bits_cnt[b], excl, lane);
+    unsigned nbits = ws.bits_cnt[b];
+    if (CGX_PARK && nbits == PARKED) {
+      // the chunk did not fit the staging buffer: its bitmaps waited in slot array b
+      nbits = m.cnt - ws.far_cnt[b];
+      const Slot* arr = ws.cls[b][0];
+      uint32_t xs = 0u, xe = 0u;
+      for (int j = 0; j < K; j++) {
+        const Slot v = arr[lane * (K + 1) + j];
+        xs += __popcll(v.a);
+        xe += __popcll(v.b);
+      }
+      uint32_t x = xs | (xe << 16);  // (a chunk holds fewer than 65536 positions)
+      const uint32_t mine = x;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, x, d);
+        if (lane >= d) x += y;
+      }
+      x -= mine;
+      extract_direct(a, arr, chunk, excl, m.cnt, x & 0xFFFFu, x >> 16, lane);
+    } else {
+      write_out(a, ws, b, chunk, nbits, excl, lane);
+    }
     // matches of a replayed segment that end beyond the bitmap: found again, stored after the others
     if (lane == 0 && ws.far_cnt[b])
-      replay_cold(a, chunk * (int64_t)CHUNKB, nullptr, ws.far_from[b], ws.far_stop[b], a.out, excl + ws.bits_cnt[b], nullptr);
+      replay_cold(a, chunk * (int64_t)CHUNKB, nullptr, ws.far_from[b], ws.far_stop[b], a.out, excl + nbits, nullptr);
     __syncwarp();
     if (lane == 0) m.state = 0;
     __syncwarp();
@@ -961,8 +999,12 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       const uint32_t bytes = left >= WINDOW ? (uint32_t)WINDOW : (uint32_t)(left & ~(int64_t)15);
       if (bytes) tma_prefetch_l2(a.h + nb, bytes);
     }
-    if (P_MODE == M_FINDALL) flush(sb ^ 1, false);  // the older staged chunk, if its offset has arrived
-    Slot(*cls)[NSLOTS1] = ws.cls;
+    if (P_MODE == M_FINDALL) {
+      // CGX_PARK: slot array sb may still hold the bitmaps of the chunk before last
+      if (CGX_PARK) flush(sb, true);
+      flush(sb ^ 1, false);  // the older staged chunk, if its offset has arrived
+    }
+    Slot(*cls)[NSLOTS1] = ws.cls[CGX_PARK ? sb : 0];
 
     // ================= phase A: classify the chunk's tiles into class bitmaps ====================
     const bool whole = cb + WINDOW <= a.n;
@@ -1170,9 +1212,11 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       }
       const bool staged = nbits <= (unsigned)CAP;
       if (staged) {
-        extract_staged(ws, sb, rk, nbits, lane);
+        extract_staged(ws, cls[0], sb, rk, nbits, lane);
       } else if (lane == 0) {
-        ws.bits_cnt[sb] = 0u;  // nothing staged: the bitmaps are turned into pairs below
+        // nothing staged: the bitmaps are turned into pairs when the offset is known — below, or
+        // (CGX_PARK) when the slot array is needed again
+        ws.bits_cnt[sb] = CGX_PARK ? PARKED : 0u;
       }
       __syncwarp();
       if (lane == 0) {
@@ -1182,9 +1226,9 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         cgx_fence_block();
         m.state = 1;
       }
-      if (!staged) {
-        // more matches than the staging buffer holds (dense patterns: `\d+`, `\w+`): wait for the
-        // offset here and store straight from the bitmaps
+      if (!staged && !CGX_PARK) {
+        // more matches than the staging buffer holds: wait for the offset here and store straight
+        // from the bitmaps
         Mail& m = cs.mail[warp][sb];
         for (;;) {
           int st = 0;
@@ -1205,7 +1249,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
           const uint32_t y = __shfl_up_sync(FULL, xe, d);
           if (lane >= d) xe += y;
         }
-        extract_direct(a, ws, cur, excl, cnt, rk, xe - mine_e, lane);
+        extract_direct(a, cls[0], cur, excl, cnt, rk, xe - mine_e, lane);
         if (lane == 0 && nfar)
           replay_cold(a, cb, nullptr, ws.far_from[sb], ws.far_stop[sb], a.out, excl + nbits, nullptr);
         __syncwarp();

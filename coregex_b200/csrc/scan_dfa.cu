@@ -83,6 +83,7 @@ struct Ctx {
   int buf;                // staging buffer of this chunk
   // multi-literal engine tables (shared memory copies)
   const uint32_t* t_fp;
+  const uint64_t* t_lit8;  // [npat] first 8 bytes, then [npat] byte masks
   const uint8_t* t_bytes;
   const int32_t* t_offs;
   const uint16_t* t_order;
@@ -174,24 +175,44 @@ __device__ __forceinline__ uint32_t teddy_mask(const Ctx& c, uint32_t b0, uint32
   return (c.t_fp[b0] & 0xFFFFu) & (c.t_fp[b1] >> 16);
 }
 
-__device__ __forceinline__ bool lit_equal(const Ctx& c, int64_t p, int id, int& len) {
+// bytes p .. p+7 of the haystack as a little-endian word (bytes at or beyond n read as anything:
+// every comparison is guarded by p + len <= n)
+__device__ __forceinline__ uint64_t load8(const Ctx& c, int64_t p) {
+  const int64_t i = p - c.gw;
+  if (i >= 0 && i + 12 <= WIN) {
+    // three aligned words of the window, shifted into place
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(c.sm.win + (i & ~(int64_t)3));
+    const uint32_t sh = ((uint32_t)i & 3u) * 8u;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+  }
+  uint64_t v = 0;
+  for (int k = 0; k < 8; k++)
+    if (p + k < c.a.n) v |= (uint64_t)byte_at(c, p + k) << (8 * k);
+  return v;
+}
+
+// does literal `id` stand at p?  hay8 = load8(p): the first eight bytes are one masked comparison
+__device__ __forceinline__ bool lit_equal(const Ctx& c, int64_t p, int id, uint64_t hay8, int& len) {
   const int o = c.t_offs[id];
   len = c.t_offs[id + 1] - o;
   if (p + len > c.a.n) return false;
-  for (int k = 0; k < len; k++)
+  if ((hay8 ^ c.t_lit8[id]) & c.t_lit8[c.a.teddy.npat + id]) return false;
+  for (int k = 8; k < len; k++)
     if (byte_at(c, p + k) != c.t_bytes[o + k]) return false;
   return true;
 }
 
 // SIMD-regime verify at global position p: buckets low -> high, insertion order inside a bucket
 __device__ int64_t teddy_verify(const Ctx& c, int64_t p, uint32_t mask) {
+  const uint64_t hay8 = load8(c, p);
   while (mask) {
     const int b = __ffs(mask) - 1;
     mask &= mask - 1;
     if (b >= c.a.teddy.nbuckets) break;
     for (int k = c.t_boff[b]; k < c.t_boff[b + 1]; k++) {
       int len;
-      if (lit_equal(c, p, c.t_order[k], len)) return p + len;
+      if (lit_equal(c, p, c.t_order[k], hay8, len)) return p + len;
     }
   }
   return -1;
@@ -199,9 +220,10 @@ __device__ int64_t teddy_verify(const Ctx& c, int64_t p, uint32_t mask) {
 // scalar-regime verify (haystack[start:] shorter than 16 bytes): plain literal-id order
 // (reference prefilter/teddy.go:447-458 findMatchScalar)
 __device__ int64_t teddy_verify_scalar(const Ctx& c, int64_t p) {
+  const uint64_t hay8 = load8(c, p);
   for (int id = 0; id < c.a.teddy.npat; id++) {
     int len;
-    if (lit_equal(c, p, id, len)) return p + len;
+    if (lit_equal(c, p, id, hay8, len)) return p + len;
   }
   return -1;
 }
@@ -1049,6 +1071,7 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
 
     Ctx c{a, sm, s_trans, s_eoi, s_lut, cbeg, gw, (int)(hi_g - gw), lane, warp, buf,
           reinterpret_cast<const uint32_t*>(t_blob),
+          reinterpret_cast<const uint64_t*>(t_blob + ((const unsigned char*)a.teddy.lit8 - g_blob)),
           t_blob + (a.teddy.bytes - g_blob),
           reinterpret_cast<const int32_t*>(t_blob + ((const unsigned char*)a.teddy.offs - g_blob)),
           reinterpret_cast<const uint16_t*>(t_blob + ((const unsigned char*)a.teddy.order - g_blob)),

@@ -79,6 +79,9 @@ struct FlatDev {
 // Multi-literal engine tables (reference prefilter/teddy.go, teddy_fat.go), device resident.
 struct TeddyDev {
   const uint32_t* fp;        // 256 entries: fp0[b] | fp1[b] << 16  (bucket masks per byte value)
+  // per literal id: its first 8 bytes as a little-endian word (zero padded), then npat byte masks
+  // (0xFF for the bytes that exist): a candidate is compared 8 bytes at a time
+  const uint64_t* lit8;
   const uint8_t* bytes;      // concatenated literals
   const int32_t* offs;       // npat + 1
   const uint16_t* order;     // literal ids, bucket-major (SIMD-regime verify order)

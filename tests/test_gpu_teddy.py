@@ -36,6 +36,31 @@ def test_known_answers():
     assert r.engine == "fat-teddy" and r.FindAllIndex(b"test p42 here") == [[5, 8]]
 
 
+# reference meta/ahocorasick_test.go:235-274 (70 literals: above Fat Teddy's 64) and :201-231.  The
+# Aho-Corasick automaton itself is an external module (github.com/coregx/ahocorasick, not in the
+# reference tree): what the reference pins is the result — here the set runs on the generic engines.
+AC70 = ("alpha|bravo|charlie|delta|echo|foxtrot|golf|hotel|india|juliet|kilo|lima|mike|november|oscar|papa|quebec|romeo|"
+        "sierra|tango|uniform|victor|whiskey|xray|yankee|zulu|anise|basil|cilantro|dill|endive|fennel|ginger|hops|ivory|"
+        "jasmine|kelp|lavender|mint|nutmeg|oregano|parsley|quassia|rosemary|sage|thyme|urtica|verbena|wasabi|xylose|"
+        "yarrow|zinnia|acacia|bamboo|cactus|dahlia|ebony|fern|grass|holly|iris|juniper|kudzu|lotus|moss|nettle|oak|plum|"
+        "reed|sorrel")
+
+
+def test_reference_large_literal_sets():
+    r = cg.Compile(AC70)
+    hay = b"this is alpha and omega, with bravo and tango at the end"
+    assert r.Match(hay) and r.Count(hay) == 3
+    assert r.FindAllIndex(hay)[0] == [8, 13]
+    r = cg.Compile("mon|tue|wed|thu|fri|sat|sun|day|week|month")
+    for h, want in [(b"monday", 1), (b"mon tue wed", 3), (b"year", 0), (b"day week month", 3)]:
+        assert r.Count(h) == want
+    rng = np.random.default_rng(5)
+    words = AC70.encode().split(b"|") + [b"omega", b"alp", b"oakplum", b"fernn", b"  ", b"\n"]
+    hay = b" ".join(words[i] for i in rng.integers(0, len(words), 3000))
+    check(AC70, hay)
+    check("|".join("w%03dx" % i for i in range(100)), b" ".join(b"w%03dx" % i for i in rng.integers(0, 140, 2000)))
+
+
 def test_fixture_corpus():
     corpus = open(os.path.join(ROOT, "tests", "golden", "stdlib_corpus.txt"), "rb").read()
     check("error|warning|fatal|critical", corpus)

@@ -61,6 +61,16 @@ def test_nullable_and_large_automata_go_to_the_pikevm_engine():
         assert cg.Compile(pat).engine == "pikevm"
 
 
+def test_literal_sets_stay_on_the_multi_literal_engines():
+    # 16 literals: Slim Teddy; 64 literals: Fat Teddy (reference prefilter/teddy_fat.go:348) — the
+    # DFA of 64 literals does not fit 160 states, which must not push the set to the PikeVM engine
+    lit16 = ["error", "warning", "fatal", "critical", "timeout", "refused", "denied", "panic", "overflow", "invalid",
+             "missing", "corrupt", "expired", "blocked", "aborted", "unknown"]
+    lit64 = ["k%02dz%s" % (i, "q" * (i % 4)) for i in range(64)]
+    assert cg.Compile("|".join(lit16)).engine == "teddy"
+    assert cg.Compile("|".join(lit64)).engine == "fat-teddy"
+
+
 def test_no_device_means_error_not_fallback():
     import torch
     if torch.cuda.is_available():

@@ -22,7 +22,7 @@ STRIDE, TILE, CHUNK = 64 * K, 2048, (32 * K - 1) * 64
 BACKEND = "sim"
 
 
-@pytest.fixture(autouse=True, params=["sim", "simjit", "simjit_k4", pytest.param("gpu", marks=pytest.mark.gpu)])
+@pytest.fixture(autouse=True, params=["sim", "simjit", "simjit_k8", pytest.param("gpu", marks=pytest.mark.gpu)])
 def backend(request):
     """Every case runs on the emulator — the interpreting build and the per-pattern specialised
     build (what jit.cu compiles for the device) — and, under -m gpu, on the device through the C ABI."""
@@ -34,13 +34,13 @@ def backend(request):
 
 def scan(pat, hay, mode=0, cap=None, grid=2, base=0):
     """(total, flag, pairs) from the selected backend."""
-    if BACKEND in ("sim", "simjit", "simjit_k4"):
+    if BACKEND in ("sim", "simjit", "simjit_k8"):
         # simjit: the per-pattern, per-mode specialised build (what jit.cu compiles for the device);
-        # simjit_k4: the same with 4 words per lane and a 3-deep window ring (other chunk geometry);
+        # simjit_k8: the same with 8 words per lane and a 4-deep window ring (other chunk geometry);
         # every emulated scan runs twice on the same scratch (stale look-back words of the first launch)
-        k4 = BACKEND == "simjit_k4"
+        k4 = BACKEND == "simjit_k8"
         return sim_lib.scan(pat, hay, mode=mode, cap=cap, grid=grid, base=base, jit=BACKEND != "sim",
-                            defs="-DCGX_K=4 -DCGX_NB=4" if k4 else "", tag="k4" if k4 else "", launches=2)
+                            defs="-DCGX_K=8 -DCGX_NB=4 -DCGX_WARPS=8 -DCGX_CAP=300" if k4 else "", tag="k8" if k4 else "", launches=2)
     import torch
     from gpu_util import scan_device
     r = cg.Compile(pat)

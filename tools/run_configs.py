@@ -38,7 +38,12 @@ def timed(fn, steps=5, warm=3):
     return e0.elapsed_time(e1) / steps
 
 
+ONLY = os.environ.get("CFG_ONLY", "")  # e.g. "C3,C5": run only the configs whose name starts so
+
+
 def run(name, pattern, kind, seed, nbytes, literals=None, submatch=False, window=64 * 4096, cap_div=40):
+    if ONLY and not any(name.startswith(p) for p in ONLY.split(",")):
+        return None
     bs = cg.SYNTH_BLOCK[kind]
     nbytes -= nbytes % (bs * (window // bs) if window % bs == 0 else bs)
     t = dev_corpus(kind, seed, nbytes, literals=literals)
