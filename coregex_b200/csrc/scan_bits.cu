@@ -73,10 +73,11 @@ constexpr int NSLOTS = 32 * (K + 1);       // word w lives in slot w + w / K (on
 // slot NSLOTS stays all zero: lane 31 has no neighbour word, it reads this one instead (no class
 // byte, no marker: a word that leaves every piece of per-lane state as it is)
 constexpr int NSLOTS1 = NSLOTS + 1;
+// staged matches per chunk (the IP corpus has ~80 per 8 KB).  CGX_PARK (dense patterns, see below):
+// every chunk parks its bitmaps; ONE staging buffer turns them into coalesced stores, CAP pairs a round
 #ifndef CGX_CAP
-#define CGX_CAP 160
+#define CGX_CAP_DEFAULT 1
 #endif
-constexpr int CAP = CGX_CAP;               // staged matches per chunk (the IP corpus has ~80 per 8 KB)
 static_assert(K == 4 || K == 8 || K == 16, "words per lane: a power of two that divides 32");
 
 // ---- pipe-aware primitives (the kernel is bound by the integer ALU pipe) -------
@@ -143,13 +144,18 @@ constexpr int NPAIR = (NC + 1) / 2;        // 16-byte slot arrays: classes (0,1)
 #define CGX_PARK 0
 #endif
 constexpr int NBUF = CGX_PARK ? 2 : 1;
+#ifdef CGX_CAP_DEFAULT
+#define CGX_CAP (CGX_PARK ? 1024 : 160)
+#endif
+constexpr int CAP = CGX_CAP;
+constexpr int NST = CGX_PARK ? 1 : 2;      // staging buffers
 // scanning warps per CTA: as many as the shared memory of one SM holds (one or two slot arrays per warp)
 // The register file is split over the four schedulers: with the resolver the CTA has 24 warps (6 per
 // scheduler, 80 registers a thread) when one slot array per warp fits the shared memory of an SM 23
 // times, 20 warps (96 registers) with two slot arrays.  Measured on B200 (IP regex, 16 GiB):
 // K=8 x 15 warps 3225 GB/s, K=4 x 19 warps 3203 GB/s, K=4 x 23 warps 3380 GB/s.
 #ifndef CGX_WARPS
-#define CGX_WARPS (NPAIR == 1 ? (CGX_PARK ? 19 : 23) : (CGX_PARK ? 11 : 19))
+#define CGX_WARPS (NPAIR == 1 ? (CGX_PARK ? 15 : 23) : (CGX_PARK ? 11 : 19))
 #endif
 constexpr int FW_WARPS = CGX_WARPS;
 constexpr int FW_THREADS = (FW_WARPS + 1) * 32;  // + one resolver warp
@@ -166,7 +172,7 @@ struct WarpSmem {
   // A chunk's matches wait here (chunk-relative u16 offsets, in match order) for the chunk's global
   // offset while the next chunk is scanned: two buffers.  A chunk with more than CAP matches keeps
   // its bitmaps instead and waits for its offset on the spot.
-  uint16_t stS[2][CAP], stE[2][CAP];
+  uint16_t stS[NST][CAP], stE[NST][CAP];
   uint64_t mbar[NB];
   // matches of a serially replayed segment that end beyond the chunk's bitmap (per staging buffer):
   // found again, and stored, when the chunk's offset is known
@@ -543,6 +549,115 @@ __device__ __noinline__ unsigned replay_cold(const ScanArgs& a, int64_t cb, Slot
   return far;
 }
 
+// The bit-parallel form of the replay for a lane whose last segment is merely OPEN (no sync byte in
+// its neighbour's first word, nothing misordered): the calling lane classifies the words from the one
+// that holds `from` (= the position after the lane's last sync byte) up to the first word with a sync
+// byte at or after `stop_min`, straight from global memory, and runs both sweeps over them on its own
+// — some hundred instructions per word instead of a dependent table walk per byte.  Matches whose end
+// lies inside the chunk's bitmap are recorded there, the others are counted (`far`, as replay_cold
+// does).  Returns false when the stretch is longer than MAXW words or turns out misordered: the
+// caller then takes the reference loop (replay_cold).
+constexpr int RB_MAXW = 8;
+__device__ __noinline__ bool replay_bits(const ScanArgs& a, const FlatDev& f, int64_t cb, Slot* res, int64_t from,
+                                         int64_t stop_min, uint32_t one, unsigned* far_out) {
+  uint64_t cr[RB_MAXW][4];  // class words, reversed orientation
+  uint64_t mk[RB_MAXW];
+  const int64_t w0 = (from - cb) >> 6;
+  int nw = 0;
+  int last_sync = -1;  // bit (forward orientation) of the closing sync byte in word nw - 1
+  for (;;) {
+    if (nw == RB_MAXW) return false;
+    const int64_t wp = cb + ((w0 + nw) << 6);  // global position of the word
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (wp + 16 * j < a.n) v = __ldg(reinterpret_cast<const uint4*>(a.h + wp) + j);  // (whole 16-byte blocks, as the bulk copies)
+      w[4 * j] = v.x;
+      w[4 * j + 1] = v.y;
+      w[4 * j + 2] = v.z;
+      w[4 * j + 3] = v.w;
+    }
+    cr[nw][0] = class_rev64<0>(f, w, one);
+    cr[nw][1] = P_NCLASSES > 1 ? class_rev64<1>(f, w, one) : 0ull;
+    cr[nw][2] = P_NCLASSES > 2 ? class_rev64<2>(f, w, one) : 0ull;
+    cr[nw][3] = P_NCLASSES > 3 ? class_rev64<3>(f, w, one) : 0ull;
+    const int64_t valid = a.n - wp;  // bytes of this word inside the input
+    if (valid < 64) {
+      const uint64_t m = valid <= 0 ? 0ull : (~0ull << (64 - valid));
+#pragma unroll
+      for (int c = 0; c < 4; c++) cr[nw][c] &= m;
+    }
+    // first sync byte of this word at or after stop_min (and, in the first word, at or after `from`)
+    uint64_t nz = ~brev64(cr[nw][0] | cr[nw][1] | cr[nw][2] | cr[nw][3]);
+    int64_t lo = (from > stop_min ? from : stop_min) - wp;
+    if (lo > 0) nz = lo >= 64 ? 0ull : (nz & (~0ull << lo));
+    nw++;
+    if (nz) {
+      last_sync = __ffsll((long long)nz) - 1;
+      break;
+    }
+  }
+  PassState st;
+  pass_reset(st);
+  for (int i = nw - 1; i >= 0; i--) mk[i] = brev64(rev_word(f, cr[i], st));
+  pass_reset(st);
+  uint32_t in = 0u, c0hi = 0u;
+  uint64_t badbits = 0ull;
+  uint64_t Sw[RB_MAXW], Ew[RB_MAXW];
+  for (int i = 0; i < nw; i++) {
+    uint64_t c[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) c[k] = brev64(cr[i][k]);
+    uint64_t own = ~0ull;
+    if (i == 0) {
+      const int lo = (int)(from - (cb + (w0 << 6)));
+      own = lo >= 64 ? 0ull : (~0ull << lo);
+    }
+    if (i == nw - 1) own &= last_sync >= 63 ? ~0ull : ((2ull << last_sync) - 1ull);  // up to and including the sync byte
+    uint64_t M = mk[i];
+    const uint64_t c0prev = shl_in<1>(c[0], c0hi);
+    c0hi = hi32(c[0]);
+    if (P_RUNSTART) M &= c[0] & ~c0prev;
+    const uint64_t S = M & own;
+    const uint64_t E = fwd_word(f, c, S, st) & own;
+    badbits |= word_misordered(S, E, in);
+    if (P_MIDRUN) badbits |= E & c[0] & c0prev;
+    Sw[i] = S;
+    Ew[i] = E;
+  }
+  if (badbits != 0ull || in != 0u) return false;
+  // starts and ends alternate (an end may stand where the next start does): pair them in order; a
+  // match is recorded when its end is inside the chunk's bitmap, counted otherwise
+  unsigned far = 0u;
+  int64_t open_start = -1;
+  for (int i = 0; i < nw; i++) {
+    uint64_t S = Sw[i], E = Ew[i];
+    const int64_t wrel = (w0 + i) << 6;
+    for (;;) {
+      if (open_start < 0) {
+        if (!S) break;
+        open_start = wrel + (__ffsll((long long)S) - 1);
+        S &= S - 1ull;
+      } else {
+        if (!E) break;
+        const int64_t e = wrel + (__ffsll((long long)E) - 1);
+        E &= E - 1ull;
+        if (e < (int64_t)WINDOW) {
+          const int ws = (int)(open_start >> 6), we = (int)(e >> 6);
+          smem_or64(&res[ws + ws / K].a, (int)(open_start & 63));
+          smem_or64(&res[we + we / K].b, (int)(e & 63));
+        } else {
+          far++;
+        }
+        open_start = -1;
+      }
+    }
+  }
+  *far_out = far;
+  return true;
+}
+
 // ---- two-level look-back ------------------------------------------------------------------------------
 // Chunk c publishes its match count in status[c] (flag LB_AGG).  Chunks form groups of 32; the
 // warp that finishes a group's last chunk publishes the group's sum in gstatus[g] (LB_AGG), and
@@ -727,16 +842,42 @@ __device__ __forceinline__ void extract_direct(const ScanArgs& a, const Slot* ar
 // set bits of its own K words (rk = starts before them).  Ends: starts and ends alternate, so the end
 // of the i-th match is the first end bit after the i-th start — one lane per MATCH, which spreads
 // the work evenly over the warp however the matches are distributed over the lanes' words.
-__device__ __forceinline__ void extract_staged(WarpSmem& ws, const Slot* all, int sb, uint32_t rk, unsigned n, int lane) {
+// Stages the matches with ranks [r0, r0 + n) of the chunk (r0 = 0 and n = all of them unless CGX_PARK
+// takes a dense chunk in rounds).
+__device__ __forceinline__ void extract_staged(WarpSmem& ws, const Slot* all, int sb, uint32_t rk, unsigned r0, unsigned n,
+                                               int lane) {
   const Slot* res = all + lane * (K + 1);
-  uint16_t* os = ws.stS[sb] + rk;
   const int wb = lane * (K * 64);
+  uint16_t* os = ws.stS[sb];
+  if (r0 == 0u && !CGX_PARK) {
+    os += rk;
 #pragma unroll 1
-  for (int j = 0; j < K; j++) {
-    const uint64_t v = res[j].a;
-    const int pb = wb + j * 64;
-    stage_half(lo32(v), pb, os);
-    stage_half(hi32(v), pb + 32, os);
+    for (int j = 0; j < K; j++) {
+      const uint64_t v = res[j].a;
+      const int pb = wb + j * 64;
+      stage_half(lo32(v), pb, os);
+      stage_half(hi32(v), pb + 32, os);
+    }
+  } else {
+    // only the starts whose rank falls into the round's window
+    unsigned i = rk;
+#pragma unroll 1
+    for (int j = 0; j < K && i < r0 + n; j++) {
+      uint64_t v = res[j].a;
+      const unsigned c = (unsigned)__popcll(v);
+      if (i + c > r0) {
+        const int pb = wb + j * 64;
+        while (v) {
+          const uint32_t lo = lo32(v);
+          const int b = lo ? __ffs((int)lo) - 1 : 31 + __ffs((int)hi32(v));
+          v &= v - 1ull;
+          if (i >= r0 && i < r0 + n) os[i - r0] = (uint16_t)(pb + b);
+          i++;
+        }
+      } else {
+        i += c;
+      }
+    }
   }
   __syncwarp();
   const uint16_t* ss = ws.stS[sb];
@@ -807,7 +948,6 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     return;
   }
   WarpSmem& ws = cs.w[warp];
-  constexpr unsigned PARKED = 0xFFFFFFFFu;  // bits_cnt of a chunk whose bitmaps are parked (CGX_PARK)
   const unsigned nwarps_total = gridDim.x * FW_WARPS;
   // FindAll: tickets are gangs (drawn by the resolver), warp w scans chunk gang * FW_WARPS + w — a
   // chunk past the end is empty; the other modes need no order: every warp draws chunks on its own
@@ -912,17 +1052,12 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     const unsigned long long excl = m.excl;
     report_total(chunk, excl + m.cnt);
     unsigned nbits = ws.bits_cnt[b];
-    if (CGX_PARK && nbits == PARKED) {
-      // the chunk did not fit the staging buffer: its bitmaps waited in slot array b
+    if (CGX_PARK) {
+      // the chunk's bitmaps waited in slot array b: rounds of CAP matches through the staging buffer
       nbits = m.cnt - ws.far_cnt[b];
       const Slot* arr = ws.cls[b][0];
-      uint32_t xs = 0u, xe = 0u;
-      for (int j = 0; j < K; j++) {
-        const Slot v = arr[lane * (K + 1) + j];
-        xs += __popcll(v.a);
-        xe += __popcll(v.b);
-      }
-      uint32_t x = xs | (xe << 16);  // (a chunk holds fewer than 65536 positions)
+      uint32_t x = 0u;
+      for (int j = 0; j < K; j++) x += __popcll(arr[lane * (K + 1) + j].a);
       const uint32_t mine = x;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -930,7 +1065,13 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         if (lane >= d) x += y;
       }
       x -= mine;
-      extract_direct(a, arr, chunk, excl, m.cnt, x & 0xFFFFu, x >> 16, lane);
+      for (unsigned r0 = 0; r0 < nbits; r0 += (unsigned)CAP) {
+        const unsigned nr = nbits - r0 < (unsigned)CAP ? nbits - r0 : (unsigned)CAP;
+        extract_staged(ws, arr, 0, x, r0, nr, lane);
+        __syncwarp();
+        write_out(a, ws, 0, chunk, nr, excl + r0, lane);
+        __syncwarp();
+      }
     } else {
       write_out(a, ws, b, chunk, nbits, excl, lane);
     }
@@ -1179,7 +1320,10 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       if (lane == 0) atomicAdd(&a.total[2], 1ull);  // diagnostics: chunks with a serial replay (cgx_debug_scratch)
       if (replay) {
         unsigned nb = 0;
-        far = replay_cold(a, cb, cls[0], rp_from, rp_stop, nullptr, 0ull, &nb);
+        if (!bad && replay_bits(a, f, cb, cls[0], rp_from, rp_stop, one, &far))
+          atomicAdd(&a.total[3], 1ull);  // diagnostics: open segments replayed bit-parallel
+        else
+          far = replay_cold(a, cb, cls[0], rp_from, rp_stop, nullptr, 0ull, &nb);
       }
       __syncwarp();
       // bits may have landed in other lanes' words: count again
@@ -1210,13 +1354,13 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         ws.far_from[sb] = rp_from;
         ws.far_stop[sb] = rp_stop;
       }
-      const bool staged = nbits <= (unsigned)CAP;
+      const bool staged = !CGX_PARK && nbits <= (unsigned)CAP;
       if (staged) {
-        extract_staged(ws, cls[0], sb, rk, nbits, lane);
+        extract_staged(ws, cls[0], sb, rk, 0u, nbits, lane);
       } else if (lane == 0) {
         // nothing staged: the bitmaps are turned into pairs when the offset is known — below, or
         // (CGX_PARK) when the slot array is needed again
-        ws.bits_cnt[sb] = CGX_PARK ? PARKED : 0u;
+        ws.bits_cnt[sb] = 0u;
       }
       __syncwarp();
       if (lane == 0) {

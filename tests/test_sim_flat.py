@@ -117,6 +117,24 @@ def test_long_spans_without_sync_bytes():
     check(IP, b"1.1.1." + b"9" * 6000)
 
 
+def test_open_segments_take_the_bit_parallel_replay():
+    # stretches without a sync byte that run past a lane's neighbour word (64 .. 500 bytes): the owning
+    # lane replays them bit-parallel from global memory (replay_bits), longer ones byte by byte
+    rng = random.Random(11)
+    for pat in (r"[a-z]+/\d+", r"\w+@\w+\.\w+", IP):
+        parts = []
+        for _ in range(300):
+            n = rng.choice([3, 20, 70, 130, 200, 260, 400, 450, 700])
+            if pat == IP:
+                body = b"".join(rng.choice([b"1", b"22", b"333"]) + rng.choice([b".", b".", b""]) for _ in range(n // 3))
+                parts.append(body + rng.choice([b" ", b" x ", b"\n"]))
+            elif "@" in pat:
+                parts.append(b"w" * n + b"@" + b"h" * rng.randrange(1, 90) + b"." + b"c" * rng.randrange(1, 40) + rng.choice([b" ", b"\n", b". "]))
+            else:
+                parts.append(bytes(rng.choice(b"abcxyz") for _ in range(n)) + b"/" + b"7" * rng.randrange(1, 80) + rng.choice([b" ", b"/x ", b"\n"]))
+        check(pat, b"".join(parts), grid=2)
+
+
 def test_class_words_of_all_ones_use_exact_carries():
     # a 64-byte piece made of class bytes only: the fast carry chain (one ballot) is not valid there
     rng = random.Random(21)

@@ -98,3 +98,5 @@ if __name__ == "__main__":
         run(r"[a-z]+/\d+", cg.SYNTH_LOG, 0xC0FFEE, 1 * GIB)
     if npat > 3:
         run(r"\d+", cg.SYNTH_LOG, 0xC0FFEE, 1 * GIB, cap_div=4)
+    if npat > 4:
+        run(r"\w+", cg.SYNTH_LOG, 0xC0FFEE, 1 * GIB, cap_div=4)

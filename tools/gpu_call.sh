@@ -2,9 +2,8 @@
 # the command of one gpurun call of round 2 (kept in a file so that retries send the current tree)
 TAG=$1
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_teddy.py tests/test_gpu_large.py -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1
+timeout 900 python -m pytest tests/test_sim_flat.py tests/test_gpu_teddy.py -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1
 tail -4 gpurun_out/${TAG}_pytest.log
-CFG_ONLY=C3,C5 timeout 600 python tools/run_configs.py > gpurun_out/${TAG}_configs.jsonl 2> gpurun_out/${TAG}_configs.err
-cut -c1-330 gpurun_out/${TAG}_configs.jsonl; tail -3 gpurun_out/${TAG}_configs.err
-CFG_ONLY=C3 CFG_SCALE=0.25 timeout 300 ncu --set full --clock-control none --import-source on -k regex:scan_dfa_kernel -s 3 -c 1 -f -o gpurun_out/${TAG}_teddy_full python tools/run_configs.py > gpurun_out/${TAG}_ncu_teddy.log 2>&1
-ls -la gpurun_out | tail -3
+AB_STEPS=10 AB_PATS=5 timeout -k 10 300 python tools/ab_flat.py 16 > gpurun_out/${TAG}_ab.jsonl 2> gpurun_out/${TAG}_ab.err
+cut -c1-400 gpurun_out/${TAG}_ab.jsonl; tail -3 gpurun_out/${TAG}_ab.err
+bash tools/gpu_round2.sh ${TAG} bench c5 ncu
