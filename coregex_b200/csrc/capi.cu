@@ -22,6 +22,8 @@ int64_t scan_dfa_chunks(int64_t n);
 cudaError_t launch_scan_dfa(const ScanArgs& a, int sm_count, cudaStream_t stream);
 int64_t scan_flat_chunks(int64_t n);
 cudaError_t launch_scan_flat(const ScanArgs& a, int sm_count, cudaStream_t stream, int* grid_out);
+int64_t scan_teddy_chunks(int64_t n);
+cudaError_t launch_scan_teddy(const ScanArgs& a, int sm_count, cudaStream_t stream, int* grid_out);
 int64_t pike_search_slices(int64_t n);
 size_t pike_search_scratch_bytes(int64_t n);
 cudaError_t launch_pike_search(const uint8_t* h, int64_t n, int64_t base, int64_t after, const uint32_t* code,
@@ -453,6 +455,9 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
     return !(e && e[0] == '0');
   }();
   const bool use_flat = c.kind == ENG_DFA && c.flat.bs_ok && re->bitstream && bs_env;
+  // literal sets run on the bitstream kernel's skeleton (scan_teddy.cu) when no literal is longer than
+  // 32 bytes (its safe-point argument); cgx_debug_set_bitstream(0) keeps them on the scan_dfa.cu engine
+  const bool use_teddy2 = c.kind == ENG_TEDDY && c.teddy.max_len <= 32 && re->bitstream && bs_env;
   // the specialised kernel of this pattern and mode (built on first use); it knows its own chunk size
   if (use_flat && re->jit_state >= 0) {
     if (!re->jit[mode]) re->jit[mode] = GetJitKernel(c.flat, mode, re->jit_error);
@@ -460,7 +465,8 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   }
   const bool use_jit = use_flat && re->jit_state == 1;
   const int64_t nchunks = use_jit ? ((int64_t)len + re->jit[mode]->chunk_bytes - 1) / re->jit[mode]->chunk_bytes
-                          : use_flat ? scan_flat_chunks((int64_t)len) : scan_dfa_chunks((int64_t)len);
+                          : use_flat ? scan_flat_chunks((int64_t)len)
+                          : use_teddy2 ? scan_teddy_chunks((int64_t)len) : scan_dfa_chunks((int64_t)len);
   if (nchunks >= 0xFFFF0000ll) {
     g_last_error = "haystack too large for one scan call (32-bit chunk tickets); shard it";
     return CGX_ERR_ARGS;
@@ -469,9 +475,15 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   if ((r = re->d_ticket_total.ensure(64))) return r;
   // look-back words: one per chunk, then (bitstream kernel) two words per 32 chunks
   const size_t ngroups = (size_t)(nchunks + 31) / 32 + 1;
-  const size_t status_bytes = (size_t)(nchunks > 0 ? nchunks : 1) * 8 + ngroups * 16;
+  const size_t status_bytes = (size_t)(nchunks > 0 ? nchunks : 1) * 8 + ngroups * 16 + 1024;
   if ((r = re->d_status.ensure(status_bytes))) return r;
-  const bool one_launch = use_flat && mode == CGX_MODE_FINDALL && nchunks > 0;
+  // The buffer is cut by its CAPACITY, not by this call's chunk count: group accumulators | group
+  // words | chunk words.  The epoched words and the self-cleaning accumulators survive from launch
+  // to launch, so a regex that scans haystacks of different sizes (the pieces of a pipelined host
+  // call) must find each of them in the same place every time.
+  const size_t status_words = re->d_status.cap / 8;
+  const size_t ng_cap = status_words / 34 + 2;  // >= ngroups, and 2 * ng_cap + nchunks <= status_words
+  const bool one_launch = (use_flat || use_teddy2) && mode == CGX_MODE_FINDALL && nchunks > 0;
   if (one_launch) {
     if (re->epoch == 0 || re->epoch >= 0xFFFFFu || re->status_cap_seen != re->d_status.cap) {
       CU(cudaMemsetAsync(re->d_status.p, 0, re->d_status.cap, st));  // new buffer, or the epoch counter wrapped
@@ -484,7 +496,7 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   } else {
     CU(cudaMemsetAsync(re->d_ticket_total.p, 0, 64, st));
     if (mode == CGX_MODE_FINDALL && nchunks > 0) {
-      CU(cudaMemsetAsync(re->d_status.p, 0, status_bytes, st));
+      CU(cudaMemsetAsync(re->d_status.p, 0, re->d_status.cap, st));
       re->epoch = 0;  // the other kernel wrote un-epoched words
     }
     re->scratch_zero = false;  // (IsMatch leaves the ticket counter wherever the early exit found it)
@@ -540,15 +552,17 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
   unsigned long long* tt = (unsigned long long*)re->d_ticket_total.p;
   a.total = tt;                        // [0] count, [1] is-match flag
   a.ticket = (unsigned int*)(tt + 4);  // separate 32-byte sector
-  a.status = (unsigned long long*)re->d_status.p;
+  a.gacc = (unsigned long long*)re->d_status.p;
+  a.gstatus = a.gacc + ng_cap;
+  a.status = a.gstatus + ng_cap;
   a.nchunks = nchunks;
-  a.gstatus = a.status + (nchunks > 0 ? nchunks : 1);
-  a.gacc = a.gstatus + ngroups;
   a.epoch = re->epoch;
   a.result = one_launch ? (unsigned long long*)d_result : nullptr;
   if (use_flat) {
     if (use_jit) CU(launch_scan_flat_jit(re->jit[mode], a, re->sm_count, st));
     else CU(launch_scan_flat(a, re->sm_count, st, nullptr));
+  } else if (use_teddy2) {
+    CU(launch_scan_teddy(a, re->sm_count, st, nullptr));
   } else {
     CU(launch_scan_dfa(a, re->sm_count, st));
   }

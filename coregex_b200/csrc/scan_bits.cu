@@ -43,6 +43,28 @@
 #include "scan_common.cuh"
 #include "scan_params.h"
 
+// CGX_TEDDY (csrc/scan_teddy.cu includes this file with it): the same skeleton — gangs of chunks,
+// per-warp TMA window ring, staged matches, one look-back per gang — with the multi-literal engine
+// in place of the class tests and sweeps.  Replaces reference prefilter/teddy.go:391-445 FindMatch
+// (teddy_ssse3_amd64.s:273, teddy_avx2_amd64.s:43) + :532-550 verifyBucket under the FindAll loop.
+//   phase A  per byte two table loads (bucket masks of fingerprint bytes 0 and 1) and one AND with
+//            predicate: a candidate bitmap per chunk;
+//   phase B  every lane runs the reference loop (candidate -> verify -> continue at the match end)
+//            over its own K words.  It enters the chain at a SAFE POINT: it first verifies the
+//            candidates of the word before its region without chaining; a position of that word's
+//            second half that lies strictly inside none of those spans cannot lie inside a kept match
+//            either (literals are at most 32 bytes long), so the chain state there is known.  No
+//            lane depends on another one, chunks need one word of context before their first
+//            owned word and one after their last.
+#ifdef CGX_TEDDY
+#define scan_flat_chunks scan_teddy_chunks
+#define scan_flat_smem_bytes scan_teddy_smem_bytes
+#define scan_flat_threads scan_teddy_threads
+#define scan_flat_warps scan_teddy_warps
+#define launch_scan_flat launch_scan_teddy
+#define sim_launch_scan_flat sim_launch_scan_teddy
+#endif
+
 namespace cgx {
 
 namespace {
@@ -68,7 +90,12 @@ constexpr int TILE = 2048;                 // one bulk copy, one classification 
 constexpr int TPC = K;                     // tiles per chunk
 constexpr int NWORDS = 32 * K;             // words of a chunk's window
 constexpr int WINDOW = NWORDS * 64;        // bytes of a chunk's window
-constexpr int CHUNKB = (NWORDS - 1) * 64;  // bytes between chunk origins: chunks overlap by one word
+#ifdef CGX_TEDDY
+constexpr int OVLW = 2;                    // a word of context before the owned words, one after
+#else
+constexpr int OVLW = 1;
+#endif
+constexpr int CHUNKB = (NWORDS - OVLW) * 64;  // bytes between chunk origins: chunks overlap by OVLW words
 constexpr int NSLOTS = 32 * (K + 1);       // word w lives in slot w + w / K (one pad slot per lane region)
 // slot NSLOTS stays all zero: lane 31 has no neighbour word, it reads this one instead (no class
 // byte, no marker: a word that leaves every piece of per-lane state as it is)
@@ -128,6 +155,9 @@ __device__ __forceinline__ uint32_t mad_fma(uint32_t x, uint32_t one, uint32_t k
 #ifdef CGX_JIT
 constexpr int NC = CGX_JIT_NCLASSES;       // class words per slot
 constexpr int NSTATE = CGX_JIT_NSTATE;     // per-step carry / shift state of a sweep
+#elif defined(CGX_TEDDY)
+constexpr int NC = 2;                      // slot = (candidates -> starts, ends)
+constexpr int NSTATE = 1;
 #else
 constexpr int NC = 4;
 constexpr int NSTATE = 24;
@@ -160,6 +190,16 @@ constexpr int NST = CGX_PARK ? 1 : 2;      // staging buffers
 constexpr int FW_WARPS = CGX_WARPS;
 constexpr int FW_THREADS = (FW_WARPS + 1) * 32;  // + one resolver warp
 static_assert(FW_WARPS <= 31, "one CTA holds at most 31 scanning warps and the resolver");
+
+// global position (relative to h) of a chunk's window: the multi-literal engine keeps one word of
+// context before the owned words (chunk 0 starts the haystack and has none)
+__device__ __forceinline__ int64_t chunk_origin(int64_t chunk) {
+#ifdef CGX_TEDDY
+  return chunk * (int64_t)CHUNKB - (chunk > 0 ? 64 : 0);
+#else
+  return chunk * (int64_t)CHUNKB;
+#endif
+}
 
 struct alignas(16) Slot {
   uint64_t a, b;
@@ -197,6 +237,11 @@ struct CtaSmem {
   // arrivals << 40 | matches of the gang being scanned (per parity of its sequence number): the
   // last warp to arrive publishes the gang's count in the look-back words
   unsigned long long gang_acc[2];
+#ifdef CGX_TEDDY
+  // bucket masks per byte value of fingerprint byte 0 / byte 1 (reference prefilter/teddy.go:271-311
+  // buildMasks, the two nibble tables of a position folded into one byte table)
+  uint16_t tfa[256], tfb[256];
+#endif
 };
 
 __device__ __forceinline__ uint64_t mk64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
@@ -282,6 +327,9 @@ __device__ __forceinline__ uint64_t class_rev64(const FlatDev& f, const uint32_t
 struct LaneRot {
   uint32_t o0;               // lane * 64 + (r << 4): offset of the quarter load 0 reads
   uint32_t sel_lo, sel_hi;   // __byte_perm selectors that swap the 16-bit fields q <-> q ^ r
+#ifdef CGX_TEDDY
+  uint32_t fsel_lo, fsel_hi; // the same for a word in forward orientation (field q = bytes 2q, 2q + 1)
+#endif
 };
 #ifndef CGX_ROT
 #define CGX_ROT 1
@@ -301,6 +349,17 @@ __device__ __forceinline__ LaneRot lane_rot(int lane) {
   }
   lr.sel_lo = sl;
   lr.sel_hi = sh;
+#ifdef CGX_TEDDY
+  uint32_t fl = 0u, fh = 0u;
+#pragma unroll
+  for (uint32_t i = 0; i < 8u; i++) {
+    const uint32_t src = 2u * ((i >> 1) ^ r) + (i & 1u);
+    if (i < 4u) fl |= src << (4u * i);
+    else fh |= src << (4u * (i - 4u));
+  }
+  lr.fsel_lo = fl;
+  lr.fsel_hi = fh;
+#endif
   return lr;
 }
 __device__ __forceinline__ void classify_piece(const FlatDev& f, const uint8_t* win, const LaneRot& lr, uint32_t one,
@@ -658,6 +717,186 @@ __device__ __noinline__ bool replay_bits(const ScanArgs& a, const FlatDev& f, in
   return true;
 }
 
+#ifdef CGX_TEDDY
+// ---- multi-literal engine ---------------------------------------------------------------------------
+// Candidate bitmap (FORWARD orientation: bit b <=> byte b) of the lane's 64-byte piece: position p is
+// a candidate when some bucket holds a literal whose first two bytes are h[p], h[p+1]
+// (tfa[h[p]] & tfb[h[p+1]] != 0).  The four quarter loads are rotated like classify_piece's; the
+// quarters are evaluated one by one (the byte after a quarter comes from shared memory), packed as
+// if load j were quarter j and put in place by two byte permutes.
+__device__ __forceinline__ uint64_t teddy_piece(const uint8_t* win, const LaneRot& lr, const uint16_t* tfa,
+                                                const uint16_t* tfb) {
+  uint32_t f16[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint32_t qoff = lr.o0 ^ (uint32_t)(j << 4);  // offset of the quarter load j reads
+    const uint4 v = *reinterpret_cast<const uint4*>(win + qoff);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    // the byte after the quarter; the one after the tile's last byte is not here: every bucket passes
+    const uint32_t nb_b = qoff + 16u < (uint32_t)TILE ? (uint32_t)tfb[win[qoff + 16u]] : 0xFFFFu;
+    uint32_t m = 0u;
+    uint32_t prev_a = tfa[w[0] & 0xFFu];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      uint32_t tb, ta = 0u;
+      if (k < 15) {
+        const uint32_t b = (w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xFFu;
+        tb = tfb[b];
+        ta = tfa[b];
+      } else {
+        tb = nb_b;
+      }
+      if (prev_a & tb) m |= 1u << k;
+      prev_a = ta;
+    }
+    f16[j] = m;
+  }
+  const uint32_t lo = f16[0] | (f16[1] << 16), hi = f16[2] | (f16[3] << 16);
+#if CGX_ROT
+  return mk64(__byte_perm(lo, hi, lr.fsel_hi), __byte_perm(lo, hi, lr.fsel_lo));
+#else
+  return mk64(hi, lo);
+#endif
+}
+
+// bytes p .. p+7 of the haystack as a little-endian word (global memory; bytes at or beyond n read
+// as anything: every comparison is guarded by p + len <= n)
+__device__ __forceinline__ uint64_t teddy_load8(const ScanArgs& a, int64_t p) {
+  const int64_t q = p & ~(int64_t)7;
+  if (q + 16 <= ((a.n + 15) & ~(int64_t)15)) {  // both words inside the readable 16-byte blocks
+    const uint64_t w0 = __ldg(reinterpret_cast<const unsigned long long*>(a.h + q));
+    const uint64_t w1 = __ldg(reinterpret_cast<const unsigned long long*>(a.h + q) + 1);
+    const unsigned sh = (unsigned)(p & 7) * 8u;
+    return sh ? (w0 >> sh) | (w1 << (64u - sh)) : w0;
+  }
+  uint64_t v = 0;
+  for (int k = 0; k < 8; k++)
+    if (p + k < a.n) v |= (uint64_t)__ldg(a.h + p + k) << (8 * k);
+  return v;
+}
+__device__ __forceinline__ bool teddy_lit_equal(const ScanArgs& a, int64_t p, int id, uint64_t hay8, int& len) {
+  const TeddyDev& t = a.teddy;
+  const int o = __ldg(t.offs + id);
+  len = __ldg(t.offs + id + 1) - o;
+  if (p + len > a.n) return false;
+  if ((hay8 ^ __ldg(reinterpret_cast<const unsigned long long*>(t.lit8) + id)) &
+      __ldg(reinterpret_cast<const unsigned long long*>(t.lit8) + t.npat + id))
+    return false;
+  for (int k = 8; k < len; k++)
+    if (__ldg(a.h + p + k) != __ldg(t.bytes + o + k)) return false;
+  return true;
+}
+// Which literal stands at p?  Returns the match end or -1.  SIMD regime: buckets low to high,
+// insertion order inside a bucket (reference prefilter/teddy.go:415-428, :532-550); scalar regime
+// (fewer than 16 bytes left from the search start, :447-458): plain literal order.
+__device__ __noinline__ int64_t teddy_verify_g(const ScanArgs& a, int64_t p, bool scalar) {
+  const TeddyDev& t = a.teddy;
+  if (p + 2 > a.n) return -1;
+  uint32_t mask = (__ldg(t.fp + __ldg(a.h + p)) & 0xFFFFu) & (__ldg(t.fp + __ldg(a.h + p + 1)) >> 16);
+  if (!mask) return -1;
+  const uint64_t hay8 = teddy_load8(a, p);
+  int len;
+  if (scalar) {
+    for (int id = 0; id < t.npat; id++)
+      if (teddy_lit_equal(a, p, id, hay8, len)) return p + len;
+    return -1;
+  }
+  while (mask) {
+    const int b = __ffs((int)mask) - 1;
+    mask &= mask - 1u;
+    if (b >= t.nbuckets) break;
+    const int k1 = __ldg(t.bucket_off + b + 1);
+    for (int k = __ldg(t.bucket_off + b); k < k1; k++)
+      if (teddy_lit_equal(a, p, (int)__ldg(t.order + k), hay8, len)) return p + len;
+  }
+  return -1;
+}
+// records the match [s, e) in the chunk's bitmaps (positions relative to the window origin cb)
+__device__ __forceinline__ void teddy_record(Slot* cls0, uint64_t* sbits, int64_t cb, int64_t s, int64_t e) {
+  const int ws = (int)((s - cb) >> 6), we = (int)((e - cb) >> 6);
+  smem_or64(&sbits[ws + ws / K], (int)((s - cb) & 63));
+  smem_or64(&cls0[we + we / K].b, (int)((e - cb) & 63));
+}
+// Cold: the reference loop for the starts in [x0, x1) from a position that is safe by construction —
+// the byte after the last record delimiter before x0 (no literal contains it) — through global
+// memory.  Used when the word before a lane's region offers no safe point and near the end of the
+// haystack, where the verify order depends on the distance from the search start to the end.
+__device__ __noinline__ void teddy_lane_cold(const ScanArgs& a, int64_t cb, Slot* cls0, uint64_t* sbits, int64_t x0,
+                                             int64_t x1) {
+  int64_t pos = x0;
+  while (pos > 0 && __ldg(a.h + pos - 1) != a.delim) pos--;
+  const TeddyDev& t = a.teddy;
+  for (int64_t p = pos; p < x1 && p + 2 <= a.n; p++) {
+    if (!((__ldg(t.fp + __ldg(a.h + p)) & 0xFFFFu) & (__ldg(t.fp + __ldg(a.h + p + 1)) >> 16))) continue;
+    const int64_t e = teddy_verify_g(a, p, a.n + a.after - pos < 16);
+    if (e < 0) continue;
+    if (p >= x0) teddy_record(cls0, sbits, cb, p, e);
+    pos = e;
+    p = e - 1;
+  }
+}
+// Phase B of a lane: the words [own_lo, own_hi) of the window at cb are its own, word own_lo - 1
+// (if any) is where it looks for its safe point.  cand: the chunk's candidate bitmap (slot .a).
+__device__ __forceinline__ void teddy_lane(const ScanArgs& a, int64_t cb, Slot* cls0, uint64_t* sbits, int own_lo,
+                                           int own_hi) {
+  if (own_hi <= own_lo) return;
+  const int64_t x0 = cb + (int64_t)own_lo * 64, x1 = cb + (int64_t)own_hi * 64;
+  if (x0 >= a.n) return;
+  // near the end of the haystack the verify order depends on the search start: exact replay
+  if (a.n + a.after - (x0 - 64) < 16 + 64 + (int64_t)(own_hi - own_lo) * 64 + 64) {
+    teddy_lane_cold(a, cb, cls0, sbits, x0, x1);
+    return;
+  }
+  int64_t pos = x0;
+  int w = own_lo;
+  if (own_lo > 0) {
+    // spans of the word before the region, unchained
+    const int pw = own_lo - 1;
+    const int64_t wp = cb + (int64_t)pw * 64;
+    uint64_t c = cls0[pw + pw / K].a, covered = 0ull;
+    bool cross = false;
+    while (c) {
+      const int b = __ffsll((long long)c) - 1;
+      c &= c - 1ull;
+      const int64_t e = teddy_verify_g(a, wp + b, false);
+      if (e < 0) continue;
+      const int len = (int)(e - (wp + b));
+      // positions strictly inside the span: b + 1 .. b + len - 1
+      if (len > 1) {
+        const uint64_t from = b + 1 >= 64 ? 0ull : (~0ull << (b + 1));
+        const uint64_t upto = b + len - 1 >= 63 ? ~0ull : ((2ull << (b + len - 1)) - 1ull);
+        covered |= from & upto;
+      }
+      if (b + len > 64) cross = true;  // x0 lies strictly inside
+    }
+    if (cross) {
+      const uint64_t safe = ~covered & 0xFFFFFFFF00000000ull;  // (a literal is at most 32 bytes long)
+      if (!safe) {
+        teddy_lane_cold(a, cb, cls0, sbits, x0, x1);
+        return;
+      }
+      pos = wp + (63 - __clzll((long long)safe));
+      w = pw;
+    }
+  }
+  for (; w < own_hi; w++) {
+    const int64_t wp = cb + (int64_t)w * 64;
+    uint64_t c = cls0[w + w / K].a;
+    if (wp < pos) c = pos - wp >= 64 ? 0ull : (c & (~0ull << (pos - wp)));
+    while (c) {
+      const int b = __ffsll((long long)c) - 1;
+      c &= c - 1ull;
+      const int64_t s = wp + b;
+      if (s < pos) continue;  // inside the match before
+      const int64_t e = teddy_verify_g(a, s, false);
+      if (e < 0) continue;
+      if (s >= x0) teddy_record(cls0, sbits, cb, s, e);
+      pos = e;
+    }
+  }
+}
+#endif  // CGX_TEDDY
+
 // ---- two-level look-back ------------------------------------------------------------------------------
 // Chunk c publishes its match count in status[c] (flag LB_AGG).  Chunks form groups of 32; the
 // warp that finishes a group's last chunk publishes the group's sum in gstatus[g] (LB_AGG), and
@@ -834,7 +1073,7 @@ __device__ __forceinline__ void extract_direct(const ScanArgs& a, const Slot* ar
   const Slot* res = arr + lane * (K + 1);
   int64_t* os = a.out + 2 * (excl + rk);
   int64_t* oe = a.out + 2 * (excl + rke) + 1;
-  const int64_t wb = chunk * (int64_t)CHUNKB + a.base + (int64_t)lane * (K * 64);
+  const int64_t wb = chunk_origin(chunk) + a.base + (int64_t)lane * (K * 64);
   if ((int64_t)(excl + cnt) <= a.cap) extract_words<false>(a, res, wb, os, oe);  // the usual case: everything fits
   else extract_words<true>(a, res, wb, os, oe);
 }
@@ -898,7 +1137,7 @@ __device__ __forceinline__ void extract_staged(WarpSmem& ws, const Slot* all, in
 // staged matches of a resolved chunk -> int64 pairs in global match order (coalesced 16-byte stores)
 __device__ __forceinline__ void write_out(const ScanArgs& a, const WarpSmem& ws, int sb, int64_t chunk, unsigned n,
                                           unsigned long long excl, int lane) {
-  const int64_t b = chunk * (int64_t)CHUNKB + a.base;
+  const int64_t b = chunk_origin(chunk) + a.base;
   const uint16_t* ss = ws.stS[sb];
   const uint16_t* se = ws.stE[sb];
   if ((int64_t)(excl + n) <= a.cap) {  // the usual case: the whole chunk fits the output
@@ -931,6 +1170,13 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
   if (tid < 2 * FW_WARPS) cs.mail[tid >> 1][tid & 1].state = 0;
   if (tid < 4) cs.tk[tid] = 0ull;
   if (tid < 2) cs.gang_acc[tid] = 0ull;
+#ifdef CGX_TEDDY
+  for (int i = tid; i < 256; i += FW_THREADS) {
+    const uint32_t t = a.teddy.fp[i];
+    cs.tfa[i] = (uint16_t)(t & 0xFFFFu);
+    cs.tfb[i] = (uint16_t)(t >> 16);
+  }
+#endif
   static_assert(2 * FW_WARPS <= FW_THREADS, "one thread per mail slot at start-up");
   if (warp < FW_WARPS && lane == 0) {
 #pragma unroll
@@ -997,7 +1243,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
   int pf_left = 0;
   bool pf_whole = false;
   auto prefetch_chunk = [&](unsigned chunk) {
-    const int64_t cbeg = chunk * (int64_t)CHUNKB;
+    const int64_t cbeg = chunk_origin(chunk);
     pf_src = a.h + cbeg;
     pf_left = TPC;
     pf_whole = cbeg + WINDOW <= a.n;
@@ -1077,7 +1323,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     }
     // matches of a replayed segment that end beyond the bitmap: found again, stored after the others
     if (lane == 0 && ws.far_cnt[b])
-      replay_cold(a, chunk * (int64_t)CHUNKB, nullptr, ws.far_from[b], ws.far_stop[b], a.out, excl + nbits, nullptr);
+      replay_cold(a, chunk_origin(chunk), nullptr, ws.far_from[b], ws.far_stop[b], a.out, excl + nbits, nullptr);
     __syncwarp();
     if (lane == 0) m.state = 0;
     __syncwarp();
@@ -1131,11 +1377,11 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       cur = nxt;
       continue;
     }
-    const int64_t cb = cur * (int64_t)CHUNKB;
+    const int64_t cb = chunk_origin(cur);
     // the next chunk is known one chunk ahead: its bytes are asked into L2 now (no shared memory
     // needed for that distance), the window ring then only has to cover the L2 latency
     if (nxt < nch && lane == 0) {
-      const int64_t nb = nxt * (int64_t)CHUNKB;
+      const int64_t nb = chunk_origin(nxt);
       const int64_t left = a.n - nb;
       const uint32_t bytes = left >= WINDOW ? (uint32_t)WINDOW : (uint32_t)(left & ~(int64_t)15);
       if (bytes) tma_prefetch_l2(a.h + nb, bytes);
@@ -1158,7 +1404,12 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         const int t = t0 + b;
         mbar_wait(&ws.mbar[b], rpar);
         uint64_t cm[4];
+#ifdef CGX_TEDDY
+        cm[0] = teddy_piece(ws.win[b], lrot, cs.tfa, cs.tfb);
+        cm[1] = 0ull;  // (the ends bitmap starts empty)
+#else
         classify_piece(f, ws.win[b], lrot, one, cm);
+#endif
         // every lane holds its piece in registers: the buffer can take the tile NB ahead
         __syncwarp();
         if (pf_left == 0 && t + NB == TPC && nxt < nch) prefetch_chunk(nxt);  // the ring moves on to the next chunk
@@ -1166,18 +1417,46 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         if (!whole) {
           // bytes at or beyond the end of input belong to no class.  Reversed bit r <=> byte 63 - r
           const int64_t v = a.n - (cb + (int64_t)t * TILE + lane * 64);  // valid bytes of this piece
+#ifdef CGX_TEDDY
+          cm[0] &= v >= 64 ? ~0ull : (v <= 0 ? 0ull : ((1ull << v) - 1ull));  // (forward orientation)
+#else
           const uint64_t m = v >= 64 ? ~0ull : (v <= 0 ? 0ull : (~0ull << (64 - v)));
 #pragma unroll
           for (int c = 0; c < 4; c++) cm[c] &= m;
+#endif
         }
         dst[0] = Slot{cm[0], cm[1]};
         if (NPAIR > 1) dst[NSLOTS1] = Slot{cm[2], cm[3]};
+#ifdef CGX_TEDDY
+        ws.mk[dst - &cls[0][0]] = 0ull;  // the starts bitmap of the chunk
+#endif
         dst += 32 + 32 / K;
       }
       rpar ^= 1u;
     }
     __syncwarp();
 
+#ifdef CGX_TEDDY
+    // ================= phase B: every lane runs the reference loop over its own words =================
+    const int s0 = lane * (K + 1);
+    unsigned cS = 0u, far = 0u;
+    int64_t rp_from = 0, rp_stop = 0;
+    {
+      const int o = cur == 0u ? 0 : 1;  // first owned word of the window
+      const int own_lo = K * lane + o;
+      int own_hi = own_lo + K;
+      if (own_hi > o + NWORDS - 2) own_hi = o + NWORDS - 2;
+      teddy_lane(a, cb, cls[0], ws.mk, own_lo, own_hi);
+      __syncwarp();
+      // the starts move next to the ends: slot = (starts, ends), as the output stage expects
+      for (int j = 0; j < K; j++) {
+        const uint64_t sj = ws.mk[s0 + j];
+        cls[0][s0 + j].a = sj;
+        cS += __popcll(sj);
+      }
+      __syncwarp();
+    }
+#else
     // ================= phase B: lane-serial marker sweeps over K words + the neighbour's first ======
     // lane 31's neighbour word would lie outside the window: its own last word is the overlap, and
     // where the others read their neighbour's word it reads the all-zero slot NSLOTS
@@ -1330,6 +1609,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       cS = 0u;
       for (int j = 0; j < K; j++) cS += __popcll(cls[0][s0 + j].a);
     }
+#endif  // !CGX_TEDDY
     // ---- counts and ranks ----
     uint32_t x = cS;
     const uint32_t mine = x;

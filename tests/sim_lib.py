@@ -85,3 +85,39 @@ def scan(pattern, hay, mode=0, cap=None, grid=2, base=0, pad=ord("1"), jit=False
     global last_diag
     last_diag = {"serial": int(res[2]), "redo": int(res[3])}
     return total, int(res[1]), out[: min(total, cap)]
+
+
+_teddy = None
+
+
+def teddy_lib():
+    global _teddy
+    if _teddy is None:
+        subprocess.check_call(["make", "-C", _DIR, "teddy"], stdout=subprocess.DEVNULL)
+        L = C.CDLL(os.path.join(_DIR, "_build", "libcgxsim_teddy.so"))
+        L.cgxsim_scan_teddy.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                        C.c_void_p, C.c_int64, C.POINTER(C.c_uint64), C.c_uint, C.c_int, C.c_int]
+        _teddy = L
+    return _teddy
+
+
+def scan_teddy(pattern, hay, mode=0, cap=None, grid=2, base=0, after=0, pad=ord("e"), launches=2):
+    """The multi-literal flavour of the kernel (scan_teddy.cu) on the emulator: (total, flag, pairs)."""
+    if isinstance(pattern, str):
+        pattern = pattern.encode()
+    a = np.frombuffer(bytes(hay), dtype=np.uint8) if not isinstance(hay, np.ndarray) else np.ascontiguousarray(hay)
+    n = a.size
+    if cap is None:
+        cap = n + 16
+    out = np.full((max(cap, 1), 2), -7, dtype=np.int64)
+    res = (C.c_uint64 * 4)()
+    r = teddy_lib().cgxsim_scan_teddy(pattern, len(pattern), a.ctypes.data if n else None, n, base, after, mode,
+                                      out.ctypes.data, cap, res, grid, pad, launches)
+    if r == -2:
+        raise NotEligible(pattern)
+    if r == -1:
+        raise RuntimeError("compile failed: %r" % pattern)
+    if r != 0:
+        raise RuntimeError("emulated launch left dirty scratch behind (code %d): %r" % (r, pattern))
+    total = int(res[0])
+    return total, int(res[1]), out[: min(total, cap)]

@@ -45,6 +45,36 @@ def _properties(out, total, base, n):
     assert bool((p[1:, 0] >= p[:-1, 1]).all())   # ascending and non-overlapping
 
 
+def test_one_regex_scans_haystacks_of_different_sizes():
+    """The look-back words and group accumulators of a regex survive from launch to launch (epochs,
+    self-cleaning): a regex that scans haystacks of different sizes — the pieces of a pipelined host
+    call — must find them in the same place every time, and a host call over several pieces must
+    equal the device scan of the whole."""
+    from oracle_lib import Oracle
+    for pat, kind, lits in [(IP, cg.SYNTH_LOG, None), ("|".join(x.decode() for x in LIT16), cg.SYNTH_TEXT, LIT16)]:
+        r = cg.Compile(pat)
+        o = Oracle(pat)
+        for blocks in [5000, 700, 9000, 64, 9000, 3, 20000]:
+            n = blocks * 4096
+            t = dev_corpus(kind, 77, n, literals=lits)
+            out, total = _scan_all(r, t)
+            w = min(n, 64 * 4096)
+            hay = cg.synth_host(kind, 77, w, first_block=0, literals=lits)
+            want = o.find_all(np.frombuffer(hay, dtype=np.uint8))
+            got = out[:total].cpu().numpy()
+            k = int(np.searchsorted(got[:, 0], w - 64))
+            kw = int(np.searchsorted(want[:, 0], w - 64))
+            assert np.array_equal(got[:k], want[:kw]), (pat, blocks)
+    # host entry: 700 MiB go through the pipeline in pieces of different sizes
+    n = 700 << 20
+    hay = cg.synth_host(cg.SYNTH_LOG, 5, n)
+    r = cg.Compile(IP)
+    got = r.find_all_index_array(hay)
+    t = torch.from_numpy(np.frombuffer(hay, dtype=np.uint8).copy()).cuda()
+    out, total = _scan_all(r, t)
+    assert total == len(got) and np.array_equal(out[:total].cpu().numpy(), got)
+
+
 def test_ns_ip_regex_beyond_4gib():
     """North-star pattern on a 6 GiB shard that sits at block 1<<22 of the logical corpus: matches
     whose offset INSIDE the buffer exceeds 4 GiB are compared with the oracle."""
