@@ -96,6 +96,14 @@ struct cgx_regex {
   // flat deterministic patterns run on the bitstream kernel (scan_bits.cu); CGX_BITSTREAM=0 or
   // cgx_debug_set_bitstream keep them on the candidate/DFA kernel (A/B runs, tests of both paths)
   bool bitstream = true;
+  // literal sets: scan_teddy.cu (the bitstream kernel's skeleton) instead of the scan_dfa.cu engine.
+  // Off by default: measured slower on B200 (C3 562 vs 891 GB/s, C5 385 vs 964 GB/s) — its per-lane
+  // verification through global memory is latency-bound at 6 of 32 lanes.
+  // CGX_TEDDY2=1 or cgx_debug_set_bitstream(re, 3) switch it on.
+  bool teddy2 = [] {
+    const char* e = getenv("CGX_TEDDY2");
+    return e && e[0] == '1';
+  }();
   // NVRTC-specialised build of that kernel for this pattern: 0 = not tried yet, 1 = in use,
   // -1 = unavailable (the generic nvcc-built kernel runs; jit_error says why)
   int jit_state = 0;
@@ -406,6 +414,7 @@ long cgx_debug_jit_compile(cgx_regex* re, char* cubin_out, size_t cap) {
 int cgx_debug_set_bitstream(cgx_regex* re, int on) {
   const int was = re->bitstream ? 1 : 0;
   re->bitstream = on != 0;
+  re->teddy2 = on == 3;  // literal sets on the bitstream skeleton (scan_teddy.cu) instead of scan_dfa.cu
   if (on == 2) {  // bitstream engine, but the generic nvcc-built kernel instead of the NVRTC one
     re->jit_state = -1;
     re->jit_error = "specialisation switched off by cgx_debug_set_bitstream(2)";
@@ -455,9 +464,9 @@ static int scan_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t ba
     return !(e && e[0] == '0');
   }();
   const bool use_flat = c.kind == ENG_DFA && c.flat.bs_ok && re->bitstream && bs_env;
-  // literal sets run on the bitstream kernel's skeleton (scan_teddy.cu) when no literal is longer than
-  // 32 bytes (its safe-point argument); cgx_debug_set_bitstream(0) keeps them on the scan_dfa.cu engine
-  const bool use_teddy2 = c.kind == ENG_TEDDY && c.teddy.max_len <= 32 && re->bitstream && bs_env;
+  // literal sets can run on the bitstream kernel's skeleton (scan_teddy.cu) when no literal is longer
+  // than 32 bytes (its safe-point argument); opt-in, see cgx_regex::teddy2
+  const bool use_teddy2 = c.kind == ENG_TEDDY && c.teddy.max_len <= 32 && re->teddy2;
   // the specialised kernel of this pattern and mode (built on first use); it knows its own chunk size
   if (use_flat && re->jit_state >= 0) {
     if (!re->jit[mode]) re->jit[mode] = GetJitKernel(c.flat, mode, re->jit_error);

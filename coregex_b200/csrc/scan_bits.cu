@@ -212,7 +212,7 @@ struct WarpSmem {
   // A chunk's matches wait here (chunk-relative u16 offsets, in match order) for the chunk's global
   // offset while the next chunk is scanned: two buffers.  A chunk with more than CAP matches keeps
   // its bitmaps instead and waits for its offset on the spot.
-  uint16_t stS[NST][CAP], stE[NST][CAP];
+  alignas(8) uint16_t st[NST][2][CAP];  // [buffer][starts | ends]; also the scratch of replay_bits
   uint64_t mbar[NB];
   // matches of a serially replayed segment that end beyond the chunk's bitmap (per staging buffer):
   // found again, and stored, when the chunk's offset is known
@@ -241,6 +241,9 @@ struct CtaSmem {
   // bucket masks per byte value of fingerprint byte 0 / byte 1 (reference prefilter/teddy.go:271-311
   // buildMasks, the two nibble tables of a position folded into one byte table)
   uint16_t tfa[256], tfb[256];
+  // the same for the third byte (every literal has three bytes or more, teddy.go:NewTeddy): cuts the
+  // candidates that reach verification by an order of magnitude
+  uint16_t tfc[256];
 #endif
 };
 
@@ -617,10 +620,13 @@ __device__ __noinline__ unsigned replay_cold(const ScanArgs& a, int64_t cb, Slot
 // does).  Returns false when the stretch is longer than MAXW words or turns out misordered: the
 // caller then takes the reference loop (replay_cold).
 constexpr int RB_MAXW = 8;
+static_assert(2 * CAP * 2 >= RB_MAXW * 7 * 8, "replay_bits keeps its words in a staging buffer");
 __device__ __noinline__ bool replay_bits(const ScanArgs& a, const FlatDev& f, int64_t cb, Slot* res, int64_t from,
-                                         int64_t stop_min, uint32_t one, unsigned* far_out) {
-  uint64_t cr[RB_MAXW][4];  // class words, reversed orientation
-  uint64_t mk[RB_MAXW];
+                                         int64_t stop_min, uint32_t one, uint64_t* scratch, unsigned* far_out) {
+  // (shared-memory scratch, not local arrays: a stack frame in this cold function cost the hot loop
+  // 4 % on B200)
+  uint64_t(*cr)[4] = reinterpret_cast<uint64_t(*)[4]>(scratch);  // class words, reversed orientation
+  uint64_t* mk = scratch + RB_MAXW * 4;
   const int64_t w0 = (from - cb) >> 6;
   int nw = 0;
   int last_sync = -1;  // bit (forward orientation) of the closing sync byte in word nw - 1
@@ -663,7 +669,8 @@ __device__ __noinline__ bool replay_bits(const ScanArgs& a, const FlatDev& f, in
   pass_reset(st);
   uint32_t in = 0u, c0hi = 0u;
   uint64_t badbits = 0ull;
-  uint64_t Sw[RB_MAXW], Ew[RB_MAXW];
+  uint64_t* Sw = scratch + RB_MAXW * 5;
+  uint64_t* Ew = scratch + RB_MAXW * 6;
   for (int i = 0; i < nw; i++) {
     uint64_t c[4];
 #pragma unroll
@@ -725,29 +732,28 @@ __device__ __noinline__ bool replay_bits(const ScanArgs& a, const FlatDev& f, in
 // quarters are evaluated one by one (the byte after a quarter comes from shared memory), packed as
 // if load j were quarter j and put in place by two byte permutes.
 __device__ __forceinline__ uint64_t teddy_piece(const uint8_t* win, const LaneRot& lr, const uint16_t* tfa,
-                                                const uint16_t* tfb) {
+                                                const uint16_t* tfb, const uint16_t* tfc) {
   uint32_t f16[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     const uint32_t qoff = lr.o0 ^ (uint32_t)(j << 4);  // offset of the quarter load j reads
     const uint4 v = *reinterpret_cast<const uint4*>(win + qoff);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    // the byte after the quarter; the one after the tile's last byte is not here: every bucket passes
-    const uint32_t nb_b = qoff + 16u < (uint32_t)TILE ? (uint32_t)tfb[win[qoff + 16u]] : 0xFFFFu;
+    // the two bytes after the quarter; those after the tile's last byte are not here: every bucket passes
+    const bool more = qoff + 16u < (uint32_t)TILE;
+    const uint32_t n1 = more ? (uint32_t)win[qoff + 16u] : 0u, n2 = more ? (uint32_t)win[qoff + 17u] : 0u;
+    uint32_t bb[18];
+#pragma unroll
+    for (int k = 0; k < 16; k++) bb[k] = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+    bb[16] = n1;
+    bb[17] = n2;
     uint32_t m = 0u;
-    uint32_t prev_a = tfa[w[0] & 0xFFu];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-      uint32_t tb, ta = 0u;
-      if (k < 15) {
-        const uint32_t b = (w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xFFu;
-        tb = tfb[b];
-        ta = tfa[b];
-      } else {
-        tb = nb_b;
-      }
-      if (prev_a & tb) m |= 1u << k;
-      prev_a = ta;
+      const uint32_t ta = tfa[bb[k]];
+      const uint32_t tb = (k + 1 < 16 || more) ? (uint32_t)tfb[bb[k + 1]] : 0xFFFFu;
+      const uint32_t tc = (k + 2 < 16 || more) ? (uint32_t)tfc[bb[k + 2]] : 0xFFFFu;
+      if (ta & tb & tc) m |= 1u << k;
     }
     f16[j] = m;
   }
@@ -789,10 +795,11 @@ __device__ __forceinline__ bool teddy_lit_equal(const ScanArgs& a, int64_t p, in
 // Which literal stands at p?  Returns the match end or -1.  SIMD regime: buckets low to high,
 // insertion order inside a bucket (reference prefilter/teddy.go:415-428, :532-550); scalar regime
 // (fewer than 16 bytes left from the search start, :447-458): plain literal order.
-__device__ __noinline__ int64_t teddy_verify_g(const ScanArgs& a, int64_t p, bool scalar) {
+__device__ __noinline__ int64_t teddy_verify_g(const ScanArgs& a, const uint16_t* tfc, int64_t p, bool scalar) {
   const TeddyDev& t = a.teddy;
-  if (p + 2 > a.n) return -1;
-  uint32_t mask = (__ldg(t.fp + __ldg(a.h + p)) & 0xFFFFu) & (__ldg(t.fp + __ldg(a.h + p + 1)) >> 16);
+  if (p + 3 > a.n) return -1;  // (every literal has three bytes or more)
+  uint32_t mask = (__ldg(t.fp + __ldg(a.h + p)) & 0xFFFFu) & (__ldg(t.fp + __ldg(a.h + p + 1)) >> 16) &
+                  (uint32_t)tfc[__ldg(a.h + p + 2)];
   if (!mask) return -1;
   const uint64_t hay8 = teddy_load8(a, p);
   int len;
@@ -817,18 +824,48 @@ __device__ __forceinline__ void teddy_record(Slot* cls0, uint64_t* sbits, int64_
   smem_or64(&sbits[ws + ws / K], (int)((s - cb) & 63));
   smem_or64(&cls0[we + we / K].b, (int)((e - cb) & 63));
 }
-// Cold: the reference loop for the starts in [x0, x1) from a position that is safe by construction —
-// the byte after the last record delimiter before x0 (no literal contains it) — through global
-// memory.  Used when the word before a lane's region offers no safe point and near the end of the
-// haystack, where the verify order depends on the distance from the search start to the end.
-__device__ __noinline__ void teddy_lane_cold(const ScanArgs& a, int64_t cb, Slot* cls0, uint64_t* sbits, int64_t x0,
-                                             int64_t x1) {
-  int64_t pos = x0;
-  while (pos > 0 && __ldg(a.h + pos - 1) != a.delim) pos--;
-  const TeddyDev& t = a.teddy;
+// Cold: the reference loop for the starts in [x0, x1) through global memory, with the verify order
+// that the distance from each search start to the end of the haystack asks for.  Used near the end
+// of the haystack and when the word before a lane's region offers no safe point.  It finds its own
+// safe point by walking back 32 bytes at a time: a position q is safe when no span that starts in
+// [q - 64, q) crosses it (spans that start earlier end before it: literals are at most 32 bytes
+// long); otherwise any position of [q - 32, q) strictly inside none of those spans is.
+__device__ __forceinline__ bool teddy_is_candidate(const ScanArgs& a, int64_t p) {
+  return p + 2 <= a.n &&
+         ((__ldg(a.teddy.fp + __ldg(a.h + p)) & 0xFFFFu) & (__ldg(a.teddy.fp + __ldg(a.h + p + 1)) >> 16)) != 0u;
+}
+__device__ __noinline__ void teddy_lane_cold(const ScanArgs& a, const uint16_t* tfc, int64_t cb, Slot* cls0,
+                                             uint64_t* sbits, int64_t x0, int64_t x1) {
+  int64_t pos = 0;
+  for (int64_t q = x0; q > 0; q -= 32) {
+    const int64_t lo = q >= 64 ? q - 64 : 0;
+    uint64_t covered = 0ull;  // bit i <=> position lo + i lies strictly inside a span
+    bool cross = false;
+    for (int64_t p = lo; p < q; p++) {
+      if (!teddy_is_candidate(a, p)) continue;
+      const int64_t e = teddy_verify_g(a, tfc, p, false);
+      if (e < 0) continue;
+      for (int64_t i = p + 1; i < e && i < q; i++) covered |= 1ull << (i - lo);
+      if (e > q) cross = true;
+    }
+    if (!cross) {
+      pos = q;
+      break;
+    }
+    int64_t u = -1;
+    for (int64_t i = q - 1; i >= q - 32 && i >= lo; i--)
+      if (!((covered >> (i - lo)) & 1ull)) {
+        u = i;
+        break;
+      }
+    if (u >= 0) {
+      pos = u;
+      break;
+    }
+  }
   for (int64_t p = pos; p < x1 && p + 2 <= a.n; p++) {
-    if (!((__ldg(t.fp + __ldg(a.h + p)) & 0xFFFFu) & (__ldg(t.fp + __ldg(a.h + p + 1)) >> 16))) continue;
-    const int64_t e = teddy_verify_g(a, p, a.n + a.after - pos < 16);
+    if (!teddy_is_candidate(a, p)) continue;
+    const int64_t e = teddy_verify_g(a, tfc, p, a.n + a.after - pos < 16);
     if (e < 0) continue;
     if (p >= x0) teddy_record(cls0, sbits, cb, p, e);
     pos = e;
@@ -837,14 +874,14 @@ __device__ __noinline__ void teddy_lane_cold(const ScanArgs& a, int64_t cb, Slot
 }
 // Phase B of a lane: the words [own_lo, own_hi) of the window at cb are its own, word own_lo - 1
 // (if any) is where it looks for its safe point.  cand: the chunk's candidate bitmap (slot .a).
-__device__ __forceinline__ void teddy_lane(const ScanArgs& a, int64_t cb, Slot* cls0, uint64_t* sbits, int own_lo,
-                                           int own_hi) {
+__device__ __forceinline__ void teddy_lane(const ScanArgs& a, const uint16_t* tfc, int64_t cb, Slot* cls0,
+                                           uint64_t* sbits, int own_lo, int own_hi) {
   if (own_hi <= own_lo) return;
   const int64_t x0 = cb + (int64_t)own_lo * 64, x1 = cb + (int64_t)own_hi * 64;
   if (x0 >= a.n) return;
   // near the end of the haystack the verify order depends on the search start: exact replay
   if (a.n + a.after - (x0 - 64) < 16 + 64 + (int64_t)(own_hi - own_lo) * 64 + 64) {
-    teddy_lane_cold(a, cb, cls0, sbits, x0, x1);
+    teddy_lane_cold(a, tfc, cb, cls0, sbits, x0, x1);
     return;
   }
   int64_t pos = x0;
@@ -858,7 +895,7 @@ __device__ __forceinline__ void teddy_lane(const ScanArgs& a, int64_t cb, Slot* 
     while (c) {
       const int b = __ffsll((long long)c) - 1;
       c &= c - 1ull;
-      const int64_t e = teddy_verify_g(a, wp + b, false);
+      const int64_t e = teddy_verify_g(a, tfc, wp + b, false);
       if (e < 0) continue;
       const int len = (int)(e - (wp + b));
       // positions strictly inside the span: b + 1 .. b + len - 1
@@ -872,7 +909,7 @@ __device__ __forceinline__ void teddy_lane(const ScanArgs& a, int64_t cb, Slot* 
     if (cross) {
       const uint64_t safe = ~covered & 0xFFFFFFFF00000000ull;  // (a literal is at most 32 bytes long)
       if (!safe) {
-        teddy_lane_cold(a, cb, cls0, sbits, x0, x1);
+        teddy_lane_cold(a, tfc, cb, cls0, sbits, x0, x1);
         return;
       }
       pos = wp + (63 - __clzll((long long)safe));
@@ -888,7 +925,7 @@ __device__ __forceinline__ void teddy_lane(const ScanArgs& a, int64_t cb, Slot* 
       c &= c - 1ull;
       const int64_t s = wp + b;
       if (s < pos) continue;  // inside the match before
-      const int64_t e = teddy_verify_g(a, s, false);
+      const int64_t e = teddy_verify_g(a, tfc, s, false);
       if (e < 0) continue;
       if (s >= x0) teddy_record(cls0, sbits, cb, s, e);
       pos = e;
@@ -1087,7 +1124,7 @@ __device__ __forceinline__ void extract_staged(WarpSmem& ws, const Slot* all, in
                                                int lane) {
   const Slot* res = all + lane * (K + 1);
   const int wb = lane * (K * 64);
-  uint16_t* os = ws.stS[sb];
+  uint16_t* os = ws.st[sb][0];
   if (r0 == 0u && !CGX_PARK) {
     os += rk;
 #pragma unroll 1
@@ -1119,8 +1156,8 @@ __device__ __forceinline__ void extract_staged(WarpSmem& ws, const Slot* all, in
     }
   }
   __syncwarp();
-  const uint16_t* ss = ws.stS[sb];
-  uint16_t* se = ws.stE[sb];
+  const uint16_t* ss = ws.st[sb][0];
+  uint16_t* se = ws.st[sb][1];
 #pragma unroll 1
   for (unsigned i = lane; i < n; i += 32) {
     const unsigned p = (unsigned)ss[i] + 1u;  // a match is not empty: its end lies after its start
@@ -1138,8 +1175,8 @@ __device__ __forceinline__ void extract_staged(WarpSmem& ws, const Slot* all, in
 __device__ __forceinline__ void write_out(const ScanArgs& a, const WarpSmem& ws, int sb, int64_t chunk, unsigned n,
                                           unsigned long long excl, int lane) {
   const int64_t b = chunk_origin(chunk) + a.base;
-  const uint16_t* ss = ws.stS[sb];
-  const uint16_t* se = ws.stE[sb];
+  const uint16_t* ss = ws.st[sb][0];
+  const uint16_t* se = ws.st[sb][1];
   if ((int64_t)(excl + n) <= a.cap) {  // the usual case: the whole chunk fits the output
     longlong2* o = reinterpret_cast<longlong2*>(a.out) + excl;
     for (unsigned i = lane; i < n; i += 32) o[i] = make_longlong2(b + ss[i], b + se[i]);
@@ -1175,6 +1212,13 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     const uint32_t t = a.teddy.fp[i];
     cs.tfa[i] = (uint16_t)(t & 0xFFFFu);
     cs.tfb[i] = (uint16_t)(t >> 16);
+    cs.tfc[i] = 0;
+  }
+  cgx_syncthreads();
+  if (tid == 0) {
+    for (int b = 0; b < a.teddy.nbuckets; b++)
+      for (int k = a.teddy.bucket_off[b]; k < a.teddy.bucket_off[b + 1]; k++)
+        cs.tfc[a.teddy.bytes[a.teddy.offs[a.teddy.order[k]] + 2]] |= (uint16_t)(1u << b);
   }
 #endif
   static_assert(2 * FW_WARPS <= FW_THREADS, "one thread per mail slot at start-up");
@@ -1405,7 +1449,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         mbar_wait(&ws.mbar[b], rpar);
         uint64_t cm[4];
 #ifdef CGX_TEDDY
-        cm[0] = teddy_piece(ws.win[b], lrot, cs.tfa, cs.tfb);
+        cm[0] = teddy_piece(ws.win[b], lrot, cs.tfa, cs.tfb, cs.tfc);
         cm[1] = 0ull;  // (the ends bitmap starts empty)
 #else
         classify_piece(f, ws.win[b], lrot, one, cm);
@@ -1446,7 +1490,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       const int own_lo = K * lane + o;
       int own_hi = own_lo + K;
       if (own_hi > o + NWORDS - 2) own_hi = o + NWORDS - 2;
-      teddy_lane(a, cb, cls[0], ws.mk, own_lo, own_hi);
+      teddy_lane(a, cs.tfc, cb, cls[0], ws.mk, own_lo, own_hi);
       __syncwarp();
       // the starts move next to the ends: slot = (starts, ends), as the output stage expects
       for (int j = 0; j < K; j++) {
@@ -1551,7 +1595,9 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
         cS += __popcll(S);
       }
     }
-    const bool bad = badbits != 0ull || in != 0u;
+    // (a match still open after the last word is what an open last segment looks like: that segment
+    // is replayed anyway, nothing is misordered)
+    const bool bad = badbits != 0ull || (in != 0u && !open);
     // ---- lanes that need the reference loop: clear what the sweeps left in the affected range ----
     const bool replay = bad || (open && seen);
 #ifdef CGX_DEBUG_PRINT
@@ -1597,12 +1643,28 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     unsigned far = 0u;
     if (__any_sync(FULL, replay)) {
       if (lane == 0) atomicAdd(&a.total[2], 1ull);  // diagnostics: chunks with a serial replay (cgx_debug_scratch)
-      if (replay) {
+#ifndef CGX_RBITS
+#define CGX_RBITS 1
+#endif
+      // open segments: bit-parallel replay, one lane at a time (the staging buffer is its scratch)
+      bool done_bits = false;
+      unsigned todo = CGX_RBITS ? __ballot_sync(FULL, replay && !bad) : 0u;
+      if (todo) {
+        if (P_MODE == M_FINDALL) flush(sb, true);  // (the buffer's previous chunk has to be out)
+        uint64_t* scratch = reinterpret_cast<uint64_t*>(&ws.st[CGX_PARK ? 0 : sb][0][0]);
+        while (todo) {
+          const int l = __ffs((int)todo) - 1;
+          todo &= todo - 1u;
+          if (lane == l && replay_bits(a, f, cb, cls[0], rp_from, rp_stop, one, scratch, &far)) {
+            done_bits = true;
+            atomicAdd(&a.total[3], 1ull);  // diagnostics: open segments replayed bit-parallel
+          }
+          __syncwarp();
+        }
+      }
+      if (replay && !done_bits) {
         unsigned nb = 0;
-        if (!bad && replay_bits(a, f, cb, cls[0], rp_from, rp_stop, one, &far))
-          atomicAdd(&a.total[3], 1ull);  // diagnostics: open segments replayed bit-parallel
-        else
-          far = replay_cold(a, cb, cls[0], rp_from, rp_stop, nullptr, 0ull, &nb);
+        far = replay_cold(a, cb, cls[0], rp_from, rp_stop, nullptr, 0ull, &nb);
       }
       __syncwarp();
       // bits may have landed in other lanes' words: count again

@@ -22,11 +22,11 @@ def find(marker):
 
 kstart = find("CGX_DYN_SMEM(smem_raw)")
 marks = [("prologue", "CGX_DYN_SMEM(smem_raw)"),
-         ("chunk head: flush (wait+extract)", "const int64_t cb = cur * (int64_t)CHUNKB;"),
+         ("chunk head: flush (wait+extract)", "const int64_t cb = chunk_origin(cur);"),
          ("phase A: tile loop", "phase A: classify the chunk's tiles"),
          ("sweep 1 (right to left)", "phase B: lane-serial marker sweeps"),
          ("sweep 2 (left to right)", "sweep 2, left to right"),
-         ("replay clear + merge + counts", "bad |= in != 0u;"),
+         ("replay clear + merge + counts", "const bool bad = badbits != 0ull"),
          ("publish / mail", "if (P_MODE == M_FINDALL) {\n      ws.rank"),
          ("epilogue", "if (P_MODE == M_FINDALL) {\n    flush(sb, true);")]
 bounds = sorted((find(m), n) for n, m in marks)

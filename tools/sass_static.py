@@ -31,11 +31,11 @@ def find(marker, start=0):
 
 # regions of the kernel body by marker comments (1-based line numbers, [lo, hi))
 marks = [("prologue", "CGX_DYN_SMEM(smem_raw)"),
-         ("chunk head (flush wait)", "const int64_t cb = cur * (int64_t)CHUNKB;"),
+         ("chunk head (flush wait)", "const int64_t cb = chunk_origin(cur);"),
          ("phase A: tile loop", "phase A: classify the chunk's tiles"),
          ("sweep 1 (right to left)", "phase B: lane-serial marker sweeps"),
          ("sweep 2 (left to right)", "sweep 2, left to right"),
-         ("replay clear + hand-over + counts", "bad |= in != 0u;"),
+         ("replay clear + hand-over + counts", "const bool bad = badbits != 0ull"),
          ("publish / mail", "if (P_MODE == M_FINDALL) {\n      const uint32_t rk"),
          ("epilogue", "if (P_MODE == M_FINDALL) {\n    flush(sb, true);")]
 kstart = find("CGX_DYN_SMEM(smem_raw)")
