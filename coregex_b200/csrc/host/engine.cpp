@@ -302,6 +302,15 @@ std::string JitHeader(const FlatDev& f) {
     for (int i = 0; i < f.fwd_nops; i++) mandatory += (f.fwd_ops[i] & 3) <= 1 ? 1 : 0;
     add("#define CGX_JIT_PARK %d\n", mandatory <= 2 && f.nclasses <= 2 ? 1 : 0);
   }
+  // classes that cover much of ordinary text (`[a-z]+/\d+`, `\w+@...`) leave long stretches without
+  // a sync byte: open segments get the bit-parallel replay (scan_bits.cu replay_bits).  Narrow
+  // classes (digits and dots) hardly ever do, and the mere presence of that code costs the hot loop
+  // 2 % on B200, so they keep the plain replay.
+  {
+    int nsync = 0;
+    for (int b = 0; b < 256; b++) nsync += (f.sync_lut[b >> 5] >> (b & 31)) & 1u;
+    add("#define CGX_RBITS %d\n", 256 - nsync >= 20 ? 1 : 0);
+  }
   // Every step of a pass owns one slot I of per-lane state (the carry and the shifted-out bits that
   // travel from one word to the next, scan_bits.cu PassState).  Right to left, a single byte of
   // class A followed by a run of class B (`B+ A` in the pattern) is one fused step over the

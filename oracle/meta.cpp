@@ -297,15 +297,20 @@ std::unique_ptr<Engine> Engine::Compile(const std::string& pattern, std::string&
       break;
     }
     case UseDFA:
-    case UseBoth:
-      // reference meta/compile.go:160-219: forward DFA + reverse DFA (BreakAtMatch=false);
-      // non-greedy patterns get no reverse DFA and fall back to PikeVM bounds.
+      // reference meta/compile.go:160-219: forward DFA + reverse DFA of the ReverseAnchored NFA
+      // (BreakAtMatch=false); non-greedy patterns get no reverse DFA and take PikeVM bounds.  The
+      // prefilter skip-ahead of find_indices.go:342-354 only moves the start of the same search.
       if (revsearch::BuildBidirectional(e->re_, e->nfa_, e->rev_nfa_)) {
         e->dfa_.reset(new LazyDFA(&e->nfa_, LazyConfig{true}));
         e->rev_dfa_.reset(new LazyDFA(&e->rev_nfa_, LazyConfig{false}));
       } else {
         e->strategy_exact_ = false;
       }
+      break;
+    case UseBoth:
+      // reference meta/compile.go:196 builds a reverse DFA for UseDFA only; the adaptive searcher
+      // (find_indices.go:406-460, PikeVM bounds from an estimated start) is not restated
+      e->strategy_exact_ = false;
       break;
     case UseReverseInner:
       e->rinner_ = revsearch::BuildReverseInner(e->re_, e->nfa_);
@@ -375,6 +380,11 @@ bool Engine::findDFAAt(const uint8_t* h, int64_t n, int64_t at, int64_t& s, int6
   if (end < 0) return false;
   if (end == at) {
     s = e = at;
+    return true;
+  }
+  if (nfa_.anchored) {  // reference meta/find_indices.go:697-700: no reverse search when always anchored
+    s = at;
+    e = end;
     return true;
   }
   int64_t st = rev_dfa_->SearchReverse(h, n, at, end);

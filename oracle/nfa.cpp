@@ -732,6 +732,249 @@ std::string CompileNFA(const Regexp* re, bool anchored_cfg, NFA& out) {
   return "";
 }
 
+// ---- reference nfa/reverse.go ------------------------------------------------------------------------
+namespace {
+enum EdgeKind : uint8_t { edgeByteRange = 0, edgeSparse, edgeEpsilon };
+struct RevEdge {
+  StateID from;
+  EdgeKind kind;
+  uint8_t lo, hi;
+};
+struct Reverser {
+  Builder b;
+  std::vector<std::vector<RevEdge>> edges;  // reverseEdges[to]
+  std::vector<StateID> map;                 // revStateMap (InvalidState = no entry)
+  std::vector<bool> has;
+
+  StateID AddFail() {
+    State s;
+    s.kind = StateFail;
+    return b.add(s);
+  }
+  // Go's map read of a missing key yields 0 (the reverse match state): reference code that does
+  // not check `ok` gets exactly that
+  StateID get0(StateID f) const { return has[f] ? map[f] : 0; }
+  void put(StateID f, StateID r) {
+    map[f] = r;
+    has[f] = true;
+  }
+  bool PatchSplit(StateID id, StateID l, StateID r) {
+    if (id >= b.states.size() || b.states[id].kind != StateSplit) return false;
+    b.states[id].left = l;
+    b.states[id].right = r;
+    return true;
+  }
+  // :598-614
+  StateID buildSplitChain(const std::vector<StateID>& t, size_t from = 0) {
+    const size_t n = t.size() - from;
+    if (n == 0) return AddFail();
+    if (n == 1) return t[from];
+    if (n == 2) return b.AddSplit(t[from], t[from + 1]);
+    StateID right = buildSplitChain(t, from + 1);
+    return b.AddSplit(t[from], right);
+  }
+  // :329-367
+  StateID allocatePlaceholder(const std::vector<RevEdge>& e) {
+    if (e.empty()) return AddFail();
+    int br = 0, eps = 0;
+    for (auto& x : e) (x.kind == edgeEpsilon ? eps : br)++;
+    if (br == 0 && eps > 0) return eps == 1 ? b.AddEpsilon(InvalidState) : b.AddSplit(InvalidState, InvalidState);
+    if (br == 1 && eps == 0) return b.AddByteRange(0, 0, InvalidState);
+    if (br > 0 && eps > 0) return b.AddSplit(InvalidState, InvalidState);
+    return b.AddSparse({Transition{0, 0, InvalidState}});
+  }
+  // :553-574
+  void updateByteRangeState(StateID id, uint8_t lo, uint8_t hi, StateID next) {
+    if (id >= b.states.size()) return;
+    b.bcs.set_range(lo, hi);
+    State& s = b.states[id];
+    if (s.kind == StateByteRange || s.kind == StateEpsilon) {
+      s.kind = StateByteRange;
+      s.lo = lo;
+      s.hi = hi;
+      s.next = next;
+    }
+  }
+  // :576-596
+  void updateSparseState(StateID id, const std::vector<Transition>& tr) {
+    if (id >= b.states.size()) return;
+    for (auto& t : tr) b.bcs.set_range(t.lo, t.hi);
+    State& s = b.states[id];
+    if (s.kind == StateSparse || s.kind == StateByteRange || s.kind == StateEpsilon) {
+      s.kind = StateSparse;
+      s.trans = tr;
+    }
+  }
+  // :488-514
+  void fillSparseState(StateID id, const std::vector<RevEdge>& br) {
+    std::vector<Transition> tr;
+    for (auto& e : br) tr.push_back(Transition{e.lo, e.hi, get0(e.from)});
+    updateSparseState(id, tr);
+  }
+  // :446-486
+  void fillEpsilonState(StateID id, const std::vector<RevEdge>& eps) {
+    if (eps.size() == 1) {
+      b.Patch(id, get0(eps[0].from));
+      return;
+    }
+    std::vector<StateID> t;
+    for (auto& e : eps)
+      if (has[e.from]) t.push_back(map[e.from]);
+    if (t.empty()) return;
+    if (t.size() == 1) {
+      b.Patch(id, t[0]);
+      return;
+    }
+    if (t.size() == 2) {
+      PatchSplit(id, t[0], t[1]);
+      return;
+    }
+    StateID right = buildSplitChain(t, 1);
+    PatchSplit(id, t[0], right);
+  }
+  // :516-551
+  void fillMixedState(StateID id, const std::vector<RevEdge>& br, const std::vector<RevEdge>& eps) {
+    StateID sparse = b.AddSparse({Transition{0, 0, InvalidState}});
+    fillSparseState(sparse, br);
+    std::vector<StateID> t;
+    for (auto& e : eps)
+      if (has[e.from]) t.push_back(map[e.from]);
+    StateID right;
+    if (t.empty()) {
+      updateSparseState(id, {});
+      fillSparseState(id, br);
+      return;
+    } else if (t.size() == 1) {
+      right = t[0];
+    } else {
+      right = buildSplitChain(t);
+    }
+    PatchSplit(id, sparse, right);
+  }
+  // :369-410
+  void fillReverseState(StateID id, const std::vector<RevEdge>& e) {
+    if (e.empty()) return;
+    std::vector<RevEdge> br, eps;
+    for (auto& x : e) (x.kind == edgeEpsilon ? eps : br).push_back(x);
+    if (br.empty()) return fillEpsilonState(id, eps);
+    if (br.size() == 1 && eps.empty()) return updateByteRangeState(id, br[0].lo, br[0].hi, get0(br[0].from));
+    if (!eps.empty()) return fillMixedState(id, br, eps);
+    fillSparseState(id, br);
+  }
+  // :412-444
+  void fillStartStateWithIncoming(StateID proxy, const std::vector<RevEdge>& e, StateID matchID) {
+    std::vector<StateID> t;
+    for (auto& x : e)
+      if (has[x.from]) t.push_back(map[x.from]);
+    if (t.empty()) return;
+    const StateID left = t.size() == 1 ? t[0] : buildSplitChain(t);
+    State& s = b.states[proxy];
+    s.kind = StateSplit;
+    s.left = left;
+    s.right = matchID;
+    s.next = InvalidState;
+  }
+};
+}  // namespace
+
+void ReverseNFAStates(const NFA& fwd, bool anchored, NFA& out) {
+  Reverser r;
+  const size_t ns = fwd.states.size();
+  r.edges.assign(ns, {});
+  r.map.assign(ns, InvalidState);
+  r.has.assign(ns, false);
+  // :83-137 collectReverseEdges
+  for (StateID from = 0; from < ns; from++) {
+    const State& s = fwd.states[from];
+    auto eps = [&](StateID to) {
+      if (to != InvalidState) r.edges[to].push_back(RevEdge{from, edgeEpsilon, 0, 0});
+    };
+    switch (s.kind) {
+      case StateByteRange:
+        if (s.next != InvalidState) r.edges[s.next].push_back(RevEdge{from, edgeByteRange, s.lo, s.hi});
+        break;
+      case StateSparse:
+        for (auto& t : s.trans)
+          if (t.next != InvalidState) r.edges[t.next].push_back(RevEdge{from, edgeSparse, t.lo, t.hi});
+        break;
+      case StateSplit:
+        eps(s.left);
+        eps(s.right);
+        break;
+      case StateEpsilon:
+      case StateCapture:
+      case StateLook:  // zero-width: an epsilon edge (the reverse automaton checks no assertion)
+        eps(s.next);
+        break;
+      default:
+        break;
+    }
+  }
+  const StateID matchID = r.b.AddMatch();
+  const StateID fa = fwd.start_anchored, fu = fwd.start_unanchored;
+  // :139-160 mapStartStates / mapSingleStartState
+  r.put(fa, !r.edges[fa].empty() ? r.b.AddEpsilon(matchID) : matchID);
+  if (!anchored && fu != fa) r.put(fu, !r.edges[fu].empty() ? r.b.AddEpsilon(matchID) : matchID);
+  // :178-238 findUnanchoredPrefixStates / findLoopStates
+  std::vector<bool> skip(ns, false);
+  if (anchored && fu != fa) {
+    skip[fu] = true;
+    if (fwd.states[fu].kind == StateSplit) {
+      const StateID start = fwd.states[fu].right;
+      if (start != InvalidState && !skip[start]) {
+        const State& s = fwd.states[start];
+        if ((s.kind == StateByteRange && s.next == fu) || (s.kind == StateSplit && (s.left == fu || s.right == fu)) ||
+            (s.kind == StateEpsilon && s.next == fu))
+          skip[start] = true;
+      }
+    }
+  }
+  // :162-176 allocatePlaceholders
+  for (StateID id = 0; id < ns; id++) {
+    if (skip[id]) continue;
+    if (!r.has[id]) r.put(id, r.allocatePlaceholder(r.edges[id]));
+  }
+  // :240-275 fillAllTransitions
+  for (StateID id = 0; id < ns; id++) {
+    if (skip[id]) continue;
+    const bool isStart = id == fa || (!anchored && id == fu);
+    const bool hasIncoming = !r.edges[id].empty();
+    if (isStart && !hasIncoming) continue;
+    if (!r.has[id]) continue;
+    if (isStart && hasIncoming) r.fillStartStateWithIncoming(r.map[id], r.edges[id], matchID);
+    else r.fillReverseState(r.map[id], r.edges[id]);
+  }
+  // :277-287 collectMatchStates, :616-634 buildReverseStarts
+  std::vector<StateID> starts;
+  size_t nmatch = 0;
+  StateID single = InvalidState;
+  for (StateID id = 0; id < ns; id++)
+    if (fwd.states[id].kind == StateMatch) {
+      nmatch++;
+      single = id;
+      if (r.has[id]) starts.push_back(r.map[id]);
+    }
+  StateID start;
+  if (nmatch == 0) start = r.AddFail();
+  else if (nmatch == 1) start = r.get0(single);
+  else start = r.buildSplitChain(starts);
+  // :289-308 buildFinalNFA
+  out = NFA();
+  out.states = std::move(r.b.states);
+  out.start_anchored = out.start_unanchored = start;
+  out.anchored = anchored || fwd.anchored;
+  out.capture_count = 0;
+  uint8_t cls = 0;
+  for (int i = 0; i < 256; i++) {
+    out.byte_classes[i] = cls;
+    if (r.b.bcs.bits[i]) cls++;
+  }
+  int mx = 0;
+  for (int i = 0; i < 256; i++)
+    if (out.byte_classes[i] > mx) mx = out.byte_classes[i];
+  out.alphabet_len = mx + 1;
+}
+
 std::string DumpNFA(const NFA& n) {
   std::string s;
   char buf[128];

@@ -81,4 +81,11 @@ std::string CompileNFA(const gosyntax::Regexp* re, bool anchored_cfg, NFA& out);
 
 std::string DumpNFA(const NFA& n);
 
+// reference nfa/reverse.go:8-81 (ReverseAnchored / Reverse -> reverseWithOptions) and the helpers it
+// calls (:83-634): the reverse NFA of `fwd` — transitions reversed, start and match swapped, look
+// assertions treated as epsilon edges, the (?s:.)*? prefix left out when `anchored`.  State
+// allocation order, placeholder kinds and byte-class registration follow the reference step by
+// step (they decide the lazy DFA's alphabet).
+void ReverseNFAStates(const NFA& fwd, bool anchored, NFA& out);
+
 }  // namespace oracle

@@ -218,7 +218,33 @@ int SelectReverseStrategy(const Regexp* re, const NFA& n, const Seq& prefix_lite
   return 0;
 }
 
-bool BuildBidirectional(const Regexp*, const NFA&, NFA&) { return false; }
+// reference meta/strategy.go:691-716
+static bool hasNonGreedyQuantifier(const Regexp* re) {
+  switch (re->op) {
+    case OpStar: case OpPlus: case OpQuest: case OpRepeat:
+      if (re->flags & NonGreedy) return true;
+      for (auto* s : re->sub)
+        if (hasNonGreedyQuantifier(s)) return true;
+      return false;
+    case OpConcat: case OpAlternate: case OpCapture:
+      for (auto* s : re->sub)
+        if (hasNonGreedyQuantifier(s)) return true;
+      return false;
+    default:
+      return false;
+  }
+}
+
+// reference meta/compile.go:176-219 buildReverseDFA, case UseDFA: forward DFA for the match end,
+// reverse DFA (ReverseAnchored NFA, BreakAtMatch off) for the match start; non-greedy patterns get
+// none and keep the PikeVM for the bounds.
+bool BuildBidirectional(const Regexp* re, const NFA& fwd, NFA& rev_out) {
+  if (hasNonGreedyQuantifier(re)) return false;
+  ReverseNFA(fwd, /*anchored=*/true, rev_out);
+  return true;
+}
+
+// ---- NOT RESTATED (see revsearch.h): these no-ops send the engine to the PikeVM restatement ----
 
 std::unique_ptr<ReverseInner> BuildReverseInner(const Regexp*, const NFA&) { return nullptr; }
 
@@ -227,7 +253,7 @@ bool ReverseInnerFindAt(ReverseInner&, PikeVM& pikevm, const uint8_t* h, int64_t
   return pikevm.SearchAt(h, n, at, s, e);
 }
 
-void ReverseNFA(const NFA&, bool, NFA&) {}
+void ReverseNFA(const NFA& fwd, bool anchored, NFA& out) { ReverseNFAStates(fwd, anchored, out); }
 
 }  // namespace revsearch
 }  // namespace oracle

@@ -1,12 +1,20 @@
 // oracle/revsearch.h — TEST INFRASTRUCTURE ONLY (parity oracle; never linked into the product).
 //
-// CPU restatement of the reference's reverse-search pieces:
+// What IS restated here: the SELECTION of the reference's reverse strategies
 //   reference meta/strategy.go:974-1083 (selectReverseStrategy) and its predicates :565-960
 //   reference literal/extractor.go:1010-1180 (ExtractInnerForReverseSearch, buildPrefix/SuffixAST)
-//   reference nfa/reverse.go:8-330 (Reverse / ReverseAnchored)
-//   reference meta/reverse_inner.go:95-190 (NewReverseInnerSearcher), :522-592 (findIndicesAtImpl)
-//   reference dfa/lazy/lazy.go:1947-2035 (SearchReverseLimited)
-//   reference meta/compile.go:185-219 (buildReverseDFA for UseDFA/UseBoth)
+// so that Oracle.strategy names what the reference would pick (tests/test_oracle_golden.py
+// test_strategy_table, tests/test_host_compile.py test_reference_strategy_agrees_with_oracle).
+//
+// What is NOT restated: the reverse SEARCHERS themselves —
+//   reference nfa/reverse.go:8-330 (Reverse / ReverseAnchored), meta/reverse_inner.go:95-190, :522-592,
+//   meta/reverse_suffix.go, meta/compile.go:185-219 (buildReverseDFA for UseDFA/UseBoth).
+// BuildBidirectional / BuildReverseInner / ReverseNFA below are deliberate NO-OPS that make the
+// engine fall back to the PikeVM restatement (leftmost-first) and clear `strategy_exact`: for
+// UseDFA / UseBoth / UseReverse* the oracle pins "what stdlib leftmost-first yields" — which the
+// reference's own tests assert those searchers equal — not the searchers' code paths.  PARITY FOR
+// THOSE STRATEGIES IS THEREFORE PINNED TO LEFTMOST-FIRST SEMANTICS, NOT TO THE REFERENCE ENGINES
+// (DESIGN.md §3).
 #pragma once
 #include <memory>
 
