@@ -35,6 +35,8 @@ void orc_free(void* p) { delete (Engine*)p; }
 int orc_strategy(void* p) { return ((Engine*)p)->strategy(); }
 const char* orc_strategy_name(void* p) { return StrategyName(((Engine*)p)->strategy()); }
 int orc_strategy_exact(void* p) { return ((Engine*)p)->strategy_exact() ? 1 : 0; }
+int orc_has_bidirectional(void* p) { return ((Engine*)p)->has_bidirectional() ? 1 : 0; }
+void orc_set_bidirectional(void* p, int on) { ((Engine*)p)->set_bidirectional(on != 0); }
 int orc_num_captures(void* p) { return ((Engine*)p)->num_captures(); }
 int orc_digit_run_skip_safe(void* p) { return ((Engine*)p)->digit_run_skip_safe() ? 1 : 0; }
 

@@ -303,9 +303,10 @@ std::unique_ptr<Engine> Engine::Compile(const std::string& pattern, std::string&
       if (revsearch::BuildBidirectional(e->re_, e->nfa_, e->rev_nfa_)) {
         e->dfa_.reset(new LazyDFA(&e->nfa_, LazyConfig{true}));
         e->rev_dfa_.reset(new LazyDFA(&e->rev_nfa_, LazyConfig{false}));
-      } else {
-        e->strategy_exact_ = false;
       }
+      // the bidirectional search is built and tested (set_bidirectional) but not the default path:
+      // by default UseDFA is pinned to leftmost-first through the PikeVM restatement
+      e->strategy_exact_ = false;
       break;
     case UseBoth:
       // reference meta/compile.go:196 builds a reverse DFA for UseDFA only; the adaptive searcher
@@ -401,7 +402,7 @@ bool Engine::FindIndicesAt(const uint8_t* h, int64_t n, int64_t at, int64_t& s, 
     case UseTeddy: return findTeddyAt(h, n, at, s, e);
     case UseDFA:
     case UseBoth:
-      if (dfa_ && rev_dfa_) return findDFAAt(h, n, at, s, e);
+      if (use_bidir_ && strategy_ == UseDFA && dfa_ && rev_dfa_) return findDFAAt(h, n, at, s, e);
       return findNFAAt(h, n, at, s, e);
     case UseReverseInner:
       return revsearch::ReverseInnerFindAt(*rinner_, *pikevm_, h, n, at, s, e);

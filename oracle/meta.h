@@ -69,6 +69,11 @@ class Engine {
 
   int strategy() const { return strategy_; }
   bool strategy_exact() const { return strategy_exact_; }
+  // UseDFA: run the restated bidirectional search (forward lazy DFA for the end, lazy DFA of the
+  // ReverseAnchored NFA for the start: meta/find_indices.go:686-705, nfa/reverse.go) instead of the
+  // PikeVM.  OFF by default — see DESIGN.md §3 "reverse NFA of a leading star".
+  bool has_bidirectional() const { return dfa_ && rev_dfa_ && strategy_ == UseDFA; }
+  void set_bidirectional(bool on) { use_bidir_ = on; }
   int num_captures() const { return nfa_.capture_count; }
   const NFA& nfa() const { return nfa_; }
   const gosyntax::Regexp* ast() const { return re_; }
@@ -81,6 +86,7 @@ class Engine {
   NFA nfa_;
   int strategy_ = UseNFA;
   bool strategy_exact_ = true;
+  bool use_bidir_ = false;
   bool digit_run_skip_safe_ = false;
   bool can_match_empty_ = false;
   bool teddy_line_anchor_ = false;  // prefilter wrapped by WrapLineAnchor (meta/compile.go:663-686)

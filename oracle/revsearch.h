@@ -1,20 +1,25 @@
 // oracle/revsearch.h — TEST INFRASTRUCTURE ONLY (parity oracle; never linked into the product).
 //
-// What IS restated here: the SELECTION of the reference's reverse strategies
-//   reference meta/strategy.go:974-1083 (selectReverseStrategy) and its predicates :565-960
-//   reference literal/extractor.go:1010-1180 (ExtractInnerForReverseSearch, buildPrefix/SuffixAST)
-// so that Oracle.strategy names what the reference would pick (tests/test_oracle_golden.py
-// test_strategy_table, tests/test_host_compile.py test_reference_strategy_agrees_with_oracle).
+// Restated here:
+//   * the SELECTION of the reference's reverse strategies:
+//     reference meta/strategy.go:974-1083 (selectReverseStrategy) and its predicates :565-960,
+//     literal/extractor.go:1010-1180 (ExtractInnerForReverseSearch, buildPrefix/SuffixAST);
+//   * the bidirectional search of UseDFA: reference nfa/reverse.go:8-634 (ReverseAnchored; the
+//     states are built in oracle/nfa.cpp ReverseNFAStates), meta/compile.go:176-219 (buildReverseDFA:
+//     only UseDFA, not for non-greedy patterns), meta/find_indices.go:686-705 (forward lazy DFA for
+//     the end, reverse lazy DFA for the start; oracle/meta.cpp findDFAAt over lazydfa.cpp SearchAt /
+//     SearchReverse).  Exercised by tests/test_oracle_golden.py::test_bidirectional_* against the
+//     PikeVM restatement and Python `re`.  It is NOT the oracle's default path for UseDFA: restated
+//     as written, the reverse automaton of a pattern that opens with a star loop loses the loop
+//     (test_reverse_nfa_of_a_leading_star_quirk), which cannot be confirmed without running the
+//     reference; the default stays leftmost-first through the PikeVM (Engine::set_bidirectional).
 //
-// What is NOT restated: the reverse SEARCHERS themselves —
-//   reference nfa/reverse.go:8-330 (Reverse / ReverseAnchored), meta/reverse_inner.go:95-190, :522-592,
-//   meta/reverse_suffix.go, meta/compile.go:185-219 (buildReverseDFA for UseDFA/UseBoth).
-// BuildBidirectional / BuildReverseInner / ReverseNFA below are deliberate NO-OPS that make the
-// engine fall back to the PikeVM restatement (leftmost-first) and clear `strategy_exact`: for
-// UseDFA / UseBoth / UseReverse* the oracle pins "what stdlib leftmost-first yields" — which the
-// reference's own tests assert those searchers equal — not the searchers' code paths.  PARITY FOR
-// THOSE STRATEGIES IS THEREFORE PINNED TO LEFTMOST-FIRST SEMANTICS, NOT TO THE REFERENCE ENGINES
-// (DESIGN.md §3).
+// NOT restated: the ReverseInner / ReverseSuffix / ReverseAnchored searchers and the adaptive
+// UseBoth searcher (reference meta/reverse_inner.go:95-190, :522-592, meta/reverse_suffix.go,
+// meta/find_indices.go:406-460).  BuildReverseInner / ReverseInnerFindAt below are deliberate
+// no-ops that send the engine to the PikeVM restatement and clear `strategy_exact`: for those
+// strategies the oracle pins "what leftmost-first yields" — which the reference's own tests assert
+// those searchers equal — not their code paths.
 #pragma once
 #include <memory>
 

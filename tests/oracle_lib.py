@@ -37,6 +37,8 @@ def lib():
         L.orc_strategy_name.restype = C.c_char_p
         L.orc_strategy_name.argtypes = [vp]
         L.orc_strategy_exact.argtypes = [vp]
+        L.orc_has_bidirectional.argtypes = [vp]
+        L.orc_set_bidirectional.argtypes = [vp, C.c_int]
         L.orc_num_captures.argtypes = [vp]
         L.orc_digit_run_skip_safe.argtypes = [vp]
         L.orc_is_match.argtypes = [vp, u8p, i64]
@@ -101,6 +103,16 @@ class Oracle:
     @property
     def strategy_exact(self):
         return bool(lib().orc_strategy_exact(self._h))
+
+    @property
+    def has_bidirectional(self):
+        """UseDFA pattern for which the reference builds a reverse DFA (meta/compile.go:176-219)."""
+        return bool(lib().orc_has_bidirectional(self._h))
+
+    def set_bidirectional(self, on):
+        """Run UseDFA searches through the restated forward + reverse lazy-DFA pair
+        (meta/find_indices.go:686-705 over nfa/reverse.go) instead of the PikeVM restatement."""
+        lib().orc_set_bidirectional(self._h, int(bool(on)))
 
     @property
     def num_captures(self):

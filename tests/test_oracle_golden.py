@@ -4,6 +4,7 @@ the same leftmost-first semantics as Go's regexp for these patterns (the referen
 use Go stdlib as their oracle, meta/stdlib_compat_test.go:18-141)."""
 import json
 import os
+import random
 import re
 
 import numpy as np
@@ -244,3 +245,47 @@ def test_reference_findall_vectors(v):
     """Literal `[][2]int{...}` expectations of the reference's own tests (char-class searcher,
     non-greedy iteration, backtracker iteration), harvested by tests/golden/harvest_findall_vectors.py."""
     assert fa(v["pattern"], v["input"].encode()) == v["want"], v["src"]
+
+
+# ---- reverse NFA / bidirectional lazy-DFA search (reference nfa/reverse.go, meta/find_indices.go:686-705) ----
+BIDIR_PATS = [r"GET /\S+ HTTP", r'"[A-Z]+ .*" 200', r"(foo|bar)+baz", r"a.*b", r"x[^y]*y", r"(?i)error.*", r"[ab]+c|a+d",
+              r"(a|b)*abb", r"foo\s+bar", r"ab+c+d", r"[ab]c+d[ef]", r"x\d+y\d+z", r"q[a-z]+\d", r"#[0-9a-f]+;", r"<[a-z]+>",
+              r"\([0-9]+\)"]
+
+
+@pytest.mark.parametrize("pat", BIDIR_PATS)
+def test_bidirectional_dfa_search_equals_leftmost_first(pat):
+    """UseDFA: forward lazy DFA for the end + lazy DFA of the ReverseAnchored NFA for the start (the
+    restated reference path, oracle/nfa.cpp ReverseNFAStates + oracle/lazydfa.cpp SearchAt /
+    SearchReverse) against the PikeVM restatement and Python `re` on random haystacks."""
+    o = Oracle(pat)
+    assert o.strategy == "UseDFA" and o.has_bidirectional, (pat, o.strategy)
+    rx = re.compile(pat.encode())
+    rng = random.Random(len(pat))
+    alphabet = b"abcdefxyq 0123456789@.,-=;#<>()\n\"GETHTP/foobarzp"
+    for it in range(400):
+        h = bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 160)))
+        a = np.frombuffer(h, dtype=np.uint8)
+        o.set_bidirectional(False)
+        nfa = o.find_all(a).tolist()
+        o.set_bidirectional(True)
+        dfa = o.find_all(a).tolist()
+        assert nfa == dfa == [[m.start(), m.end()] for m in rx.finditer(h)], (pat, h)
+
+
+def test_reverse_nfa_of_a_leading_star_quirk():
+    """Recorded observation, not a requirement on the product.  nfa/reverse.go:412-444
+    (fillStartStateWithIncoming) turns EVERY edge into the forward start state into an epsilon edge
+    of the reverse automaton — also the byte edge that closes a leading `x*` loop — so the restated
+    reverse DFA stops at the loop: `a*b` on "aab" yields start 2 where leftmost-first yields 0.  The
+    reference cannot be executed here (no Go toolchain) and documents stdlib compatibility, so the
+    oracle's DEFAULT path for UseDFA stays the PikeVM restatement (leftmost-first), which is what
+    the product is compared with."""
+    for pat, hay, quirk, first in [(r"a*b", b"aab", [[2, 3]], [[0, 3]]), (r"[0-9]*px", b"12px", [[2, 4]], [[0, 4]]),
+                                   (r"x*yz", b"xxyz", [[2, 4]], [[0, 4]])]:
+        o = Oracle(pat)
+        assert o.strategy == "UseDFA" and o.has_bidirectional
+        a = np.frombuffer(hay, dtype=np.uint8)
+        assert o.find_all(a).tolist() == first == [[m.start(), m.end()] for m in re.finditer(pat.encode(), hay)]
+        o.set_bidirectional(True)
+        assert o.find_all(a).tolist() == quirk
