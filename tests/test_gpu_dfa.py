@@ -476,3 +476,10 @@ def test_reference_findall_vectors_on_device(v):
     r.set_bitstream(1 if BITSTREAM else 0)
     got = r.FindAllIndex(v["input"].encode(), -1) or []
     assert got == v["want"], v["src"]
+
+
+def test_dangling_at_sign_vector():
+    # SURVEY §8a A9 (reference strategy UseReverseInner): an `@` that starts no match
+    r = cg.Compile(r"\w+@\w+\.\w+")
+    for hay, want in [(b"a@b c@d.e", [[4, 9]]), (b"@@a@b.c@", [[2, 7]]), (b"x@y z@w.", None), (b"a@b.c@d.e", [[0, 5]])]:
+        assert r.FindAllIndex(hay) == want

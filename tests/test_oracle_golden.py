@@ -289,3 +289,14 @@ def test_reverse_nfa_of_a_leading_star_quirk():
         assert o.find_all(a).tolist() == first == [[m.start(), m.end()] for m in re.finditer(pat.encode(), hay)]
         o.set_bidirectional(True)
         assert o.find_all(a).tolist() == quirk
+
+
+def test_dangling_at_sign_vector():
+    """`\\w+@\\w+\\.\\w+` selects UseReverseInner in the reference, whose searcher is not
+    restated (oracle/revsearch.h); the adversarial input with an `@` that starts no match is pinned
+    to leftmost-first semantics here and on the device (tests/test_gpu_dfa.py)."""
+    o = Oracle(r"\w+@\w+\.\w+")
+    assert not o.strategy_exact  # (the engine falls back to its PikeVM restatement and says so)
+    for hay, want in [(b"a@b c@d.e", [[4, 9]]), (b"@@a@b.c@", [[2, 7]]), (b"x@y z@w.", []), (b"a@b.c@d.e", [[0, 5]])]:
+        assert o.find_all(np.frombuffer(hay, dtype=np.uint8)).tolist() == want
+        assert [[m.start(), m.end()] for m in re.finditer(rb"\w+@\w+\.\w+", hay)] == want
