@@ -26,6 +26,26 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line
+# when NCCL_DEBUG is set in the environment): file descriptor 1 is pointed at stderr for the whole
+# run and the line goes out through a private copy of the original stdout.
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """(only when run as a program: tests import this module)"""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 PATTERN = r"\d+\.\d+\.\d+\.\d+"
 SEED = 0xC0FFEE
 GIB = 1 << 30
@@ -188,7 +208,7 @@ def run_reference(args):
                                    "no Go toolchain)" % (sample >> 20, threads)},
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def init_dist():
@@ -457,7 +477,7 @@ def main():
         "clocks": clocks, "gpu_launches": int(launches), "parity": parity, "e2e": e2e, "roofline": roof,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist:
         dist.destroy_process_group()
 
@@ -583,10 +603,11 @@ def main_c5(args):
                      "peak": peak, "unit": "GB/s", "frac": round((n + 16 * matches) / (per_rank[0][0] * 1e-3) / 1e9 / peak, 4),
                      "peak_source": peak_src, "traffic": None},
     }
-    print(json.dumps(line))
+    emit(line)
     if dist:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
+    claim_stdout()
     main()

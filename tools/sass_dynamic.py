@@ -27,7 +27,7 @@ marks = [("prologue", "CGX_DYN_SMEM(smem_raw)"),
          ("sweep 1 (right to left)", "phase B: lane-serial marker sweeps"),
          ("sweep 2 (left to right)", "sweep 2, left to right"),
          ("replay clear + merge + counts", "const bool bad = badbits != 0ull"),
-         ("publish / mail", "if (P_MODE == M_FINDALL) {\n      ws.rank"),
+         ("publish / mail", "if (P_MODE == M_FINDALL) {\n      const uint32_t rk"),
          ("epilogue", "if (P_MODE == M_FINDALL) {\n    flush(sb, true);")]
 bounds = sorted((find(m), n) for n, m in marks)
 
