@@ -178,6 +178,23 @@ int cgx_synth_device(int kind, uint64_t seed, uint64_t first_block, uint8_t* d_o
 int cgx_synth_host(int kind, uint64_t seed, uint64_t first_block, uint8_t* out, size_t len,
                    const uint8_t* literals, const int32_t* lit_offsets, int nlit);
 
+/* ---- the byte-search family of the reference's prefilter layer, device resident ------------------
+ * "The first position whose byte is in a set" — reference simd/memchr_amd64.go:67 Memchr, :114
+ * Memchr2, :159 Memchr3, simd/memchr_digit_amd64.go:17 MemchrDigit (:34 MemchrDigitAt = the same on
+ * the tail of the buffer), simd/memchr_class_amd64.go:35 MemchrWord, :58 MemchrNotWord, :76
+ * MemchrInTable, :90 MemchrNotInTable all are cgx_memchr_table_device with the right 256-entry
+ * table (non-zero = in the set); :202 MemchrPair and simd/memmem.go:53 Memmem have their own entry.
+ * d_h: device haystack, 16-byte aligned.  d_result: device int64[2]; [0] receives the index or -1
+ * (the reference's return value), [1] is scratch.  The scan stops shortly after the first hit.
+ * Needles of cgx_memmem_device are at most 256 bytes long (CGX_ERR_UNSUPPORTED beyond).           */
+int cgx_memchr_table_device(const uint8_t* d_h, size_t n, const uint8_t* table256, int64_t* d_result, void* stream);
+/* the same from position `at` on (absolute index back): MemchrDigitAt, memchr_digit_amd64.go:34 */
+int cgx_memchr_table_at_device(const uint8_t* d_h, size_t n, size_t at, const uint8_t* table256, int64_t* d_result,
+                               void* stream);
+int cgx_memchr_pair_device(const uint8_t* d_h, size_t n, uint8_t byte1, uint8_t byte2, int64_t offset,
+                           int64_t* d_result, void* stream);
+int cgx_memmem_device(const uint8_t* d_h, size_t n, const uint8_t* needle, size_t m, int64_t* d_result, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
