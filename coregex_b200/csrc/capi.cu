@@ -377,7 +377,18 @@ int cgx_set_longest(cgx_regex* re, int longest) {
   return CGX_OK;
 }
 const char* cgx_strategy(const cgx_regex* re) { return RefStrategyName(re->c->an.strategy); }
-const char* cgx_engine(const cgx_regex* re) { return re->c->engine_name.c_str(); }
+// The engine name says which kernel runs: "...+bitstream" is the NVRTC-specialised kernel; once a
+// device scan has found NVRTC unusable (no libnvrtc.so.12, compile error) the name becomes
+// "...+bitstream-generic" — the interpreting nvcc-built kernel, about a quarter of the speed
+// (cgx_last_error after cgx_debug_jit_state says why).
+const char* cgx_engine(const cgx_regex* re) {
+  if (re->jit_state < 0 && re->c->kind == ENG_DFA && re->c->flat.bs_ok) {
+    thread_local std::string name;
+    name = re->c->engine_name + "-generic";
+    return name.c_str();
+  }
+  return re->c->engine_name.c_str();
+}
 int cgx_num_captures(const cgx_regex* re) { return re->c->prog.num_captures; }
 uint64_t cgx_launch_count(const cgx_regex* re) { return re->launches.load(); }
 // 1: the NVRTC-specialised kernel is in use, -1: unavailable (generic kernel; cgx_last_error has
@@ -720,8 +731,11 @@ static size_t forced_piece() {
   return v;
 }
 
+// limit > 0: the caller wants the first `limit` matches only — no further piece is queued once
+// the pieces finished so far hold that many (the reference's loop stops at n matches,
+// meta/findall.go:176-290; pieces are in haystack order, so what they hold is a prefix).
 static int host_scan_pipelined(cgx_regex* re, const uint8_t* h, size_t len, int mode, int64_t* out, size_t cap,
-                               uint64_t result[2]) {
+                               uint64_t result[2], int64_t limit) {
   int r;
   if ((r = re->ensure_pipeline())) return r;
   const uint8_t delim = re->c->kind == ENG_TEDDY ? (uint8_t)'\n' : (uint8_t)re->c->delim;
@@ -827,6 +841,7 @@ static int host_scan_pipelined(cgx_regex* re, const uint8_t* h, size_t len, int 
       total += t;
       flag |= f;
       if (mode == CGX_MODE_ISMATCH && flag) stop = true;
+      if (limit > 0 && total >= (uint64_t)limit) stop = true;
       return CGX_OK;
     }
   };
@@ -847,13 +862,13 @@ static int host_scan_pipelined(cgx_regex* re, const uint8_t* h, size_t len, int 
 
 // host wrapper shared by is_match / count / find_all
 static int host_scan(cgx_regex* re, const uint8_t* h, size_t len, int mode, int64_t* out, size_t cap,
-                     uint64_t result[2]) {
+                     uint64_t result[2], int64_t limit = 0) {
   if (!re || (!h && len)) return CGX_ERR_ARGS;
   std::lock_guard<std::mutex> lk(re->mu);
   int r = re->ensure_device();
   if (r) return r;
   if (re->c->has_delim && len >= (forced_piece() ? 2 * forced_piece() : kPipelineMin))
-    return host_scan_pipelined(re, h, len, mode, out, cap, result);
+    return host_scan_pipelined(re, h, len, mode, out, cap, result, limit);
   if ((r = re->d_hay.ensure(len + 16))) return r;
   if (mode == CGX_MODE_FINDALL && cap && (r = re->d_out.ensure(cap * 16))) return r;
   cudaStream_t st = 0;
@@ -882,7 +897,7 @@ int cgx_count(cgx_regex* re, const uint8_t* h, size_t len, int64_t limit, size_t
   if (count) *count = 0;
   if (limit == 0) return CGX_OK;
   uint64_t res[2] = {0, 0};
-  int r = host_scan(re, h, len, CGX_MODE_COUNT, nullptr, 0, res);
+  int r = host_scan(re, h, len, CGX_MODE_COUNT, nullptr, 0, res, limit);
   if (r) return r;
   size_t c = (size_t)res[0];
   if (limit > 0 && c > (size_t)limit) c = (size_t)limit;
@@ -897,7 +912,7 @@ int cgx_find_all_index(cgx_regex* re, const uint8_t* h, size_t len, int64_t limi
   uint64_t res[2] = {0, 0};
   size_t want = cap;
   if (limit > 0 && (size_t)limit < want) want = (size_t)limit;
-  int r = host_scan(re, h, len, (out && want) ? CGX_MODE_FINDALL : CGX_MODE_COUNT, out, want, res);
+  int r = host_scan(re, h, len, (out && want) ? CGX_MODE_FINDALL : CGX_MODE_COUNT, out, want, res, limit);
   if (r) return r;
   size_t c = (size_t)res[0];
   if (limit > 0 && c > (size_t)limit) c = (size_t)limit;  // first `limit` matches are a prefix

@@ -69,8 +69,17 @@ def test_digit_and_word_classes():
 
 
 def test_memchr_pair():
-    # reference simd/memchr_amd64.go:180-221 (doc examples and edge rules)
-    assert simd.MemchrPair(b"contact@test.com for info", ord("@"), ord("c"), 9) == 7
+    # reference simd/memchr_test.go:684-711 (the doc example of memchr_amd64.go:196-200 — "@", "c", 9
+    # -> 7 — contradicts memchrPairGeneric, simd/memchr_generic_impl.go:253-266, and is not a test)
+    for hay, b1, b2, off, want in [(b"hello", "h", "e", 1, 0), (b"hello", "l", "o", 2, 2), (b"hello", "h", "o", 1, -1),
+                                   (b"hello", "x", "e", 1, -1), (b"hello", "h", "x", 1, -1), (b"", "a", "b", 1, -1),
+                                   (b"hello", "h", "h", 0, 0), (b"hello", "h", "e", 0, -1), (b"hi", "h", "i", 5, -1),
+                                   (b"hello", "h", "e", -1, -1), (b"test@example.com", "@", ".", 8, 4),
+                                   (b"http://localhost", ":", "/", 1, 4), (b'{"key": "value"}', '"', ":", 5, 1),
+                                   (b"abababab", "a", "b", 1, 0), (b"xxabxxab", "a", "b", 1, 2),
+                                   (b"a0123456789b", "a", "b", 11, 0), (b"xxxxxab", "a", "b", 1, 5), (b"ab", "a", "b", 1, 0)]:
+        assert simd.MemchrPair(hay, ord(b1), ord(b2), off) == want, (hay, b1, b2, off)
+    assert simd.MemchrPair(b"contact@test.com for info", ord("@"), ord("c"), 6) == 7
     assert simd.MemchrPair(b"abcabc", ord("a"), ord("c"), 2) == 0
     assert simd.MemchrPair(b"abxabc", ord("a"), ord("c"), 2) == 3
     assert simd.MemchrPair(b"abc", ord("a"), ord("c"), -1) == -1
