@@ -244,6 +244,10 @@ struct CtaSmem {
   // the same for the third byte (every literal has three bytes or more, teddy.go:NewTeddy): cuts the
   // candidates that reach verification by an order of magnitude
   uint16_t tfc[256];
+  // the literals as the verify wants them (at most 64: Fat Teddy's limit): first 8 bytes, byte mask,
+  // length, bucket-major order — a verify is one round trip to the haystack and shared-memory reads
+  unsigned long long tlit8[64], tmsk8[64];
+  uint16_t tlen[64], torder[64], tboff[17];
 #endif
 };
 
@@ -780,41 +784,46 @@ __device__ __forceinline__ uint64_t teddy_load8(const ScanArgs& a, int64_t p) {
     if (p + k < a.n) v |= (uint64_t)__ldg(a.h + p + k) << (8 * k);
   return v;
 }
-__device__ __forceinline__ bool teddy_lit_equal(const ScanArgs& a, int64_t p, int id, uint64_t hay8, int& len) {
-  const TeddyDev& t = a.teddy;
-  const int o = __ldg(t.offs + id);
-  len = __ldg(t.offs + id + 1) - o;
+// the engine's shared-memory tables (CtaSmem)
+struct TeddyTab {
+  const uint16_t *tfa, *tfb, *tfc;
+  const unsigned long long *lit8, *msk8;
+  const uint16_t *len, *order, *boff;
+};
+__device__ __forceinline__ bool teddy_lit_equal(const ScanArgs& a, const TeddyTab& tt, int64_t p, int id, uint64_t hay8,
+                                                int& len) {
+  len = tt.len[id];
+  if ((hay8 ^ tt.lit8[id]) & tt.msk8[id]) return false;
   if (p + len > a.n) return false;
-  if ((hay8 ^ __ldg(reinterpret_cast<const unsigned long long*>(t.lit8) + id)) &
-      __ldg(reinterpret_cast<const unsigned long long*>(t.lit8) + t.npat + id))
-    return false;
-  for (int k = 8; k < len; k++)
-    if (__ldg(a.h + p + k) != __ldg(t.bytes + o + k)) return false;
+  if (len > 8) {
+    const int o = __ldg(a.teddy.offs + id);
+    for (int k = 8; k < len; k++)
+      if (__ldg(a.h + p + k) != __ldg(a.teddy.bytes + o + k)) return false;
+  }
   return true;
 }
 // Which literal stands at p?  Returns the match end or -1.  SIMD regime: buckets low to high,
 // insertion order inside a bucket (reference prefilter/teddy.go:415-428, :532-550); scalar regime
-// (fewer than 16 bytes left from the search start, :447-458): plain literal order.
-__device__ __noinline__ int64_t teddy_verify_g(const ScanArgs& a, const uint16_t* tfc, int64_t p, bool scalar) {
-  const TeddyDev& t = a.teddy;
+// (fewer than 16 bytes left from the search start, :447-458): plain literal order.  One round trip
+// to the haystack (8 bytes); masks and literals come from shared memory.
+__device__ __noinline__ int64_t teddy_verify_g(const ScanArgs& a, const TeddyTab& tt, int64_t p, bool scalar) {
   if (p + 3 > a.n) return -1;  // (every literal has three bytes or more)
-  uint32_t mask = (__ldg(t.fp + __ldg(a.h + p)) & 0xFFFFu) & (__ldg(t.fp + __ldg(a.h + p + 1)) >> 16) &
-                  (uint32_t)tfc[__ldg(a.h + p + 2)];
-  if (!mask) return -1;
   const uint64_t hay8 = teddy_load8(a, p);
+  uint32_t mask = (uint32_t)tt.tfa[hay8 & 0xFFu] & tt.tfb[(hay8 >> 8) & 0xFFu] & tt.tfc[(hay8 >> 16) & 0xFFu];
+  if (!mask) return -1;
   int len;
   if (scalar) {
-    for (int id = 0; id < t.npat; id++)
-      if (teddy_lit_equal(a, p, id, hay8, len)) return p + len;
+    for (int id = 0; id < a.teddy.npat; id++)
+      if (teddy_lit_equal(a, tt, p, id, hay8, len)) return p + len;
     return -1;
   }
   while (mask) {
     const int b = __ffs((int)mask) - 1;
     mask &= mask - 1u;
-    if (b >= t.nbuckets) break;
-    const int k1 = __ldg(t.bucket_off + b + 1);
-    for (int k = __ldg(t.bucket_off + b); k < k1; k++)
-      if (teddy_lit_equal(a, p, (int)__ldg(t.order + k), hay8, len)) return p + len;
+    if (b >= a.teddy.nbuckets) break;
+    const int k1 = tt.boff[b + 1];
+    for (int k = tt.boff[b]; k < k1; k++)
+      if (teddy_lit_equal(a, tt, p, (int)tt.order[k], hay8, len)) return p + len;
   }
   return -1;
 }
@@ -834,7 +843,7 @@ __device__ __forceinline__ bool teddy_is_candidate(const ScanArgs& a, int64_t p)
   return p + 2 <= a.n &&
          ((__ldg(a.teddy.fp + __ldg(a.h + p)) & 0xFFFFu) & (__ldg(a.teddy.fp + __ldg(a.h + p + 1)) >> 16)) != 0u;
 }
-__device__ __noinline__ void teddy_lane_cold(const ScanArgs& a, const uint16_t* tfc, int64_t cb, Slot* cls0,
+__device__ __noinline__ void teddy_lane_cold(const ScanArgs& a, const TeddyTab& tt, int64_t cb, Slot* cls0,
                                              uint64_t* sbits, int64_t x0, int64_t x1) {
   int64_t pos = 0;
   for (int64_t q = x0; q > 0; q -= 32) {
@@ -843,7 +852,7 @@ __device__ __noinline__ void teddy_lane_cold(const ScanArgs& a, const uint16_t* 
     bool cross = false;
     for (int64_t p = lo; p < q; p++) {
       if (!teddy_is_candidate(a, p)) continue;
-      const int64_t e = teddy_verify_g(a, tfc, p, false);
+      const int64_t e = teddy_verify_g(a, tt, p, false);
       if (e < 0) continue;
       for (int64_t i = p + 1; i < e && i < q; i++) covered |= 1ull << (i - lo);
       if (e > q) cross = true;
@@ -865,7 +874,7 @@ __device__ __noinline__ void teddy_lane_cold(const ScanArgs& a, const uint16_t* 
   }
   for (int64_t p = pos; p < x1 && p + 2 <= a.n; p++) {
     if (!teddy_is_candidate(a, p)) continue;
-    const int64_t e = teddy_verify_g(a, tfc, p, a.n + a.after - pos < 16);
+    const int64_t e = teddy_verify_g(a, tt, p, a.n + a.after - pos < 16);
     if (e < 0) continue;
     if (p >= x0) teddy_record(cls0, sbits, cb, p, e);
     pos = e;
@@ -874,14 +883,14 @@ __device__ __noinline__ void teddy_lane_cold(const ScanArgs& a, const uint16_t* 
 }
 // Phase B of a lane: the words [own_lo, own_hi) of the window at cb are its own, word own_lo - 1
 // (if any) is where it looks for its safe point.  cand: the chunk's candidate bitmap (slot .a).
-__device__ __forceinline__ void teddy_lane(const ScanArgs& a, const uint16_t* tfc, int64_t cb, Slot* cls0,
+__device__ __forceinline__ void teddy_lane(const ScanArgs& a, const TeddyTab& tt, int64_t cb, Slot* cls0,
                                            uint64_t* sbits, int own_lo, int own_hi) {
   if (own_hi <= own_lo) return;
   const int64_t x0 = cb + (int64_t)own_lo * 64, x1 = cb + (int64_t)own_hi * 64;
   if (x0 >= a.n) return;
   // near the end of the haystack the verify order depends on the search start: exact replay
   if (a.n + a.after - (x0 - 64) < 16 + 64 + (int64_t)(own_hi - own_lo) * 64 + 64) {
-    teddy_lane_cold(a, tfc, cb, cls0, sbits, x0, x1);
+    teddy_lane_cold(a, tt, cb, cls0, sbits, x0, x1);
     return;
   }
   int64_t pos = x0;
@@ -895,7 +904,7 @@ __device__ __forceinline__ void teddy_lane(const ScanArgs& a, const uint16_t* tf
     while (c) {
       const int b = __ffsll((long long)c) - 1;
       c &= c - 1ull;
-      const int64_t e = teddy_verify_g(a, tfc, wp + b, false);
+      const int64_t e = teddy_verify_g(a, tt, wp + b, false);
       if (e < 0) continue;
       const int len = (int)(e - (wp + b));
       // positions strictly inside the span: b + 1 .. b + len - 1
@@ -909,7 +918,7 @@ __device__ __forceinline__ void teddy_lane(const ScanArgs& a, const uint16_t* tf
     if (cross) {
       const uint64_t safe = ~covered & 0xFFFFFFFF00000000ull;  // (a literal is at most 32 bytes long)
       if (!safe) {
-        teddy_lane_cold(a, tfc, cb, cls0, sbits, x0, x1);
+        teddy_lane_cold(a, tt, cb, cls0, sbits, x0, x1);
         return;
       }
       pos = wp + (63 - __clzll((long long)safe));
@@ -925,7 +934,7 @@ __device__ __forceinline__ void teddy_lane(const ScanArgs& a, const uint16_t* tf
       c &= c - 1ull;
       const int64_t s = wp + b;
       if (s < pos) continue;  // inside the match before
-      const int64_t e = teddy_verify_g(a, tfc, s, false);
+      const int64_t e = teddy_verify_g(a, tt, s, false);
       if (e < 0) continue;
       if (s >= x0) teddy_record(cls0, sbits, cb, s, e);
       pos = e;
@@ -1220,6 +1229,13 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       for (int k = a.teddy.bucket_off[b]; k < a.teddy.bucket_off[b + 1]; k++)
         cs.tfc[a.teddy.bytes[a.teddy.offs[a.teddy.order[k]] + 2]] |= (uint16_t)(1u << b);
   }
+  for (int i = tid; i < a.teddy.npat && i < 64; i += FW_THREADS) {
+    cs.tlit8[i] = reinterpret_cast<const unsigned long long*>(a.teddy.lit8)[i];
+    cs.tmsk8[i] = reinterpret_cast<const unsigned long long*>(a.teddy.lit8)[a.teddy.npat + i];
+    cs.tlen[i] = (uint16_t)(a.teddy.offs[i + 1] - a.teddy.offs[i]);
+    cs.torder[i] = a.teddy.order[i];
+  }
+  for (int i = tid; i <= a.teddy.nbuckets && i < 17; i += FW_THREADS) cs.tboff[i] = a.teddy.bucket_off[i];
 #endif
   static_assert(2 * FW_WARPS <= FW_THREADS, "one thread per mail slot at start-up");
   if (warp < FW_WARPS && lane == 0) {
@@ -1441,7 +1457,10 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     const bool whole = cb + WINDOW <= a.n;
     // word t * 32 + lane lives in slot (t * 32 + lane) + (t * 32 + lane) / K: 32 + 32 / K slots further per tile
     Slot* dst = &cls[0][lane + lane / K];
-#pragma unroll 1
+#ifndef CGX_UNROLL_A
+#define CGX_UNROLL_A 1     // trips around the window ring unrolled in the tile loop
+#endif
+#pragma unroll CGX_UNROLL_A
     for (int t0 = 0; t0 < TPC; t0 += NB) {
 #pragma unroll
       for (int b = 0; b < NB; b++) {
@@ -1490,7 +1509,8 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
       const int own_lo = K * lane + o;
       int own_hi = own_lo + K;
       if (own_hi > o + NWORDS - 2) own_hi = o + NWORDS - 2;
-      teddy_lane(a, cs.tfc, cb, cls[0], ws.mk, own_lo, own_hi);
+      const TeddyTab tt{cs.tfa, cs.tfb, cs.tfc, cs.tlit8, cs.tmsk8, cs.tlen, cs.torder, cs.tboff};
+      teddy_lane(a, tt, cb, cls[0], ws.mk, own_lo, own_hi);
       __syncwarp();
       // the starts move next to the ends: slot = (starts, ends), as the output stage expects
       for (int j = 0; j < K; j++) {

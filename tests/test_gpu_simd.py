@@ -98,7 +98,7 @@ def test_memchr_pair():
 def test_memmem():
     # reference simd/memmem_test.go:17-63, :82-150
     for hay, needle, want in [(b"hello", b"", 0), (b"", b"", 0), (b"", b"a", -1), (b"hi", b"hello", -1), (b"hello", b"ll", 2),
-                              (b"hello!", b"!", 5), (b"hello world", b"wo", 6), (b"aaaaaabaaaa", b"aab", 5),
+                              (b"hello!", b"!", 5), (b"hello world", b"wo", 6), (b"aaaaaabaaaa", b"aab", 4),
                               (b"hello world", b"xyz", -1), (b"hello", b"hello", 0)]:
         assert simd.Memmem(hay, needle) == want == hay.find(needle)
     for m in (2, 4, 8, 16, 32, 64, 128, 256):
