@@ -86,6 +86,10 @@ constexpr int K = CGX_K;
 constexpr int FW_CTAS = CGX_CTAS;
 constexpr int NB = CGX_NB;
 constexpr int UNROLL = CGX_UNROLL;
+#ifndef CGX_UNROLL_A
+#define CGX_UNROLL_A 1     // trips around the window ring unrolled in the tile loop
+#endif
+constexpr int UNROLL_A = CGX_UNROLL_A;
 constexpr int TILE = 2048;                 // one bulk copy, one classification round (64 B per lane)
 constexpr int TPC = K;                     // tiles per chunk
 constexpr int NWORDS = 32 * K;             // words of a chunk's window
@@ -1457,10 +1461,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     const bool whole = cb + WINDOW <= a.n;
     // word t * 32 + lane lives in slot (t * 32 + lane) + (t * 32 + lane) / K: 32 + 32 / K slots further per tile
     Slot* dst = &cls[0][lane + lane / K];
-#ifndef CGX_UNROLL_A
-#define CGX_UNROLL_A 1     // trips around the window ring unrolled in the tile loop
-#endif
-#pragma unroll CGX_UNROLL_A
+#pragma unroll UNROLL_A
     for (int t0 = 0; t0 < TPC; t0 += NB) {
 #pragma unroll
       for (int b = 0; b < NB; b++) {
