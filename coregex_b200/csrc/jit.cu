@@ -151,8 +151,9 @@ bool JitCompileCubin(const FlatDev& f, int mode, std::vector<char>& cubin, std::
     return false;
   }
   const std::string mode_def = "-DCGX_JIT_MODE=" + std::to_string(mode);
+  // (-default-device: the generic lambda of the kernel's tile loop has no execution-space annotation)
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DCGX_JIT=1",
-                                   mode_def.c_str()};
+                                   "-default-device", mode_def.c_str()};
   for (auto& o : xo) opts.push_back(o.c_str());
   const nvrtcResult rc = n.compile(prog, (int)opts.size(), opts.data());
   if (rc != NVRTC_SUCCESS) {

@@ -90,6 +90,10 @@ constexpr int UNROLL = CGX_UNROLL;
 #define CGX_UNROLL_A 1     // trips around the window ring unrolled in the tile loop
 #endif
 constexpr int UNROLL_A = CGX_UNROLL_A;
+#ifndef CGX_FAST_UNROLL
+#define CGX_FAST_UNROLL 1  // the same in the fast form of the tile loop (fully unrolled it ran 9 % slower: instruction cache)
+#endif
+constexpr int FAST_UNROLL = CGX_FAST_UNROLL;
 constexpr int TILE = 2048;                 // one bulk copy, one classification round (64 B per lane)
 constexpr int TPC = K;                     // tiles per chunk
 constexpr int NWORDS = 32 * K;             // words of a chunk's window
@@ -204,6 +208,11 @@ __device__ __forceinline__ int64_t chunk_origin(int64_t chunk) {
   return chunk * (int64_t)CHUNKB;
 #endif
 }
+
+template <bool B>
+struct BoolC {
+  static constexpr bool value = B;
+};
 
 struct alignas(16) Slot {
   uint64_t a, b;
@@ -1461,43 +1470,68 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     const bool whole = cb + WINDOW <= a.n;
     // word t * 32 + lane lives in slot (t * 32 + lane) + (t * 32 + lane) / K: 32 + 32 / K slots further per tile
     Slot* dst = &cls[0][lane + lane / K];
-#pragma unroll UNROLL_A
-    for (int t0 = 0; t0 < TPC; t0 += NB) {
+    // The tile loop exists twice: FAST for a chunk whose window — and that of the chunk the ring
+    // moves on to — lies wholly inside the input (no end-of-input masks, no partial copies, the
+    // ring's bookkeeping folded at compile time), and the general form.
+    auto tile_loop = [&](auto fast) {
+      constexpr bool FAST = decltype(fast)::value;
+#pragma unroll(FAST ? FAST_UNROLL : UNROLL_A)
+      for (int t0 = 0; t0 < TPC; t0 += NB) {
 #pragma unroll
-      for (int b = 0; b < NB; b++) {
-        const int t = t0 + b;
-        mbar_wait(&ws.mbar[b], rpar);
-        uint64_t cm[4];
+        for (int b = 0; b < NB; b++) {
+          const int t = t0 + b;
+          mbar_wait(&ws.mbar[b], rpar);
+          uint64_t cm[4];
 #ifdef CGX_TEDDY
-        cm[0] = teddy_piece(ws.win[b], lrot, cs.tfa, cs.tfb, cs.tfc);
-        cm[1] = 0ull;  // (the ends bitmap starts empty)
+          cm[0] = teddy_piece(ws.win[b], lrot, cs.tfa, cs.tfb, cs.tfc);
+          cm[1] = 0ull;  // (the ends bitmap starts empty)
 #else
-        classify_piece(f, ws.win[b], lrot, one, cm);
+          classify_piece(f, ws.win[b], lrot, one, cm);
 #endif
-        // every lane holds its piece in registers: the buffer can take the tile NB ahead
-        __syncwarp();
-        if (pf_left == 0 && t + NB == TPC && nxt < nch) prefetch_chunk(nxt);  // the ring moves on to the next chunk
-        if (pf_left) issue_next(b);
-        if (!whole) {
-          // bytes at or beyond the end of input belong to no class.  Reversed bit r <=> byte 63 - r
-          const int64_t v = a.n - (cb + (int64_t)t * TILE + lane * 64);  // valid bytes of this piece
+          // every lane holds its piece in registers: the buffer can take the tile NB ahead
+          __syncwarp();
+          if (FAST) {
+            // (the ring is exactly NB tiles ahead: tiles of this chunk until t + NB reaches its end,
+            // then the next chunk's)
+            if (t + NB == TPC && nxt < nch) prefetch_chunk(nxt);
+            if (t + NB < TPC || nxt < nch) {
+              if (lane == 0) {
+                mbar_expect_tx(&ws.mbar[b], (uint32_t)TILE);
+                tma_load_1d(ws.win[b], pf_src, (uint32_t)TILE, &ws.mbar[b]);
+              }
+              pf_src += TILE;
+              pf_left--;
+            }
+          } else {
+            if (pf_left == 0 && t + NB == TPC && nxt < nch) prefetch_chunk(nxt);  // the ring moves on to the next chunk
+            if (pf_left) issue_next(b);
+            if (!whole) {
+              // bytes at or beyond the end of input belong to no class.  Reversed bit r <=> byte 63 - r
+              const int64_t v = a.n - (cb + (int64_t)t * TILE + lane * 64);  // valid bytes of this piece
 #ifdef CGX_TEDDY
-          cm[0] &= v >= 64 ? ~0ull : (v <= 0 ? 0ull : ((1ull << v) - 1ull));  // (forward orientation)
+              cm[0] &= v >= 64 ? ~0ull : (v <= 0 ? 0ull : ((1ull << v) - 1ull));  // (forward orientation)
 #else
-          const uint64_t m = v >= 64 ? ~0ull : (v <= 0 ? 0ull : (~0ull << (64 - v)));
+              const uint64_t m = v >= 64 ? ~0ull : (v <= 0 ? 0ull : (~0ull << (64 - v)));
 #pragma unroll
-          for (int c = 0; c < 4; c++) cm[c] &= m;
+              for (int c = 0; c < 4; c++) cm[c] &= m;
 #endif
+            }
+          }
+          dst[0] = Slot{cm[0], cm[1]};
+          if (NPAIR > 1) dst[NSLOTS1] = Slot{cm[2], cm[3]};
+#ifdef CGX_TEDDY
+          ws.mk[dst - &cls[0][0]] = 0ull;  // the starts bitmap of the chunk
+#endif
+          dst += 32 + 32 / K;
         }
-        dst[0] = Slot{cm[0], cm[1]};
-        if (NPAIR > 1) dst[NSLOTS1] = Slot{cm[2], cm[3]};
-#ifdef CGX_TEDDY
-        ws.mk[dst - &cls[0][0]] = 0ull;  // the starts bitmap of the chunk
-#endif
-        dst += 32 + 32 / K;
+        rpar ^= 1u;
       }
-      rpar ^= 1u;
-    }
+    };
+#ifndef CGX_FASTA
+#define CGX_FASTA 1
+#endif
+    if (CGX_FASTA && whole && pf_left == TPC - NB && (nxt >= nch || chunk_origin(nxt) + WINDOW <= a.n)) tile_loop(BoolC<true>{});
+    else tile_loop(BoolC<false>{});
     __syncwarp();
 
 #ifdef CGX_TEDDY

@@ -1,10 +1,4 @@
 #!/bin/bash
-# the command of one gpurun call of round 2 (kept in a file so that retries send the current tree)
 TAG=$1
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_simd.py tests/test_sim_teddy.py -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1
-tail -4 gpurun_out/${TAG}_pytest.log
-CGX_TEDDY2=1 CFG_ONLY=C3,C5 timeout 600 python tools/run_configs.py > gpurun_out/${TAG}_configs.jsonl 2> gpurun_out/${TAG}_configs.err
-cut -c1-330 gpurun_out/${TAG}_configs.jsonl; tail -3 gpurun_out/${TAG}_configs.err
-CGX_TEDDY2=1 CFG_ONLY=C3 CFG_SCALE=0.25 timeout 300 ncu --set full --clock-control none --import-source on -k regex:scan_flat_kernel -s 3 -c 1 -f -o gpurun_out/${TAG}_teddy_full python tools/run_configs.py > gpurun_out/${TAG}_ncu_teddy.log 2>&1
-ls -la gpurun_out | tail -3
+AB_PATS=2 bash tools/gpu_exp.sh ${TAG} "" "-DCGX_FASTA=0" "-DCGX_FAST_UNROLL=2" ""
