@@ -1042,7 +1042,9 @@ __device__ __forceinline__ void publish_count(const ScanArgs& a, int64_t chunk, 
 // count over, turns the counts into offsets within the gang (one warp scan), resolves the gang's
 // global offset by the two-level look-back — one L2 round trip per gang, not per chunk — and hands
 // every warp the global index of its chunk's first match; the scanning warps store their staged
-// matches themselves when they next need the buffer.  It also draws the CTA's gang tickets.
+// matches themselves when they next need the buffer.  It also draws the CTA's gang tickets — one
+// gang per ticket: handing a CTA RUNS of consecutive gangs (so that only a run's first gang looks
+// back) serialises the CTAs behind each other's runs with two buffers per warp (measured: 44 GB/s).
 __device__ void resolver_warp(const ScanArgs& a, CtaSmem& cs, int lane, unsigned ngangs) {
   auto fetch = [&](unsigned seq) -> unsigned {
     unsigned t = 0;

@@ -96,7 +96,8 @@ if __name__ == "__main__":
         run(r"\w+@\w+\.\w+", cg.SYNTH_EMAIL, 0xC0FFEE + 4, 80 * 10_000_000, window=80 * 4000)
     if npat > 2:
         run(r"[a-z]+/\d+", cg.SYNTH_LOG, 0xC0FFEE, 1 * GIB)
+    dense = int(float(os.environ.get("AB_DENSE_GIB", "1")) * GIB)
     if npat > 3:
-        run(r"\d+", cg.SYNTH_LOG, 0xC0FFEE, 1 * GIB, cap_div=4)
+        run(r"\d+", cg.SYNTH_LOG, 0xC0FFEE, dense, cap_div=4)
     if npat > 4:
-        run(r"\w+", cg.SYNTH_LOG, 0xC0FFEE, 1 * GIB, cap_div=4)
+        run(r"\w+", cg.SYNTH_LOG, 0xC0FFEE, dense, cap_div=4)

@@ -5,7 +5,7 @@ TAG=$1; shift
 mkdir -p gpurun_out
 for v in "$@"; do
   echo "== defs=$v"
-  CGX_JIT_DEFS="$v" AB_STEPS=${AB_STEPS:-20} AB_ARMS=jit AB_PATS=${AB_PATS:-2} timeout -k 10 150 python tools/ab_flat.py 16 2>&1 | python -c "
+  CGX_JIT_DEFS="$v" AB_STEPS=${AB_STEPS:-20} AB_ARMS=jit AB_PATS=${AB_PATS:-2} timeout -k 10 200 python tools/ab_flat.py 16 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     try: d = json.loads(l); print('   ', d['pattern'][:18], d['bitstream']['GBps'], d['bitstream']['matches'], d['bitstream'].get('serial_replays'))
