@@ -70,7 +70,7 @@ struct Compiled {
 
 // Source of "cgx_jit_prog.h" for the bitstream kernel specialised to this flat program: the class
 // tests with their constants as immediates and the two marker passes as straight-line macro lists
-// (scan_flat.cu, CGX_JIT).  Also the cache key of the compiled kernel.
+// (scan_bits.cu, CGX_JIT).  Also the cache key of the compiled kernel.
 std::string JitHeader(const FlatDev& f);
 
 enum CompileStatus { COMPILE_OK = 0, COMPILE_SYNTAX = -1, COMPILE_UNSUPPORTED = -2 };

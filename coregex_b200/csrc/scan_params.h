@@ -64,7 +64,7 @@ struct FlatDev {
   // from the constant bank: mode 0 = XOR-alignable range (3 ops/word), 1 = generic (5 ops/word)
   uint8_t cls_mode[4][4];
   uint32_t cls_k1[4][4], cls_k2[4][4];
-  // ---- bitstream engine (scan_flat.cu) --------------------------------------------------------
+  // ---- bitstream engine (scan_bits.cu) --------------------------------------------------------
   // bs_ok: the pattern is flat AND deterministic (every repeated/optional item's class is disjoint
   // from whatever can follow it), so the leftmost-first match from a start is the forced greedy
   // one and its END can be computed by a forward marker pass over the same class bitmaps.

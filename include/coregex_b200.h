@@ -82,7 +82,7 @@ int cgx_set_longest(cgx_regex* re, int longest);
 const char* cgx_strategy(const cgx_regex* re);
 /* which GPU engine runs it: "dfa-runstart", "dfa-byteset", "dfa-lut" (+"+flat": bit-parallel
  * start filter in front of the DFA walk; +"+bitstream": flat deterministic pattern, starts AND
- * ends bit-parallel, scan_flat.cu), "line-dfa", "teddy", "fat-teddy"                            */
+ * ends bit-parallel, scan_bits.cu), "line-dfa", "teddy", "fat-teddy"                            */
 const char* cgx_engine(const cgx_regex* re);
 /* the record delimiter of this pattern: a byte no match can contain ('\n' whenever the pattern
  * allows it).  The scan treats the haystack as records separated by it; callers that split a

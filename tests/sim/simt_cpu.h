@@ -1,5 +1,5 @@
 // simt_cpu.h — TEST HARNESS ONLY.  A tiny single-threaded SIMT emulator that lets the kernel
-// SOURCE (coregex_b200/csrc/scan_flat.cu) be compiled with g++ and stepped on the CPU, one
+// SOURCE (coregex_b200/csrc/scan_bits.cu) be compiled with g++ and stepped on the CPU, one
 // ucontext fiber per CUDA thread, so that warp-level logic (shuffles, ballots, look-back
 // protocol, mbarrier phases) can be debugged in this GPU-less container before GPU minutes are
 // spent.  It is never linked into libcoregex_b200.so; the product has no CPU path.

@@ -20,7 +20,7 @@ BITSTREAM = True
 
 @pytest.fixture(autouse=True, params=["bitstream", "dfa-kernel"])
 def kernel_choice(request):
-    """Flat deterministic patterns can run on two kernels (scan_flat.cu / scan_dfa.cu): every case
+    """Flat deterministic patterns can run on two kernels (scan_bits.cu / scan_dfa.cu): every case
     that goes through check() is run on both (the switch is a no-op for other patterns)."""
     global BITSTREAM
     BITSTREAM = request.param == "bitstream"

@@ -150,7 +150,7 @@ def test_class_words_of_all_ones_use_exact_carries():
 
 
 def test_alternation_criterion_exhaustive():
-    """word_misordered() in scan_flat.cu, restated: per word, with `inn` = starts below - ends below,
+    """word_misordered() in scan_bits.cu, restated: per word, with `inn` = starts below - ends below,
     D = E - S - inn must satisfy D ^ (D << 1 | inn) == S ^ E and inn in {0,1}; plus equal totals.
     Checked against the definition (spans sorted by start never overlap, ends distinct) for every
     assignment of ends to every set of starts on three 3-bit words."""

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of the two kernels that can run a flat deterministic pattern: the bitstream kernel
-(scan_flat.cu) and the candidate+DFA kernel (scan_dfa.cu), on the same device-resident corpus.
+(scan_bits.cu) and the candidate+DFA kernel (scan_dfa.cu), on the same device-resident corpus.
 Checks that the two independent implementations produce IDENTICAL (start,end) arrays at full size
 (a size-independent parity property next to the oracle window check) and times both.
   python tools/ab_flat.py [GiB ...]            (default 1 16)

@@ -15,7 +15,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, kname = sys.argv[1], sys.argv[2]
-cu = sys.argv[3] if len(sys.argv) > 3 else "scan_flat.cu"
+cu = sys.argv[3] if len(sys.argv) > 3 else "scan_bits.cu"
 so = os.path.join(ROOT, "coregex_b200", "lib", "libcoregex_b200.so")
 
 tmp = tempfile.mkdtemp()
