@@ -192,10 +192,11 @@ struct cgx_regex {
     memset(&teddy_dev, 0, sizeof teddy_dev);
     if (c->kind == ENG_TEDDY) {
       // one allocation: fp[256] u32 | lit8[npat] u64 | mask8[npat] u64 | offs[npat+1] i32 | order[npat] u16 |
-      // bucket_off[nb+1] u16 | bytes
+      // bucket_off[nb+1] u16 | fp2[256] u16 | bytes
       const TeddyTables& t = c->teddy;
       size_t o_fp = 0, o_lit8 = o_fp + 1024, o_offs = o_lit8 + (size_t)t.npat * 16, o_order = o_offs + (t.npat + 1) * 4;
-      size_t o_boff = o_order + ((t.npat * 2 + 3) & ~3), o_bytes = o_boff + (((t.nbuckets + 1) * 2 + 3) & ~3);
+      size_t o_boff = o_order + ((t.npat * 2 + 3) & ~3), o_fp2 = o_boff + (((t.nbuckets + 1) * 2 + 3) & ~3);
+      size_t o_bytes = o_fp2 + 512;
       size_t total = o_bytes + t.bytes.size();
       std::vector<uint8_t> blob((total + 3) & ~(size_t)3, 0);
       memcpy(&blob[o_fp], t.fp_packed.data(), 1024);
@@ -212,6 +213,13 @@ struct cgx_regex {
       memcpy(&blob[o_offs], t.offs.data(), (t.npat + 1) * 4);
       memcpy(&blob[o_order], t.order_simd.data(), t.npat * 2);
       memcpy(&blob[o_boff], t.bucket_off.data(), (t.nbuckets + 1) * 2);
+      for (int id = 0; id < t.npat; id++) {
+        uint16_t m;
+        const size_t at = o_fp2 + 2 * (size_t)t.bytes[t.offs[id] + 2];
+        memcpy(&m, &blob[at], 2);
+        m |= (uint16_t)(1u << t.bucket_of[id]);
+        memcpy(&blob[at], &m, 2);
+      }
       memcpy(&blob[o_bytes], t.bytes.data(), t.bytes.size());
       int r;
       if ((r = d_teddy.ensure(blob.size()))) return r;
@@ -219,6 +227,12 @@ struct cgx_regex {
       const uint8_t* b = (const uint8_t*)d_teddy.p;
       teddy_dev.fp = (const uint32_t*)(b + o_fp);
       teddy_dev.lit8 = (const uint64_t*)(b + o_lit8);
+      teddy_dev.fp2 = (const uint16_t*)(b + o_fp2);
+      teddy_dev.use_fp2 = 0;
+      for (int id = 0; id < t.npat; id++) {
+        auto letter = [](uint8_t ch) { return (ch >= 'a' && ch <= 'z') || (ch >= 'A' && ch <= 'Z') || ch == ' '; };
+        if (letter(t.bytes[t.offs[id]]) && letter(t.bytes[t.offs[id] + 1])) teddy_dev.use_fp2 = 1;
+      }
       teddy_dev.offs = (const int32_t*)(b + o_offs);
       teddy_dev.order = (const uint16_t*)(b + o_order);
       teddy_dev.bucket_off = (const uint16_t*)(b + o_boff);

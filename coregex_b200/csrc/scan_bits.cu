@@ -1236,13 +1236,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_CTAS) scan_flat_kernel(const __
     const uint32_t t = a.teddy.fp[i];
     cs.tfa[i] = (uint16_t)(t & 0xFFFFu);
     cs.tfb[i] = (uint16_t)(t >> 16);
-    cs.tfc[i] = 0;
-  }
-  cgx_syncthreads();
-  if (tid == 0) {
-    for (int b = 0; b < a.teddy.nbuckets; b++)
-      for (int k = a.teddy.bucket_off[b]; k < a.teddy.bucket_off[b + 1]; k++)
-        cs.tfc[a.teddy.bytes[a.teddy.offs[a.teddy.order[k]] + 2]] |= (uint16_t)(1u << b);
+    cs.tfc[i] = a.teddy.fp2[i];
   }
   for (int i = tid; i < a.teddy.npat && i < 64; i += FW_THREADS) {
     cs.tlit8[i] = reinterpret_cast<const unsigned long long*>(a.teddy.lit8)[i];

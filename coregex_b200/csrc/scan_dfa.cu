@@ -84,6 +84,7 @@ struct Ctx {
   // multi-literal engine tables (shared memory copies)
   const uint32_t* t_fp;
   const uint64_t* t_lit8;  // [npat] first 8 bytes, then [npat] byte masks
+  const uint16_t* t_fp2;   // bucket masks of the third byte
   const uint8_t* t_bytes;
   const int32_t* t_offs;
   const uint16_t* t_order;
@@ -244,16 +245,25 @@ __device__ void phase_a_teddy(const Ctx& c) {
     load32(p, w);
     uint32_t m = 0;
     uint32_t tprev = c.t_fp[w[0] & 255u];
+    // bytes k + 1 and k + 2 of position k: from the registers, the last two from the window
+    auto byte = [&](int i) -> uint32_t { return i < 32 ? ((w[i >> 2] >> (8 * (i & 3))) & 255u) : (uint32_t)p[i]; };
+    uint32_t tn = c.t_fp[byte(1)];
+    // the last piece of the window: the bytes after it are not here (sentinel) — its last two
+    // positions pass on what is known, whoever continues beyond the window verifies them
+    const bool edge = rel + 32 == CH + OVER;
+    const bool use3 = c.a.teddy.use_fp2 != 0;
 #pragma unroll
     for (int k = 0; k < 32; k++) {
-      const uint32_t nb = k == 31 ? (uint32_t)p[32] : ((w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 255u);
-      const uint32_t tn = c.t_fp[nb];
-      if ((tprev & 0xFFFFu) & (tn >> 16)) m |= 1u << k;
+      uint32_t t2 = use3 ? (uint32_t)c.t_fp2[byte(k + 2)] : 0xFFFFu;
+      if (k >= 30 && edge) t2 = 0xFFFFu;
+      if (k == 31 && edge) tn = 0xFFFF0000u;
+      if ((tprev & 0xFFFFu) & (tn >> 16) & t2) m |= 1u << k;  // three-byte fingerprint
       tprev = tn;
+      tn = c.t_fp[byte(k + 2)];
     }
-    const int64_t gp = c.cbeg + rel;  // a 2-byte fingerprint needs position+1 < n
-    if (gp + 33 > c.a.n) {
-      const int64_t v = c.a.n - 1 - gp;
+    const int64_t gp = c.cbeg + rel;  // a 3-byte fingerprint needs position + 2 < n
+    if (gp + 34 > c.a.n) {
+      const int64_t v = c.a.n - 2 - gp;
       m = v <= 0 ? 0u : (v >= 32 ? m : (m & ((1u << v) - 1u)));
     }
     c.sm.cand[t * 32 + c.lane] = m;
@@ -1072,6 +1082,7 @@ __global__ void __launch_bounds__(THREADS, 3) scan_dfa_kernel(const ScanArgs a) 
     Ctx c{a, sm, s_trans, s_eoi, s_lut, cbeg, gw, (int)(hi_g - gw), lane, warp, buf,
           reinterpret_cast<const uint32_t*>(t_blob),
           reinterpret_cast<const uint64_t*>(t_blob + ((const unsigned char*)a.teddy.lit8 - g_blob)),
+          reinterpret_cast<const uint16_t*>(t_blob + ((const unsigned char*)a.teddy.fp2 - g_blob)),
           t_blob + (a.teddy.bytes - g_blob),
           reinterpret_cast<const int32_t*>(t_blob + ((const unsigned char*)a.teddy.offs - g_blob)),
           reinterpret_cast<const uint16_t*>(t_blob + ((const unsigned char*)a.teddy.order - g_blob)),

@@ -82,6 +82,14 @@ struct TeddyDev {
   // per literal id: its first 8 bytes as a little-endian word (zero padded), then npat byte masks
   // (0xFF for the bytes that exist): a candidate is compared 8 bytes at a time
   const uint64_t* lit8;
+  // 256 entries: bucket masks per byte value of the THIRD byte (every literal has three bytes or
+  // more): the candidate filter tests three bytes, an order of magnitude fewer candidates to verify
+  const uint16_t* fp2;
+  // 1: phase A tests the third byte as well.  It pays when two-byte candidates are frequent in text
+  // (literals that open with two letters: 5 % of positions for 16 English words, C3 892 -> 1308
+  // GB/s); for sets like `k00z..k63z` they are rare anyway and the third lookup per byte only costs
+  // (C5 965 -> 890 GB/s), so the host switches it per literal set.
+  int use_fp2;
   const uint8_t* bytes;      // concatenated literals
   const int32_t* offs;       // npat + 1
   const uint16_t* order;     // literal ids, bucket-major (SIMD-regime verify order)

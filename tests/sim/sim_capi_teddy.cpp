@@ -36,6 +36,8 @@ int cgxsim_scan_teddy(const char* pat, size_t plen, const uint8_t* h, int64_t n,
       lit8[t.npat + id] |= 0xFFull << (8 * k);
     }
   }
+  std::vector<uint16_t> fp2(256, 0);
+  for (int id = 0; id < t.npat; id++) fp2[t.bytes[t.offs[id] + 2]] |= (uint16_t)(1u << t.bucket_of[id]);
   const size_t padded = ((size_t)n + 15) / 16 * 16 + 64;
   uint8_t* hb = (uint8_t*)aligned_alloc(128, (padded + 127) / 128 * 128);
   memset(hb, pad_byte, (padded + 127) / 128 * 128);
@@ -53,6 +55,7 @@ int cgxsim_scan_teddy(const char* pat, size_t plen, const uint8_t* h, int64_t n,
   a.after = after;
   a.teddy.fp = t.fp_packed.data();
   a.teddy.lit8 = lit8.data();
+  a.teddy.fp2 = fp2.data();
   a.teddy.bytes = t.bytes.data();
   a.teddy.offs = t.offs.data();
   a.teddy.order = t.order_simd.data();

@@ -1,6 +1,8 @@
 #!/bin/bash
 TAG=$1
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_sim_flat.py -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1
-tail -3 gpurun_out/${TAG}_pytest.log
-AB_DENSE_GIB=6 AB_PATS=5 bash tools/gpu_exp.sh ${TAG} "" "-DCGX_RUN=1" "-DCGX_RUN=8"
+python tools/dbg_teddy.py 2>&1 | tail -8
+timeout 900 python -m pytest tests/test_sim_teddy.py tests/test_gpu_teddy.py tests/test_gpu_large.py -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1
+tail -4 gpurun_out/${TAG}_pytest.log
+CFG_ONLY=C3,C5 timeout 600 python tools/run_configs.py > gpurun_out/${TAG}_configs.jsonl 2> gpurun_out/${TAG}_configs.err
+cut -c1-330 gpurun_out/${TAG}_configs.jsonl; tail -3 gpurun_out/${TAG}_configs.err
