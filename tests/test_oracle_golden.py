@@ -300,3 +300,16 @@ def test_dangling_at_sign_vector():
     for hay, want in [(b"a@b c@d.e", [[4, 9]]), (b"@@a@b.c@", [[2, 7]]), (b"x@y z@w.", []), (b"a@b.c@d.e", [[0, 5]])]:
         assert o.find_all(np.frombuffer(hay, dtype=np.uint8)).tolist() == want
         assert [[m.start(), m.end()] for m in re.finditer(rb"\w+@\w+\.\w+", hay)] == want
+
+
+def test_ast_dump_fixture():
+    """The restated Go parser (syntax/parse.cpp) is shared by product and oracle, so no
+    oracle-vs-device test can see a parser regression: its AST dumps for 106 patterns (the
+    reference's stdlib-compat table, the suites' patterns, syntax corner cases and error messages)
+    are pinned in tests/golden/ast_dumps.json (tests/golden/make_ast_fixture.py); the independent
+    check of the parser's MEANING stays the Python-`re` differential above."""
+    with open(os.path.join(GOLDEN, "ast_dumps.json")) as fh:
+        fixture = json.load(fh)
+    assert len(fixture) >= 100
+    for pat, want in fixture.items():
+        assert dump_ast(pat) == want, pat
