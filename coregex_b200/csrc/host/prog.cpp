@@ -1,6 +1,8 @@
 // prog.cpp — AST -> Pike-style program (continuation-passing construction, built back to front).
 #include "prog.h"
 
+#include <functional>
+#include <map>
 #include <memory>
 
 namespace cgx {
@@ -149,6 +151,57 @@ struct Builder {
     for (size_t i = entries.size() - 1; i-- > 0;) acc = emitSplit(entries[i], acc);
     return acc;
   }
+  // Large classes (\pL: 650 ranges, 1500 sequences): the alternatives are UTF-8 sequences of
+  // DISJOINT rune ranges, and the lead byte fixes the length, so whichever alternative takes a
+  // position takes the same bytes — their order is not observable.  That allows sharing common
+  // prefixes (a trie over byte sets) and common suffixes (equal subtrees emitted once): the same
+  // byte language in a fraction of the instructions, which is what keeps such classes inside the
+  // limits of the DFA builder and of the PikeVM search kernel.
+  int emitShared(const std::vector<Seq>& alts, int next) {
+    struct Node {
+      std::vector<std::pair<ByteSet, int>> kids;  // child node, -1 = the sequence ends here
+    };
+    std::vector<Node> trie(1);
+    for (const Seq& q0 : alts) {
+      Seq q = q0;
+      if (reverse) std::reverse(q.begin(), q.end());
+      int at = 0;
+      for (size_t i = 0; i < q.size(); i++) {
+        const bool last = i + 1 == q.size();
+        int hit = -2;
+        for (auto& k : trie[at].kids)
+          if (k.first == q[i]) hit = k.second;
+        if (hit == -2) {
+          hit = last ? -1 : (int)trie.size();
+          trie[at].kids.push_back({q[i], hit});
+          if (!last) trie.emplace_back();
+        } else if ((hit == -1) != last) {
+          return emitAlts(alts, next);  // one sequence a proper prefix of another: keep the plain form
+        }
+        at = hit;
+      }
+    }
+    using Edge = std::pair<ByteSet, int>;             // byte set, target instruction
+    std::map<Edge, int> edge_memo;                    // equal edges are one instruction
+    std::map<std::vector<Edge>, int> node_memo;       // equal subtrees are one split chain
+    std::function<int(int)> emitNode = [&](int n) -> int {
+      std::vector<Edge> key;
+      for (auto& k : trie[n].kids) key.push_back({k.first, k.second < 0 ? next : emitNode(k.second)});
+      auto it = node_memo.find(key);
+      if (it != node_memo.end()) return it->second;
+      std::vector<int> entries;
+      for (const Edge& e : key) {
+        auto em = edge_memo.find(e);
+        if (em == edge_memo.end()) em = edge_memo.emplace(e, emitSet(e.first, e.second)).first;
+        entries.push_back(em->second);
+      }
+      int acc = entries.back();
+      for (size_t i = entries.size() - 1; i-- > 0;) acc = emitSplit(entries[i], acc);
+      node_memo[key] = acc;
+      return acc;
+    };
+    return emitNode(0);
+  }
   // every well-formed multi-byte sequence (the eight rows of the Unicode standard's table 3-7)
   static void validMultiByte(std::vector<Seq>& alts) {
     const ByteSet cont = range(0x80, 0xBF);
@@ -256,6 +309,7 @@ struct Builder {
       alts.push_back({range(0x80, 0xFF)});
     } else {
       for (auto& w : wide) wideRange(w.first, w.second, alts);
+      if (alts.size() > 8) return emitShared(alts, next);
     }
     return emitAlts(alts, next);
   }

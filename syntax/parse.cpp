@@ -31,16 +31,32 @@ const char* ErrUnsupportedUnicode = "unsupported: Unicode class";
 using Runes = std::vector<int32_t>;
 using sv = std::string;  // we pass (string, offset) pairs as std::string substrings for clarity
 
-// ---- unicode.SimpleFold restricted to the orbits that touch ASCII --------------------------
+// ---- Unicode data: \p{..} range tables and simple-case-folding orbits ------------------------
+// The reference parses with Go's regexp/syntax (standard library, not in the reference tree), which
+// reads unicode.Categories / unicode.Scripts / unicode.SimpleFold (Unicode 15.0.0).  The tables here
+// are regenerated from an independent 15.0.0 database by tools/gen_unicode_tables.py.
+struct UnicodeTable {
+  const char* name;
+  const int32_t* r;  // inclusive ranges lo,hi,...
+  int n;             // number of int32 in r
+  int is_script;
+  const int32_t* fold;  // runes outside the table whose case orbit reaches into it (may be null)
+  int nfold;
+};
+struct UnicodeAlias {
+  const char* alias;
+  const char* name;
+};
+#include "unicode_tables.inc"
+
+// unicode.SimpleFold: the next larger rune of r's case orbit, wrapping around to the smallest
 int32_t simpleFold(int32_t r) {
-  if (r == 'K') return 'k';
-  if (r == 'k') return 0x212A;
-  if (r == 0x212A) return 'K';
-  if (r == 'S') return 's';
-  if (r == 's') return 0x17F;
-  if (r == 0x17F) return 'S';
-  if (r >= 'A' && r <= 'Z') return r + 32;
-  if (r >= 'a' && r <= 'z') return r - 32;
+  size_t lo = 0, hi = sizeof(kCaseOrbit) / sizeof(kCaseOrbit[0]);
+  while (lo < hi) {
+    size_t mid = (lo + hi) / 2;
+    if (kCaseOrbit[mid][0] < r) lo = mid + 1; else hi = mid;
+  }
+  if (lo < sizeof(kCaseOrbit) / sizeof(kCaseOrbit[0]) && kCaseOrbit[lo][0] == r) return kCaseOrbit[lo][1];
   return r;
 }
 const int32_t minFold = 0x0041, maxFold = 0x1e943;
@@ -80,13 +96,8 @@ void appendFoldedRange(Runes& r, int32_t lo, int32_t hi) {
     appendRange(r, maxFold + 1, hi);
     hi = maxFold;
   }
-  // Brute force over the part of the range that can fold.  Only ASCII (+ U+017F, U+212A) has
-  // non-trivial orbits in this restatement, so cap the brute-force walk there.
+  // brute force; appendRange coalesces on the fly
   for (int32_t c = lo; c <= hi; c++) {
-    if (c > 0x212A) {  // nothing above folds in our table: append the rest in one piece
-      appendRange(r, c, hi);
-      break;
-    }
     appendRange(r, c, c);
     for (int32_t f = simpleFold(c); f != c; f = simpleFold(f)) appendRange(r, f, f);
   }
@@ -159,6 +170,43 @@ struct CharGroup {
   int sign;
   Runes cls;
 };
+
+// Go 1.25 regexp/syntax unicodeTable: names compare case-insensitively with spaces, underscores and
+// hyphens ignored; Any / ASCII / Assigned are built in, categories answer to their aliases too
+std::string canonicalUnicodeName(const std::string& name) {
+  std::string out;
+  for (char c : name) {
+    if (c == ' ' || c == '_' || c == '-') continue;
+    out.push_back((c >= 'A' && c <= 'Z') ? (char)(c + 32) : c);
+  }
+  return out;
+}
+
+// false: no such table.  sign is flipped for names defined as a complement (Assigned = not Cn)
+bool unicodeTable(const std::string& name, Runes& tab, Runes& fold, int& sign) {
+  const std::string want = canonicalUnicodeName(name);
+  if (want.empty()) return false;
+  if (want == "any") {
+    tab = {0, kMaxRune};
+    return true;
+  }
+  if (want == "ascii") {
+    tab = {0, 0x7F};
+    return true;
+  }
+  std::string key = want == "assigned" ? "cn" : want;
+  if (want == "assigned") sign = -sign;
+  for (const UnicodeAlias& a : kUnicodeAliases)
+    if (canonicalUnicodeName(a.alias) == key) key = canonicalUnicodeName(a.name);
+  for (int pass = 0; pass < 2; pass++)  // categories first, then scripts
+    for (const UnicodeTable& t : kUnicodeTables)
+      if (t.is_script == pass && canonicalUnicodeName(t.name) == key) {
+        tab.assign(t.r, t.r + t.n);
+        fold.assign(t.fold, t.fold + t.nfold);
+        return true;
+      }
+  return false;
+}
 
 const Runes code_d = {'0', '9'};
 const Runes code_s = {0x9, 0xa, 0xc, 0xd, 0x20, 0x20};
@@ -858,6 +906,51 @@ struct Parser {
     }
   }
 
+  // \p{Name} \pN \P{Name} \p{^Name}: 0 = not one, 1 = consumed, -1 = error
+  int parseUnicodeClass(const std::string& t, size_t& i, Runes& r, Error& err) {
+    if (!(flags & UnicodeGroups) || i + 2 > t.size() || t[i] != '\\' || (t[i + 1] != 'p' && t[i + 1] != 'P')) return 0;
+    int sign = t[i + 1] == 'P' ? -1 : +1;
+    size_t k = i + 2;
+    std::string seq, name;
+    if (k < t.size() && t[k] == '{') {
+      size_t end = t.find('}', i);
+      if (end == std::string::npos) {
+        err = {ErrInvalidCharRange, t.substr(i)};
+        return -1;
+      }
+      seq = t.substr(i, end + 1 - i);
+      name = t.substr(i + 3, end - (i + 3));
+      k = end + 1;
+    } else {
+      int32_t c = 0;
+      if (k < t.size() && !nextRune(t, k, c)) {
+        err = {ErrInvalidUTF8, t.substr(k)};
+        return -1;
+      }
+      seq = t.substr(i, k - i);
+      name = seq.substr(2);
+    }
+    if (!name.empty() && name[0] == '^') {
+      sign = -sign;
+      name = name.substr(1);
+    }
+    Runes tab, fold;
+    if (!unicodeTable(name, tab, fold, sign)) {
+      err = {ErrInvalidCharRange, seq};
+      return -1;
+    }
+    if ((flags & FoldCase) && !fold.empty()) {
+      tab.insert(tab.end(), fold.begin(), fold.end());
+      cleanClass(tab);
+    }
+    if (sign > 0)
+      appendClass(r, tab);
+    else
+      appendNegatedClass(r, tab);
+    i = k;
+    return 1;
+  }
+
   // returns true if a Perl class escape was consumed
   bool parsePerlClassEscape(const std::string& t, size_t& i, Runes& r) {
     if (!(flags & PerlX) || i + 2 > t.size() || t[i] != '\\') return false;
@@ -925,10 +1018,10 @@ struct Parser {
         if (k < 0) return false;
         if (k > 0) continue;
       }
-      if (i + 1 < t.size() && t[i] == '\\' && (t[i + 1] == 'p' || t[i + 1] == 'P') &&
-          (flags & UnicodeGroups)) {
-        err = {ErrUnsupportedUnicode, t.substr(i, 2)};
-        return false;
+      {
+        int k = parseUnicodeClass(t, i, cls, err);
+        if (k < 0) return false;
+        if (k > 0) continue;
       }
       if (parsePerlClassEscape(t, i, cls)) continue;
       size_t rng = i;
@@ -1142,12 +1235,16 @@ struct Parser {
             }
             if (handled) break;
           }
-          if (i + 1 < t.size() && (t[i + 1] == 'p' || t[i + 1] == 'P')) {
-            err = {ErrUnsupportedUnicode, t.substr(i, 2)};
-            return nullptr;
-          }
           Regexp* re = newRegexp(OpCharClass);
           re->flags = flags;
+          if (i + 1 < t.size() && (t[i + 1] == 'p' || t[i + 1] == 'P')) {
+            int k = parseUnicodeClass(t, i, re->rune, err);
+            if (k < 0) return nullptr;
+            if (k > 0) {
+              push(re);
+              break;
+            }
+          }
           if (parsePerlClassEscape(t, i, re->rune)) {
             push(re);
             break;

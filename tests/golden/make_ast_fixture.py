@@ -19,7 +19,8 @@ EXTRA = [
     r"GET /\S+ HTTP", r'"[A-Z]+ .*" 200', r"(foo|bar)+baz", r"a.*b", r"x[^y]*y", r"(?i)error.*", r"\bfoo\b", r"[ab]+c|a+d",
     r"(a|b)*abb", r"(?i)straße|x.z", r"[α-ω]+", r"[^\x00-\x{7FF}\n]+", r"é+", r"[^\d\n]{2,3}", r"a{2,}", r"a{,3}", r"a{3}?",
     r"(?P<user>\w+)@(?P<host>[a-z]+)", r"(a|ab)(c|bcd)(d*)x", r"((a)(b))+c", r"(\d+)-(\d+)?x", r"([a-z]+?)(\d+)", r"(?U)a+b",
-    r"\Aabc\z", r"^$", r"(?:a|b)c", r"[[:alpha:]]+", r"[^[:space:]]", r"\pL", r"\x41\x{1F600}", r"\Q.*\E", r"a|b|c|d",
+    r"\Aabc\z", r"^$", r"(?:a|b)c", r"[[:alpha:]]+", r"[^[:space:]]", r"\p{Zs}", r"\P{Zs}", r"\p{^Zs}+", r"[\p{Zl}\p{Zp}x]", r"\pZ", r"\p{Lt}", r"(?i)\p{Lt}", r"\p{Braille}",
+    r"\p{space separator}", r"[^\p{Nl}]", r"\p{Any}", r"\p{ASCII}", r"\p{Foo}", r"\p{Zs", r"(?i)я", r"(?i)[а-в]", r"(?i)ǆ", r"\x41\x{1F600}", r"\Q.*\E", r"a|b|c|d",
     r"abc|abd", r"two|three", r"(a|b|c)+", r"x{1,3}y{0}z", r"[a-c-e]", r"[]a]", r"[^]a]", r"\C", r"(?i)k", r"(?i)[k-l]s",
     r"a**", r"(", r")", r"x{1001}", r"[z-a]", r"\8", r"(?P<n>a)(?P<n>b)", r"a{2,1}", r"*a", r"(?z)", r"\pX", "[a",
 ]

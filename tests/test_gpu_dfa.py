@@ -289,7 +289,9 @@ def test_pipelined_host_path_matches_oracle(tmp_path):
 
 # ---- `.`, negated and non-ASCII classes (UTF-8 byte automata), well-formed and malformed input ---------
 UTF8_GPU = [r"a.c", r"foo.*bar", r"[^a\n]+", r"\S+", r"[α-ω]+", r"key=[^\s;]+", r"[^\d\n]{2,3}", r"x.y.z",
-            r"[а-я]+ [а-я]+", r"(?i)straße|x.z", r"GET .* HTTP", r"[^\x00-\x{7FF}\n]+", r"é+"]
+            r"[а-я]+ [а-я]+", r"(?i)straße|x.z", r"GET .* HTTP", r"[^\x00-\x{7FF}\n]+", r"é+",
+            # Unicode property classes (generated 15.0.0 tables, shared-prefix/suffix UTF-8 automata)
+            r"\pL+", r"\p{Lu}\p{Ll}+", r"\p{Greek}+", r"\pN+", r"\p{Cyrillic}+ \p{Cyrillic}+", r"(?i)[а-в]+", r"\P{L}+", r"\p{Han}+"]
 
 
 def _utf8_corpus(rng, n):

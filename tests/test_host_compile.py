@@ -43,10 +43,20 @@ def test_compile_errors_are_go_formatted():
     assert str(ei.value).startswith("regexp: Compile(`(`): error parsing regexp")
 
 
-def test_unsupported_patterns_fail_loudly():
-    for pat in [r"\pL", r"\p{Greek}+"]:  # Unicode property tables
-        with pytest.raises(cg.UnsupportedError):
+def test_unicode_property_classes_compile_to_the_table_engines():
+    # \p{..} resolves through the generated Unicode 15.0.0 tables (syntax/unicode_tables.inc); the
+    # UTF-8 automaton of a large class shares prefixes and suffixes (host/prog.cpp emitShared), which
+    # keeps even \pL (650 ranges) inside the 160-state table kernels
+    for pat in [r"\pL", r"\pL+", r"\pN+", r"\p{Greek}+", r"\p{Han}+", r"[\p{Lu}\d]+", r"\p{Lu}\p{Ll}+"]:
+        assert cg.Compile(pat).engine.startswith("dfa"), pat
+    for pat, msg in [(r"\p{Foo}", "invalid character class range: `\\p{Foo}`"), (r"\pX", "invalid character class range: `\\pX`"),
+                     (r"\p{Greek", "invalid character class range: `\\p{Greek`")]:
+        with pytest.raises(cg.Error) as ei:
             cg.Compile(pat)
+        assert msg in str(ei.value)
+
+
+def test_unsupported_patterns_fail_loudly():
     # matches that may contain every byte value leave no record delimiter: one record, one lane
     for pat in [r"(?s)x.y", r"(?s).+", r"(?m)^POST\s+\S+"]:
         r = cg.Compile(pat)
@@ -203,7 +213,10 @@ def test_flat_start_filter_is_exact_superset(pat):
 
 UTF8_PATTERNS = [r"a.c", r"foo.*bar", r"[^a\n]+", r"\S+", r"[α-ω]+", r"x.y.z", r"[^\s\"]+=.", r"[\x{100}-\x{17F}]+x",
                  r"[^\x00-\x{7FF}\n]+", r"é+", r"(?i)straße|x.z", r"[\x{10000}-\x{10200}]", r"[\x{90000}-\x{10FFFF}]x", r"a[^b\n]c",
-                 r"[\x{7F0}-\x{810}]+", r"[\x{D700}-\x{E010}]", r"[^\d\n]{2,3}", r"[^x\n]{3}y"]
+                 r"[\x{7F0}-\x{810}]+", r"[\x{D700}-\x{E010}]", r"[^\d\n]{2,3}", r"[^x\n]{3}y",
+                 # Unicode property classes: large tables take the shared-prefix/suffix emission (host/prog.cpp emitShared)
+                 r"\pL+", r"\pL", r"\p{Lu}\p{Ll}+", r"\p{Greek}+", r"[\p{Lu}\d]+x", r"\pN+", r"\p{Han}", r"\pS", r"(?i)\p{Lu}+",
+                 r"\p{Latin}+", r"(?i)[а-в]+", r"(?i)я"]
 
 
 @pytest.mark.parametrize("pat", UTF8_PATTERNS)
