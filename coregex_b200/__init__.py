@@ -258,6 +258,23 @@ class Regex:
             return None
         return out[: c.value].tolist()
 
+    def find_all_into(self, b, out, n=-1, submatch=False):
+        """FindAllIndex / FindAllSubmatchIndex of a host buffer into a caller-owned int64 buffer
+        (numpy array or CPU torch tensor, pinned for full PCIe speed) of shape (cap, 2) or
+        (cap, 2 * (NumSubexp() + 1)); nothing is allocated per call.  Returns the number of matches,
+        which may exceed cap (the first cap rows are written) — the buffered-append forms of the
+        reference (regex.go AppendAllIndex family) in one call."""
+        p, ln, keep = _host_buf(b)
+        if n == 0:
+            return 0
+        stride = 2 * _lib.cgx_num_captures(self._h) if submatch else 2
+        optr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        cap = (out.numel() if hasattr(out, "numel") else out.size) // stride
+        c = C.c_size_t(0)
+        fn = _lib.cgx_find_all_submatch_index if submatch else _lib.cgx_find_all_index
+        _check(fn(self._h, p, ln, n, optr, cap, C.byref(c)))
+        return c.value
+
     # -- device-resident API -----------------------------------------------------------------------
     def scan_device(self, d_ptr, length, mode=MODE_FINDALL, out_ptr=0, cap_pairs=0, result_ptr=0,
                     base_offset=0, stream=0, bytes_after=0):

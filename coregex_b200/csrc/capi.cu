@@ -684,18 +684,18 @@ int cgx_scan_records_device(cgx_regex* re, const uint8_t* d_h, size_t len, const
 
 // scan -> (start,end) pairs -> one Pike lane per match for the group offsets
 static int submatch_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base, int64_t* d_out,
-                           size_t cap, uint64_t* d_result, cudaStream_t st) {
+                           size_t cap, uint64_t* d_result, cudaStream_t st, int64_t after = 0) {
   Compiled& c = *re->c;
   const int nslots = 2 * c.prog.num_captures;
   if (nslots == 2)  // no groups: the pairs ARE the result (reference meta/findall.go:109-112)
-    return scan_locked(re, d_h, len, base, CGX_MODE_FINDALL, d_out, cap, d_result, st);
+    return scan_locked(re, d_h, len, base, CGX_MODE_FINDALL, d_out, cap, d_result, st, after);
   // flat deterministic pattern whose groups enclose whole items: the group offsets are item
   // boundaries of the forced greedy walk (flat_caps.cu) — no NFA simulation.  Leftmost-longest
   // changes nothing for a deterministic pattern (one match per start).
   if (c.kind == ENG_DFA && c.flat.bs_ok && c.flat_caps.ok && c.flat_caps.nslots == nslots) {
     int r;
     if ((r = re->d_pairs.ensure((cap ? cap : 1) * 16))) return r;
-    if ((r = scan_locked(re, d_h, len, base, CGX_MODE_FINDALL, (int64_t*)re->d_pairs.p, cap, d_result, st))) return r;
+    if ((r = scan_locked(re, d_h, len, base, CGX_MODE_FINDALL, (int64_t*)re->d_pairs.p, cap, d_result, st, after))) return r;
     CU(launch_flat_captures(d_h, (int64_t)len, base, (const int64_t*)re->d_pairs.p,
                             (const unsigned long long*)re->d_ticket_total.p, cap, c.flat, c.flat_caps.at, nslots, d_out,
                             st));
@@ -712,7 +712,7 @@ static int submatch_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_
   }
   int r;
   if ((r = re->d_pairs.ensure((cap ? cap : 1) * 16))) return r;
-  if ((r = scan_locked(re, d_h, len, base, CGX_MODE_FINDALL, (int64_t*)re->d_pairs.p, cap, d_result, st))) return r;
+  if ((r = scan_locked(re, d_h, len, base, CGX_MODE_FINDALL, (int64_t*)re->d_pairs.p, cap, d_result, st, after))) return r;
   const uint32_t* code = (const uint32_t*)re->d_pike.p;
   const uint32_t* sets = code + c.pike.code.size();
   CU(launch_pike_captures(d_h, (int64_t)len, base, (const int64_t*)re->d_pairs.p,
@@ -748,9 +748,18 @@ static size_t forced_piece() {
 // limit > 0: the caller wants the first `limit` matches only — no further piece is queued once
 // the pieces finished so far hold that many (the reference's loop stops at n matches,
 // meta/findall.go:176-290; pieces are in haystack order, so what they hold is a prefix).
+// `nslots` > 2: FindAllSubmatchIndex — every piece also runs its captures pass on the scan stream and
+// the rows that travel back are nslots int64 wide instead of pairs.
 static int host_scan_pipelined(cgx_regex* re, const uint8_t* h, size_t len, int mode, int64_t* out, size_t cap,
-                               uint64_t result[2], int64_t limit) {
+                               uint64_t result[2], int64_t limit, int nslots = 2) {
   int r;
+  const size_t row = (size_t)nslots * 8;  // bytes per match in `out`
+  auto piece_scan = [&](const uint8_t* d_h, size_t plen, int64_t off, int m, int64_t* d_out, size_t pc,
+                        int64_t after) -> int {
+    if (nslots > 2 && m == CGX_MODE_FINDALL)
+      return submatch_locked(re, d_h, plen, off, d_out, pc, nullptr, re->s_scan, after);
+    return scan_locked(re, d_h, plen, off, m, d_out, pc, nullptr, re->s_scan, after);
+  };
   if ((r = re->ensure_pipeline())) return r;
   const uint8_t delim = re->c->kind == ENG_TEDDY ? (uint8_t)'\n' : (uint8_t)re->c->delim;
   size_t nominal = len / 16;
@@ -806,15 +815,14 @@ static int host_scan_pipelined(cgx_regex* re, const uint8_t* h, size_t len, int 
         pc = plen / 16 + 1024;
         if (pc > cap) pc = cap;
         int rr;
-        if ((rr = re->d_out2[sl].ensure(pc * 16))) return rr;
+        if ((rr = re->d_out2[sl].ensure(pc * row))) return rr;
         CU(cudaStreamWaitEvent(re->s_scan, re->ev_d2h[sl], 0));  // output slot drained (piece k-2)
       }
     }
     pcap[sl] = pc;
     pmode[sl] = m;
-    int rr = scan_locked(re, (const uint8_t*)re->d_hay2[sl].p, plen, (int64_t)off, m,
-                         pc ? (int64_t*)re->d_out2[sl].p : nullptr, pc, nullptr, re->s_scan,
-                         (int64_t)(len - cut[k + 1]));
+    int rr = piece_scan((const uint8_t*)re->d_hay2[sl].p, plen, (int64_t)off, m,
+                        pc ? (int64_t*)re->d_out2[sl].p : nullptr, pc, (int64_t)(len - cut[k + 1]));
     if (rr) return rr;
     CU(cudaMemcpyAsync(re->pinned_res + 2 * sl, re->d_ticket_total.p, 16, cudaMemcpyDeviceToHost, re->s_scan));
     CU(cudaEventRecord(re->ev_scan[sl], re->s_scan));
@@ -834,11 +842,10 @@ static int host_scan_pipelined(cgx_regex* re, const uint8_t* h, size_t len, int 
           CU(cudaStreamSynchronize(re->s_d2h));
           CU(cudaStreamSynchronize(re->s_scan));
           int rr;
-          if ((rr = re->d_out2[sl].ensure(need * 16))) return rr;
+          if ((rr = re->d_out2[sl].ensure(need * row))) return rr;
           pcap[sl] = need;
-          if ((rr = scan_locked(re, (const uint8_t*)re->d_hay2[sl].p, plen, (int64_t)off, CGX_MODE_FINDALL,
-                                (int64_t*)re->d_out2[sl].p, need, nullptr, re->s_scan,
-                                (int64_t)(len - cut[k + 1]))))
+          if ((rr = piece_scan((const uint8_t*)re->d_hay2[sl].p, plen, (int64_t)off, CGX_MODE_FINDALL,
+                               (int64_t*)re->d_out2[sl].p, need, (int64_t)(len - cut[k + 1]))))
             return rr;
           CU(cudaMemcpyAsync(re->pinned_res + 2 * sl, re->d_ticket_total.p, 16, cudaMemcpyDeviceToHost,
                              re->s_scan));
@@ -847,7 +854,8 @@ static int host_scan_pipelined(cgx_regex* re, const uint8_t* h, size_t len, int 
         }
         if (need) {
           CU(cudaStreamWaitEvent(re->s_d2h, re->ev_scan[sl], 0));
-          CU(cudaMemcpyAsync(out + 2 * written, re->d_out2[sl].p, need * 16, cudaMemcpyDeviceToHost, re->s_d2h));
+          CU(cudaMemcpyAsync(out + (size_t)nslots * written, re->d_out2[sl].p, need * row, cudaMemcpyDeviceToHost,
+                             re->s_d2h));
           written += need;
         }
         CU(cudaEventRecord(re->ev_d2h[sl], re->s_d2h));
@@ -945,6 +953,16 @@ int cgx_find_all_submatch_index(cgx_regex* re, const uint8_t* h, size_t len, int
   size_t want = cap;
   if (limit > 0 && (size_t)limit < want) want = (size_t)limit;
   const size_t stride = 2 * (size_t)re->c->prog.num_captures;
+  if (re->c->has_delim && out && want &&
+      len >= (forced_piece() ? 2 * forced_piece() : kPipelineMin)) {
+    // same three-stream pipeline as FindAllIndex: H2D(k+1) | scan + captures(k) | D2H(k-1)
+    uint64_t res[2] = {0, 0};
+    if ((r = host_scan_pipelined(re, h, len, CGX_MODE_FINDALL, out, want, res, limit, (int)stride))) return r;
+    size_t c = (size_t)res[0];
+    if (limit > 0 && c > (size_t)limit) c = (size_t)limit;
+    if (count) *count = c;
+    return CGX_OK;
+  }
   if ((r = re->d_hay.ensure(len + 16))) return r;
   if ((r = re->d_out.ensure((want ? want : 1) * stride * 8))) return r;
   cudaStream_t st = 0;

@@ -130,3 +130,43 @@ def test_c4_sized_device_entry():
         want = o.find_all_submatch(hay)
         want = np.where(want >= 0, want + lo * 80, want)
         assert np.array_equal(m[lo:lo + 1000], want)
+
+
+# ---- FindAllSubmatchIndex of a large HOST buffer: pieces cut at record delimiters flow through
+# H2D | scan + captures | D2H (capi.cu host_scan_pipelined, rows of 2*(groups+1) int64).  The piece size
+# is read once per process, so the pipelined run happens in a child.
+_PIPE_SUB_CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import coregex_b200 as cg
+from oracle_lib import Oracle
+ok = True
+email = cg.synth_host(cg.SYNTH_EMAIL, 21, 80 * 30000)
+log = cg.synth_host(cg.SYNTH_LOG, 22, 4096 * 500)
+for pat, hay in [(r"(\w+)@(\w+)\.(\w+)", email),            # flat captures pass (flat_caps.cu)
+                 (r"(\d+)\.(\d+)\.(\d+)\.(\d+)", log),
+                 (r"(\w+)@((\w+)\.)+(\w+)", email),           # group under a quantifier: Pike captures pass
+                 (r"(GET|POST) (/\S*)", log),
+                 (r"(a*)(\d*)", log[:300000]),                # nullable: PikeVM search kernel + captures
+                 (r"\w+@\w+", email)]:                        # no groups: rows are the pairs
+    r, o = cg.Compile(pat), Oracle(pat)
+    want = o.find_all_submatch(hay)
+    got = r.FindAllSubmatchIndex(hay)
+    good = (got is None and len(want) == 0) or np.array_equal(np.array(got, dtype=np.int64), want)
+    part = r.FindAllSubmatchIndex(hay, 777)
+    good = good and np.array_equal(np.array(part, dtype=np.int64), want[:777])
+    small = np.full((100, want.shape[1]), -7, dtype=np.int64)   # caller buffer smaller than the result
+    cnt = r.find_all_into(hay, small, submatch=True)
+    good = good and cnt == len(want) and np.array_equal(small, want[:100])
+    print(pat, len(hay), len(want), r.engine, good)
+    ok = ok and good
+sys.exit(0 if ok else 1)
+"""
+
+
+def test_pipelined_host_submatch_matches_oracle():
+    import subprocess
+    import sys
+    env = dict(os.environ, CGX_PIPELINE_PIECE=str(160 * 1024))
+    p = subprocess.run([sys.executable, "-c", _PIPE_SUB_CHILD, ROOT], env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout + p.stderr

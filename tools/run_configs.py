@@ -38,6 +38,8 @@ def timed(fn, steps=5, warm=3):
     return e0.elapsed_time(e1) / steps
 
 
+E2E = os.environ.get("CFG_E2E", "1") == "1"
+E2E_MAX = 4 * GIB + (1 << 20)
 ONLY = os.environ.get("CFG_ONLY", "")  # e.g. "C3,C5": run only the configs whose name starts so
 
 
@@ -73,6 +75,23 @@ def run(name, pattern, kind, seed, nbytes, literals=None, submatch=False, window
             "bytes": nbytes, "matches": total, "ms": round(ms, 3), "GBps": round(nbytes / ms / 1e6, 1),
             "engine": r.engine, "reference_strategy": r.strategy, "oracle_window_ok": ok,
             "frac_hbm_input_only": round(nbytes / ms / 1e6 / 6570.3, 4)}
+    if E2E and nbytes <= E2E_MAX:
+        # the same call through the host-buffer C ABI: pinned input and output, H2D + scan (+ captures)
+        # + D2H inside the timed region, pieces pipelined over three streams
+        import time
+        hbuf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        hbuf.copy_(t)
+        hout = torch.empty((total + 16, stride), dtype=torch.int64, pin_memory=True)
+        cnt = r.find_all_into(hbuf, hout, submatch=submatch)  # warm: allocates the staging buffers
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            cnt = r.find_all_into(hbuf, hout, submatch=submatch)
+        dt = (time.perf_counter() - t0) / 3
+        same = cnt == total and bool(torch.equal(hout[:total], out[:total].cpu()))
+        line["e2e"] = {"GBps": round(nbytes / dt / 1e9, 2), "ms": round(dt * 1e3, 2), "h2d_bytes": nbytes,
+                       "d2h_bytes": total * stride * 8, "equals_device_result": same}
+        del hbuf, hout
     print(json.dumps(line), flush=True)
     del t, out
     torch.cuda.empty_cache()
