@@ -36,7 +36,7 @@ cudaError_t launch_flat_captures(const uint8_t* h, int64_t n, int64_t base, cons
 cudaError_t launch_pike_captures(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
                                  const unsigned long long* d_total, unsigned long long cap,
                                  const uint32_t* code, const uint32_t* sets, int start_pc, int nslots,
-                                 int64_t* out, cudaStream_t stream);
+                                 int64_t* out, cudaStream_t stream, bool large);
 }  // namespace cgx
 
 using namespace cgx;
@@ -419,7 +419,7 @@ int cgx_debug_captures_engine(cgx_regex* re) {
   const int nslots = 2 * c.prog.num_captures;
   if (nslots == 2) return 0;
   if (c.kind == ENG_DFA && c.flat.bs_ok && c.flat_caps.ok && c.flat_caps.nslots == nslots) return 1;
-  return c.has_pike ? 2 : -1;
+  return c.has_pike ? (c.pike.large ? 3 : 2) : -1;  // 3: the 512-instruction form of the Pike captures kernel
 }
 // NVRTC only (no device needed): size of the specialised cubin, or -1 with cgx_last_error set
 long cgx_debug_jit_compile(cgx_regex* re, char* cubin_out, size_t cap) {
@@ -717,7 +717,7 @@ static int submatch_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_
   const uint32_t* sets = code + c.pike.code.size();
   CU(launch_pike_captures(d_h, (int64_t)len, base, (const int64_t*)re->d_pairs.p,
                           (const unsigned long long*)re->d_ticket_total.p, cap, code, sets, c.pike.start, nslots,
-                          d_out, st));
+                          d_out, st, c.pike.large));
   re->launches++;
   return CGX_OK;
 }

@@ -4,7 +4,8 @@
 // code[2*pc+1] = out | out1 << 16  (0xFFFF = none)
 // sets[8*k .. 8*k+7] = 256-bit membership of byte set k
 // Limits of the captures kernel (per-lane state lives in registers/local memory):
-//   <= 64 instructions, <= 32 byte-consuming instructions (live threads), <= 8 groups.
+//   small form <= 64 instructions and <= 32 live threads, large form <= 512 instructions and <= 64
+//   simultaneously live threads (proved by a subset construction, pike_pack.cpp); <= 8 groups.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -18,6 +19,7 @@ struct PikePacked {
   std::vector<uint32_t> code;
   std::vector<uint32_t> sets;
   int ninst = 0, start = 0, nslots = 0, nthreads = 0;
+  bool large = false;  // captures kernel: the 512-instruction form
 };
 
 // returns "" or the reason the program does not fit the kernel

@@ -180,8 +180,9 @@ __global__ void __launch_bounds__(128) pike_search_kernel(const PikeArgs a) {
       rs++;
     }
     // (the empty record after a trailing delimiter — or an empty haystack — starts at n: it belongs
-    // to the last slice; only a pattern that matches the empty string finds anything there)
-    const bool last_slice = slice == a.nslices - 1;
+    // to the last slice; only a pattern that matches the empty string finds anything there).  In a
+    // shard that other bytes follow (after > 0) position n is the first record of the NEXT shard.
+    const bool last_slice = slice == a.nslices - 1 && a.after == 0;
     while (rs < hi || (last_slice && rs == a.n)) {
       int64_t rend = rs;
       if (a.delim > 255) rend = a.n;

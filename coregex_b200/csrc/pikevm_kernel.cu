@@ -17,14 +17,43 @@ namespace cgx {
 
 namespace {
 
-constexpr int MAXT = 32;    // live threads per generation
 constexpr int MAXS = 16;    // capture slots (2 per group, 8 groups)
-constexpr int MAXSTK = 96;  // closure stack frames
 
+// Two sizes of the same kernel (the host proves which one a program fits, host/pike_pack.cpp):
+//   small: <= 64 instructions (one visited word), <= 32 live threads, 96 closure frames
+//   large: <= 512 instructions, <= 64 live threads, 520 closure frames — patterns whose groups hold
+//          `.`, `\S`, negated or non-ASCII classes (UTF-8 byte automata), at ~13 KB of local memory a lane
+struct Small {
+  static constexpr int MAXT = 32, VW = 1, MAXSTK = 96;
+  using Pc = uint8_t;
+};
+struct Large {
+  static constexpr int MAXT = 64, VW = 8, MAXSTK = 520;
+  using Pc = uint16_t;
+};
+
+template <class Z>
 struct ThreadList {
-  uint8_t pc[MAXT];
-  int32_t slots[MAXT][MAXS];  // relative to the match start; -1 = unset
+  typename Z::Pc pc[Z::MAXT];
+  int32_t slots[Z::MAXT][MAXS];  // relative to the match start; -1 = unset
   int n;
+};
+
+template <class Z>
+struct Visited {
+  unsigned long long w[Z::VW];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int k = 0; k < Z::VW; k++) w[k] = 0ull;
+  }
+  // true when pc was already marked; marks it
+  __device__ __forceinline__ bool test_and_set(int pc) {
+    unsigned long long& x = w[Z::VW == 1 ? 0 : pc >> 6];
+    const unsigned long long bit = 1ull << (pc & 63);
+    const bool was = (x & bit) != 0;
+    x |= bit;
+    return was;
+  }
 };
 
 __device__ __forceinline__ bool is_word(int b) {
@@ -56,8 +85,10 @@ struct Vm {
 };
 
 // epsilon closure of pc at position pos (relative rp = pos - s), appending to `tl`
-__device__ void add_thread(const Vm& vm, ThreadList& tl, unsigned long long& visited, int pc0, int64_t pos,
+template <class Z>
+__device__ void add_thread(const Vm& vm, ThreadList<Z>& tl, Visited<Z>& visited, int pc0, int64_t pos,
                            int32_t* cur) {
+  constexpr int MAXT = Z::MAXT, MAXSTK = Z::MAXSTK;
   // frame: low 16 bits pc (0xFFFF = restore frame), then slot and old value
   int32_t stk_a[MAXSTK];
   int32_t stk_b[MAXSTK];
@@ -73,8 +104,7 @@ __device__ void add_thread(const Vm& vm, ThreadList& tl, unsigned long long& vis
     }
     const int pc = fa;
     if (pc == 0xFFFF) continue;
-    if ((visited >> pc) & 1ull) continue;
-    visited |= 1ull << pc;
+    if (visited.test_and_set(pc)) continue;
     const uint32_t w0 = vm.code[2 * pc], w1 = vm.code[2 * pc + 1];
     const int op = w0 & 255, arg = (int)(w0 >> 8);
     const int out = w1 & 0xFFFF, out1 = w1 >> 16;
@@ -82,7 +112,7 @@ __device__ void add_thread(const Vm& vm, ThreadList& tl, unsigned long long& vis
       case 1:    // I_SET
       case 6: {  // I_MATCH
         if (tl.n < MAXT) {
-          tl.pc[tl.n] = (uint8_t)pc;
+          tl.pc[tl.n] = (typename Z::Pc)pc;
           for (int k = 0; k < vm.nslots; k++) tl.slots[tl.n][k] = cur[k];
           tl.n++;
         }
@@ -120,6 +150,7 @@ __device__ void add_thread(const Vm& vm, ThreadList& tl, unsigned long long& vis
 }
 
 // nmatches = min(*d_total, cap): the match count is only known on the device
+template <class Z>
 __global__ void pike_captures_kernel(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
                                      const unsigned long long* d_total, unsigned long long cap,
                                      const uint32_t* code, const uint32_t* sets, int start_pc, int nslots,
@@ -128,12 +159,13 @@ __global__ void pike_captures_kernel(const uint8_t* h, int64_t n, int64_t base, 
   const unsigned long long nmatches = *d_total < cap ? *d_total : cap;
   if (i >= nmatches) return;
   Vm vm{code, sets, h, n, matches[2 * i] - base, nslots, base == 0};
-  ThreadList a, b;
-  ThreadList* cur = &a;
-  ThreadList* nxt = &b;
+  ThreadList<Z> a, b;
+  ThreadList<Z>* cur = &a;
+  ThreadList<Z>* nxt = &b;
   int32_t work[MAXS];
   for (int k = 0; k < MAXS; k++) work[k] = -1;
-  unsigned long long visited = 0;
+  Visited<Z> visited;
+  visited.clear();
   cur->n = 0;
   add_thread(vm, *cur, visited, start_pc, vm.s, work);
   int64_t best_end = -1;
@@ -141,7 +173,7 @@ __global__ void pike_captures_kernel(const uint8_t* h, int64_t n, int64_t base, 
   for (int k = 0; k < MAXS; k++) best[k] = -1;
   for (int64_t pos = vm.s;; pos++) {
     const int byte = pos < n ? (int)h[pos] : -1;
-    visited = 0;
+    visited.clear();
     nxt->n = 0;
     for (int t = 0; t < cur->n; t++) {
       const int pc = cur->pc[t];
@@ -160,7 +192,7 @@ __global__ void pike_captures_kernel(const uint8_t* h, int64_t n, int64_t base, 
       }
     }
     if (byte < 0 || nxt->n == 0) break;
-    ThreadList* tmp = cur;
+    ThreadList<Z>* tmp = cur;
     cur = nxt;
     nxt = tmp;
   }
@@ -181,12 +213,16 @@ __global__ void pike_captures_kernel(const uint8_t* h, int64_t n, int64_t base, 
 cudaError_t launch_pike_captures(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
                                  const unsigned long long* d_total, unsigned long long cap,
                                  const uint32_t* code, const uint32_t* sets, int start_pc, int nslots,
-                                 int64_t* out, cudaStream_t stream) {
+                                 int64_t* out, cudaStream_t stream, bool large) {
   if (cap == 0) return cudaSuccess;
   const int threads = 128;
   const unsigned long long blocks = (cap + threads - 1) / threads;
-  pike_captures_kernel<<<(unsigned)blocks, threads, 0, stream>>>(h, n, base, matches, d_total, cap, code, sets,
-                                                                 start_pc, nslots, out);
+  if (large)
+    pike_captures_kernel<Large><<<(unsigned)blocks, threads, 0, stream>>>(h, n, base, matches, d_total, cap, code,
+                                                                          sets, start_pc, nslots, out);
+  else
+    pike_captures_kernel<Small><<<(unsigned)blocks, threads, 0, stream>>>(h, n, base, matches, d_total, cap, code,
+                                                                          sets, start_pc, nslots, out);
   return cudaGetLastError();
 }
 

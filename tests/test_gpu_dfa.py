@@ -263,7 +263,9 @@ def corpus(kind):
         return b"1.2.3.4 " * 300000 + b"\n" + b"9.9.9.9 x\n" * 1000 + b"7.7.7.7"   # one 2.4 MB line
 for pat, kind in [(r"\d+\.\d+\.\d+\.\d+", "log"), (r"error|err|errors|warning|warn|fatal", "lit"), (r"warning|fatal|critical|timeout", "lit"),
                   (r"^(error|warn)", "lit"), (r"(?m)^(error|warn)\w*", "lit"), (r"\d+\.\d+\.\d+\.\d+", "longline"),
-                  (r"(?m)\d$", "longline")]:
+                  (r"(?m)\d$", "longline"),
+                  # nullable: the empty record after a piece's trailing delimiter belongs to the next piece
+                  (r"\d*", "lit"), (r"(?m)^", "lit"), (r"[a-f]*", "log")]:
     hay = corpus(kind)
     hay = hay.tobytes() if hasattr(hay, 'tobytes') else hay
     r = cg.Compile(pat)

@@ -91,6 +91,38 @@ def test_flat_pattern_groups(pat):
             assert np.array_equal(np.array(got, dtype=np.int64), want), (pat, h)
 
 
+# groups around `.`, `\S`, negated and non-ASCII classes: UTF-8 byte automata, more instructions than the
+# 64-instruction form of the captures kernel holds — the 512-instruction form (engine code 3), its
+# thread lists sized by the proved widest generation (host/pike_pack.cpp MaxLiveThreads)
+LARGE_PATS = [r"(\S+)@(\S+)", r"(.*)=(.*)", r"([^,\n]+),([^,\n]+)", r"(\w{1,40})-(\w{1,40})", r"([а-я]+) ([а-я]+)",
+              r"(GET|POST) (/\S*)", r'"([A-Z]+) (.*)" (\d+)', r"(?i)(error|warn): (.+)", r"(\S+?)=(\S*?);", r"(é|e)+(.)"]
+
+
+@pytest.mark.parametrize("pat", LARGE_PATS)
+def test_groups_around_utf8_classes(pat):
+    rng = np.random.default_rng(31)
+    pieces = [b"a", b"b", b"x", b" ", b" ", b"\n", b",", b"@", b"=", b";", b"-", b"e", b"error", b"WARN: ", b"12", b"GET /",
+              b"POST /a", b'"GET ', b'" 200', "é".encode(), "мир".encode(), "привет".encode(), "世界".encode(),
+              "😀".encode(), b"\xff", b"\xe0\x80", b"\xc3", b"user@host", b"k=v;"]
+    r, o = cg.Compile(pat), Oracle(pat)
+    assert _engine(r) in (2, 3), (pat, r.engine, _engine(r))
+    for it in range(50):
+        h = b"".join(pieces[int(i)] for i in rng.integers(0, len(pieces), int(rng.integers(0, 90))))
+        want = o.find_all_submatch(h)
+        got = r.FindAllSubmatchIndex(h)
+        if len(want) == 0:
+            assert got is None, (pat, h)
+        else:
+            assert np.array_equal(np.array(got, dtype=np.int64), want), (pat, h)
+    h = b"".join(pieces[int(i)] for i in rng.integers(0, len(pieces), 60000))
+    assert np.array_equal(np.array(r.FindAllSubmatchIndex(h), dtype=np.int64), o.find_all_submatch(h)), pat
+
+
+def test_large_form_is_selected_by_instruction_count_or_width():
+    assert _engine(cg.Compile(r"(\S+)@(\S+)")) == 3 and _engine(cg.Compile(r"(\w{1,40})-(\w{1,40})")) == 3
+    assert _engine(cg.Compile(r"(GET|POST) (/\S*)")) == 2      # 40 consuming instructions, 9 alive at once
+
+
 @pytest.mark.parametrize("lines", [1, 100, 4000, 100000])
 def test_c4_email_lines(lines):
     hay = cg.synth_host(cg.SYNTH_EMAIL, 0xC0FFEE + 4, 80 * lines)

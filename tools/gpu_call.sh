@@ -1,3 +1,6 @@
 #!/bin/bash
-# the call of the moment: whole tree on one B200 (tests, bench, reference arm, config 5, other configs)
-TEST_TIMEOUT=1500 bash tools/gpu_round2.sh ${1:-r04} tests bench c5 configs
+# the call of the moment: captures kernel forms + pipelined host submatch
+TAG=${1:-r06}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_pikevm.py -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1
+tail -25 gpurun_out/${TAG}_pytest.log | cut -c1-600
