@@ -98,6 +98,7 @@ def _load():
     L.cgx_scan_device.argtypes = [vp, u8p, sz, i64, C.c_int, C.c_void_p, sz, C.c_void_p, C.c_void_p]
     L.cgx_scan_shard_device.argtypes = [vp, u8p, sz, i64, i64, C.c_int, C.c_void_p, sz, C.c_void_p, C.c_void_p]
     L.cgx_scan_submatch_device.argtypes = [vp, u8p, sz, i64, C.c_void_p, sz, C.c_void_p, C.c_void_p]
+    L.cgx_scan_submatch_shard_device.argtypes = [vp, u8p, sz, i64, i64, C.c_void_p, sz, C.c_void_p, C.c_void_p]
     L.cgx_scan_records_device.argtypes = [vp, u8p, sz, C.c_void_p, sz, i64, C.c_void_p, sz, C.c_void_p, C.c_void_p,
                                           C.c_void_p]
     L.cgx_wire_bytes.restype = sz
@@ -291,9 +292,9 @@ class Regex:
                                             cap_pairs, rec_prefix_ptr, result_ptr, stream))
 
     def scan_submatch_device(self, d_ptr, length, out_ptr, cap_matches, result_ptr, base_offset=0,
-                             stream=0):
-        _check(_lib.cgx_scan_submatch_device(self._h, d_ptr, length, base_offset, out_ptr,
-                                             cap_matches, result_ptr, stream))
+                             stream=0, bytes_after=0):
+        _check(_lib.cgx_scan_submatch_shard_device(self._h, d_ptr, length, base_offset, bytes_after, out_ptr,
+                                                   cap_matches, result_ptr, stream))
 
 
 def Compile(pattern):

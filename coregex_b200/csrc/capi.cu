@@ -36,7 +36,7 @@ cudaError_t launch_flat_captures(const uint8_t* h, int64_t n, int64_t base, cons
 cudaError_t launch_pike_captures(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
                                  const unsigned long long* d_total, unsigned long long cap,
                                  const uint32_t* code, const uint32_t* sets, int start_pc, int nslots,
-                                 int64_t* out, cudaStream_t stream, bool large);
+                                 int64_t* out, cudaStream_t stream, bool large, bool text_end);
 }  // namespace cgx
 
 using namespace cgx;
@@ -717,7 +717,7 @@ static int submatch_locked(cgx_regex* re, const uint8_t* d_h, size_t len, int64_
   const uint32_t* sets = code + c.pike.code.size();
   CU(launch_pike_captures(d_h, (int64_t)len, base, (const int64_t*)re->d_pairs.p,
                           (const unsigned long long*)re->d_ticket_total.p, cap, code, sets, c.pike.start, nslots,
-                          d_out, st, c.pike.large));
+                          d_out, st, c.pike.large, after == 0));
   re->launches++;
   return CGX_OK;
 }
@@ -729,6 +729,15 @@ int cgx_scan_submatch_device(cgx_regex* re, const uint8_t* d_h, size_t len, int6
   int r = re->ensure_device();
   if (r) return r;
   return submatch_locked(re, d_h, len, base, d_out, cap, d_result, (cudaStream_t)stream);
+}
+
+int cgx_scan_submatch_shard_device(cgx_regex* re, const uint8_t* d_h, size_t len, int64_t base, int64_t bytes_after,
+                                   int64_t* d_out, size_t cap, uint64_t* d_result, void* stream) {
+  if (!re || base < 0 || bytes_after < 0) return CGX_ERR_ARGS;
+  std::lock_guard<std::mutex> lk(re->mu);
+  int r = re->ensure_device();
+  if (r) return r;
+  return submatch_locked(re, d_h, len, base, d_out, cap, d_result, (cudaStream_t)stream, bytes_after);
 }
 
 // Large host haystacks are cut at record delimiters into pieces that flow through

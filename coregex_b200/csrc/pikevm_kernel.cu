@@ -154,11 +154,20 @@ template <class Z>
 __global__ void pike_captures_kernel(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
                                      const unsigned long long* d_total, unsigned long long cap,
                                      const uint32_t* code, const uint32_t* sets, int start_pc, int nslots,
-                                     int64_t* out) {
+                                     int64_t* out, bool text_end) {
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long nmatches = *d_total < cap ? *d_total : cap;
   if (i >= nmatches) return;
   Vm vm{code, sets, h, n, matches[2 * i] - base, nslots, base == 0};
+  if (text_end && vm.s == n) {
+    // reference nfa/pikevm.go:2201-2206: a search that starts AT the end of the haystack answers
+    // from matchesEmptyAt and builds its captures from no slots at all — the groups of the empty
+    // match at the very end are reported unset (stdlib reports them as empty at n)
+    int64_t* o = out + i * (unsigned long long)nslots;
+    o[0] = o[1] = matches[2 * i];
+    for (int k = 2; k < nslots; k++) o[k] = -1;
+    return;
+  }
   ThreadList<Z> a, b;
   ThreadList<Z>* cur = &a;
   ThreadList<Z>* nxt = &b;
@@ -213,16 +222,16 @@ __global__ void pike_captures_kernel(const uint8_t* h, int64_t n, int64_t base, 
 cudaError_t launch_pike_captures(const uint8_t* h, int64_t n, int64_t base, const int64_t* matches,
                                  const unsigned long long* d_total, unsigned long long cap,
                                  const uint32_t* code, const uint32_t* sets, int start_pc, int nslots,
-                                 int64_t* out, cudaStream_t stream, bool large) {
+                                 int64_t* out, cudaStream_t stream, bool large, bool text_end) {
   if (cap == 0) return cudaSuccess;
   const int threads = 128;
   const unsigned long long blocks = (cap + threads - 1) / threads;
   if (large)
     pike_captures_kernel<Large><<<(unsigned)blocks, threads, 0, stream>>>(h, n, base, matches, d_total, cap, code,
-                                                                          sets, start_pc, nslots, out);
+                                                                          sets, start_pc, nslots, out, text_end);
   else
     pike_captures_kernel<Small><<<(unsigned)blocks, threads, 0, stream>>>(h, n, base, matches, d_total, cap, code,
-                                                                          sets, start_pc, nslots, out);
+                                                                          sets, start_pc, nslots, out, text_end);
   return cudaGetLastError();
 }
 

@@ -150,6 +150,12 @@ int cgx_scan_records_device(cgx_regex* re, const uint8_t* d_haystack, size_t len
 int cgx_scan_submatch_device(cgx_regex* re, const uint8_t* d_haystack, size_t len,
                              int64_t base_offset, int64_t* d_out, size_t cap_matches,
                              uint64_t* d_result, void* stream);
+/* ... of a shard that bytes_after more bytes of the logical haystack follow (as cgx_scan_shard_device):
+ * `\z`, the empty record behind a trailing delimiter and the reference's treatment of a match AT the
+ * end of the haystack (groups unset, nfa/pikevm.go:2201-2206) apply to the last shard only        */
+int cgx_scan_submatch_shard_device(cgx_regex* re, const uint8_t* d_haystack, size_t len,
+                                   int64_t base_offset, int64_t bytes_after, int64_t* d_out,
+                                   size_t cap_matches, uint64_t* d_result, void* stream);
 
 /* ---- compact offset wire format (multi-GPU offset gather, SURVEY.md §8e / BASELINE config 5) ----
  * The reference returns [][2]int (16 B per match, regex.go:710-723); between GPUs a shard's sorted

@@ -375,6 +375,28 @@ def test_record_engine_on_log_corpus_and_shards():
     assert np.array_equal(np.concatenate(parts), want)
 
 
+@pytest.mark.parametrize("pat", [r"\d*", r"(?m)^", r"a*", r"\b", r"(?m)$"])
+def test_nullable_patterns_in_two_shards(pat):
+    """The empty record after a shard's trailing delimiter is the FIRST record of the next shard: the
+    two shards' lists concatenated equal the list of the whole haystack (no empty match twice)."""
+    import torch
+    r, o = cg.Compile(pat), Oracle(pat)
+    assert r.engine == "pikevm"
+    for hay in [b"ab 12\n\nx9\n" * 700 + b"tail 7", b"a\n" * 5000, b"12\n" * 3000 + b"\n"]:
+        want = o.find_all(hay)
+        for cut in sorted({hay.find(b"\n", len(hay) // 3) + 1, hay.rfind(b"\n") + 1} - {len(hay)}):  # no empty shard
+            parts = []
+            for piece, base, after in ((hay[:cut], 0, len(hay) - cut), (hay[cut:], cut, 0)):
+                t = torch.frombuffer(bytearray(piece + b"\0" * 16), dtype=torch.uint8).cuda()
+                res = torch.zeros(2, dtype=torch.int64, device="cuda")
+                out = torch.empty((len(want) + 8, 2), dtype=torch.int64, device="cuda")
+                r.scan_device(t.data_ptr(), len(piece), cg.MODE_FINDALL, out.data_ptr(), out.shape[0], res.data_ptr(),
+                              base_offset=base, bytes_after=after)
+                torch.cuda.synchronize()
+                parts.append(out[: int(res[0].item())].cpu().numpy())
+            assert np.array_equal(np.concatenate(parts), want), (pat, len(hay), cut)
+
+
 # ---- patterns whose matches can contain '\n': records are cut at another byte the pattern cannot consume ----
 NON_LF_GPU = [r"\s+", r"[^a]+", r"[a-z]+\s+[a-z]+", r"\W+", r"[^e]{3}", r"\D+", r"[\s,]+"]
 

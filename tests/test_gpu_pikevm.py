@@ -202,3 +202,28 @@ def test_pipelined_host_submatch_matches_oracle():
     env = dict(os.environ, CGX_PIPELINE_PIECE=str(160 * 1024))
     p = subprocess.run([sys.executable, "-c", _PIPE_SUB_CHILD, ROOT], env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout + p.stderr
+
+
+def test_groups_of_the_empty_match_at_the_end_of_the_haystack_are_unset():
+    """Reference nfa/pikevm.go:2201-2206: a capture search that starts AT len(haystack) answers from
+    matchesEmptyAt and builds the result from no slots — `(a*)(\\d*)` on "x" is [0 0 0 0 0 0] and
+    [1 1 -1 -1 -1 -1] (stdlib: [1 1 1 1 1 1]).  Restated in the oracle, reproduced by the captures kernel,
+    for the LAST shard only."""
+    import torch
+    assert cg.Compile(r"(a*)(\d*)").FindAllSubmatchIndex(b"x") == [[0, 0, 0, 0, 0, 0], [1, 1, -1, -1, -1, -1]]
+    assert cg.Compile(r"(\d*)").FindAllSubmatchIndex(b"") == [[0, 0, -1, -1]]
+    for pat in [r"(a*)(\d*)", r"(\d*)", r"(x?)(y?)"]:
+        check(pat, cg.synth_host(cg.SYNTH_LOG, 22, 4096 * 20)[:70001])
+        check(pat, b"ab 12\n\nx9\n")
+    # two shards: the first shard's end is not the end of the haystack
+    pat, hay = r"(a*)(\d*)", b"ab 12\nxa7\n"
+    r, want = cg.Compile(pat), Oracle(pat).find_all_submatch(b"ab 12\nxa7\n")
+    parts = []
+    for piece, base, after in ((hay[:6], 0, 4), (hay[6:], 6, 0)):
+        t = torch.frombuffer(bytearray(piece + b"\0" * 16), dtype=torch.uint8).cuda()
+        res = torch.zeros(2, dtype=torch.int64, device="cuda")
+        out = torch.empty((64, 6), dtype=torch.int64, device="cuda")
+        r.scan_submatch_device(t.data_ptr(), len(piece), out.data_ptr(), 64, res.data_ptr(), base_offset=base, bytes_after=after)
+        torch.cuda.synchronize()
+        parts.append(out[: int(res[0].item())].cpu().numpy())
+    assert np.array_equal(np.concatenate(parts), want)
