@@ -12,6 +12,8 @@ import os
 
 import numpy as np
 
+from .wrappers import RegexWrappers, quote_meta as QuoteMeta  # noqa: E402  (reference regex.go:233)
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "lib", "libcoregex_b200.so")
 
@@ -88,6 +90,8 @@ def _load():
     L.cgx_engine.restype = C.c_char_p
     L.cgx_engine.argtypes = [vp]
     L.cgx_num_captures.argtypes = [vp]
+    L.cgx_subexp_name.restype = C.c_char_p
+    L.cgx_subexp_name.argtypes = [vp, C.c_int]
     L.cgx_delimiter.argtypes = [vp]
     L.cgx_debug_set_bitstream.argtypes = [vp, C.c_int]
     L.cgx_last_error.restype = C.c_char_p
@@ -142,10 +146,12 @@ def _host_buf(b):
     return a.ctypes.data, a.size, a
 
 
-class Regex:
-    """A compiled pattern.  Mirrors reference regex.go `type Regex` for the bulk-scan path."""
+class Regex(RegexWrappers):
+    """A compiled pattern.  Mirrors reference regex.go `type Regex`: the searches below run on the
+    device; the text / replace / split forms (wrappers.py) are host plumbing over their results."""
 
     def __init__(self, pattern, config=None):
+        self._config = config
         if isinstance(pattern, str):
             pattern = pattern.encode()
         self._pattern = pattern
@@ -170,6 +176,10 @@ class Regex:
     def Longest(self):
         """reference regex.go:464: leftmost-longest matching for all later searches."""
         _check(_lib.cgx_set_longest(self._h, 1))
+        self._longest = True
+
+    def _subexp_name(self, i):
+        return _lib.cgx_subexp_name(self._h, i).decode()
 
     # -- introspection --------------------------------------------------------------------------
     def String(self):
@@ -209,8 +219,6 @@ class Regex:
         m = C.c_int(0)
         _check(_lib.cgx_is_match(self._h, p, n, C.byref(m)))
         return bool(m.value)
-
-    MatchString = Match
 
     def Count(self, b, n=-1):
         p, ln, keep = _host_buf(b)
@@ -313,6 +321,16 @@ def MustCompile(pattern):
         return Regex(pattern)
     except Error as e:
         raise Error("regexp: Compile(`%s`): %s" % (pattern if isinstance(pattern, str) else pattern.decode(), e))
+
+
+def Match(pattern, b):
+    """reference regex.go:170: compile + Match in one call"""
+    return Regex(pattern).Match(b)
+
+
+def MatchString(pattern, s):
+    """reference regex.go:181"""
+    return Regex(pattern).MatchString(s)
 
 
 # ---- synthetic corpora (bench / tests) ----------------------------------------------------------

@@ -404,6 +404,10 @@ const char* cgx_engine(const cgx_regex* re) {
   return re->c->engine_name.c_str();
 }
 int cgx_num_captures(const cgx_regex* re) { return re->c->prog.num_captures; }
+const char* cgx_subexp_name(const cgx_regex* re, int i) {
+  if (!re || i < 0 || i >= (int)re->c->prog.cap_names.size()) return "";
+  return re->c->prog.cap_names[i].c_str();
+}
 uint64_t cgx_launch_count(const cgx_regex* re) { return re->launches.load(); }
 // 1: the NVRTC-specialised kernel is in use, -1: unavailable (generic kernel; cgx_last_error has
 // the reason after this call), 0: no device scan has happened yet / pattern not on that engine

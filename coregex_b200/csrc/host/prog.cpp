@@ -507,6 +507,12 @@ std::string build(const Regexp* re, Prog& out, bool reverse) {
   if (start < 0) return b.err.empty() ? "compile failed" : b.err;
   out.start = start;
   out.num_captures = MaxCap(re) + 1;
+  out.cap_names.assign(out.num_captures, "");
+  std::function<void(const Regexp*)> names = [&](const Regexp* x) {
+    if (x->op == OpCapture && x->cap > 0 && x->cap < out.num_captures) out.cap_names[x->cap] = x->name;
+    for (const Regexp* sub : x->sub) names(sub);
+  };
+  names(re);
   out.anchored_start = patternAnchored(re);
   return "";
 }

@@ -43,6 +43,7 @@ struct Prog {
   std::vector<ByteSet> sets;
   int start = 0;          // anchored entry
   int num_captures = 1;   // groups incl. group 0
+  std::vector<std::string> cap_names;  // num_captures entries; "" for group 0 and unnamed groups
   bool anchored_start = false;  // pattern begins with \A (reference nfa/compile.go:1755-1775)
   bool has_looks = false;
   bool has_word_looks = false;

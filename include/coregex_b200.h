@@ -90,6 +90,9 @@ const char* cgx_engine(const cgx_regex* re);
 int cgx_delimiter(const cgx_regex* re);
 /* reference meta.Engine.NumCaptures() (meta/engine.go:232): groups including group 0          */
 int cgx_num_captures(const cgx_regex* re);
+/* reference meta.Engine.SubexpNames() (regex.go:575): name of group i ("" for group 0, unnamed groups
+ * and i out of range); the pointer lives as long as the regex                                    */
+const char* cgx_subexp_name(const cgx_regex* re, int i);
 const char* cgx_last_error(void);
 
 /* ---- host-buffer searches (haystack in host memory; H2D/D2H inside the call) ----------------
