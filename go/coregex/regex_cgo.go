@@ -184,3 +184,54 @@ func (r *Regex) FindAllSubmatchIndex(b []byte, n int) [][]int {
 		capM = int(c)
 	}
 }
+
+// SubexpNames mirrors reference regex.go:575 (names[0] == "").
+func (r *Regex) SubexpNames() []string {
+	names := make([]string, r.NumSubexp()+1)
+	for i := range names {
+		names[i] = C.GoString(C.cgx_subexp_name(r.h, C.int(i)))
+	}
+	return names
+}
+
+// ReplaceAllLiteral mirrors reference regex.go:790.  The reference walks the haystack match by match
+// (FindIndicesAt from the previous end, :797-840); that walk IS the FindAllIndex loop, so here it is
+// one batch call and a stitch.
+func (r *Regex) ReplaceAllLiteral(src, repl []byte) []byte {
+	pairs := r.AppendAllIndex(nil, src, -1)
+	out := make([]byte, 0, len(src))
+	last := 0
+	for _, m := range pairs {
+		out = append(out, src[last:m[0]]...)
+		out = append(out, repl...)
+		last = m[1]
+	}
+	return append(out, src[last:]...)
+}
+
+// Split mirrors reference regex.go:1288 (same skips of an empty match at 0 and at len(s)).
+func (r *Regex) Split(s string, n int) []string {
+	if n == 0 {
+		return nil
+	}
+	idx := r.FindAllStringIndex(s, -1)
+	if len(idx) == 0 {
+		return []string{s}
+	}
+	var out []string
+	last := 0
+	for _, m := range idx {
+		if last == 0 && m[0] == 0 && m[1] == 0 {
+			continue
+		}
+		if m[0] == len(s) && m[1] == len(s) {
+			break
+		}
+		out = append(out, s[last:m[0]])
+		last = m[1]
+		if n > 0 && len(out) >= n-1 {
+			return append(out, s[last:])
+		}
+	}
+	return append(out, s[last:])
+}
