@@ -323,6 +323,26 @@ def MustCompile(pattern):
         raise Error("regexp: Compile(`%s`): %s" % (pattern if isinstance(pattern, str) else pattern.decode(), e))
 
 
+def CompilePOSIX(pattern):
+    """reference regex.go:146: Compile + Longest()"""
+    re = Regex(pattern)
+    re.Longest()
+    return re
+
+
+def MustCompilePOSIX(pattern):
+    """reference regex.go:159"""
+    try:
+        return CompilePOSIX(pattern)
+    except Error as e:
+        raise Error("regexp: CompilePOSIX(`%s`): %s" % (pattern if isinstance(pattern, str) else pattern.decode(), e))
+
+
+def MatchReader(pattern, reader):
+    """reference regex.go:1672"""
+    return Regex(pattern).MatchReader(reader)
+
+
 def Match(pattern, b):
     """reference regex.go:170: compile + Match in one call"""
     return Regex(pattern).Match(b)

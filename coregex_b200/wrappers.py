@@ -252,6 +252,22 @@ class RegexWrappers:
         parts = split(b, self.FindAllIndex(b, -1) or [], n)
         return None if parts is None else [_s(p) for p in parts]
 
+    # -- readers (reference regex.go:1619-1670: the reference drains the RuneReader into a string and
+    # calls the string form; a Python text stream's read() is that drain)
+    @staticmethod
+    def _drain(reader):
+        data = reader.read()
+        return data if isinstance(data, str) else _s(data)
+
+    def MatchReader(self, reader):
+        return self.MatchString(self._drain(reader))
+
+    def FindReaderIndex(self, reader):
+        return self.FindStringIndex(self._drain(reader))
+
+    def FindReaderSubmatchIndex(self, reader):
+        return self.FindStringSubmatchIndex(self._drain(reader))
+
     # -- group names, copies, text marshalling (reference regex.go:575-604, :1585-1616)
     def SubexpNames(self):
         return [self._subexp_name(i) for i in range(self.NumSubexp() + 1)]

@@ -100,6 +100,9 @@ def test_func_and_text_forms(kind):
     assert e.FindAllSubmatch(b"a@b.c", -1) == [[b"a@b.c", b"a", b"b", b"c"]]
     o = _mk(kind, r"(a)|(b)")
     assert o.FindSubmatch(b"b") == [b"b", None, b"b"] and o.FindStringSubmatch("b") == ["b", "", "b"]
+    import io
+    assert r.MatchReader(io.StringIO("abc 7")) and not r.MatchReader(io.StringIO("abc"))           # regex.go:1619
+    assert r.FindReaderIndex(io.StringIO("ab 77")) == [3, 5] and e.FindReaderSubmatchIndex(io.StringIO("a@b.c")) == [0, 5, 0, 1, 2, 3, 4, 5]
     u = _mk(kind, "мир")
     assert u.FindStringIndex("привет мир") == [13, 19] and u.ReplaceAllString("привет мир", "world") == "привет world"
     assert u.Split("aмирb", -1) == ["a", "b"]
@@ -113,5 +116,9 @@ def test_quote_meta_and_names():
     assert (r.SubexpIndex("year"), r.SubexpIndex("month"), r.SubexpIndex("day"), r.SubexpIndex("")) == (1, 2, -1, -1)
     assert cg.Compile(r"(?P<bob>a+)(?P<bob>b+)|(c)").SubexpIndex("bob") == 1                   # :582-585
     assert cg.Compile(r"(a)(?:b)(?P<n>c)").SubexpNames() == ["", "", "n"]
+    with pytest.raises(cg.Error) as ei:
+        cg.MustCompilePOSIX("a(")
+    assert str(ei.value).startswith("regexp: CompilePOSIX(`a(`): error parsing regexp: missing closing )")   # regex.go:162
+    assert cg.CompilePOSIX("a+|a+b").String() == "a+|a+b"
     c = r.Copy()
     assert c.String() == r.String() and c is not r and r.MarshalText() == rb"(?P<year>\d+)-(?P<month>\d+)"
