@@ -1,5 +1,5 @@
 #!/bin/bash
-TAG=${1:-r10}
+TAG=${1:-r11}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_wrappers.py -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1
-tail -40 gpurun_out/${TAG}_pytest.log | cut -c1-500
+timeout 500 python -m pytest tests/test_ref_patterns.py tests/test_cpp_header.py -m gpu -q --durations=3 > gpurun_out/${TAG}_pytest.log 2>&1
+tail -30 gpurun_out/${TAG}_pytest.log | cut -c1-1500
