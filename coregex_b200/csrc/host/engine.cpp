@@ -514,7 +514,10 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
     // forward DFA pass for the match end, one reverse DFA pass for its start — per record, linear.
     int first = 0;
     for (int b = 0; b < 256; b++) first += set_has(c->dfa.first_bytes, b) ? 1 : 0;
-    if (!c->flat.nops && first > 64) {
+    // (the record engine marks delimiters with the SWAR byte test of phase A, which holds for bytes
+    // below 0x80 only: a pattern whose only safe delimiters are high bytes — `\P{Han}+`, cut at
+    // 0xC0 — stays on the candidate + anchored-walk engine)
+    if (!c->flat.nops && first > 64 && c->delim < 0x80) {
       Prog rprog;
       if (CompileReverseProg(pr.re, rprog).empty() &&
           BuildDFA(c->prog, /*anchored=*/false, 160, c->udfa).empty() &&

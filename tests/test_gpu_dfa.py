@@ -293,7 +293,8 @@ def test_pipelined_host_path_matches_oracle(tmp_path):
 UTF8_GPU = [r"a.c", r"foo.*bar", r"[^a\n]+", r"\S+", r"[α-ω]+", r"key=[^\s;]+", r"[^\d\n]{2,3}", r"x.y.z",
             r"[а-я]+ [а-я]+", r"(?i)straße|x.z", r"GET .* HTTP", r"[^\x00-\x{7FF}\n]+", r"é+",
             # Unicode property classes (generated 15.0.0 tables, shared-prefix/suffix UTF-8 automata)
-            r"\pL+", r"\p{Lu}\p{Ll}+", r"\p{Greek}+", r"\pN+", r"\p{Cyrillic}+ \p{Cyrillic}+", r"(?i)[а-в]+", r"\P{L}+", r"\p{Han}+"]
+            r"\pL+", r"\p{Lu}\p{Ll}+", r"\p{Greek}+", r"\pN+", r"\p{Cyrillic}+ \p{Cyrillic}+", r"(?i)[а-в]+", r"\P{L}+", r"\p{Han}+",
+            r"\P{Han}+", r"\P{Greek}+x"]
 
 
 def _utf8_corpus(rng, n):

@@ -56,6 +56,16 @@ def test_unicode_property_classes_compile_to_the_table_engines():
         assert msg in str(ei.value)
 
 
+def test_record_engine_needs_an_ascii_delimiter():
+    # found by the sweep over the reference's test patterns: `\P{Han}+` can contain every ASCII byte, its
+    # record delimiter is 0xC0, and the record engine's phase A marks delimiters with a SWAR test that
+    # is exact below 0x80 only — such patterns stay on the candidate + anchored-walk engine
+    for pat in [r"\P{Han}+", r"\P{Greek}+"]:
+        r = cg.Compile(pat)
+        assert r.delimiter[0] >= 0x80 and r.engine != "line-dfa", (pat, r.engine, r.delimiter)
+    assert cg.Compile(r"[^\x00-\x7f]+").engine == "line-dfa"
+
+
 def test_unsupported_patterns_fail_loudly():
     # matches that may contain every byte value leave no record delimiter: one record, one lane
     for pat in [r"(?s)x.y", r"(?s).+", r"(?m)^POST\s+\S+"]:
@@ -216,7 +226,9 @@ UTF8_PATTERNS = [r"a.c", r"foo.*bar", r"[^a\n]+", r"\S+", r"[α-ω]+", r"x.y.z",
                  r"[\x{7F0}-\x{810}]+", r"[\x{D700}-\x{E010}]", r"[^\d\n]{2,3}", r"[^x\n]{3}y",
                  # Unicode property classes: large tables take the shared-prefix/suffix emission (host/prog.cpp emitShared)
                  r"\pL+", r"\pL", r"\p{Lu}\p{Ll}+", r"\p{Greek}+", r"[\p{Lu}\d]+x", r"\pN+", r"\p{Han}", r"\pS", r"(?i)\p{Lu}+",
-                 r"\p{Latin}+", r"(?i)[а-в]+", r"(?i)я"]
+                 r"\p{Latin}+", r"(?i)[а-в]+", r"(?i)я",
+                 # only high bytes are safe record delimiters: not the record engine (its delimiter test is 7-bit SWAR)
+                 r"\P{Han}+", r"\P{Greek}+x"]
 
 
 @pytest.mark.parametrize("pat", UTF8_PATTERNS)
