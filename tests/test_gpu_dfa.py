@@ -294,7 +294,9 @@ UTF8_GPU = [r"a.c", r"foo.*bar", r"[^a\n]+", r"\S+", r"[α-ω]+", r"key=[^\s;]+"
             r"[а-я]+ [а-я]+", r"(?i)straße|x.z", r"GET .* HTTP", r"[^\x00-\x{7FF}\n]+", r"é+",
             # Unicode property classes (generated 15.0.0 tables, shared-prefix/suffix UTF-8 automata)
             r"\pL+", r"\p{Lu}\p{Ll}+", r"\p{Greek}+", r"\pN+", r"\p{Cyrillic}+ \p{Cyrillic}+", r"(?i)[а-в]+", r"\P{L}+", r"\p{Han}+",
-            r"\P{Han}+", r"\P{Greek}+x"]
+            r"\P{Han}+", r"\P{Greek}+x",
+            # every ASCII byte can be part of a match: the record delimiter is a high byte
+            r"[\x00-\x7f]+", r"[\x00-\x7f]+x", r"[\x01-\x7f]+"]
 
 
 def _utf8_corpus(rng, n):
