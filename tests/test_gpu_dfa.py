@@ -237,7 +237,9 @@ def test_overlap_chain_dense_single_line():
     # every byte a candidate, matches back to back and overlapping candidates inside each match
     check(r"\d\d\d", b"1234567890" * 9000)
     check(r"aa", b"a" * 70001)
-    check(r"[a-c][a-z]*x", b"abcabcx" * 9000 + b"\n" + b"aaaa" * 5000)
+    # (the tail is quadratic by construction — every byte a candidate whose walk runs to the end of the
+    # record — in the reference's anchored-verify strategies as here: 6 KB keep the suite short)
+    check(r"[a-c][a-z]*x", b"abcabcx" * 9000 + b"\n" + b"aaaa" * 1500)
 
 
 # ---- pipelined host path (H2D | scan | D2H over delimiter-cut pieces) ---------------------------------
