@@ -259,7 +259,7 @@ def parity_windows(cg, out, matches, n, first_block, k, seed=SEED, kind=None, pa
     picks.add(0)
     while len(picks) < min(k, nwin):
         picks.add(int(rng.integers(0, nwin)))
-    starts = out[:matches, 0]
+    starts = out[:matches, 0].contiguous()  # searchsorted wants a dense boundary tensor (parity check, untimed)
     base = first_block * 4096
     checked, above = 0, 0
     for w in sorted(picks):

@@ -1,7 +1,9 @@
 #!/bin/bash
-# the call of the moment: whole GPU suite, four workers on the one GPU (the tests are host-bound)
-TAG=${1:-r12}
+# the call of the moment: smoke + the bench line + the reference arm on the final tree
+TAG=${1:-r13}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -n 4 --durations=8 > gpurun_out/${TAG}_pytest.log 2>&1
-echo "pytest exit $?" | tee -a gpurun_out/${TAG}_pytest.log
-tail -40 gpurun_out/${TAG}_pytest.log | cut -c1-400
+timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+timeout 300 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+cut -c1-400 gpurun_out/${TAG}_bench.json; tail -2 gpurun_out/${TAG}_bench.err
+timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
+cut -c1-300 gpurun_out/${TAG}_bench_ref.json
