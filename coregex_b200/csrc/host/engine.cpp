@@ -8,10 +8,10 @@ namespace cgx {
 
 using namespace gosyntax;
 
-bool BuildTeddyTables(const std::vector<std::string>& patterns, TeddyTables& t) {
+bool BuildTeddyTables(const std::vector<std::string>& patterns, TeddyTables& t, size_t max_patterns) {
   t = TeddyTables();
   const size_t n = patterns.size();
-  if (n < 2 || n > 64) return false;
+  if (n < 2 || n > max_patterns) return false;
   size_t mn = patterns[0].size(), mx = 0;
   for (auto& p : patterns) {
     if (p.size() < 3) return false;
@@ -29,25 +29,17 @@ bool BuildTeddyTables(const std::vector<std::string>& patterns, TeddyTables& t) 
     t.bytes.insert(t.bytes.end(), p.begin(), p.end());
     t.offs.push_back((int32_t)t.bytes.size());
   }
-  uint16_t lo[2][16] = {}, hi[2][16] = {};
+  uint16_t exact[2][256] = {};
   t.bucket_of.resize(n);
   std::vector<std::vector<uint16_t>> buckets(t.nbuckets);
   for (size_t id = 0; id < n; id++) {
     int b = (int)(id % t.nbuckets);
     t.bucket_of[id] = (uint8_t)b;
     buckets[b].push_back((uint16_t)id);
-    for (int pos = 0; pos < 2; pos++) {
-      uint8_t c = (uint8_t)patterns[id][pos];
-      lo[pos][c & 15] |= (uint16_t)(1u << b);
-      hi[pos][c >> 4] |= (uint16_t)(1u << b);
-    }
+    for (int pos = 0; pos < 2; pos++) exact[pos][(uint8_t)patterns[id][pos]] |= (uint16_t)(1u << b);
   }
-  t.fp0.resize(256);
-  t.fp1.resize(256);
-  for (int c = 0; c < 256; c++) {
-    t.fp0[c] = lo[0][c & 15] & hi[0][c >> 4];
-    t.fp1[c] = lo[1][c & 15] & hi[1][c >> 4];
-  }
+  t.fp0.assign(exact[0], exact[0] + 256);
+  t.fp1.assign(exact[1], exact[1] + 256);
   t.bucket_off.push_back(0);
   for (auto& b : buckets) {
     for (uint16_t id : b) t.order_simd.push_back(id);
@@ -405,6 +397,27 @@ int CompilePattern(const std::string& pattern, std::unique_ptr<Compiled>& out, s
     if (!has_nl && BuildTeddyTables(pats, c->teddy)) {
       c->kind = ENG_TEDDY;
       c->engine_name = c->teddy.nbuckets == 16 ? "fat-teddy" : "teddy";
+    }
+  }
+  // More than 64 complete literals: the reference's Aho-Corasick strategy (meta/strategy.go:1165; the
+  // automaton is the external module github.com/coregx/ahocorasick, not in the reference tree).  What
+  // it returns is the leftmost match, and among literals that start there the first of the
+  // alternation.  When no literal is a prefix of another, at most one literal matches at a position,
+  // the order of verification cannot be observed, and the set runs on the multi-literal engine with
+  // 16 buckets (fingerprint filter + byte-for-byte verification) instead of a DFA that does not fit
+  // the table kernels.  Sets with prefix-related literals keep the generic engines.
+  if (c->an.strategy == RS_UseAhoCorasick && !c->an.has_anchors) {
+    std::vector<std::string> pats;
+    for (auto& l : c->an.prefixes) pats.push_back(l.bytes);
+    bool ok = true;
+    for (size_t i = 0; i < pats.size() && ok; i++) {
+      if (pats[i].find('\n') != std::string::npos) ok = false;
+      for (size_t j = 0; j < pats.size() && ok; j++)
+        if (i != j && pats[j].size() >= pats[i].size() && pats[j].compare(0, pats[i].size(), pats[i]) == 0) ok = false;
+    }
+    if (ok && BuildTeddyTables(pats, c->teddy, 1024)) {
+      c->kind = ENG_TEDDY;
+      c->engine_name = "teddy-large";
     }
   }
 

@@ -231,7 +231,15 @@ __device__ int64_t teddy_verify_scalar(const Ctx& c, int64_t p) {
 
 // batch verify from window index i0; returns end window index or -1
 __device__ __forceinline__ int teddy_walk(const Ctx& c, int i0) {
-  const uint32_t m = teddy_mask(c, c.sm.win[i0], c.sm.win[i0 + 1]);
+  // The last position of the window has its second byte outside it (win[wend] is the sentinel, not
+  // haystack): a long record that the owner follows beyond its window can start a literal exactly
+  // there, so that byte comes from the haystack itself.
+  uint32_t b1 = c.sm.win[i0 + 1];
+  if (i0 + 1 >= c.wend) {
+    if (c.gw + i0 + 1 >= c.a.n) return -1;  // a literal has three bytes or more
+    b1 = byte_at(c, c.gw + i0 + 1);
+  }
+  const uint32_t m = teddy_mask(c, c.sm.win[i0], b1);
   if (!m) return -1;
   const int64_t e = teddy_verify(c, c.gw + i0, m);
   return e < 0 ? -1 : (int)(e - c.gw);

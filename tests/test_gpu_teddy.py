@@ -67,6 +67,49 @@ def test_reference_large_literal_sets():
         assert got.shape == want.shape and np.array_equal(got, want), (r.engine, len(h))
 
 
+def _words(n, seed=1, length=6):
+    import random
+    rnd = random.Random(seed)
+    out = []
+    while len(out) < n:
+        w = "".join(rnd.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(length + len(out) % 3))
+        if not any(x.startswith(w) or w.startswith(x) for x in out):
+            out.append(w)
+    return out
+
+
+@pytest.mark.parametrize("n", [70, 130, 250])
+def test_large_prefix_free_sets_run_on_the_literal_engine(n):
+    """68..255 complete literals are the reference's Aho-Corasick strategy (meta/strategy.go:1165, the
+    automaton an external module).  A prefix-free set has at most one literal per start position, so
+    the multi-literal engine (16 buckets, exact byte fingerprints, byte-for-byte verification) returns
+    the leftmost-first list — compared with the oracle on text made of the words, their truncations
+    and one-letter corruptions."""
+    words = _words(n)
+    pat = "|".join(words)
+    r, o = cg.Compile(pat), Oracle(pat)
+    assert o.strategy == "UseAhoCorasick" and r.strategy == "UseAhoCorasick" and r.engine == "teddy-large", (r.strategy, r.engine)
+    rng = np.random.default_rng(n)
+    pieces = [w.encode() for w in words] + [w[:-1].encode() for w in words[:40]] + [(w[:2] + "Q" + w[3:]).encode() for w in words[:40]]
+    pieces += [b" ", b" ", b"\n", b"", b"zz", b","]
+    for size in (0, 5, 400, 30000):
+        hay = b"".join(pieces[int(i)] + (b" " if rng.integers(0, 3) else b"") for i in rng.integers(0, len(pieces), size))
+        want = o.find_all(hay)
+        got = r.find_all_index_array(hay)
+        assert got.shape == want.shape and np.array_equal(got, want), (n, size)
+        assert r.Count(hay) == len(want) and r.Match(hay) == (len(want) > 0)
+    big = cg.synth_host(cg.SYNTH_TEXT, 900 + n, 4096 * 600, literals=[w.encode() for w in words[:64]])
+    assert np.array_equal(r.find_all_index_array(big), o.find_all(big))
+
+
+def test_large_sets_with_prefix_related_literals_keep_the_generic_engines():
+    words = _words(70) + ["zzzzzzq", "zzzzzzqx"]
+    r = cg.Compile("|".join(words))
+    assert r.engine != "teddy-large"
+    hay = b"a zzzzzzqx b " + " ".join(words[:30]).encode()
+    assert np.array_equal(r.find_all_index_array(hay), Oracle("|".join(words)).find_all(hay))
+
+
 def test_fixture_corpus():
     corpus = open(os.path.join(ROOT, "tests", "golden", "stdlib_corpus.txt"), "rb").read()
     check("error|warning|fatal|critical", corpus)
@@ -117,6 +160,11 @@ def test_dense_and_boundaries():
     for off in range(31744 - 8, 31744 + 3):
         check("error|warning|fatal|critical", b"x" * off + b"critical error\nfatal")
     check("error|warning|fatal|critical", b"z" * 100000 + b"warning")
+    # a record that runs past its owner's window (31744 + 1024 bytes) with a literal starting at the
+    # last positions of that window: the second / third fingerprint byte lies outside the window
+    for off in range(32768 - 9, 32768 + 3):
+        check("error|warning|fatal|critical", b"x" * off + b"critical error fatal\nwarning")
+        check("error|warning|fatal|critical", b"y" * 31744 + b"x" * off + b"errorfatalerror\n")
 
 
 def test_c3_sized_properties_512mb():

@@ -89,6 +89,10 @@ def test_literal_sets_stay_on_the_multi_literal_engines():
     lit64 = ["k%02dz%s" % (i, "q" * (i % 4)) for i in range(64)]
     assert cg.Compile("|".join(lit16)).engine == "teddy"
     assert cg.Compile("|".join(lit64)).engine == "fat-teddy"
+    # 68..255 complete, prefix-free literals (the reference's Aho-Corasick strategy): same engine, 16 buckets
+    big = ["w%03dx%s" % (i, "abcdefghij"[i % 10] * (i % 3)) for i in range(0, 990, 9)]
+    r = cg.Compile("|".join(big))
+    assert (r.strategy, r.engine) in (("UseAhoCorasick", "teddy-large"), ("UseNFA", r.engine)), (r.strategy, r.engine)
 
 
 def test_no_device_means_error_not_fallback():

@@ -1,9 +1,5 @@
 #!/bin/bash
-# the call of the moment: smoke + the bench line + the reference arm on the final tree
-TAG=${1:-r13}
+TAG=${1:-r16}
 mkdir -p gpurun_out
-timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
-timeout 300 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
-cut -c1-400 gpurun_out/${TAG}_bench.json; tail -2 gpurun_out/${TAG}_bench.err
-timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
-cut -c1-300 gpurun_out/${TAG}_bench_ref.json
+timeout 400 python -m pytest tests/test_gpu_teddy.py -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1
+tail -8 gpurun_out/${TAG}_pytest.log | cut -c1-600

@@ -114,5 +114,14 @@ if __name__ == "__main__":
         int(1 * GIB * scale))
     run("X3 UTF-8 dot `\"[A-Z]+ .*\" 200`, 1 GB log lines", r'"[A-Z]+ .*" 200', cg.SYNTH_LOG, 0xC0FFEE + 2,
         int(1 * GIB * scale))
+    # 200 prefix-free literals: the reference's Aho-Corasick strategy, here the literal engine with 16 buckets
+    import random
+    rnd, big = random.Random(1), []
+    while len(big) < 200:
+        w = "".join(rnd.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(6 + len(big) % 3))
+        if not any(x.startswith(w) or w.startswith(x) for x in big):
+            big.append(w)
+    run("X5 200 literals (Aho-Corasick strategy), 1 GB text", "|".join(big), cg.SYNTH_TEXT, 0xC0FFEE + 6,
+        int(1 * GIB * scale), literals=[w.encode() for w in big[:64]])
     run("X4 char-class runs `\\w+` (dense output), 1 GB log lines", r"\w+", cg.SYNTH_LOG, 0xC0FFEE + 2, int(1 * GIB * scale),
         cap_div=4)
