@@ -110,6 +110,67 @@ def test_oracle_equals_stdlib_semantics_on_every_reference_test_pattern():
     assert stats["equal"] >= 500, stats
 
 
+def test_oracle_captures_equal_stdlib_semantics_on_every_reference_test_pattern():
+    """The same sweep for FindAllSubmatchIndex: every pattern with capture groups (125 of the 570)
+    against Python `re` group spans.  One reference rule is applied to the expected side: the groups
+    of the empty match AT len(haystack) are unset (nfa/pikevm.go:2201-2206)."""
+    ascii_hay, _ = haystacks()
+    equal, bad = 0, []
+
+    def on_alarm(*_):
+        raise _Timeout()
+
+    old = signal.signal(signal.SIGALRM, on_alarm)
+    try:
+        for p in PATS:
+            try:
+                o = Oracle(p)
+            except OracleError:
+                continue
+            if o.num_captures < 2 or any(ord(ch) > 127 for ch in p) or "[:" in p or "{," in p or r"\C" in p:
+                continue
+            try:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("error")
+                    rx = re.compile(p.encode())
+            except Exception:
+                continue
+            signal.alarm(5)
+            try:
+                want, last, prev_empty_at, comparable = [], -1, -1, True
+                for m in rx.finditer(ascii_hay):
+                    s, e = m.start(), m.end()
+                    if e > s and s == prev_empty_at:
+                        comparable = False   # see _go_find_all
+                        break
+                    prev_empty_at = s if s == e else -1
+                    if s == e and s == last:
+                        continue
+                    row = [s, e]
+                    for g in range(1, rx.groups + 1):
+                        row += [m.start(g), m.end(g)]
+                    want.append(row)
+                    if e > s:
+                        last = e
+            except _Timeout:
+                continue
+            finally:
+                signal.alarm(0)
+            if not comparable:
+                continue
+            got = o.find_all_submatch(ascii_hay).tolist()
+            if want and got and want[-1][0] == len(ascii_hay) == got[-1][0]:
+                want[-1] = [want[-1][0], want[-1][1]] + [-1] * (len(want[-1]) - 2)
+            if got == want:
+                equal += 1
+            else:
+                bad.append(p)
+    finally:
+        signal.signal(signal.SIGALRM, old)
+    assert not bad, bad[:10]
+    assert equal >= 110, equal
+
+
 def test_product_and_oracle_accept_the_same_patterns():
     for p in PATS:
         try:

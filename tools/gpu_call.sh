@@ -1,5 +1,6 @@
 #!/bin/bash
-TAG=${1:-r16}
+# the call of the moment: the bench line on the final tree
+TAG=${1:-r17}
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests/test_gpu_teddy.py -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1
-tail -8 gpurun_out/${TAG}_pytest.log | cut -c1-600
+timeout 100 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+cut -c1-260 gpurun_out/${TAG}_bench.json; tail -2 gpurun_out/${TAG}_bench.err | cut -c1-300
