@@ -393,3 +393,20 @@ def test_ast_dump_fixture():
     assert len(fixture) >= 100
     for pat, want in fixture.items():
         assert dump_ast(pat) == want, pat
+
+
+def fa_sub(p, h):
+    return Oracle(p).find_all_submatch(h).tolist()
+
+
+def test_end_of_haystack_capture_shortcut_depends_on_where_the_search_starts():
+    """Reference nfa/pikevm.go:2201-2206: a capture search that STARTS at len(haystack) builds its
+    result from no slots.  Whether the last search of a FindAllSubmatch loop starts there depends on
+    the strategy and on the previous match:"""
+    # direct strategies: the loop reaches len only behind a match (or a skipped empty match) ending at len-1
+    assert fa_sub(r"(a*)(\d*)", b"x") == [[0, 0, 0, 0, 0, 0], [1, 1, -1, -1, -1, -1]]      # previous match empty at len-1
+    assert fa_sub(r"(\d*)", b"1x") == [[0, 1, 0, 1], [2, 2, -1, -1]]                       # skipped empty match at len-1
+    assert fa_sub(r"(^)|($)", b"ab") == [[0, 0, 0, 0, -1, -1], [2, 2, -1, -1, 2, 2]]       # search started at 1: real slots
+    assert fa_sub(r"(\d*)", b"") == [[0, 0, -1, -1]]                                       # empty haystack: starts at len
+    # span-first strategies run the captures from the match start, which IS len
+    assert Oracle(r"($)").strategy == "UseReverseAnchored" and fa_sub(r"($)", b"ab") == [[2, 2, -1, -1]]

@@ -159,7 +159,8 @@ def test_oracle_captures_equal_stdlib_semantics_on_every_reference_test_pattern(
             if not comparable:
                 continue
             got = o.find_all_submatch(ascii_hay).tolist()
-            if want and got and want[-1][0] == len(ascii_hay) == got[-1][0]:
+            if want and got and want[-1][0] == len(ascii_hay) == got[-1][0] and got[-1][2:] == [-1] * (len(got[-1]) - 2):
+                # the shortcut fired (it depends on where the last search started)
                 want[-1] = [want[-1][0], want[-1][1]] + [-1] * (len(want[-1]) - 2)
             if got == want:
                 equal += 1
