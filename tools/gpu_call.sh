@@ -1,6 +1,7 @@
 #!/bin/bash
-# the call of the moment: the bench line on the final tree
-TAG=${1:-r17}
+# One call's worth of confirmation on a B200 (gpurun --timeout 1500 -- 'bash tools/gpu_call.sh <tag>'):
+# the whole GPU suite, smoke, the bench line, the reference arm, config 5 and the other configs.
+TAG=${1:-r02x}
 mkdir -p gpurun_out
-timeout 100 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
-cut -c1-260 gpurun_out/${TAG}_bench.json; tail -2 gpurun_out/${TAG}_bench.err | cut -c1-300
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+TEST_TIMEOUT=1500 bash tools/gpu_round2.sh $TAG tests bench c5 configs
