@@ -410,3 +410,22 @@ def test_end_of_haystack_capture_shortcut_depends_on_where_the_search_starts():
     assert fa_sub(r"(\d*)", b"") == [[0, 0, -1, -1]]                                       # empty haystack: starts at len
     # span-first strategies run the captures from the match start, which IS len
     assert Oracle(r"($)").strategy == "UseReverseAnchored" and fa_sub(r"($)", b"ab") == [[2, 2, -1, -1]]
+
+
+def test_unicode_tables_are_what_the_generator_writes(tmp_path):
+    """syntax/unicode_tables.inc is generated (tools/gen_unicode_tables.py: perl Unicode::UCD 15.0.0,
+    cross-checked against Python unicodedata): regenerating must reproduce the committed file."""
+    import shutil
+    import subprocess
+    import sys
+    import unicodedata
+    if shutil.which("perl") is None or unicodedata.unidata_version != "15.0.0":
+        pytest.skip("needs perl and a Unicode 15.0.0 unicodedata")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "unicode_tables.inc"
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_unicode_tables.py"), str(out)], capture_output=True, text=True)
+    if p.returncode != 0 and "want 15.0.0" in (p.stdout + p.stderr):
+        pytest.skip("perl's Unicode database is not 15.0.0")
+    assert p.returncode == 0, p.stdout + p.stderr
+    with open(os.path.join(root, "syntax", "unicode_tables.inc")) as a, open(out) as b:
+        assert a.read() == b.read()
